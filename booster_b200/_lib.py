@@ -1,0 +1,105 @@
+"""ctypes binding of libbooster_b200.so (include/bridge.h + include/booster_b200.h).
+
+The shared library is the product; this module only declares prototypes. It is built in-tree by
+`make` / `__graft_entry__.build()` and must exist: there is no Python or CPU fallback for any compute entry.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbooster_b200.so")
+
+_lib = None
+
+# every symbol the two headers declare (tests check the .so exports exactly these)
+BRIDGE_SYMBOLS = ["init", "initContext", "doInference", "stopInference", "status", "promptEval",
+                  "getPromptTokenCount", "timing", "getSeed"]
+B200_SYMBOLS = ["b200_last_error", "b200_device_count", "b200_version", "b200_model_load", "b200_model_free",
+                "b200_model_info", "b200_model_weight_bytes", "b200_ctx_new", "b200_ctx_free", "b200_n_ctx",
+                "b200_kv_clear", "b200_decode", "b200_generate_greedy", "b200_set_taps", "b200_get_tap",
+                "b200_timings", "b200_reset_timings", "b200_kernel_launches", "b200_comm_unique_id",
+                "b200_comm_init", "b200_pipeline_generate_greedy", "b200_pipeline_decode", "b200_stage_forward",
+                "b200_stage_logits", "b200_stage_argmax", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
+                "b200_op_dequantize_row", "b200_op_mul_mat_vec", "b200_op_rms_norm", "b200_op_rope",
+                "b200_op_attention"]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+                           "booster_b200 has no fallback path.")
+    L = C.CDLL(LIB_PATH)
+    i32p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    vp, cp = C.c_void_p, C.c_char_p
+
+    def sig(name, res, args):
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+
+    # include/bridge.h
+    sig("init", None, [cp, cp])
+    sig("initContext", vp, [C.c_int, cp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                            C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
+                            C.c_int, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_uint32, cp])
+    sig("doInference", C.c_int64, [C.c_int, vp, cp, cp, cp])
+    sig("stopInference", None, [C.c_int])
+    sig("status", cp, [cp])
+    sig("promptEval", C.c_int64, [cp])
+    sig("getPromptTokenCount", C.c_int64, [cp])
+    sig("timing", C.c_int64, [cp])
+    sig("getSeed", C.c_uint32, [cp])
+    sig("b200_job_timing_us", C.c_int, [cp, C.POINTER(C.c_double), C.POINTER(C.c_double)])
+    # include/booster_b200.h
+    sig("b200_last_error", cp, [])
+    sig("b200_device_count", C.c_int, [])
+    sig("b200_version", cp, [])
+    sig("b200_model_load", vp, [cp, C.c_int, C.c_int, C.c_int])
+    sig("b200_model_free", None, [vp])
+    sig("b200_model_info", C.c_int, [vp, i32p])
+    sig("b200_model_weight_bytes", C.c_int64, [vp])
+    sig("b200_ctx_new", vp, [vp, C.c_int])
+    sig("b200_ctx_free", None, [vp])
+    sig("b200_n_ctx", C.c_int, [vp])
+    sig("b200_kv_clear", None, [vp])
+    sig("b200_decode", C.c_int, [vp, i32p, C.c_int, C.c_int, f32p])
+    sig("b200_generate_greedy", C.c_int, [vp, C.c_int32, C.c_int, C.c_int, i32p])
+    sig("b200_set_taps", None, [vp, C.c_int])
+    sig("b200_get_tap", C.c_int64, [vp, cp, C.c_int, f32p, C.c_int64])
+    sig("b200_timings", None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)])
+    sig("b200_reset_timings", None, [vp])
+    sig("b200_kernel_launches", C.c_int64, [vp])
+    sig("b200_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)])
+    sig("b200_comm_init", C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)])
+    sig("b200_pipeline_generate_greedy", C.c_int, [vp, C.c_int32, C.c_int, C.c_int, i32p])
+    sig("b200_pipeline_decode", C.c_int, [vp, i32p, C.c_int, C.c_int, f32p])
+    sig("b200_stage_forward", C.c_int, [vp, C.c_int32, C.c_int, C.c_int, vp])
+    sig("b200_stage_logits", C.c_int, [vp, f32p])
+    sig("b200_stage_argmax", C.c_int, [vp, i32p])
+    sig("b200_op_quantize_q8_K", C.c_int, [f32p, C.c_int64, vp])
+    sig("b200_op_quantize_q8_0", C.c_int, [f32p, C.c_int64, vp])
+    sig("b200_op_dequantize_row", C.c_int, [C.c_int, vp, C.c_int64, f32p])
+    sig("b200_op_mul_mat_vec", C.c_int, [C.c_int, vp, C.c_int64, C.c_int64, f32p, f32p])
+    sig("b200_op_rms_norm", C.c_int, [f32p, f32p, C.c_int64, C.c_float, f32p])
+    sig("b200_op_rope", C.c_int, [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p])
+    sig("b200_op_attention", C.c_int, [f32p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_float, f32p])
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().b200_last_error().decode(errors="replace")
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise B200Error(f"{what}: {last_error()}")

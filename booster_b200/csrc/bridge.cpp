@@ -1,0 +1,286 @@
+// bridge.cpp — the nine cgo entry points of include/bridge.h on top of the B200 engine.
+//
+// Host-side mirror of cpp/bridge.cpp's operator interface for the hot path: same symbols, same argument
+// meaning, same return codes. The generation loop follows the reference's control flow
+// (cpp/bridge.cpp:175-658: tokenize -> reject if > n_ctx-4 -> clear KV -> prompt in n_batch chunks ->
+// sample/decode one token at a time until EOG / n_predict / n_ctx-4 / stop flag -> per-token timings), but every
+// llama_decode is the CUDA engine. Differences, all documented in DESIGN.md / INTEGRATION.md:
+//   * sampler: greedy arg-max on the device (the Janus sampler is SURVEY.md §8 row f-2, "next");
+//   * tokenizer: models with tokenizer.ggml.model == "no_vocab" take prompts that are white-space separated
+//     token ids and render pieces as "<id> "; text tokenizers (BPE/SPM) are row f-1, see tokenizer.hpp;
+//   * context shift / Self-Extend (cpp/bridge.cpp:487-524) are row f-3: generation stops at n_ctx-4 instead;
+//   * status() returns a per-thread snapshot instead of a pointer into a string another thread appends to
+//     (the reference race).
+#include "../../include/bridge.h"
+#include "../../include/booster_b200.h"
+#include "tokenizer.hpp"
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int MAX_PODS = 8;   // cpp/bridge.cpp:102-110: all per-pod arrays are sized 8
+
+struct Pod {
+    std::string model_path;
+    int n_ctx = 0, n_batch = 512, n_predict = -1;
+    uint32_t seed = 0;
+    std::vector<b200_model *> models;   // one per stage (in-process layer split)
+    std::vector<b200_ctx *>   stages;
+    std::unique_ptr<b200::Tokenizer> tok;
+    int n_vocab = 0;
+};
+
+Pod               g_pods[MAX_PODS];
+std::atomic<bool> g_stop[MAX_PODS];
+bool              g_debug_cuda = false;
+
+struct Job {
+    std::string text;           // prompt pieces + generated pieces (cpp/bridge.cpp:628-632)
+    int64_t prompt_eval_ms = 0; // ms per prompt token, integer-truncated (cpp/bridge.cpp:653)
+    int64_t timing_ms = 0;      // ms per generated token (cpp/bridge.cpp:654)
+    int64_t prompt_tokens = 0;
+    uint32_t seed = 0;
+    double  prompt_us_per_tok = 0, gen_us_per_tok = 0;   // µs-resolution copies (additive, see b200_job_timing_us)
+};
+std::mutex                 g_mu;
+std::map<std::string, Job> g_jobs;
+
+double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// layer -> device assignment by cumulative proportions, as llm_load_tensors does
+// (cpp/src/llama.cpp:5932-5968: normalised cumulative splits, std::upper_bound on (i / act_gpu_layers))
+std::vector<int> split_layers(int n_layer, const std::vector<float> & prop) {
+    std::vector<float> cum(prop.size());
+    float sum = 0.f;
+    for (size_t i = 0; i < prop.size(); i++) { sum += prop[i]; cum[i] = sum; }
+    for (auto & c : cum) c /= sum;
+    const int act = n_layer + 1;   // all layers + output are offloaded (cpp/bridge.cpp:746-750: n_gpu_layers = sum)
+    std::vector<int> dev((size_t) n_layer);
+    for (int il = 0; il < n_layer; il++) {
+        const float f = (float) il / (float) act;
+        size_t d = 0;
+        while (d + 1 < cum.size() && !(f < cum[d])) d++;   // upper_bound
+        dev[(size_t) il] = (int) d;
+    }
+    return dev;
+}
+
+int run_token(Pod & p, int32_t token, int pos, int batch_gt1) {
+    b200_ctx * prev = nullptr;
+    for (b200_ctx * c : p.stages) {
+        if (b200_stage_forward(c, token, pos, batch_gt1, prev) != 0) return 1;
+        prev = c;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void init(char * swap, char * debug) {
+    (void) swap;   // session directory: accepted and ignored, as in the reference (sessions are commented out)
+    g_debug_cuda = debug && std::strstr(debug, "cuda") != nullptr;
+    for (auto & s : g_stop) s.store(false);
+}
+
+void * initContext(
+    int idx, char * modelName, int threads, int batch_size,
+    int gpu1, int gpu2, int gpu3, int gpu4,
+    int context, int predict,
+    int32_t mirostat, float mirostat_tau, float mirostat_eta,
+    float temperature, int top_k, float top_p, float typical_p,
+    float repetition_penalty, int penalty_last_n,
+    int32_t janus, int32_t depth, float scale, float hi, float lo,
+    uint32_t seed, char * debug) {
+    (void) threads; (void) mirostat; (void) mirostat_tau; (void) mirostat_eta; (void) temperature; (void) top_k;
+    (void) top_p; (void) typical_p; (void) repetition_penalty; (void) penalty_last_n; (void) janus; (void) depth;
+    (void) scale; (void) hi; (void) lo; (void) debug;
+    if (idx < 0 || idx >= MAX_PODS || !modelName) return nullptr;
+    Pod & p = g_pods[idx];
+    p = Pod();
+    p.model_path = modelName;
+    p.seed = seed;
+    p.n_predict = predict;
+    const int n_dev = b200_device_count();
+    if (n_dev <= 0) {
+        std::fprintf(stderr, "initContext: no CUDA device: %s\n", "booster_b200 has no CPU path");
+        return nullptr;
+    }
+    // proportions: gpu1..gpu4 (server.go:514-530), or env BOOSTER_B200_SPLIT="p0,p1,..,p7" for up to 8 devices
+    std::vector<float> prop;
+    if (const char * env = std::getenv("BOOSTER_B200_SPLIT")) {
+        std::string s = env; size_t q = 0;
+        while (q < s.size()) { size_t e = s.find(',', q); if (e == std::string::npos) e = s.size(); prop.push_back((float) std::atof(s.substr(q, e - q).c_str())); q = e + 1; }
+    } else {
+        prop = { (float) gpu1, (float) gpu2, (float) gpu3, (float) gpu4 };
+    }
+    if ((int) prop.size() > n_dev) {
+        for (size_t i = (size_t) n_dev; i < prop.size(); i++) if (prop[i] > 0) { std::fprintf(stderr, "initContext: split names device %zu but only %d visible\n", i, n_dev); return nullptr; }
+        prop.resize((size_t) n_dev);
+    }
+    float sum = 0; for (float f : prop) sum += f;
+    if (sum <= 0) { prop.assign(1, 1.f); }   // the reference would run on the CPU; this library is the GPU path
+
+    // peek hyper-parameters with a first-stage load of the first device that has a share
+    // (cheap way: load stage ranges after reading n_layer from a probe load of layer 0 only)
+    int first_dev = 0; while (first_dev < (int) prop.size() && prop[(size_t) first_dev] <= 0) first_dev++;
+    b200_model * probe = b200_model_load(modelName, first_dev, 0, 1);
+    if (!probe) { std::fprintf(stderr, "initContext: %s\n", b200_last_error()); return nullptr; }
+    int32_t info[B200_INFO_COUNT];
+    b200_model_info(probe, info);
+    b200_model_free(probe);
+    const int n_layer = info[B200_INFO_N_LAYER];
+    const std::vector<int> dev = split_layers(n_layer, prop);
+    int n_ctx = context > 0 ? context : info[B200_INFO_N_CTX_TRAIN];
+    for (int il = 0; il < n_layer;) {
+        int e = il; while (e < n_layer && dev[(size_t) e] == dev[(size_t) il]) e++;
+        b200_model * m = b200_model_load(modelName, dev[(size_t) il], il, e);
+        if (!m) { std::fprintf(stderr, "initContext: %s\n", b200_last_error()); return nullptr; }
+        b200_ctx * c = b200_ctx_new(m, n_ctx);
+        if (!c) { std::fprintf(stderr, "initContext: %s\n", b200_last_error()); return nullptr; }
+        p.models.push_back(m); p.stages.push_back(c);
+        il = e;
+    }
+    p.n_ctx = b200_n_ctx(p.stages[0]);
+    p.n_vocab = info[B200_INFO_N_VOCAB];
+    // batch (cpp/bridge.cpp:154-160): 0 -> 512 on GPU
+    p.n_batch = (batch_size > 0 && batch_size <= p.n_ctx) ? batch_size : 512;
+    std::string terr;
+    p.tok = b200::make_tokenizer(modelName, terr);
+    if (!p.tok) { std::fprintf(stderr, "initContext: %s\n", terr.c_str()); return nullptr; }
+    return (void *) &p;
+}
+
+int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * prompt) {
+    (void) sessionID;
+    if (idx < 0 || idx >= MAX_PODS || !ctx || !jobID || !prompt) return 0;
+    Pod & p = g_pods[idx];
+    if ((void *) &p != ctx || p.stages.empty()) return 0;
+    const std::string job = jobID;         // callee copies: the Go side never frees its C strings (server.go:73)
+    const std::string text = prompt;
+    g_stop[idx].store(false);
+
+    const uint32_t seed = p.seed ? p.seed : (uint32_t) std::time(nullptr);   // cpp/bridge.cpp:216-221
+    { std::lock_guard<std::mutex> lk(g_mu); Job & j = g_jobs[job]; j = Job(); j.seed = seed; }
+
+    std::vector<int32_t> inp;
+    if (!p.tok->tokenize(text, inp)) return 0;
+    { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].prompt_tokens = (int64_t) inp.size(); }
+    const int max_embd = p.n_ctx - 4;
+    if ((int) inp.size() > max_embd || inp.empty()) {     // cpp/bridge.cpp:382-386
+        std::fprintf(stderr, "doInference: prompt is too long (%d tokens, max %d) or empty\n", (int) inp.size(), max_embd);
+        return 0;
+    }
+    for (b200_ctx * c : p.stages) b200_kv_clear(c);        // cpp/bridge.cpp:459
+
+    int n_past = 0;
+    int64_t n_p_eval = 0, n_eval = 0;
+    double t_p_us = 0, t_e_us = 0;
+    int n_remain = p.n_predict;                            // -1 = until EOG / context
+    b200_ctx * last = p.stages.back();
+
+    // ---- prompt, in chunks of n_batch (cpp/bridge.cpp:549-560, 613-624); pieces are published per chunk
+    size_t consumed = 0;
+    while (consumed < inp.size() && !g_stop[idx].load()) {
+        const size_t n = std::min((size_t) p.n_batch, inp.size() - consumed);
+        const double t0 = now_us();
+        for (size_t i = 0; i < n; i++) {
+            if (run_token(p, inp[consumed + i], n_past + (int) i, n > 1 ? 1 : 0) != 0) return 1;   // llama_decode failed: bridge.cpp:556-558
+        }
+        // synchronise the chain end so that the chunk time is real (the last chunk is synchronised by the
+        // first arg-max of the generation loop)
+        if (consumed + n != inp.size()) { int32_t t; if (b200_stage_argmax(last, &t) != 0) return 1; }
+        const double dt = now_us() - t0;
+        if (n > 1) { t_p_us += dt; n_p_eval += (int64_t) n; } else { t_e_us += dt; n_eval += 1; }
+        n_past += (int) n;
+        std::string pieces;
+        for (size_t i = 0; i < n; i++) pieces += p.tok->piece(inp[consumed + i]);
+        { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += pieces; }
+        consumed += n;
+    }
+
+    // ---- generation: sample (greedy, on device) then decode the sampled token (cpp/bridge.cpp:586-646)
+    while (n_remain != 0 && n_past < max_embd && !g_stop[idx].load()) {
+        int32_t id = 0;
+        const double t0 = now_us();
+        if (b200_stage_argmax(last, &id) != 0) return 1;
+        --n_remain;
+        { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += p.tok->piece(id); }
+        if (p.tok->is_eog(id)) break;                      // cpp/bridge.cpp:640
+        if (n_remain == 0 || n_past >= max_embd) break;
+        if (run_token(p, id, n_past, 0) != 0) return 1;
+        n_past += 1;
+        // launches are asynchronous: the interval that ends at the NEXT arg-max's sync is what one token costs
+        t_e_us += now_us() - t0; n_eval += 1;
+    }
+    // per-token timings, integer milliseconds like the reference (cpp/bridge.cpp:650-655)
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Job & j = g_jobs[job];
+        j.prompt_us_per_tok = n_p_eval ? t_p_us / (double) n_p_eval : 0;
+        j.gen_us_per_tok    = n_eval ? t_e_us / (double) n_eval : 0;
+        j.prompt_eval_ms = (int64_t) (j.prompt_us_per_tok / 1000.0);
+        j.timing_ms      = (int64_t) (j.gen_us_per_tok / 1000.0);
+    }
+    return n_p_eval + n_eval;
+}
+
+void stopInference(int idx) {
+    if (idx >= 0 && idx < MAX_PODS) g_stop[idx].store(true);
+}
+
+const char * status(char * jobID) {
+    static thread_local std::string snap;
+    if (!jobID) return "";
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_jobs.find(jobID);
+    snap = it == g_jobs.end() ? std::string() : it->second.text;
+    return snap.c_str();
+}
+
+int64_t promptEval(char * jobID) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_jobs.find(jobID ? jobID : "");
+    return it == g_jobs.end() ? 0 : it->second.prompt_eval_ms;
+}
+int64_t getPromptTokenCount(char * jobID) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_jobs.find(jobID ? jobID : "");
+    return it == g_jobs.end() ? 0 : it->second.prompt_tokens;
+}
+int64_t timing(char * jobID) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_jobs.find(jobID ? jobID : "");
+    return it == g_jobs.end() ? 0 : it->second.timing_ms;
+}
+uint32_t getSeed(char * jobID) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_jobs.find(jobID ? jobID : "");
+    return it == g_jobs.end() ? 0 : it->second.seed;
+}
+
+// additive: µs-resolution per-token timings (the bridge's ms-truncated values read 0 on a B200)
+int b200_job_timing_us(const char * jobID, double * prompt_us_per_token, double * gen_us_per_token) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_jobs.find(jobID ? jobID : "");
+    if (it == g_jobs.end()) return 1;
+    *prompt_us_per_token = it->second.prompt_us_per_tok;
+    *gen_us_per_token    = it->second.gen_us_per_tok;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,992 @@
+// engine.cu — the B200 decode engine behind include/booster_b200.h.
+//
+// A fixed-function LLaMA-architecture decoder (not a graph interpreter): the per-token work of
+// llama_decode_internal (cpp/src/llama.cpp:14537-14840) + build_llama (:8781-8925) is a fixed sequence of
+// 6 fused kernels per layer, captured once into a CUDA graph and replayed per token; the per-token scalars
+// (token, pos) live in device memory (DecodeState) so the graph never needs re-instantiation.
+//
+//   per layer:  k_matvec<QKV>   [RMSNorm(attn_norm)+Q8_K quant] -> wq|wk|wv -> RoPE -> q (f32), K/V (f16 cache)
+//               k_attn_partial  split-KV attention over the f16 cache (GQA group per CTA)
+//               k_attn_combine  merge splits -> kqv_merged_cont
+//               k_matvec<RESID> [quant] -> wo -> + residual                          (ffn_inp)
+//               k_matvec<SILU>  [RMSNorm(ffn_norm)+quant] -> gate|up -> silu(g)*u    (ffn_gate_par)
+//               k_matvec<RESID> [quant] -> down -> + residual                        (l_out)
+//   head:       k_matvec<STORE> [RMSNorm(output_norm)+quant] -> output -> logits
+//
+// There is no CPU fallback: every entry point fails with an error when no CUDA device is present.
+#include "../../include/booster_b200.h"
+#include "gguf.hpp"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int set_err(const std::string & s) { g_err = s; return 1; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+
+extern "C" const char * b200_last_error(void) { return g_err.c_str(); }
+extern "C" const char * b200_version(void) { return "booster_b200 0.1 (sm_100a)"; }
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+static void require_gpu() {
+    if (b200_device_count() <= 0)
+        throw std::runtime_error("no CUDA device visible: booster_b200 has no CPU fallback (the CUDA path is the product)");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// re-tiling kernels: ggml block layout -> planes (one thread per block; one-time at load)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_repack_q4k(const uint8_t * __restrict__ src, size_t n_blocks, uint8_t * p0, uint8_t * p1, uint8_t * p2) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    const uint8_t * b = src + i * 144;   // {half d, half dmin, u8 scales[12], u8 qs[128]}  ggml-common.h:267-277
+    for (int j = 0; j < 4; j++)   p2[i * 4 + j] = b[j];
+    for (int j = 0; j < 12; j++)  p1[i * 12 + j] = b[4 + j];
+    for (int j = 0; j < 128; j++) p0[i * 128 + j] = b[16 + j];
+}
+__global__ void k_repack_q5k(const uint8_t * __restrict__ src, size_t n_blocks, uint8_t * p0, uint8_t * p1, uint8_t * p2, uint8_t * p3) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    const uint8_t * b = src + i * 176;   // {half d, half dmin, u8 scales[12], u8 qh[32], u8 qs[128]}  :284-295
+    for (int j = 0; j < 4; j++)   p2[i * 4 + j] = b[j];
+    for (int j = 0; j < 12; j++)  p1[i * 12 + j] = b[4 + j];
+    for (int j = 0; j < 32; j++)  p3[i * 32 + j] = b[16 + j];
+    for (int j = 0; j < 128; j++) p0[i * 128 + j] = b[48 + j];
+}
+__global__ void k_repack_q6k(const uint8_t * __restrict__ src, size_t n_blocks, uint8_t * p0, uint8_t * p1, uint8_t * p2, uint8_t * p3) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    const uint8_t * b = src + i * 210;   // {u8 ql[128], u8 qh[64], i8 scales[16], half d}  :302-307
+    for (int j = 0; j < 128; j++) p0[i * 128 + j] = b[j];
+    for (int j = 0; j < 64; j++)  p1[i * 64 + j] = b[128 + j];
+    for (int j = 0; j < 16; j++)  p2[i * 16 + j] = b[192 + j];
+    p3[i * 2] = b[208]; p3[i * 2 + 1] = b[209];
+}
+__global__ void k_repack_q80(const uint8_t * __restrict__ src, size_t n_blocks, uint8_t * p0, uint8_t * p1) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    const uint8_t * b = src + i * 34;    // {half d, i8 qs[32]}  :186-190
+    p1[i * 2] = b[0]; p1[i * 2 + 1] = b[1];
+    for (int j = 0; j < 32; j++) p0[i * 32 + j] = b[2 + j];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------------------
+struct DevMat {
+    QMat m;
+    void * alloc = nullptr;
+    size_t bytes = 0;       // algorithmic bytes (== ggml tensor bytes)
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// upload a [n_rows x k] tensor in ggml block layout (host pointer) and re-tile it into planes
+static DevMat upload_matrix(int type, const void * host, int64_t n_rows, int64_t k, cudaStream_t st) {
+    if (k % 256 != 0) throw std::runtime_error("matrix inner dimension must be a multiple of 256 (got " + std::to_string(k) + ")");
+    if (n_rows % 2 != 0) throw std::runtime_error("matrix row count must be even");
+    DevMat d;
+    d.m.type = type; d.m.n_rows = (int) n_rows; d.m.k = (int) k;
+    const size_t raw = (size_t) ggml_row_bytes((uint32_t) type, (uint64_t) k) * (size_t) n_rows;
+    d.bytes = raw;
+    size_t sz[4] = {0, 0, 0, 0};
+    size_t n_blocks = 0;
+    switch (type) {
+        case T_Q4_K: n_blocks = (size_t) n_rows * (k / 256); sz[0] = n_blocks * 128; sz[1] = n_blocks * 12; sz[2] = n_blocks * 4; break;
+        case T_Q5_K: n_blocks = (size_t) n_rows * (k / 256); sz[0] = n_blocks * 128; sz[1] = n_blocks * 12; sz[2] = n_blocks * 4; sz[3] = n_blocks * 32; break;
+        case T_Q6_K: n_blocks = (size_t) n_rows * (k / 256); sz[0] = n_blocks * 128; sz[1] = n_blocks * 64; sz[2] = n_blocks * 16; sz[3] = n_blocks * 2; break;
+        case T_Q8_0: n_blocks = (size_t) n_rows * (k / 32);  sz[0] = n_blocks * 32;  sz[1] = n_blocks * 2; break;
+        default: throw std::runtime_error("unsupported matrix type " + std::to_string(type) + " (supported: Q4_K, Q5_K, Q6_K, Q8_0)");
+    }
+    size_t off[4], total = 0;
+    for (int i = 0; i < 4; i++) { off[i] = total; total += align_up(sz[i], 256); }
+    uint8_t * base = nullptr;
+    CU(cudaMalloc(&base, total));
+    d.alloc = base;
+    uint8_t * tmp = nullptr;
+    CU(cudaMalloc(&tmp, raw));
+    CU(cudaMemcpyAsync(tmp, host, raw, cudaMemcpyHostToDevice, st));
+    uint8_t * p[4] = { base + off[0], base + off[1], base + off[2], base + off[3] };
+    const int thr = 128;
+    const unsigned grid = (unsigned) ((n_blocks + thr - 1) / thr);
+    switch (type) {
+        case T_Q4_K: k_repack_q4k<<<grid, thr, 0, st>>>(tmp, n_blocks, p[0], p[1], p[2]); break;
+        case T_Q5_K: k_repack_q5k<<<grid, thr, 0, st>>>(tmp, n_blocks, p[0], p[1], p[2], p[3]); break;
+        case T_Q6_K: k_repack_q6k<<<grid, thr, 0, st>>>(tmp, n_blocks, p[0], p[1], p[2], p[3]); break;
+        case T_Q8_0: k_repack_q80<<<grid, thr, 0, st>>>(tmp, n_blocks, p[0], p[1]); break;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    CU(cudaFree(tmp));
+    d.m.p0 = p[0]; d.m.p1 = p[1]; d.m.p2 = sz[2] ? p[2] : nullptr; d.m.p3 = sz[3] ? p[3] : nullptr;
+    return d;
+}
+
+struct LayerW {
+    DevMat wq, wk, wv, wo, gate, up, down;
+    float * attn_norm = nullptr;
+    float * ffn_norm = nullptr;
+};
+
+struct b200_model {
+    int device = 0;
+    int n_vocab = 0, n_embd = 0, n_layer = 0, n_head = 0, n_head_kv = 0, n_ff = 0, head_dim = 0, n_ctx_train = 0;
+    int layer_begin = 0, layer_end = 0;
+    int ftype = -1;
+    float rms_eps = 1e-5f;
+    float rope_freq_base = 10000.f, rope_freq_scale = 1.f;
+    int   rope_dim = 0;
+    int   n_ctx_orig = 0;
+    float yarn_ext_factor = 0.f, yarn_attn_factor = 1.f, yarn_beta_fast = 32.f, yarn_beta_slow = 1.f;
+    std::vector<float> rope_freq_factors;   // rope_freqs.weight (llama 3.1), empty if absent
+    std::vector<LayerW> layers;             // indexed by il - layer_begin
+    // first stage
+    int      embd_type = 0;
+    uint8_t * embd_rows = nullptr;          // token_embd in ORIGINAL ggml layout (one row read per token)
+    size_t   embd_row_bytes = 0;
+    // last stage
+    float *  output_norm = nullptr;
+    DevMat   output;
+    int64_t  weight_bytes = 0;
+    // tokenizer metadata kept for the bridge (host side)
+    std::string tok_model;
+    std::vector<std::string> tok_tokens;
+    int32_t tok_eos = -1, tok_bos = -1;
+    bool has_embd() const { return layer_begin == 0; }
+    bool has_head() const { return layer_end == n_layer; }
+};
+
+static float * upload_f32(const gguf_tensor * t, int64_t n, cudaStream_t st) {
+    if (!t) throw std::runtime_error("missing norm tensor");
+    if (t->type != 0) throw std::runtime_error("norm tensor " + t->name + " must be F32");
+    if ((int64_t) t->ne[0] != n) throw std::runtime_error("norm tensor " + t->name + " has wrong length");
+    float * d = nullptr;
+    CU(cudaMalloc(&d, (size_t) n * 4));
+    CU(cudaMemcpyAsync(d, t->data, (size_t) n * 4, cudaMemcpyHostToDevice, st));
+    return d;
+}
+
+static DevMat upload_named(const gguf_file & g, const std::string & name, int64_t rows, int64_t k, cudaStream_t st) {
+    const gguf_tensor * t = g.find(name);
+    if (!t) throw std::runtime_error("missing tensor " + name);
+    if ((int64_t) t->ne[0] != k || (int64_t) t->ne[1] != rows)
+        throw std::runtime_error("tensor " + name + " has shape [" + std::to_string(t->ne[0]) + "," + std::to_string(t->ne[1]) +
+                                 "], expected [" + std::to_string(k) + "," + std::to_string(rows) + "]");
+    return upload_matrix((int) t->type, t->data, rows, k, st);
+}
+
+extern "C" b200_model * b200_model_load(const char * path, int device, int layer_begin, int layer_end) {
+    try {
+        require_gpu();
+        gguf_file g;
+        const std::string err = g.open(path);
+        if (!err.empty()) throw std::runtime_error(err);
+        const std::string arch = g.get_s("general.architecture", "");
+        if (arch != "llama") throw std::runtime_error("unsupported architecture '" + arch + "' (this path covers LLM_ARCH_LLAMA only)");
+        auto m = std::make_unique<b200_model>();
+        m->device = device;
+        CU(cudaSetDevice(device));
+        // hparams: cpp/src/llama.cpp:4571-4700
+        m->n_ctx_train = (int) g.get_u("llama.context_length", 0);
+        m->n_embd      = (int) g.get_u("llama.embedding_length", 0);
+        m->n_layer     = (int) g.get_u("llama.block_count", 0);
+        m->n_ff        = (int) g.get_u("llama.feed_forward_length", 0);
+        m->n_head      = (int) g.get_u("llama.attention.head_count", 0);
+        m->n_head_kv   = (int) g.get_u("llama.attention.head_count_kv", (uint64_t) m->n_head);
+        m->rms_eps     = (float) g.get_f("llama.attention.layer_norm_rms_epsilon", 1e-5);
+        m->ftype       = (int) g.get_u("general.file_type", (uint64_t) -1);
+        if (m->n_embd <= 0 || m->n_layer <= 0 || m->n_head <= 0 || m->n_ff <= 0) throw std::runtime_error("missing llama.* hyper-parameters");
+        m->head_dim    = (int) g.get_u("llama.attention.key_length", (uint64_t) (m->n_embd / m->n_head));
+        m->rope_dim    = (int) g.get_u("llama.rope.dimension_count", (uint64_t) m->head_dim);
+        if (m->rope_dim != m->head_dim) throw std::runtime_error("n_rot != head_dim is not supported on this path");
+        if (m->head_dim % 8 != 0 || m->head_dim > 256) throw std::runtime_error("head_dim must be a multiple of 8 and <= 256");
+        if (m->n_head % m->n_head_kv != 0 || m->n_head / m->n_head_kv > ATT_MAX_GQA) throw std::runtime_error("unsupported GQA ratio");
+        m->rope_freq_base = (float) g.get_f("llama.rope.freq_base", 10000.0);
+        // rope scaling: cpp/src/llama.cpp:4630-4650, 16655-16690
+        const std::string rs = g.get_s("llama.rope.scaling.type", "linear");
+        float ropescale = (float) g.get_f("llama.rope.scaling.factor", 0.0);
+        if (ropescale == 0.f) ropescale = (float) g.get_f("llama.rope.scale_linear", 0.0);
+        m->rope_freq_scale = ropescale == 0.f ? 1.f : 1.f / ropescale;
+        if (rs == "none") m->rope_freq_scale = 1.f;
+        m->n_ctx_orig = (int) g.get_u("llama.rope.scaling.original_context_length", (uint64_t) m->n_ctx_train);
+        m->yarn_ext_factor = rs == "yarn" ? 1.f : 0.f;
+        m->yarn_attn_factor = (float) g.get_f("llama.rope.scaling.attn_factor", 1.0);
+        const gguf_tensor * te = g.find("token_embd.weight");
+        if (!te) throw std::runtime_error("missing token_embd.weight");
+        m->n_vocab = (int) te->ne[1];
+        if (layer_end < 0 || layer_end > m->n_layer) layer_end = m->n_layer;
+        if (layer_begin < 0 || layer_begin >= layer_end) throw std::runtime_error("bad layer range");
+        m->layer_begin = layer_begin; m->layer_end = layer_end;
+
+        m->tok_model = g.get_s("tokenizer.ggml.model", "no_vocab");
+        auto itk = g.kv.find("tokenizer.ggml.tokens");
+        if (itk != g.kv.end()) m->tok_tokens = itk->second.arr_s;
+        m->tok_eos = (int32_t) g.get_u("tokenizer.ggml.eos_token_id", (uint64_t) -1);
+        m->tok_bos = (int32_t) g.get_u("tokenizer.ggml.bos_token_id", (uint64_t) -1);
+
+        cudaStream_t st;
+        CU(cudaStreamCreate(&st));
+        const int E = m->n_embd, HD = m->head_dim, KV = m->n_head_kv * HD, Q = m->n_head * HD, FF = m->n_ff;
+        if (const gguf_tensor * rf = g.find("rope_freqs.weight")) {
+            if (rf->type != 0) throw std::runtime_error("rope_freqs.weight must be F32");
+            m->rope_freq_factors.assign((const float *) rf->data, (const float *) rf->data + rf->ne[0]);
+        }
+        int64_t wb = 0;
+        for (int il = layer_begin; il < layer_end; il++) {
+            const std::string p = "blk." + std::to_string(il) + ".";
+            LayerW L;
+            L.attn_norm = upload_f32(g.find(p + "attn_norm.weight"), E, st);
+            L.ffn_norm  = upload_f32(g.find(p + "ffn_norm.weight"), E, st);
+            L.wq   = upload_named(g, p + "attn_q.weight", Q, E, st);
+            L.wk   = upload_named(g, p + "attn_k.weight", KV, E, st);
+            L.wv   = upload_named(g, p + "attn_v.weight", KV, E, st);
+            L.wo   = upload_named(g, p + "attn_output.weight", E, Q, st);
+            L.gate = upload_named(g, p + "ffn_gate.weight", FF, E, st);
+            L.up   = upload_named(g, p + "ffn_up.weight", FF, E, st);
+            L.down = upload_named(g, p + "ffn_down.weight", E, FF, st);
+            if (L.gate.m.type != L.up.m.type) throw std::runtime_error("ffn_gate and ffn_up must share a block type");
+            const bool q80 = L.wq.m.type == T_Q8_0;
+            for (const DevMat * d : { &L.wq, &L.wk, &L.wv, &L.wo, &L.gate, &L.up, &L.down })
+                if ((d->m.type == T_Q8_0) != q80) throw std::runtime_error("mixing Q8_0 and K-quant matrices inside one layer is not supported");
+            wb += (int64_t) (L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.gate.bytes + L.up.bytes + L.down.bytes) + 2 * (int64_t) E * 4;
+            m->layers.push_back(L);
+        }
+        if (m->has_embd()) {
+            m->embd_type = (int) te->type;
+            m->embd_row_bytes = (size_t) ggml_row_bytes(te->type, te->ne[0]);
+            if (m->embd_row_bytes == 0) throw std::runtime_error("unsupported token_embd type " + std::to_string(te->type));
+            CU(cudaMalloc(&m->embd_rows, te->nbytes));
+            CU(cudaMemcpyAsync(m->embd_rows, te->data, te->nbytes, cudaMemcpyHostToDevice, st));
+        }
+        if (m->has_head()) {
+            m->output_norm = upload_f32(g.find("output_norm.weight"), E, st);
+            // tied embeddings: output falls back to token_embd (cpp/src/llama.cpp:6077-6084)
+            const std::string on = g.find("output.weight") ? "output.weight" : "token_embd.weight";
+            m->output = upload_named(g, on, m->n_vocab, E, st);
+            wb += (int64_t) m->output.bytes + (int64_t) E * 4;
+        }
+        CU(cudaStreamSynchronize(st));
+        CU(cudaStreamDestroy(st));
+        m->weight_bytes = wb;
+        return m.release();
+    } catch (const std::exception & e) {
+        set_err(e.what());
+        return nullptr;
+    }
+}
+
+extern "C" void b200_model_free(b200_model * m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (auto & L : m->layers) {
+        for (DevMat * d : { &L.wq, &L.wk, &L.wv, &L.wo, &L.gate, &L.up, &L.down }) cudaFree(d->alloc);
+        cudaFree(L.attn_norm); cudaFree(L.ffn_norm);
+    }
+    cudaFree(m->embd_rows); cudaFree(m->output_norm); cudaFree(m->output.alloc);
+    delete m;
+}
+
+extern "C" int b200_model_info(const b200_model * m, int32_t info[B200_INFO_COUNT]) {
+    if (!m) return set_err("null model");
+    std::memset(info, 0, sizeof(int32_t) * B200_INFO_COUNT);
+    info[B200_INFO_N_VOCAB] = m->n_vocab; info[B200_INFO_N_EMBD] = m->n_embd; info[B200_INFO_N_LAYER] = m->n_layer;
+    info[B200_INFO_N_HEAD] = m->n_head; info[B200_INFO_N_HEAD_KV] = m->n_head_kv; info[B200_INFO_N_FF] = m->n_ff;
+    info[B200_INFO_HEAD_DIM] = m->head_dim; info[B200_INFO_N_CTX_TRAIN] = m->n_ctx_train;
+    info[B200_INFO_LAYER_BEGIN] = m->layer_begin; info[B200_INFO_LAYER_END] = m->layer_end; info[B200_INFO_FTYPE] = m->ftype;
+    return 0;
+}
+extern "C" int64_t b200_model_weight_bytes(const b200_model * m) { return m ? m->weight_bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------------------
+// RoPE table on the host — restates ggml_rope_cache_init + rope_yarn + corr dims
+// (cpp/ggml/src/ggml.c:13987-14041): theta starts at pos and is multiplied by theta_scale each pair.
+// Built with the host libm so it is bit-identical to the CPU reference on the same machine.
+// ------------------------------------------------------------------------------------------------------------
+static float yarn_corr_dim(int n_dims, int n_ctx_orig, float n_rot, float base) {
+    return n_dims * logf(n_ctx_orig / (n_rot * 2 * (float) M_PI)) / (2 * logf(base));
+}
+static void build_rope_table(const b200_model & m, int n_ctx, std::vector<float2> & tab) {
+    const int hd = m.head_dim;
+    const float theta_scale = powf(m.rope_freq_base, -2.0f / hd);
+    float corr[2];
+    {
+        const float start = floorf(yarn_corr_dim(hd, m.n_ctx_orig, m.yarn_beta_fast, m.rope_freq_base));
+        const float end   = ceilf(yarn_corr_dim(hd, m.n_ctx_orig, m.yarn_beta_slow, m.rope_freq_base));
+        corr[0] = std::max(0.f, start);
+        corr[1] = std::min((float) (hd - 1), end);
+    }
+    tab.resize((size_t) n_ctx * (hd / 2));
+    for (int p = 0; p < n_ctx; p++) {
+        float theta = (float) p;
+        for (int i0 = 0; i0 < hd; i0 += 2) {
+            const float ff = m.rope_freq_factors.empty() ? 1.0f : m.rope_freq_factors[(size_t) (i0 / 2)];
+            const float theta_extrap = theta / ff;
+            float theta_interp = m.rope_freq_scale * theta_extrap;
+            float th = theta_interp;
+            float mscale = m.yarn_attn_factor;
+            if (m.yarn_ext_factor != 0.0f) {
+                const float y = (i0 / 2 - corr[0]) / std::max(0.001f, corr[1] - corr[0]);
+                const float ramp_mix = (1 - std::min(1.f, std::max(0.f, y))) * m.yarn_ext_factor;
+                th = theta_interp * (1 - ramp_mix) + theta_extrap * ramp_mix;
+                mscale *= 1.0f + 0.1f * logf(1.0f / m.rope_freq_scale);
+            }
+            tab[(size_t) p * (hd / 2) + i0 / 2] = make_float2(cosf(th) * mscale, sinf(th) * mscale);
+            theta *= theta_scale;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily (single-GPU use never touches it)
+// ------------------------------------------------------------------------------------------------------------
+struct NcclId { char b[128]; };   // ncclUniqueId is passed BY VALUE (nccl.h: struct { char internal[128]; })
+struct NcclApi {
+    void * h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char * (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static void nccl_load() {
+    if (g_nccl.h) return;
+    const char * names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char * n : names) { g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+    if (!g_nccl.h) throw std::runtime_error("cannot dlopen libnccl.so.2 (needed for multi-GPU pipeline)");
+    auto sym = [&](const char * s) { void * p = dlsym(g_nccl.h, s); if (!p) throw std::runtime_error(std::string("missing NCCL symbol ") + s); return p; };
+    *(void **) &g_nccl.GetUniqueId    = sym("ncclGetUniqueId");
+    *(void **) &g_nccl.CommInitRank   = sym("ncclCommInitRank");
+    *(void **) &g_nccl.Send           = sym("ncclSend");
+    *(void **) &g_nccl.Recv           = sym("ncclRecv");
+    *(void **) &g_nccl.GroupStart     = sym("ncclGroupStart");
+    *(void **) &g_nccl.GroupEnd       = sym("ncclGroupEnd");
+    *(void **) &g_nccl.CommDestroy    = sym("ncclCommDestroy");
+    *(void **) &g_nccl.GetErrorString = sym("ncclGetErrorString");
+}
+#define NC(call) do { int r_ = (call); if (r_ != 0) throw std::runtime_error(std::string(#call) + ": " + g_nccl.GetErrorString(r_)); } while (0)
+static constexpr int NCCL_FLOAT32 = 7, NCCL_INT32 = 2;   // ncclDataType_t (nccl.h)
+
+// ------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------
+struct TapStore { std::map<std::string, std::vector<float>> v; };
+
+struct b200_ctx {
+    b200_model * m = nullptr;
+    int n_ctx = 0;
+    int n_splits = 1;
+    int max_chunk = 0;
+    cudaStream_t st = nullptr;
+    // activations
+    float * x = nullptr;        // residual stream [n_embd]
+    float * q = nullptr;        // [n_head*hd]
+    float * att = nullptr;      // kqv_merged_cont [n_head*hd]
+    float * ffh = nullptr;      // silu(gate)*up [n_ff]
+    float * logits = nullptr;   // [n_vocab]
+    float * part_o = nullptr, * part_ml = nullptr;
+    std::vector<__half *> kc, vc;   // per local layer
+    float2 * rope = nullptr;
+    DecodeState * d_state = nullptr;
+    DecodeState * h_state = nullptr;   // pinned
+    float * h_logits = nullptr;        // pinned
+    int32_t * d_out_tokens = nullptr;
+    int out_tokens_cap = 0;
+    cudaGraphExec_t g_logits = nullptr;   // H2D state -> forward -> D2H logits
+    cudaGraphExec_t g_greedy = nullptr;   // forward -> argmax -> advance
+    cudaGraphExec_t g_pipe = nullptr;     // pipeline stage step (recv -> forward -> send)
+    int sm_count = 148;
+    bool taps = false;
+    TapStore tapstore;
+    // pipeline
+    void * comm = nullptr;
+    int rank = 0, world = 1;
+    cudaEvent_t ev_done = nullptr;     // in-process stage chain hand-off
+    // counters
+    int64_t launches = 0;
+    double t_prompt_us = 0, t_gen_us = 0;
+    int64_t n_prompt = 0, n_gen = 0;
+};
+
+extern "C" int b200_n_ctx(const b200_ctx * c) { return c ? c->n_ctx : 0; }
+extern "C" int64_t b200_kernel_launches(const b200_ctx * c) { return c ? c->launches : 0; }
+
+template <int EPI>
+static void launch_matvec(b200_ctx * c, const MatvecArgs & a) {
+    const size_t smem = act_smem_bytes(a.k, a.act_q8_0);
+    const int max_ctas = c->sm_count * 2;
+    int grid = (a.n_pairs + MV_WARPS - 1) / MV_WARPS;
+    grid = std::max(1, std::min(grid, max_ctas));
+    k_matvec<EPI><<<grid, MV_THREADS, smem, c->st>>>(a);
+    c->launches++;
+}
+
+static void launch_attention(b200_ctx * c, const AttnArgs & a) {
+    const int gqa = a.n_head / a.n_head_kv;
+    const int chunk_cap = a.n_kv_override > 0 ? (a.n_kv_override + a.n_splits - 1) / a.n_splits : c->max_chunk;
+    const size_t smem = (size_t) gqa * a.head_dim * 4 + (size_t) gqa * chunk_cap * 4;
+    const dim3 grid((unsigned) a.n_head_kv, (unsigned) a.n_splits);
+    switch (gqa) {
+        case 1: k_attn_partial<1><<<grid, ATT_THREADS, smem, c->st>>>(a); break;
+        case 2: k_attn_partial<2><<<grid, ATT_THREADS, smem, c->st>>>(a); break;
+        case 4: k_attn_partial<4><<<grid, ATT_THREADS, smem, c->st>>>(a); break;
+        case 8: k_attn_partial<8><<<grid, ATT_THREADS, smem, c->st>>>(a); break;
+        default: throw std::runtime_error("GQA ratio must be 1, 2, 4 or 8");
+    }
+    k_attn_combine<<<a.n_head, 128, 0, c->st>>>(a);
+    c->launches += 2;
+}
+
+static void tap(b200_ctx * c, const std::string & name, int il, const float * dptr, size_t n) {
+    if (!c->taps) return;
+    CU(cudaStreamSynchronize(c->st));
+    std::vector<float> h(n);
+    CU(cudaMemcpy(h.data(), dptr, n * 4, cudaMemcpyDeviceToHost));
+    c->tapstore.v[name + "-" + std::to_string(il)] = std::move(h);
+}
+
+// enqueue the layers of this stage (+ embedding on the first stage, + head on the last) for ONE token whose
+// scalars are in c->d_state
+static void enqueue_forward(b200_ctx * c) {
+    b200_model & m = *c->m;
+    const int E = m.n_embd, HD = m.head_dim, KVD = m.n_head_kv * HD, QD = m.n_head * HD, FF = m.n_ff;
+    if (m.has_embd()) {
+        const int thr = 256;
+        k_embed<<<(E + thr - 1) / thr, thr, 0, c->st>>>(m.embd_type, m.embd_rows, m.embd_row_bytes, E, c->d_state, 0, c->x);
+        c->launches++;
+    }
+    for (int li = 0; li < (int) m.layers.size(); li++) {
+        LayerW & L = m.layers[(size_t) li];
+        const int il = m.layer_begin + li;
+        const int q80 = L.wq.m.type == T_Q8_0;
+        {   // QKV
+            MatvecArgs a{};
+            a.seg[0] = L.wq.m; a.seg[1] = L.wk.m; a.seg[2] = L.wv.m; a.n_seg = 3;
+            a.pair_mode = PAIR_ADJACENT; a.n_pairs = (QD + 2 * KVD) / 2; a.k = E;
+            a.x = c->x; a.norm_w = L.attn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
+            a.q_out = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
+            a.n_q = QD; a.n_k = KVD; a.head_dim = HD; a.kv_dim = KVD; a.rope = c->rope; a.st = c->d_state;
+            launch_matvec<EPI_QKV>(c, a);
+            tap(c, "Qcur", il, c->q, (size_t) QD);
+        }
+        {   // attention
+            AttnArgs a{};
+            a.q = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
+            a.part_o = c->part_o; a.part_ml = c->part_ml; a.out = c->att;
+            a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD; a.n_splits = c->n_splits;
+            a.scale = 1.0f / sqrtf((float) HD);
+            a.st = c->d_state; a.n_kv_override = 0;
+            launch_attention(c, a);
+            tap(c, "kqv_merged_cont", il, c->att, (size_t) QD);
+        }
+        {   // wo + residual
+            MatvecArgs a{};
+            a.seg[0] = L.wo.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = E / 2; a.k = QD;
+            a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = q80;
+            a.out = c->x; a.resid = c->x;
+            launch_matvec<EPI_RESID>(c, a);
+            tap(c, "ffn_inp", il, c->x, (size_t) E);
+        }
+        {   // gate/up
+            MatvecArgs a{};
+            a.seg[0] = L.gate.m; a.seg[1] = L.up.m; a.n_seg = 2; a.pair_mode = PAIR_ZIP; a.n_pairs = FF; a.k = E;
+            a.x = c->x; a.norm_w = L.ffn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
+            a.out = c->ffh;
+            launch_matvec<EPI_SILU>(c, a);
+            tap(c, "ffn_gate_par", il, c->ffh, (size_t) FF);
+        }
+        {   // down + residual
+            MatvecArgs a{};
+            a.seg[0] = L.down.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = E / 2; a.k = FF;
+            a.x = c->ffh; a.norm_w = nullptr; a.act_q8_0 = q80;
+            a.out = c->x; a.resid = c->x;
+            launch_matvec<EPI_RESID>(c, a);
+            tap(c, "l_out", il, c->x, (size_t) E);
+        }
+    }
+    if (m.has_head()) {
+        MatvecArgs a{};
+        a.seg[0] = m.output.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = m.n_vocab / 2; a.k = E;
+        a.x = c->x; a.norm_w = m.output_norm; a.eps = m.rms_eps; a.act_q8_0 = m.output.m.type == T_Q8_0;
+        a.out = c->logits;
+        launch_matvec<EPI_STORE>(c, a);
+        tap(c, "result_output", -1, c->logits, (size_t) m.n_vocab);
+    }
+}
+
+static cudaGraphExec_t capture(b200_ctx * c, const std::function<void()> & body) {
+    cudaGraph_t g;
+    const int64_t l0 = c->launches;
+    CU(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+    body();
+    CU(cudaStreamEndCapture(c->st, &g));
+    c->launches = l0;   // capture is not execution
+    cudaGraphExec_t ge;
+    CU(cudaGraphInstantiate(&ge, g, 0));
+    CU(cudaGraphDestroy(g));
+    return ge;
+}
+static int64_t forward_launch_count(const b200_ctx * c) {
+    const b200_model & m = *c->m;
+    return (m.has_embd() ? 1 : 0) + (int64_t) m.layers.size() * 6 + (m.has_head() ? 1 : 0);
+}
+
+extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
+    try {
+        require_gpu();
+        if (!m) throw std::runtime_error("null model");
+        auto c = std::make_unique<b200_ctx>();
+        c->m = m;
+        CU(cudaSetDevice(m->device));
+        if (n_ctx <= 0) n_ctx = m->n_ctx_train;
+        c->n_ctx = (n_ctx + 31) / 32 * 32;                       // GGML_PAD(n_ctx, 32): cpp/src/llama.cpp:16655
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, m->device));
+        c->sm_count = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        const int E = m->n_embd, HD = m->head_dim, KVD = m->n_head_kv * HD, QD = m->n_head * HD;
+        // split count: about 2 CTAs per SM over (kv heads x splits), at least 32 positions per split at full context
+        int ns = std::max(1, (2 * c->sm_count) / m->n_head_kv);
+        ns = std::min(ns, std::max(1, c->n_ctx / 32));
+        c->n_splits = ns;
+        c->max_chunk = (c->n_ctx + ns - 1) / ns;
+        CU(cudaMalloc(&c->x, (size_t) E * 4));
+        CU(cudaMalloc(&c->q, (size_t) QD * 4));
+        CU(cudaMalloc(&c->att, (size_t) QD * 4));
+        CU(cudaMalloc(&c->ffh, (size_t) m->n_ff * 4));
+        CU(cudaMalloc(&c->logits, (size_t) m->n_vocab * 4));
+        CU(cudaMalloc(&c->part_o, (size_t) m->n_head * ns * HD * 4));
+        CU(cudaMalloc(&c->part_ml, (size_t) m->n_head * ns * 2 * 4));
+        for (size_t i = 0; i < m->layers.size(); i++) {
+            __half * k = nullptr, * v = nullptr;
+            CU(cudaMalloc(&k, (size_t) c->n_ctx * KVD * 2));
+            CU(cudaMalloc(&v, (size_t) c->n_ctx * KVD * 2));
+            CU(cudaMemset(k, 0, (size_t) c->n_ctx * KVD * 2));
+            CU(cudaMemset(v, 0, (size_t) c->n_ctx * KVD * 2));
+            c->kc.push_back(k); c->vc.push_back(v);
+        }
+        std::vector<float2> tab;
+        build_rope_table(*m, c->n_ctx, tab);
+        CU(cudaMalloc(&c->rope, tab.size() * sizeof(float2)));
+        CU(cudaMemcpy(c->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_state, sizeof(DecodeState)));
+        CU(cudaMemset(c->d_state, 0, sizeof(DecodeState)));
+        CU(cudaMallocHost(&c->h_state, sizeof(DecodeState)));
+        CU(cudaMallocHost(&c->h_logits, (size_t) m->n_vocab * 4));
+        c->out_tokens_cap = c->n_ctx + 8;
+        CU(cudaMalloc(&c->d_out_tokens, (size_t) c->out_tokens_cap * 4));
+        return c.release();
+    } catch (const std::exception & e) {
+        set_err(e.what());
+        return nullptr;
+    }
+}
+
+extern "C" void b200_ctx_free(b200_ctx * c) {
+    if (!c) return;
+    cudaSetDevice(c->m->device);
+    cudaStreamSynchronize(c->st);
+    if (c->g_logits) cudaGraphExecDestroy(c->g_logits);
+    if (c->g_greedy) cudaGraphExecDestroy(c->g_greedy);
+    if (c->g_pipe)   cudaGraphExecDestroy(c->g_pipe);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto p : c->kc) cudaFree(p);
+    for (auto p : c->vc) cudaFree(p);
+    cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->logits);
+    cudaFree(c->part_o); cudaFree(c->part_ml); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
+    cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits);
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+extern "C" void b200_kv_clear(b200_ctx * c) {
+    if (!c) return;
+    // the cache is addressed by position and attention only reads slots [0, pos]; clearing is a reset of counters
+    cudaSetDevice(c->m->device);
+    cudaStreamSynchronize(c->st);
+}
+
+extern "C" void b200_set_taps(b200_ctx * c, int enable) { if (c) { c->taps = enable != 0; c->tapstore.v.clear(); } }
+extern "C" int64_t b200_get_tap(b200_ctx * c, const char * name, int layer, float * out, int64_t cap) {
+    if (!c) return 0;
+    auto it = c->tapstore.v.find(std::string(name) + "-" + std::to_string(layer));
+    if (it == c->tapstore.v.end()) return 0;
+    const int64_t n = (int64_t) it->second.size();
+    if (out) std::memcpy(out, it->second.data(), (size_t) std::min(n, cap) * 4);
+    return n;
+}
+extern "C" void b200_timings(b200_ctx * c, double * tp, int64_t * np, double * tg, int64_t * ng) {
+    *tp = c->t_prompt_us; *np = c->n_prompt; *tg = c->t_gen_us; *ng = c->n_gen;
+}
+extern "C" void b200_reset_timings(b200_ctx * c) { c->t_prompt_us = c->t_gen_us = 0; c->n_prompt = c->n_gen = 0; }
+
+static double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, float * logits_out) {
+    try {
+        require_gpu();
+        if (!c || !tokens || n <= 0) throw std::runtime_error("bad arguments");
+        b200_model & m = *c->m;
+        if (!m.has_embd() || !m.has_head()) throw std::runtime_error("b200_decode needs a single-stage model; use b200_pipeline_decode");
+        if (pos0 < 0 || pos0 + n > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");   // find_slot failure: llama.cpp:14690
+        for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= m.n_vocab) throw std::runtime_error("token id out of range");
+        CU(cudaSetDevice(m.device));
+        const double t0 = now_us();
+        // reference semantics for batch > 1: q is rounded to f16 before K.q (cpp/ggml/src/ggml.c:12345-12371)
+        const int round_q = n > 1 ? 1 : 0;
+        for (int i = 0; i < n; i++) {
+            const bool last = i == n - 1;
+            c->h_state->token = tokens[i]; c->h_state->pos = pos0 + i; c->h_state->round_q = round_q; c->h_state->step = 0;
+            if (c->taps) {
+                CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
+                enqueue_forward(c);
+                CU(cudaStreamSynchronize(c->st));
+                if (last && logits_out) CU(cudaMemcpy(logits_out, c->logits, (size_t) m.n_vocab * 4, cudaMemcpyDeviceToHost));
+                continue;
+            }
+            if (!c->g_logits) {
+                c->g_logits = capture(c, [&]() {
+                    CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
+                    enqueue_forward(c);
+                    CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t) m.n_vocab * 4, cudaMemcpyDeviceToHost, c->st));
+                });
+            }
+            CU(cudaGraphLaunch(c->g_logits, c->st));
+            c->launches += forward_launch_count(c);
+            CU(cudaStreamSynchronize(c->st));   // h_state is reused for the next token
+            if (last && logits_out) std::memcpy(logits_out, c->h_logits, (size_t) m.n_vocab * 4);
+        }
+        const double dt = now_us() - t0;
+        if (n > 1) { c->t_prompt_us += dt; c->n_prompt += n; } else { c->t_gen_us += dt; c->n_gen += 1; }
+        return 0;
+    } catch (const std::exception & e) {
+        return set_err(e.what());
+    }
+}
+
+extern "C" int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0, int n_steps, int32_t * out_tokens) {
+    try {
+        require_gpu();
+        if (!c || n_steps <= 0) throw std::runtime_error("bad arguments");
+        b200_model & m = *c->m;
+        if (!m.has_embd() || !m.has_head()) throw std::runtime_error("single-stage model required; use b200_pipeline_generate_greedy");
+        if (pos0 < 0 || pos0 + n_steps > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");
+        if (n_steps > c->out_tokens_cap) throw std::runtime_error("n_steps too large");
+        CU(cudaSetDevice(m.device));
+        const double t0 = now_us();
+        c->h_state->token = first_token; c->h_state->pos = pos0; c->h_state->round_q = 0; c->h_state->step = 0;
+        CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
+        if (!c->g_greedy) {
+            CU(cudaStreamSynchronize(c->st));
+            c->g_greedy = capture(c, [&]() {
+                enqueue_forward(c);
+                k_argmax_advance<<<1, 1024, 0, c->st>>>(c->logits, m.n_vocab, c->d_state, c->d_out_tokens);
+            });
+        }
+        for (int s = 0; s < n_steps; s++) CU(cudaGraphLaunch(c->g_greedy, c->st));
+        c->launches += (forward_launch_count(c) + 1) * (int64_t) n_steps;
+        if (out_tokens) CU(cudaMemcpyAsync(out_tokens, c->d_out_tokens, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        c->t_gen_us += now_us() - t0; c->n_gen += n_steps;
+        return 0;
+    } catch (const std::exception & e) {
+        return set_err(e.what());
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pipeline over NCCL: rank r holds one stage; one send/recv of f32[n_embd] per boundary per token
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int b200_comm_unique_id(uint8_t id[128]) {
+    try { nccl_load(); NC(g_nccl.GetUniqueId(id)); return 0; } catch (const std::exception & e) { return set_err(e.what()); }
+}
+extern "C" int b200_comm_init(b200_ctx * c, int rank, int world, const uint8_t id[128]) {
+    try {
+        require_gpu();
+        nccl_load();
+        CU(cudaSetDevice(c->m->device));
+        NcclId nid; std::memcpy(nid.b, id, 128);
+        NC(g_nccl.CommInitRank(&c->comm, world, nid, rank));
+        c->rank = rank; c->world = world;
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+// one token through this rank's stage: [recv x] -> forward -> [send x] ; last stage: argmax -> token to stage 0
+static void enqueue_stage_step(b200_ctx * c, bool greedy) {
+    b200_model & m = *c->m;
+    const bool first = c->rank == 0, last = c->rank == c->world - 1;
+    if (!first) NC(g_nccl.Recv(c->x, (size_t) m.n_embd, NCCL_FLOAT32, c->rank - 1, c->comm, c->st));
+    enqueue_forward(c);
+    if (!last) NC(g_nccl.Send(c->x, (size_t) m.n_embd, NCCL_FLOAT32, c->rank + 1, c->comm, c->st));
+    if (greedy) {
+        if (last) {
+            k_argmax_advance<<<1, 1024, 0, c->st>>>(c->logits, m.n_vocab, c->d_state, c->d_out_tokens);
+            if (c->world > 1) NC(g_nccl.Send(&c->d_state->token, 1, NCCL_INT32, 0, c->comm, c->st));
+        } else {
+            k_advance<<<1, 32, 0, c->st>>>(c->d_state);
+            if (first) NC(g_nccl.Recv(&c->d_state->token, 1, NCCL_INT32, c->world - 1, c->comm, c->st));
+        }
+        c->launches++;
+    }
+}
+
+extern "C" int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, int pos0, int n_steps, int32_t * out_tokens) {
+    try {
+        require_gpu();
+        if (!c || n_steps <= 0) throw std::runtime_error("bad arguments");
+        if (c->world == 1) return b200_generate_greedy(c, first_token, pos0, n_steps, out_tokens);
+        if (!c->comm) throw std::runtime_error("b200_comm_init not called");
+        b200_model & m = *c->m;
+        CU(cudaSetDevice(m.device));
+        c->h_state->token = first_token; c->h_state->pos = pos0; c->h_state->round_q = 0; c->h_state->step = 0;
+        CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
+        for (int s = 0; s < n_steps; s++) enqueue_stage_step(c, true);
+        // every rank gets the ids: last rank broadcasts point-to-point
+        const bool last = c->rank == c->world - 1;
+        NC(g_nccl.GroupStart());
+        if (last) { for (int r = 0; r < c->world - 1; r++) NC(g_nccl.Send(c->d_out_tokens, (size_t) n_steps, NCCL_INT32, r, c->comm, c->st)); }
+        else      NC(g_nccl.Recv(c->d_out_tokens, (size_t) n_steps, NCCL_INT32, c->world - 1, c->comm, c->st));
+        NC(g_nccl.GroupEnd());
+        if (out_tokens) CU(cudaMemcpyAsync(out_tokens, c->d_out_tokens, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+extern "C" int b200_pipeline_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, float * logits_out) {
+    try {
+        require_gpu();
+        if (!c || !tokens || n <= 0) throw std::runtime_error("bad arguments");
+        if (c->world == 1) return b200_decode(c, tokens, n, pos0, logits_out);
+        if (!c->comm) throw std::runtime_error("b200_comm_init not called");
+        b200_model & m = *c->m;
+        CU(cudaSetDevice(m.device));
+        const int round_q = n > 1 ? 1 : 0;
+        for (int i = 0; i < n; i++) {
+            c->h_state->token = tokens[i]; c->h_state->pos = pos0 + i; c->h_state->round_q = round_q; c->h_state->step = 0;
+            CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
+            enqueue_stage_step(c, false);
+            CU(cudaStreamSynchronize(c->st));
+        }
+        if (c->rank == c->world - 1 && logits_out) CU(cudaMemcpy(logits_out, c->logits, (size_t) m.n_vocab * 4, cudaMemcpyDeviceToHost));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// in-process layer split: stage chain inside one process (what the Go server drives through the bridge)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batch_gt1, b200_ctx * prev) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        b200_model & m = *c->m;
+        if (pos < 0 || pos >= c->n_ctx) throw std::runtime_error("position exceeds n_ctx");
+        if (m.has_embd() && (token < 0 || token >= m.n_vocab)) throw std::runtime_error("token id out of range");
+        if (m.has_embd() != (prev == nullptr)) throw std::runtime_error("stage chain mismatch: only the first stage has no predecessor");
+        CU(cudaSetDevice(m.device));
+        if (prev) {
+            // hand-off of the residual stream l_out -> next device (cf. cpp/ggml/src/ggml-cuda.cu:2386-2407)
+            if (!prev->ev_done) { CU(cudaSetDevice(prev->m->device)); CU(cudaEventCreateWithFlags(&prev->ev_done, cudaEventDisableTiming)); CU(cudaSetDevice(m.device)); }
+            CU(cudaSetDevice(prev->m->device));
+            CU(cudaEventRecord(prev->ev_done, prev->st));
+            CU(cudaSetDevice(m.device));
+            CU(cudaStreamWaitEvent(c->st, prev->ev_done, 0));
+            CU(cudaMemcpyPeerAsync(c->x, m.device, prev->x, prev->m->device, (size_t) m.n_embd * 4, c->st));
+        }
+        DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = batch_gt1 ? 1 : 0; hs.step = 0;
+        k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
+        c->launches++;
+        enqueue_forward(c);
+        CU(cudaGetLastError());
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+extern "C" int b200_stage_logits(b200_ctx * c, float * logits_out) {
+    try {
+        require_gpu();
+        if (!c || !c->m->has_head()) throw std::runtime_error("not the last stage");
+        CU(cudaSetDevice(c->m->device));
+        CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t) c->m->n_vocab * 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        std::memcpy(logits_out, c->h_logits, (size_t) c->m->n_vocab * 4);
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+extern "C" int b200_stage_argmax(b200_ctx * c, int32_t * token_out) {
+    try {
+        require_gpu();
+        if (!c || !c->m->has_head()) throw std::runtime_error("not the last stage");
+        CU(cudaSetDevice(c->m->device));
+        k_argmax_only<<<1, 1024, 0, c->st>>>(c->logits, c->m->n_vocab, c->d_out_tokens);
+        c->launches++;
+        CU(cudaMemcpyAsync(&c->h_state->token, c->d_out_tokens, 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        *token_out = c->h_state->token;
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// operator-level entry points (tests): host in, host out, SAME kernels
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct DBuf {
+    void * p = nullptr;
+    explicit DBuf(size_t n) { CU(cudaMalloc(&p, n ? n : 1)); }
+    ~DBuf() { cudaFree(p); }
+    template <typename T> T * as() { return (T *) p; }
+};
+}  // namespace
+
+static int op_quantize(const float * x, int64_t k, void * out, int q80) {
+    try {
+        require_gpu();
+        if (k <= 0 || k % 256 != 0) throw std::runtime_error("k must be a positive multiple of 256");
+        const size_t ob = q80 ? (size_t) (k / 32) * 34 : (size_t) (k / 256) * 292;
+        DBuf dx((size_t) k * 4), dout(ob);
+        CU(cudaMemcpy(dx.p, x, (size_t) k * 4, cudaMemcpyHostToDevice));
+        const size_t smem = act_smem_bytes((int) k, q80);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_quantize_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        k_quantize_export<<<1, MV_THREADS, smem>>>(dx.as<float>(), (int) k, q80, dout.as<uint8_t>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(out, dout.p, ob, cudaMemcpyDeviceToHost));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+extern "C" int b200_op_quantize_q8_K(const float * x, int64_t k, void * out) { return op_quantize(x, k, out, 0); }
+extern "C" int b200_op_quantize_q8_0(const float * x, int64_t k, void * out) { return op_quantize(x, k, out, 1); }
+
+extern "C" int b200_op_dequantize_row(int type, const void * w, int64_t k, float * y) {
+    try {
+        require_gpu();
+        const size_t rb = (size_t) ggml_row_bytes((uint32_t) type, (uint64_t) k);
+        if (rb == 0) throw std::runtime_error("unsupported type");
+        DBuf dw(rb), dy((size_t) k * 4);
+        CU(cudaMemcpy(dw.p, w, rb, cudaMemcpyHostToDevice));
+        k_embed<<<(unsigned) ((k + 255) / 256), 256>>>(type, dw.as<uint8_t>(), rb, (int) k, nullptr, 0, dy.as<float>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(y, dy.p, (size_t) k * 4, cudaMemcpyDeviceToHost));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+extern "C" int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int64_t k, const float * x, float * y) {
+    try {
+        require_gpu();
+        cudaStream_t st;
+        CU(cudaStreamCreate(&st));
+        DevMat d = upload_matrix(type, w, n_rows, k, st);
+        DBuf dx((size_t) k * 4), dy((size_t) n_rows * 4);
+        CU(cudaMemcpyAsync(dx.p, x, (size_t) k * 4, cudaMemcpyHostToDevice, st));
+        b200_ctx tmp;   // only st / sm_count / launches are used by launch_matvec
+        tmp.st = st;
+        int dev = 0; CU(cudaGetDevice(&dev));
+        cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
+        tmp.sm_count = prop.multiProcessorCount;
+        MatvecArgs a{};
+        a.seg[0] = d.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = (int) (n_rows / 2); a.k = (int) k;
+        a.x = dx.as<float>(); a.norm_w = nullptr; a.act_q8_0 = type == T_Q8_0; a.out = dy.as<float>();
+        launch_matvec<EPI_STORE>(&tmp, a);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(y, dy.p, (size_t) n_rows * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        cudaFree(d.alloc);
+        CU(cudaStreamDestroy(st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+extern "C" int b200_op_rms_norm(const float * x, const float * w, int64_t k, float eps, float * y) {
+    try {
+        require_gpu();
+        DBuf dx((size_t) k * 4), dw((size_t) k * 4), dy((size_t) k * 4);
+        CU(cudaMemcpy(dx.p, x, (size_t) k * 4, cudaMemcpyHostToDevice));
+        if (w) CU(cudaMemcpy(dw.p, w, (size_t) k * 4, cudaMemcpyHostToDevice));
+        k_rms_norm<<<1, 256>>>(dx.as<float>(), w ? dw.as<float>() : nullptr, (int) k, eps, dy.as<float>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(y, dy.p, (size_t) k * 4, cudaMemcpyDeviceToHost));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+extern "C" int b200_op_rope(float * x, int n_heads, int head_dim, int pos, float freq_base, float freq_scale,
+                            const float * freq_factors) {
+    try {
+        require_gpu();
+        b200_model m;
+        m.head_dim = head_dim; m.rope_freq_base = freq_base; m.rope_freq_scale = freq_scale; m.n_ctx_orig = 4096;
+        if (freq_factors) m.rope_freq_factors.assign(freq_factors, freq_factors + head_dim / 2);
+        std::vector<float2> tab;
+        build_rope_table(m, pos + 1, tab);
+        DBuf dt((size_t) (head_dim / 2) * sizeof(float2)), dx((size_t) n_heads * head_dim * 4);
+        CU(cudaMemcpy(dt.p, tab.data() + (size_t) pos * (head_dim / 2), (size_t) (head_dim / 2) * sizeof(float2), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dx.p, x, (size_t) n_heads * head_dim * 4, cudaMemcpyHostToDevice));
+        const int n = n_heads * head_dim / 2;
+        k_rope<<<(n + 127) / 128, 128>>>(dx.as<float>(), n_heads, head_dim, dt.as<float2>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(x, dx.p, (size_t) n_heads * head_dim * 4, cudaMemcpyDeviceToHost));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, const uint16_t * v_cache, int n_kv,
+                                 int n_head, int n_head_kv, int head_dim, float scale, float * out) {
+    try {
+        require_gpu();
+        if (n_kv <= 0) throw std::runtime_error("n_kv must be positive");
+        const int kvd = n_head_kv * head_dim, qd = n_head * head_dim;
+        cudaStream_t st;
+        CU(cudaStreamCreate(&st));
+        int dev = 0; CU(cudaGetDevice(&dev));
+        cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
+        b200_ctx tmp;
+        tmp.st = st; tmp.sm_count = prop.multiProcessorCount;
+        int ns = std::max(1, (2 * tmp.sm_count) / n_head_kv);
+        ns = std::min(ns, std::max(1, (n_kv + 31) / 32));
+        DBuf dq((size_t) qd * 4), dk((size_t) n_kv * kvd * 2), dv((size_t) n_kv * kvd * 2), dout((size_t) qd * 4);
+        DBuf po((size_t) n_head * ns * head_dim * 4), pml((size_t) n_head * ns * 2 * 4);
+        CU(cudaMemcpyAsync(dq.p, q, (size_t) qd * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dk.p, k_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dv.p, v_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
+        b200_model mm; tmp.m = &mm;
+        AttnArgs a{};
+        a.q = dq.as<float>(); a.k_cache = dk.as<__half>(); a.v_cache = dv.as<__half>();
+        a.part_o = po.as<float>(); a.part_ml = pml.as<float>(); a.out = dout.as<float>();
+        a.n_head = n_head; a.n_head_kv = n_head_kv; a.head_dim = head_dim; a.kv_dim = kvd; a.n_splits = ns;
+        a.scale = scale; a.st = nullptr; a.n_kv_override = n_kv;
+        launch_attention(&tmp, a);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, dout.p, (size_t) qd * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaStreamDestroy(st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}

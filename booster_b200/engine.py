@@ -1,0 +1,189 @@
+"""Python mirror of the token-level interface (include/booster_b200.h), named after the llama.h calls
+the reference's bridge makes on the hot path (cpp/bridge.cpp:118-171, 549-560; cpp/janus.cpp:224) so that the
+parity tests read like tests of the reference: load_model_from_file -> new_context_with_model -> decode ->
+get_logits. All compute happens inside libbooster_b200.so on the GPU; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200Error, check
+
+INFO = ["n_vocab", "n_embd", "n_layer", "n_head", "n_head_kv", "n_ff", "head_dim", "n_ctx_train",
+        "layer_begin", "layer_end", "ftype"]
+TYPE = {"F32": 0, "F16": 1, "Q8_0": 8, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}
+
+
+def device_count() -> int:
+    return _lib.lib().b200_device_count()
+
+
+class Model:
+    """llama_load_model_from_file (cpp/bridge.cpp:131) for one pipeline stage [layer_begin, layer_end)."""
+
+    def __init__(self, path: str, device: int = 0, layer_begin: int = 0, layer_end: int = -1):
+        self.L = _lib.lib()
+        self.h = self.L.b200_model_load(path.encode(), device, layer_begin, layer_end)
+        if not self.h:
+            raise B200Error(f"b200_model_load({path}): {_lib.last_error()}")
+        arr = (C.c_int32 * 16)()
+        self.L.b200_model_info(self.h, arr)
+        for i, k in enumerate(INFO):
+            setattr(self, k, int(arr[i]))
+        self.weight_bytes = int(self.L.b200_model_weight_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.b200_model_free(self.h)
+            self.h = None
+
+
+class Context:
+    """llama_new_context_with_model (cpp/bridge.cpp:162) + the decode calls."""
+
+    def __init__(self, model: Model, n_ctx: int = 2048):
+        self.L, self.model = model.L, model
+        self.h = self.L.b200_ctx_new(model.h, n_ctx)
+        if not self.h:
+            raise B200Error(f"b200_ctx_new: {_lib.last_error()}")
+        self.n_ctx = self.L.b200_n_ctx(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.b200_ctx_free(self.h)
+            self.h = None
+
+    def kv_clear(self):
+        self.L.b200_kv_clear(self.h)
+
+    def decode(self, tokens: Sequence[int], pos0: int, want_logits: bool = True) -> Optional[np.ndarray]:
+        """llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0)) then llama_get_logits (last token's row)."""
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty(self.model.n_vocab, dtype=np.float32) if want_logits else None
+        check(self.L.b200_decode(self.h, toks.ctypes.data_as(C.POINTER(C.c_int32)), len(toks), pos0,
+                                 out.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None), "b200_decode")
+        return out
+
+    def generate_greedy(self, first_token: int, pos0: int, n_steps: int) -> np.ndarray:
+        out = np.empty(n_steps, dtype=np.int32)
+        check(self.L.b200_generate_greedy(self.h, first_token, pos0, n_steps, out.ctypes.data_as(C.POINTER(C.c_int32))),
+              "b200_generate_greedy")
+        return out
+
+    def greedy(self, prompt: Sequence[int], n_gen: int) -> (List[int], List[np.ndarray]):
+        """Same protocol as oracle.ref.RefModel.greedy: prefill in one batch, n_gen arg-max steps with logits."""
+        self.kv_clear()
+        logits = self.decode(prompt, 0)
+        pos = len(prompt)
+        ids, all_logits = [], []
+        for _ in range(n_gen):
+            all_logits.append(logits)
+            t = int(np.argmax(logits))
+            ids.append(t)
+            logits = self.decode([t], pos)
+            pos += 1
+        return ids, all_logits
+
+    def set_taps(self, enable: bool):
+        self.L.b200_set_taps(self.h, int(enable))
+
+    def get_tap(self, name: str, layer: int) -> Optional[np.ndarray]:
+        n = self.L.b200_get_tap(self.h, name.encode(), layer, None, 0)
+        if n == 0:
+            return None
+        out = np.empty(n, dtype=np.float32)
+        self.L.b200_get_tap(self.h, name.encode(), layer, out.ctypes.data_as(C.POINTER(C.c_float)), n)
+        return out
+
+    def kernel_launches(self) -> int:
+        return int(self.L.b200_kernel_launches(self.h))
+
+    # pipeline over NCCL (one process per GPU)
+    def comm_init(self, rank: int, world: int, uid: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        check(self.L.b200_comm_init(self.h, rank, world, buf), "b200_comm_init")
+
+    def pipeline_generate_greedy(self, first_token: int, pos0: int, n_steps: int) -> np.ndarray:
+        out = np.empty(n_steps, dtype=np.int32)
+        check(self.L.b200_pipeline_generate_greedy(self.h, first_token, pos0, n_steps,
+                                                   out.ctypes.data_as(C.POINTER(C.c_int32))), "b200_pipeline_generate_greedy")
+        return out
+
+    def pipeline_decode(self, tokens: Sequence[int], pos0: int, want_logits: bool = False) -> Optional[np.ndarray]:
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty(self.model.n_vocab, dtype=np.float32) if want_logits else None
+        check(self.L.b200_pipeline_decode(self.h, toks.ctypes.data_as(C.POINTER(C.c_int32)), len(toks), pos0,
+                                          out.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None), "b200_pipeline_decode")
+        return out
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    check(_lib.lib().b200_comm_unique_id(buf), "b200_comm_unique_id")
+    return bytes(buf)
+
+
+# ---- operator-level wrappers (parity tests) ----------------------------------------------------------------
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def op_quantize_q8_K(x) -> np.ndarray:
+    x = _f32(x)
+    out = np.empty(x.size // 256 * 292, dtype=np.uint8)
+    check(_lib.lib().b200_op_quantize_q8_K(x.ctypes.data_as(C.POINTER(C.c_float)), x.size, out.ctypes.data), "op_quantize_q8_K")
+    return out
+
+
+def op_quantize_q8_0(x) -> np.ndarray:
+    x = _f32(x)
+    out = np.empty(x.size // 32 * 34, dtype=np.uint8)
+    check(_lib.lib().b200_op_quantize_q8_0(x.ctypes.data_as(C.POINTER(C.c_float)), x.size, out.ctypes.data), "op_quantize_q8_0")
+    return out
+
+
+def op_dequantize_row(t: int, raw, k: int) -> np.ndarray:
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    out = np.empty(k, dtype=np.float32)
+    check(_lib.lib().b200_op_dequantize_row(t, raw.ctypes.data, k, out.ctypes.data_as(C.POINTER(C.c_float))), "op_dequantize_row")
+    return out
+
+
+def op_mul_mat_vec(t: int, w_raw, n_rows: int, k: int, x) -> np.ndarray:
+    w_raw = np.ascontiguousarray(w_raw, dtype=np.uint8)
+    x = _f32(x)
+    y = np.empty(n_rows, dtype=np.float32)
+    check(_lib.lib().b200_op_mul_mat_vec(t, w_raw.ctypes.data, n_rows, k, x.ctypes.data_as(C.POINTER(C.c_float)),
+                                         y.ctypes.data_as(C.POINTER(C.c_float))), "op_mul_mat_vec")
+    return y
+
+
+def op_rms_norm(x, w, eps: float) -> np.ndarray:
+    x = _f32(x)
+    y = np.empty_like(x)
+    wp = _f32(w).ctypes.data_as(C.POINTER(C.c_float)) if w is not None else None
+    check(_lib.lib().b200_op_rms_norm(x.ctypes.data_as(C.POINTER(C.c_float)), wp, x.size, eps,
+                                      y.ctypes.data_as(C.POINTER(C.c_float))), "op_rms_norm")
+    return y
+
+
+def op_rope(x, n_heads: int, head_dim: int, pos: int, freq_base: float, freq_scale: float = 1.0, freq_factors=None) -> np.ndarray:
+    y = _f32(x).copy()
+    ff = _f32(freq_factors).ctypes.data_as(C.POINTER(C.c_float)) if freq_factors is not None else None
+    check(_lib.lib().b200_op_rope(y.ctypes.data_as(C.POINTER(C.c_float)), n_heads, head_dim, pos, freq_base, freq_scale, ff), "op_rope")
+    return y
+
+
+def op_attention(q, k_cache_f16, v_cache_f16, n_kv: int, n_head: int, n_head_kv: int, head_dim: int, scale: float) -> np.ndarray:
+    q = _f32(q)
+    k = np.ascontiguousarray(k_cache_f16, dtype=np.float16).view(np.uint16)
+    v = np.ascontiguousarray(v_cache_f16, dtype=np.float16).view(np.uint16)
+    out = np.empty(n_head * head_dim, dtype=np.float32)
+    check(_lib.lib().b200_op_attention(q.ctypes.data_as(C.POINTER(C.c_float)), k.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                       v.ctypes.data_as(C.POINTER(C.c_uint16)), n_kv, n_head, n_head_kv, head_dim, scale,
+                                       out.ctypes.data_as(C.POINTER(C.c_float))), "op_attention")
+    return out

@@ -1,0 +1,143 @@
+/* include/booster_b200.h — ADDITIVE token-level and operator-level C-ABI of libbooster_b200.so.
+ *
+ * include/bridge.h is the boundary Booster's Go server binds. The entry points below sit one seam
+ * lower — the llama.h calls cpp/bridge.cpp makes on the hot path — so that the CUDA path can be
+ * parity-tested against the reference's CPU path on token ids and logits, without tokenizer or
+ * sampler in between (SURVEY.md §8b "inner seams"). Every function cites the reference interface it
+ * replaces. Plain C, host pointers and sizes only; all device memory is owned by the library.
+ *
+ * Error convention: functions returning int return 0 on success, non-zero on failure;
+ * b200_last_error() returns a thread-local message. There is NO CPU fallback anywhere: without a CUDA
+ * device every compute entry point fails loudly.
+ */
+#ifndef BOOSTER_B200_H
+#define BOOSTER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_model b200_model;   /* replaces struct llama_model   (cpp/include/llama.h) */
+typedef struct b200_ctx   b200_ctx;     /* replaces struct llama_context (cpp/include/llama.h) */
+
+/* ggml tensor type ids of the block formats on the path (cpp/ggml/include/ggml.h:360-375) */
+enum b200_type {
+    B200_TYPE_F32  = 0,
+    B200_TYPE_F16  = 1,
+    B200_TYPE_Q8_0 = 8,
+    B200_TYPE_Q4_K = 12,
+    B200_TYPE_Q5_K = 13,
+    B200_TYPE_Q6_K = 14,
+};
+
+const char * b200_last_error(void);
+int          b200_device_count(void);                 /* 0 when no CUDA device is visible */
+const char * b200_version(void);
+
+/* ---- model + context -------------------------------------------------------------------------------------
+ * b200_model_load     replaces llama_load_model_from_file (cpp/bridge.cpp:131; loader cpp/src/llama.cpp:16539,
+ *                     tensors :6062-6110). Parses the GGUF, keeps every matrix in its block format
+ *                     (re-tiled into 16-byte-aligned planes, same bytes) in HBM of CUDA device `device`.
+ *                     A pipeline stage holds layers [layer_begin, layer_end); pass 0,-1 for the whole model.
+ *                     The stage with layer_begin == 0 also holds token_embd; the stage with
+ *                     layer_end == n_layer also holds output_norm + output (cf. cpp/src/llama.cpp:5932-5968).
+ * b200_ctx_new        replaces llama_new_context_with_model (cpp/bridge.cpp:162; cpp/src/llama.cpp:16592-16993):
+ *                     f16 KV cache for the stage's layers (:2926-3022), n_ctx padded to 32 (:16655).            */
+b200_model * b200_model_load(const char * gguf_path, int device, int layer_begin, int layer_end);
+void         b200_model_free(b200_model * m);
+
+enum { B200_INFO_N_VOCAB = 0, B200_INFO_N_EMBD, B200_INFO_N_LAYER, B200_INFO_N_HEAD, B200_INFO_N_HEAD_KV,
+       B200_INFO_N_FF, B200_INFO_HEAD_DIM, B200_INFO_N_CTX_TRAIN, B200_INFO_LAYER_BEGIN, B200_INFO_LAYER_END,
+       B200_INFO_FTYPE, B200_INFO_COUNT = 16 };
+int     b200_model_info(const b200_model * m, int32_t info[B200_INFO_COUNT]);
+/* algorithmic HBM bytes one decoded token reads from this stage's matrices + norm vectors
+ * (token_embd excluded: one row) — SURVEY.md §8(d) / BASELINE.md §3 */
+int64_t b200_model_weight_bytes(const b200_model * m);
+
+b200_ctx * b200_ctx_new(b200_model * m, int n_ctx);
+void       b200_ctx_free(b200_ctx * c);
+int        b200_n_ctx(const b200_ctx * c);
+void       b200_kv_clear(b200_ctx * c);               /* llama_kv_cache_clear (cpp/bridge.cpp:459) */
+
+/* ---- the hot path ------------------------------------------------------------------------------------------
+ * b200_decode == llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0))  (cpp/bridge.cpp:549-560,
+ *                cpp/src/llama.cpp:18517 → llama_decode_internal :14537-14840) followed by
+ *                llama_get_logits (cpp/janus.cpp:224): logits_out[n_vocab] receives the LAST token's logits
+ *                (the only row llama_batch_get_one keeps). logits_out may be NULL (prompt chunks).
+ *                Single-stage contexts only; pipeline stages use b200_stage_step.                            */
+int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, float * logits_out);
+
+/* Device-resident greedy loop: token → decode → argmax → next token, n_steps times, one CUDA-graph replay
+ * per token, no host round trip between tokens. Equivalent to the reference loop cpp/bridge.cpp:467-646 with
+ * argmax sampling (cpp/bridge.cpp:962-981 sample_top_token). out_tokens[n_steps] receives the sampled ids. */
+int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0, int n_steps, int32_t * out_tokens);
+
+/* Per-node taps for layer-wise parity (the counterpart of llama_context_params.cb_eval,
+ * cpp/include/llama.h:324-325; node names cpp/src/llama.cpp:13812-13817). When enabled, b200_decode runs
+ * un-graphed and keeps host copies of: "Qcur" (post-RoPE), "kqv_merged_cont", "ffn_inp", "ffn_gate_par",
+ * "l_out" per layer and "result_output". Returns the element count, copies min(count, cap) floats. */
+void    b200_set_taps(b200_ctx * c, int enable);
+int64_t b200_get_tap(b200_ctx * c, const char * name, int layer, float * out, int64_t cap);
+
+/* µs-resolution counters (the reference's are ms-truncated at the bridge: cpp/bridge.cpp:650-655) */
+void b200_timings(b200_ctx * c, double * t_prompt_us, int64_t * n_prompt, double * t_gen_us, int64_t * n_gen);
+void b200_reset_timings(b200_ctx * c);
+/* number of kernels launched by this library's own code since the context was created */
+int64_t b200_kernel_launches(const b200_ctx * c);
+
+/* ---- layer-split pipeline over NCCL (replaces ggml_backend_cuda_cpy_tensor_async,
+ * cpp/ggml/src/ggml-cuda.cu:2386-2407, invoked from cpp/ggml/src/ggml-backend.c:1782) ---------------------
+ * One process per GPU. Rank r owns the stage its model was loaded with. Per token each boundary moves the
+ * residual stream f32[n_embd] with ONE ncclSend/ncclRecv; the last stage returns the argmax token to
+ * stage 0 with one more 4-byte send/recv (greedy) or the logits stay on the last rank.                      */
+int b200_comm_unique_id(uint8_t id[128]);
+int b200_comm_init(b200_ctx * c, int rank, int world, const uint8_t id[128]);
+/* All ranks call this collectively: run n_steps greedy tokens through the pipeline, starting from
+ * first_token at position pos0. Every rank receives the token ids in out_tokens. */
+int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, int pos0, int n_steps, int32_t * out_tokens);
+/* Collective: feed n prompt tokens (positions pos0..) through the pipeline; logits_out (may be NULL)
+ * is filled on the LAST rank only. */
+int b200_pipeline_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, float * logits_out);
+
+/* ---- in-process layer split (one process, several GPUs — what the Go server uses when `gpus: [..]` names more
+ * than one device; replaces ggml_backend_sched_compute_splits + cudaMemcpyPeerAsync + event,
+ * cpp/ggml/src/ggml-backend.c:1751-1844, cpp/ggml/src/ggml-cuda.cu:2386-2407) -----------------------------
+ * b200_stage_forward runs ONE token through the layers of stage `c`. If `prev` is non-NULL the residual
+ * stream f32[n_embd] is first copied from prev's device (peer copy ordered by an event, no host sync).
+ * batch_gt1 != 0 selects the reference's batch>1 arithmetic (q rounded to f16 before K.q).
+ * b200_stage_logits / b200_stage_argmax synchronise and read the LAST stage's result.                       */
+int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batch_gt1, b200_ctx * prev);
+int b200_stage_logits(b200_ctx * c, float * logits_out);
+int b200_stage_argmax(b200_ctx * c, int32_t * token_out);
+
+/* ---- operator-level entry points (parity tests; host pointers, compute on the GPU with the SAME kernels
+ * the engine launches) ----------------------------------------------------------------------------------- */
+/* quantize_row_q8_K (cpp/ggml/src/ggml-quants.c:3593-3630): out = block_q8_K[k/256] in ggml layout (292 B each) */
+int b200_op_quantize_q8_K(const float * x, int64_t k, void * out);
+/* quantize_row_q8_0, AVX path (cpp/ggml/src/ggml-quants.c:866-1000): out = block_q8_0[k/32] (34 B each) */
+int b200_op_quantize_q8_0(const float * x, int64_t k, void * out);
+/* dequantize_row_q4_K/q5_K/q6_K/q8_0 (cpp/ggml/src/ggml-quants.c:2548,2756,2970,1609) = the embedding
+ * get_rows path (cpp/ggml/src/ggml.c:13186): w = one row of blocks in ggml layout */
+int b200_op_dequantize_row(int type, const void * w, int64_t k, float * y);
+/* ggml_compute_forward_mul_mat at batch 1 (cpp/ggml/src/ggml.c:12277-12490) with vec_dot_{q4_K,q5_K,q6_K}_q8_K /
+ * q8_0_q8_0 (cpp/ggml/src/ggml-quants.c:6832,7400,8037,5227): y[n_rows] = W[n_rows x k] . x[k];
+ * w = n_rows rows of blocks in ggml row-major layout */
+int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int64_t k, const float * x, float * y);
+/* ggml_compute_forward_rms_norm_f32 then ggml_mul by the weight (cpp/ggml/src/ggml.c:11850-11896,
+ * cpp/src/llama.cpp:7928-7958). w may be NULL. */
+int b200_op_rms_norm(const float * x, const float * w, int64_t k, float eps, float * y);
+/* ggml_compute_forward_rope_f32, NORM mode (cpp/ggml/src/ggml.c:14043-14166): x[n_heads][head_dim] in place
+ * for position pos. freq_factors may be NULL. */
+int b200_op_rope(float * x, int n_heads, int head_dim, int pos, float freq_base, float freq_scale,
+                 const float * freq_factors);
+/* the default (non-flash) attention route at batch 1 (cpp/src/llama.cpp:8188-8299): q[n_head][hd] f32,
+ * k_cache/v_cache = f16 bits [n_kv][n_head_kv*hd] (position-major), out[n_head*hd]. */
+int b200_op_attention(const float * q, const uint16_t * k_cache, const uint16_t * v_cache, int n_kv,
+                      int n_head, int n_head_kv, int head_dim, float scale, float * out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOOSTER_B200_H */
