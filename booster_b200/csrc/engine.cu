@@ -425,6 +425,11 @@ struct b200_ctx {
     void * comm = nullptr;
     int rank = 0, world = 1;
     cudaEvent_t ev_done = nullptr;     // in-process stage chain hand-off
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // device time of the last generate/decode call
+    float last_device_ms = 0.f;
+    // per-launch profiling (bench.py's live roofline): event pairs around every launch of one token
+    bool prof = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_ev;   // (kind, (start, stop))
     // counters
     int64_t launches = 0;
     double t_prompt_us = 0, t_gen_us = 0;
@@ -434,8 +439,17 @@ struct b200_ctx {
 extern "C" int b200_n_ctx(const b200_ctx * c) { return c ? c->n_ctx : 0; }
 extern "C" int64_t b200_kernel_launches(const b200_ctx * c) { return c ? c->launches : 0; }
 
+enum { KIND_EMBED = 0, KIND_QKV, KIND_ATTN, KIND_WO, KIND_GATEUP, KIND_DOWN, KIND_HEAD, KIND_COUNT };
+static int g_kind = KIND_EMBED;   // set by enqueue_forward before each launch group
+struct ProfScope {
+    b200_ctx * c; cudaEvent_t a = nullptr, b = nullptr;
+    explicit ProfScope(b200_ctx * c_);
+    ~ProfScope();
+};
+
 template <int EPI>
 static void launch_matvec(b200_ctx * c, const MatvecArgs & a) {
+    ProfScope ps(c);
     const size_t smem = act_smem_bytes(a.k, a.act_q8_0);
     const int max_ctas = c->sm_count * 2;
     int grid = (a.n_pairs + MV_WARPS - 1) / MV_WARPS;
@@ -445,6 +459,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a) {
 }
 
 static void launch_attention(b200_ctx * c, const AttnArgs & a) {
+    ProfScope ps(c);
     const int gqa = a.n_head / a.n_head_kv;
     const int chunk_cap = a.n_kv_override > 0 ? (a.n_kv_override + a.n_splits - 1) / a.n_splits : c->max_chunk;
     const size_t smem = (size_t) gqa * a.head_dim * 4 + (size_t) gqa * chunk_cap * 4;
@@ -458,6 +473,17 @@ static void launch_attention(b200_ctx * c, const AttnArgs & a) {
     }
     k_attn_combine<<<a.n_head, 128, 0, c->st>>>(a);
     c->launches += 2;
+}
+
+ProfScope::ProfScope(b200_ctx * c_) : c(c_) {
+    if (!c->prof) return;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, c->st));
+}
+ProfScope::~ProfScope() {
+    if (!c->prof) return;
+    cudaEventRecord(b, c->st);
+    c->prof_ev.push_back({g_kind, {a, b}});
 }
 
 static void tap(b200_ctx * c, const std::string & name, int il, const float * dptr, size_t n) {
@@ -475,6 +501,8 @@ static void enqueue_forward(b200_ctx * c) {
     const int E = m.n_embd, HD = m.head_dim, KVD = m.n_head_kv * HD, QD = m.n_head * HD, FF = m.n_ff;
     if (m.has_embd()) {
         const int thr = 256;
+        g_kind = KIND_EMBED;
+        ProfScope ps(c);
         k_embed<<<(E + thr - 1) / thr, thr, 0, c->st>>>(m.embd_type, m.embd_rows, m.embd_row_bytes, E, c->d_state, 0, c->x);
         c->launches++;
     }
@@ -483,6 +511,7 @@ static void enqueue_forward(b200_ctx * c) {
         const int il = m.layer_begin + li;
         const int q80 = L.wq.m.type == T_Q8_0;
         {   // QKV
+            g_kind = KIND_QKV;
             MatvecArgs a{};
             a.seg[0] = L.wq.m; a.seg[1] = L.wk.m; a.seg[2] = L.wv.m; a.n_seg = 3;
             a.pair_mode = PAIR_ADJACENT; a.n_pairs = (QD + 2 * KVD) / 2; a.k = E;
@@ -493,6 +522,7 @@ static void enqueue_forward(b200_ctx * c) {
             tap(c, "Qcur", il, c->q, (size_t) QD);
         }
         {   // attention
+            g_kind = KIND_ATTN;
             AttnArgs a{};
             a.q = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
             a.part_o = c->part_o; a.part_ml = c->part_ml; a.out = c->att;
@@ -503,6 +533,7 @@ static void enqueue_forward(b200_ctx * c) {
             tap(c, "kqv_merged_cont", il, c->att, (size_t) QD);
         }
         {   // wo + residual
+            g_kind = KIND_WO;
             MatvecArgs a{};
             a.seg[0] = L.wo.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = E / 2; a.k = QD;
             a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = q80;
@@ -511,6 +542,7 @@ static void enqueue_forward(b200_ctx * c) {
             tap(c, "ffn_inp", il, c->x, (size_t) E);
         }
         {   // gate/up
+            g_kind = KIND_GATEUP;
             MatvecArgs a{};
             a.seg[0] = L.gate.m; a.seg[1] = L.up.m; a.n_seg = 2; a.pair_mode = PAIR_ZIP; a.n_pairs = FF; a.k = E;
             a.x = c->x; a.norm_w = L.ffn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
@@ -519,6 +551,7 @@ static void enqueue_forward(b200_ctx * c) {
             tap(c, "ffn_gate_par", il, c->ffh, (size_t) FF);
         }
         {   // down + residual
+            g_kind = KIND_DOWN;
             MatvecArgs a{};
             a.seg[0] = L.down.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = E / 2; a.k = FF;
             a.x = c->ffh; a.norm_w = nullptr; a.act_q8_0 = q80;
@@ -528,6 +561,7 @@ static void enqueue_forward(b200_ctx * c) {
         }
     }
     if (m.has_head()) {
+        g_kind = KIND_HEAD;
         MatvecArgs a{};
         a.seg[0] = m.output.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = m.n_vocab / 2; a.k = E;
         a.x = c->x; a.norm_w = m.output_norm; a.eps = m.rms_eps; a.act_q8_0 = m.output.m.type == T_Q8_0;
@@ -584,20 +618,23 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
             __half * k = nullptr, * v = nullptr;
             CU(cudaMalloc(&k, (size_t) c->n_ctx * KVD * 2));
             CU(cudaMalloc(&v, (size_t) c->n_ctx * KVD * 2));
-            CU(cudaMemset(k, 0, (size_t) c->n_ctx * KVD * 2));
-            CU(cudaMemset(v, 0, (size_t) c->n_ctx * KVD * 2));
+            // on the context's own (non-blocking) stream: the legacy default stream does not order against it
+            CU(cudaMemsetAsync(k, 0, (size_t) c->n_ctx * KVD * 2, c->st));
+            CU(cudaMemsetAsync(v, 0, (size_t) c->n_ctx * KVD * 2, c->st));
             c->kc.push_back(k); c->vc.push_back(v);
         }
         std::vector<float2> tab;
         build_rope_table(*m, c->n_ctx, tab);
         CU(cudaMalloc(&c->rope, tab.size() * sizeof(float2)));
-        CU(cudaMemcpy(c->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(c->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
         CU(cudaMalloc(&c->d_state, sizeof(DecodeState)));
-        CU(cudaMemset(c->d_state, 0, sizeof(DecodeState)));
+        CU(cudaMemsetAsync(c->d_state, 0, sizeof(DecodeState), c->st));
         CU(cudaMallocHost(&c->h_state, sizeof(DecodeState)));
         CU(cudaMallocHost(&c->h_logits, (size_t) m->n_vocab * 4));
         c->out_tokens_cap = c->n_ctx + 8;
         CU(cudaMalloc(&c->d_out_tokens, (size_t) c->out_tokens_cap * 4));
+        CU(cudaStreamSynchronize(c->st));
+        CU(cudaDeviceSynchronize());
         return c.release();
     } catch (const std::exception & e) {
         set_err(e.what());
@@ -708,15 +745,49 @@ extern "C" int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0,
                 k_argmax_advance<<<1, 1024, 0, c->st>>>(c->logits, m.n_vocab, c->d_state, c->d_out_tokens);
             });
         }
+        if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
+        CU(cudaEventRecord(c->ev_t0, c->st));
         for (int s = 0; s < n_steps; s++) CU(cudaGraphLaunch(c->g_greedy, c->st));
+        CU(cudaEventRecord(c->ev_t1, c->st));
         c->launches += (forward_launch_count(c) + 1) * (int64_t) n_steps;
         if (out_tokens) CU(cudaMemcpyAsync(out_tokens, c->d_out_tokens, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
+        CU(cudaEventElapsedTime(&c->last_device_ms, c->ev_t0, c->ev_t1));
         c->t_gen_us += now_us() - t0; c->n_gen += n_steps;
         return 0;
     } catch (const std::exception & e) {
         return set_err(e.what());
     }
+}
+
+extern "C" float b200_last_device_ms(const b200_ctx * c) { return c ? c->last_device_ms : 0.f; }
+
+// One token, un-graphed, with a CUDA-event pair around every launch on the engine's own stream:
+// ms_by_kind[k] = summed device time of kind k, n_by_kind[k] = launches of that kind
+// (kinds: 0 embed, 1 qkv, 2 attention(partial+combine), 3 wo, 4 gate/up, 5 down, 6 head).
+extern "C" int b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms_by_kind[8], int32_t n_by_kind[8]) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        b200_model & m = *c->m;
+        if (pos < 0 || pos >= c->n_ctx || token < 0 || token >= m.n_vocab) throw std::runtime_error("bad token/pos");
+        CU(cudaSetDevice(m.device));
+        DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = 0; hs.step = 0;
+        k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
+        c->prof = true; c->prof_ev.clear();
+        enqueue_forward(c);
+        c->prof = false;
+        CU(cudaStreamSynchronize(c->st));
+        for (int k = 0; k < 8; k++) { ms_by_kind[k] = 0.f; n_by_kind[k] = 0; }
+        for (auto & pe : c->prof_ev) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, pe.second.first, pe.second.second));
+            ms_by_kind[pe.first] += ms; n_by_kind[pe.first] += 1;
+            cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second);
+        }
+        c->prof_ev.clear();
+        return 0;
+    } catch (const std::exception & e) { c->prof = false; return set_err(e.what()); }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -557,8 +557,8 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
     } else {
         for (int b = threadIdx.x; b < k / 32; b += blockDim.x) {
             uint8_t * o = out + (size_t) b * 34;
-            const unsigned short hb = __half_as_ushort(__float2half_rn(A.dx[b]));   // dx is already an exact f16 value
-            o[0] = (uint8_t) (hb & 0xff); o[1] = (uint8_t) (hb >> 8);
+            const __half hd = __float2half_rn(A.dx[b]);     // dx is already an exact f16 value
+            *reinterpret_cast<__half *>(o) = hd;              // 34*b is even: 2-byte aligned
             for (int i = 0; i < 32; i++) o[2 + i] = (uint8_t) A.q[b * 32 + i];
         }
     }

@@ -99,6 +99,18 @@ class Context:
         self.L.b200_get_tap(self.h, name.encode(), layer, out.ctypes.data_as(C.POINTER(C.c_float)), n)
         return out
 
+    def last_device_ms(self) -> float:
+        return float(self.L.b200_last_device_ms(self.h))
+
+    def profile_token(self, token: int, pos: int):
+        """device ms and launch count per kernel kind for one un-graphed token (event pair around every launch)"""
+        ms = np.zeros(8, dtype=np.float32)
+        cnt = np.zeros(8, dtype=np.int32)
+        check(self.L.b200_profile_token(self.h, token, pos, ms.ctypes.data_as(C.POINTER(C.c_float)),
+                                        cnt.ctypes.data_as(C.POINTER(C.c_int32))), "b200_profile_token")
+        kinds = ["embed", "qkv", "attention", "wo", "gate_up", "down", "head"]
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(kinds)}
+
     def kernel_launches(self) -> int:
         return int(self.L.b200_kernel_launches(self.h))
 

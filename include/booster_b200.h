@@ -86,6 +86,15 @@ void b200_timings(b200_ctx * c, double * t_prompt_us, int64_t * n_prompt, double
 void b200_reset_timings(b200_ctx * c);
 /* number of kernels launched by this library's own code since the context was created */
 int64_t b200_kernel_launches(const b200_ctx * c);
+/* device time (CUDA events on the engine's stream) of the last b200_generate_greedy call, milliseconds */
+float   b200_last_device_ms(const b200_ctx * c);
+/* one token, un-graphed, with an event pair around every launch: summed device ms and launch count per kernel
+ * kind (0 embed, 1 qkv, 2 attention, 3 wo, 4 gate/up, 5 down, 6 head) — the live per-kernel roofline of bench.py */
+int     b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms_by_kind[8], int32_t n_by_kind[8]);
+
+/* µs-resolution per-token timings of a finished bridge job (additive companion of promptEval()/timing(),
+ * whose integer-millisecond values read 0 on a B200) */
+int b200_job_timing_us(const char * jobID, double * prompt_us_per_token, double * gen_us_per_token);
 
 /* ---- layer-split pipeline over NCCL (replaces ggml_backend_cuda_cpy_tensor_async,
  * cpp/ggml/src/ggml-cuda.cu:2386-2407, invoked from cpp/ggml/src/ggml-backend.c:1782) ---------------------

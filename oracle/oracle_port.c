@@ -1,0 +1,404 @@
+/* oracle/oracle_port.c — TEST INFRASTRUCTURE, NOT PRODUCT ("port" oracle).
+ *
+ * A plain-C restatement of the reference's CPU arithmetic for the quantized LLaMA decode path, written
+ * from the reference sources under /root/reference/cpp (every function cites the file:line it follows).
+ * It exists so that parity can be checked where /root/reference is absent (the GPU box) and so that the
+ * algorithm is stated once in readable scalar code. It is PINNED against the real reference: tests/ compare
+ * it with oracle/_ref (the unmodified reference compiled by oracle/Makefile) and with the golden vectors under
+ * tests/golden/ that oracle/_ref generated (tests/golden/make_golden.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library. The product (booster_b200/) never does.
+ *
+ * Float summation ORDER of the quantized dot products follows the reference's AVX2 code path (the one an
+ * x86-64 Booster build runs: 8 fp32 lanes, FMA, then a fixed horizontal add), so on x86 the port's mat-vec
+ * is bit-identical to the reference's; attention/softmax use straightforward scalar order and libm expf
+ * (the reference uses tinyBLAS tiles and a SIMD exp polynomial), i.e. they agree to fp32 round-off.
+ * Compile with -ffp-contract=off: contraction is written explicitly with fmaf where the reference uses FMA.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define QK_K 256
+
+/* ---- fp16 <-> fp32, IEEE round-to-nearest-even (what F16C _cvtss_sh / _cvtsh_ss do; ggml-impl.h) ---------- */
+static float h2f(uint16_t h) {
+    const uint32_t s = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1f, m = h & 0x3ffu, u;
+    if (e == 0) {
+        if (m == 0) u = s;
+        else { e = 1; while (!(m & 0x400u)) { m <<= 1; e--; } m &= 0x3ffu; u = s | ((e + 112) << 23) | (m << 13); }
+    } else if (e == 31) u = s | 0x7f800000u | (m << 13);
+    else u = s | ((e + 112) << 23) | (m << 13);
+    float f; memcpy(&f, &u, 4); return f;
+}
+static uint16_t f2h(float f) {
+    uint32_t u; memcpy(&u, &f, 4);
+    const uint32_t s = (u >> 16) & 0x8000u;
+    const int32_t e = (int32_t)((u >> 23) & 0xff) - 127 + 15;
+    uint32_t m = u & 0x7fffffu;
+    if (((u >> 23) & 0xff) == 0xff) return (uint16_t)(s | 0x7c00u | (m ? 0x200u : 0));
+    if (e >= 31) return (uint16_t)(s | 0x7c00u);
+    if (e <= 0) {
+        if (e < -10) return (uint16_t) s;
+        m |= 0x800000u;
+        const int shift = 14 - e;
+        uint32_t r = m >> shift;
+        const uint32_t rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (r & 1))) r++;
+        return (uint16_t)(s | r);
+    }
+    uint32_t r = ((uint32_t) e << 10) | (m >> 13);
+    const uint32_t rem = m & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (r & 1))) r++;
+    return (uint16_t)(s | r);
+}
+static uint16_t rd16(const uint8_t * p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+/* round-half-even of a float to int: nearest_int(), cpp/ggml/src/ggml-quants.c:1632-1637 (magic-number add) */
+static int nearest_int(float fval) {
+    float val = fval + 12582912.f;
+    int i; memcpy(&i, &val, sizeof(int));
+    return (i & 0x007fffff) - 0x00400000;
+}
+
+/* ---- activation quantization ----------------------------------------------------------------------------- */
+/* quantize_row_q8_K_ref, cpp/ggml/src/ggml-quants.c:3593-3630. out: block_q8_K {float d; int8 qs[256];
+ * int16 bsums[16]} = 292 bytes per block (cpp/ggml/src/ggml-common.h:311-315). */
+void port_quantize_row_q8_K(const float * x, uint8_t * out, int64_t k) {
+    for (int64_t b = 0; b < k / QK_K; b++, x += QK_K, out += 292) {
+        float max = 0, amax = 0;
+        for (int j = 0; j < QK_K; j++) { const float ax = fabsf(x[j]); if (ax > amax) { amax = ax; max = x[j]; } }
+        int8_t * qs = (int8_t *)(out + 4);
+        if (!amax) { memset(out, 0, 292); continue; }
+        const float iscale = -127.f / max;
+        for (int j = 0; j < QK_K; j++) { int v = nearest_int(iscale * x[j]); qs[j] = (int8_t)(v < 127 ? v : 127); }
+        for (int j = 0; j < 16; j++) {
+            int sum = 0;
+            for (int i = 0; i < 16; i++) sum += qs[16 * j + i];
+            const int16_t s16 = (int16_t) sum; memcpy(out + 260 + 2 * j, &s16, 2);
+        }
+        const float d = 1 / iscale; memcpy(out, &d, 4);
+    }
+}
+/* quantize_row_q8_0, AVX path, cpp/ggml/src/ggml-quants.c:936-1000: d = amax/127 -> fp16, id = 127/amax,
+ * q = round-half-even(x*id). out: block_q8_0 {half d; int8 qs[32]} = 34 bytes (ggml-common.h:186-190). */
+void port_quantize_row_q8_0(const float * x, uint8_t * out, int64_t k) {
+    for (int64_t b = 0; b < k / 32; b++, x += 32, out += 34) {
+        float amax = 0;
+        for (int j = 0; j < 32; j++) { const float ax = fabsf(x[j]); if (ax > amax) amax = ax; }
+        const float d = amax / 127.f;
+        const uint16_t dh = f2h(d); out[0] = (uint8_t)(dh & 0xff); out[1] = (uint8_t)(dh >> 8);
+        const float id = amax != 0.0f ? 127.f / amax : 0.0f;
+        for (int j = 0; j < 32; j++) out[2 + j] = (uint8_t)(int8_t) lrintf(x[j] * id);   /* default rounding mode = RNE */
+    }
+}
+
+/* ---- block formats (cpp/ggml/src/ggml-common.h:186-316) and scale unpacking ------------------------------- */
+/* get_scale_min_k4, cpp/ggml/src/ggml-quants.c:1891-1898 */
+static void scale_min_k4(int j, const uint8_t * q, int * sc, int * m) {
+    if (j < 4) { *sc = q[j] & 63; *m = q[j + 4] & 63; }
+    else { *sc = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4); *m = (q[j + 4] >> 4) | ((q[j] >> 6) << 4); }
+}
+
+/* dequantize_row_q4_K :2548, q5_K :2756, q6_K :2970, q8_0 :1609 (cpp/ggml/src/ggml-quants.c);
+ * this is also the embedding get_rows path (cpp/ggml/src/ggml.c:13186). */
+void port_dequantize_row(int type, const uint8_t * x, float * y, int64_t k) {
+    if (type == 0) { memcpy(y, x, (size_t) k * 4); return; }
+    if (type == 1) { for (int64_t i = 0; i < k; i++) y[i] = h2f(rd16(x + 2 * i)); return; }
+    if (type == 8) {
+        for (int64_t b = 0; b < k / 32; b++, x += 34) {
+            const float d = h2f(rd16(x));
+            for (int j = 0; j < 32; j++) *y++ = (int8_t) x[2 + j] * d;
+        }
+    } else if (type == 12 || type == 13) {
+        const int bb = type == 12 ? 144 : 176;
+        for (int64_t b = 0; b < k / QK_K; b++, x += bb) {
+            const float d = h2f(rd16(x)), min = h2f(rd16(x + 2));
+            const uint8_t * scales = x + 4;
+            const uint8_t * qh = x + 16;                       /* q5_K only */
+            const uint8_t * q = type == 12 ? x + 16 : x + 48;
+            int is = 0; uint8_t u1 = 1, u2 = 2;
+            for (int j = 0; j < QK_K; j += 64) {
+                int sc, m;
+                scale_min_k4(is + 0, scales, &sc, &m); const float d1 = d * sc, m1 = min * m;
+                scale_min_k4(is + 1, scales, &sc, &m); const float d2 = d * sc, m2 = min * m;
+                for (int l = 0; l < 32; l++) *y++ = d1 * ((q[l] & 0xF) + (type == 13 && (qh[l] & u1) ? 16 : 0)) - m1;
+                for (int l = 0; l < 32; l++) *y++ = d2 * ((q[l] >> 4) + (type == 13 && (qh[l] & u2) ? 16 : 0)) - m2;
+                q += 32; is += 2; u1 <<= 2; u2 <<= 2;
+            }
+        }
+    } else if (type == 14) {
+        for (int64_t b = 0; b < k / QK_K; b++, x += 210) {
+            const float d = h2f(rd16(x + 208));
+            const uint8_t * ql = x, * qh = x + 128; const int8_t * sc = (const int8_t *)(x + 192);
+            for (int n = 0; n < QK_K; n += 128) {
+                for (int l = 0; l < 32; l++) {
+                    const int is = l / 16;
+                    const int8_t q1 = (int8_t)((ql[l] & 0xF) | (((qh[l] >> 0) & 3) << 4)) - 32;
+                    const int8_t q2 = (int8_t)((ql[l + 32] & 0xF) | (((qh[l] >> 2) & 3) << 4)) - 32;
+                    const int8_t q3 = (int8_t)((ql[l] >> 4) | (((qh[l] >> 4) & 3) << 4)) - 32;
+                    const int8_t q4 = (int8_t)((ql[l + 32] >> 4) | (((qh[l] >> 6) & 3) << 4)) - 32;
+                    y[l] = d * sc[is] * q1; y[l + 32] = d * sc[is + 2] * q2;
+                    y[l + 64] = d * sc[is + 4] * q3; y[l + 96] = d * sc[is + 6] * q4;
+                }
+                y += 128; ql += 64; qh += 32; sc += 8;
+            }
+        }
+    }
+}
+
+/* ---- quantized dot products, in the reference's AVX2 lane order ------------------------------------------- */
+/* hsum_float_8, cpp/ggml/src/ggml-quants.c:47-53 */
+static float hsum8(const float * a) {
+    const float r0 = a[4] + a[0], r1 = a[5] + a[1], r2 = a[6] + a[2], r3 = a[7] + a[3];
+    const float s0 = r0 + r2, s1 = r1 + r3;
+    return s0 + s1;
+}
+/* the 8 scale bytes and 8 min bytes of a Q4_K/Q5_K super-block (utmp shuffle, ggml-quants.c:6925-6930) */
+static void k4_all(const uint8_t * scales, int * sc8, int * m8) {
+    for (int j = 0; j < 8; j++) scale_min_k4(j, scales, &sc8[j], &m8[j]);
+}
+
+/* ggml_vec_dot_q4_K_q8_K (AVX2 :6914-6977) and ggml_vec_dot_q5_K_q8_K (AVX2 :7487-7560):
+ * lane m of the 8-wide int32 accumulator collects bytes 4m..4m+3 of every 32-byte group. */
+static float vec_dot_q45_K(int n, const uint8_t * x, const uint8_t * y, int q5) {
+    const int nb = n / QK_K, bb = q5 ? 176 : 144;
+    float acc[8] = {0}, acc_m[4] = {0}, summs = 0.f;
+    for (int i = 0; i < nb; i++, x += bb, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        int16_t bsums[16]; memcpy(bsums, y + 260, 32);
+        const float d = yd * h2f(rd16(x)), dmin = -yd * h2f(rd16(x + 2));
+        int sc8[8], m8[8]; k4_all(x + 4, sc8, m8);
+        const uint8_t * qh = x + 16;
+        const uint8_t * q4 = q5 ? x + 48 : x + 16;
+        /* mins: prod lane l = m[2l]*(bsums pair 2l) + m[2l+1]*(bsums pair 2l+1) */
+        int prod[4];
+        for (int l = 0; l < 4; l++)
+            prod[l] = m8[2 * l] * (bsums[4 * l] + bsums[4 * l + 1]) + m8[2 * l + 1] * (bsums[4 * l + 2] + bsums[4 * l + 3]);
+        if (!q5) for (int l = 0; l < 4; l++) acc_m[l] = fmaf(dmin, (float) prod[l], acc_m[l]);
+        else     summs += dmin * (float)(prod[0] + prod[1] + prod[2] + prod[3]);
+        int sumi[8] = {0};
+        for (int j = 0; j < 4; j++) {
+            for (int m = 0; m < 8; m++) {
+                int lo = 0, hi = 0;
+                for (int t = 0; t < 4; t++) {
+                    const int l = 4 * m + t;
+                    int ql = q4[32 * j + l] & 0xF, qhh = q4[32 * j + l] >> 4;
+                    if (q5) { ql += ((qh[l] >> (2 * j)) & 1) << 4; qhh += ((qh[l] >> (2 * j + 1)) & 1) << 4; }
+                    lo += ql * q8[64 * j + l];
+                    hi += qhh * q8[64 * j + 32 + l];
+                }
+                sumi[m] += sc8[2 * j] * lo + sc8[2 * j + 1] * hi;
+            }
+        }
+        for (int m = 0; m < 8; m++) acc[m] = fmaf(d, (float) sumi[m], acc[m]);
+    }
+    if (!q5) {
+        const float a0 = acc_m[0] + acc_m[2], a1 = acc_m[1] + acc_m[3];
+        return hsum8(acc) + (a0 + a1);
+    }
+    return hsum8(acc) + summs;
+}
+/* ggml_vec_dot_q6_K_q8_K, AVX2 :8145-8220: lanes 0-3 use scale 2k, lanes 4-7 scale 2k+1 of each 32-group */
+static float vec_dot_q6_K(int n, const uint8_t * x, const uint8_t * y) {
+    const int nb = n / QK_K;
+    float acc[8] = {0};
+    for (int i = 0; i < nb; i++, x += 210, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        const float d = yd * h2f(rd16(x + 208));
+        const uint8_t * ql = x, * qh = x + 128; const int8_t * sc = (const int8_t *)(x + 192);
+        int sumi[8] = {0};
+        for (int j = 0; j < 2; j++) {
+            for (int g = 0; g < 4; g++) {
+                for (int m = 0; m < 8; m++) {
+                    int s = 0;
+                    for (int t = 0; t < 4; t++) {
+                        const int l = 4 * m + t;
+                        const uint8_t qlb = ql[64 * j + 32 * (g & 1) + l];
+                        const int lo = (g >> 1) ? (qlb >> 4) : (qlb & 0xF);
+                        const int q = (lo | (((qh[32 * j + l] >> (2 * g)) & 3) << 4)) - 32;
+                        s += q * q8[128 * j + 32 * g + l];
+                    }
+                    sumi[m] += sc[8 * j + 2 * g + (m >> 2)] * s;
+                }
+            }
+        }
+        for (int m = 0; m < 8; m++) acc[m] = fmaf(d, (float) sumi[m], acc[m]);
+    }
+    return hsum8(acc);
+}
+/* ggml_vec_dot_q8_0_q8_0, AVX2 :5361-5382 (and tinyBLAS_Q0_AVX, cpp/ggml/src/llamafile/sgemm.cpp, which the
+ * model path takes for Q8_0 x Q8_0: same 8-lane fma(d_w*d_x, sum4, acc) structure) */
+static float vec_dot_q8_0(int n, const uint8_t * x, const uint8_t * y) {
+    float acc[8] = {0};
+    for (int i = 0; i < n / 32; i++, x += 34, y += 34) {
+        const float d = h2f(rd16(x)) * h2f(rd16(y));
+        for (int m = 0; m < 8; m++) {
+            int s = 0;
+            for (int t = 0; t < 4; t++) s += (int8_t) x[2 + 4 * m + t] * (int8_t) y[2 + 4 * m + t];
+            acc[m] = fmaf(d, (float) s, acc[m]);
+        }
+    }
+    return hsum8(acc);
+}
+
+static int64_t row_bytes(int type, int64_t k) {
+    switch (type) { case 0: return k * 4; case 1: return k * 2; case 8: return k / 32 * 34; case 12: return k / 256 * 144;
+                    case 13: return k / 256 * 176; case 14: return k / 256 * 210; default: return 0; }
+}
+
+/* ggml_compute_forward_mul_mat for one activation row (cpp/ggml/src/ggml.c:12277-12490): quantize x to the
+ * weight type's vec_dot_type (Q8_K for K-quants, Q8_0 for Q8_0; type_traits cpp/ggml/src/ggml.c:769-855), then one
+ * vec_dot per weight row. y[n_rows]. */
+void port_mul_mat_vec(int type, const uint8_t * w, int64_t n_rows, int64_t k, const float * x, float * y) {
+    const int64_t rb = row_bytes(type, k);
+    uint8_t * xq = (uint8_t *) malloc((size_t)(type == 8 ? k / 32 * 34 : k / 256 * 292));
+    if (type == 8) port_quantize_row_q8_0(x, xq, k); else port_quantize_row_q8_K(x, xq, k);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n_rows; r++) {
+        const uint8_t * wr = w + r * rb;
+        y[r] = type == 8 ? vec_dot_q8_0((int) k, wr, xq) : type == 14 ? vec_dot_q6_K((int) k, wr, xq)
+                                                                       : vec_dot_q45_K((int) k, wr, xq, type == 13);
+    }
+    free(xq);
+}
+
+/* ---- float ops ------------------------------------------------------------------------------------------------ */
+/* ggml_compute_forward_rms_norm_f32 (cpp/ggml/src/ggml.c:11850-11896) then ggml_mul by the weight
+ * (llm_build_norm, cpp/src/llama.cpp:7928-7958) */
+void port_rms_norm(const float * x, const float * w, int64_t k, float eps, float * y) {
+    double sum = 0.0;
+    for (int64_t i = 0; i < k; i++) sum += (double)(x[i] * x[i]);
+    const float mean = (float)(sum / (double) k);
+    const float scale = 1.0f / sqrtf(mean + eps);
+    for (int64_t i = 0; i < k; i++) { const float v = x[i] * scale; y[i] = w ? v * w[i] : v; }
+}
+
+/* ggml_rope_cache_init + rope_yarn (ext_factor = 0 branch) + NORM-mode rotation
+ * (cpp/ggml/src/ggml.c:13994-14031, 14121-14135): theta starts at pos, multiplied by theta_scale per pair */
+void port_rope(float * x, int n_heads, int head_dim, int pos, float freq_base, float freq_scale, const float * ff) {
+    const float theta_scale = powf(freq_base, -2.0f / head_dim);
+    for (int h = 0; h < n_heads; h++) {
+        float theta = (float) pos;
+        float * p = x + (int64_t) h * head_dim;
+        for (int i0 = 0; i0 < head_dim; i0 += 2) {
+            const float f = ff ? ff[i0 / 2] : 1.0f;
+            const float th = freq_scale * (theta / f);
+            const float c = cosf(th), s = sinf(th);
+            const float x0 = p[i0], x1 = p[i0 + 1];
+            p[i0] = x0 * c - x1 * s;
+            p[i0 + 1] = x0 * s + x1 * c;
+            theta *= theta_scale;
+        }
+    }
+}
+
+static float silu(float x) { return x / (1.0f + expf(-x)); }   /* ggml_silu_f32, cpp/ggml/src/ggml.c:2393 */
+
+/* ---- the model ------------------------------------------------------------------------------------------------ */
+typedef struct { int32_t type; int32_t pad; const uint8_t * data; int64_t rows, k; } port_mat;
+typedef struct {
+    port_mat wq, wk, wv, wo, gate, up, down;
+    const float * attn_norm; const float * ffn_norm;
+} port_layer;
+typedef struct {
+    int32_t n_layer, n_embd, n_head, n_head_kv, head_dim, n_ff, n_vocab, n_ctx;
+    float rms_eps, rope_freq_base, rope_freq_scale, pad;
+    const float * rope_freq_factors;
+    port_mat tok_embd, output;
+    const float * output_norm;
+    const port_layer * layers;
+    uint16_t * k_cache;     /* [n_layer][n_ctx][kv_dim] f16 bits, K post-RoPE (llm_build_kv_store, llama.cpp:7849-7853) */
+    uint16_t * v_cache;     /* same layout (the reference's non-FA cache is transposed; layout is not arithmetic) */
+    float * tap_l_out;      /* optional [n_layer][n_embd]: l_out of the LAST token of the call */
+    float * tap_q;          /* optional [n_layer][n_head*head_dim]: Qcur (post-RoPE) of the last token */
+    float * tap_kqv;        /* optional [n_layer][n_head*head_dim]: kqv_merged_cont of the last token */
+} port_model;
+
+/* default (non-flash) attention for one query token at position pos (llm_build_kqv, cpp/src/llama.cpp:8248-8297):
+ * kq = K.q (f16 K widened to f32; q f32 at batch 1, rounded to f16 at batch > 1: cpp/ggml/src/ggml.c:12325-12371),
+ * soft_max_ext(kq*scale + mask) with a double row sum (cpp/ggml/src/ggml.c:13682-13778), kqv = V.p */
+static void attention(const port_model * M, int il, const float * q, int pos, int round_q, float * out) {
+    const int hd = M->head_dim, kvd = M->n_head_kv * hd, gqa = M->n_head / M->n_head_kv, n_kv = pos + 1;
+    const uint16_t * kc = M->k_cache + (int64_t) il * M->n_ctx * kvd;
+    const uint16_t * vc = M->v_cache + (int64_t) il * M->n_ctx * kvd;
+    const float scale = 1.0f / sqrtf((float) hd);
+#pragma omp parallel for schedule(static)
+    for (int h = 0; h < M->n_head; h++) {
+        const int g = h / gqa;
+        float * p = (float *) malloc(sizeof(float) * (size_t) n_kv);
+        float qh[512];
+        for (int d = 0; d < hd; d++) qh[d] = round_q ? h2f(f2h(q[h * hd + d])) : q[h * hd + d];
+        float max = -INFINITY;
+        for (int t = 0; t < n_kv; t++) {
+            const uint16_t * kr = kc + (int64_t) t * kvd + g * hd;
+            float s = 0.f;
+            for (int d = 0; d < hd; d++) s = fmaf(h2f(kr[d]), qh[d], s);
+            p[t] = s * scale;
+            if (p[t] > max) max = p[t];
+        }
+        double sum = 0.0;
+        for (int t = 0; t < n_kv; t++) { p[t] = expf(p[t] - max); sum += (double) p[t]; }
+        const float inv = (float)(1.0 / sum);
+        for (int t = 0; t < n_kv; t++) p[t] *= inv;
+        for (int d = 0; d < hd; d++) {
+            float o = 0.f;
+            for (int t = 0; t < n_kv; t++) o = fmaf(h2f(vc[(int64_t) t * kvd + g * hd + d]), p[t], o);
+            out[h * hd + d] = o;
+        }
+        free(p);
+    }
+}
+
+/* llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0)) + llama_get_logits for LLM_ARCH_LLAMA
+ * (llama_decode_internal cpp/src/llama.cpp:14537-14840; graph build_llama :8781-8925). Tokens are processed one
+ * after the other — per-token arithmetic of a batch is independent in the reference except for the f16 rounding
+ * of q when n > 1. logits[n_vocab] = last token's row. Returns 0, or 1 if positions exceed n_ctx. */
+int port_decode(const port_model * M, const int32_t * tokens, int n, int pos0, float * logits) {
+    const int E = M->n_embd, hd = M->head_dim, QD = M->n_head * hd, KVD = M->n_head_kv * hd, FF = M->n_ff;
+    if (pos0 < 0 || pos0 + n > M->n_ctx) return 1;
+    float * x = malloc(sizeof(float) * E), * nx = malloc(sizeof(float) * E), * q = malloc(sizeof(float) * QD);
+    float * kk = malloc(sizeof(float) * KVD), * vv = malloc(sizeof(float) * KVD), * att = malloc(sizeof(float) * QD);
+    float * tmp = malloc(sizeof(float) * E), * g = malloc(sizeof(float) * FF), * u = malloc(sizeof(float) * FF);
+    const int round_q = n > 1;
+    for (int t = 0; t < n; t++) {
+        const int pos = pos0 + t, last = t == n - 1;
+        /* inp_embd = get_rows(tok_embd, token): cpp/src/llama.cpp:7802-7828 */
+        port_dequantize_row(M->tok_embd.type, M->tok_embd.data + (int64_t) tokens[t] * row_bytes(M->tok_embd.type, E), x, E);
+        for (int il = 0; il < M->n_layer; il++) {
+            const port_layer * L = &M->layers[il];
+            port_rms_norm(x, L->attn_norm, E, M->rms_eps, nx);
+            port_mul_mat_vec(L->wq.type, L->wq.data, QD, E, nx, q);
+            port_mul_mat_vec(L->wk.type, L->wk.data, KVD, E, nx, kk);
+            port_mul_mat_vec(L->wv.type, L->wv.data, KVD, E, nx, vv);
+            port_rope(q, M->n_head, hd, pos, M->rope_freq_base, M->rope_freq_scale, M->rope_freq_factors);
+            port_rope(kk, M->n_head_kv, hd, pos, M->rope_freq_base, M->rope_freq_scale, M->rope_freq_factors);
+            uint16_t * kc = M->k_cache + ((int64_t) il * M->n_ctx + pos) * KVD;
+            uint16_t * vc = M->v_cache + ((int64_t) il * M->n_ctx + pos) * KVD;
+            for (int i = 0; i < KVD; i++) { kc[i] = f2h(kk[i]); vc[i] = f2h(vv[i]); }
+            attention(M, il, q, pos, round_q, att);
+            if (last && M->tap_q)   memcpy(M->tap_q + (int64_t) il * QD, q, sizeof(float) * QD);
+            if (last && M->tap_kqv) memcpy(M->tap_kqv + (int64_t) il * QD, att, sizeof(float) * QD);
+            port_mul_mat_vec(L->wo.type, L->wo.data, E, QD, att, tmp);
+            for (int i = 0; i < E; i++) x[i] = tmp[i] + x[i];                 /* ffn_inp = cur + inpSA, :8865 */
+            port_rms_norm(x, L->ffn_norm, E, M->rms_eps, nx);
+            port_mul_mat_vec(L->up.type, L->up.data, FF, E, nx, u);          /* llm_build_ffn :7960-8085 */
+            port_mul_mat_vec(L->gate.type, L->gate.data, FF, E, nx, g);
+            for (int i = 0; i < FF; i++) g[i] = silu(g[i]) * u[i];
+            port_mul_mat_vec(L->down.type, L->down.data, E, FF, g, tmp);
+            for (int i = 0; i < E; i++) x[i] = tmp[i] + x[i];                 /* l_out = cur + ffn_inp, :8901 */
+            if (last && M->tap_l_out) memcpy(M->tap_l_out + (int64_t) il * E, x, sizeof(float) * E);
+        }
+        if (last && logits) {
+            port_rms_norm(x, M->output_norm, E, M->rms_eps, nx);
+            port_mul_mat_vec(M->output.type, M->output.data, M->n_vocab, E, nx, logits);
+        }
+    }
+    free(x); free(nx); free(q); free(kk); free(vv); free(att); free(tmp); free(g); free(u);
+    return 0;
+}

@@ -1,0 +1,210 @@
+"""oracle/port.py — TEST INFRASTRUCTURE, NOT PRODUCT.
+
+ctypes driver for liboracle_port.so (oracle/oracle_port.c, the plain-C restatement of the reference CPU path).
+Mirrors oracle/ref.py's interface so tests can swap one for the other. Pinned against oracle/_ref and the
+golden vectors in tests/golden (see tests/test_oracle_pinned.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle_port.so")
+_lib = None
+
+
+class PortMat(C.Structure):
+    _fields_ = [("type", C.c_int32), ("pad", C.c_int32), ("data", C.c_void_p), ("rows", C.c_int64), ("k", C.c_int64)]
+
+
+class PortLayer(C.Structure):
+    _fields_ = [(n, PortMat) for n in ("wq", "wk", "wv", "wo", "gate", "up", "down")] + \
+               [("attn_norm", C.c_void_p), ("ffn_norm", C.c_void_p)]
+
+
+class PortModel(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_layer", "n_embd", "n_head", "n_head_kv", "head_dim", "n_ff", "n_vocab", "n_ctx")] + \
+               [(n, C.c_float) for n in ("rms_eps", "rope_freq_base", "rope_freq_scale", "pad")] + \
+               [("rope_freq_factors", C.c_void_p), ("tok_embd", PortMat), ("output", PortMat), ("output_norm", C.c_void_p),
+                ("layers", C.POINTER(PortLayer)), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+                ("tap_l_out", C.c_void_p), ("tap_q", C.c_void_p), ("tap_kqv", C.c_void_p)]
+
+
+def build() -> None:
+    subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "oracle_port.c")
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+            build()
+        L = C.CDLL(_SO)
+        L.port_quantize_row_q8_K.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.port_quantize_row_q8_0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.port_dequantize_row.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.port_mul_mat_vec.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        L.port_rms_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
+        L.port_rope.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.port_decode.argtypes = [C.POINTER(PortModel), C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.port_decode.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def quantize_row_q8_K(x) -> np.ndarray:
+    x = _f32(x)
+    out = np.empty(x.size // 256 * 292, dtype=np.uint8)
+    lib().port_quantize_row_q8_K(x.ctypes.data, out.ctypes.data, x.size)
+    return out
+
+
+def quantize_row_q8_0(x) -> np.ndarray:
+    x = _f32(x)
+    out = np.empty(x.size // 32 * 34, dtype=np.uint8)
+    lib().port_quantize_row_q8_0(x.ctypes.data, out.ctypes.data, x.size)
+    return out
+
+
+def dequantize_row(t: int, raw, k: int) -> np.ndarray:
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    out = np.empty(k, dtype=np.float32)
+    lib().port_dequantize_row(t, raw.ctypes.data, out.ctypes.data, k)
+    return out
+
+
+def mul_mat_vec(t: int, w_raw, n_rows: int, k: int, x) -> np.ndarray:
+    w_raw = np.ascontiguousarray(w_raw, dtype=np.uint8)
+    x = _f32(x)
+    y = np.empty(n_rows, dtype=np.float32)
+    lib().port_mul_mat_vec(t, w_raw.ctypes.data, n_rows, k, x.ctypes.data, y.ctypes.data)
+    return y
+
+
+def rms_norm(x, w, eps: float) -> np.ndarray:
+    x = _f32(x)
+    y = np.empty_like(x)
+    wv = _f32(w) if w is not None else None
+    lib().port_rms_norm(x.ctypes.data, wv.ctypes.data if wv is not None else None, x.size, eps, y.ctypes.data)
+    return y
+
+
+def rope(x, n_heads: int, head_dim: int, pos: int, freq_base: float, freq_scale: float = 1.0, freq_factors=None) -> np.ndarray:
+    y = _f32(x).copy()
+    ff = _f32(freq_factors) if freq_factors is not None else None
+    lib().port_rope(y.ctypes.data, n_heads, head_dim, pos, freq_base, freq_scale, ff.ctypes.data if ff is not None else None)
+    return y
+
+
+def attention_ref_numpy(q, k_cache_f16, v_cache_f16, n_kv, n_head, n_head_kv, head_dim, scale, round_q=False) -> np.ndarray:
+    """numpy statement of the default attention route at batch 1 (cpp/src/llama.cpp:8248-8297) in float64-free fp32."""
+    q = _f32(q).reshape(n_head, head_dim)
+    if round_q:
+        q = q.astype(np.float16).astype(np.float32)
+    k = np.asarray(k_cache_f16, dtype=np.float16)[:n_kv].astype(np.float32).reshape(n_kv, n_head_kv, head_dim)
+    v = np.asarray(v_cache_f16, dtype=np.float16)[:n_kv].astype(np.float32).reshape(n_kv, n_head_kv, head_dim)
+    gqa = n_head // n_head_kv
+    out = np.empty((n_head, head_dim), dtype=np.float32)
+    for h in range(n_head):
+        g = h // gqa
+        s = (k[:, g, :] @ q[h]).astype(np.float32) * np.float32(scale)
+        p = np.exp(s - s.max()).astype(np.float32)
+        p = (p * np.float32(1.0 / np.sum(p, dtype=np.float64))).astype(np.float32)
+        out[h] = p @ v[:, g, :]
+    return out.reshape(-1)
+
+
+class PortModelRunner:
+    """Same interface as oracle.ref.RefModel (decode / greedy / kv_clear), running oracle_port.c."""
+
+    def __init__(self, path: str, n_ctx: int = 512):
+        from booster_b200 import gguf_io as G   # container parsing only (no compute)
+        self.L = lib()
+        self.f = G.read_gguf(path)
+        kv = self.f.kv
+        self._keep = []
+        M = PortModel()
+        M.n_layer = int(kv["llama.block_count"]); M.n_embd = int(kv["llama.embedding_length"])
+        M.n_head = int(kv["llama.attention.head_count"]); M.n_head_kv = int(kv.get("llama.attention.head_count_kv", M.n_head))
+        M.head_dim = M.n_embd // M.n_head; M.n_ff = int(kv["llama.feed_forward_length"])
+        M.n_ctx = (n_ctx + 31) // 32 * 32
+        M.rms_eps = float(kv.get("llama.attention.layer_norm_rms_epsilon", 1e-5))
+        M.rope_freq_base = float(kv.get("llama.rope.freq_base", 10000.0))
+        sf = float(kv.get("llama.rope.scaling.factor", 0.0))
+        M.rope_freq_scale = 1.0 if sf == 0.0 or kv.get("llama.rope.scaling.type", "linear") == "none" else 1.0 / sf
+
+        def mat(name) -> PortMat:
+            t = self.f.tensors[name]
+            arr = np.ascontiguousarray(t.data)
+            self._keep.append(arr)
+            return PortMat(t.type, 0, arr.ctypes.data, t.ne[1], t.ne[0])
+
+        def vec(name):
+            arr = np.ascontiguousarray(self.f.tensors[name].data).view(np.float32)
+            self._keep.append(arr)
+            return arr.ctypes.data
+
+        M.tok_embd = mat("token_embd.weight")
+        M.n_vocab = int(self.f.tensors["token_embd.weight"].ne[1])
+        M.output = mat("output.weight" if "output.weight" in self.f.tensors else "token_embd.weight")
+        M.output_norm = vec("output_norm.weight")
+        if "rope_freqs.weight" in self.f.tensors:
+            M.rope_freq_factors = vec("rope_freqs.weight")
+        layers = (PortLayer * M.n_layer)()
+        for i in range(M.n_layer):
+            p = f"blk.{i}."
+            for fld, nm in (("wq", "attn_q"), ("wk", "attn_k"), ("wv", "attn_v"), ("wo", "attn_output"),
+                            ("gate", "ffn_gate"), ("up", "ffn_up"), ("down", "ffn_down")):
+                setattr(layers[i], fld, mat(p + nm + ".weight"))
+            layers[i].attn_norm = vec(p + "attn_norm.weight")
+            layers[i].ffn_norm = vec(p + "ffn_norm.weight")
+        self._layers = layers
+        M.layers = C.cast(layers, C.POINTER(PortLayer))
+        kvd = M.n_head_kv * M.head_dim
+        self.kc = np.zeros((M.n_layer, M.n_ctx, kvd), dtype=np.uint16)
+        self.vc = np.zeros_like(self.kc)
+        M.k_cache, M.v_cache = self.kc.ctypes.data, self.vc.ctypes.data
+        self.tap_l_out = np.zeros((M.n_layer, M.n_embd), dtype=np.float32)
+        self.tap_q = np.zeros((M.n_layer, M.n_head * M.head_dim), dtype=np.float32)
+        self.tap_kqv = np.zeros_like(self.tap_q)
+        M.tap_l_out, M.tap_q, M.tap_kqv = self.tap_l_out.ctypes.data, self.tap_q.ctypes.data, self.tap_kqv.ctypes.data
+        self.M = M
+        self.n_vocab, self.n_ctx = M.n_vocab, M.n_ctx
+
+    def close(self):
+        pass
+
+    def kv_clear(self):
+        self.kc[:] = 0
+        self.vc[:] = 0
+
+    def decode(self, tokens: Sequence[int], pos0: int) -> np.ndarray:
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty(self.n_vocab, dtype=np.float32)
+        rc = self.L.port_decode(C.byref(self.M), toks.ctypes.data, len(toks), pos0, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"port_decode rc={rc}")
+        return out
+
+    def greedy(self, prompt: Sequence[int], n_gen: int) -> (List[int], List[np.ndarray]):
+        self.kv_clear()
+        logits = self.decode(prompt, 0)
+        pos = len(prompt)
+        ids, all_logits = [], []
+        for _ in range(n_gen):
+            all_logits.append(logits)
+            t = int(np.argmax(logits))
+            ids.append(t)
+            logits = self.decode([t], pos)
+            pos += 1
+        return ids, all_logits

@@ -92,3 +92,50 @@ if __name__ == "__main__":
             model_parity(cfg, ft)
     if "timing" in what:
         timing_8b()
+
+
+def taps(cfg_name, ftype, tokens, n_ctx=64):
+    """layer-wise localisation: reference cb_eval taps vs engine taps for one llama_decode call."""
+    cfg = G.CONFIGS[cfg_name]
+    path = os.path.join(TMP, f"{cfg_name}_{ftype}.gguf")
+    if not os.path.exists(path):
+        G.synth_llama(path, cfg, ftype, seed=7, source="blocks")
+    names = []
+    for il in range(cfg.n_layer):
+        names += [f"Qcur-{il}", f"kqv_merged_cont-{il}", f"ffn_inp-{il}", f"ffn_gate_par-{il}", f"l_out-{il}", f"attn_norm-{il}", f"Vcur-{il}", f"kq_soft_max_ext-{il}"]
+    names += ["result_output", "result_norm"]
+    r = ref.RefModel(path, n_ctx=n_ctx)
+    r.set_taps(names)
+    lr = r.decode(tokens, 0)
+    m = engine.Model(path); c = engine.Context(m, n_ctx)
+    c.set_taps(True)
+    lg = c.decode(tokens, 0)
+    print(f"--- taps {cfg_name} {ftype} n_tokens={len(tokens)} logits rel={rel(lg, lr):.2e}")
+    T = len(tokens)
+    for il in range(cfg.n_layer):
+        for nm in ("Qcur", "kqv_merged_cont", "ffn_inp", "ffn_gate_par", "l_out"):
+            a = c.get_tap(nm, il); b = r.get_tap(f"{nm}-{il}")
+            if a is None or b is None:
+                print(f"   {nm}-{il}: missing gpu={a is None} ref={b is None}"); continue
+            # the reference tensors hold all T tokens ([.., T]) except after the last layer's get_rows; ours the last token
+            bl = b.reshape(T, -1)[-1] if b.size == a.size * T else b
+            if nm == "Qcur" and b.size == a.size * T:
+                bl = b.reshape(T, -1)[-1]
+            print(f"   {nm}-{il}: rel={rel(a, bl):.2e}  (ref size {b.size}, gpu size {a.size})")
+    c.close(); m.close(); r.close()
+
+
+def q80_debug():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(256).astype(np.float32)
+    a, b = engine.op_quantize_q8_0(x).reshape(-1, 34), ref.quantize_row_q8_0(x).reshape(-1, 34)
+    print("q80 diff per column:", (a != b).sum(0).tolist())
+    print("gpu", a[0, :8].tolist(), "ref", b[0, :8].tolist())
+
+
+if __name__ == "__main__" and "taps" in sys.argv[1:]:
+    q80_debug()
+    taps("llama3-8b-2l", "Q4_K_M", [5])
+    taps("tiny-gqa4", "Q5_K_M", [5, 9, 200, 17, 3, 99, 42, 7, 11, 300, 1, 2])
+    taps("tiny-gqa4", "Q8_0", [5])
+    taps("tiny", "Q4_K_M", [5, 9, 200, 17, 3, 99, 42, 7, 11, 300, 1, 2])

@@ -1,0 +1,94 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference (oracle/_ref, built from
+/root/reference by oracle/Makefile). Run in the build container (needs oracle/_ref); the outputs are committed
+so that the GPU box — where /root/reference does not exist — can check both the port oracle and the CUDA path
+against vectors the reference itself produced.
+
+    python tests/golden/make_golden.py
+
+Outputs:
+  tiny_<ftype>.gguf     tiny LLaMA-shaped models, F32 ~ N(0, 0.02^2) weights quantized by the reference's own
+                        llama_model_quantize (cpp/src/llama.cpp:15435-) to Q4_K_M / Q5_K_M / Q8_0
+  tiny_<ftype>.npz      reference logits: prefill of a 12-token prompt in one llama_decode (batch arithmetic),
+                        8 greedy steps (batch-1 arithmetic), plus l_out taps of the prefill call
+  ops.npz               operator vectors: quantize_row_q8_K / q8_0 (incl. ties at +-max and all-zero blocks),
+                        reference-quantized weight rows of each block type with their dequantization and
+                        ggml_vec_dot_* results
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from booster_b200 import gguf_io as G  # noqa: E402
+from oracle import ref  # noqa: E402
+
+PROMPT = [5, 9, 200, 17, 3, 99, 42, 7, 11, 300, 1, 2]
+N_GEN = 8
+MODELS = [("tiny", "Q4_K_M", 15), ("tiny", "Q5_K_M", 17), ("tiny", "Q8_0", 7), ("tiny-gqa4", "Q4_K_M", 15)]
+
+
+def make_models():
+    for cfg_name, ftype, code in MODELS:
+        cfg = G.CONFIGS[cfg_name]
+        out = os.path.join(HERE, f"{cfg_name}_{ftype}.gguf")
+        with tempfile.TemporaryDirectory() as td:
+            f32 = os.path.join(td, "f32.gguf")
+            G.synth_llama(f32, cfg, seed=1234, source="f32")
+            ref.quantize_model(f32, out, code, nthread=4)
+        r = ref.RefModel(out, n_ctx=64, n_threads=4)
+        names = [f"l_out-{i}" for i in range(cfg.n_layer)] + [f"Qcur-{i}" for i in range(cfg.n_layer)] + \
+                [f"kqv_merged_cont-{i}" for i in range(cfg.n_layer)]
+        r.set_taps(names)
+        r.kv_clear()
+        logits = [r.decode(PROMPT, 0)]
+        taps = {n.replace("-", "_"): r.get_tap(n) for n in names}
+        r.set_taps([])
+        ids = []
+        pos = len(PROMPT)
+        for _ in range(N_GEN):
+            t = int(np.argmax(logits[-1]))
+            ids.append(t)
+            logits.append(r.decode([t], pos))
+            pos += 1
+        # token-by-token (batch-1 arithmetic from position 0)
+        r.kv_clear()
+        single = [r.decode([t], i) for i, t in enumerate(PROMPT[:6])]
+        np.savez_compressed(os.path.join(HERE, f"{cfg_name}_{ftype}.npz"), prompt=np.array(PROMPT, dtype=np.int32),
+                            ids=np.array(ids, dtype=np.int32), logits=np.stack(logits), single=np.stack(single), **taps)
+        r.close()
+        print(f"{cfg_name} {ftype}: {os.path.getsize(out) / 1e6:.2f} MB, greedy ids {ids}")
+
+
+def make_ops():
+    rng = np.random.default_rng(99)
+    out = {}
+    # activation vectors: gaussian, ties at +max/-max (first occurrence must win), an all-zero block, tiny values
+    x = rng.standard_normal(256 * 6).astype(np.float32)
+    x[256:512] = 0.0
+    x[512 + 7] = 3.5; x[512 + 100] = -3.5; x[512:768] = np.clip(x[512:768], -3.5, 3.5)
+    x[768 + 200] = -4.25; x[768 + 13] = 4.25; x[768:1024] = np.clip(x[768:1024], -4.25, 4.25)
+    x[1024:1280] *= 1e-6
+    x[1280:1536] = np.round(x[1280:1536] * 4) / 4   # many exact .5 products
+    out["act_x"] = x
+    out["act_q8_K"] = ref.quantize_row_q8_K(x)
+    out["act_q8_0"] = ref.quantize_row_q8_0(x)
+    for name, t in ref.GGML_TYPE.items():
+        n, k = 16, 1536
+        w = ref.quantize_weights(0.02 * rng.standard_normal((n, k)).astype(np.float32), t)
+        out[f"w_{name}"] = w
+        out[f"deq_{name}"] = np.stack([ref.dequantize_row(t, w[r * G.row_bytes(t, k):(r + 1) * G.row_bytes(t, k)], k) for r in range(n)])
+        out[f"dot_{name}"] = ref.mul_mat_vec(t, w, n, k, x)
+    np.savez_compressed(os.path.join(HERE, "ops.npz"), **out)
+    print("ops.npz written")
+
+
+if __name__ == "__main__":
+    if not ref.available():
+        sys.exit("oracle/_ref is not built: run `make -C oracle ref` in the build container")
+    print("reference variant:", ref.variant())
+    make_ops()
+    make_models()

@@ -1,0 +1,113 @@
+"""Operator-level parity of the CUDA kernels (through the C-ABI, same kernels the engine launches) against
+the golden vectors the reference produced and against the port oracle on seeded inputs.
+Integer/byte work is bit-exact; fp32 results agree to summation-order round-off."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import q8k_equal, rel_err
+from booster_b200 import engine, gguf_io as G
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+TYPES = {"Q8_0": 8, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}
+
+
+@pytest.fixture(scope="module")
+def ops(golden_dir):
+    return np.load(os.path.join(golden_dir, "ops.npz"))
+
+
+def test_quantize_q8_K_bit_exact_golden(ops):
+    assert q8k_equal(engine.op_quantize_q8_K(ops["act_x"]), ops["act_q8_K"])
+
+
+def test_quantize_q8_0_bit_exact_golden(ops):
+    assert np.array_equal(engine.op_quantize_q8_0(ops["act_x"]), ops["act_q8_0"])
+
+
+@pytest.mark.parametrize("k", [256, 4096, 14336, 28672])
+def test_quantize_bit_exact_vs_port(k):
+    rng = np.random.default_rng(k)
+    x = (rng.standard_normal(k) * rng.choice([1e-3, 1.0, 50.0])).astype(np.float32)
+    x[::97] = 0.0
+    assert q8k_equal(engine.op_quantize_q8_K(x), port.quantize_row_q8_K(x))
+    assert np.array_equal(engine.op_quantize_q8_0(x), port.quantize_row_q8_0(x))
+
+
+@pytest.mark.parametrize("name", list(TYPES))
+def test_dequantize_bit_exact_golden(ops, name):
+    t, k = TYPES[name], 1536
+    rb = G.row_bytes(t, k)
+    for r in (0, 7, 15):
+        assert np.array_equal(engine.op_dequantize_row(t, ops[f"w_{name}"][r * rb:(r + 1) * rb], k), ops[f"deq_{name}"][r])
+
+
+@pytest.mark.parametrize("name", list(TYPES))
+def test_mul_mat_vec_golden(ops, name):
+    # the reference's own ggml_vec_dot_* results: integer sums are exact, only the fp32 order across blocks differs
+    y = engine.op_mul_mat_vec(TYPES[name], ops[f"w_{name}"], 16, 1536, ops["act_x"])
+    assert rel_err(y, ops[f"dot_{name}"]) < 2e-6
+
+
+@pytest.mark.parametrize("name", list(TYPES))
+@pytest.mark.parametrize("shape", [(64, 256), (1024, 4096), (4096, 4096), (256, 14336), (128, 8192), (64, 28672)])
+def test_mul_mat_vec_vs_port(name, shape):
+    n, k = shape
+    t = TYPES[name]
+    rng = np.random.default_rng(n * 31 + k)
+    w = G.random_blocks(rng, t, n, k)
+    x = rng.standard_normal(k).astype(np.float32)
+    y, yr = engine.op_mul_mat_vec(t, w, n, k, x), port.mul_mat_vec(t, w, n, k, x)
+    assert rel_err(y, yr) < 2e-6
+    assert np.abs(y - yr).max() <= 1e-5 * max(1.0, np.abs(yr).max())
+
+
+def test_mul_mat_vec_edge_activations():
+    # all-zero activation blocks, ties at +-max: the integer path must still be exact
+    rng = np.random.default_rng(5)
+    k, n = 1024, 32
+    x = rng.standard_normal(k).astype(np.float32)
+    x[:256] = 0.0
+    x[300] = 9.0; x[400] = -9.0
+    for t in TYPES.values():
+        w = G.random_blocks(rng, t, n, k)
+        assert rel_err(engine.op_mul_mat_vec(t, w, n, k, x), port.mul_mat_vec(t, w, n, k, x)) < 2e-6
+
+
+@pytest.mark.parametrize("k", [256, 4096, 8192])
+def test_rms_norm(k):
+    rng = np.random.default_rng(k)
+    x = rng.standard_normal(k).astype(np.float32) * 3
+    w = (1 + 0.1 * rng.standard_normal(k)).astype(np.float32)
+    y, yr = engine.op_rms_norm(x, w, 1e-5), port.rms_norm(x, w, 1e-5)
+    # double accumulation on both sides: identical unless the mean lands on a float rounding boundary
+    assert np.array_equal(y, yr) or rel_err(y, yr) < 1e-7
+    assert rel_err(engine.op_rms_norm(x, None, 1e-6), port.rms_norm(x, None, 1e-6)) < 1e-7
+
+
+@pytest.mark.parametrize("pos", [0, 1, 17, 2047, 8191])
+@pytest.mark.parametrize("base", [10000.0, 500000.0])
+def test_rope(pos, base):
+    rng = np.random.default_rng(pos)
+    x = rng.standard_normal(8 * 128).astype(np.float32)
+    y, yr = engine.op_rope(x, 8, 128, pos, base), port.rope(x, 8, 128, pos, base)
+    # the table is built with the host libm exactly like ggml_rope_cache_init; rotation is un-fused mul/sub
+    assert np.array_equal(y, yr)
+    ff = (1 + rng.random(64)).astype(np.float32)
+    assert np.array_equal(engine.op_rope(x, 8, 128, pos, base, 0.5, ff), port.rope(x, 8, 128, pos, base, 0.5, ff))
+
+
+@pytest.mark.parametrize("cfg", [(4, 1, 1), (4, 1, 33), (32, 8, 257), (32, 8, 2048), (64, 8, 700), (8, 8, 64), (2, 1, 5)])
+def test_attention(cfg):
+    n_head, n_head_kv, n_kv = cfg
+    hd = 128
+    rng = np.random.default_rng(n_kv)
+    q = rng.standard_normal(n_head * hd).astype(np.float32)
+    k = rng.standard_normal((n_kv, n_head_kv * hd)).astype(np.float16)
+    v = rng.standard_normal((n_kv, n_head_kv * hd)).astype(np.float16)
+    scale = 1.0 / np.sqrt(hd)
+    y = engine.op_attention(q, k, v, n_kv, n_head, n_head_kv, hd, scale)
+    yr = port.attention_ref_numpy(q, k, v, n_kv, n_head, n_head_kv, hd, scale)
+    assert rel_err(y, yr) < 5e-6
