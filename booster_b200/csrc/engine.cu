@@ -398,8 +398,6 @@ struct TapStore { std::map<std::string, std::vector<float>> v; };
 struct b200_ctx {
     b200_model * m = nullptr;
     int n_ctx = 0;
-    int n_splits = 1;
-    int max_chunk = 0;
     cudaStream_t st = nullptr;
     // activations
     float * x = nullptr;        // residual stream [n_embd]
@@ -408,6 +406,8 @@ struct b200_ctx {
     float * ffh = nullptr;      // silu(gate)*up [n_ff]
     float * logits = nullptr;   // [n_vocab]
     float * part_o = nullptr, * part_ml = nullptr;
+    unsigned int * tickets = nullptr;
+    unsigned long long * amax_key = nullptr;
     std::vector<__half *> kc, vc;   // per local layer
     float2 * rope = nullptr;
     DecodeState * d_state = nullptr;
@@ -460,19 +460,17 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a) {
 
 static void launch_attention(b200_ctx * c, const AttnArgs & a) {
     ProfScope ps(c);
+    if (a.head_dim != 128) throw std::runtime_error("attention kernel is specialised for head_dim 128");
     const int gqa = a.n_head / a.n_head_kv;
-    const int chunk_cap = a.n_kv_override > 0 ? (a.n_kv_override + a.n_splits - 1) / a.n_splits : c->max_chunk;
-    const size_t smem = (size_t) gqa * a.head_dim * 4 + (size_t) gqa * chunk_cap * 4;
-    const dim3 grid((unsigned) a.n_head_kv, (unsigned) a.n_splits);
+    const dim3 grid((unsigned) a.n_head_kv, (unsigned) ATT_SPLITS);
     switch (gqa) {
-        case 1: k_attn_partial<1><<<grid, ATT_THREADS, smem, c->st>>>(a); break;
-        case 2: k_attn_partial<2><<<grid, ATT_THREADS, smem, c->st>>>(a); break;
-        case 4: k_attn_partial<4><<<grid, ATT_THREADS, smem, c->st>>>(a); break;
-        case 8: k_attn_partial<8><<<grid, ATT_THREADS, smem, c->st>>>(a); break;
+        case 1: k_attn<1><<<grid, ATT_THREADS, 0, c->st>>>(a); break;
+        case 2: k_attn<2><<<grid, ATT_THREADS, 0, c->st>>>(a); break;
+        case 4: k_attn<4><<<grid, ATT_THREADS, 0, c->st>>>(a); break;
+        case 8: k_attn<8><<<grid, ATT_THREADS, 0, c->st>>>(a); break;
         default: throw std::runtime_error("GQA ratio must be 1, 2, 4 or 8");
     }
-    k_attn_combine<<<a.n_head, 128, 0, c->st>>>(a);
-    c->launches += 2;
+    c->launches += 1;
 }
 
 ProfScope::ProfScope(b200_ctx * c_) : c(c_) {
@@ -525,8 +523,8 @@ static void enqueue_forward(b200_ctx * c) {
             g_kind = KIND_ATTN;
             AttnArgs a{};
             a.q = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
-            a.part_o = c->part_o; a.part_ml = c->part_ml; a.out = c->att;
-            a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD; a.n_splits = c->n_splits;
+            a.part_o = c->part_o; a.part_ml = c->part_ml; a.tickets = c->tickets; a.out = c->att;
+            a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD;
             a.scale = 1.0f / sqrtf((float) HD);
             a.st = c->d_state; a.n_kv_override = 0;
             launch_attention(c, a);
@@ -571,6 +569,12 @@ static void enqueue_forward(b200_ctx * c) {
     }
 }
 
+static void enqueue_argmax(b200_ctx * c, int advance) {
+    k_argmax_partial<<<c->sm_count, 256, 0, c->st>>>(c->logits, c->m->n_vocab, c->amax_key);
+    k_argmax_finish<<<1, 32, 0, c->st>>>(c->amax_key, c->d_state, c->d_out_tokens, advance);
+    c->launches += 2;
+}
+
 static cudaGraphExec_t capture(b200_ctx * c, const std::function<void()> & body) {
     cudaGraph_t g;
     const int64_t l0 = c->launches;
@@ -585,7 +589,7 @@ static cudaGraphExec_t capture(b200_ctx * c, const std::function<void()> & body)
 }
 static int64_t forward_launch_count(const b200_ctx * c) {
     const b200_model & m = *c->m;
-    return (m.has_embd() ? 1 : 0) + (int64_t) m.layers.size() * 6 + (m.has_head() ? 1 : 0);
+    return (m.has_embd() ? 1 : 0) + (int64_t) m.layers.size() * 5 + (m.has_head() ? 1 : 0);
 }
 
 extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
@@ -602,18 +606,17 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         c->sm_count = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
         const int E = m->n_embd, HD = m->head_dim, KVD = m->n_head_kv * HD, QD = m->n_head * HD;
-        // split count: about 2 CTAs per SM over (kv heads x splits), at least 32 positions per split at full context
-        int ns = std::max(1, (2 * c->sm_count) / m->n_head_kv);
-        ns = std::min(ns, std::max(1, c->n_ctx / 32));
-        c->n_splits = ns;
-        c->max_chunk = (c->n_ctx + ns - 1) / ns;
         CU(cudaMalloc(&c->x, (size_t) E * 4));
         CU(cudaMalloc(&c->q, (size_t) QD * 4));
         CU(cudaMalloc(&c->att, (size_t) QD * 4));
         CU(cudaMalloc(&c->ffh, (size_t) m->n_ff * 4));
         CU(cudaMalloc(&c->logits, (size_t) m->n_vocab * 4));
-        CU(cudaMalloc(&c->part_o, (size_t) m->n_head * ns * HD * 4));
-        CU(cudaMalloc(&c->part_ml, (size_t) m->n_head * ns * 2 * 4));
+        CU(cudaMalloc(&c->part_o, (size_t) m->n_head * ATT_SPLITS * HD * 4));
+        CU(cudaMalloc(&c->part_ml, (size_t) m->n_head * ATT_SPLITS * 2 * 4));
+        CU(cudaMalloc(&c->amax_key, 8));
+        CU(cudaMemsetAsync(c->amax_key, 0, 8, c->st));
+        CU(cudaMalloc(&c->tickets, (size_t) m->n_head_kv * 4));
+        CU(cudaMemsetAsync(c->tickets, 0, (size_t) m->n_head_kv * 4, c->st));
         for (size_t i = 0; i < m->layers.size(); i++) {
             __half * k = nullptr, * v = nullptr;
             CU(cudaMalloc(&k, (size_t) c->n_ctx * KVD * 2));
@@ -653,7 +656,7 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     for (auto p : c->kc) cudaFree(p);
     for (auto p : c->vc) cudaFree(p);
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->logits);
-    cudaFree(c->part_o); cudaFree(c->part_ml); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
+    cudaFree(c->part_o); cudaFree(c->part_ml); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits);
     cudaStreamDestroy(c->st);
     delete c;
@@ -742,14 +745,14 @@ extern "C" int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0,
             CU(cudaStreamSynchronize(c->st));
             c->g_greedy = capture(c, [&]() {
                 enqueue_forward(c);
-                k_argmax_advance<<<1, 1024, 0, c->st>>>(c->logits, m.n_vocab, c->d_state, c->d_out_tokens);
+                enqueue_argmax(c, 1);
             });
         }
         if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
         CU(cudaEventRecord(c->ev_t0, c->st));
         for (int s = 0; s < n_steps; s++) CU(cudaGraphLaunch(c->g_greedy, c->st));
         CU(cudaEventRecord(c->ev_t1, c->st));
-        c->launches += (forward_launch_count(c) + 1) * (int64_t) n_steps;
+        c->launches += (forward_launch_count(c) + 2) * (int64_t) n_steps;
         if (out_tokens) CU(cudaMemcpyAsync(out_tokens, c->d_out_tokens, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
         CU(cudaEventElapsedTime(&c->last_device_ms, c->ev_t0, c->ev_t1));
@@ -817,7 +820,7 @@ static void enqueue_stage_step(b200_ctx * c, bool greedy) {
     if (!last) NC(g_nccl.Send(c->x, (size_t) m.n_embd, NCCL_FLOAT32, c->rank + 1, c->comm, c->st));
     if (greedy) {
         if (last) {
-            k_argmax_advance<<<1, 1024, 0, c->st>>>(c->logits, m.n_vocab, c->d_state, c->d_out_tokens);
+            enqueue_argmax(c, 1);
             if (c->world > 1) NC(g_nccl.Send(&c->d_state->token, 1, NCCL_INT32, 0, c->comm, c->st));
         } else {
             k_advance<<<1, 32, 0, c->st>>>(c->d_state);
@@ -916,8 +919,7 @@ extern "C" int b200_stage_argmax(b200_ctx * c, int32_t * token_out) {
         require_gpu();
         if (!c || !c->m->has_head()) throw std::runtime_error("not the last stage");
         CU(cudaSetDevice(c->m->device));
-        k_argmax_only<<<1, 1024, 0, c->st>>>(c->logits, c->m->n_vocab, c->d_out_tokens);
-        c->launches++;
+        enqueue_argmax(c, 0);
         CU(cudaMemcpyAsync(&c->h_state->token, c->d_out_tokens, 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
         *token_out = c->h_state->token;
@@ -1040,18 +1042,16 @@ extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, cons
         cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
         b200_ctx tmp;
         tmp.st = st; tmp.sm_count = prop.multiProcessorCount;
-        int ns = std::max(1, (2 * tmp.sm_count) / n_head_kv);
-        ns = std::min(ns, std::max(1, (n_kv + 31) / 32));
         DBuf dq((size_t) qd * 4), dk((size_t) n_kv * kvd * 2), dv((size_t) n_kv * kvd * 2), dout((size_t) qd * 4);
-        DBuf po((size_t) n_head * ns * head_dim * 4), pml((size_t) n_head * ns * 2 * 4);
+        DBuf po((size_t) n_head * ATT_SPLITS * head_dim * 4), pml((size_t) n_head * ATT_SPLITS * 2 * 4), tk((size_t) n_head_kv * 4);
+        CU(cudaMemsetAsync(tk.p, 0, (size_t) n_head_kv * 4, st));
         CU(cudaMemcpyAsync(dq.p, q, (size_t) qd * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(dk.p, k_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(dv.p, v_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
-        b200_model mm; tmp.m = &mm;
         AttnArgs a{};
         a.q = dq.as<float>(); a.k_cache = dk.as<__half>(); a.v_cache = dv.as<__half>();
-        a.part_o = po.as<float>(); a.part_ml = pml.as<float>(); a.out = dout.as<float>();
-        a.n_head = n_head; a.n_head_kv = n_head_kv; a.head_dim = head_dim; a.kv_dim = kvd; a.n_splits = ns;
+        a.part_o = po.as<float>(); a.part_ml = pml.as<float>(); a.tickets = tk.as<unsigned int>(); a.out = dout.as<float>();
+        a.n_head = n_head; a.n_head_kv = n_head_kv; a.head_dim = head_dim; a.kv_dim = kvd;
         a.scale = scale; a.st = nullptr; a.n_kv_override = n_kv;
         launch_attention(&tmp, a);
         CU(cudaGetLastError());

@@ -646,234 +646,247 @@ __global__ void k_embed(int type, const uint8_t * __restrict__ rows, size_t row_
 // ------------------------------------------------------------------------------------------------------------
 // decode attention, default (non-flash) route at batch 1 (cpp/src/llama.cpp:8248-8297):
 //   kq = K(f16->f32) . q(f32)  [tinyBLAS F16xF32, cpp/ggml/src/ggml.c:12325-12341]
-//   softmax(kq*scale + mask)   [cpp/ggml/src/ggml.c:13682-13778; causality from (pos) instead of a mask tensor]
+//   softmax(kq*scale + mask)   [cpp/ggml/src/ggml.c:13682-13778; causality from `pos`, no mask tensor]
 //   kqv = V(f16->f32) . p      [same tinyBLAS route]
-// split-KV flash-decode: grid (n_head_kv, n_splits); each CTA serves the `gqa` query heads that share its
-// KV head so K and V rows are read once per group (cf. cpp/ggml/src/ggml.c:12207-12243 broadcast).
-// Partials (unnormalised o, running max m, sum l) are merged by k_attn_combine.
+// Split-KV flash-decode, one launch: grid (n_head_kv, ATT_SPLITS), 256 threads. A CTA serves the `GQA` query
+// heads that share its KV head (K and V rows are read once per group, cf. the broadcast in
+// cpp/ggml/src/ggml.c:12207-12243) over 64-position tiles t = split, split + ATT_SPLITS, ...
+// Latency design (HBM-bound, 8.4 MB per layer at ctx 2048 => every byte must be in flight at once):
+//   * all K loads (4 x 16 B per thread: 4 lanes per key row) AND all V loads (16 x 4 B per thread) of a tile are
+//     issued before any arithmetic, so a tile costs one DRAM round trip;
+//   * scores: 32-dim partial dots per lane, 2 shuffles per head; softmax state per head kept in shared memory;
+//   * P.V: thread = (dim pair, 16-position group), partial sums merged through shared memory;
+//   * the last CTA of a KV head (atomic ticket) merges the splits — no separate combine launch.
 // ------------------------------------------------------------------------------------------------------------
-static constexpr int ATT_THREADS = 128;
+static constexpr int ATT_THREADS = 256;
+static constexpr int ATT_TILE    = 64;
+static constexpr int ATT_SPLITS  = 32;
 static constexpr int ATT_MAX_GQA = 8;
 
 struct AttnArgs {
     const float * q;          // [n_head][hd] post-RoPE
     const __half * k_cache;   // [n_ctx][kv_dim]
     const __half * v_cache;
-    float * part_o;           // [n_head][n_splits][hd]
-    float * part_ml;          // [n_head][n_splits][2]
-    float * out;              // [n_head*hd]
-    int n_head, n_head_kv, head_dim, kv_dim, n_splits;
+    float * part_o;           // [n_head][ATT_SPLITS][hd]  un-normalised
+    float * part_ml;          // [n_head][ATT_SPLITS][2]   (running max, sum)
+    unsigned int * tickets;   // [n_head_kv] zero-initialised, self-resetting
+    float * out;              // [n_head*hd]  (kqv_merged_cont)
+    int n_head, n_head_kv, head_dim, kv_dim;
     float scale;
     const DecodeState * st;
     int n_kv_override;        // >0: use instead of st->pos+1 (operator-level test)
 };
 
 template <int GQA>
-__global__ void __launch_bounds__(ATT_THREADS) k_attn_partial(const AttnArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int hd = a.head_dim;                 // 128 on every config; kernel assumes hd % 8 == 0, hd <= 256
-    float * qs = reinterpret_cast<float *>(smem_raw);            // [GQA][hd]
-    float * ps = qs + GQA * hd;                                  // [GQA][chunk]
-    __shared__ float red[GQA][ATT_THREADS / 32];
-    __shared__ float bcast[GQA];
+__global__ void __launch_bounds__(ATT_THREADS) k_attn(const AttnArgs a) {
+    constexpr int HD = 128;                                   // every LLaMA/Mistral config on this path
+    __shared__ __align__(16) float qs[GQA][HD];
+    __shared__ __align__(16) float sc[GQA][ATT_TILE];         // scores, then probabilities
+    __shared__ float run_m[GQA], run_l[GQA], resc[GQA];
+    __shared__ __align__(16) float red_o[4][GQA][HD];         // P.V partials of the 4 position groups
+    __shared__ float wsplit[GQA][ATT_SPLITS];
+    __shared__ unsigned int s_ticket;
 
-    const int g = blockIdx.x, s = blockIdx.y;
+    const int g = blockIdx.x, split = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_kv = a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1;
     const int round_q = a.st ? a.st->round_q : 0;
-    const int chunk = (n_kv + a.n_splits - 1) / a.n_splits;
-    const int p0 = s * chunk;
-    const int p1 = min(n_kv, p0 + chunk);
-    const int len = max(0, p1 - p0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_tiles = (n_kv + ATT_TILE - 1) / ATT_TILE;
 
-    for (int i = tid; i < GQA * hd; i += ATT_THREADS) {
-        float v = a.q[(size_t) (g * GQA) * hd + i];
-        if (round_q) v = __half2float(__float2half_rn(v));
-        qs[i] = v;
+    for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
+        float v = a.q[(size_t) (g * GQA) * HD + i];
+        if (round_q) v = __half2float(__float2half_rn(v));    // batch > 1: q is rounded to f16 (ggml.c:12345-12371)
+        (&qs[0][0])[i] = v;
     }
+    if (tid < GQA) { run_m[tid] = -INFINITY; run_l[tid] = 0.f; }
+
+    // thread roles
+    const int kp = tid >> 2, kq4 = tid & 3;                   // scores: key position in tile, 32-dim quarter
+    const int dp = tid & 63, pg = tid >> 6;                   // P.V: dim pair, position group (16 positions)
+    float o[GQA][2];
+#pragma unroll
+    for (int h = 0; h < GQA; h++) { o[h][0] = 0.f; o[h][1] = 0.f; }
     __syncthreads();
 
-    // phase 1: one thread per key position
-    float lmax[GQA];
+    for (int tile = split; tile < n_tiles; tile += ATT_SPLITS) {
+        const int p0 = tile * ATT_TILE;
+        // ---- issue every load of the tile
+        uint4 kreg[4];
+        const bool kvalid = p0 + kp < n_kv;
+        if (kvalid) {
+            const uint4 * kr = reinterpret_cast<const uint4 *>(a.k_cache + (size_t) (p0 + kp) * a.kv_dim + g * HD + kq4 * 32);
 #pragma unroll
-    for (int h = 0; h < GQA; h++) lmax[h] = -INFINITY;
-    for (int i = tid; i < len; i += ATT_THREADS) {
-        const uint4 * kr = reinterpret_cast<const uint4 *>(a.k_cache + (size_t) (p0 + i) * a.kv_dim + g * hd);
+            for (int i = 0; i < 4; i++) kreg[i] = ldg_stream_v4(kr + i);
+        }
+        uint32_t vreg[16];
+        const __half * vbase = a.v_cache + (size_t) (p0 + pg * 16) * a.kv_dim + g * HD + 2 * dp;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            vreg[i] = 0u;
+            if (p0 + pg * 16 + i < n_kv) vreg[i] = __ldg(reinterpret_cast<const uint32_t *>(vbase + (size_t) i * a.kv_dim));
+        }
+        // ---- scores
         float acc[GQA];
 #pragma unroll
         for (int h = 0; h < GQA; h++) acc[h] = 0.f;
-        for (int c = 0; c < hd / 8; c++) {
-            const uint4 kv = kr[c];
-            const __half2 * k2 = reinterpret_cast<const __half2 *>(&kv);
-            float kf[8];
+        if (kvalid) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) { const float2 f = __half22float2(k2[e]); kf[2 * e] = f.x; kf[2 * e + 1] = f.y; }
+            for (int i = 0; i < 4; i++) {
+                const __half2 * k2 = reinterpret_cast<const __half2 *>(&kreg[i]);
+                float kf[8];
 #pragma unroll
-            for (int h = 0; h < GQA; h++) {
-                const float4 qa = *reinterpret_cast<const float4 *>(qs + h * hd + c * 8);
-                const float4 qb = *reinterpret_cast<const float4 *>(qs + h * hd + c * 8 + 4);
-                acc[h] = fmaf(kf[0], qa.x, acc[h]); acc[h] = fmaf(kf[1], qa.y, acc[h]);
-                acc[h] = fmaf(kf[2], qa.z, acc[h]); acc[h] = fmaf(kf[3], qa.w, acc[h]);
-                acc[h] = fmaf(kf[4], qb.x, acc[h]); acc[h] = fmaf(kf[5], qb.y, acc[h]);
-                acc[h] = fmaf(kf[6], qb.z, acc[h]); acc[h] = fmaf(kf[7], qb.w, acc[h]);
+                for (int e = 0; e < 4; e++) { const float2 f = __half22float2(k2[e]); kf[2 * e] = f.x; kf[2 * e + 1] = f.y; }
+#pragma unroll
+                for (int h = 0; h < GQA; h++) {
+                    const float4 qa = *reinterpret_cast<const float4 *>(&qs[h][kq4 * 32 + i * 8]);
+                    const float4 qb = *reinterpret_cast<const float4 *>(&qs[h][kq4 * 32 + i * 8 + 4]);
+                    acc[h] = fmaf(kf[0], qa.x, acc[h]); acc[h] = fmaf(kf[1], qa.y, acc[h]);
+                    acc[h] = fmaf(kf[2], qa.z, acc[h]); acc[h] = fmaf(kf[3], qa.w, acc[h]);
+                    acc[h] = fmaf(kf[4], qb.x, acc[h]); acc[h] = fmaf(kf[5], qb.y, acc[h]);
+                    acc[h] = fmaf(kf[6], qb.z, acc[h]); acc[h] = fmaf(kf[7], qb.w, acc[h]);
+                }
             }
         }
 #pragma unroll
         for (int h = 0; h < GQA; h++) {
-            const float sc = __fmul_rn(acc[h], a.scale);
-            ps[h * chunk + i] = sc;
-            lmax[h] = fmaxf(lmax[h], sc);
+            float s = acc[h];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (kq4 == 0) sc[h][kp] = kvalid ? __fmul_rn(s, a.scale) : -INFINITY;
         }
-    }
-#pragma unroll
-    for (int h = 0; h < GQA; h++) {
-        const float m = warp_max(lmax[h]);
-        if (lane == 0) red[h][warp] = m;
-    }
-    __syncthreads();
-    if (tid < GQA) {
-        float m = -INFINITY;
-        for (int w = 0; w < ATT_THREADS / 32; w++) m = fmaxf(m, red[tid][w]);
-        bcast[tid] = m;
-    }
-    __syncthreads();
-    float mh[GQA];
-#pragma unroll
-    for (int h = 0; h < GQA; h++) mh[h] = bcast[h];
-    __syncthreads();
-
-    // phase 2: p = exp(s - m), l = sum p
-    float lsum[GQA];
-#pragma unroll
-    for (int h = 0; h < GQA; h++) lsum[h] = 0.f;
-    for (int i = tid; i < len; i += ATT_THREADS) {
-#pragma unroll
-        for (int h = 0; h < GQA; h++) {
-            const float p = expf(ps[h * chunk + i] - mh[h]);
-            ps[h * chunk + i] = p;
-            lsum[h] += p;
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < GQA; h++) {
-        const float l = warp_sum(lsum[h]);
-        if (lane == 0) red[h][warp] = l;
-    }
-    __syncthreads();
-    if (tid < GQA) {
-        float l = 0.f;
-        for (int w = 0; w < ATT_THREADS / 32; w++) l += red[tid][w];
-        const size_t o = ((size_t) (g * GQA + tid) * a.n_splits + s) * 2;
-        a.part_ml[o]     = len > 0 ? mh[tid] : -INFINITY;
-        a.part_ml[o + 1] = l;
-    }
-
-    // phase 3: o[h][d] = sum_i p[h][i] * V[i][d]; thread owns dims (2 per thread when hd == 2*threads ... general loop)
-    for (int d = tid; d < hd; d += ATT_THREADS) {
-        float o[GQA];
-#pragma unroll
-        for (int h = 0; h < GQA; h++) o[h] = 0.f;
-        const __half * vcol = a.v_cache + (size_t) p0 * a.kv_dim + g * hd + d;
-        int i = 0;
-        for (; i + 4 <= len; i += 4) {
-            const float v0 = __half2float(vcol[(size_t) (i + 0) * a.kv_dim]);
-            const float v1 = __half2float(vcol[(size_t) (i + 1) * a.kv_dim]);
-            const float v2 = __half2float(vcol[(size_t) (i + 2) * a.kv_dim]);
-            const float v3 = __half2float(vcol[(size_t) (i + 3) * a.kv_dim]);
-#pragma unroll
-            for (int h = 0; h < GQA; h++) {
-                const float * pp = ps + h * chunk + i;
-                o[h] = fmaf(pp[0], v0, o[h]); o[h] = fmaf(pp[1], v1, o[h]);
-                o[h] = fmaf(pp[2], v2, o[h]); o[h] = fmaf(pp[3], v3, o[h]);
+        __syncthreads();
+        // ---- online softmax state: warp h owns head h (64 scores = 2 per lane)
+        if (warp < GQA) {
+            const float s0 = sc[warp][lane], s1 = sc[warp][lane + 32];
+            const float mt = warp_max(fmaxf(s0, s1));
+            const float m_old = run_m[warp];
+            const float m_new = fmaxf(m_old, mt);
+            const float p0v = expf(s0 - m_new), p1v = expf(s1 - m_new);     // exp(-inf) = 0 for masked slots
+            const float lt = warp_sum(p0v + p1v);
+            sc[warp][lane] = p0v; sc[warp][lane + 32] = p1v;
+            if (lane == 0) {
+                const float r = m_old == -INFINITY ? 0.f : expf(m_old - m_new);
+                resc[warp] = r;
+                run_l[warp] = run_l[warp] * r + lt;
+                run_m[warp] = m_new;
             }
         }
-        for (; i < len; i++) {
-            const float v0 = __half2float(vcol[(size_t) i * a.kv_dim]);
+        __syncthreads();
+        // ---- P.V for this thread's 16 positions x 2 dims
 #pragma unroll
-            for (int h = 0; h < GQA; h++) o[h] = fmaf(ps[h * chunk + i], v0, o[h]);
+        for (int h = 0; h < GQA; h++) {
+            const float r = resc[h];
+            float o0 = o[h][0] * r, o1 = o[h][1] * r;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; i4++) {
+                const float4 pv = *reinterpret_cast<const float4 *>(&sc[h][pg * 16 + i4 * 4]);
+                const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(&vreg[i4 * 4 + e]));
+                    o0 = fmaf(pp[e], vf.x, o0);
+                    o1 = fmaf(pp[e], vf.y, o1);
+                }
+            }
+            o[h][0] = o0; o[h][1] = o1;
         }
-#pragma unroll
-        for (int h = 0; h < GQA; h++) a.part_o[((size_t) (g * GQA + h) * a.n_splits + s) * hd + d] = o[h];
+        __syncthreads();     // sc / resc are rewritten by the next tile
     }
-}
 
-__global__ void k_attn_combine(const AttnArgs a) {
-    const int h = blockIdx.x, hd = a.head_dim;
-    const float * ml = a.part_ml + (size_t) h * a.n_splits * 2;
-    float M = -INFINITY;
-    for (int s = 0; s < a.n_splits; s++) M = fmaxf(M, ml[2 * s]);
-    float L = 0.f;
-    for (int s = 0; s < a.n_splits; s++) if (ml[2 * s + 1] > 0.f) L += ml[2 * s + 1] * expf(ml[2 * s] - M);
-    const float inv = 1.0f / L;
-    for (int d = threadIdx.x; d < hd; d += blockDim.x) {
-        float o = 0.f;
-        for (int s = 0; s < a.n_splits; s++) {
-            if (ml[2 * s + 1] > 0.f) o += a.part_o[((size_t) h * a.n_splits + s) * hd + d] * expf(ml[2 * s] - M);
+    // ---- merge the 4 position groups, publish this split's partial
+#pragma unroll
+    for (int h = 0; h < GQA; h++) { red_o[pg][h][2 * dp] = o[h][0]; red_o[pg][h][2 * dp + 1] = o[h][1]; }
+    __syncthreads();
+    for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
+        const int h = i / HD, d = i % HD;
+        const float v = red_o[0][h][d] + red_o[1][h][d] + red_o[2][h][d] + red_o[3][h][d];
+        a.part_o[((size_t) (g * GQA + h) * ATT_SPLITS + split) * HD + d] = v;
+    }
+    if (tid < GQA) {
+        const size_t oi = ((size_t) (g * GQA + tid) * ATT_SPLITS + split) * 2;
+        a.part_ml[oi] = run_m[tid]; a.part_ml[oi + 1] = run_l[tid];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&a.tickets[g], 1u);
+    __syncthreads();
+    if (s_ticket != ATT_SPLITS - 1) return;
+    // ---- last CTA of this KV head: combine the splits
+    __threadfence();
+    if (tid == 0) a.tickets[g] = 0u;                          // self-reset for the next launch
+    for (int i = tid; i < GQA * ATT_SPLITS; i += ATT_THREADS) {
+        const int h = i / ATT_SPLITS, s = i % ATT_SPLITS;
+        (&wsplit[0][0])[i] = __ldcg(&a.part_ml[((size_t) (g * GQA + h) * ATT_SPLITS + s) * 2]);   // m_s for now
+    }
+    __syncthreads();
+    if (tid < GQA) {
+        float M = -INFINITY;
+        for (int s = 0; s < ATT_SPLITS; s++) M = fmaxf(M, wsplit[tid][s]);
+        float L = 0.f;
+        for (int s = 0; s < ATT_SPLITS; s++) {
+            const float ms = wsplit[tid][s];
+            const float w = ms == -INFINITY ? 0.f : expf(ms - M);
+            L += w * __ldcg(&a.part_ml[((size_t) (g * GQA + tid) * ATT_SPLITS + s) * 2 + 1]);
+            wsplit[tid][s] = w;
         }
-        a.out[(size_t) h * hd + d] = o * inv;   // kqv_merged_cont layout: [n_head*hd]
+        run_l[tid] = 1.0f / L;
+    }
+    __syncthreads();
+    for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
+        const int h = i / HD, d = i % HD;
+        float v = 0.f;
+        for (int s = 0; s < ATT_SPLITS; s++) {
+            const float w = wsplit[h][s];
+            if (w != 0.f) v = fmaf(w, __ldcg(&a.part_o[((size_t) (g * GQA + h) * ATT_SPLITS + s) * HD + d]), v);
+        }
+        a.out[(size_t) (g * GQA + h) * HD + d] = v * run_l[h];   // kqv_merged_cont layout: [n_head*hd]
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// greedy sampling on device: first index of the maximum (sample_top_token, cpp/bridge.cpp:962-981 keeps the
-// first strictly-greater logit) and hand-over to the next step's DecodeState.
+// greedy sampling on device: arg-max over the logits with the lowest index winning ties (a strictly-greater scan
+// like sample_top_token, cpp/bridge.cpp:962-981), two tiny launches: per-CTA reduction + one 64-bit atomicMax on
+// a packed (orderable value, ~index) key, then a 1-thread finish that hands the token to the next step.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_argmax_advance(const float * __restrict__ logits, int n, DecodeState * st, int32_t * out_tokens) {
-    __shared__ float sv[32];
-    __shared__ int   si[32];
-    float best = -INFINITY; int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float v = logits[i];
-        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+__device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+    uint32_t u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);            // monotone map float -> uint
+    return ((unsigned long long) u << 32) | (unsigned long long) (0xffffffffu - (uint32_t) idx);
+}
+__global__ void k_argmax_partial(const float * __restrict__ logits, int n, unsigned long long * key) {
+    __shared__ unsigned long long sk[32];
+    unsigned long long best = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long kk = argmax_key(logits[i], i);
+        best = kk > best ? kk : best;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int   oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
+        best = ok > best ? ok : best;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+    if (lane == 0) sk[warp] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int) (blockDim.x >> 5); w++) {
-            if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
-        }
-        if (out_tokens) out_tokens[st->step] = bi;
-        st->token = bi;
-        st->pos  += 1;
-        st->step += 1;
+        for (int w = 1; w < (int) (blockDim.x >> 5); w++) best = sk[w] > best ? sk[w] : best;
+        atomicMax(key, best);
     }
 }
-
+// advance != 0: greedy loop (token -> next step's DecodeState, out_tokens[step]); advance == 0: out_tokens[0] only
+__global__ void k_argmax_finish(unsigned long long * key, DecodeState * st, int32_t * out_tokens, int advance) {
+    if (threadIdx.x != 0) return;
+    const int idx = (int) (0xffffffffu - (uint32_t) (*key & 0xffffffffull));
+    *key = 0ull;
+    if (advance) {
+        if (out_tokens) out_tokens[st->step] = idx;
+        st->token = idx; st->pos += 1; st->step += 1;
+    } else {
+        out_tokens[0] = idx;
+    }
+}
 
 __global__ void k_set_state(DecodeState * st, const DecodeState v) { *st = v; }
-
-// argmax without touching the DecodeState (bridge loop: the host feeds the next token)
-__global__ void k_argmax_only(const float * __restrict__ logits, int n, int32_t * out) {
-    __shared__ float sv[32];
-    __shared__ int   si[32];
-    float best = -INFINITY; int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float v = logits[i];
-        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int   oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sv[warp] = best; si[warp] = bi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int) (blockDim.x >> 5); w++) {
-            if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
-        }
-        out[0] = bi;
-    }
-}
 
 // advance (pos, step) on stages that do not sample (pipeline stages other than the last)
 __global__ void k_advance(DecodeState * st) {

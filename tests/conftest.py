@@ -57,3 +57,15 @@ def q8k_equal(a, b) -> bool:
     a[zero, 260:] = 0
     b[zero, 260:] = 0
     return bool(np.array_equal(a, b))
+
+
+def greedy_consistent(ours, theirs) -> bool:
+    """arg-max agreement up to a provable near-tie: either the ids are equal, or the reference's margin between
+    its own arg-max and ours is smaller than twice the max-abs deviation of our logits from the reference's at this
+    step (a deviation the flip bound allows) — i.e. the two candidates are tied within the arithmetic noise."""
+    ours = np.asarray(ours, dtype=np.float64)
+    theirs = np.asarray(theirs, dtype=np.float64)
+    a, t = int(np.argmax(ours)), int(np.argmax(theirs))
+    if a == t:
+        return True
+    return bool(theirs[t] - theirs[a] <= 2.0 * np.abs(ours - theirs).max())
