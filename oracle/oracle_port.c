@@ -10,11 +10,14 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * library. The product (booster_b200/) never does.
  *
- * Float summation ORDER of the quantized dot products follows the reference's AVX2 code path (the one an
- * x86-64 Booster build runs: 8 fp32 lanes, FMA, then a fixed horizontal add), so on x86 the port's mat-vec
- * is bit-identical to the reference's; attention/softmax use straightforward scalar order and libm expf
- * (the reference uses tinyBLAS tiles and a SIMD exp polynomial), i.e. they agree to fp32 round-off.
- * Compile with -ffp-contract=off: contraction is written explicitly with fmaf where the reference uses FMA.
+ * EVERY floating-point operation is restated in the reference's exact order for its AVX-512 ("native",
+ * -march=native on Sapphire Rapids, what Booster's own build flags produce) build: the K-quant dot products follow
+ * the AVX2 code path (8 fp32 lanes, FMA chains over super-blocks, fixed horizontal add), K.q and V.p follow
+ * tinyBLAS<16> (16-lane FMA chains + _mm512_reduce_add_ps), batch>1 K.q follows ggml_vec_dot_f16, silu and softmax
+ * use the ggml_v_expf polynomial, row sums are accumulated in double. Result: whole-model logits are
+ * BIT-IDENTICAL to the reference's (tests/test_oracle_pinned.py checks array_equal against golden vectors and
+ * against oracle/_ref live). Compile with -ffp-contract=off: contraction is written explicitly with fmaf where the
+ * reference uses FMA.
  */
 #include <math.h>
 #include <stdint.h>
@@ -298,7 +301,35 @@ void port_rope(float * x, int n_heads, int head_dim, int pos, float freq_base, f
     }
 }
 
-static float silu(float x) { return x / (1.0f + expf(-x)); }   /* ggml_silu_f32, cpp/ggml/src/ggml.c:2393 */
+/* ---- the reference's SIMD exp/silu, lane-exact -------------------------------------------------------------
+ * ggml_v_expf, AVX-512 variant (cpp/ggml/src/ggml.c:2447-2472): every step is an element-wise IEEE operation
+ * (fmadd / fnmadd / mul / scalef), restated here with fmaf and ldexpf. The AVX2 variant of the reference
+ * (:2487-) scales differently in its last step and is NOT bit-identical; this port follows the "native"
+ * (AVX-512) build, which is what Booster's -march=native produces on the hosts in question. */
+static float v_expf(float x) {
+    const float r = 0x1.8p23f;
+    const float z = fmaf(x, 0x1.715476p+0f, r);
+    const float n = z - r;
+    const float b = fmaf(-n, 0x1.7f7d1cp-20f, fmaf(-n, 0x1.62e4p-1f, x));
+    const int   big = fabsf(n) > 192.f;
+    const float u = b * b;
+    const float j = fmaf(fmaf(fmaf(0x1.0e4020p-7f, b, 0x1.573e2ep-5f), u, fmaf(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)), u,
+                         fmaf(0x1.ffffecp-1f, b, 1.0f));
+    if (big) return n <= 0.f ? 0.f : INFINITY;       /* also catches x = -inf (n = -inf) */
+    return ldexpf(j, (int) n);                        /* _mm512_scalef_ps(j, n): exact scaling by 2^n */
+}
+/* ggml_v_silu (cpp/ggml/src/ggml.c:2475-2482): x / (1 + exp(0 - x)) */
+static float silu(float x) { return x / (1.0f + v_expf(0.0f - x)); }
+
+/* _mm512_reduce_add_ps as GCC expands it (avx512fintrin.h __MM512_REDUCE_OP): upper+lower 256, upper+lower 128,
+ * then (0+2), (1+3), and the final pair */
+static float reduce_add16(const float * a) {
+    float t3[8], t6[4];
+    for (int i = 0; i < 8; i++) t3[i] = a[8 + i] + a[i];
+    for (int i = 0; i < 4; i++) t6[i] = t3[4 + i] + t3[i];
+    const float t80 = t6[0] + t6[2], t81 = t6[1] + t6[3];
+    return t80 + t81;
+}
 
 /* ---- the model ------------------------------------------------------------------------------------------------ */
 typedef struct { int32_t type; int32_t pad; const uint8_t * data; int64_t rows, k; } port_mat;
@@ -320,36 +351,64 @@ typedef struct {
     float * tap_kqv;        /* optional [n_layer][n_head*head_dim]: kqv_merged_cont of the last token */
 } port_model;
 
-/* default (non-flash) attention for one query token at position pos (llm_build_kqv, cpp/src/llama.cpp:8248-8297):
- * kq = K.q (f16 K widened to f32; q f32 at batch 1, rounded to f16 at batch > 1: cpp/ggml/src/ggml.c:12325-12371),
- * soft_max_ext(kq*scale + mask) with a double row sum (cpp/ggml/src/ggml.c:13682-13778), kqv = V.p */
+/* default (non-flash) attention for one query token at position pos (llm_build_kqv, cpp/src/llama.cpp:8248-8297),
+ * in the exact operation order of the reference's AVX-512 build:
+ *   kq   batch 1 : tinyBLAS<16> F16xF32 (cpp/ggml/src/llamafile/sgemm.cpp:408-430): 16 lanes, lane c chains
+ *                  fma(k[16s+c], q[16s+c], acc) over s, then _mm512_reduce_add_ps
+ *        batch>1 : q rounded to f16, ggml_vec_dot_f16 (cpp/ggml/src/ggml.c:2038-2075): 4 accumulators x 16 lanes
+ *                  over steps of 64, reduced (0+2),(1+3),(0+1), then _mm512_reduce_add_ps
+ *   soft_max_ext : x*scale (+mask), max, ggml_v_expf(x-max) per 16 lanes, double sum of the per-vector
+ *                  _mm512_reduce_add_ps, then p *= (float)(1/sum)   (cpp/ggml/src/ggml.c:13682-13778, 2619-2640)
+ *   kqv          : tinyBLAS<16> over the (32-padded) kv length: lane c chains fma(v[16s+c][d], p[16s+c], acc)
+ * n_kv is padded to 32 by the reference (kv_self.n, cpp/src/llama.cpp:14698); padded slots have p = 0. */
 static void attention(const port_model * M, int il, const float * q, int pos, int round_q, float * out) {
     const int hd = M->head_dim, kvd = M->n_head_kv * hd, gqa = M->n_head / M->n_head_kv, n_kv = pos + 1;
+    const int n_pad = (n_kv + 31) / 32 * 32;
     const uint16_t * kc = M->k_cache + (int64_t) il * M->n_ctx * kvd;
     const uint16_t * vc = M->v_cache + (int64_t) il * M->n_ctx * kvd;
     const float scale = 1.0f / sqrtf((float) hd);
 #pragma omp parallel for schedule(static)
     for (int h = 0; h < M->n_head; h++) {
         const int g = h / gqa;
-        float * p = (float *) malloc(sizeof(float) * (size_t) n_kv);
+        float * p = (float *) malloc(sizeof(float) * (size_t) n_pad);
         float qh[512];
         for (int d = 0; d < hd; d++) qh[d] = round_q ? h2f(f2h(q[h * hd + d])) : q[h * hd + d];
         float max = -INFINITY;
-        for (int t = 0; t < n_kv; t++) {
+        for (int t = 0; t < n_pad; t++) {
+            if (t >= n_kv) { p[t] = -INFINITY; continue; }
             const uint16_t * kr = kc + (int64_t) t * kvd + g * hd;
-            float s = 0.f;
-            for (int d = 0; d < hd; d++) s = fmaf(h2f(kr[d]), qh[d], s);
+            float s;
+            if (!round_q) {
+                float acc[16] = {0};
+                for (int l = 0; l < hd; l += 16)
+                    for (int c = 0; c < 16; c++) acc[c] = fmaf(h2f(kr[l + c]), qh[l + c], acc[c]);
+                s = reduce_add16(acc);
+            } else {
+                float acc[4][16] = {{0}};
+                for (int i = 0; i < hd; i += 64)
+                    for (int j = 0; j < 4; j++)
+                        for (int c = 0; c < 16; c++) acc[j][c] = fmaf(h2f(kr[i + 16 * j + c]), qh[i + 16 * j + c], acc[j][c]);
+                float r[16];
+                for (int c = 0; c < 16; c++) r[c] = (acc[0][c] + acc[2][c]) + (acc[1][c] + acc[3][c]);
+                s = reduce_add16(r);
+            }
             p[t] = s * scale;
             if (p[t] > max) max = p[t];
         }
         double sum = 0.0;
-        for (int t = 0; t < n_kv; t++) { p[t] = expf(p[t] - max); sum += (double) p[t]; }
-        const float inv = (float)(1.0 / sum);
-        for (int t = 0; t < n_kv; t++) p[t] *= inv;
+        for (int t0 = 0; t0 < n_pad; t0 += 16) {
+            float v[16];
+            for (int c = 0; c < 16; c++) { v[c] = v_expf(p[t0 + c] - max); p[t0 + c] = v[c]; }
+            sum += (double) reduce_add16(v);
+        }
+        const float inv = (float) (1.0 / sum);
+        for (int t = 0; t < n_pad; t++) p[t] *= inv;
         for (int d = 0; d < hd; d++) {
-            float o = 0.f;
-            for (int t = 0; t < n_kv; t++) o = fmaf(h2f(vc[(int64_t) t * kvd + g * hd + d]), p[t], o);
-            out[h * hd + d] = o;
+            float acc[16] = {0};
+            for (int t0 = 0; t0 < n_kv; t0 += 16)
+                for (int c = 0; c < 16 && t0 + c < n_kv; c++)
+                    acc[c] = fmaf(h2f(vc[(int64_t) (t0 + c) * kvd + g * hd + d]), p[t0 + c], acc[c]);
+            out[h * hd + d] = reduce_add16(acc);
         }
         free(p);
     }

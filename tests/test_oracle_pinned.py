@@ -44,35 +44,30 @@ def test_vec_dot_bit_exact(ops, name):
     assert np.array_equal(y, ops[f"dot_{name}"]), f"max abs diff {np.abs(y - ops[f'dot_{name}']).max()}"
 
 
-# A 1-ulp difference upstream (the port uses libm expf, the reference a SIMD polynomial) can flip ONE int8 of a
-# Q8_K/Q8_0 activation; in these tiny models (K = 256..768) a single flip moves a layer output by ~1e-3 and the
-# logits by up to ~1e-2 (measured: tiny-gqa4 at position 2). So model-level criteria are flip-robust:
-# most steps agree to fp32 round-off, every step stays within the flip bound, greedy ids are exact.
-ROUNDOFF, FLIP_BOUND = 5e-6, 5e-2
-
-
+# The port restates EVERY floating-point operation of the reference's AVX-512 ("native") build in its exact
+# order — AVX2-lane fma chains of the K-quant dots, tinyBLAS 16-lane chains + _mm512_reduce_add_ps for K.q and
+# V.p, ggml_vec_dot_f16 for batch > 1, the ggml_v_expf polynomial in silu/softmax, double row sums — so whole-model
+# logits are BIT-IDENTICAL to the reference's, step after step. Bitwise equality is the criterion: with quantized
+# activations anything weaker is meaningless, because a 1-ulp upstream difference eventually flips an int8 of a
+# Q8_K block and the deviation cascades to ~1e-2 and persists through the KV cache (DESIGN.md "why bit-exact").
 @pytest.mark.parametrize("model", ["tiny_Q4_K_M", "tiny_Q5_K_M", "tiny_Q8_0", "tiny-gqa4_Q4_K_M"])
-def test_model_logits_vs_golden(golden_dir, model):
+def test_model_logits_vs_golden_bitwise(golden_dir, model):
     g = np.load(os.path.join(golden_dir, model + ".npz"))
     m = port.PortModelRunner(os.path.join(golden_dir, model + ".gguf"), n_ctx=64)
     prompt = g["prompt"].tolist()
-    errs = []
-    # batch (n>1) arithmetic, then batch-1 steps, feeding the REFERENCE's token ids
-    lg = m.decode(prompt, 0)
-    errs.append(rel_err(lg, g["logits"][0]))
+    lg = m.decode(prompt, 0)                                   # batch (n > 1) arithmetic
+    assert np.array_equal(lg, g["logits"][0])
+    n_layer = m.M.n_layer
+    assert np.array_equal(m.tap_l_out[n_layer - 1], g[f"l_out_{n_layer - 1}"])
     pos = len(prompt)
     for i, t in enumerate(g["ids"].tolist()):
-        assert int(np.argmax(lg)) == t, f"greedy id differs at step {i}"
-        lg = m.decode([t], pos)
+        assert int(np.argmax(lg)) == t
+        lg = m.decode([t], pos)                                # batch-1 arithmetic
         pos += 1
-        errs.append(rel_err(lg, g["logits"][i + 1]))
+        assert np.array_equal(lg, g["logits"][i + 1]), f"step {i}"
     m.kv_clear()
     for i, t in enumerate(prompt[:6]):
-        errs.append(rel_err(m.decode([t], i), g["single"][i]))
-    errs = np.array(errs)
-    assert errs.max() < FLIP_BOUND, errs
-    assert np.median(errs) < ROUNDOFF, errs
-    assert (errs < ROUNDOFF).mean() >= 0.6, errs
+        assert np.array_equal(m.decode([t], i), g["single"][i])
 
 
 def test_port_vs_reference_live(ref_or_none, model_dir):
@@ -91,6 +86,14 @@ def test_port_vs_reference_live(ref_or_none, model_dir):
     r = ref.RefModel(path, n_ctx=64, n_threads=4)
     p = port.PortModelRunner(path, n_ctx=64)
     toks = [3, 1, 4, 1, 5, 9, 2, 6]
-    assert rel_err(p.decode(toks, 0), r.decode(toks, 0)) < FLIP_BOUND
-    assert rel_err(p.decode([7], len(toks)), r.decode([7], len(toks))) < FLIP_BOUND
+    if ref.variant() != "native":
+        pytest.skip("bit-exactness is defined against the AVX-512 (native) build of the reference")
+    lp, lr = p.decode(toks, 0), r.decode(toks, 0)
+    assert np.array_equal(lp, lr)
+    pos = len(toks)
+    for _ in range(6):
+        t = int(np.argmax(lr))
+        lp, lr = p.decode([t], pos), r.decode([t], pos)
+        pos += 1
+        assert np.array_equal(lp, lr)
     r.close()
