@@ -89,7 +89,7 @@ def lib() -> C.CDLL:
     sig("b200_op_rms_norm", C.c_int, [f32p, f32p, C.c_int64, C.c_float, f32p])
     sig("b200_op_rope", C.c_int, [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p])
     sig("b200_op_attention", C.c_int, [f32p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int,
-                                       C.c_int, C.c_float, f32p])
+                                       C.c_int, C.c_float, C.c_int, f32p])
     _lib = L
     return L
 

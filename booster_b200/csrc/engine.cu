@@ -54,96 +54,111 @@ static void require_gpu() {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// re-tiling kernels: ggml block layout -> planes (one thread per block; one-time at load)
+// re-tiling kernels: ggml block layout -> tiles (one thread per block; one-time at load). `vstride`/`voff` place
+// a tensor's row r at virtual row r*vstride + voff of the destination (gate/up interleave: vstride 2, voff 0/1).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_repack_q4k(const uint8_t * __restrict__ src, size_t n_blocks, uint8_t * p0, uint8_t * p1, uint8_t * p2) {
-    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) return;
-    const uint8_t * b = src + i * 144;   // {half d, half dmin, u8 scales[12], u8 qs[128]}  ggml-common.h:267-277
-    for (int j = 0; j < 4; j++)   p2[i * 4 + j] = b[j];
-    for (int j = 0; j < 12; j++)  p1[i * 12 + j] = b[4 + j];
-    for (int j = 0; j < 128; j++) p0[i * 128 + j] = b[16 + j];
+__device__ __forceinline__ void copy16(uint8_t * dst, const uint8_t * src) {
+    for (int j = 0; j < 16; j++) dst[j] = src[j];
 }
-__global__ void k_repack_q5k(const uint8_t * __restrict__ src, size_t n_blocks, uint8_t * p0, uint8_t * p1, uint8_t * p2, uint8_t * p3) {
-    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) return;
-    const uint8_t * b = src + i * 176;   // {half d, half dmin, u8 scales[12], u8 qh[32], u8 qs[128]}  :284-295
-    for (int j = 0; j < 4; j++)   p2[i * 4 + j] = b[j];
-    for (int j = 0; j < 12; j++)  p1[i * 12 + j] = b[4 + j];
-    for (int j = 0; j < 32; j++)  p3[i * 32 + j] = b[16 + j];
-    for (int j = 0; j < 128; j++) p0[i * 128 + j] = b[48 + j];
-}
-__global__ void k_repack_q6k(const uint8_t * __restrict__ src, size_t n_blocks, uint8_t * p0, uint8_t * p1, uint8_t * p2, uint8_t * p3) {
-    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) return;
-    const uint8_t * b = src + i * 210;   // {u8 ql[128], u8 qh[64], i8 scales[16], half d}  :302-307
-    for (int j = 0; j < 128; j++) p0[i * 128 + j] = b[j];
-    for (int j = 0; j < 64; j++)  p1[i * 64 + j] = b[128 + j];
-    for (int j = 0; j < 16; j++)  p2[i * 16 + j] = b[192 + j];
-    p3[i * 2] = b[208]; p3[i * 2 + 1] = b[209];
-}
-__global__ void k_repack_q80(const uint8_t * __restrict__ src, size_t n_blocks, uint8_t * p0, uint8_t * p1) {
-    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) return;
-    const uint8_t * b = src + i * 34;    // {half d, i8 qs[32]}  :186-190
-    p1[i * 2] = b[0]; p1[i * 2 + 1] = b[1];
-    for (int j = 0; j < 32; j++) p0[i * 32 + j] = b[2 + j];
+__global__ void k_retile(int type, const uint8_t * __restrict__ src, int64_t n_rows, int nb, int vstride, int voff,
+                         uint8_t * p0, uint8_t * p1, uint8_t * p2, uint8_t * p3) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;   // source block index = row*nb + bi
+    if (i >= n_rows * nb) return;
+    const int64_t row = i / nb, bi = i % nb;
+    const int64_t f = (row * vstride + voff) * nb + bi;                   // flattened destination block
+    const int64_t T = f >> 5; const int lane = (int) (f & 31);
+    if (type == T_Q4_K) {
+        const uint8_t * b = src + i * 144;   // {half d, half dmin, u8 scales[12], u8 qs[128]}  ggml-common.h:267-277
+        for (int c = 0; c < 8; c++) copy16(p0 + T * 4096 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
+        for (int w = 0; w < 3; w++) for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) w * 32 + lane) * 4 + j] = b[4 + 4 * w + j];
+        for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) 3 * 32 + lane) * 4 + j] = b[j];
+    } else if (type == T_Q5_K) {
+        const uint8_t * b = src + i * 176;   // {half d, half dmin, u8 scales[12], u8 qh[32], u8 qs[128]}  :284-295
+        for (int c = 0; c < 8; c++) copy16(p0 + T * 4096 + ((size_t) c * 32 + lane) * 16, b + 48 + 16 * c);
+        for (int c = 0; c < 2; c++) copy16(p2 + T * 1024 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
+        for (int w = 0; w < 3; w++) for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) w * 32 + lane) * 4 + j] = b[4 + 4 * w + j];
+        for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) 3 * 32 + lane) * 4 + j] = b[j];
+    } else if (type == T_Q6_K) {
+        const uint8_t * b = src + i * 210;   // {u8 ql[128], u8 qh[64], i8 scales[16], half d}  :302-307
+        for (int c = 0; c < 8; c++) copy16(p0 + T * 4096 + ((size_t) c * 32 + lane) * 16, b + 16 * c);
+        for (int c = 0; c < 4; c++) copy16(p2 + T * 2048 + ((size_t) c * 32 + lane) * 16, b + 128 + 16 * c);
+        for (int w = 0; w < 4; w++) for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) w * 32 + lane) * 4 + j] = b[192 + 4 * w + j];
+        p3[T * 64 + lane * 2] = b[208]; p3[T * 64 + lane * 2 + 1] = b[209];
+    } else {                                 // T_Q8_0: {half d, i8 qs[32]}  :186-190
+        const uint8_t * b = src + i * 34;
+        for (int c = 0; c < 2; c++) copy16(p0 + T * 1024 + ((size_t) c * 32 + lane) * 16, b + 2 + 16 * c);
+        p3[T * 64 + lane * 2] = b[0]; p3[T * 64 + lane * 2 + 1] = b[1];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // model
 // ------------------------------------------------------------------------------------------------------------
 struct DevMat {
-    QMat m;
+    TMat m;
     void * alloc = nullptr;
     size_t bytes = 0;       // algorithmic bytes (== ggml tensor bytes)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
 
-// upload a [n_rows x k] tensor in ggml block layout (host pointer) and re-tile it into planes
-static DevMat upload_matrix(int type, const void * host, int64_t n_rows, int64_t k, cudaStream_t st) {
+struct HostTensor { int type; const void * data; int64_t rows; int64_t k; };
+
+// upload n_src tensors of identical type/shape (1, or 2 for the gate/up interleave) as ONE tiled virtual matrix
+static DevMat upload_tiled(const HostTensor * src, int n_src, cudaStream_t st) {
+    const int type = src[0].type;
+    const int64_t k = src[0].k, rows1 = src[0].rows;
+    for (int i = 1; i < n_src; i++)
+        if (src[i].type != type || src[i].k != k || src[i].rows != rows1) throw std::runtime_error("interleaved tensors must share type and shape");
     if (k % 256 != 0) throw std::runtime_error("matrix inner dimension must be a multiple of 256 (got " + std::to_string(k) + ")");
-    if (n_rows % 2 != 0) throw std::runtime_error("matrix row count must be even");
-    DevMat d;
-    d.m.type = type; d.m.n_rows = (int) n_rows; d.m.k = (int) k;
-    const size_t raw = (size_t) ggml_row_bytes((uint32_t) type, (uint64_t) k) * (size_t) n_rows;
-    d.bytes = raw;
-    size_t sz[4] = {0, 0, 0, 0};
-    size_t n_blocks = 0;
+    int blk_bytes = 0, wpb = 256;
+    size_t tb[4] = {0, 0, 0, 0};   // bytes per tile of each plane
     switch (type) {
-        case T_Q4_K: n_blocks = (size_t) n_rows * (k / 256); sz[0] = n_blocks * 128; sz[1] = n_blocks * 12; sz[2] = n_blocks * 4; break;
-        case T_Q5_K: n_blocks = (size_t) n_rows * (k / 256); sz[0] = n_blocks * 128; sz[1] = n_blocks * 12; sz[2] = n_blocks * 4; sz[3] = n_blocks * 32; break;
-        case T_Q6_K: n_blocks = (size_t) n_rows * (k / 256); sz[0] = n_blocks * 128; sz[1] = n_blocks * 64; sz[2] = n_blocks * 16; sz[3] = n_blocks * 2; break;
-        case T_Q8_0: n_blocks = (size_t) n_rows * (k / 32);  sz[0] = n_blocks * 32;  sz[1] = n_blocks * 2; break;
+        case T_Q4_K: blk_bytes = 144; tb[0] = 4096; tb[1] = 512; break;
+        case T_Q5_K: blk_bytes = 176; tb[0] = 4096; tb[1] = 512; tb[2] = 1024; break;
+        case T_Q6_K: blk_bytes = 210; tb[0] = 4096; tb[1] = 512; tb[2] = 2048; tb[3] = 64; break;
+        case T_Q8_0: blk_bytes = 34; wpb = 32; tb[0] = 1024; tb[3] = 64; break;
         default: throw std::runtime_error("unsupported matrix type " + std::to_string(type) + " (supported: Q4_K, Q5_K, Q6_K, Q8_0)");
     }
+    DevMat d;
+    const int nb = (int) (k / wpb);
+    const int64_t vrows = rows1 * n_src;
+    int rows_unit = 32 / gcd_i(nb, 32);
+    if (rows_unit & 1) rows_unit *= 2;                 // RoPE pairs / (gate, up) pairs live in one unit
+    if (vrows % rows_unit != 0) throw std::runtime_error("row count " + std::to_string(vrows) + " is not a multiple of the work-unit height " + std::to_string(rows_unit));
+    d.m.type = type; d.m.n_rows = (int) vrows; d.m.nb = nb; d.m.rows_unit = rows_unit;
+    d.m.tiles_unit = rows_unit * nb / 32; d.m.n_units = (int) (vrows / rows_unit);
+    if (rows_unit > 32 || rows_unit * (type == T_Q4_K ? 12 : type == T_Q5_K ? 9 : 8) > 32 * MAX_CHAIN_SLOTS) throw std::runtime_error("work unit too tall");
+    const size_t n_tiles = (size_t) vrows * nb / 32;
+    const size_t raw1 = (size_t) blk_bytes * nb * rows1;
+    d.bytes = raw1 * n_src;
     size_t off[4], total = 0;
-    for (int i = 0; i < 4; i++) { off[i] = total; total += align_up(sz[i], 256); }
+    for (int i = 0; i < 4; i++) { off[i] = total; total += align_up(tb[i] * n_tiles, 256); }
     uint8_t * base = nullptr;
     CU(cudaMalloc(&base, total));
     d.alloc = base;
-    uint8_t * tmp = nullptr;
-    CU(cudaMalloc(&tmp, raw));
-    CU(cudaMemcpyAsync(tmp, host, raw, cudaMemcpyHostToDevice, st));
     uint8_t * p[4] = { base + off[0], base + off[1], base + off[2], base + off[3] };
-    const int thr = 128;
-    const unsigned grid = (unsigned) ((n_blocks + thr - 1) / thr);
-    switch (type) {
-        case T_Q4_K: k_repack_q4k<<<grid, thr, 0, st>>>(tmp, n_blocks, p[0], p[1], p[2]); break;
-        case T_Q5_K: k_repack_q5k<<<grid, thr, 0, st>>>(tmp, n_blocks, p[0], p[1], p[2], p[3]); break;
-        case T_Q6_K: k_repack_q6k<<<grid, thr, 0, st>>>(tmp, n_blocks, p[0], p[1], p[2], p[3]); break;
-        case T_Q8_0: k_repack_q80<<<grid, thr, 0, st>>>(tmp, n_blocks, p[0], p[1]); break;
+    uint8_t * tmp = nullptr;
+    CU(cudaMalloc(&tmp, raw1));
+    for (int i = 0; i < n_src; i++) {
+        CU(cudaMemcpyAsync(tmp, src[i].data, raw1, cudaMemcpyHostToDevice, st));
+        const int64_t n_blocks = rows1 * nb;
+        k_retile<<<(unsigned) ((n_blocks + 127) / 128), 128, 0, st>>>(type, tmp, rows1, nb, n_src, i, p[0], p[1], p[2], p[3]);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
     }
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
     CU(cudaFree(tmp));
-    d.m.p0 = p[0]; d.m.p1 = p[1]; d.m.p2 = sz[2] ? p[2] : nullptr; d.m.p3 = sz[3] ? p[3] : nullptr;
+    d.m.p0 = p[0]; d.m.p1 = tb[1] ? p[1] : nullptr; d.m.p2 = tb[2] ? p[2] : nullptr; d.m.p3 = tb[3] ? p[3] : nullptr;
     return d;
+}
+static DevMat upload_matrix(int type, const void * host, int64_t n_rows, int64_t k, cudaStream_t st) {
+    const HostTensor h{type, host, n_rows, k};
+    return upload_tiled(&h, 1, st);
 }
 
 struct LayerW {
-    DevMat wq, wk, wv, wo, gate, up, down;
+    DevMat wq, wk, wv, wo, gateup, down;    // gateup = ffn_gate/ffn_up interleaved row by row
     float * attn_norm = nullptr;
     float * ffn_norm = nullptr;
 };
@@ -261,14 +276,20 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
             L.wk   = upload_named(g, p + "attn_k.weight", KV, E, st);
             L.wv   = upload_named(g, p + "attn_v.weight", KV, E, st);
             L.wo   = upload_named(g, p + "attn_output.weight", E, Q, st);
-            L.gate = upload_named(g, p + "ffn_gate.weight", FF, E, st);
-            L.up   = upload_named(g, p + "ffn_up.weight", FF, E, st);
+            {
+                const gguf_tensor * tg = g.find(p + "ffn_gate.weight"), * tu = g.find(p + "ffn_up.weight");
+                if (!tg || !tu) throw std::runtime_error("missing ffn_gate/ffn_up in layer " + std::to_string(il));
+                if ((int64_t) tg->ne[0] != E || (int64_t) tg->ne[1] != FF || (int64_t) tu->ne[0] != E || (int64_t) tu->ne[1] != FF)
+                    throw std::runtime_error("ffn_gate/ffn_up have unexpected shapes");
+                if (tg->type != tu->type) throw std::runtime_error("ffn_gate and ffn_up must share a block type");
+                const HostTensor hs[2] = { {(int) tg->type, tg->data, FF, E}, {(int) tu->type, tu->data, FF, E} };
+                L.gateup = upload_tiled(hs, 2, st);
+            }
             L.down = upload_named(g, p + "ffn_down.weight", E, FF, st);
-            if (L.gate.m.type != L.up.m.type) throw std::runtime_error("ffn_gate and ffn_up must share a block type");
             const bool q80 = L.wq.m.type == T_Q8_0;
-            for (const DevMat * d : { &L.wq, &L.wk, &L.wv, &L.wo, &L.gate, &L.up, &L.down })
+            for (const DevMat * d : { &L.wq, &L.wk, &L.wv, &L.wo, &L.gateup, &L.down })
                 if ((d->m.type == T_Q8_0) != q80) throw std::runtime_error("mixing Q8_0 and K-quant matrices inside one layer is not supported");
-            wb += (int64_t) (L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.gate.bytes + L.up.bytes + L.down.bytes) + 2 * (int64_t) E * 4;
+            wb += (int64_t) (L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.gateup.bytes + L.down.bytes) + 2 * (int64_t) E * 4;
             m->layers.push_back(L);
         }
         if (m->has_embd()) {
@@ -299,7 +320,7 @@ extern "C" void b200_model_free(b200_model * m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (auto & L : m->layers) {
-        for (DevMat * d : { &L.wq, &L.wk, &L.wv, &L.wo, &L.gate, &L.up, &L.down }) cudaFree(d->alloc);
+        for (DevMat * d : { &L.wq, &L.wk, &L.wv, &L.wo, &L.gateup, &L.down }) cudaFree(d->alloc);
         cudaFree(L.attn_norm); cudaFree(L.ffn_norm);
     }
     cudaFree(m->embd_rows); cudaFree(m->output_norm); cudaFree(m->output.alloc);
@@ -405,8 +426,7 @@ struct b200_ctx {
     float * att = nullptr;      // kqv_merged_cont [n_head*hd]
     float * ffh = nullptr;      // silu(gate)*up [n_ff]
     float * logits = nullptr;   // [n_vocab]
-    float * part_o = nullptr, * part_ml = nullptr;
-    unsigned int * tickets = nullptr;
+    float * S = nullptr;        // attention scores / probabilities [n_head][n_ctx]
     unsigned long long * amax_key = nullptr;
     std::vector<__half *> kc, vc;   // per local layer
     float2 * rope = nullptr;
@@ -451,26 +471,34 @@ template <int EPI>
 static void launch_matvec(b200_ctx * c, const MatvecArgs & a) {
     ProfScope ps(c);
     const size_t smem = act_smem_bytes(a.k, a.act_q8_0);
+    static bool attr_set = false;
+    if (!attr_set) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
     const int max_ctas = c->sm_count * 2;
-    int grid = (a.n_pairs + MV_WARPS - 1) / MV_WARPS;
+    int grid = (a.n_units + MV_WARPS - 1) / MV_WARPS;
     grid = std::max(1, std::min(grid, max_ctas));
     k_matvec<EPI><<<grid, MV_THREADS, smem, c->st>>>(a);
     c->launches++;
 }
 
-static void launch_attention(b200_ctx * c, const AttnArgs & a) {
+template <int GQA>
+static void launch_attention_t(b200_ctx * c, const AttnArgs & a, int n_ctx_pad) {
+    const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
+    k_attn_scores<GQA><<<gs, ATT_THREADS, 0, c->st>>>(a);
+    k_attn_softmax<<<a.n_head, 256, (size_t) (n_ctx_pad / 16) * sizeof(double), c->st>>>(a);
+    const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PV_DIMS));
+    k_attn_pv<GQA><<<gp, PV_DIMS * 16, 0, c->st>>>(a);
+}
+static void launch_attention(b200_ctx * c, const AttnArgs & a, int n_ctx_pad) {
     ProfScope ps(c);
-    if (a.head_dim != 128) throw std::runtime_error("attention kernel is specialised for head_dim 128");
-    const int gqa = a.n_head / a.n_head_kv;
-    const dim3 grid((unsigned) a.n_head_kv, (unsigned) ATT_SPLITS);
-    switch (gqa) {
-        case 1: k_attn<1><<<grid, ATT_THREADS, 0, c->st>>>(a); break;
-        case 2: k_attn<2><<<grid, ATT_THREADS, 0, c->st>>>(a); break;
-        case 4: k_attn<4><<<grid, ATT_THREADS, 0, c->st>>>(a); break;
-        case 8: k_attn<8><<<grid, ATT_THREADS, 0, c->st>>>(a); break;
+    if (a.head_dim != 128) throw std::runtime_error("attention kernels are specialised for head_dim 128");
+    switch (a.n_head / a.n_head_kv) {
+        case 1: launch_attention_t<1>(c, a, n_ctx_pad); break;
+        case 2: launch_attention_t<2>(c, a, n_ctx_pad); break;
+        case 4: launch_attention_t<4>(c, a, n_ctx_pad); break;
+        case 8: launch_attention_t<8>(c, a, n_ctx_pad); break;
         default: throw std::runtime_error("GQA ratio must be 1, 2, 4 or 8");
     }
-    c->launches += 1;
+    c->launches += 3;
 }
 
 ProfScope::ProfScope(b200_ctx * c_) : c(c_) {
@@ -512,7 +540,7 @@ static void enqueue_forward(b200_ctx * c) {
             g_kind = KIND_QKV;
             MatvecArgs a{};
             a.seg[0] = L.wq.m; a.seg[1] = L.wk.m; a.seg[2] = L.wv.m; a.n_seg = 3;
-            a.pair_mode = PAIR_ADJACENT; a.n_pairs = (QD + 2 * KVD) / 2; a.k = E;
+            a.n_units = L.wq.m.n_units + L.wk.m.n_units + L.wv.m.n_units; a.k = E;
             a.x = c->x; a.norm_w = L.attn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
             a.q_out = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
             a.n_q = QD; a.n_k = KVD; a.head_dim = HD; a.kv_dim = KVD; a.rope = c->rope; a.st = c->d_state;
@@ -523,26 +551,26 @@ static void enqueue_forward(b200_ctx * c) {
             g_kind = KIND_ATTN;
             AttnArgs a{};
             a.q = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
-            a.part_o = c->part_o; a.part_ml = c->part_ml; a.tickets = c->tickets; a.out = c->att;
+            a.S = c->S; a.s_stride = c->n_ctx; a.out = c->att;
             a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD;
             a.scale = 1.0f / sqrtf((float) HD);
-            a.st = c->d_state; a.n_kv_override = 0;
-            launch_attention(c, a);
+            a.st = c->d_state; a.n_kv_override = 0; a.round_q_override = 0;
+            launch_attention(c, a, c->n_ctx);
             tap(c, "kqv_merged_cont", il, c->att, (size_t) QD);
         }
         {   // wo + residual
             g_kind = KIND_WO;
             MatvecArgs a{};
-            a.seg[0] = L.wo.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = E / 2; a.k = QD;
+            a.seg[0] = L.wo.m; a.n_seg = 1; a.n_units = L.wo.m.n_units; a.k = QD;
             a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = q80;
             a.out = c->x; a.resid = c->x;
             launch_matvec<EPI_RESID>(c, a);
             tap(c, "ffn_inp", il, c->x, (size_t) E);
         }
-        {   // gate/up
+        {   // gate/up (interleaved virtual matrix) + SiLU*mul
             g_kind = KIND_GATEUP;
             MatvecArgs a{};
-            a.seg[0] = L.gate.m; a.seg[1] = L.up.m; a.n_seg = 2; a.pair_mode = PAIR_ZIP; a.n_pairs = FF; a.k = E;
+            a.seg[0] = L.gateup.m; a.n_seg = 1; a.n_units = L.gateup.m.n_units; a.k = E;
             a.x = c->x; a.norm_w = L.ffn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
             a.out = c->ffh;
             launch_matvec<EPI_SILU>(c, a);
@@ -551,7 +579,7 @@ static void enqueue_forward(b200_ctx * c) {
         {   // down + residual
             g_kind = KIND_DOWN;
             MatvecArgs a{};
-            a.seg[0] = L.down.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = E / 2; a.k = FF;
+            a.seg[0] = L.down.m; a.n_seg = 1; a.n_units = L.down.m.n_units; a.k = FF;
             a.x = c->ffh; a.norm_w = nullptr; a.act_q8_0 = q80;
             a.out = c->x; a.resid = c->x;
             launch_matvec<EPI_RESID>(c, a);
@@ -561,7 +589,7 @@ static void enqueue_forward(b200_ctx * c) {
     if (m.has_head()) {
         g_kind = KIND_HEAD;
         MatvecArgs a{};
-        a.seg[0] = m.output.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = m.n_vocab / 2; a.k = E;
+        a.seg[0] = m.output.m; a.n_seg = 1; a.n_units = m.output.m.n_units; a.k = E;
         a.x = c->x; a.norm_w = m.output_norm; a.eps = m.rms_eps; a.act_q8_0 = m.output.m.type == T_Q8_0;
         a.out = c->logits;
         launch_matvec<EPI_STORE>(c, a);
@@ -589,7 +617,7 @@ static cudaGraphExec_t capture(b200_ctx * c, const std::function<void()> & body)
 }
 static int64_t forward_launch_count(const b200_ctx * c) {
     const b200_model & m = *c->m;
-    return (m.has_embd() ? 1 : 0) + (int64_t) m.layers.size() * 5 + (m.has_head() ? 1 : 0);
+    return (m.has_embd() ? 1 : 0) + (int64_t) m.layers.size() * 7 + (m.has_head() ? 1 : 0);
 }
 
 extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
@@ -611,12 +639,10 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         CU(cudaMalloc(&c->att, (size_t) QD * 4));
         CU(cudaMalloc(&c->ffh, (size_t) m->n_ff * 4));
         CU(cudaMalloc(&c->logits, (size_t) m->n_vocab * 4));
-        CU(cudaMalloc(&c->part_o, (size_t) m->n_head * ATT_SPLITS * HD * 4));
-        CU(cudaMalloc(&c->part_ml, (size_t) m->n_head * ATT_SPLITS * 2 * 4));
+        CU(cudaMalloc(&c->S, (size_t) m->n_head * c->n_ctx * 4));
         CU(cudaMalloc(&c->amax_key, 8));
         CU(cudaMemsetAsync(c->amax_key, 0, 8, c->st));
-        CU(cudaMalloc(&c->tickets, (size_t) m->n_head_kv * 4));
-        CU(cudaMemsetAsync(c->tickets, 0, (size_t) m->n_head_kv * 4, c->st));
+        if (HD != 128) throw std::runtime_error("attention kernels are specialised for head_dim 128");
         for (size_t i = 0; i < m->layers.size(); i++) {
             __half * k = nullptr, * v = nullptr;
             CU(cudaMalloc(&k, (size_t) c->n_ctx * KVD * 2));
@@ -656,7 +682,7 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     for (auto p : c->kc) cudaFree(p);
     for (auto p : c->vc) cudaFree(p);
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->logits);
-    cudaFree(c->part_o); cudaFree(c->part_ml); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
+    cudaFree(c->S); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits);
     cudaStreamDestroy(c->st);
     delete c;
@@ -985,7 +1011,7 @@ extern "C" int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int
         cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
         tmp.sm_count = prop.multiProcessorCount;
         MatvecArgs a{};
-        a.seg[0] = d.m; a.n_seg = 1; a.pair_mode = PAIR_ADJACENT; a.n_pairs = (int) (n_rows / 2); a.k = (int) k;
+        a.seg[0] = d.m; a.n_seg = 1; a.n_units = d.m.n_units; a.k = (int) k;
         a.x = dx.as<float>(); a.norm_w = nullptr; a.act_q8_0 = type == T_Q8_0; a.out = dy.as<float>();
         launch_matvec<EPI_STORE>(&tmp, a);
         CU(cudaGetLastError());
@@ -1031,7 +1057,7 @@ extern "C" int b200_op_rope(float * x, int n_heads, int head_dim, int pos, float
 }
 
 extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, const uint16_t * v_cache, int n_kv,
-                                 int n_head, int n_head_kv, int head_dim, float scale, float * out) {
+                                 int n_head, int n_head_kv, int head_dim, float scale, int round_q, float * out) {
     try {
         require_gpu();
         if (n_kv <= 0) throw std::runtime_error("n_kv must be positive");
@@ -1042,18 +1068,18 @@ extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, cons
         cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
         b200_ctx tmp;
         tmp.st = st; tmp.sm_count = prop.multiProcessorCount;
+        const int n_pad = (n_kv + 31) / 32 * 32;
         DBuf dq((size_t) qd * 4), dk((size_t) n_kv * kvd * 2), dv((size_t) n_kv * kvd * 2), dout((size_t) qd * 4);
-        DBuf po((size_t) n_head * ATT_SPLITS * head_dim * 4), pml((size_t) n_head * ATT_SPLITS * 2 * 4), tk((size_t) n_head_kv * 4);
-        CU(cudaMemsetAsync(tk.p, 0, (size_t) n_head_kv * 4, st));
+        DBuf dS((size_t) n_head * n_pad * 4);
         CU(cudaMemcpyAsync(dq.p, q, (size_t) qd * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(dk.p, k_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(dv.p, v_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
         AttnArgs a{};
         a.q = dq.as<float>(); a.k_cache = dk.as<__half>(); a.v_cache = dv.as<__half>();
-        a.part_o = po.as<float>(); a.part_ml = pml.as<float>(); a.tickets = tk.as<unsigned int>(); a.out = dout.as<float>();
+        a.S = dS.as<float>(); a.s_stride = n_pad; a.out = dout.as<float>();
         a.n_head = n_head; a.n_head_kv = n_head_kv; a.head_dim = head_dim; a.kv_dim = kvd;
-        a.scale = scale; a.st = nullptr; a.n_kv_override = n_kv;
-        launch_attention(&tmp, a);
+        a.scale = scale; a.st = nullptr; a.n_kv_override = n_kv; a.round_q_override = round_q;
+        launch_attention(&tmp, a, n_pad);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out, dout.p, (size_t) qd * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -1,25 +1,31 @@
-// kernels.cuh — hand-written sm_100a kernels for the quantized LLaMA decode path.
+// kernels.cuh — hand-written sm_100a kernels for the quantized LLaMA decode path, BIT-EXACT with the
+// reference's CPU arithmetic (its AVX-512 "native" build; oracle/oracle_port.c is the scalar statement).
 //
-// Arithmetic contract (what "parity" means; the oracle is the reference CPU path):
-//   * activations are quantized exactly as the CPU reference does before every quantized matmul:
-//     Q8_K (256-wide, fp32 scale, -127/max sign trick, round-half-even) for Q4_K/Q5_K/Q6_K weights
-//     (cpp/ggml/src/ggml-quants.c:3593-3630) and Q8_0 (32-wide, fp16 scale) for Q8_0 weights (:936-1000);
-//     NOT the Q8_1 scheme of the reference's CUDA backend (cpp/ggml/src/ggml-cuda/quantize.cu:4-38).
-//   * inside one 256-weight super-block all integer sums are exact, identical to
-//     ggml_vec_dot_q{4,5,6}_K_q8_K (cpp/ggml/src/ggml-quants.c:6832,7400,8037); only the fp32 summation
-//     order across super-blocks differs (parallel tree instead of 8 AVX lanes).
-//   * RMSNorm accumulates x*x in double like ggml_compute_forward_rms_norm_f32 (cpp/ggml/src/ggml.c:11850).
-//   * RoPE takes cos/sin from a host-built table that follows ggml_rope_cache_init (cpp/ggml/src/ggml.c:14017).
-//   * attention follows the DEFAULT (non-flash) route of llm_build_kqv at batch 1
-//     (cpp/src/llama.cpp:8248-8297): f16 K/V widened to f32, f32 q, f32 softmax.
+// Why bit-exact and not "within tolerance": activations are re-quantized to int8 (Q8_K / Q8_0) before every
+// mat-mul. A 1-ulp difference in any upstream fp32 value eventually flips one int8, which moves that layer's
+// output by ~1e-3, which flips dozens of int8 in the next quantization, and within two or three layers the
+// deviation saturates at the quantization-noise floor (~1e-2 of the logits) and stays there through the KV cache.
+// (Measured: DESIGN.md "why bit-exact".) The north-star tolerance of 1e-3 is therefore only reachable by
+// reproducing every fp32 operation of the reference in its exact order:
+//   * quantized dots: integer sums per super-block are exact; the fp32 part follows ggml_vec_dot_q{4,5,6}_K_q8_K's
+//     AVX2 code (cpp/ggml/src/ggml-quants.c:6914-6977, 7487-7560, 8145-8220): 8 lanes, lane m owns bytes 4m..4m+3
+//     of every 32-byte group, acc[m] = fma(d_b, (float) sumi_b[m], acc[m]) sequentially over super-blocks b,
+//     then hsum_float_8 (:47-53). Q8_0 follows ggml_vec_dot_q8_0_q8_0 / tinyBLAS_Q0_AVX (:5361-5382).
+//   * RMSNorm: double accumulation (cpp/ggml/src/ggml.c:11850-11896).
+//   * RoPE: cos/sin from a host-built table (ggml_rope_cache_init, cpp/ggml/src/ggml.c:14017-14031).
+//   * attention (default route, cpp/src/llama.cpp:8248-8297): K.q and V.p as tinyBLAS<16> computes them
+//     (cpp/ggml/src/llamafile/sgemm.cpp:408-430: 16 lanes, fma chain over k, _mm512_reduce_add_ps), batch>1 K.q as
+//     ggml_vec_dot_f16 (cpp/ggml/src/ggml.c:2038-2075), softmax with the ggml_v_expf polynomial (:2447-2472).
+//   * SiLU: ggml_v_silu (cpp/ggml/src/ggml.c:2475-2482).
 //
-// Weight layout in HBM ("planes"): every matrix keeps its GGUF block bytes but split per field so that
-// each plane is a dense 16-byte-aligned stream per row (Q4_K's 144 B and Q6_K's 210 B blocks are not):
-//   Q4_K: p0 qs[n][nb*128]  p1 scales[n][nb*12]  p2 dm(half2)[n][nb]
-//   Q5_K: p0 qs[n][nb*128]  p1 scales[n][nb*12]  p2 dm(half2)[n][nb]   p3 qh[n][nb*32]
-//   Q6_K: p0 ql[n][nb*128]  p1 qh[n][nb*64]      p2 scales(i8)[n][nb*16] p3 d(half)[n][nb]
-//   Q8_0: p0 qs[n][k]       p1 d(half)[n][k/32]
-// Total bytes are exactly the GGUF tensor bytes (the algorithmic bytes of SURVEY.md §8d).
+// HBM layout ("tiles"): a matrix keeps exactly its GGUF bytes, re-tiled once at load. Blocks are numbered
+// f = row*nb + block_in_row; tile T = f/32 holds 32 consecutive blocks, one per lane, every field transposed so
+// that a warp-wide load of one field is a dense 128/512-byte stream:
+//   Q4_K: p0 qs uint4[8][32] (4096 B)  p1 u32[4][32] = 12 scale bytes + (d,dmin) (512 B)
+//   Q5_K: same + p2 qh uint4[2][32] (1024 B)
+//   Q6_K: p0 ql uint4[8][32]  p2 qh uint4[4][32] (2048 B)  p1 scales u32[4][32]  p3 d u16[32] (64 B)
+//   Q8_0: p0 qs uint4[2][32] (1024 B)  p3 d u16[32]      (blocks of 32 weights)
+// ffn_gate and ffn_up are interleaved row by row into one virtual matrix (row 2r = gate r, 2r+1 = up r).
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -29,10 +35,13 @@ namespace b200 {
 
 enum { T_F32 = 0, T_F16 = 1, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
 
-struct QMat {
+struct TMat {
     int type = 0;
-    int n_rows = 0;
-    int k = 0;
+    int n_rows = 0;       // (virtual) rows
+    int nb = 0;           // blocks per row: 256-weight super-blocks, or 32-weight blocks for Q8_0
+    int rows_unit = 0;    // rows per warp work unit (even; rows_unit*nb is a multiple of 32)
+    int tiles_unit = 0;   // = rows_unit*nb/32
+    int n_units = 0;      // = n_rows/rows_unit
     const uint8_t * p0 = nullptr;
     const uint8_t * p1 = nullptr;
     const uint8_t * p2 = nullptr;
@@ -43,18 +52,16 @@ struct QMat {
 struct DecodeState {
     int32_t token;     // input token id of this step
     int32_t pos;       // its position == KV slot it is written to
-    int32_t round_q;   // 1: round q to f16 before K.q (reference behaviour for batch > 1, ggml.c:12345-12371)
+    int32_t round_q;   // 1: batch > 1 arithmetic for K.q (q rounded to f16, ggml_vec_dot_f16 order)
     int32_t step;      // greedy loop: index into out_tokens
 };
 
 enum { EPI_STORE = 0, EPI_RESID = 1, EPI_QKV = 2, EPI_SILU = 3 };
-enum { PAIR_ADJACENT = 0, PAIR_ZIP = 1 };
 
 struct MatvecArgs {
-    QMat seg[3];
+    TMat seg[3];
     int n_seg;
-    int pair_mode;
-    int n_pairs;
+    int n_units;               // total over segments
     int k;
     // prologue: x f32[k]; optional RMSNorm (norm_w != nullptr) then activation quantization into smem
     const float * x;
@@ -75,25 +82,23 @@ struct MatvecArgs {
 
 static constexpr int MV_THREADS = 256;
 static constexpr int MV_WARPS   = MV_THREADS / 32;
+static constexpr int STG_STRIDE = 33;                       // padded row stride of the per-warp staging array
+static constexpr int STG_WORDS  = 14 * STG_STRIDE;          // d, s[8], dmin, prod[4]
+static constexpr int MAX_CHAIN_SLOTS = 12;                  // rows_unit(<=32) * chains(<=12) / 32
 
 // ------------------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ldg_stream_v4(const void * p) {
-    // streaming 16-byte load: read-only path, do not pollute L1 (weights are touched once per token)
-    uint4 r;
+    uint4 r;   // streaming 16-byte load: read-only path, no L1 allocation (weights are touched once per token)
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint32_t ldg_u32(const void * p) { return __ldg((const uint32_t *) p); }
 __device__ __forceinline__ uint32_t ldg_u16(const void * p) { return __ldg((const uint16_t *) p); }
+__device__ __forceinline__ float h16_to_f32(uint32_t bits) { return __half2float(__ushort_as_half((unsigned short) bits)); }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -104,51 +109,68 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ int dot16(const uint4 & w, const int4 & a, int acc) {
-    acc = __dp4a((int) w.x, a.x, acc);
-    acc = __dp4a((int) w.y, a.y, acc);
-    acc = __dp4a((int) w.z, a.z, acc);
-    acc = __dp4a((int) w.w, a.w, acc);
-    return acc;
+__device__ __forceinline__ uint32_t word_of(const uint4 & v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ int      word_of(const int4 & v, int i)  { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+// ggml_v_expf, AVX-512 variant (cpp/ggml/src/ggml.c:2447-2472), one lane. All steps are element-wise IEEE ops.
+__device__ __forceinline__ float v_expf(float x) {
+    const float r = 0x1.8p23f;
+    const float z = __fmaf_rn(x, 0x1.715476p+0f, r);
+    const float n = __fsub_rn(z, r);
+    const float b = __fmaf_rn(-n, 0x1.7f7d1cp-20f, __fmaf_rn(-n, 0x1.62e4p-1f, x));
+    const bool big = fabsf(n) > 192.f;
+    const float u = __fmul_rn(b, b);
+    const float j = __fmaf_rn(__fmaf_rn(__fmaf_rn(0x1.0e4020p-7f, b, 0x1.573e2ep-5f), u,
+                                         __fmaf_rn(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)),
+                              u, __fmaf_rn(0x1.ffffecp-1f, b, 1.0f));
+    if (big) return n <= 0.f ? 0.f : INFINITY;
+    return ldexpf(j, (int) n);                                          // _mm512_scalef_ps: exact scaling by 2^n
 }
-__device__ __forceinline__ uint4 and4(const uint4 & v, uint32_t m) { return make_uint4(v.x & m, v.y & m, v.z & m, v.w & m); }
-__device__ __forceinline__ uint4 shr4(const uint4 & v, int s)      { return make_uint4(v.x >> s, v.y >> s, v.z >> s, v.w >> s); }
-__device__ __forceinline__ uint4 shl4(const uint4 & v, int s)      { return make_uint4(v.x << s, v.y << s, v.z << s, v.w << s); }
-__device__ __forceinline__ uint4 or4(const uint4 & a, const uint4 & b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+// ggml_v_silu (cpp/ggml/src/ggml.c:2475-2482)
+__device__ __forceinline__ float silu_exact(float x) {
+    return __fdiv_rn(x, __fadd_rn(1.0f, v_expf(__fsub_rn(0.0f, x))));
+}
+// _mm512_reduce_add_ps over 16 consecutive lanes of a half-warp (lane & 15 = element), GCC's expansion:
+// (a[8+i]+a[i]) -> (t[4+i]+t[i]) -> (u0+u2, u1+u3) -> sum. Result valid in the lane with (lane & 15) == 0.
+__device__ __forceinline__ float reduce_add16_shfl(float v) {
+    v = __fadd_rn(__shfl_down_sync(0xffffffffu, v, 8, 16), v);
+    v = __fadd_rn(__shfl_down_sync(0xffffffffu, v, 4, 16), v);
+    v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 2, 16));
+    v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1, 16));
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------------------------
-// activation quantization (block-cooperative, result in shared memory)
-//   smem layout: int8 q[k] | float dx[k/256 or k/32] | int16 bsums[k/16] (Q8_K only)
+// activation quantization (block-cooperative, result in shared memory, TRANSPOSED for the tile kernels)
+//   Q8_K: qT[slot 0..15][nb] x 16 B | dx[nb] f32 | bp[2][nb] int4 = sums of the 8 sub-blocks of 32
+//   Q8_0: qT[half 0..1][nb32] x 16 B | dx[nb32] f32 (already rounded through fp16)
 // ------------------------------------------------------------------------------------------------------------
 struct ActSmem {
-    int8_t  * q;
-    float   * dx;
-    int16_t * bsums;
+    int8_t * q;
+    float  * dx;
+    int    * bp;
 };
 __host__ __device__ __forceinline__ size_t act_smem_bytes(int k, int act_q8_0) {
-    size_t n = (size_t) k;                                    // q
+    size_t n = (size_t) k;
+    n += (size_t) (act_q8_0 ? k / 32 : k / 256) * 4;
     n = (n + 15) / 16 * 16;
-    n += (size_t) (act_q8_0 ? k / 32 : k / 256) * 4;         // dx
-    n = (n + 15) / 16 * 16;
-    if (!act_q8_0) n += (size_t) (k / 16) * 2;               // bsums
+    if (!act_q8_0) n += (size_t) (k / 256) * 32;
     return (n + 15) / 16 * 16;
 }
 __device__ __forceinline__ ActSmem act_smem_carve(uint8_t * base, int k, int act_q8_0) {
     ActSmem a;
     a.q = (int8_t *) base;
-    size_t off = ((size_t) k + 15) / 16 * 16;
-    a.dx = (float *) (base + off);
-    off += (size_t) (act_q8_0 ? k / 32 : k / 256) * 4;
+    a.dx = (float *) (base + k);
+    size_t off = (size_t) k + (size_t) (act_q8_0 ? k / 32 : k / 256) * 4;
     off = (off + 15) / 16 * 16;
-    a.bsums = (int16_t *) (base + off);
+    a.bp = (int *) (base + off);
     return a;
 }
 
-// One warp quantizes 256 consecutive values (8 per lane) to Q8_K. Restates quantize_row_q8_K_ref
-// (cpp/ggml/src/ggml-quants.c:3593-3630): `max` is the FIRST element of largest magnitude (strict >),
-// iscale = -127/max, q = min(127, round_half_even(iscale*x)), d = 1/iscale, bsums over groups of 16.
-__device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, int8_t * q_out /* 256 */,
-                                               float * d_out, int16_t * bsums_out /* 16 */) {
+// One warp quantizes 256 consecutive values (8 per lane) to Q8_K — quantize_row_q8_K_ref
+// (cpp/ggml/src/ggml-quants.c:3593-3630): `max` is the FIRST element of largest magnitude, iscale = -127/max,
+// q = min(127, round_half_even(iscale*x)), d = 1/iscale.
+__device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, int b, int nb, const ActSmem & A) {
     float amax = 0.f, mval = 0.f;
     int   midx = 0;
 #pragma unroll
@@ -178,17 +200,16 @@ __device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, in
         }
         d = __fdiv_rn(1.f, iscale);
     }
-    *reinterpret_cast<uint2 *>(q_out + lane * 8) = make_uint2(w0, w1);
-    const int s16 = s8 + __shfl_xor_sync(0xffffffffu, s8, 1);
-    if ((lane & 1) == 0) bsums_out[lane >> 1] = (int16_t) s16;
-    if (lane == 0) *d_out = d;
+    // element e = lane*8 + i of the block lives in slot e/16, byte e%16
+    *reinterpret_cast<uint2 *>(A.q + ((size_t) ((lane >> 1) * nb + b)) * 16 + (lane & 1) * 8) = make_uint2(w0, w1);
+    int s32 = s8 + __shfl_xor_sync(0xffffffffu, s8, 1);
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 2);                 // sum of sub-block lane/4 (32 values)
+    if ((lane & 3) == 0) { const int s = lane >> 2; A.bp[((size_t) ((s >> 2) * nb + b)) * 4 + (s & 3)] = s32; }
+    if (lane == 0) A.dx[b] = d;
 }
-
-// One warp quantizes 256 consecutive values = 8 Q8_0 blocks of 32 (4 lanes each). Restates the AVX path of
-// quantize_row_q8_0 (cpp/ggml/src/ggml-quants.c:936-1000): d = amax/127 stored as fp16, id = 127/amax,
-// q = round_half_even(x*id). The dot product later uses the fp16-rounded d.
-__device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, int8_t * q_out /* 256 */,
-                                                float * d_out /* 8 */) {
+// One warp quantizes 256 consecutive values = 8 Q8_0 blocks of 32 — AVX path of quantize_row_q8_0
+// (cpp/ggml/src/ggml-quants.c:936-1000): d = amax/127 kept as fp16, id = 127/amax, q = round_half_even(x*id).
+__device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, int b256, int nb32, const ActSmem & A) {
     float amax = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
@@ -203,17 +224,16 @@ __device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, i
         if (i < 4) w0 |= ((uint32_t) (qi & 0xff)) << (8 * i);
         else       w1 |= ((uint32_t) (qi & 0xff)) << (8 * (i - 4));
     }
-    *reinterpret_cast<uint2 *>(q_out + lane * 8) = make_uint2(w0, w1);
-    if ((lane & 3) == 0) d_out[lane >> 2] = __half2float(__float2half_rn(d));
+    const int blk = b256 * 8 + (lane >> 2);                       // 32-block; element offset (lane&3)*8 inside it
+    *reinterpret_cast<uint2 *>(A.q + ((size_t) (((lane >> 1) & 1) * nb32 + blk)) * 16 + (lane & 1) * 8) = make_uint2(w0, w1);
+    if ((lane & 3) == 0) A.dx[blk] = __half2float(__float2half_rn(d));
 }
 
 // Block-cooperative prologue: optional RMSNorm(+weight) then activation quantization into shared memory.
-// RMSNorm restates ggml_compute_forward_rms_norm_f32 (cpp/ggml/src/ggml.c:11850-11896: double accumulation
-// of float x*x, scale = 1/sqrtf(mean+eps), y = x*scale) followed by the separate ggml_mul with the norm
-// weight (cpp/src/llama.cpp:7928-7958).
+// RMSNorm = ggml_compute_forward_rms_norm_f32 (double sum of float x*x, scale = 1/sqrtf(mean+eps), y = x*scale)
+// followed by the separate ggml_mul with the norm weight (cpp/src/llama.cpp:7928-7958).
 __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, const float * __restrict__ norm_w,
-                                                  float eps, int k, int act_q8_0, const ActSmem & A,
-                                                  float * red_smem /* >= 16 doubles */) {
+                                                  float eps, int k, int act_q8_0, const ActSmem & A, double * red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
     float scale = 1.f;
@@ -227,7 +247,6 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
             s += (double) __fmul_rn(v.w, v.w);
         }
         s = warp_sum_d(s);
-        double * red = reinterpret_cast<double *>(red_smem);
         if (lane == 0) red[warp] = s;
         __syncthreads();
         double tot = 0.0;
@@ -248,284 +267,271 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fmul_rn(v[i], scale), ww[i]);
         }
-        if (act_q8_0) q80_blocks_warp(v, lane, A.q + b * 256, A.dx + b * 8);
-        else          q8k_block_warp(v, lane, A.q + b * 256, A.dx + b, A.bsums + b * 16);
+        if (act_q8_0) q80_blocks_warp(v, lane, b, k / 32, A);
+        else          q8k_block_warp(v, lane, b, n256, A);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// per-type dot products: R rows at a time against the quantized activation vector in shared memory.
-// Each returns per-lane partial sums in acc[]; the caller warp-reduces.
+// per-type block arithmetic: ONE lane = ONE block. Produces the exact per-block integers the reference's AVX2
+// lanes hold (s[m] = the m-th int32 lane of `sumi`, prod[l] = the l-th lane of the mins product) and the
+// per-block fp32 coefficients, and writes them to the warp's staging array stg[k*STG_STRIDE + lane].
+//   k = 0: d_b   1..8: s[0..7]   9: dmin_b   10..13: prod[0..3] (Q4_K) / 10: sum of prod (Q5_K)
 // ------------------------------------------------------------------------------------------------------------
-struct RowPtrs { const uint8_t * p0; const uint8_t * p1; const uint8_t * p2; const uint8_t * p3; };
+__device__ __forceinline__ int4 lds_act(const ActSmem & A, int slot, int nb, int bi) {
+    return *reinterpret_cast<const int4 *>(A.q + ((size_t) (slot * nb + bi)) * 16);
+}
 
-// scale / min bytes of sub-blocks 2j and 2j+1 from the 12 packed bytes (format: get_scale_min_k4,
-// cpp/ggml/src/ggml-quants.c:1891-1898); returns sc_lo | sc_hi<<8 in .x and m_lo | m_hi<<8 in .y
-__device__ __forceinline__ uint2 k4_scales_pair(uint32_t s0, uint32_t s1, uint32_t s2, int j) {
-    const uint32_t sc_a = s0 & 0x3f3f3f3fu;
-    const uint32_t m_a  = s1 & 0x3f3f3f3fu;
+template <bool Q5>
+__device__ __forceinline__ void block_q45k(const TMat & m, size_t T, int lane, int bi, const ActSmem & A, uint32_t * stg) {
+    const uint4 * qp = reinterpret_cast<const uint4 *>(m.p0 + T * 4096) + lane;
+    uint4 w[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) w[c] = ldg_stream_v4(qp + c * 32);
+    uint4 qh[2];
+    if (Q5) {
+        const uint4 * hp = reinterpret_cast<const uint4 *>(m.p2 + T * 1024) + lane;
+        qh[0] = ldg_stream_v4(hp); qh[1] = ldg_stream_v4(hp + 32);
+    }
+    const uint32_t * sd = reinterpret_cast<const uint32_t *>(m.p1 + T * 512) + lane;
+    const uint32_t s0 = ldg_u32(sd), s1 = ldg_u32(sd + 32), s2 = ldg_u32(sd + 64), dmw = ldg_u32(sd + 96);
+    // the 8 scale bytes and 8 min bytes (get_scale_min_k4 packing, cpp/ggml/src/ggml-quants.c:1891-1898)
+    const uint32_t sc_a = s0 & 0x3f3f3f3fu, m_a = s1 & 0x3f3f3f3fu;
     const uint32_t sc_b = (s2 & 0x0f0f0f0fu) | (((s0 >> 6) & 0x03030303u) << 4);
     const uint32_t m_b  = ((s2 >> 4) & 0x0f0f0f0fu) | (((s1 >> 6) & 0x03030303u) << 4);
-    const uint32_t scw = j < 2 ? sc_a : sc_b;
-    const uint32_t mw  = j < 2 ? m_a : m_b;
-    const int sh = (j & 1) * 16;
-    return make_uint2((scw >> sh) & 0xffffu, (mw >> sh) & 0xffffu);
-}
-
-template <int R, int UNR, bool Q5>
-__device__ __forceinline__ void dot_q45k(const RowPtrs (&rp)[R], int nb, int lane, const ActSmem & A, float (&acc)[R]) {
-    // unit = one 16-byte chunk of qs: sub-block pair j, half h -> 16 low-nibble + 16 high-nibble weights
-    const int n_units = nb * 8;
-    const int cc = lane & 7, j = cc >> 1, h = cc & 1;
-    const int a_off = 64 * j + 16 * h;
-    for (int u0 = lane; u0 < n_units; u0 += 32 * UNR) {
-        uint4    w[UNR][R];
-        uint4    qh[UNR][R];
-        uint32_t s0[UNR][R], s1[UNR][R], s2[UNR][R], dmv[UNR][R];
+    const int nb = m.nb;
+    int s[8];
 #pragma unroll
-        for (int t = 0; t < UNR; t++) {
-            const int u = u0 + 32 * t;
-            if (u < n_units) {
-                const int b = u >> 3;
+    for (int i = 0; i < 8; i++) s[i] = 0;
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    w[t][r]   = ldg_stream_v4(rp[r].p0 + (size_t) u * 16);
-                    s0[t][r]  = ldg_u32(rp[r].p1 + b * 12);
-                    s1[t][r]  = ldg_u32(rp[r].p1 + b * 12 + 4);
-                    s2[t][r]  = ldg_u32(rp[r].p1 + b * 12 + 8);
-                    dmv[t][r] = ldg_u32(rp[r].p2 + b * 4);
-                    if (Q5) qh[t][r] = ldg_stream_v4(rp[r].p3 + b * 32 + 16 * h);
+    for (int j = 0; j < 4; j++) {
+        const uint32_t scw = j < 2 ? sc_a : sc_b;
+        const int sc_lo = (int) ((scw >> ((j & 1) * 16)) & 0xff), sc_hi = (int) ((scw >> ((j & 1) * 16 + 8)) & 0xff);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int4 alo = lds_act(A, 4 * j + h, nb, bi);
+            const int4 ahi = lds_act(A, 4 * j + 2 + h, nb, bi);
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                const uint32_t W = word_of(w[2 * j + h], wi);
+                uint32_t lo = W & 0x0f0f0f0fu, hi = (W >> 4) & 0x0f0f0f0fu;
+                if (Q5) {
+                    // qh bit 2j -> +16 on the low-nibble weight, bit 2j+1 -> +16 on the high-nibble one
+                    const uint32_t H = word_of(qh[h], wi);
+                    lo |= ((H >> (2 * j)) & 0x01010101u) << 4;
+                    hi |= ((H >> (2 * j + 1)) & 0x01010101u) << 4;
                 }
+                const int L = __dp4a((int) lo, word_of(alo, wi), 0);
+                const int Hh = __dp4a((int) hi, word_of(ahi, wi), 0);
+                s[4 * h + wi] += sc_lo * L + sc_hi * Hh;
             }
         }
+    }
+    // mins: lane l of the reference's _mm_madd_epi16(mins, q8s) = m[2l]*bp[2l] + m[2l+1]*bp[2l+1]
+    const int4 bp0 = *reinterpret_cast<const int4 *>(A.bp + ((size_t) (0 * nb + bi)) * 4);
+    const int4 bp1 = *reinterpret_cast<const int4 *>(A.bp + ((size_t) (1 * nb + bi)) * 4);
+    const int p0 = (int) (m_a & 0xff) * bp0.x + (int) ((m_a >> 8) & 0xff) * bp0.y;
+    const int p1 = (int) ((m_a >> 16) & 0xff) * bp0.z + (int) (m_a >> 24) * bp0.w;
+    const int p2 = (int) (m_b & 0xff) * bp1.x + (int) ((m_b >> 8) & 0xff) * bp1.y;
+    const int p3 = (int) ((m_b >> 16) & 0xff) * bp1.z + (int) (m_b >> 24) * bp1.w;
+    const float yd = A.dx[bi];
+    const __half2 dmh = *reinterpret_cast<const __half2 *>(&dmw);
+    const float d    = __fmul_rn(yd, __low2float(dmh));           // y[i].d * fp16(x[i].d)
+    const float dmin = __fmul_rn(-yd, __high2float(dmh));         // -y[i].d * fp16(x[i].dmin)
+    stg[0 * STG_STRIDE + lane] = __float_as_uint(d);
 #pragma unroll
-        for (int t = 0; t < UNR; t++) {
-            const int u = u0 + 32 * t;
-            if (u < n_units) {
-                const int b = u >> 3;
-                const int4 alo = *reinterpret_cast<const int4 *>(A.q + b * 256 + a_off);
-                const int4 ahi = *reinterpret_cast<const int4 *>(A.q + b * 256 + a_off + 32);
-                const float dx = A.dx[b];
-                const int bs_lo = A.bsums[b * 16 + 4 * j + h];
-                const int bs_hi = A.bsums[b * 16 + 4 * j + 2 + h];
+    for (int i = 0; i < 8; i++) stg[(1 + i) * STG_STRIDE + lane] = (uint32_t) s[i];
+    stg[9 * STG_STRIDE + lane] = __float_as_uint(dmin);
+    if (Q5) {
+        stg[10 * STG_STRIDE + lane] = (uint32_t) (p0 + p1 + p2 + p3);
+    } else {
+        stg[10 * STG_STRIDE + lane] = (uint32_t) p0; stg[11 * STG_STRIDE + lane] = (uint32_t) p1;
+        stg[12 * STG_STRIDE + lane] = (uint32_t) p2; stg[13 * STG_STRIDE + lane] = (uint32_t) p3;
+    }
+}
+
+// q (0..63 per byte) -> q - 32 as signed bytes, without inter-byte borrows
+__device__ __forceinline__ uint32_t sub32_bytes(uint32_t q) { return ((q | 0x80808080u) - 0x20202020u) ^ 0x80808080u; }
+
+__device__ __forceinline__ void block_q6k(const TMat & m, size_t T, int lane, int bi, const ActSmem & A, uint32_t * stg) {
+    const uint4 * lp = reinterpret_cast<const uint4 *>(m.p0 + T * 4096) + lane;
+    const uint4 * hp = reinterpret_cast<const uint4 *>(m.p2 + T * 2048) + lane;
+    uint4 ql[8], qh[4];
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    uint4 lo = and4(w[t][r], 0x0f0f0f0fu);
-                    uint4 hi = and4(shr4(w[t][r], 4), 0x0f0f0f0fu);
-                    if (Q5) {
-                        // qh bit 2j -> +16 on the low-nibble weights, bit 2j+1 -> +16 on the high-nibble ones
-                        // (dequantize_row_q5_K, cpp/ggml/src/ggml-quants.c:2756-2782)
-                        lo = or4(lo, shl4(and4(shr4(qh[t][r], 2 * j), 0x01010101u), 4));
-                        hi = or4(hi, shl4(and4(shr4(qh[t][r], 2 * j + 1), 0x01010101u), 4));
-                    }
-                    const int isum_lo = dot16(lo, alo, 0);
-                    const int isum_hi = dot16(hi, ahi, 0);
-                    const uint2 sm = k4_scales_pair(s0[t][r], s1[t][r], s2[t][r], j);
-                    const int isc = (int) (sm.x & 0xff) * isum_lo + (int) (sm.x >> 8) * isum_hi;
-                    const int ism = (int) (sm.y & 0xff) * bs_lo + (int) (sm.y >> 8) * bs_hi;
-                    const __half2 dmh = *reinterpret_cast<const __half2 *>(&dmv[t][r]);
-                    const float d    = __low2float(dmh) * dx;
-                    const float dmin = __high2float(dmh) * dx;
-                    acc[r] = fmaf(d, (float) isc, acc[r]);
-                    acc[r] = fmaf(-dmin, (float) ism, acc[r]);
+    for (int c = 0; c < 8; c++) ql[c] = ldg_stream_v4(lp + c * 32);
+#pragma unroll
+    for (int c = 0; c < 4; c++) qh[c] = ldg_stream_v4(hp + c * 32);
+    const uint32_t * sp = reinterpret_cast<const uint32_t *>(m.p1 + T * 512) + lane;
+    uint32_t sw[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) sw[i] = ldg_u32(sp + i * 32);
+    const float dw = h16_to_f32(ldg_u16(m.p3 + T * 64 + lane * 2));
+    const int nb = m.nb;
+    int s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = 0;
+    // layout of a super-block: dequantize_row_q6_K (cpp/ggml/src/ggml-quants.c:2970-3000); half n, group g of 32
+    // weights: ql byte 64n + 32(g&1) + l, nibble g>>1; qh byte 32n + l, bits 2g..2g+1; scale 8n + 2g + l/16
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+#pragma unroll
+            for (int mq = 0; mq < 2; mq++) {
+                const int si = 8 * n + 2 * g + mq;
+                const int sc = (int) (int8_t) ((sw[si >> 2] >> ((si & 3) * 8)) & 0xff);
+                const int4 a = lds_act(A, 8 * n + 2 * g + mq, nb, bi);
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++) {
+                    const uint32_t QL = word_of(ql[4 * n + 2 * (g & 1) + mq], wi);
+                    const uint32_t QH = word_of(qh[2 * n + mq], wi);
+                    const uint32_t lo = (g >> 1) ? ((QL >> 4) & 0x0f0f0f0fu) : (QL & 0x0f0f0f0fu);
+                    const uint32_t q  = lo | (((QH >> (2 * g)) & 0x03030303u) << 4);
+                    s[4 * mq + wi] += sc * __dp4a((int) sub32_bytes(q), word_of(a, wi), 0);
                 }
             }
         }
     }
+    const float d = __fmul_rn(A.dx[bi], dw);                       // y[i].d * fp16(x[i].d)
+    stg[0 * STG_STRIDE + lane] = __float_as_uint(d);
+#pragma unroll
+    for (int i = 0; i < 8; i++) stg[(1 + i) * STG_STRIDE + lane] = (uint32_t) s[i];
 }
 
-template <int R, int UNR>
-__device__ __forceinline__ void dot_q6k(const RowPtrs (&rp)[R], int nb, int lane, const ActSmem & A, float (&acc)[R]) {
-    // unit = 64 weights: half n of the super-block, 16-lane slice uu: ql[64n+16uu], ql[64n+32+16uu], qh[32n+16uu]
-    // (layout: dequantize_row_q6_K, cpp/ggml/src/ggml-quants.c:2970-3000)
-    const int n_units = nb * 4;
-    const int n = (lane >> 1) & 1, uu = lane & 1;
-    for (int u0 = lane; u0 < n_units; u0 += 32 * UNR) {
-        uint4    ql0[UNR][R], ql1[UNR][R], qh[UNR][R];
-        uint32_t sc4[UNR][R][2];
-        uint32_t dv[UNR][R];
+__device__ __forceinline__ void block_q80(const TMat & m, size_t T, int lane, int bi, const ActSmem & A, uint32_t * stg) {
+    const uint4 * qp = reinterpret_cast<const uint4 *>(m.p0 + T * 1024) + lane;
+    const uint4 w0 = ldg_stream_v4(qp), w1 = ldg_stream_v4(qp + 32);
+    const float dw = h16_to_f32(ldg_u16(m.p3 + T * 64 + lane * 2));
+    const int4 a0 = lds_act(A, 0, m.nb, bi), a1 = lds_act(A, 1, m.nb, bi);
+    const float d = __fmul_rn(dw, A.dx[bi]);                       // fp16(x.d) * fp16(y.d)
+    stg[0 * STG_STRIDE + lane] = __float_as_uint(d);
 #pragma unroll
-        for (int t = 0; t < UNR; t++) {
-            const int u = u0 + 32 * t;
-            if (u < n_units) {
-                const int b = u >> 2;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    ql0[t][r] = ldg_stream_v4(rp[r].p0 + (size_t) b * 128 + 64 * n + 16 * uu);
-                    ql1[t][r] = ldg_stream_v4(rp[r].p0 + (size_t) b * 128 + 64 * n + 32 + 16 * uu);
-                    qh[t][r]  = ldg_stream_v4(rp[r].p1 + (size_t) b * 64 + 32 * n + 16 * uu);
-                    // the 8 int8 scales of half n (two aligned words); group g uses byte 2g+uu
-                    sc4[t][r][0] = ldg_u32(rp[r].p2 + b * 16 + 8 * n);
-                    sc4[t][r][1] = ldg_u32(rp[r].p2 + b * 16 + 8 * n + 4);
-                    dv[t][r]     = ldg_u16(rp[r].p3 + b * 2);
-                }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < UNR; t++) {
-            const int u = u0 + 32 * t;
-            if (u < n_units) {
-                const int b = u >> 2;
-                const int8_t * ab = A.q + b * 256 + 128 * n + 16 * uu;
-                const int4 a0 = *reinterpret_cast<const int4 *>(ab);
-                const int4 a1 = *reinterpret_cast<const int4 *>(ab + 32);
-                const int4 a2 = *reinterpret_cast<const int4 *>(ab + 64);
-                const int4 a3 = *reinterpret_cast<const int4 *>(ab + 96);
-                const float dx = A.dx[b];
-                const int16_t * bs = A.bsums + b * 16 + 8 * n + uu;
-                const int bs0 = bs[0], bs1 = bs[2], bs2 = bs[4], bs3 = bs[6];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const uint4 h = qh[t][r];
-                    const uint4 q0 = or4(and4(ql0[t][r], 0x0f0f0f0fu), and4(shl4(h, 4), 0x30303030u));
-                    const uint4 q1 = or4(and4(ql1[t][r], 0x0f0f0f0fu), and4(shl4(h, 2), 0x30303030u));
-                    const uint4 q2 = or4(and4(shr4(ql0[t][r], 4), 0x0f0f0f0fu), and4(h, 0x30303030u));
-                    const uint4 q3 = or4(and4(shr4(ql1[t][r], 4), 0x0f0f0f0fu), and4(shr4(h, 2), 0x30303030u));
-                    const int d0 = dot16(q0, a0, 0) - 32 * bs0;
-                    const int d1 = dot16(q1, a1, 0) - 32 * bs1;
-                    const int d2 = dot16(q2, a2, 0) - 32 * bs2;
-                    const int d3 = dot16(q3, a3, 0) - 32 * bs3;
-                    const uint32_t sa = sc4[t][r][0], sb = sc4[t][r][1];
-                    const int sh = 8 * uu;
-                    const int c0 = (int) (int8_t) ((sa >> sh) & 0xff);
-                    const int c1 = (int) (int8_t) ((sa >> (sh + 16)) & 0xff);
-                    const int c2 = (int) (int8_t) ((sb >> sh) & 0xff);
-                    const int c3 = (int) (int8_t) ((sb >> (sh + 16)) & 0xff);
-                    const int isum = c0 * d0 + c1 * d1 + c2 * d2 + c3 * d3;
-                    const float d = __half2float(__ushort_as_half((unsigned short) dv[t][r])) * dx;
-                    acc[r] = fmaf(d, (float) isum, acc[r]);
-                }
-            }
-        }
+    for (int wi = 0; wi < 4; wi++) {
+        stg[(1 + wi) * STG_STRIDE + lane] = (uint32_t) __dp4a((int) word_of(w0, wi), word_of(a0, wi), 0);
+        stg[(5 + wi) * STG_STRIDE + lane] = (uint32_t) __dp4a((int) word_of(w1, wi), word_of(a1, wi), 0);
     }
 }
 
-template <int R, int UNR>
-__device__ __forceinline__ void dot_q80(const RowPtrs (&rp)[R], int nb32, int lane, const ActSmem & A, float (&acc)[R]) {
-    // unit = 16 int8 weights (half a Q8_0 block); ggml_vec_dot_q8_0_q8_0 (cpp/ggml/src/ggml-quants.c:5227)
-    const int n_units = nb32 * 2;
-    for (int u0 = lane; u0 < n_units; u0 += 32 * UNR) {
-        uint4    w[UNR][R];
-        uint32_t dv[UNR][R];
-#pragma unroll
-        for (int t = 0; t < UNR; t++) {
-            const int u = u0 + 32 * t;
-            if (u < n_units) {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    w[t][r]  = ldg_stream_v4(rp[r].p0 + (size_t) u * 16);
-                    dv[t][r] = ldg_u16(rp[r].p1 + (u >> 1) * 2);
-                }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < UNR; t++) {
-            const int u = u0 + 32 * t;
-            if (u < n_units) {
-                const int4 a = *reinterpret_cast<const int4 *>(A.q + u * 16);
-                const float dx = A.dx[u >> 1];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int isum = dot16(w[t][r], a, 0);
-                    const float d = __half2float(__ushort_as_half((unsigned short) dv[t][r])) * dx;
-                    acc[r] = fmaf(d, (float) isum, acc[r]);
-                }
-            }
-        }
-    }
-}
+__device__ __forceinline__ int chains_of(int type) { return type == T_Q4_K ? 12 : type == T_Q5_K ? 9 : 8; }
 
-__device__ __forceinline__ RowPtrs row_ptrs(int type, int kk, const uint8_t * p0, const uint8_t * p1, const uint8_t * p2,
-                                            const uint8_t * p3, int row) {
-    RowPtrs r;
-    const size_t k = (size_t) kk;
-    const size_t nb = k / 256;
-    switch (type) {
-        case T_Q4_K: r.p0 = p0 + row * nb * 128; r.p1 = p1 + row * nb * 12; r.p2 = p2 + row * nb * 4;  r.p3 = nullptr; break;
-        case T_Q5_K: r.p0 = p0 + row * nb * 128; r.p1 = p1 + row * nb * 12; r.p2 = p2 + row * nb * 4;  r.p3 = p3 + row * nb * 32; break;
-        case T_Q6_K: r.p0 = p0 + row * nb * 128; r.p1 = p1 + row * nb * 64; r.p2 = p2 + row * nb * 16; r.p3 = p3 + row * nb * 2; break;
-        default:     r.p0 = p0 + row * k;        r.p1 = p1 + row * (k / 32) * 2; r.p2 = nullptr; r.p3 = nullptr; break;   // T_Q8_0
-    }
-    return r;
+// hsum_float_8 (cpp/ggml/src/ggml-quants.c:47-53) + the type's tail, from the row's chain results c[0..]
+__device__ __forceinline__ float finish_row(int type, const float * c) {
+    const float r0 = __fadd_rn(c[4], c[0]), r1 = __fadd_rn(c[5], c[1]), r2 = __fadd_rn(c[6], c[2]), r3 = __fadd_rn(c[7], c[3]);
+    const float h = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+    if (type == T_Q4_K) return __fadd_rn(h, __fadd_rn(__fadd_rn(c[8], c[10]), __fadd_rn(c[9], c[11])));   // + acc_m
+    if (type == T_Q5_K) return __fadd_rn(h, c[8]);                                                       // + summs
+    return h;
 }
-
-__device__ __forceinline__ float silu_f32(float x) { return x / (1.0f + expf(-x)); }   // ggml_silu_f32, ggml.c:2393
 
 // ------------------------------------------------------------------------------------------------------------
-// The fused quantized mat-vec: [RMSNorm] + activation quant (prologue) -> W.x over row pairs -> epilogue.
-// Grid-stride over row PAIRS, one warp per pair per pass.
-//   PAIR_ADJACENT: pair p = rows (2p, 2p+1) of the virtual concatenation seg[0] ++ seg[1] ++ seg[2]
-//                  (the RoPE partner of row 2i is row 2i+1: NORM mode, cpp/ggml/src/ggml.c:14121-14135)
-//   PAIR_ZIP     : pair p = (seg[0] row p, seg[1] row p)  (gate/up, cpp/src/llama.cpp:8875-8880)
+// The fused quantized mat-vec: [RMSNorm] + activation quant (prologue) -> exact W.x -> epilogue.
+// A warp owns work units of `rows_unit` whole rows (= tiles_unit tiles). Per tile: every lane computes its
+// block's integers (block_*), then the chain lanes advance the rows' fp32 fma chains over this tile's blocks in
+// block order; after the unit's last tile one lane per row finishes (hsum) and the epilogue runs on row pairs.
 // ------------------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(MV_THREADS, 2) k_matvec(const MatvecArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ double red_smem[MV_WARPS];
+    __shared__ uint32_t stage_all[MV_WARPS][STG_WORDS];
     const ActSmem A = act_smem_carve(smem_raw, a.k, a.act_q8_0);
 
-    prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, reinterpret_cast<float *>(red_smem));
+    prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int warp_global = blockIdx.x * MV_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t * stg = stage_all[warp];
+    const int warp_global = blockIdx.x * MV_WARPS + warp;
     const int n_warps = gridDim.x * MV_WARPS;
 
-    for (int pair = warp_global; pair < a.n_pairs; pair += n_warps) {
-        int si0 = 0, r0 = 0, si1 = 0, r1 = 0;
-        if (a.pair_mode == PAIR_ZIP) {
-            si0 = 0; r0 = pair; si1 = 1; r1 = pair;
-        } else {
-            int row = 2 * pair;
-            int s = 0;
-            while (s < a.n_seg - 1 && row >= a.seg[s].n_rows) { row -= a.seg[s].n_rows; s++; }
-            si0 = si1 = s; r0 = row; r1 = row + 1;
+    for (int unit = warp_global; unit < a.n_units; unit += n_warps) {
+        // segment lookup by branches (dynamic indexing of the parameter struct would force a local copy)
+        int u = unit, si = 0, row_base = 0;
+        if (a.n_seg > 1 && u >= a.seg[0].n_units) { u -= a.seg[0].n_units; row_base += a.seg[0].n_rows; si = 1;
+            if (a.n_seg > 2 && u >= a.seg[1].n_units) { u -= a.seg[1].n_units; row_base += a.seg[1].n_rows; si = 2; } }
+        const TMat & m = si == 0 ? a.seg[0] : (si == 1 ? a.seg[1] : a.seg[2]);
+        const int type = m.type, nb = m.nb, C = chains_of(type);
+        const int n_chains = m.rows_unit * C;
+        float acc[MAX_CHAIN_SLOTS];
+#pragma unroll
+        for (int i = 0; i < MAX_CHAIN_SLOTS; i++) acc[i] = 0.f;
+
+        for (int t = 0; t < m.tiles_unit; t++) {
+            const size_t T = (size_t) u * m.tiles_unit + t;
+            const int li = t * 32 + lane;                          // block index inside the unit
+            const int bi = li % nb;
+            switch (type) {
+                case T_Q4_K: block_q45k<false>(m, T, lane, bi, A, stg); break;
+                case T_Q5_K: block_q45k<true>(m, T, lane, bi, A, stg); break;
+                case T_Q6_K: block_q6k(m, T, lane, bi, A, stg); break;
+                default:     block_q80(m, T, lane, bi, A, stg); break;
+            }
+            __syncwarp();
+            // chain phase: chain ch = (row r of the unit, lane-of-AVX k); blocks of row r inside this tile, in order
+#pragma unroll
+            for (int cs = 0; cs < MAX_CHAIN_SLOTS; cs++) {
+                const int ch = cs * 32 + lane;
+                if (cs * 32 < n_chains && ch < n_chains) {
+                    const int r = ch / C, k = ch - r * C;
+                    const int lo = max(r * nb, t * 32) - t * 32, hi = min(r * nb + nb, t * 32 + 32) - t * 32;
+                    const int coef_row = k < 8 ? 0 : 9;
+                    const int val_row  = k < 8 ? 1 + k : 10 + (k - 8);
+                    float v = acc[cs];
+                    if (type == T_Q5_K && k == 8) {
+                        // summs += dmin * (float) sum(prod): separate mul and add (cpp/ggml/src/ggml-quants.c:7516)
+                        for (int l = lo; l < hi; l++)
+                            v = __fadd_rn(v, __fmul_rn(__uint_as_float(stg[9 * STG_STRIDE + l]), (float) (int) stg[10 * STG_STRIDE + l]));
+                    } else {
+#pragma unroll 4
+                        for (int l = lo; l < hi; l++)
+                            v = __fmaf_rn(__uint_as_float(stg[coef_row * STG_STRIDE + l]), (float) (int) stg[val_row * STG_STRIDE + l], v);
+                    }
+                    acc[cs] = v;
+                }
+            }
+            __syncwarp();
         }
-        // select the segment with branches (dynamic indexing of the kernel-parameter struct would force a local copy)
-        const QMat & m0 = si0 == 0 ? a.seg[0] : (si0 == 1 ? a.seg[1] : a.seg[2]);
-        const QMat & m1 = si1 == 0 ? a.seg[0] : (si1 == 1 ? a.seg[1] : a.seg[2]);
-        const int type = m0.type;
-        const RowPtrs rp[2] = { row_ptrs(type, m0.k, m0.p0, m0.p1, m0.p2, m0.p3, r0), row_ptrs(type, m1.k, m1.p0, m1.p1, m1.p2, m1.p3, r1) };
-        float acc[2] = {0.f, 0.f};
-        switch (type) {
-            case T_Q4_K: dot_q45k<2, 2, false>(rp, a.k / 256, lane, A, acc); break;
-            case T_Q5_K: dot_q45k<2, 1, true>(rp, a.k / 256, lane, A, acc); break;
-            case T_Q6_K: dot_q6k<2, 1>(rp, a.k / 256, lane, A, acc); break;
-            default:     dot_q80<2, 2>(rp, a.k / 32, lane, A, acc); break;
+        // publish chain results, finish one row per lane
+        float * fin = reinterpret_cast<float *>(stg);
+#pragma unroll
+        for (int cs = 0; cs < MAX_CHAIN_SLOTS; cs++) {
+            const int ch = cs * 32 + lane;
+            if (cs * 32 < n_chains && ch < n_chains) fin[ch] = acc[cs];
         }
-        const float v0 = warp_sum(acc[0]);
-        const float v1 = warp_sum(acc[1]);
-        if (lane == 0) {
+        __syncwarp();
+        float val = 0.f;
+        if (lane < m.rows_unit) val = finish_row(type, fin + lane * C);
+        const float nxt = __shfl_down_sync(0xffffffffu, val, 1);
+        __syncwarp();
+        if (lane < m.rows_unit && (lane & 1) == 0) {
+            const float v0 = val, v1 = nxt;
+            const int row = row_base + u * m.rows_unit + lane;     // virtual row of v0; v1 is row + 1
             if (EPI == EPI_STORE) {
-                a.out[2 * pair]     = v0;
-                a.out[2 * pair + 1] = v1;
+                a.out[row] = v0; a.out[row + 1] = v1;
             } else if (EPI == EPI_RESID) {
                 // ggml_add(cur, inpSA) / ggml_add(cur, ffn_inp): cpp/src/llama.cpp:8865, 8901
-                a.out[2 * pair]     = __fadd_rn(v0, a.resid[2 * pair]);
-                a.out[2 * pair + 1] = __fadd_rn(v1, a.resid[2 * pair + 1]);
+                a.out[row] = __fadd_rn(v0, a.resid[row]); a.out[row + 1] = __fadd_rn(v1, a.resid[row + 1]);
             } else if (EPI == EPI_SILU) {
-                // silu(gate) * up: cpp/src/llama.cpp:7960-8085 (LLM_FFN_SILU, LLM_FFN_PAR)
-                a.out[pair] = __fmul_rn(silu_f32(v0), v1);
+                // rows (2r, 2r+1) = (gate r, up r): silu(gate) * up, cpp/src/llama.cpp:7960-8085
+                a.out[row >> 1] = __fmul_rn(silu_exact(v0), v1);
             } else {  // EPI_QKV
-                const int row = 2 * pair;
                 const int pos = a.st->pos;
                 if (row < a.n_q + a.n_k) {
                     // RoPE NORM mode on the pair (x0, x1): cpp/ggml/src/ggml.c:14121-14135
                     const int i0 = row % a.head_dim;
-                    const float2 cs = a.rope[(size_t) pos * (a.head_dim / 2) + (i0 >> 1)];
-                    const float y0 = __fsub_rn(__fmul_rn(v0, cs.x), __fmul_rn(v1, cs.y));
-                    const float y1 = __fadd_rn(__fmul_rn(v0, cs.y), __fmul_rn(v1, cs.x));
+                    const float2 cs2 = a.rope[(size_t) pos * (a.head_dim / 2) + (i0 >> 1)];
+                    const float y0 = __fsub_rn(__fmul_rn(v0, cs2.x), __fmul_rn(v1, cs2.y));
+                    const float y1 = __fadd_rn(__fmul_rn(v0, cs2.y), __fmul_rn(v1, cs2.x));
                     if (row < a.n_q) {
-                        a.q_out[row]     = y0;
-                        a.q_out[row + 1] = y1;
+                        a.q_out[row] = y0; a.q_out[row + 1] = y1;
                     } else {
                         // K stored post-RoPE as f16 at slot `pos`: llm_build_kv_store, cpp/src/llama.cpp:7849-7853
-                        __half2 * dst = reinterpret_cast<__half2 *>(a.k_cache + (size_t) pos * a.kv_dim + (row - a.n_q));
-                        *dst = __halves2half2(__float2half_rn(y0), __float2half_rn(y1));
+                        *reinterpret_cast<__half2 *>(a.k_cache + (size_t) pos * a.kv_dim + (row - a.n_q)) =
+                            __halves2half2(__float2half_rn(y0), __float2half_rn(y1));
                     }
                 } else {
-                    __half2 * dst = reinterpret_cast<__half2 *>(a.v_cache + (size_t) pos * a.kv_dim + (row - a.n_q - a.n_k));
-                    *dst = __halves2half2(__float2half_rn(v0), __float2half_rn(v1));
+                    *reinterpret_cast<__half2 *>(a.v_cache + (size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)) =
+                        __halves2half2(__float2half_rn(v0), __float2half_rn(v1));
                 }
             }
         }
@@ -533,33 +539,34 @@ __global__ void __launch_bounds__(MV_THREADS, 2) k_matvec(const MatvecArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// stand-alone activation quantization kernels (operator-level tests; same device functions as the prologue)
-// out layouts are the ggml block structs: block_q8_K {float d; int8 qs[256]; int16 bsums[16]} (292 B),
-// block_q8_0 {half d; int8 qs[32]} (34 B)  (cpp/ggml/src/ggml-common.h:311-315, 186-190)
+// stand-alone activation quantization (operator-level tests; same device functions as the prologue).
+// out = ggml block structs: block_q8_K {float d; int8 qs[256]; int16 bsums[16]} (292 B), block_q8_0 {half d;
+// int8 qs[32]} (34 B)  (cpp/ggml/src/ggml-common.h:311-315, 186-190). bsums are re-derived from the quants.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q8_0, uint8_t * __restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ double red_smem[MV_WARPS];
     const ActSmem A = act_smem_carve(smem_raw, k, act_q8_0);
-    prologue_quantize(x, nullptr, 0.f, k, act_q8_0, A, reinterpret_cast<float *>(red_smem));
+    prologue_quantize(x, nullptr, 0.f, k, act_q8_0, A, red_smem);
     __syncthreads();
     if (!act_q8_0) {
-        for (int b = 0; b < k / 256; b++) {
+        const int nb = k / 256;
+        for (int b = 0; b < nb; b++) {
             uint8_t * o = out + (size_t) b * 292;
             if (threadIdx.x == 0) *reinterpret_cast<float *>(o) = A.dx[b];
-            for (int i = threadIdx.x; i < 256; i += blockDim.x) o[4 + i] = (uint8_t) A.q[b * 256 + i];
+            for (int e = threadIdx.x; e < 256; e += blockDim.x) o[4 + e] = (uint8_t) A.q[((size_t) ((e >> 4) * nb + b)) * 16 + (e & 15)];
             for (int i = threadIdx.x; i < 16; i += blockDim.x) {
-                const int16_t s = A.bsums[b * 16 + i];
-                o[260 + 2 * i] = (uint8_t) (s & 0xff);
-                o[261 + 2 * i] = (uint8_t) ((s >> 8) & 0xff);
+                int s = 0;
+                for (int e = 16 * i; e < 16 * i + 16; e++) s += A.q[((size_t) ((e >> 4) * nb + b)) * 16 + (e & 15)];
+                o[260 + 2 * i] = (uint8_t) (s & 0xff); o[261 + 2 * i] = (uint8_t) ((s >> 8) & 0xff);
             }
         }
     } else {
-        for (int b = threadIdx.x; b < k / 32; b += blockDim.x) {
+        const int nb32 = k / 32;
+        for (int b = threadIdx.x; b < nb32; b += blockDim.x) {
             uint8_t * o = out + (size_t) b * 34;
-            const __half hd = __float2half_rn(A.dx[b]);     // dx is already an exact f16 value
-            *reinterpret_cast<__half *>(o) = hd;              // 34*b is even: 2-byte aligned
-            for (int i = 0; i < 32; i++) o[2 + i] = (uint8_t) A.q[b * 32 + i];
+            *reinterpret_cast<__half *>(o) = __float2half_rn(A.dx[b]);     // dx is an exact f16 value; 34*b is even
+            for (int e = 0; e < 32; e++) o[2 + e] = (uint8_t) A.q[((size_t) ((e >> 4) * nb32 + b)) * 16 + (e & 15)];
         }
     }
 }
@@ -644,202 +651,219 @@ __global__ void k_embed(int type, const uint8_t * __restrict__ rows, size_t row_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// decode attention, default (non-flash) route at batch 1 (cpp/src/llama.cpp:8248-8297):
-//   kq = K(f16->f32) . q(f32)  [tinyBLAS F16xF32, cpp/ggml/src/ggml.c:12325-12341]
-//   softmax(kq*scale + mask)   [cpp/ggml/src/ggml.c:13682-13778; causality from `pos`, no mask tensor]
-//   kqv = V(f16->f32) . p      [same tinyBLAS route]
-// Split-KV flash-decode, one launch: grid (n_head_kv, ATT_SPLITS), 256 threads. A CTA serves the `GQA` query
-// heads that share its KV head (K and V rows are read once per group, cf. the broadcast in
-// cpp/ggml/src/ggml.c:12207-12243) over 64-position tiles t = split, split + ATT_SPLITS, ...
-// Latency design (HBM-bound, 8.4 MB per layer at ctx 2048 => every byte must be in flight at once):
-//   * all K loads (4 x 16 B per thread: 4 lanes per key row) AND all V loads (16 x 4 B per thread) of a tile are
-//     issued before any arithmetic, so a tile costs one DRAM round trip;
-//   * scores: 32-dim partial dots per lane, 2 shuffles per head; softmax state per head kept in shared memory;
-//   * P.V: thread = (dim pair, 16-position group), partial sums merged through shared memory;
-//   * the last CTA of a KV head (atomic ticket) merges the splits — no separate combine launch.
+// decode attention, default (non-flash) route (cpp/src/llama.cpp:8248-8297), exact order, three launches:
+//   k_attn_scores : S[h][t] = (K[t] . q[h]) * scale for t <= pos, -inf for the padded tail (n_kv is padded to 32,
+//                   cpp/src/llama.cpp:14698; the mask adds -inf there). 4 lanes per key row; lane c4 owns the
+//                   tinyBLAS chains 4c4..4c4+3 (element 16s+c of step s) and the _mm512_reduce_add_ps tree is
+//                   completed with two shuffles. round_q: ggml_vec_dot_f16 order (4 accumulators x 16 lanes).
+//   k_attn_softmax: per head: max, p = ggml_v_expf(s - max), per-16 partial sums (_mm512_reduce_add_ps),
+//                   double sum, p *= (float)(1/sum)   (cpp/ggml/src/ggml.c:13682-13778, 2619-2640)
+//   k_attn_pv     : out[h][d] = sum_t V[t][d] p[t] as tinyBLAS computes it: chain c = t mod 16 over t, then the
+//                   reduce tree. One thread per (kv head, d, c), all GQA heads of the group share each V load.
 // ------------------------------------------------------------------------------------------------------------
 static constexpr int ATT_THREADS = 256;
-static constexpr int ATT_TILE    = 64;
-static constexpr int ATT_SPLITS  = 32;
+static constexpr int ATT_TILE    = 64;       // key positions per scores CTA
 static constexpr int ATT_MAX_GQA = 8;
+static constexpr int PV_DIMS     = 16;       // dims per P.V CTA (x 16 chains = 256 threads; 16 dims = one 32-byte sector)
+static constexpr int PV_CHUNK    = 1024;     // positions of p staged in shared memory at a time
 
 struct AttnArgs {
     const float * q;          // [n_head][hd] post-RoPE
     const __half * k_cache;   // [n_ctx][kv_dim]
     const __half * v_cache;
-    float * part_o;           // [n_head][ATT_SPLITS][hd]  un-normalised
-    float * part_ml;          // [n_head][ATT_SPLITS][2]   (running max, sum)
-    unsigned int * tickets;   // [n_head_kv] zero-initialised, self-resetting
+    float * S;                // [n_head][s_stride] scores, then probabilities
+    int s_stride;             // >= n_ctx padded to 32
     float * out;              // [n_head*hd]  (kqv_merged_cont)
     int n_head, n_head_kv, head_dim, kv_dim;
     float scale;
     const DecodeState * st;
     int n_kv_override;        // >0: use instead of st->pos+1 (operator-level test)
+    int round_q_override;     // operator-level test of the batch>1 arithmetic
 };
+__device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1; }
 
 template <int GQA>
-__global__ void __launch_bounds__(ATT_THREADS) k_attn(const AttnArgs a) {
-    constexpr int HD = 128;                                   // every LLaMA/Mistral config on this path
+__global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
+    constexpr int HD = 128;
     __shared__ __align__(16) float qs[GQA][HD];
-    __shared__ __align__(16) float sc[GQA][ATT_TILE];         // scores, then probabilities
-    __shared__ float run_m[GQA], run_l[GQA], resc[GQA];
-    __shared__ __align__(16) float red_o[4][GQA][HD];         // P.V partials of the 4 position groups
-    __shared__ float wsplit[GQA][ATT_SPLITS];
-    __shared__ unsigned int s_ticket;
-
-    const int g = blockIdx.x, split = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_kv = a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1;
-    const int round_q = a.st ? a.st->round_q : 0;
-    const int n_tiles = (n_kv + ATT_TILE - 1) / ATT_TILE;
-
+    const int g = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
+    const int n_kv = attn_n_kv(a);
+    const int n_pad = (n_kv + 31) / 32 * 32;
+    if (tile * ATT_TILE >= n_pad) return;
+    const int round_q = a.st ? a.st->round_q : a.round_q_override;
     for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
         float v = a.q[(size_t) (g * GQA) * HD + i];
-        if (round_q) v = __half2float(__float2half_rn(v));    // batch > 1: q is rounded to f16 (ggml.c:12345-12371)
+        if (round_q) v = __half2float(__float2half_rn(v));    // src1 converted to the vec_dot_type F16 (ggml.c:12345-12371)
         (&qs[0][0])[i] = v;
     }
-    if (tid < GQA) { run_m[tid] = -INFINITY; run_l[tid] = 0.f; }
-
-    // thread roles
-    const int kp = tid >> 2, kq4 = tid & 3;                   // scores: key position in tile, 32-dim quarter
-    const int dp = tid & 63, pg = tid >> 6;                   // P.V: dim pair, position group (16 positions)
-    float o[GQA][2];
-#pragma unroll
-    for (int h = 0; h < GQA; h++) { o[h][0] = 0.f; o[h][1] = 0.f; }
     __syncthreads();
-
-    for (int tile = split; tile < n_tiles; tile += ATT_SPLITS) {
-        const int p0 = tile * ATT_TILE;
-        // ---- issue every load of the tile
-        uint4 kreg[4];
-        const bool kvalid = p0 + kp < n_kv;
-        if (kvalid) {
-            const uint4 * kr = reinterpret_cast<const uint4 *>(a.k_cache + (size_t) (p0 + kp) * a.kv_dim + g * HD + kq4 * 32);
+    const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
+    if (t >= n_pad) return;                                   // whole 4-lane group exits together
+    float res[GQA];
 #pragma unroll
-            for (int i = 0; i < 4; i++) kreg[i] = ldg_stream_v4(kr + i);
+    for (int h = 0; h < GQA; h++) res[h] = 0.f;
+    // every lane of a group takes the same branch (t is shared), but groups of one warp may differ: shuffles are
+    // executed unconditionally on zeros for the padded positions
+    float kf[8][4];
+#pragma unroll
+    for (int s = 0; s < 8; s++) { kf[s][0] = 0.f; kf[s][1] = 0.f; kf[s][2] = 0.f; kf[s][3] = 0.f; }
+    if (t < n_kv) {
+        const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const uint2 kv = __ldg(kr + s * 4);               // 4 halfs at element 16s + 4c4
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv.x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv.y));
+            kf[s][0] = f0.x; kf[s][1] = f0.y; kf[s][2] = f1.x; kf[s][3] = f1.y;
         }
-        uint32_t vreg[16];
-        const __half * vbase = a.v_cache + (size_t) (p0 + pg * 16) * a.kv_dim + g * HD + 2 * dp;
+    }
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            vreg[i] = 0u;
-            if (p0 + pg * 16 + i < n_kv) vreg[i] = __ldg(reinterpret_cast<const uint32_t *>(vbase + (size_t) i * a.kv_dim));
-        }
-        // ---- scores
-        float acc[GQA];
+    for (int h = 0; h < GQA; h++) {
+        float ch[4];
+        if (!round_q) {
+            // tinyBLAS<16>: lane c: acc = fma(k[16s+c], q[16s+c], acc), s = 0..7
 #pragma unroll
-        for (int h = 0; h < GQA; h++) acc[h] = 0.f;
-        if (kvalid) {
+            for (int e = 0; e < 4; e++) ch[e] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const __half2 * k2 = reinterpret_cast<const __half2 *>(&kreg[i]);
-                float kf[8];
-#pragma unroll
-                for (int e = 0; e < 4; e++) { const float2 f = __half22float2(k2[e]); kf[2 * e] = f.x; kf[2 * e + 1] = f.y; }
-#pragma unroll
-                for (int h = 0; h < GQA; h++) {
-                    const float4 qa = *reinterpret_cast<const float4 *>(&qs[h][kq4 * 32 + i * 8]);
-                    const float4 qb = *reinterpret_cast<const float4 *>(&qs[h][kq4 * 32 + i * 8 + 4]);
-                    acc[h] = fmaf(kf[0], qa.x, acc[h]); acc[h] = fmaf(kf[1], qa.y, acc[h]);
-                    acc[h] = fmaf(kf[2], qa.z, acc[h]); acc[h] = fmaf(kf[3], qa.w, acc[h]);
-                    acc[h] = fmaf(kf[4], qb.x, acc[h]); acc[h] = fmaf(kf[5], qb.y, acc[h]);
-                    acc[h] = fmaf(kf[6], qb.z, acc[h]); acc[h] = fmaf(kf[7], qb.w, acc[h]);
-                }
+            for (int s = 0; s < 8; s++) {
+                const float4 qv = *reinterpret_cast<const float4 *>(&qs[h][16 * s + 4 * c4]);
+                ch[0] = __fmaf_rn(kf[s][0], qv.x, ch[0]); ch[1] = __fmaf_rn(kf[s][1], qv.y, ch[1]);
+                ch[2] = __fmaf_rn(kf[s][2], qv.z, ch[2]); ch[3] = __fmaf_rn(kf[s][3], qv.w, ch[3]);
             }
-        }
+        } else {
+            // ggml_vec_dot_f16: sum[j][c] over i in {0, 64}: element i + 16j + c; then (0+2)+(1+3)
+            float aj[4][4];
 #pragma unroll
-        for (int h = 0; h < GQA; h++) {
-            float s = acc[h];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (kq4 == 0) sc[h][kp] = kvalid ? __fmul_rn(s, a.scale) : -INFINITY;
+            for (int j = 0; j < 4; j++) {
+                const float4 q0 = *reinterpret_cast<const float4 *>(&qs[h][16 * j + 4 * c4]);
+                const float4 q1 = *reinterpret_cast<const float4 *>(&qs[h][64 + 16 * j + 4 * c4]);
+                aj[j][0] = __fmaf_rn(kf[4 + j][0], q1.x, __fmul_rn(kf[j][0], q0.x));
+                aj[j][1] = __fmaf_rn(kf[4 + j][1], q1.y, __fmul_rn(kf[j][1], q0.y));
+                aj[j][2] = __fmaf_rn(kf[4 + j][2], q1.z, __fmul_rn(kf[j][2], q0.z));
+                aj[j][3] = __fmaf_rn(kf[4 + j][3], q1.w, __fmul_rn(kf[j][3], q0.w));
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) ch[e] = __fadd_rn(__fadd_rn(aj[0][e], aj[2][e]), __fadd_rn(aj[1][e], aj[3][e]));
+        }
+        // _mm512_reduce_add_ps over the 16 chains: lanes c4=0..3 hold chains 4c4..4c4+3
+        float t3[4], t6[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) t3[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, ch[e], 2), ch[e]);   // a[8+i] + a[i] (valid in c4 = 0,1)
+#pragma unroll
+        for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);   // t3[4+i] + t3[i] (valid in c4 = 0)
+        res[h] = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
+    }
+    if (c4 == 0) {
+#pragma unroll
+        for (int h = 0; h < GQA; h++)
+            a.S[(size_t) (g * GQA + h) * a.s_stride + t] = t < n_kv ? __fmul_rn(res[h], a.scale) : -INFINITY;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_attn_softmax(const AttnArgs a) {
+    extern __shared__ double gsum[];                          // one partial per 16-group
+    __shared__ float red[8];
+    __shared__ float bc[2];
+    const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_pad = (attn_n_kv(a) + 31) / 32 * 32;
+    float * S = a.S + (size_t) h * a.s_stride;
+    float mx = -INFINITY;
+    for (int i = tid; i < n_pad; i += 256) mx = fmaxf(mx, S[i]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) { float m2 = red[0]; for (int w = 1; w < 8; w++) m2 = fmaxf(m2, red[w]); bc[0] = m2; }
+    __syncthreads();
+    mx = bc[0];
+    // n_pad is a multiple of 32 and the stride is 256, so every warp iteration is either fully in or fully out of
+    // range and half-warps coincide with the reference's 16-wide vectors
+    for (int i = tid; i < n_pad; i += 256) {
+        const float p = v_expf(__fsub_rn(S[i], mx));
+        S[i] = p;
+        const float gs = reduce_add16_shfl(p);
+        if ((lane & 15) == 0) gsum[i >> 4] = (double) gs;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int i = 0; i < n_pad / 16; i++) sum += gsum[i];  // sequential double accumulation, as the reference
+        bc[1] = (float) (1.0 / sum);
+    }
+    __syncthreads();
+    const float inv = bc[1];
+    for (int i = tid; i < n_pad; i += 256) S[i] = __fmul_rn(S[i], inv);
+}
+
+template <int GQA>
+__global__ void __launch_bounds__(PV_DIMS * 16) k_attn_pv(const AttnArgs a) {
+    constexpr int HD = 128;
+    constexpr int NT = PV_DIMS * 16;
+    __shared__ __align__(16) float ps[GQA][PV_CHUNK];
+    __shared__ float red[GQA][16][PV_DIMS + 1];
+    // thread = (chain c, dim dl): the 16 lanes of a half-warp read 32 contiguous bytes of one V row
+    const int g = blockIdx.x, c = threadIdx.x / PV_DIMS, dl = threadIdx.x % PV_DIMS, d = blockIdx.y * PV_DIMS + dl;
+    const int n_kv = attn_n_kv(a);
+    const int n_pad = (n_kv + 31) / 32 * 32;
+    float acc[GQA];
+#pragma unroll
+    for (int h = 0; h < GQA; h++) acc[h] = 0.f;
+    const __half * vcol = a.v_cache + g * HD + d;
+    for (int t0 = 0; t0 < n_pad; t0 += PV_CHUNK) {
+        const int len = min(PV_CHUNK, n_pad - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < GQA * len; i += NT) {
+            const int h = i / len, tt = i - h * len;
+            ps[h][tt] = a.S[(size_t) (g * GQA + h) * a.s_stride + t0 + tt];
         }
         __syncthreads();
-        // ---- online softmax state: warp h owns head h (64 scores = 2 per lane)
-        if (warp < GQA) {
-            const float s0 = sc[warp][lane], s1 = sc[warp][lane + 32];
-            const float mt = warp_max(fmaxf(s0, s1));
-            const float m_old = run_m[warp];
-            const float m_new = fmaxf(m_old, mt);
-            const float p0v = expf(s0 - m_new), p1v = expf(s1 - m_new);     // exp(-inf) = 0 for masked slots
-            const float lt = warp_sum(p0v + p1v);
-            sc[warp][lane] = p0v; sc[warp][lane + 32] = p1v;
-            if (lane == 0) {
-                const float r = m_old == -INFINITY ? 0.f : expf(m_old - m_new);
-                resc[warp] = r;
-                run_l[warp] = run_l[warp] * r + lt;
-                run_m[warp] = m_new;
+        const int steps = len / 16;
+        int s = 0;
+        for (; s + 32 <= steps; s += 32) {                     // 32 independent loads in flight per thread
+            float vf[32];
+#pragma unroll
+            for (int e = 0; e < 32; e++) {
+                const int t = t0 + 16 * (s + e) + c;
+                vf[e] = t < n_kv ? __half2float(vcol[(size_t) t * a.kv_dim]) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; e++) {
+#pragma unroll
+                for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(vf[e], ps[h][16 * (s + e) + c], acc[h]);
             }
         }
-        __syncthreads();
-        // ---- P.V for this thread's 16 positions x 2 dims
+        for (; s + 4 <= steps; s += 4) {
+            float vf[4];
 #pragma unroll
-        for (int h = 0; h < GQA; h++) {
-            const float r = resc[h];
-            float o0 = o[h][0] * r, o1 = o[h][1] * r;
-#pragma unroll
-            for (int i4 = 0; i4 < 4; i4++) {
-                const float4 pv = *reinterpret_cast<const float4 *>(&sc[h][pg * 16 + i4 * 4]);
-                const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(&vreg[i4 * 4 + e]));
-                    o0 = fmaf(pp[e], vf.x, o0);
-                    o1 = fmaf(pp[e], vf.y, o1);
-                }
+            for (int e = 0; e < 4; e++) {
+                const int t = t0 + 16 * (s + e) + c;
+                vf[e] = t < n_kv ? __half2float(vcol[(size_t) t * a.kv_dim]) : 0.f;
             }
-            o[h][0] = o0; o[h][1] = o1;
-        }
-        __syncthreads();     // sc / resc are rewritten by the next tile
-    }
-
-    // ---- merge the 4 position groups, publish this split's partial
 #pragma unroll
-    for (int h = 0; h < GQA; h++) { red_o[pg][h][2 * dp] = o[h][0]; red_o[pg][h][2 * dp + 1] = o[h][1]; }
-    __syncthreads();
-    for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
-        const int h = i / HD, d = i % HD;
-        const float v = red_o[0][h][d] + red_o[1][h][d] + red_o[2][h][d] + red_o[3][h][d];
-        a.part_o[((size_t) (g * GQA + h) * ATT_SPLITS + split) * HD + d] = v;
-    }
-    if (tid < GQA) {
-        const size_t oi = ((size_t) (g * GQA + tid) * ATT_SPLITS + split) * 2;
-        a.part_ml[oi] = run_m[tid]; a.part_ml[oi + 1] = run_l[tid];
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&a.tickets[g], 1u);
-    __syncthreads();
-    if (s_ticket != ATT_SPLITS - 1) return;
-    // ---- last CTA of this KV head: combine the splits
-    __threadfence();
-    if (tid == 0) a.tickets[g] = 0u;                          // self-reset for the next launch
-    for (int i = tid; i < GQA * ATT_SPLITS; i += ATT_THREADS) {
-        const int h = i / ATT_SPLITS, s = i % ATT_SPLITS;
-        (&wsplit[0][0])[i] = __ldcg(&a.part_ml[((size_t) (g * GQA + h) * ATT_SPLITS + s) * 2]);   // m_s for now
-    }
-    __syncthreads();
-    if (tid < GQA) {
-        float M = -INFINITY;
-        for (int s = 0; s < ATT_SPLITS; s++) M = fmaxf(M, wsplit[tid][s]);
-        float L = 0.f;
-        for (int s = 0; s < ATT_SPLITS; s++) {
-            const float ms = wsplit[tid][s];
-            const float w = ms == -INFINITY ? 0.f : expf(ms - M);
-            L += w * __ldcg(&a.part_ml[((size_t) (g * GQA + tid) * ATT_SPLITS + s) * 2 + 1]);
-            wsplit[tid][s] = w;
+            for (int e = 0; e < 4; e++) {
+#pragma unroll
+                for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(vf[e], ps[h][16 * (s + e) + c], acc[h]);
+            }
         }
-        run_l[tid] = 1.0f / L;
-    }
-    __syncthreads();
-    for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
-        const int h = i / HD, d = i % HD;
-        float v = 0.f;
-        for (int s = 0; s < ATT_SPLITS; s++) {
-            const float w = wsplit[h][s];
-            if (w != 0.f) v = fmaf(w, __ldcg(&a.part_o[((size_t) (g * GQA + h) * ATT_SPLITS + s) * HD + d]), v);
+        for (; s < steps; s++) {
+            const int t = t0 + 16 * s + c;
+            const float v = t < n_kv ? __half2float(vcol[(size_t) t * a.kv_dim]) : 0.f;
+#pragma unroll
+            for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(v, ps[h][16 * s + c], acc[h]);
         }
-        a.out[(size_t) (g * GQA + h) * HD + d] = v * run_l[h];   // kqv_merged_cont layout: [n_head*hd]
+    }
+#pragma unroll
+    for (int h = 0; h < GQA; h++) red[h][c][dl] = acc[h];
+    __syncthreads();
+    for (int i = threadIdx.x; i < GQA * PV_DIMS; i += NT) {
+        const int h = i / PV_DIMS, dd = i % PV_DIMS;
+        // _mm512_reduce_add_ps over the 16 chains
+        float t3[8], t6[4];
+#pragma unroll
+        for (int j = 0; j < 8; j++) t3[j] = __fadd_rn(red[h][8 + j][dd], red[h][j][dd]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) t6[j] = __fadd_rn(t3[4 + j], t3[j]);
+        a.out[(size_t) (g * GQA + h) * HD + blockIdx.y * PV_DIMS + dd] =
+            __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));     // kqv_merged_cont layout: [n_head*hd]
     }
 }
 

@@ -190,12 +190,13 @@ def op_rope(x, n_heads: int, head_dim: int, pos: int, freq_base: float, freq_sca
     return y
 
 
-def op_attention(q, k_cache_f16, v_cache_f16, n_kv: int, n_head: int, n_head_kv: int, head_dim: int, scale: float) -> np.ndarray:
+def op_attention(q, k_cache_f16, v_cache_f16, n_kv: int, n_head: int, n_head_kv: int, head_dim: int, scale: float,
+                 round_q: bool = False) -> np.ndarray:
     q = _f32(q)
     k = np.ascontiguousarray(k_cache_f16, dtype=np.float16).view(np.uint16)
     v = np.ascontiguousarray(v_cache_f16, dtype=np.float16).view(np.uint16)
     out = np.empty(n_head * head_dim, dtype=np.float32)
     check(_lib.lib().b200_op_attention(q.ctypes.data_as(C.POINTER(C.c_float)), k.ctypes.data_as(C.POINTER(C.c_uint16)),
-                                       v.ctypes.data_as(C.POINTER(C.c_uint16)), n_kv, n_head, n_head_kv, head_dim, scale,
+                                       v.ctypes.data_as(C.POINTER(C.c_uint16)), n_kv, n_head, n_head_kv, head_dim, scale, int(round_q),
                                        out.ctypes.data_as(C.POINTER(C.c_float))), "op_attention")
     return out

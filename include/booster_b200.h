@@ -141,10 +141,11 @@ int b200_op_rms_norm(const float * x, const float * w, int64_t k, float eps, flo
  * for position pos. freq_factors may be NULL. */
 int b200_op_rope(float * x, int n_heads, int head_dim, int pos, float freq_base, float freq_scale,
                  const float * freq_factors);
-/* the default (non-flash) attention route at batch 1 (cpp/src/llama.cpp:8188-8299): q[n_head][hd] f32,
- * k_cache/v_cache = f16 bits [n_kv][n_head_kv*hd] (position-major), out[n_head*hd]. */
+/* the default (non-flash) attention route (cpp/src/llama.cpp:8188-8299): q[n_head][hd] f32,
+ * k_cache/v_cache = f16 bits [n_kv][n_head_kv*hd] (position-major), out[n_head*hd].
+ * round_q = 0: batch-1 arithmetic (tinyBLAS F16xF32); 1: batch>1 (q rounded to f16, ggml_vec_dot_f16). */
 int b200_op_attention(const float * q, const uint16_t * k_cache, const uint16_t * v_cache, int n_kv,
-                      int n_head, int n_head_kv, int head_dim, float scale, float * out);
+                      int n_head, int n_head_kv, int head_dim, float scale, int round_q, float * out);
 
 #ifdef __cplusplus
 }

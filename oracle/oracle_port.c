@@ -361,14 +361,12 @@ typedef struct {
  *                  _mm512_reduce_add_ps, then p *= (float)(1/sum)   (cpp/ggml/src/ggml.c:13682-13778, 2619-2640)
  *   kqv          : tinyBLAS<16> over the (32-padded) kv length: lane c chains fma(v[16s+c][d], p[16s+c], acc)
  * n_kv is padded to 32 by the reference (kv_self.n, cpp/src/llama.cpp:14698); padded slots have p = 0. */
-static void attention(const port_model * M, int il, const float * q, int pos, int round_q, float * out) {
-    const int hd = M->head_dim, kvd = M->n_head_kv * hd, gqa = M->n_head / M->n_head_kv, n_kv = pos + 1;
+void port_attention(const float * q, const uint16_t * kc, const uint16_t * vc, int n_kv, int n_head, int n_head_kv,
+                    int hd, float scale, int round_q, float * out) {
+    const int kvd = n_head_kv * hd, gqa = n_head / n_head_kv;
     const int n_pad = (n_kv + 31) / 32 * 32;
-    const uint16_t * kc = M->k_cache + (int64_t) il * M->n_ctx * kvd;
-    const uint16_t * vc = M->v_cache + (int64_t) il * M->n_ctx * kvd;
-    const float scale = 1.0f / sqrtf((float) hd);
 #pragma omp parallel for schedule(static)
-    for (int h = 0; h < M->n_head; h++) {
+    for (int h = 0; h < n_head; h++) {
         const int g = h / gqa;
         float * p = (float *) malloc(sizeof(float) * (size_t) n_pad);
         float qh[512];
@@ -412,6 +410,12 @@ static void attention(const port_model * M, int il, const float * q, int pos, in
         }
         free(p);
     }
+}
+
+static void attention(const port_model * M, int il, const float * q, int pos, int round_q, float * out) {
+    const int kvd = M->n_head_kv * M->head_dim;
+    port_attention(q, M->k_cache + (int64_t) il * M->n_ctx * kvd, M->v_cache + (int64_t) il * M->n_ctx * kvd, pos + 1,
+                   M->n_head, M->n_head_kv, M->head_dim, 1.0f / sqrtf((float) M->head_dim), round_q, out);
 }
 
 /* llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0)) + llama_get_logits for LLM_ARCH_LLAMA

@@ -52,6 +52,7 @@ def lib() -> C.CDLL:
         L.port_mul_mat_vec.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.port_rms_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
         L.port_rope.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.port_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.port_decode.argtypes = [C.POINTER(PortModel), C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.port_decode.restype = C.c_int
         _lib = L
@@ -106,22 +107,14 @@ def rope(x, n_heads: int, head_dim: int, pos: int, freq_base: float, freq_scale:
     return y
 
 
-def attention_ref_numpy(q, k_cache_f16, v_cache_f16, n_kv, n_head, n_head_kv, head_dim, scale, round_q=False) -> np.ndarray:
-    """numpy statement of the default attention route at batch 1 (cpp/src/llama.cpp:8248-8297) in float64-free fp32."""
-    q = _f32(q).reshape(n_head, head_dim)
-    if round_q:
-        q = q.astype(np.float16).astype(np.float32)
-    k = np.asarray(k_cache_f16, dtype=np.float16)[:n_kv].astype(np.float32).reshape(n_kv, n_head_kv, head_dim)
-    v = np.asarray(v_cache_f16, dtype=np.float16)[:n_kv].astype(np.float32).reshape(n_kv, n_head_kv, head_dim)
-    gqa = n_head // n_head_kv
-    out = np.empty((n_head, head_dim), dtype=np.float32)
-    for h in range(n_head):
-        g = h // gqa
-        s = (k[:, g, :] @ q[h]).astype(np.float32) * np.float32(scale)
-        p = np.exp(s - s.max()).astype(np.float32)
-        p = (p * np.float32(1.0 / np.sum(p, dtype=np.float64))).astype(np.float32)
-        out[h] = p @ v[:, g, :]
-    return out.reshape(-1)
+def attention(q, k_cache_f16, v_cache_f16, n_kv, n_head, n_head_kv, head_dim, scale, round_q=False) -> np.ndarray:
+    """the default attention route in the reference's exact operation order (oracle_port.c port_attention)"""
+    q = _f32(q)
+    k = np.ascontiguousarray(k_cache_f16, dtype=np.float16).view(np.uint16)
+    v = np.ascontiguousarray(v_cache_f16, dtype=np.float16).view(np.uint16)
+    out = np.empty(n_head * head_dim, dtype=np.float32)
+    lib().port_attention(q.ctypes.data, k.ctypes.data, v.ctypes.data, n_kv, n_head, n_head_kv, head_dim, scale, int(round_q), out.ctypes.data)
+    return out
 
 
 class PortModelRunner:

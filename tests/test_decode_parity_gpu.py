@@ -1,24 +1,28 @@
-"""Model-level parity of the CUDA decode path (through the C-ABI) against
-  * golden logits the unmodified reference produced for reference-quantized tiny models (tests/golden),
-  * the port oracle on seeded random-block twins with the real 8B / 70B per-layer shapes,
-  * the reference itself (oracle/_ref) when it loads on this host,
-and size-independent properties at BASELINE.json's full sizes (determinism, graph == un-graphed, device-greedy
+"""Model-level parity of the CUDA decode path (through the C-ABI): logits BIT-IDENTICAL to
+  * the golden logits the unmodified reference produced for reference-quantized tiny models (tests/golden),
+  * the port oracle (itself bit-identical to the reference) on seeded random-block twins with the real 8B / 70B
+    per-layer shapes,
+  * the reference itself (oracle/_ref, AVX-512 build) when it loads on this host,
+plus size-independent properties at BASELINE.json's full sizes (determinism, graph == un-graphed, device-greedy
 == host-greedy, stage split == single stage).
 
-Tolerances: fp32 round-off 5e-6 for most steps; a single int8 activation-quantization flip (see
-tests/test_oracle_pinned.py) bounds every step: 5e-2 on the tiny models (K <= 768), 1e-3 — the north-star
-tolerance — on the 8B/70B-shaped twins (K >= 4096)."""
+Bitwise equality is the only meaningful criterion here: activations are re-quantized to int8 before every
+mat-mul, so any 1-ulp deviation eventually flips a quant and cascades to ~1e-2 (DESIGN.md "why bit-exact").
+It also makes greedy decoding token-id-exact by construction."""
 import os
 
 import numpy as np
 import pytest
 
-from conftest import greedy_consistent, rel_err
+from conftest import rel_err
 from booster_b200 import engine, gguf_io as G
 from oracle import port
 
 pytestmark = pytest.mark.gpu
-ROUNDOFF, FLIP_TINY, NORTH_STAR = 5e-6, 5e-2, 1e-3
+
+
+def _same(a, b, what=""):
+    assert np.array_equal(a, b), f"{what}: max abs diff {np.abs(np.asarray(a) - np.asarray(b)).max():.3e} rel {rel_err(a, b):.3e}"
 
 
 def _synth(model_dir, cfg, ftype, seed=7):
@@ -29,35 +33,27 @@ def _synth(model_dir, cfg, ftype, seed=7):
 
 
 @pytest.mark.parametrize("model", ["tiny_Q4_K_M", "tiny_Q5_K_M", "tiny_Q8_0", "tiny-gqa4_Q4_K_M"])
-def test_golden_models(golden_dir, model):
+def test_golden_models_bitwise(golden_dir, model):
     g = np.load(os.path.join(golden_dir, model + ".npz"))
     m = engine.Model(os.path.join(golden_dir, model + ".gguf"))
     c = engine.Context(m, 64)
     prompt = g["prompt"].tolist()
-    errs = []
     lg = c.decode(prompt, 0)                                  # batch > 1 arithmetic
-    errs.append(rel_err(lg, g["logits"][0]))
+    _same(lg, g["logits"][0], "prefill")
     pos = len(prompt)
-    exact = 0
     for i, t in enumerate(g["ids"].tolist()):
-        # teacher-forced with the reference's ids; arg-max must agree except at provable near-ties
-        assert greedy_consistent(lg, g["logits"][i]), f"greedy id differs from the reference at step {i}"
-        exact += int(np.argmax(lg)) == t
+        assert int(np.argmax(lg)) == t, f"greedy id differs from the reference at step {i}"
         lg = c.decode([t], pos)
         pos += 1
-        errs.append(rel_err(lg, g["logits"][i + 1]))
-    assert exact >= len(g["ids"]) - 1
+        _same(lg, g["logits"][i + 1], f"step {i}")
     c.kv_clear()
     for i, t in enumerate(prompt[:6]):                        # batch-1 arithmetic from position 0
-        errs.append(rel_err(c.decode([t], i), g["single"][i]))
-    errs = np.array(errs)
-    assert errs.max() < FLIP_TINY, errs
-    assert np.median(errs) < ROUNDOFF, errs
+        _same(c.decode([t], i), g["single"][i], f"single {i}")
     c.close(); m.close()
 
 
 @pytest.mark.parametrize("model", ["tiny_Q4_K_M", "tiny-gqa4_Q4_K_M"])
-def test_golden_layer_taps(golden_dir, model):
+def test_golden_layer_taps_bitwise(golden_dir, model):
     """layer-wise: Qcur / kqv_merged_cont / l_out of the prefill call vs the reference's cb_eval taps"""
     g = np.load(os.path.join(golden_dir, model + ".npz"))
     m = engine.Model(os.path.join(golden_dir, model + ".gguf"))
@@ -70,50 +66,54 @@ def test_golden_layer_taps(golden_dir, model):
         for ours, theirs in (("Qcur", f"Qcur_{il}"), ("kqv_merged_cont", f"kqv_merged_cont_{il}"), ("l_out", f"l_out_{il}")):
             a, b = c.get_tap(ours, il), g[theirs]
             b_last = b.reshape(T, -1)[-1] if b.size == a.size * T else b     # the last layer keeps only the last row
-            assert rel_err(a, b_last) < FLIP_TINY, (ours, il)
+            _same(a, b_last, f"{ours}-{il}")
     c.close(); m.close()
 
 
 @pytest.mark.parametrize("cfg,ftype,n_gen", [("llama3-8b-2l", "Q4_K_M", 24), ("llama3-8b-2l", "Q8_0", 8),
                                               ("llama3-8b-2l", "Q5_K_M", 8), ("llama3-70b-1l", "Q4_K_M", 8)])
-def test_fullshape_twins_vs_port(model_dir, cfg, ftype, n_gen):
+def test_fullshape_twins_vs_port_bitwise(model_dir, cfg, ftype, n_gen):
     """the real per-layer shapes (n_embd 4096/8192, n_ff 14336/28672, GQA 4/8) with few layers: CUDA vs port"""
     path = _synth(model_dir, cfg, ftype)
     conf = G.CONFIGS[cfg]
-    prompt = np.random.default_rng(42).integers(0, conf.n_vocab, size=16).tolist()
+    prompt = np.random.default_rng(42).integers(0, conf.n_vocab, size=40).tolist()
     p = port.PortModelRunner(path, n_ctx=128)
     ids_p, lg_p = p.greedy(prompt, n_gen)
     m = engine.Model(path)
     c = engine.Context(m, 128)
     ids_g, lg_g = c.greedy(prompt, n_gen)
-    # free-running greedy on both sides: compare while the trajectories coincide
-    n_same = next((i for i, (a, b) in enumerate(zip(ids_g, ids_p)) if a != b), len(ids_p))
-    errs = np.array([rel_err(a, b) for a, b in zip(lg_g[:n_same + 1], lg_p[:n_same + 1])])
-    print("rel errs", errs, "n_same", n_same)
-    assert errs.max() < NORTH_STAR, errs
-    if n_same < len(ids_p):
-        assert greedy_consistent(lg_g[n_same], lg_p[n_same]), (n_same, ids_g, ids_p)
+    assert ids_g == ids_p
+    for i, (a, b) in enumerate(zip(lg_g, lg_p)):
+        _same(a, b, f"step {i}")
     c.close(); m.close()
 
 
-def test_fullshape_twin_vs_reference_live(model_dir, ref_or_none):
+def test_fullshape_twin_vs_reference_live_bitwise(model_dir, ref_or_none):
     ref = ref_or_none
-    if ref is None:
-        pytest.skip("oracle/_ref does not load on this host")
+    if ref is None or ref.variant() != "native":
+        pytest.skip("the AVX-512 build of oracle/_ref does not load on this host")
     path = _synth(model_dir, "llama3-8b-2l", "Q4_K_M")
-    prompt = np.random.default_rng(42).integers(0, 4096, size=16).tolist()
+    prompt = np.random.default_rng(42).integers(0, 4096, size=40).tolist()
     r = ref.RefModel(path, n_ctx=128, n_threads=min(16, os.cpu_count() or 1))
     ids_r, lg_r = r.greedy(prompt, 16)
     m = engine.Model(path)
     c = engine.Context(m, 128)
     ids_g, lg_g = c.greedy(prompt, 16)
-    n_same = next((i for i, (a, b) in enumerate(zip(ids_g, ids_r)) if a != b), len(ids_r))
-    errs = np.array([rel_err(a, b) for a, b in zip(lg_g[:n_same + 1], lg_r[:n_same + 1])])
-    print("rel errs", errs, "n_same", n_same)
-    assert errs.max() < NORTH_STAR, errs
-    if n_same < len(ids_r):
-        assert greedy_consistent(lg_g[n_same], lg_r[n_same]), (n_same, ids_g, ids_r)
+    assert ids_g == ids_r
+    for i, (a, b) in enumerate(zip(lg_g, lg_r)):
+        _same(a, b, f"step {i}")
     r.close(); c.close(); m.close()
+
+
+def test_long_context_bitwise(model_dir):
+    """attention across several 64-position tiles and a non-multiple-of-32 kv length"""
+    path = _synth(model_dir, "llama3-8b-2l", "Q4_K_M")
+    prompt = np.random.default_rng(1).integers(0, 4096, size=300).tolist()
+    p = port.PortModelRunner(path, n_ctx=512)
+    m = engine.Model(path); c = engine.Context(m, 512)
+    _same(c.decode(prompt, 0), p.decode(prompt, 0), "prefill 300")
+    _same(c.decode([17], 300), p.decode([17], 300), "decode @300")
+    c.close(); m.close()
 
 
 def test_device_greedy_equals_host_greedy_and_is_deterministic(model_dir):
