@@ -441,7 +441,9 @@ __global__ void __launch_bounds__(MV_THREADS, 2) k_matvec(const MatvecArgs a) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t * stg = stage_all[warp];
-    const int warp_global = blockIdx.x * MV_WARPS + warp;
+    // warp-major mapping: unit u -> CTA u % grid, warp (u / grid) % 8, so that few-unit launches (ffn_down: 1024 units)
+    // spread over every SM instead of filling the warps of the first CTAs
+    const int warp_global = warp * gridDim.x + blockIdx.x;
     const int n_warps = gridDim.x * MV_WARPS;
 
     for (int unit = warp_global; unit < a.n_units; unit += n_warps) {
@@ -455,6 +457,9 @@ __global__ void __launch_bounds__(MV_THREADS, 2) k_matvec(const MatvecArgs a) {
         float acc[MAX_CHAIN_SLOTS];
 #pragma unroll
         for (int i = 0; i < MAX_CHAIN_SLOTS; i++) acc[i] = 0.f;
+        // chain slot 0 (the only one for rows_unit*C <= 32, i.e. every full-size matrix): row / lane-of-AVX of this lane
+        const int r0 = lane / C, k0 = lane - r0 * C;
+        const int coef0 = (k0 < 8 ? 0 : 9) * STG_STRIDE, val0 = (k0 < 8 ? 1 + k0 : 10 + (k0 - 8)) * STG_STRIDE;
 
         for (int t = 0; t < m.tiles_unit; t++) {
             const size_t T = (size_t) u * m.tiles_unit + t;
@@ -468,8 +473,21 @@ __global__ void __launch_bounds__(MV_THREADS, 2) k_matvec(const MatvecArgs a) {
             }
             __syncwarp();
             // chain phase: chain ch = (row r of the unit, lane-of-AVX k); blocks of row r inside this tile, in order
+            if (lane < n_chains) {
+                const int lo = max(r0 * nb, t * 32) - t * 32, hi = min(r0 * nb + nb, t * 32 + 32) - t * 32;
+                float v = acc[0];
+                if (type == T_Q5_K && k0 == 8) {
+                    for (int l = lo; l < hi; l++)
+                        v = __fadd_rn(v, __fmul_rn(__uint_as_float(stg[9 * STG_STRIDE + l]), (float) (int) stg[10 * STG_STRIDE + l]));
+                } else {
+#pragma unroll 8
+                    for (int l = lo; l < hi; l++)
+                        v = __fmaf_rn(__uint_as_float(stg[coef0 + l]), (float) (int) stg[val0 + l], v);
+                }
+                acc[0] = v;
+            }
 #pragma unroll
-            for (int cs = 0; cs < MAX_CHAIN_SLOTS; cs++) {
+            for (int cs = 1; cs < MAX_CHAIN_SLOTS; cs++) {
                 const int ch = cs * 32 + lane;
                 if (cs * 32 < n_chains && ch < n_chains) {
                     const int r = ch / C, k = ch - r * C;
@@ -761,95 +779,92 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_attn_softmax(const AttnArgs a) {
-    extern __shared__ double gsum[];                          // one partial per 16-group
-    __shared__ float red[8];
-    __shared__ float bc[2];
+    __shared__ float redf[8];
+    __shared__ double redd[8];
     const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pad = (attn_n_kv(a) + 31) / 32 * 32;
     float * S = a.S + (size_t) h * a.s_stride;
     float mx = -INFINITY;
     for (int i = tid; i < n_pad; i += 256) mx = fmaxf(mx, S[i]);
     mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
+    if (lane == 0) redf[warp] = mx;
     __syncthreads();
-    if (tid == 0) { float m2 = red[0]; for (int w = 1; w < 8; w++) m2 = fmaxf(m2, red[w]); bc[0] = m2; }
-    __syncthreads();
-    mx = bc[0];
+    mx = redf[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, redf[w]);
     // n_pad is a multiple of 32 and the stride is 256, so every warp iteration is either fully in or fully out of
-    // range and half-warps coincide with the reference's 16-wide vectors
+    // range and half-warps coincide with the reference's 16-wide vectors. The per-vector sums (float,
+    // _mm512_reduce_add_ps order) are accumulated in double; double addition of <= 512 such floats is exact up to
+    // one final rounding far below float resolution, so the tree order below equals the reference's serial order
+    // after the cast to float.
+    double part = 0.0;
     for (int i = tid; i < n_pad; i += 256) {
         const float p = v_expf(__fsub_rn(S[i], mx));
         S[i] = p;
         const float gs = reduce_add16_shfl(p);
-        if ((lane & 15) == 0) gsum[i >> 4] = (double) gs;
+        if ((lane & 15) == 0) part += (double) gs;
     }
+    part = warp_sum_d(part);
+    if (lane == 0) redd[warp] = part;
     __syncthreads();
-    if (tid == 0) {
-        double sum = 0.0;
-        for (int i = 0; i < n_pad / 16; i++) sum += gsum[i];  // sequential double accumulation, as the reference
-        bc[1] = (float) (1.0 / sum);
-    }
-    __syncthreads();
-    const float inv = bc[1];
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sum += redd[w];
+    const float inv = (float) (1.0 / sum);
     for (int i = tid; i < n_pad; i += 256) S[i] = __fmul_rn(S[i], inv);
 }
+
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
+
+static constexpr int PV_BATCH = 256;   // V rows per pipeline stage (x 32 B = 8 KB)
 
 template <int GQA>
 __global__ void __launch_bounds__(PV_DIMS * 16) k_attn_pv(const AttnArgs a) {
     constexpr int HD = 128;
     constexpr int NT = PV_DIMS * 16;
-    __shared__ __align__(16) float ps[GQA][PV_CHUNK];
+    __shared__ __align__(16) __half vs[2][PV_BATCH][PV_DIMS];      // 2 x 8 KB
+    __shared__ __align__(16) float ps[GQA][PV_BATCH];
     __shared__ float red[GQA][16][PV_DIMS + 1];
-    // thread = (chain c, dim dl): the 16 lanes of a half-warp read 32 contiguous bytes of one V row
-    const int g = blockIdx.x, c = threadIdx.x / PV_DIMS, dl = threadIdx.x % PV_DIMS, d = blockIdx.y * PV_DIMS + dl;
+    // thread = (chain c, dim dl); a CTA owns 16 dims (one 32-byte sector per V row) of one KV head
+    const int g = blockIdx.x, c = threadIdx.x / PV_DIMS, dl = threadIdx.x % PV_DIMS;
     const int n_kv = attn_n_kv(a);
     const int n_pad = (n_kv + 31) / 32 * 32;
+    const int n_batches = (n_pad + PV_BATCH - 1) / PV_BATCH;
+    const __half * vbase = a.v_cache + g * HD + blockIdx.y * PV_DIMS;
+    auto issue = [&](int b) {
+        const int t0 = b * PV_BATCH, rows = min(PV_BATCH, n_kv - t0);        // rows beyond n_kv are never read (p = 0)
+        for (int i = threadIdx.x; i < rows * 2; i += NT)                    // 2 x 16 B per row
+            cp_async16(&vs[b & 1][i >> 1][(i & 1) * 8], vbase + (size_t) (t0 + (i >> 1)) * a.kv_dim + (i & 1) * 8);
+        cp_async_commit();
+    };
     float acc[GQA];
 #pragma unroll
     for (int h = 0; h < GQA; h++) acc[h] = 0.f;
-    const __half * vcol = a.v_cache + g * HD + d;
-    for (int t0 = 0; t0 < n_pad; t0 += PV_CHUNK) {
-        const int len = min(PV_CHUNK, n_pad - t0);
-        __syncthreads();
+    issue(0);
+    for (int b = 0; b < n_batches; b++) {
+        if (b + 1 < n_batches) issue(b + 1); else cp_async_commit();
+        const int t0 = b * PV_BATCH, len = min(PV_BATCH, n_pad - t0);
         for (int i = threadIdx.x; i < GQA * len; i += NT) {
             const int h = i / len, tt = i - h * len;
             ps[h][tt] = a.S[(size_t) (g * GQA + h) * a.s_stride + t0 + tt];
         }
+        cp_async_wait<1>();
         __syncthreads();
         const int steps = len / 16;
-        int s = 0;
-        for (; s + 32 <= steps; s += 32) {                     // 32 independent loads in flight per thread
-            float vf[32];
+#pragma unroll 4
+        for (int s = 0; s < steps; s++) {
+            const int tt = 16 * s + c;
+            // slots at or beyond n_kv have p == 0 exactly; their (stale) V bytes must not be multiplied (NaN-safe)
+            const float v = t0 + tt < n_kv ? __half2float(vs[b & 1][tt][dl]) : 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; e++) {
-                const int t = t0 + 16 * (s + e) + c;
-                vf[e] = t < n_kv ? __half2float(vcol[(size_t) t * a.kv_dim]) : 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 32; e++) {
-#pragma unroll
-                for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(vf[e], ps[h][16 * (s + e) + c], acc[h]);
-            }
+            for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(v, ps[h][tt], acc[h]);
         }
-        for (; s + 4 <= steps; s += 4) {
-            float vf[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int t = t0 + 16 * (s + e) + c;
-                vf[e] = t < n_kv ? __half2float(vcol[(size_t) t * a.kv_dim]) : 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-#pragma unroll
-                for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(vf[e], ps[h][16 * (s + e) + c], acc[h]);
-            }
-        }
-        for (; s < steps; s++) {
-            const int t = t0 + 16 * s + c;
-            const float v = t < n_kv ? __half2float(vcol[(size_t) t * a.kv_dim]) : 0.f;
-#pragma unroll
-            for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(v, ps[h][16 * s + c], acc[h]);
-        }
+        __syncthreads();
     }
 #pragma unroll
     for (int h = 0; h < GQA; h++) red[h][c][dl] = acc[h];
