@@ -427,6 +427,7 @@ struct b200_ctx {
     float * ffh = nullptr;      // silu(gate)*up [n_ff]
     float * logits = nullptr;   // [n_vocab]
     float * S = nullptr;        // attention scores / probabilities [n_head][n_ctx]
+    unsigned int * tickets = nullptr;
     unsigned long long * amax_key = nullptr;
     std::vector<__half *> kc, vc;   // per local layer
     float2 * rope = nullptr;
@@ -459,7 +460,7 @@ struct b200_ctx {
 extern "C" int b200_n_ctx(const b200_ctx * c) { return c ? c->n_ctx : 0; }
 extern "C" int64_t b200_kernel_launches(const b200_ctx * c) { return c ? c->launches : 0; }
 
-enum { KIND_EMBED = 0, KIND_QKV, KIND_ATTN, KIND_WO, KIND_GATEUP, KIND_DOWN, KIND_HEAD, KIND_COUNT };
+enum { KIND_EMBED = 0, KIND_QKV, KIND_ATTN, KIND_WO, KIND_GATEUP, KIND_DOWN, KIND_HEAD, KIND_ATTN_PV, KIND_COUNT };
 static int g_kind = KIND_EMBED;   // set by enqueue_forward before each launch group
 struct ProfScope {
     b200_ctx * c; cudaEvent_t a = nullptr, b = nullptr;
@@ -468,28 +469,48 @@ struct ProfScope {
 };
 
 template <int EPI>
-static void launch_matvec(b200_ctx * c, const MatvecArgs & a) {
+static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     ProfScope ps(c);
-    const size_t smem = act_smem_bytes(a.k, a.act_q8_0);
+    MatvecArgs a = a_in;
+    a.tiles_unit = a.seg[0].tiles_unit;
+    int sb = 0;
+    for (int i = 0; i < a.n_seg; i++) {
+        if (a.seg[i].tiles_unit != a.tiles_unit) throw std::runtime_error("segments of one launch must share the unit shape");
+        sb = std::max(sb, tile_bytes_of(a.seg[i].type));
+    }
+    a.stage_bytes = (sb + 15) / 16 * 16;
+    a.prefetch = RING_BYTES / a.stage_bytes >= 3 ? 2 : 1;
+    const size_t smem = act_smem_bytes(a.k, a.act_q8_0) + (size_t) MV_WARPS * STG_WORDS * 4 + (size_t) MV_WARPS * RING_BYTES;
     static bool attr_set = false;
-    if (!attr_set) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
-    const int max_ctas = c->sm_count * 2;
-    int grid = (a.n_units + MV_WARPS - 1) / MV_WARPS;
-    grid = std::max(1, std::min(grid, max_ctas));
+    if (!attr_set) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+    if (smem > 227 * 1024) throw std::runtime_error("activation vector too long for the shared-memory budget");
+    const int grid = std::max(1, std::min(a.n_units, c->sm_count));
     k_matvec<EPI><<<grid, MV_THREADS, smem, c->st>>>(a);
     c->launches++;
 }
 
 template <int GQA>
-static void launch_attention_t(b200_ctx * c, const AttnArgs & a, int n_ctx_pad) {
+static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
+    AttnArgs a = a_in;
+    // p chunk: as much of the row as ~96 KB of shared memory holds for the GQA heads, in whole V batches
+    int pch = (96 * 1024) / (GQA * 4) / PV_BATCH * PV_BATCH;
+    pch = std::min(pch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
+    a.p_chunk = pch;
+    const size_t pv_smem = (size_t) GQA * pch * 4;
+    static bool attr_set = false;
+    if (!attr_set) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
     const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
-    k_attn_scores<GQA><<<gs, ATT_THREADS, 0, c->st>>>(a);
-    k_attn_softmax<<<a.n_head, 256, (size_t) (n_ctx_pad / 16) * sizeof(double), c->st>>>(a);
-    const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PV_DIMS));
-    k_attn_pv<GQA><<<gp, PV_DIMS * 16, 0, c->st>>>(a);
+    {
+        g_kind = KIND_ATTN; ProfScope ps(c);
+        k_attn_scores<GQA><<<gs, ATT_THREADS, 0, c->st>>>(a);    // + softmax in the last CTA of each KV head
+    }
+    {
+        g_kind = KIND_ATTN_PV; ProfScope ps(c);
+        const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PV_DIMS));
+        k_attn_pv<GQA><<<gp, PV_DIMS * 16, pv_smem, c->st>>>(a);
+    }
 }
 static void launch_attention(b200_ctx * c, const AttnArgs & a, int n_ctx_pad) {
-    ProfScope ps(c);
     if (a.head_dim != 128) throw std::runtime_error("attention kernels are specialised for head_dim 128");
     switch (a.n_head / a.n_head_kv) {
         case 1: launch_attention_t<1>(c, a, n_ctx_pad); break;
@@ -498,7 +519,7 @@ static void launch_attention(b200_ctx * c, const AttnArgs & a, int n_ctx_pad) {
         case 8: launch_attention_t<8>(c, a, n_ctx_pad); break;
         default: throw std::runtime_error("GQA ratio must be 1, 2, 4 or 8");
     }
-    c->launches += 3;
+    c->launches += 2;
 }
 
 ProfScope::ProfScope(b200_ctx * c_) : c(c_) {
@@ -551,7 +572,7 @@ static void enqueue_forward(b200_ctx * c) {
             g_kind = KIND_ATTN;
             AttnArgs a{};
             a.q = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
-            a.S = c->S; a.s_stride = c->n_ctx; a.out = c->att;
+            a.S = c->S; a.s_stride = c->n_ctx; a.out = c->att; a.tickets = c->tickets;
             a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD;
             a.scale = 1.0f / sqrtf((float) HD);
             a.st = c->d_state; a.n_kv_override = 0; a.round_q_override = 0;
@@ -617,7 +638,7 @@ static cudaGraphExec_t capture(b200_ctx * c, const std::function<void()> & body)
 }
 static int64_t forward_launch_count(const b200_ctx * c) {
     const b200_model & m = *c->m;
-    return (m.has_embd() ? 1 : 0) + (int64_t) m.layers.size() * 7 + (m.has_head() ? 1 : 0);
+    return (m.has_embd() ? 1 : 0) + (int64_t) m.layers.size() * 6 + (m.has_head() ? 1 : 0);
 }
 
 extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
@@ -640,6 +661,8 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         CU(cudaMalloc(&c->ffh, (size_t) m->n_ff * 4));
         CU(cudaMalloc(&c->logits, (size_t) m->n_vocab * 4));
         CU(cudaMalloc(&c->S, (size_t) m->n_head * c->n_ctx * 4));
+        CU(cudaMalloc(&c->tickets, (size_t) m->n_head_kv * 4));
+        CU(cudaMemsetAsync(c->tickets, 0, (size_t) m->n_head_kv * 4, c->st));
         CU(cudaMalloc(&c->amax_key, 8));
         CU(cudaMemsetAsync(c->amax_key, 0, 8, c->st));
         if (HD != 128) throw std::runtime_error("attention kernels are specialised for head_dim 128");
@@ -682,7 +705,7 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     for (auto p : c->kc) cudaFree(p);
     for (auto p : c->vc) cudaFree(p);
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->logits);
-    cudaFree(c->S); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
+    cudaFree(c->S); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits);
     cudaStreamDestroy(c->st);
     delete c;
@@ -1070,13 +1093,14 @@ extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, cons
         tmp.st = st; tmp.sm_count = prop.multiProcessorCount;
         const int n_pad = (n_kv + 31) / 32 * 32;
         DBuf dq((size_t) qd * 4), dk((size_t) n_kv * kvd * 2), dv((size_t) n_kv * kvd * 2), dout((size_t) qd * 4);
-        DBuf dS((size_t) n_head * n_pad * 4);
+        DBuf dS((size_t) n_head * n_pad * 4), dT((size_t) n_head_kv * 4);
+        CU(cudaMemsetAsync(dT.p, 0, (size_t) n_head_kv * 4, st));
         CU(cudaMemcpyAsync(dq.p, q, (size_t) qd * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(dk.p, k_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(dv.p, v_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
         AttnArgs a{};
         a.q = dq.as<float>(); a.k_cache = dk.as<__half>(); a.v_cache = dv.as<__half>();
-        a.S = dS.as<float>(); a.s_stride = n_pad; a.out = dout.as<float>();
+        a.S = dS.as<float>(); a.s_stride = n_pad; a.out = dout.as<float>(); a.tickets = dT.as<unsigned int>();
         a.n_head = n_head; a.n_head_kv = n_head_kv; a.head_dim = head_dim; a.kv_dim = kvd;
         a.scale = scale; a.st = nullptr; a.n_kv_override = n_kv; a.round_q_override = round_q;
         launch_attention(&tmp, a, n_pad);

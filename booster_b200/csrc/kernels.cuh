@@ -68,6 +68,9 @@ struct MatvecArgs {
     const float * norm_w;
     float eps;
     int act_q8_0;              // 0: Q8_K activations, 1: Q8_0 activations
+    int tiles_unit;            // identical for every segment of a launch (same K, same block width)
+    int stage_bytes;           // ring slot size = largest tile of the launch (16-byte multiple)
+    int prefetch;              // tiles in flight ahead of the one being computed (1 or 2); stages = prefetch + 1
     // epilogue
     float * out;
     const float * resid;
@@ -80,8 +83,9 @@ struct MatvecArgs {
     const DecodeState * st;
 };
 
-static constexpr int MV_THREADS = 256;
+static constexpr int MV_THREADS = 384;                      // one persistent CTA per SM
 static constexpr int MV_WARPS   = MV_THREADS / 32;
+static constexpr int RING_BYTES = 13824;                    // per-warp weight ring: 3 Q4_K tiles / 2 Q5_K|Q6_K tiles
 static constexpr int STG_STRIDE = 33;                       // padded row stride of the per-warp staging array
 static constexpr int STG_WORDS  = 14 * STG_STRIDE;          // d, s[8], dmin, prod[4]
 static constexpr int MAX_CHAIN_SLOTS = 12;                  // rows_unit(<=32) * chains(<=12) / 32
@@ -273,6 +277,60 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// weight staging: every warp streams ITS tiles through a private shared-memory ring with cp.async (LDGSTS, 16 B
+// per lane per instruction, no register staging), `prefetch` tiles ahead of the one it is computing, so HBM
+// latency is overlapped with the integer work instead of being exposed once per tile.
+// Slot layout = the tile's planes back to back:  Q4_K qs|sd  Q5_K qs|sd|qh  Q6_K ql|qh|sc|d  Q8_0 qs|d
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__host__ __device__ __forceinline__ int tile_bytes_of(int type) {
+    return type == T_Q4_K ? 4608 : type == T_Q5_K ? 5632 : type == T_Q6_K ? 6720 : 1088;
+}
+__device__ __forceinline__ void issue_tile(const TMat & m, size_t T, int lane, uint8_t * slot) {
+    switch (m.type) {
+        case T_Q4_K: case T_Q5_K: {
+            const uint8_t * q = m.p0 + T * 4096 + lane * 16;
+#pragma unroll
+            for (int c = 0; c < 8; c++) cp_async16(slot + c * 512 + lane * 16, q + c * 512);
+            cp_async16(slot + 4096 + lane * 16, m.p1 + T * 512 + lane * 16);
+            if (m.type == T_Q5_K) {
+                cp_async16(slot + 4608 + lane * 16, m.p2 + T * 1024 + lane * 16);
+                cp_async16(slot + 5120 + lane * 16, m.p2 + T * 1024 + 512 + lane * 16);
+            }
+        } break;
+        case T_Q6_K: {
+            const uint8_t * q = m.p0 + T * 4096 + lane * 16;
+#pragma unroll
+            for (int c = 0; c < 8; c++) cp_async16(slot + c * 512 + lane * 16, q + c * 512);
+            const uint8_t * h = m.p2 + T * 2048 + lane * 16;
+#pragma unroll
+            for (int c = 0; c < 4; c++) cp_async16(slot + 4096 + c * 512 + lane * 16, h + c * 512);
+            cp_async16(slot + 6144 + lane * 16, m.p1 + T * 512 + lane * 16);
+            if (lane < 4) cp_async16(slot + 6656 + lane * 16, m.p3 + T * 64 + lane * 16);
+        } break;
+        default: {
+            cp_async16(slot + lane * 16, m.p0 + T * 1024 + lane * 16);
+            cp_async16(slot + 512 + lane * 16, m.p0 + T * 1024 + 512 + lane * 16);
+            if (lane < 4) cp_async16(slot + 1024 + lane * 16, m.p3 + T * 64 + lane * 16);
+        } break;
+    }
+}
+__device__ __forceinline__ uint4 lds_u4(const uint8_t * p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ uint32_t lds_u32(const uint8_t * p) { return *reinterpret_cast<const uint32_t *>(p); }
+// dp4a with an UNSIGNED first operand (bytes 0..255) and a signed second one
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // per-type block arithmetic: ONE lane = ONE block. Produces the exact per-block integers the reference's AVX2
 // lanes hold (s[m] = the m-th int32 lane of `sumi`, prod[l] = the l-th lane of the mins product) and the
 // per-block fp32 coefficients, and writes them to the warp's staging array stg[k*STG_STRIDE + lane].
@@ -283,47 +341,44 @@ __device__ __forceinline__ int4 lds_act(const ActSmem & A, int slot, int nb, int
 }
 
 template <bool Q5>
-__device__ __forceinline__ void block_q45k(const TMat & m, size_t T, int lane, int bi, const ActSmem & A, uint32_t * stg) {
-    const uint4 * qp = reinterpret_cast<const uint4 *>(m.p0 + T * 4096) + lane;
-    uint4 w[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) w[c] = ldg_stream_v4(qp + c * 32);
-    uint4 qh[2];
-    if (Q5) {
-        const uint4 * hp = reinterpret_cast<const uint4 *>(m.p2 + T * 1024) + lane;
-        qh[0] = ldg_stream_v4(hp); qh[1] = ldg_stream_v4(hp + 32);
-    }
-    const uint32_t * sd = reinterpret_cast<const uint32_t *>(m.p1 + T * 512) + lane;
-    const uint32_t s0 = ldg_u32(sd), s1 = ldg_u32(sd + 32), s2 = ldg_u32(sd + 64), dmw = ldg_u32(sd + 96);
+__device__ __forceinline__ void block_q45k(const uint8_t * slot, int nb, int lane, int bi, const ActSmem & A, uint32_t * stg) {
+    const uint8_t * qp = slot + lane * 16;
+    const uint8_t * sd = slot + 4096 + lane * 4;
+    const uint32_t s0 = lds_u32(sd), s1 = lds_u32(sd + 128), s2 = lds_u32(sd + 256), dmw = lds_u32(sd + 384);
     // the 8 scale bytes and 8 min bytes (get_scale_min_k4 packing, cpp/ggml/src/ggml-quants.c:1891-1898)
     const uint32_t sc_a = s0 & 0x3f3f3f3fu, m_a = s1 & 0x3f3f3f3fu;
     const uint32_t sc_b = (s2 & 0x0f0f0f0fu) | (((s0 >> 6) & 0x03030303u) << 4);
     const uint32_t m_b  = ((s2 >> 4) & 0x0f0f0f0fu) | (((s1 >> 6) & 0x03030303u) << 4);
-    const int nb = m.nb;
-    int s[8];
+    uint4 qh[2];
+    if (Q5) { qh[0] = lds_u4(slot + 4608 + lane * 16); qh[1] = lds_u4(slot + 5120 + lane * 16); }
+    // s = s_lo + (s_hi16 >> 4): the high nibbles are multiplied IN PLACE (mask 0xf0, i.e. 16 x value, unsigned dp4a),
+    // their scaled sum is an exact multiple of 16, so the shift is exact
+    int s_lo[8], s_hi[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = 0;
+    for (int i = 0; i < 8; i++) { s_lo[i] = 0; s_hi[i] = 0; }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const uint32_t scw = j < 2 ? sc_a : sc_b;
         const int sc_lo = (int) ((scw >> ((j & 1) * 16)) & 0xff), sc_hi = (int) ((scw >> ((j & 1) * 16 + 8)) & 0xff);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            const uint4 w = lds_u4(qp + (2 * j + h) * 512);
             const int4 alo = lds_act(A, 4 * j + h, nb, bi);
             const int4 ahi = lds_act(A, 4 * j + 2 + h, nb, bi);
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
-                const uint32_t W = word_of(w[2 * j + h], wi);
-                uint32_t lo = W & 0x0f0f0f0fu, hi = (W >> 4) & 0x0f0f0f0fu;
-                if (Q5) {
+                const uint32_t W = word_of(w, wi);
+                if (!Q5) {
+                    s_lo[4 * h + wi] += sc_lo * __dp4a((int) (W & 0x0f0f0f0fu), word_of(alo, wi), 0);
+                    s_hi[4 * h + wi] += sc_hi * dp4a_us(W & 0xf0f0f0f0u, word_of(ahi, wi), 0);
+                } else {
                     // qh bit 2j -> +16 on the low-nibble weight, bit 2j+1 -> +16 on the high-nibble one
                     const uint32_t H = word_of(qh[h], wi);
-                    lo |= ((H >> (2 * j)) & 0x01010101u) << 4;
-                    hi |= ((H >> (2 * j + 1)) & 0x01010101u) << 4;
+                    const uint32_t lo = (W & 0x0f0f0f0fu) | (((H >> (2 * j)) & 0x01010101u) << 4);
+                    const uint32_t hi = ((W >> 4) & 0x0f0f0f0fu) | (((H >> (2 * j + 1)) & 0x01010101u) << 4);
+                    s_lo[4 * h + wi] += sc_lo * __dp4a((int) lo, word_of(alo, wi), 0);
+                    s_hi[4 * h + wi] += 16 * sc_hi * __dp4a((int) hi, word_of(ahi, wi), 0);
                 }
-                const int L = __dp4a((int) lo, word_of(alo, wi), 0);
-                const int Hh = __dp4a((int) hi, word_of(ahi, wi), 0);
-                s[4 * h + wi] += sc_lo * L + sc_hi * Hh;
             }
         }
     }
@@ -340,7 +395,7 @@ __device__ __forceinline__ void block_q45k(const TMat & m, size_t T, int lane, i
     const float dmin = __fmul_rn(-yd, __high2float(dmh));         // -y[i].d * fp16(x[i].dmin)
     stg[0 * STG_STRIDE + lane] = __float_as_uint(d);
 #pragma unroll
-    for (int i = 0; i < 8; i++) stg[(1 + i) * STG_STRIDE + lane] = (uint32_t) s[i];
+    for (int i = 0; i < 8; i++) stg[(1 + i) * STG_STRIDE + lane] = (uint32_t) (s_lo[i] + (s_hi[i] >> 4));
     stg[9 * STG_STRIDE + lane] = __float_as_uint(dmin);
     if (Q5) {
         stg[10 * STG_STRIDE + lane] = (uint32_t) (p0 + p1 + p2 + p3);
@@ -353,20 +408,13 @@ __device__ __forceinline__ void block_q45k(const TMat & m, size_t T, int lane, i
 // q (0..63 per byte) -> q - 32 as signed bytes, without inter-byte borrows
 __device__ __forceinline__ uint32_t sub32_bytes(uint32_t q) { return ((q | 0x80808080u) - 0x20202020u) ^ 0x80808080u; }
 
-__device__ __forceinline__ void block_q6k(const TMat & m, size_t T, int lane, int bi, const ActSmem & A, uint32_t * stg) {
-    const uint4 * lp = reinterpret_cast<const uint4 *>(m.p0 + T * 4096) + lane;
-    const uint4 * hp = reinterpret_cast<const uint4 *>(m.p2 + T * 2048) + lane;
-    uint4 ql[8], qh[4];
-#pragma unroll
-    for (int c = 0; c < 8; c++) ql[c] = ldg_stream_v4(lp + c * 32);
-#pragma unroll
-    for (int c = 0; c < 4; c++) qh[c] = ldg_stream_v4(hp + c * 32);
-    const uint32_t * sp = reinterpret_cast<const uint32_t *>(m.p1 + T * 512) + lane;
+__device__ __forceinline__ void block_q6k(const uint8_t * slot, int nb, int lane, int bi, const ActSmem & A, uint32_t * stg) {
+    const uint8_t * lp = slot + lane * 16;
+    const uint8_t * hp = slot + 4096 + lane * 16;
     uint32_t sw[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) sw[i] = ldg_u32(sp + i * 32);
-    const float dw = h16_to_f32(ldg_u16(m.p3 + T * 64 + lane * 2));
-    const int nb = m.nb;
+    for (int i = 0; i < 4; i++) sw[i] = lds_u32(slot + 6144 + (i * 32 + lane) * 4);
+    const float dw = __half2float(*reinterpret_cast<const __half *>(slot + 6656 + lane * 2));
     int s[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = 0;
@@ -375,19 +423,24 @@ __device__ __forceinline__ void block_q6k(const TMat & m, size_t T, int lane, in
 #pragma unroll
     for (int n = 0; n < 2; n++) {
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
+        for (int mq = 0; mq < 2; mq++) {
+            const uint4 qh = lds_u4(hp + (2 * n + mq) * 512);
 #pragma unroll
-            for (int mq = 0; mq < 2; mq++) {
-                const int si = 8 * n + 2 * g + mq;
-                const int sc = (int) (int8_t) ((sw[si >> 2] >> ((si & 3) * 8)) & 0xff);
-                const int4 a = lds_act(A, 8 * n + 2 * g + mq, nb, bi);
+            for (int gl = 0; gl < 2; gl++) {                      // ql chunk serves groups gl (low nibble) and gl+2 (high)
+                const uint4 ql = lds_u4(lp + (4 * n + 2 * gl + mq) * 512);
 #pragma unroll
-                for (int wi = 0; wi < 4; wi++) {
-                    const uint32_t QL = word_of(ql[4 * n + 2 * (g & 1) + mq], wi);
-                    const uint32_t QH = word_of(qh[2 * n + mq], wi);
-                    const uint32_t lo = (g >> 1) ? ((QL >> 4) & 0x0f0f0f0fu) : (QL & 0x0f0f0f0fu);
-                    const uint32_t q  = lo | (((QH >> (2 * g)) & 0x03030303u) << 4);
-                    s[4 * mq + wi] += sc * __dp4a((int) sub32_bytes(q), word_of(a, wi), 0);
+                for (int gh = 0; gh < 2; gh++) {
+                    const int g = gl + 2 * gh;
+                    const int si = 8 * n + 2 * g + mq;
+                    const int sc = (int) (int8_t) ((sw[si >> 2] >> ((si & 3) * 8)) & 0xff);
+                    const int4 a = lds_act(A, 8 * n + 2 * g + mq, nb, bi);
+#pragma unroll
+                    for (int wi = 0; wi < 4; wi++) {
+                        const uint32_t QL = word_of(ql, wi), QH = word_of(qh, wi);
+                        const uint32_t lo = gh ? ((QL >> 4) & 0x0f0f0f0fu) : (QL & 0x0f0f0f0fu);
+                        const uint32_t q  = lo | (((QH >> (2 * g)) & 0x03030303u) << 4);
+                        s[4 * mq + wi] += sc * __dp4a((int) sub32_bytes(q), word_of(a, wi), 0);
+                    }
                 }
             }
         }
@@ -398,11 +451,10 @@ __device__ __forceinline__ void block_q6k(const TMat & m, size_t T, int lane, in
     for (int i = 0; i < 8; i++) stg[(1 + i) * STG_STRIDE + lane] = (uint32_t) s[i];
 }
 
-__device__ __forceinline__ void block_q80(const TMat & m, size_t T, int lane, int bi, const ActSmem & A, uint32_t * stg) {
-    const uint4 * qp = reinterpret_cast<const uint4 *>(m.p0 + T * 1024) + lane;
-    const uint4 w0 = ldg_stream_v4(qp), w1 = ldg_stream_v4(qp + 32);
-    const float dw = h16_to_f32(ldg_u16(m.p3 + T * 64 + lane * 2));
-    const int4 a0 = lds_act(A, 0, m.nb, bi), a1 = lds_act(A, 1, m.nb, bi);
+__device__ __forceinline__ void block_q80(const uint8_t * slot, int nb, int lane, int bi, const ActSmem & A, uint32_t * stg) {
+    const uint4 w0 = lds_u4(slot + lane * 16), w1 = lds_u4(slot + 512 + lane * 16);
+    const float dw = __half2float(*reinterpret_cast<const __half *>(slot + 1024 + lane * 2));
+    const int4 a0 = lds_act(A, 0, nb, bi), a1 = lds_act(A, 1, nb, bi);
     const float d = __fmul_rn(dw, A.dx[bi]);                       // fp16(x.d) * fp16(y.d)
     stg[0 * STG_STRIDE + lane] = __float_as_uint(d);
 #pragma unroll
@@ -429,87 +481,112 @@ __device__ __forceinline__ float finish_row(int type, const float * c) {
 // block's integers (block_*), then the chain lanes advance the rows' fp32 fma chains over this tile's blocks in
 // block order; after the unit's last tile one lane per row finishes (hsum) and the epilogue runs on row pairs.
 // ------------------------------------------------------------------------------------------------------------
+struct UnitRef { int si; int u; int row_base; };
+__device__ __forceinline__ UnitRef locate_unit(const MatvecArgs & a, int unit) {
+    UnitRef r; r.si = 0; r.u = unit; r.row_base = 0;
+    if (a.n_seg > 1 && r.u >= a.seg[0].n_units) { r.u -= a.seg[0].n_units; r.row_base += a.seg[0].n_rows; r.si = 1;
+        if (a.n_seg > 2 && r.u >= a.seg[1].n_units) { r.u -= a.seg[1].n_units; r.row_base += a.seg[1].n_rows; r.si = 2; } }
+    return r;
+}
+
 template <int EPI>
-__global__ void __launch_bounds__(MV_THREADS, 2) k_matvec(const MatvecArgs a) {
+__global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const MatvecArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ double red_smem[MV_WARPS];
-    __shared__ uint32_t stage_all[MV_WARPS][STG_WORDS];
+    const size_t act_bytes = act_smem_bytes(a.k, a.act_q8_0);
     const ActSmem A = act_smem_carve(smem_raw, a.k, a.act_q8_0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t * stg = reinterpret_cast<uint32_t *>(smem_raw + act_bytes) + warp * STG_WORDS;
+    uint8_t * ring = smem_raw + act_bytes + (size_t) MV_WARPS * STG_WORDS * 4 + (size_t) warp * RING_BYTES;
+
+    // warp-major mapping: unit u -> CTA u % grid, warp (u / grid) % MV_WARPS, so that few-unit launches
+    // (ffn_down: 1024 units) spread over every SM
+    const int warp_global = warp * gridDim.x + blockIdx.x;
+    const int n_warps = gridDim.x * MV_WARPS;
+    const int TU = a.tiles_unit, PF = a.prefetch, NST = PF + 1;
+    const int my_units = warp_global < a.n_units ? (a.n_units - warp_global + n_warps - 1) / n_warps : 0;
+    const int my_tiles = my_units * TU;
+
+    auto issue = [&](int q) {
+        if (q < my_tiles) {
+            const int j = q / TU, t = q - j * TU;
+            const UnitRef ur = locate_unit(a, warp_global + j * n_warps);
+            const TMat & m = ur.si == 0 ? a.seg[0] : (ur.si == 1 ? a.seg[1] : a.seg[2]);
+            issue_tile(m, (size_t) ur.u * TU + t, lane, ring + (size_t) (q % NST) * a.stage_bytes);
+        }
+        cp_async_commit();
+    };
+    // the weights do not depend on the activations: start streaming before the prologue
+    for (int q = 0; q < PF; q++) issue(q);
 
     prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t * stg = stage_all[warp];
-    // warp-major mapping: unit u -> CTA u % grid, warp (u / grid) % 8, so that few-unit launches (ffn_down: 1024 units)
-    // spread over every SM instead of filling the warps of the first CTAs
-    const int warp_global = warp * gridDim.x + blockIdx.x;
-    const int n_warps = gridDim.x * MV_WARPS;
-
-    for (int unit = warp_global; unit < a.n_units; unit += n_warps) {
-        // segment lookup by branches (dynamic indexing of the parameter struct would force a local copy)
-        int u = unit, si = 0, row_base = 0;
-        if (a.n_seg > 1 && u >= a.seg[0].n_units) { u -= a.seg[0].n_units; row_base += a.seg[0].n_rows; si = 1;
-            if (a.n_seg > 2 && u >= a.seg[1].n_units) { u -= a.seg[1].n_units; row_base += a.seg[1].n_rows; si = 2; } }
-        const TMat & m = si == 0 ? a.seg[0] : (si == 1 ? a.seg[1] : a.seg[2]);
-        const int type = m.type, nb = m.nb, C = chains_of(type);
-        const int n_chains = m.rows_unit * C;
-        float acc[MAX_CHAIN_SLOTS];
+    float acc[MAX_CHAIN_SLOTS];
+    UnitRef ur; ur.si = 0; ur.u = 0; ur.row_base = 0;
+    int type = 0, nb = 1, C = 8, n_chains = 0, rows_unit = 2, r0 = 0, k0 = 0, coef0 = 0, val0 = 0;
+    for (int q = 0; q < my_tiles; q++) {
+        issue(q + PF);
+        if (PF == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+        __syncwarp();
+        const int j = q / TU, t = q - j * TU;
+        if (t == 0) {
+            ur = locate_unit(a, warp_global + j * n_warps);
+            const TMat & m = ur.si == 0 ? a.seg[0] : (ur.si == 1 ? a.seg[1] : a.seg[2]);
+            type = m.type; nb = m.nb; C = chains_of(type); rows_unit = m.rows_unit; n_chains = rows_unit * C;
 #pragma unroll
-        for (int i = 0; i < MAX_CHAIN_SLOTS; i++) acc[i] = 0.f;
-        // chain slot 0 (the only one for rows_unit*C <= 32, i.e. every full-size matrix): row / lane-of-AVX of this lane
-        const int r0 = lane / C, k0 = lane - r0 * C;
-        const int coef0 = (k0 < 8 ? 0 : 9) * STG_STRIDE, val0 = (k0 < 8 ? 1 + k0 : 10 + (k0 - 8)) * STG_STRIDE;
-
-        for (int t = 0; t < m.tiles_unit; t++) {
-            const size_t T = (size_t) u * m.tiles_unit + t;
-            const int li = t * 32 + lane;                          // block index inside the unit
-            const int bi = li % nb;
-            switch (type) {
-                case T_Q4_K: block_q45k<false>(m, T, lane, bi, A, stg); break;
-                case T_Q5_K: block_q45k<true>(m, T, lane, bi, A, stg); break;
-                case T_Q6_K: block_q6k(m, T, lane, bi, A, stg); break;
-                default:     block_q80(m, T, lane, bi, A, stg); break;
+            for (int i = 0; i < MAX_CHAIN_SLOTS; i++) acc[i] = 0.f;
+            // chain slot 0 (the only one when rows_unit*C <= 32, i.e. for every full-size matrix)
+            r0 = lane / C; k0 = lane - r0 * C;
+            coef0 = (k0 < 8 ? 0 : 9) * STG_STRIDE; val0 = (k0 < 8 ? 1 + k0 : 10 + (k0 - 8)) * STG_STRIDE;
+        }
+        const uint8_t * slot = ring + (size_t) (q % NST) * a.stage_bytes;
+        const int bi = (t * 32 + lane) % nb;
+        switch (type) {
+            case T_Q4_K: block_q45k<false>(slot, nb, lane, bi, A, stg); break;
+            case T_Q5_K: block_q45k<true>(slot, nb, lane, bi, A, stg); break;
+            case T_Q6_K: block_q6k(slot, nb, lane, bi, A, stg); break;
+            default:     block_q80(slot, nb, lane, bi, A, stg); break;
+        }
+        __syncwarp();
+        // chain phase: chain = (row r of the unit, lane-of-AVX k); blocks of row r inside this tile, in block order
+        if (lane < n_chains) {
+            const int lo = max(r0 * nb, t * 32) - t * 32, hi = min(r0 * nb + nb, t * 32 + 32) - t * 32;
+            float v = acc[0];
+            if (type == T_Q5_K && k0 == 8) {
+                // summs += dmin * (float) sum(prod): separate mul and add (cpp/ggml/src/ggml-quants.c:7516)
+                for (int l = lo; l < hi; l++)
+                    v = __fadd_rn(v, __fmul_rn(__uint_as_float(stg[9 * STG_STRIDE + l]), (float) (int) stg[10 * STG_STRIDE + l]));
+            } else {
+#pragma unroll 8
+                for (int l = lo; l < hi; l++)
+                    v = __fmaf_rn(__uint_as_float(stg[coef0 + l]), (float) (int) stg[val0 + l], v);
             }
-            __syncwarp();
-            // chain phase: chain ch = (row r of the unit, lane-of-AVX k); blocks of row r inside this tile, in order
-            if (lane < n_chains) {
-                const int lo = max(r0 * nb, t * 32) - t * 32, hi = min(r0 * nb + nb, t * 32 + 32) - t * 32;
-                float v = acc[0];
-                if (type == T_Q5_K && k0 == 8) {
+            acc[0] = v;
+        }
+#pragma unroll
+        for (int cs = 1; cs < MAX_CHAIN_SLOTS; cs++) {
+            const int ch = cs * 32 + lane;
+            if (cs * 32 < n_chains && ch < n_chains) {
+                const int r = ch / C, kk = ch - r * C;
+                const int lo = max(r * nb, t * 32) - t * 32, hi = min(r * nb + nb, t * 32 + 32) - t * 32;
+                const int coef_row = kk < 8 ? 0 : 9;
+                const int val_row  = kk < 8 ? 1 + kk : 10 + (kk - 8);
+                float v = acc[cs];
+                if (type == T_Q5_K && kk == 8) {
                     for (int l = lo; l < hi; l++)
                         v = __fadd_rn(v, __fmul_rn(__uint_as_float(stg[9 * STG_STRIDE + l]), (float) (int) stg[10 * STG_STRIDE + l]));
                 } else {
-#pragma unroll 8
                     for (int l = lo; l < hi; l++)
-                        v = __fmaf_rn(__uint_as_float(stg[coef0 + l]), (float) (int) stg[val0 + l], v);
+                        v = __fmaf_rn(__uint_as_float(stg[coef_row * STG_STRIDE + l]), (float) (int) stg[val_row * STG_STRIDE + l], v);
                 }
-                acc[0] = v;
+                acc[cs] = v;
             }
-#pragma unroll
-            for (int cs = 1; cs < MAX_CHAIN_SLOTS; cs++) {
-                const int ch = cs * 32 + lane;
-                if (cs * 32 < n_chains && ch < n_chains) {
-                    const int r = ch / C, k = ch - r * C;
-                    const int lo = max(r * nb, t * 32) - t * 32, hi = min(r * nb + nb, t * 32 + 32) - t * 32;
-                    const int coef_row = k < 8 ? 0 : 9;
-                    const int val_row  = k < 8 ? 1 + k : 10 + (k - 8);
-                    float v = acc[cs];
-                    if (type == T_Q5_K && k == 8) {
-                        // summs += dmin * (float) sum(prod): separate mul and add (cpp/ggml/src/ggml-quants.c:7516)
-                        for (int l = lo; l < hi; l++)
-                            v = __fadd_rn(v, __fmul_rn(__uint_as_float(stg[9 * STG_STRIDE + l]), (float) (int) stg[10 * STG_STRIDE + l]));
-                    } else {
-#pragma unroll 4
-                        for (int l = lo; l < hi; l++)
-                            v = __fmaf_rn(__uint_as_float(stg[coef_row * STG_STRIDE + l]), (float) (int) stg[val_row * STG_STRIDE + l], v);
-                    }
-                    acc[cs] = v;
-                }
-            }
-            __syncwarp();
         }
-        // publish chain results, finish one row per lane
+        __syncwarp();
+        if (t != TU - 1) continue;
+
+        // ---- unit complete: publish chain results, finish one row per lane, epilogue on row pairs
         float * fin = reinterpret_cast<float *>(stg);
 #pragma unroll
         for (int cs = 0; cs < MAX_CHAIN_SLOTS; cs++) {
@@ -518,12 +595,12 @@ __global__ void __launch_bounds__(MV_THREADS, 2) k_matvec(const MatvecArgs a) {
         }
         __syncwarp();
         float val = 0.f;
-        if (lane < m.rows_unit) val = finish_row(type, fin + lane * C);
+        if (lane < rows_unit) val = finish_row(type, fin + lane * C);
         const float nxt = __shfl_down_sync(0xffffffffu, val, 1);
         __syncwarp();
-        if (lane < m.rows_unit && (lane & 1) == 0) {
+        if (lane < rows_unit && (lane & 1) == 0) {
             const float v0 = val, v1 = nxt;
-            const int row = row_base + u * m.rows_unit + lane;     // virtual row of v0; v1 is row + 1
+            const int row = ur.row_base + ur.u * rows_unit + lane;  // virtual row of v0; v1 is row + 1
             if (EPI == EPI_STORE) {
                 a.out[row] = v0; a.out[row + 1] = v1;
             } else if (EPI == EPI_RESID) {
@@ -554,6 +631,7 @@ __global__ void __launch_bounds__(MV_THREADS, 2) k_matvec(const MatvecArgs a) {
             }
         }
     }
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -697,85 +775,128 @@ struct AttnArgs {
     const DecodeState * st;
     int n_kv_override;        // >0: use instead of st->pos+1 (operator-level test)
     int round_q_override;     // operator-level test of the batch>1 arithmetic
+    unsigned int * tickets;   // [n_head_kv] zero-initialised, self-resetting (last scores CTA of a KV head runs the softmax)
+    int p_chunk;              // positions of p staged in shared memory by k_attn_pv (multiple of PV_BATCH)
 };
 __device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1; }
+
+// soft_max_ext of one head row by `nw` cooperating warps (w = 0..nw-1), see k_attn_softmax for the order argument
+__device__ __forceinline__ void softmax_row(float * S, int n_pad, int w, int nw, int lane, float * redf, double * redd,
+                                            int bar_id, int bar_threads) {
+    float mx = -INFINITY;
+    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) mx = fmaxf(mx, __ldcg(S + i));
+    mx = warp_max(mx);
+    if (lane == 0) redf[w] = mx;
+    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
+    mx = redf[0];
+    for (int j = 1; j < nw; j++) mx = fmaxf(mx, redf[j]);
+    double part = 0.0;
+    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) {
+        const float p = v_expf(__fsub_rn(__ldcg(S + i), mx));
+        S[i] = p;
+        const float gs = reduce_add16_shfl(p);
+        if ((lane & 15) == 0) part += (double) gs;
+    }
+    part = warp_sum_d(part);
+    if (lane == 0) redd[w] = part;
+    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
+    double sum = 0.0;
+    for (int j = 0; j < nw; j++) sum += redd[j];
+    const float inv = (float) (1.0 / sum);
+    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) S[i] = __fmul_rn(S[i], inv);   // own elements only
+}
 
 template <int GQA>
 __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     constexpr int HD = 128;
     __shared__ __align__(16) float qs[GQA][HD];
+    __shared__ float redf[GQA][8];
+    __shared__ double redd[GQA][8];
+    __shared__ unsigned int s_ticket;
     const int g = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
     const int n_kv = attn_n_kv(a);
     const int n_pad = (n_kv + 31) / 32 * 32;
     if (tile * ATT_TILE >= n_pad) return;
     const int round_q = a.st ? a.st->round_q : a.round_q_override;
+    const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
+    // K first (it does not depend on q): 8 x 8-byte loads per lane in flight while q is fetched
+    float kf[8][4];
+#pragma unroll
+    for (int s = 0; s < 8; s++) { kf[s][0] = 0.f; kf[s][1] = 0.f; kf[s][2] = 0.f; kf[s][3] = 0.f; }
+    if (t < n_kv) {
+        const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
+        uint2 kv[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);        // 4 halfs at element 16s + 4c4
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].y));
+            kf[s][0] = f0.x; kf[s][1] = f0.y; kf[s][2] = f1.x; kf[s][3] = f1.y;
+        }
+    }
     for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
         float v = a.q[(size_t) (g * GQA) * HD + i];
         if (round_q) v = __half2float(__float2half_rn(v));    // src1 converted to the vec_dot_type F16 (ggml.c:12345-12371)
         (&qs[0][0])[i] = v;
     }
     __syncthreads();
-    const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
-    if (t >= n_pad) return;                                   // whole 4-lane group exits together
-    float res[GQA];
+    if (t < n_pad) {                                          // n_pad % 32 == 0: whole warps take this branch together
+        float res[GQA];
 #pragma unroll
-    for (int h = 0; h < GQA; h++) res[h] = 0.f;
-    // every lane of a group takes the same branch (t is shared), but groups of one warp may differ: shuffles are
-    // executed unconditionally on zeros for the padded positions
-    float kf[8][4];
+        for (int h = 0; h < GQA; h++) {
+            float ch[4];
+            if (!round_q) {
+                // tinyBLAS<16>: lane c: acc = fma(k[16s+c], q[16s+c], acc), s = 0..7
 #pragma unroll
-    for (int s = 0; s < 8; s++) { kf[s][0] = 0.f; kf[s][1] = 0.f; kf[s][2] = 0.f; kf[s][3] = 0.f; }
-    if (t < n_kv) {
-        const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
+                for (int e = 0; e < 4; e++) ch[e] = 0.f;
 #pragma unroll
-        for (int s = 0; s < 8; s++) {
-            const uint2 kv = __ldg(kr + s * 4);               // 4 halfs at element 16s + 4c4
-            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv.x));
-            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv.y));
-            kf[s][0] = f0.x; kf[s][1] = f0.y; kf[s][2] = f1.x; kf[s][3] = f1.y;
+                for (int s = 0; s < 8; s++) {
+                    const float4 qv = *reinterpret_cast<const float4 *>(&qs[h][16 * s + 4 * c4]);
+                    ch[0] = __fmaf_rn(kf[s][0], qv.x, ch[0]); ch[1] = __fmaf_rn(kf[s][1], qv.y, ch[1]);
+                    ch[2] = __fmaf_rn(kf[s][2], qv.z, ch[2]); ch[3] = __fmaf_rn(kf[s][3], qv.w, ch[3]);
+                }
+            } else {
+                // ggml_vec_dot_f16: sum[j][c] over i in {0, 64}: element i + 16j + c; then (0+2)+(1+3)
+                float aj[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float4 q0 = *reinterpret_cast<const float4 *>(&qs[h][16 * j + 4 * c4]);
+                    const float4 q1 = *reinterpret_cast<const float4 *>(&qs[h][64 + 16 * j + 4 * c4]);
+                    aj[j][0] = __fmaf_rn(kf[4 + j][0], q1.x, __fmul_rn(kf[j][0], q0.x));
+                    aj[j][1] = __fmaf_rn(kf[4 + j][1], q1.y, __fmul_rn(kf[j][1], q0.y));
+                    aj[j][2] = __fmaf_rn(kf[4 + j][2], q1.z, __fmul_rn(kf[j][2], q0.z));
+                    aj[j][3] = __fmaf_rn(kf[4 + j][3], q1.w, __fmul_rn(kf[j][3], q0.w));
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) ch[e] = __fadd_rn(__fadd_rn(aj[0][e], aj[2][e]), __fadd_rn(aj[1][e], aj[3][e]));
+            }
+            // _mm512_reduce_add_ps over the 16 chains: lanes c4=0..3 hold chains 4c4..4c4+3
+            float t3[4], t6[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) t3[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, ch[e], 2), ch[e]);   // a[8+i] + a[i] (valid in c4 = 0,1)
+#pragma unroll
+            for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);   // t3[4+i] + t3[i] (valid in c4 = 0)
+            res[h] = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
+        }
+        if (c4 == 0) {
+#pragma unroll
+            for (int h = 0; h < GQA; h++)
+                a.S[(size_t) (g * GQA + h) * a.s_stride + t] = t < n_kv ? __fmul_rn(res[h], a.scale) : -INFINITY;
         }
     }
-#pragma unroll
-    for (int h = 0; h < GQA; h++) {
-        float ch[4];
-        if (!round_q) {
-            // tinyBLAS<16>: lane c: acc = fma(k[16s+c], q[16s+c], acc), s = 0..7
-#pragma unroll
-            for (int e = 0; e < 4; e++) ch[e] = 0.f;
-#pragma unroll
-            for (int s = 0; s < 8; s++) {
-                const float4 qv = *reinterpret_cast<const float4 *>(&qs[h][16 * s + 4 * c4]);
-                ch[0] = __fmaf_rn(kf[s][0], qv.x, ch[0]); ch[1] = __fmaf_rn(kf[s][1], qv.y, ch[1]);
-                ch[2] = __fmaf_rn(kf[s][2], qv.z, ch[2]); ch[3] = __fmaf_rn(kf[s][3], qv.w, ch[3]);
-            }
-        } else {
-            // ggml_vec_dot_f16: sum[j][c] over i in {0, 64}: element i + 16j + c; then (0+2)+(1+3)
-            float aj[4][4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float4 q0 = *reinterpret_cast<const float4 *>(&qs[h][16 * j + 4 * c4]);
-                const float4 q1 = *reinterpret_cast<const float4 *>(&qs[h][64 + 16 * j + 4 * c4]);
-                aj[j][0] = __fmaf_rn(kf[4 + j][0], q1.x, __fmul_rn(kf[j][0], q0.x));
-                aj[j][1] = __fmaf_rn(kf[4 + j][1], q1.y, __fmul_rn(kf[j][1], q0.y));
-                aj[j][2] = __fmaf_rn(kf[4 + j][2], q1.z, __fmul_rn(kf[j][2], q0.z));
-                aj[j][3] = __fmaf_rn(kf[4 + j][3], q1.w, __fmul_rn(kf[j][3], q0.w));
-            }
-#pragma unroll
-            for (int e = 0; e < 4; e++) ch[e] = __fadd_rn(__fadd_rn(aj[0][e], aj[2][e]), __fadd_rn(aj[1][e], aj[3][e]));
-        }
-        // _mm512_reduce_add_ps over the 16 chains: lanes c4=0..3 hold chains 4c4..4c4+3
-        float t3[4], t6[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) t3[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, ch[e], 2), ch[e]);   // a[8+i] + a[i] (valid in c4 = 0,1)
-#pragma unroll
-        for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);   // t3[4+i] + t3[i] (valid in c4 = 0)
-        res[h] = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
-    }
-    if (c4 == 0) {
-#pragma unroll
-        for (int h = 0; h < GQA; h++)
-            a.S[(size_t) (g * GQA + h) * a.s_stride + t] = t < n_kv ? __fmul_rn(res[h], a.scale) : -INFINITY;
-    }
+    // ---- the last CTA of this KV head (atomic ticket) normalises the GQA rows: no separate softmax launch
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&a.tickets[g], 1u);
+    __syncthreads();
+    const unsigned n_act = (unsigned) ((n_pad + ATT_TILE - 1) / ATT_TILE);
+    if (s_ticket != n_act - 1) return;
+    __threadfence();
+    if (tid == 0) a.tickets[g] = 0u;
+    constexpr int NW = 8 / GQA;                               // warps per head (8 warps, GQA in {1,2,4,8})
+    const int warp = tid >> 5, lane = tid & 31, hl = warp / NW, w = warp % NW;
+    softmax_row(a.S + (size_t) (g * GQA + hl) * a.s_stride, n_pad, w, NW, lane, redf[hl], redd[hl], 1 + hl, NW * 32);
 }
 
 __global__ void __launch_bounds__(256) k_attn_softmax(const AttnArgs a) {
@@ -814,58 +935,67 @@ __global__ void __launch_bounds__(256) k_attn_softmax(const AttnArgs a) {
     for (int i = tid; i < n_pad; i += 256) S[i] = __fmul_rn(S[i], inv);
 }
 
-__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
-    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
-
 static constexpr int PV_BATCH = 256;   // V rows per pipeline stage (x 32 B = 8 KB)
 
 template <int GQA>
 __global__ void __launch_bounds__(PV_DIMS * 16) k_attn_pv(const AttnArgs a) {
     constexpr int HD = 128;
     constexpr int NT = PV_DIMS * 16;
-    __shared__ __align__(16) __half vs[2][PV_BATCH][PV_DIMS];      // 2 x 8 KB
-    __shared__ __align__(16) float ps[GQA][PV_BATCH];
+    extern __shared__ __align__(16) float ps_dyn[];                 // [GQA][p_chunk]
+    __shared__ __align__(16) __half vs[3][PV_BATCH][PV_DIMS];      // 3 x 8 KB ring
     __shared__ float red[GQA][16][PV_DIMS + 1];
     // thread = (chain c, dim dl); a CTA owns 16 dims (one 32-byte sector per V row) of one KV head
     const int g = blockIdx.x, c = threadIdx.x / PV_DIMS, dl = threadIdx.x % PV_DIMS;
     const int n_kv = attn_n_kv(a);
     const int n_pad = (n_kv + 31) / 32 * 32;
+    const int PCH = a.p_chunk;
     const int n_batches = (n_pad + PV_BATCH - 1) / PV_BATCH;
     const __half * vbase = a.v_cache + g * HD + blockIdx.y * PV_DIMS;
-    auto issue = [&](int b) {
-        const int t0 = b * PV_BATCH, rows = min(PV_BATCH, n_kv - t0);        // rows beyond n_kv are never read (p = 0)
-        for (int i = threadIdx.x; i < rows * 2; i += NT)                    // 2 x 16 B per row
-            cp_async16(&vs[b & 1][i >> 1][(i & 1) * 8], vbase + (size_t) (t0 + (i >> 1)) * a.kv_dim + (i & 1) * 8);
+    auto issue_v = [&](int b) {
+        if (b < n_batches) {
+            const int t0 = b * PV_BATCH, rows = min(PV_BATCH, n_kv - t0);    // rows beyond n_kv are never read (p = 0)
+            for (int i = threadIdx.x; i < rows * 2; i += NT)                // 2 x 16 B per row
+                cp_async16(&vs[b % 3][i >> 1][(i & 1) * 8], vbase + (size_t) (t0 + (i >> 1)) * a.kv_dim + (i & 1) * 8);
+        }
         cp_async_commit();
+    };
+    auto issue_p = [&](int pc) {                                   // probabilities of chunk pc for the GQA heads
+        const int t0 = pc * PCH, len = min(PCH, n_pad - t0);       // len is a multiple of 32: 16-byte pieces
+        for (int i = threadIdx.x; i < GQA * (len / 4); i += NT) {
+            const int h = i / (len / 4), j = i - h * (len / 4);
+            cp_async16(ps_dyn + (size_t) h * PCH + 4 * j, a.S + (size_t) (g * GQA + h) * a.s_stride + t0 + 4 * j);
+        }
     };
     float acc[GQA];
 #pragma unroll
     for (int h = 0; h < GQA; h++) acc[h] = 0.f;
-    issue(0);
+    issue_p(0);
+    issue_v(0);
+    issue_v(1);
     for (int b = 0; b < n_batches; b++) {
-        if (b + 1 < n_batches) issue(b + 1); else cp_async_commit();
-        const int t0 = b * PV_BATCH, len = min(PV_BATCH, n_pad - t0);
-        for (int i = threadIdx.x; i < GQA * len; i += NT) {
-            const int h = i / len, tt = i - h * len;
-            ps[h][tt] = a.S[(size_t) (g * GQA + h) * a.s_stride + t0 + tt];
+        const int t0 = b * PV_BATCH;
+        if (b > 0 && t0 % PCH == 0) {                              // next p chunk (contexts longer than p_chunk only)
+            __syncthreads();
+            issue_p(t0 / PCH);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
         }
-        cp_async_wait<1>();
+        issue_v(b + 2);
+        cp_async_wait<2>();
         __syncthreads();
-        const int steps = len / 16;
+        const int len = min(PV_BATCH, n_pad - t0), steps = len / 16, pt0 = t0 % PCH;
 #pragma unroll 4
         for (int s = 0; s < steps; s++) {
             const int tt = 16 * s + c;
             // slots at or beyond n_kv have p == 0 exactly; their (stale) V bytes must not be multiplied (NaN-safe)
-            const float v = t0 + tt < n_kv ? __half2float(vs[b & 1][tt][dl]) : 0.f;
+            const float v = t0 + tt < n_kv ? __half2float(vs[b % 3][tt][dl]) : 0.f;
 #pragma unroll
-            for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(v, ps[h][tt], acc[h]);
+            for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(v, ps_dyn[(size_t) h * PCH + pt0 + tt], acc[h]);
         }
         __syncthreads();
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int h = 0; h < GQA; h++) red[h][c][dl] = acc[h];
     __syncthreads();

@@ -89,7 +89,8 @@ int64_t b200_kernel_launches(const b200_ctx * c);
 /* device time (CUDA events on the engine's stream) of the last b200_generate_greedy call, milliseconds */
 float   b200_last_device_ms(const b200_ctx * c);
 /* one token, un-graphed, with an event pair around every launch: summed device ms and launch count per kernel
- * kind (0 embed, 1 qkv, 2 attention, 3 wo, 4 gate/up, 5 down, 6 head) — the live per-kernel roofline of bench.py */
+ * kind (0 embed, 1 qkv, 2 attention scores+softmax, 3 wo, 4 gate/up, 5 down, 6 head, 7 attention P.V) — the live
+ * per-kernel roofline of bench.py */
 int     b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms_by_kind[8], int32_t n_by_kind[8]);
 
 /* µs-resolution per-token timings of a finished bridge job (additive companion of promptEval()/timing(),

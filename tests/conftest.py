@@ -4,6 +4,9 @@ helpers. `-m "not gpu"` covers the oracle against the golden vectors, host logic
 import os
 import sys
 
+# the CPU oracles are OpenMP code: on a 128-core GPU host the default thread count oversubscribes badly
+os.environ.setdefault("OMP_NUM_THREADS", "16")
+
 import numpy as np
 import pytest
 
