@@ -481,9 +481,9 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     a.stage_bytes = (sb + 15) / 16 * 16;
     a.prefetch = RING_BYTES / a.stage_bytes >= 3 ? 2 : 1;
     const size_t smem = act_smem_bytes(a.k, a.act_q8_0) + (size_t) MV_WARPS * STG_WORDS * 4 + (size_t) MV_WARPS * RING_BYTES;
-    static bool attr_set = false;
-    if (!attr_set) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
-    if (smem > 227 * 1024) throw std::runtime_error("activation vector too long for the shared-memory budget");
+    static size_t attr_smem = 0;
+    if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
+    if (smem > attr_smem) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem = smem; }
     const int grid = std::max(1, std::min(a.n_units, c->sm_count));
     k_matvec<EPI><<<grid, MV_THREADS, smem, c->st>>>(a);
     c->launches++;
@@ -497,8 +497,8 @@ static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pa
     pch = std::min(pch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
     a.p_chunk = pch;
     const size_t pv_smem = (size_t) GQA * pch * 4;
-    static bool attr_set = false;
-    if (!attr_set) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    static size_t attr_smem = 48 * 1024 - 1;
+    if (pv_smem > attr_smem) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_smem = pv_smem; }
     const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
     {
         g_kind = KIND_ATTN; ProfScope ps(c);
