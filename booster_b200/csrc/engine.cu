@@ -497,7 +497,7 @@ static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pa
     pch = std::min(pch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
     a.p_chunk = pch;
     const size_t pv_smem = (size_t) GQA * pch * 4;
-    static size_t attr_smem = 48 * 1024 - 1;
+    static size_t attr_smem = 0;     // static + dynamic exceeds 48 KB even for short contexts: always opt in
     if (pv_smem > attr_smem) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_smem = pv_smem; }
     const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
     {
