@@ -492,17 +492,23 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
 template <int GQA>
 static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
     AttnArgs a = a_in;
-    // p chunk: as much of the row as ~96 KB of shared memory holds for the GQA heads, in whole V batches
-    int pch = (96 * 1024) / (GQA * 4) / PV_BATCH * PV_BATCH;
+    // P.V chunk: p rows (GQA x 4 B) + V rows (32 B) per position, up to ~200 KB of shared memory
+    int pch = (200 * 1024) / (GQA * 4 + 32) / PV_BATCH * PV_BATCH;
     pch = std::min(pch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
     a.p_chunk = pch;
-    const size_t pv_smem = (size_t) GQA * pch * 4;
-    static size_t attr_smem = 0;     // static + dynamic exceeds 48 KB even for short contexts: always opt in
-    if (pv_smem > attr_smem) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_smem = pv_smem; }
+    const size_t pv_smem = (size_t) pch * (GQA * 4 + 32);
+    // fused softmax needs the GQA score rows in the shared memory of every scores CTA: only worth it (and only
+    // possible) for rows up to 64 KB; longer contexts run the stand-alone softmax kernel
+    a.fuse_softmax = (size_t) GQA * a.s_stride * 4 <= 64 * 1024;
+    const size_t sc_smem = a.fuse_softmax ? (size_t) GQA * a.s_stride * 4 : 0;
+    static size_t attr_pv = 0, attr_sc = 0;
+    if (pv_smem > attr_pv) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_pv = pv_smem; }
+    if (sc_smem > attr_sc) { CU(cudaFuncSetAttribute(k_attn_scores<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc_smem)); attr_sc = sc_smem; }
     const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
     {
         g_kind = KIND_ATTN; ProfScope ps(c);
-        k_attn_scores<GQA><<<gs, ATT_THREADS, 0, c->st>>>(a);    // + softmax in the last CTA of each KV head
+        k_attn_scores<GQA><<<gs, ATT_THREADS, sc_smem, c->st>>>(a);    // + softmax in the last CTA of each KV head
+        if (!a.fuse_softmax) k_attn_softmax<<<a.n_head, 256, 0, c->st>>>(a);
     }
     {
         g_kind = KIND_ATTN_PV; ProfScope ps(c);

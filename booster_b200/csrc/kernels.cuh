@@ -777,14 +777,16 @@ struct AttnArgs {
     int round_q_override;     // operator-level test of the batch>1 arithmetic
     unsigned int * tickets;   // [n_head_kv] zero-initialised, self-resetting (last scores CTA of a KV head runs the softmax)
     int p_chunk;              // positions of p staged in shared memory by k_attn_pv (multiple of PV_BATCH)
+    int fuse_softmax;         // 1: the last scores CTA of a KV head normalises its rows; 0: k_attn_softmax follows
 };
 __device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1; }
 
-// soft_max_ext of one head row by `nw` cooperating warps (w = 0..nw-1), see k_attn_softmax for the order argument
-__device__ __forceinline__ void softmax_row(float * S, int n_pad, int w, int nw, int lane, float * redf, double * redd,
-                                            int bar_id, int bar_threads) {
+// soft_max_ext of one head row by `nw` cooperating warps (w = 0..nw-1) on a shared-memory copy `row` of the
+// scores; the normalised probabilities are written to S. See k_attn_softmax for the summation-order argument.
+__device__ __forceinline__ void softmax_row(float * row, float * S, int n_pad, int w, int nw, int lane, float * redf,
+                                            double * redd, int bar_id, int bar_threads) {
     float mx = -INFINITY;
-    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) mx = fmaxf(mx, __ldcg(S + i));
+    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) mx = fmaxf(mx, row[i]);
     mx = warp_max(mx);
     if (lane == 0) redf[w] = mx;
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
@@ -792,8 +794,8 @@ __device__ __forceinline__ void softmax_row(float * S, int n_pad, int w, int nw,
     for (int j = 1; j < nw; j++) mx = fmaxf(mx, redf[j]);
     double part = 0.0;
     for (int i = w * 32 + lane; i < n_pad; i += nw * 32) {
-        const float p = v_expf(__fsub_rn(__ldcg(S + i), mx));
-        S[i] = p;
+        const float p = v_expf(__fsub_rn(row[i], mx));
+        row[i] = p;
         const float gs = reduce_add16_shfl(p);
         if ((lane & 15) == 0) part += (double) gs;
     }
@@ -803,12 +805,13 @@ __device__ __forceinline__ void softmax_row(float * S, int n_pad, int w, int nw,
     double sum = 0.0;
     for (int j = 0; j < nw; j++) sum += redd[j];
     const float inv = (float) (1.0 / sum);
-    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) S[i] = __fmul_rn(S[i], inv);   // own elements only
+    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) S[i] = __fmul_rn(row[i], inv);   // own elements only
 }
 
 template <int GQA>
 __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     constexpr int HD = 128;
+    extern __shared__ __align__(16) float rows_dyn[];          // [GQA][s_stride] score rows, used by the last CTA only
     __shared__ __align__(16) float qs[GQA][HD];
     __shared__ float redf[GQA][8];
     __shared__ double redd[GQA][8];
@@ -886,6 +889,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
         }
     }
     // ---- the last CTA of this KV head (atomic ticket) normalises the GQA rows: no separate softmax launch
+    if (!a.fuse_softmax) return;
     __threadfence();
     __syncthreads();
     if (tid == 0) s_ticket = atomicAdd(&a.tickets[g], 1u);
@@ -894,9 +898,18 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     if (s_ticket != n_act - 1) return;
     __threadfence();
     if (tid == 0) a.tickets[g] = 0u;
+    // one memory round trip: the GQA score rows (written by the other CTAs of this KV head) -> shared memory
+    for (int i = tid; i < GQA * (n_pad / 4); i += ATT_THREADS) {
+        const int h = i / (n_pad / 4), j = i - h * (n_pad / 4);
+        cp_async16(rows_dyn + (size_t) h * a.s_stride + 4 * j, a.S + (size_t) (g * GQA + h) * a.s_stride + 4 * j);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
     constexpr int NW = 8 / GQA;                               // warps per head (8 warps, GQA in {1,2,4,8})
     const int warp = tid >> 5, lane = tid & 31, hl = warp / NW, w = warp % NW;
-    softmax_row(a.S + (size_t) (g * GQA + hl) * a.s_stride, n_pad, w, NW, lane, redf[hl], redd[hl], 1 + hl, NW * 32);
+    softmax_row(rows_dyn + (size_t) hl * a.s_stride, a.S + (size_t) (g * GQA + hl) * a.s_stride, n_pad, w, NW, lane,
+                redf[hl], redd[hl], 1 + hl, NW * 32);
 }
 
 __global__ void __launch_bounds__(256) k_attn_softmax(const AttnArgs a) {
@@ -935,67 +948,48 @@ __global__ void __launch_bounds__(256) k_attn_softmax(const AttnArgs a) {
     for (int i = tid; i < n_pad; i += 256) S[i] = __fmul_rn(S[i], inv);
 }
 
-static constexpr int PV_BATCH = 256;   // V rows per pipeline stage (x 32 B = 8 KB)
+static constexpr int PV_BATCH = 256;   // granularity of the p/V chunk
 
 template <int GQA>
 __global__ void __launch_bounds__(PV_DIMS * 16) k_attn_pv(const AttnArgs a) {
     constexpr int HD = 128;
     constexpr int NT = PV_DIMS * 16;
-    extern __shared__ __align__(16) float ps_dyn[];                 // [GQA][p_chunk]
-    __shared__ __align__(16) __half vs[3][PV_BATCH][PV_DIMS];      // 3 x 8 KB ring
+    extern __shared__ __align__(16) uint8_t pv_dyn[];              // [GQA][p_chunk] f32 | [p_chunk][16] f16
     __shared__ float red[GQA][16][PV_DIMS + 1];
+    const int PCH = a.p_chunk;
+    float * ps = reinterpret_cast<float *>(pv_dyn);
+    __half (*vs)[PV_DIMS] = reinterpret_cast<__half (*)[PV_DIMS]>(pv_dyn + (size_t) GQA * PCH * 4);
     // thread = (chain c, dim dl); a CTA owns 16 dims (one 32-byte sector per V row) of one KV head
     const int g = blockIdx.x, c = threadIdx.x / PV_DIMS, dl = threadIdx.x % PV_DIMS;
     const int n_kv = attn_n_kv(a);
     const int n_pad = (n_kv + 31) / 32 * 32;
-    const int PCH = a.p_chunk;
-    const int n_batches = (n_pad + PV_BATCH - 1) / PV_BATCH;
     const __half * vbase = a.v_cache + g * HD + blockIdx.y * PV_DIMS;
-    auto issue_v = [&](int b) {
-        if (b < n_batches) {
-            const int t0 = b * PV_BATCH, rows = min(PV_BATCH, n_kv - t0);    // rows beyond n_kv are never read (p = 0)
-            for (int i = threadIdx.x; i < rows * 2; i += NT)                // 2 x 16 B per row
-                cp_async16(&vs[b % 3][i >> 1][(i & 1) * 8], vbase + (size_t) (t0 + (i >> 1)) * a.kv_dim + (i & 1) * 8);
-        }
-        cp_async_commit();
-    };
-    auto issue_p = [&](int pc) {                                   // probabilities of chunk pc for the GQA heads
-        const int t0 = pc * PCH, len = min(PCH, n_pad - t0);       // len is a multiple of 32: 16-byte pieces
-        for (int i = threadIdx.x; i < GQA * (len / 4); i += NT) {
-            const int h = i / (len / 4), j = i - h * (len / 4);
-            cp_async16(ps_dyn + (size_t) h * PCH + 4 * j, a.S + (size_t) (g * GQA + h) * a.s_stride + t0 + 4 * j);
-        }
-    };
     float acc[GQA];
 #pragma unroll
     for (int h = 0; h < GQA; h++) acc[h] = 0.f;
-    issue_p(0);
-    issue_v(0);
-    issue_v(1);
-    for (int b = 0; b < n_batches; b++) {
-        const int t0 = b * PV_BATCH;
-        if (b > 0 && t0 % PCH == 0) {                              // next p chunk (contexts longer than p_chunk only)
-            __syncthreads();
-            issue_p(t0 / PCH);
-            cp_async_commit();
-            cp_async_wait<0>();
-            __syncthreads();
+    for (int t0 = 0; t0 < n_pad; t0 += PCH) {
+        const int len = min(PCH, n_pad - t0), rows = min(len, n_kv - t0);     // rows beyond n_kv are never read (p = 0)
+        if (t0) __syncthreads();
+        // every byte of the chunk in flight at once: V rows (2 x 16 B each) and the GQA probability rows
+        for (int i = threadIdx.x; i < rows * 2; i += NT)
+            cp_async16(&vs[i >> 1][(i & 1) * 8], vbase + (size_t) (t0 + (i >> 1)) * a.kv_dim + (i & 1) * 8);
+        for (int i = threadIdx.x; i < GQA * (len / 4); i += NT) {
+            const int h = i / (len / 4), j = i - h * (len / 4);
+            cp_async16(ps + (size_t) h * PCH + 4 * j, a.S + (size_t) (g * GQA + h) * a.s_stride + t0 + 4 * j);
         }
-        issue_v(b + 2);
-        cp_async_wait<2>();
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
-        const int len = min(PV_BATCH, n_pad - t0), steps = len / 16, pt0 = t0 % PCH;
-#pragma unroll 4
+        const int steps = len / 16;
+#pragma unroll 8
         for (int s = 0; s < steps; s++) {
             const int tt = 16 * s + c;
-            // slots at or beyond n_kv have p == 0 exactly; their (stale) V bytes must not be multiplied (NaN-safe)
-            const float v = t0 + tt < n_kv ? __half2float(vs[b % 3][tt][dl]) : 0.f;
+            // slots at or beyond n_kv have p == 0 exactly; their V bytes were not loaded and must not be multiplied
+            const float v = t0 + tt < n_kv ? __half2float(vs[tt][dl]) : 0.f;
 #pragma unroll
-            for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(v, ps_dyn[(size_t) h * PCH + pt0 + tt], acc[h]);
+            for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(v, ps[(size_t) h * PCH + tt], acc[h]);
         }
-        __syncthreads();
     }
-    cp_async_wait<0>();
 #pragma unroll
     for (int h = 0; h < GQA; h++) red[h][c][dl] = acc[h];
     __syncthreads();
