@@ -65,8 +65,8 @@ __global__ void k_retile(int type, const uint8_t * __restrict__ src, int64_t n_r
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;   // source block index = row*nb + bi
     if (i >= n_rows * nb) return;
     const int64_t row = i / nb, bi = i % nb;
-    const int64_t f = (row * vstride + voff) * nb + bi;                   // flattened destination block
-    const int64_t T = f >> 5; const int lane = (int) (f & 31);
+    const int64_t vrow = row * vstride + voff;                            // destination (virtual) row
+    const int64_t T = (vrow >> 5) * nb + bi; const int lane = (int) (vrow & 31);   // tile = block bi of 32 rows, one row per lane
     if (type == T_Q4_K) {
         const uint8_t * b = src + i * 144;   // {half d, half dmin, u8 scales[12], u8 qs[128]}  ggml-common.h:267-277
         for (int c = 0; c < 8; c++) copy16(p0 + T * 4096 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
@@ -124,12 +124,9 @@ static DevMat upload_tiled(const HostTensor * src, int n_src, cudaStream_t st) {
     DevMat d;
     const int nb = (int) (k / wpb);
     const int64_t vrows = rows1 * n_src;
-    int rows_unit = 32 / gcd_i(nb, 32);
-    if (rows_unit & 1) rows_unit *= 2;                 // RoPE pairs / (gate, up) pairs live in one unit
-    if (vrows % rows_unit != 0) throw std::runtime_error("row count " + std::to_string(vrows) + " is not a multiple of the work-unit height " + std::to_string(rows_unit));
-    d.m.type = type; d.m.n_rows = (int) vrows; d.m.nb = nb; d.m.rows_unit = rows_unit;
-    d.m.tiles_unit = rows_unit * nb / 32; d.m.n_units = (int) (vrows / rows_unit);
-    if (rows_unit > 32 || rows_unit * (type == T_Q4_K ? 12 : type == T_Q5_K ? 9 : 8) > 32 * MAX_CHAIN_SLOTS) throw std::runtime_error("work unit too tall");
+    if (vrows % 32 != 0) throw std::runtime_error("row count " + std::to_string(vrows) + " is not a multiple of the work-unit height 32");
+    d.m.type = type; d.m.n_rows = (int) vrows; d.m.nb = nb; d.m.rows_unit = 32;
+    d.m.tiles_unit = nb; d.m.n_units = (int) (vrows / 32);
     const size_t n_tiles = (size_t) vrows * nb / 32;
     const size_t raw1 = (size_t) blk_bytes * nb * rows1;
     d.bytes = raw1 * n_src;
@@ -418,6 +415,7 @@ struct TapStore { std::map<std::string, std::vector<float>> v; };
 
 struct b200_ctx {
     b200_model * m = nullptr;
+    int device = 0;
     int n_ctx = 0;
     cudaStream_t st = nullptr;
     // activations
@@ -473,17 +471,15 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     ProfScope ps(c);
     MatvecArgs a = a_in;
     a.tiles_unit = a.seg[0].tiles_unit;
-    int sb = 0;
-    for (int i = 0; i < a.n_seg; i++) {
+    for (int i = 0; i < a.n_seg; i++)
         if (a.seg[i].tiles_unit != a.tiles_unit) throw std::runtime_error("segments of one launch must share the unit shape");
-        sb = std::max(sb, tile_bytes_of(a.seg[i].type));
-    }
-    a.stage_bytes = (sb + 15) / 16 * 16;
-    a.prefetch = RING_BYTES / a.stage_bytes >= 3 ? 2 : 1;
-    const size_t smem = act_smem_bytes(a.k, a.act_q8_0) + (size_t) MV_WARPS * STG_WORDS * 4 + (size_t) MV_WARPS * RING_BYTES;
-    static size_t attr_smem = 0;
+    // warps per 32-row unit: as many (4, 2, 1) as still leave every unit resident in ONE wave of sm_count x 12 warps
+    const int slots = c->sm_count * MV_WARPS;
+    a.group = a.n_units * 4 <= slots ? 4 : (a.n_units * 2 <= slots ? 2 : 1);
+    const size_t smem = act_smem_bytes(a.k, a.act_q8_0) + (size_t) (MV_WARPS / a.group) * HANDOFF_WORDS * 4;
+    static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
-    if (smem > attr_smem) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem = smem; }
+    if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }
     const int grid = std::max(1, std::min(a.n_units, c->sm_count));
     k_matvec<EPI><<<grid, MV_THREADS, smem, c->st>>>(a);
     c->launches++;
@@ -501,9 +497,10 @@ static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pa
     // possible) for rows up to 64 KB; longer contexts run the stand-alone softmax kernel
     a.fuse_softmax = (size_t) GQA * a.s_stride * 4 <= 64 * 1024;
     const size_t sc_smem = a.fuse_softmax ? (size_t) GQA * a.s_stride * 4 : 0;
-    static size_t attr_pv = 0, attr_sc = 0;
-    if (pv_smem > attr_pv) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_pv = pv_smem; }
-    if (sc_smem > attr_sc) { CU(cudaFuncSetAttribute(k_attn_scores<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc_smem)); attr_sc = sc_smem; }
+    static size_t attr_pv[64] = {0}, attr_sc[64] = {0};   // per device (function attributes are per device)
+    const int dv = c->device & 63;
+    if (pv_smem > attr_pv[dv]) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_pv[dv] = pv_smem; }
+    if (sc_smem > attr_sc[dv]) { CU(cudaFuncSetAttribute(k_attn_scores<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc_smem)); attr_sc[dv] = sc_smem; }
     const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
     {
         g_kind = KIND_ATTN; ProfScope ps(c);
@@ -653,6 +650,7 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         if (!m) throw std::runtime_error("null model");
         auto c = std::make_unique<b200_ctx>();
         c->m = m;
+        c->device = m->device;
         CU(cudaSetDevice(m->device));
         if (n_ctx <= 0) n_ctx = m->n_ctx_train;
         c->n_ctx = (n_ctx + 31) / 32 * 32;                       // GGML_PAD(n_ctx, 32): cpp/src/llama.cpp:16655
@@ -1031,14 +1029,24 @@ extern "C" int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int
         require_gpu();
         cudaStream_t st;
         CU(cudaStreamCreate(&st));
-        DevMat d = upload_matrix(type, w, n_rows, k, st);
-        DBuf dx((size_t) k * 4), dy((size_t) n_rows * 4);
+        // the operator accepts any row count: pad with all-zero blocks (d = 0 -> 0.0) up to the work-unit height
+        const int64_t rows_pad = (n_rows + 31) / 32 * 32;
+        std::vector<uint8_t> padded;
+        if (rows_pad != n_rows) {
+            const size_t rb = ggml_row_bytes(type, k);
+            padded.assign((size_t) rows_pad * rb, 0);
+            memcpy(padded.data(), w, (size_t) n_rows * rb);
+            w = padded.data();
+        }
+        DevMat d = upload_matrix(type, w, rows_pad, k, st);
+        DBuf dx((size_t) k * 4), dy((size_t) rows_pad * 4);
         CU(cudaMemcpyAsync(dx.p, x, (size_t) k * 4, cudaMemcpyHostToDevice, st));
         b200_ctx tmp;   // only st / sm_count / launches are used by launch_matvec
         tmp.st = st;
         int dev = 0; CU(cudaGetDevice(&dev));
         cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
         tmp.sm_count = prop.multiProcessorCount;
+        tmp.device = dev;
         MatvecArgs a{};
         a.seg[0] = d.m; a.n_seg = 1; a.n_units = d.m.n_units; a.k = (int) k;
         a.x = dx.as<float>(); a.norm_w = nullptr; a.act_q8_0 = type == T_Q8_0; a.out = dy.as<float>();

@@ -18,9 +18,10 @@
 //     ggml_vec_dot_f16 (cpp/ggml/src/ggml.c:2038-2075), softmax with the ggml_v_expf polynomial (:2447-2472).
 //   * SiLU: ggml_v_silu (cpp/ggml/src/ggml.c:2475-2482).
 //
-// HBM layout ("tiles"): a matrix keeps exactly its GGUF bytes, re-tiled once at load. Blocks are numbered
-// f = row*nb + block_in_row; tile T = f/32 holds 32 consecutive blocks, one per lane, every field transposed so
-// that a warp-wide load of one field is a dense 128/512-byte stream:
+// HBM layout ("tiles"): a matrix keeps exactly its GGUF bytes, re-tiled once at load. Tile T = (row/32)*nb + b
+// holds block b of 32 consecutive rows, ONE ROW PER LANE, every field transposed so that a warp-wide load of one
+// field is a dense 128/512-byte stream. A lane therefore walks the blocks of its own row in order and its fp32
+// fma chains never leave its registers:
 //   Q4_K: p0 qs uint4[8][32] (4096 B)  p1 u32[4][32] = 12 scale bytes + (d,dmin) (512 B)
 //   Q5_K: same + p2 qh uint4[2][32] (1024 B)
 //   Q6_K: p0 ql uint4[8][32]  p2 qh uint4[4][32] (2048 B)  p1 scales u32[4][32]  p3 d u16[32] (64 B)
@@ -39,9 +40,9 @@ struct TMat {
     int type = 0;
     int n_rows = 0;       // (virtual) rows
     int nb = 0;           // blocks per row: 256-weight super-blocks, or 32-weight blocks for Q8_0
-    int rows_unit = 0;    // rows per warp work unit (even; rows_unit*nb is a multiple of 32)
-    int tiles_unit = 0;   // = rows_unit*nb/32
-    int n_units = 0;      // = n_rows/rows_unit
+    int rows_unit = 32;   // a work unit = 32 rows (one per lane) x all nb blocks
+    int tiles_unit = 0;   // = nb
+    int n_units = 0;      // = n_rows/32
     const uint8_t * p0 = nullptr;
     const uint8_t * p1 = nullptr;
     const uint8_t * p2 = nullptr;
@@ -69,8 +70,7 @@ struct MatvecArgs {
     float eps;
     int act_q8_0;              // 0: Q8_K activations, 1: Q8_0 activations
     int tiles_unit;            // identical for every segment of a launch (same K, same block width)
-    int stage_bytes;           // ring slot size = largest tile of the launch (16-byte multiple)
-    int prefetch;              // tiles in flight ahead of the one being computed (1 or 2); stages = prefetch + 1
+    int group;                 // G = warps sharing one 32-row unit (1, 2 or 4): tile t is computed by warp t % G
     // epilogue
     float * out;
     const float * resid;
@@ -85,10 +85,7 @@ struct MatvecArgs {
 
 static constexpr int MV_THREADS = 384;                      // one persistent CTA per SM
 static constexpr int MV_WARPS   = MV_THREADS / 32;
-static constexpr int RING_BYTES = 13824;                    // per-warp weight ring: 3 Q4_K tiles / 2 Q5_K|Q6_K tiles
-static constexpr int STG_STRIDE = 33;                       // padded row stride of the per-warp staging array
-static constexpr int STG_WORDS  = 14 * STG_STRIDE;          // d, s[8], dmin, prod[4]
-static constexpr int MAX_CHAIN_SLOTS = 12;                  // rows_unit(<=32) * chains(<=12) / 32
+static constexpr int HANDOFF_WORDS = 12 * 32;               // chain state of one unit: 12 fp32 chains x 32 rows
 
 // ------------------------------------------------------------------------------------------------------------
 // small helpers
@@ -145,9 +142,10 @@ __device__ __forceinline__ float reduce_add16_shfl(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// activation quantization (block-cooperative, result in shared memory, TRANSPOSED for the tile kernels)
-//   Q8_K: qT[slot 0..15][nb] x 16 B | dx[nb] f32 | bp[2][nb] int4 = sums of the 8 sub-blocks of 32
-//   Q8_0: qT[half 0..1][nb32] x 16 B | dx[nb32] f32 (already rounded through fp16)
+// activation quantization (block-cooperative, result in shared memory in natural order: all lanes of a warp work
+// on the same block b of their own rows, so every activation read is a warp-wide broadcast)
+//   Q8_K: q[k] int8 | dx[nb] f32 | bp[nb][8] int = sums of the 8 sub-blocks of 32
+//   Q8_0: q[k] int8 | dx[k/32] f32 (already rounded through fp16)
 // ------------------------------------------------------------------------------------------------------------
 struct ActSmem {
     int8_t * q;
@@ -174,7 +172,7 @@ __device__ __forceinline__ ActSmem act_smem_carve(uint8_t * base, int k, int act
 // One warp quantizes 256 consecutive values (8 per lane) to Q8_K — quantize_row_q8_K_ref
 // (cpp/ggml/src/ggml-quants.c:3593-3630): `max` is the FIRST element of largest magnitude, iscale = -127/max,
 // q = min(127, round_half_even(iscale*x)), d = 1/iscale.
-__device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, int b, int nb, const ActSmem & A) {
+__device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, int b, const ActSmem & A) {
     float amax = 0.f, mval = 0.f;
     int   midx = 0;
 #pragma unroll
@@ -204,16 +202,15 @@ __device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, in
         }
         d = __fdiv_rn(1.f, iscale);
     }
-    // element e = lane*8 + i of the block lives in slot e/16, byte e%16
-    *reinterpret_cast<uint2 *>(A.q + ((size_t) ((lane >> 1) * nb + b)) * 16 + (lane & 1) * 8) = make_uint2(w0, w1);
+    *reinterpret_cast<uint2 *>(A.q + (size_t) b * 256 + lane * 8) = make_uint2(w0, w1);
     int s32 = s8 + __shfl_xor_sync(0xffffffffu, s8, 1);
     s32 += __shfl_xor_sync(0xffffffffu, s32, 2);                 // sum of sub-block lane/4 (32 values)
-    if ((lane & 3) == 0) { const int s = lane >> 2; A.bp[((size_t) ((s >> 2) * nb + b)) * 4 + (s & 3)] = s32; }
+    if ((lane & 3) == 0) A.bp[(size_t) b * 8 + (lane >> 2)] = s32;
     if (lane == 0) A.dx[b] = d;
 }
 // One warp quantizes 256 consecutive values = 8 Q8_0 blocks of 32 — AVX path of quantize_row_q8_0
 // (cpp/ggml/src/ggml-quants.c:936-1000): d = amax/127 kept as fp16, id = 127/amax, q = round_half_even(x*id).
-__device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, int b256, int nb32, const ActSmem & A) {
+__device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, int b256, const ActSmem & A) {
     float amax = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
@@ -228,9 +225,8 @@ __device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, i
         if (i < 4) w0 |= ((uint32_t) (qi & 0xff)) << (8 * i);
         else       w1 |= ((uint32_t) (qi & 0xff)) << (8 * (i - 4));
     }
-    const int blk = b256 * 8 + (lane >> 2);                       // 32-block; element offset (lane&3)*8 inside it
-    *reinterpret_cast<uint2 *>(A.q + ((size_t) (((lane >> 1) & 1) * nb32 + blk)) * 16 + (lane & 1) * 8) = make_uint2(w0, w1);
-    if ((lane & 3) == 0) A.dx[blk] = __half2float(__float2half_rn(d));
+    *reinterpret_cast<uint2 *>(A.q + (size_t) b256 * 256 + lane * 8) = make_uint2(w0, w1);
+    if ((lane & 3) == 0) A.dx[b256 * 8 + (lane >> 2)] = __half2float(__float2half_rn(d));
 }
 
 // Block-cooperative prologue: optional RMSNorm(+weight) then activation quantization into shared memory.
@@ -271,16 +267,13 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fmul_rn(v[i], scale), ww[i]);
         }
-        if (act_q8_0) q80_blocks_warp(v, lane, b, k / 32, A);
-        else          q8k_block_warp(v, lane, b, n256, A);
+        if (act_q8_0) q80_blocks_warp(v, lane, b, A);
+        else          q8k_block_warp(v, lane, b, A);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// weight staging: every warp streams ITS tiles through a private shared-memory ring with cp.async (LDGSTS, 16 B
-// per lane per instruction, no register staging), `prefetch` tiles ahead of the one it is computing, so HBM
-// latency is overlapped with the integer work instead of being exposed once per tile.
-// Slot layout = the tile's planes back to back:  Q4_K qs|sd  Q5_K qs|sd|qh  Q6_K ql|qh|sc|d  Q8_0 qs|d
+// cp.async helpers (attention kernels)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
     const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
@@ -289,40 +282,6 @@ __device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-__host__ __device__ __forceinline__ int tile_bytes_of(int type) {
-    return type == T_Q4_K ? 4608 : type == T_Q5_K ? 5632 : type == T_Q6_K ? 6720 : 1088;
-}
-__device__ __forceinline__ void issue_tile(const TMat & m, size_t T, int lane, uint8_t * slot) {
-    switch (m.type) {
-        case T_Q4_K: case T_Q5_K: {
-            const uint8_t * q = m.p0 + T * 4096 + lane * 16;
-#pragma unroll
-            for (int c = 0; c < 8; c++) cp_async16(slot + c * 512 + lane * 16, q + c * 512);
-            cp_async16(slot + 4096 + lane * 16, m.p1 + T * 512 + lane * 16);
-            if (m.type == T_Q5_K) {
-                cp_async16(slot + 4608 + lane * 16, m.p2 + T * 1024 + lane * 16);
-                cp_async16(slot + 5120 + lane * 16, m.p2 + T * 1024 + 512 + lane * 16);
-            }
-        } break;
-        case T_Q6_K: {
-            const uint8_t * q = m.p0 + T * 4096 + lane * 16;
-#pragma unroll
-            for (int c = 0; c < 8; c++) cp_async16(slot + c * 512 + lane * 16, q + c * 512);
-            const uint8_t * h = m.p2 + T * 2048 + lane * 16;
-#pragma unroll
-            for (int c = 0; c < 4; c++) cp_async16(slot + 4096 + c * 512 + lane * 16, h + c * 512);
-            cp_async16(slot + 6144 + lane * 16, m.p1 + T * 512 + lane * 16);
-            if (lane < 4) cp_async16(slot + 6656 + lane * 16, m.p3 + T * 64 + lane * 16);
-        } break;
-        default: {
-            cp_async16(slot + lane * 16, m.p0 + T * 1024 + lane * 16);
-            cp_async16(slot + 512 + lane * 16, m.p0 + T * 1024 + 512 + lane * 16);
-            if (lane < 4) cp_async16(slot + 1024 + lane * 16, m.p3 + T * 64 + lane * 16);
-        } break;
-    }
-}
-__device__ __forceinline__ uint4 lds_u4(const uint8_t * p) { return *reinterpret_cast<const uint4 *>(p); }
-__device__ __forceinline__ uint32_t lds_u32(const uint8_t * p) { return *reinterpret_cast<const uint32_t *>(p); }
 // dp4a with an UNSIGNED first operand (bytes 0..255) and a signed second one
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
     int d;
@@ -331,27 +290,61 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// per-type block arithmetic: ONE lane = ONE block. Produces the exact per-block integers the reference's AVX2
-// lanes hold (s[m] = the m-th int32 lane of `sumi`, prod[l] = the l-th lane of the mins product) and the
-// per-block fp32 coefficients, and writes them to the warp's staging array stg[k*STG_STRIDE + lane].
-//   k = 0: d_b   1..8: s[0..7]   9: dmin_b   10..13: prod[0..3] (Q4_K) / 10: sum of prod (Q5_K)
+// One lane = one ROW. A tile is block b of 32 rows; a lane streams its row's blocks through registers (coalesced
+// 16-byte loads thanks to the transposed tile layout; the next tile is in flight while this one is computed),
+// computes the block's exact integers — s[m] = the m-th int32 lane of the reference's AVX2 `sumi`, p[l] = the
+// l-th lane of its mins product — and advances its own 12 fp32 chains:
+//   acc[m] = fma(d_b, (float) s[m], acc[m])                      (ggml-quants.c:6972, 7556, 8216, 5376)
+//   Q4_K: acc[8+l] = fma(dmin_b, (float) p[l], acc[8+l])  (:6934)      Q5_K: acc[8] += dmin_b * (float) sum p  (:7516)
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int4 lds_act(const ActSmem & A, int slot, int nb, int bi) {
-    return *reinterpret_cast<const int4 *>(A.q + ((size_t) (slot * nb + bi)) * 16);
+struct TileRegs  { uint4 q[12]; uint32_t s[5]; };
+struct BlockInts { int s[8]; int p[4]; float d, dmin; };
+
+__device__ __forceinline__ void load_tile(const TMat & m, size_t T, int lane, TileRegs & r) {
+    switch (m.type) {
+        case T_Q4_K: case T_Q5_K: {
+            const uint8_t * q = m.p0 + T * 4096 + lane * 16;
+#pragma unroll
+            for (int c = 0; c < 8; c++) r.q[c] = ldg_stream_v4(q + c * 512);
+            const uint8_t * sd = m.p1 + T * 512 + lane * 4;
+#pragma unroll
+            for (int w = 0; w < 4; w++) r.s[w] = ldg_u32(sd + w * 128);
+            if (m.type == T_Q5_K) {
+                r.q[8] = ldg_stream_v4(m.p2 + T * 1024 + lane * 16);
+                r.q[9] = ldg_stream_v4(m.p2 + T * 1024 + 512 + lane * 16);
+            }
+        } break;
+        case T_Q6_K: {
+            const uint8_t * q = m.p0 + T * 4096 + lane * 16;
+#pragma unroll
+            for (int c = 0; c < 8; c++) r.q[c] = ldg_stream_v4(q + c * 512);
+            const uint8_t * h = m.p2 + T * 2048 + lane * 16;
+#pragma unroll
+            for (int c = 0; c < 4; c++) r.q[8 + c] = ldg_stream_v4(h + c * 512);
+            const uint8_t * sc = m.p1 + T * 512 + lane * 4;
+#pragma unroll
+            for (int w = 0; w < 4; w++) r.s[w] = ldg_u32(sc + w * 128);
+            r.s[4] = ldg_u16(m.p3 + T * 64 + lane * 2);
+        } break;
+        default: {
+            r.q[0] = ldg_stream_v4(m.p0 + T * 1024 + lane * 16);
+            r.q[1] = ldg_stream_v4(m.p0 + T * 1024 + 512 + lane * 16);
+            r.s[4] = ldg_u16(m.p3 + T * 64 + lane * 2);
+        } break;
+    }
 }
 
+// 16 activation bytes of the current block, same address in every lane (broadcast)
+__device__ __forceinline__ int4 act16(const int8_t * ab, int slot) { return *reinterpret_cast<const int4 *>(ab + slot * 16); }
+
 template <bool Q5>
-__device__ __forceinline__ void block_q45k(const uint8_t * slot, int nb, int lane, int bi, const ActSmem & A, uint32_t * stg) {
-    const uint8_t * qp = slot + lane * 16;
-    const uint8_t * sd = slot + 4096 + lane * 4;
-    const uint32_t s0 = lds_u32(sd), s1 = lds_u32(sd + 128), s2 = lds_u32(sd + 256), dmw = lds_u32(sd + 384);
+__device__ __forceinline__ void ints_q45k(const TileRegs & r, const int8_t * ab, const int * bp, float yd, BlockInts & o) {
+    const uint32_t s0 = r.s[0], s1 = r.s[1], s2 = r.s[2], dmw = r.s[3];
     // the 8 scale bytes and 8 min bytes (get_scale_min_k4 packing, cpp/ggml/src/ggml-quants.c:1891-1898)
     const uint32_t sc_a = s0 & 0x3f3f3f3fu, m_a = s1 & 0x3f3f3f3fu;
     const uint32_t sc_b = (s2 & 0x0f0f0f0fu) | (((s0 >> 6) & 0x03030303u) << 4);
     const uint32_t m_b  = ((s2 >> 4) & 0x0f0f0f0fu) | (((s1 >> 6) & 0x03030303u) << 4);
-    uint4 qh[2];
-    if (Q5) { qh[0] = lds_u4(slot + 4608 + lane * 16); qh[1] = lds_u4(slot + 5120 + lane * 16); }
-    // s = s_lo + (s_hi16 >> 4): the high nibbles are multiplied IN PLACE (mask 0xf0, i.e. 16 x value, unsigned dp4a),
+    // s = s_lo + (s_hi16 >> 4): the high nibbles are multiplied IN PLACE (mask 0xf0 = 16 x value, unsigned dp4a);
     // their scaled sum is an exact multiple of 16, so the shift is exact
     int s_lo[8], s_hi[8];
 #pragma unroll
@@ -362,9 +355,8 @@ __device__ __forceinline__ void block_q45k(const uint8_t * slot, int nb, int lan
         const int sc_lo = (int) ((scw >> ((j & 1) * 16)) & 0xff), sc_hi = (int) ((scw >> ((j & 1) * 16 + 8)) & 0xff);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const uint4 w = lds_u4(qp + (2 * j + h) * 512);
-            const int4 alo = lds_act(A, 4 * j + h, nb, bi);
-            const int4 ahi = lds_act(A, 4 * j + 2 + h, nb, bi);
+            const uint4 w = r.q[2 * j + h];
+            const int4 alo = act16(ab, 4 * j + h), ahi = act16(ab, 4 * j + 2 + h);
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
                 const uint32_t W = word_of(w, wi);
@@ -373,7 +365,7 @@ __device__ __forceinline__ void block_q45k(const uint8_t * slot, int nb, int lan
                     s_hi[4 * h + wi] += sc_hi * dp4a_us(W & 0xf0f0f0f0u, word_of(ahi, wi), 0);
                 } else {
                     // qh bit 2j -> +16 on the low-nibble weight, bit 2j+1 -> +16 on the high-nibble one
-                    const uint32_t H = word_of(qh[h], wi);
+                    const uint32_t H = word_of(r.q[8 + h], wi);
                     const uint32_t lo = (W & 0x0f0f0f0fu) | (((H >> (2 * j)) & 0x01010101u) << 4);
                     const uint32_t hi = ((W >> 4) & 0x0f0f0f0fu) | (((H >> (2 * j + 1)) & 0x01010101u) << 4);
                     s_lo[4 * h + wi] += sc_lo * __dp4a((int) lo, word_of(alo, wi), 0);
@@ -382,92 +374,69 @@ __device__ __forceinline__ void block_q45k(const uint8_t * slot, int nb, int lan
             }
         }
     }
-    // mins: lane l of the reference's _mm_madd_epi16(mins, q8s) = m[2l]*bp[2l] + m[2l+1]*bp[2l+1]
-    const int4 bp0 = *reinterpret_cast<const int4 *>(A.bp + ((size_t) (0 * nb + bi)) * 4);
-    const int4 bp1 = *reinterpret_cast<const int4 *>(A.bp + ((size_t) (1 * nb + bi)) * 4);
-    const int p0 = (int) (m_a & 0xff) * bp0.x + (int) ((m_a >> 8) & 0xff) * bp0.y;
-    const int p1 = (int) ((m_a >> 16) & 0xff) * bp0.z + (int) (m_a >> 24) * bp0.w;
-    const int p2 = (int) (m_b & 0xff) * bp1.x + (int) ((m_b >> 8) & 0xff) * bp1.y;
-    const int p3 = (int) ((m_b >> 16) & 0xff) * bp1.z + (int) (m_b >> 24) * bp1.w;
-    const float yd = A.dx[bi];
-    const __half2 dmh = *reinterpret_cast<const __half2 *>(&dmw);
-    const float d    = __fmul_rn(yd, __low2float(dmh));           // y[i].d * fp16(x[i].d)
-    const float dmin = __fmul_rn(-yd, __high2float(dmh));         // -y[i].d * fp16(x[i].dmin)
-    stg[0 * STG_STRIDE + lane] = __float_as_uint(d);
 #pragma unroll
-    for (int i = 0; i < 8; i++) stg[(1 + i) * STG_STRIDE + lane] = (uint32_t) (s_lo[i] + (s_hi[i] >> 4));
-    stg[9 * STG_STRIDE + lane] = __float_as_uint(dmin);
-    if (Q5) {
-        stg[10 * STG_STRIDE + lane] = (uint32_t) (p0 + p1 + p2 + p3);
-    } else {
-        stg[10 * STG_STRIDE + lane] = (uint32_t) p0; stg[11 * STG_STRIDE + lane] = (uint32_t) p1;
-        stg[12 * STG_STRIDE + lane] = (uint32_t) p2; stg[13 * STG_STRIDE + lane] = (uint32_t) p3;
-    }
+    for (int i = 0; i < 8; i++) o.s[i] = s_lo[i] + (s_hi[i] >> 4);
+    // mins: lane l of the reference's _mm_madd_epi16(mins, q8s) = m[2l]*bsum[2l] + m[2l+1]*bsum[2l+1]
+    const int4 bp0 = *reinterpret_cast<const int4 *>(bp), bp1 = *reinterpret_cast<const int4 *>(bp + 4);
+    o.p[0] = (int) (m_a & 0xff) * bp0.x + (int) ((m_a >> 8) & 0xff) * bp0.y;
+    o.p[1] = (int) ((m_a >> 16) & 0xff) * bp0.z + (int) (m_a >> 24) * bp0.w;
+    o.p[2] = (int) (m_b & 0xff) * bp1.x + (int) ((m_b >> 8) & 0xff) * bp1.y;
+    o.p[3] = (int) ((m_b >> 16) & 0xff) * bp1.z + (int) (m_b >> 24) * bp1.w;
+    const __half2 dmh = *reinterpret_cast<const __half2 *>(&dmw);
+    o.d    = __fmul_rn(yd, __low2float(dmh));            // y[i].d * fp16(x[i].d)
+    o.dmin = __fmul_rn(-yd, __high2float(dmh));          // -y[i].d * fp16(x[i].dmin)
 }
 
 // q (0..63 per byte) -> q - 32 as signed bytes, without inter-byte borrows
 __device__ __forceinline__ uint32_t sub32_bytes(uint32_t q) { return ((q | 0x80808080u) - 0x20202020u) ^ 0x80808080u; }
 
-__device__ __forceinline__ void block_q6k(const uint8_t * slot, int nb, int lane, int bi, const ActSmem & A, uint32_t * stg) {
-    const uint8_t * lp = slot + lane * 16;
-    const uint8_t * hp = slot + 4096 + lane * 16;
-    uint32_t sw[4];
+__device__ __forceinline__ void ints_q6k(const TileRegs & r, const int8_t * ab, float yd, BlockInts & o) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) sw[i] = lds_u32(slot + 6144 + (i * 32 + lane) * 4);
-    const float dw = __half2float(*reinterpret_cast<const __half *>(slot + 6656 + lane * 2));
-    int s[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = 0;
+    for (int i = 0; i < 8; i++) o.s[i] = 0;
     // layout of a super-block: dequantize_row_q6_K (cpp/ggml/src/ggml-quants.c:2970-3000); half n, group g of 32
     // weights: ql byte 64n + 32(g&1) + l, nibble g>>1; qh byte 32n + l, bits 2g..2g+1; scale 8n + 2g + l/16
 #pragma unroll
     for (int n = 0; n < 2; n++) {
 #pragma unroll
         for (int mq = 0; mq < 2; mq++) {
-            const uint4 qh = lds_u4(hp + (2 * n + mq) * 512);
+            const uint4 qh = r.q[8 + 2 * n + mq];
 #pragma unroll
-            for (int gl = 0; gl < 2; gl++) {                      // ql chunk serves groups gl (low nibble) and gl+2 (high)
-                const uint4 ql = lds_u4(lp + (4 * n + 2 * gl + mq) * 512);
+            for (int gl = 0; gl < 2; gl++) {                      // one ql chunk serves groups gl (low nibble) and gl+2 (high)
+                const uint4 ql = r.q[4 * n + 2 * gl + mq];
 #pragma unroll
                 for (int gh = 0; gh < 2; gh++) {
                     const int g = gl + 2 * gh;
                     const int si = 8 * n + 2 * g + mq;
-                    const int sc = (int) (int8_t) ((sw[si >> 2] >> ((si & 3) * 8)) & 0xff);
-                    const int4 a = lds_act(A, 8 * n + 2 * g + mq, nb, bi);
+                    const int sc = (int) (int8_t) ((r.s[si >> 2] >> ((si & 3) * 8)) & 0xff);
+                    const int4 a = act16(ab, 8 * n + 2 * g + mq);
 #pragma unroll
                     for (int wi = 0; wi < 4; wi++) {
                         const uint32_t QL = word_of(ql, wi), QH = word_of(qh, wi);
                         const uint32_t lo = gh ? ((QL >> 4) & 0x0f0f0f0fu) : (QL & 0x0f0f0f0fu);
                         const uint32_t q  = lo | (((QH >> (2 * g)) & 0x03030303u) << 4);
-                        s[4 * mq + wi] += sc * __dp4a((int) sub32_bytes(q), word_of(a, wi), 0);
+                        o.s[4 * mq + wi] += sc * __dp4a((int) sub32_bytes(q), word_of(a, wi), 0);
                     }
                 }
             }
         }
     }
-    const float d = __fmul_rn(A.dx[bi], dw);                       // y[i].d * fp16(x[i].d)
-    stg[0 * STG_STRIDE + lane] = __float_as_uint(d);
-#pragma unroll
-    for (int i = 0; i < 8; i++) stg[(1 + i) * STG_STRIDE + lane] = (uint32_t) s[i];
+    o.d = __fmul_rn(yd, h16_to_f32(r.s[4]));             // y[i].d * fp16(x[i].d)
+    o.dmin = 0.f;
 }
 
-__device__ __forceinline__ void block_q80(const uint8_t * slot, int nb, int lane, int bi, const ActSmem & A, uint32_t * stg) {
-    const uint4 w0 = lds_u4(slot + lane * 16), w1 = lds_u4(slot + 512 + lane * 16);
-    const float dw = __half2float(*reinterpret_cast<const __half *>(slot + 1024 + lane * 2));
-    const int4 a0 = lds_act(A, 0, nb, bi), a1 = lds_act(A, 1, nb, bi);
-    const float d = __fmul_rn(dw, A.dx[bi]);                       // fp16(x.d) * fp16(y.d)
-    stg[0 * STG_STRIDE + lane] = __float_as_uint(d);
+__device__ __forceinline__ void ints_q80(const TileRegs & r, const int8_t * ab, float yd, BlockInts & o) {
+    const int4 a0 = act16(ab, 0), a1 = act16(ab, 1);
 #pragma unroll
     for (int wi = 0; wi < 4; wi++) {
-        stg[(1 + wi) * STG_STRIDE + lane] = (uint32_t) __dp4a((int) word_of(w0, wi), word_of(a0, wi), 0);
-        stg[(5 + wi) * STG_STRIDE + lane] = (uint32_t) __dp4a((int) word_of(w1, wi), word_of(a1, wi), 0);
+        o.s[wi]     = __dp4a((int) word_of(r.q[0], wi), word_of(a0, wi), 0);
+        o.s[4 + wi] = __dp4a((int) word_of(r.q[1], wi), word_of(a1, wi), 0);
     }
+    o.d = __fmul_rn(h16_to_f32(r.s[4]), yd);             // fp16(x.d) * fp16(y.d)
+    o.dmin = 0.f;
 }
 
-__device__ __forceinline__ int chains_of(int type) { return type == T_Q4_K ? 12 : type == T_Q5_K ? 9 : 8; }
-
-// hsum_float_8 (cpp/ggml/src/ggml-quants.c:47-53) + the type's tail, from the row's chain results c[0..]
-__device__ __forceinline__ float finish_row(int type, const float * c) {
+// hsum_float_8 (cpp/ggml/src/ggml-quants.c:47-53) + the type's tail, from the row's 12 chain values
+__device__ __forceinline__ float finish_row(int type, const float (&c)[12]) {
     const float r0 = __fadd_rn(c[4], c[0]), r1 = __fadd_rn(c[5], c[1]), r2 = __fadd_rn(c[6], c[2]), r3 = __fadd_rn(c[7], c[3]);
     const float h = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
     if (type == T_Q4_K) return __fadd_rn(h, __fadd_rn(__fadd_rn(c[8], c[10]), __fadd_rn(c[9], c[11])));   // + acc_m
@@ -475,12 +444,6 @@ __device__ __forceinline__ float finish_row(int type, const float * c) {
     return h;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// The fused quantized mat-vec: [RMSNorm] + activation quant (prologue) -> exact W.x -> epilogue.
-// A warp owns work units of `rows_unit` whole rows (= tiles_unit tiles). Per tile: every lane computes its
-// block's integers (block_*), then the chain lanes advance the rows' fp32 fma chains over this tile's blocks in
-// block order; after the unit's last tile one lane per row finishes (hsum) and the epilogue runs on row pairs.
-// ------------------------------------------------------------------------------------------------------------
 struct UnitRef { int si; int u; int row_base; };
 __device__ __forceinline__ UnitRef locate_unit(const MatvecArgs & a, int unit) {
     UnitRef r; r.si = 0; r.u = unit; r.row_base = 0;
@@ -488,7 +451,16 @@ __device__ __forceinline__ UnitRef locate_unit(const MatvecArgs & a, int unit) {
         if (a.n_seg > 2 && r.u >= a.seg[1].n_units) { r.u -= a.seg[1].n_units; r.row_base += a.seg[1].n_rows; r.si = 2; } }
     return r;
 }
+__device__ __forceinline__ void bar_sync_n(int id, int n)   { asm volatile("bar.sync %0, %1;"   :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
+// ------------------------------------------------------------------------------------------------------------
+// The fused quantized mat-vec: [RMSNorm] + activation quant (prologue) -> exact W.x -> epilogue.
+// A work unit is 32 rows. G warps (1, 2 or 4 — chosen by the host so that matrices with few rows still occupy
+// every SM) share a unit: warp w computes the integers of tiles t = w, w+G, ... concurrently with the others,
+// while the 12 fp32 chains of each row advance strictly in block order, handed from warp to warp through shared
+// memory under named barriers (producer bar.arrive / consumer bar.sync on the edge w -> w+1).
+// ------------------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const MatvecArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -496,142 +468,112 @@ __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const MatvecArgs a) {
     const size_t act_bytes = act_smem_bytes(a.k, a.act_q8_0);
     const ActSmem A = act_smem_carve(smem_raw, a.k, a.act_q8_0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t * stg = reinterpret_cast<uint32_t *>(smem_raw + act_bytes) + warp * STG_WORDS;
-    uint8_t * ring = smem_raw + act_bytes + (size_t) MV_WARPS * STG_WORDS * 4 + (size_t) warp * RING_BYTES;
+    const int G = a.group, TU = a.tiles_unit;
+    const int grp = warp / G, w = warp - grp * G;              // group inside the CTA, warp inside the group
+    float * handoff = reinterpret_cast<float *>(smem_raw + act_bytes) + (size_t) grp * HANDOFF_WORDS;
+    const int bar_in  = 1 + grp * G + (w + G - 1) % G;         // edge (w-1) -> w
+    const int bar_out = 1 + grp * G + w;                       // edge w -> (w+1)
 
-    // warp-major mapping: unit u -> CTA u % grid, warp (u / grid) % MV_WARPS, so that few-unit launches
-    // (ffn_down: 1024 units) spread over every SM
-    const int warp_global = warp * gridDim.x + blockIdx.x;
-    const int n_warps = gridDim.x * MV_WARPS;
-    const int TU = a.tiles_unit, PF = a.prefetch, NST = PF + 1;
-    const int my_units = warp_global < a.n_units ? (a.n_units - warp_global + n_warps - 1) / n_warps : 0;
-    const int my_tiles = my_units * TU;
+    // group-major mapping: unit u -> CTA u % grid, group (u / grid) % groups_per_cta, so that launches with few
+    // units spread over every SM
+    const int groups_per_cta = MV_WARPS / G;
+    const int group_global = grp * gridDim.x + blockIdx.x;
+    const int n_groups = gridDim.x * groups_per_cta;
+    const int my_units = group_global < a.n_units ? (a.n_units - group_global + n_groups - 1) / n_groups : 0;
+    // the group's tiles form ONE sequence g = j*TU + t over its units j; warp w computes g = w, w+G, ... so the
+    // hand-off ring w -> w+1 -> ... -> w never produces twice on an edge before the consumer has taken the first
+    const int total = my_units * TU;
+    const int n_items = w < total ? (total - w + G - 1) / G : 0;
 
-    auto issue = [&](int q) {
-        if (q < my_tiles) {
-            const int j = q / TU, t = q - j * TU;
-            const UnitRef ur = locate_unit(a, warp_global + j * n_warps);
-            const TMat & m = ur.si == 0 ? a.seg[0] : (ur.si == 1 ? a.seg[1] : a.seg[2]);
-            issue_tile(m, (size_t) ur.u * TU + t, lane, ring + (size_t) (q % NST) * a.stage_bytes);
-        }
-        cp_async_commit();
+    auto prefetch = [&](int i, TileRegs & r) {
+        const int g = w + i * G, j = g / TU, t = g - j * TU;
+        const UnitRef ur = locate_unit(a, group_global + j * n_groups);
+        const TMat & m = ur.si == 0 ? a.seg[0] : (ur.si == 1 ? a.seg[1] : a.seg[2]);
+        load_tile(m, (size_t) ur.u * TU + t, lane, r);
     };
-    // the weights do not depend on the activations: start streaming before the prologue
-    for (int q = 0; q < PF; q++) issue(q);
+
+    TileRegs ra, rb;
+    if (n_items > 0) prefetch(0, ra);                          // weights do not depend on x: stream before the prologue
 
     prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem);
     __syncthreads();
 
-    float acc[MAX_CHAIN_SLOTS];
-    UnitRef ur; ur.si = 0; ur.u = 0; ur.row_base = 0;
-    int type = 0, nb = 1, C = 8, n_chains = 0, rows_unit = 2, r0 = 0, k0 = 0, coef0 = 0, val0 = 0;
-    for (int q = 0; q < my_tiles; q++) {
-        issue(q + PF);
-        if (PF == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-        __syncwarp();
-        const int j = q / TU, t = q - j * TU;
-        if (t == 0) {
-            ur = locate_unit(a, warp_global + j * n_warps);
-            const TMat & m = ur.si == 0 ? a.seg[0] : (ur.si == 1 ? a.seg[1] : a.seg[2]);
-            type = m.type; nb = m.nb; C = chains_of(type); rows_unit = m.rows_unit; n_chains = rows_unit * C;
+    float acc[12];
 #pragma unroll
-            for (int i = 0; i < MAX_CHAIN_SLOTS; i++) acc[i] = 0.f;
-            // chain slot 0 (the only one when rows_unit*C <= 32, i.e. for every full-size matrix)
-            r0 = lane / C; k0 = lane - r0 * C;
-            coef0 = (k0 < 8 ? 0 : 9) * STG_STRIDE; val0 = (k0 < 8 ? 1 + k0 : 10 + (k0 - 8)) * STG_STRIDE;
-        }
-        const uint8_t * slot = ring + (size_t) (q % NST) * a.stage_bytes;
-        const int bi = (t * 32 + lane) % nb;
+    for (int c = 0; c < 12; c++) acc[c] = 0.f;
+    auto process = [&](int i, const TileRegs & r) {
+        const int g = w + i * G, j = g / TU, t = g - j * TU;
+        const UnitRef ur = locate_unit(a, group_global + j * n_groups);
+        const int type = ur.si == 0 ? a.seg[0].type : (ur.si == 1 ? a.seg[1].type : a.seg[2].type);
+        BlockInts bi;
+#pragma unroll
+        for (int l = 0; l < 4; l++) bi.p[l] = 0;
         switch (type) {
-            case T_Q4_K: block_q45k<false>(slot, nb, lane, bi, A, stg); break;
-            case T_Q5_K: block_q45k<true>(slot, nb, lane, bi, A, stg); break;
-            case T_Q6_K: block_q6k(slot, nb, lane, bi, A, stg); break;
-            default:     block_q80(slot, nb, lane, bi, A, stg); break;
+            case T_Q4_K: ints_q45k<false>(r, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi); break;
+            case T_Q5_K: ints_q45k<true>(r, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi); break;
+            case T_Q6_K: ints_q6k(r, A.q + (size_t) t * 256, A.dx[t], bi); break;
+            default:     ints_q80(r, A.q + (size_t) t * 32, A.dx[t], bi); break;
         }
-        __syncwarp();
-        // chain phase: chain = (row r of the unit, lane-of-AVX k); blocks of row r inside this tile, in block order
-        if (lane < n_chains) {
-            const int lo = max(r0 * nb, t * 32) - t * 32, hi = min(r0 * nb + nb, t * 32 + 32) - t * 32;
-            float v = acc[0];
-            if (type == T_Q5_K && k0 == 8) {
-                // summs += dmin * (float) sum(prod): separate mul and add (cpp/ggml/src/ggml-quants.c:7516)
-                for (int l = lo; l < hi; l++)
-                    v = __fadd_rn(v, __fmul_rn(__uint_as_float(stg[9 * STG_STRIDE + l]), (float) (int) stg[10 * STG_STRIDE + l]));
+        // ---- chain step, strictly in block order
+        if (G > 1 && g > 0) bar_sync_n(bar_in, 64);               // step g-1 is done (and its chain state published)
+        if (t == 0) {
+#pragma unroll
+            for (int c = 0; c < 12; c++) acc[c] = 0.f;
+        } else if (G > 1) {
+#pragma unroll
+            for (int c = 0; c < 12; c++) acc[c] = handoff[c * 32 + lane];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[c] = __fmaf_rn(bi.d, (float) bi.s[c], acc[c]);
+        if (type == T_Q4_K) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) acc[8 + l] = __fmaf_rn(bi.dmin, (float) bi.p[l], acc[8 + l]);
+        } else if (type == T_Q5_K) {
+            acc[8] = __fadd_rn(acc[8], __fmul_rn(bi.dmin, (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3])));
+        }
+        if (G > 1 && g != total - 1) {
+            if (t != TU - 1) {
+#pragma unroll
+                for (int c = 0; c < 12; c++) handoff[c * 32 + lane] = acc[c];
+                __threadfence_block();
+            }
+            bar_arrive_n(bar_out, 64);
+        }
+        if (t != TU - 1) return;
+        // ---- unit complete: this lane's row
+        const float val = finish_row(type, acc);
+        const float oth = __shfl_xor_sync(0xffffffffu, val, 1);    // partner row (2i <-> 2i+1)
+        const int row = ur.row_base + ur.u * 32 + lane;
+        if (EPI == EPI_STORE) {
+            a.out[row] = val;
+        } else if (EPI == EPI_RESID) {
+            a.out[row] = __fadd_rn(val, a.resid[row]);             // ggml_add(cur, inpSA / ffn_inp): llama.cpp:8865, 8901
+        } else if (EPI == EPI_SILU) {
+            // rows (2r, 2r+1) = (gate r, up r): silu(gate) * up, cpp/src/llama.cpp:7960-8085
+            if ((lane & 1) == 0) a.out[row >> 1] = __fmul_rn(silu_exact(val), oth);
+        } else {  // EPI_QKV
+            const int pos = a.st->pos;
+            const float v0 = (lane & 1) ? oth : val, v1 = (lane & 1) ? val : oth;   // (x0, x1) of this row's RoPE pair
+            if (row < a.n_q + a.n_k) {
+                // RoPE NORM mode on the pair (x0, x1): cpp/ggml/src/ggml.c:14121-14135
+                const int i0 = (row & ~1) % a.head_dim;
+                const float2 cs2 = a.rope[(size_t) pos * (a.head_dim / 2) + (i0 >> 1)];
+                const float y = (lane & 1) ? __fadd_rn(__fmul_rn(v0, cs2.y), __fmul_rn(v1, cs2.x))
+                                           : __fsub_rn(__fmul_rn(v0, cs2.x), __fmul_rn(v1, cs2.y));
+                if (row < a.n_q) a.q_out[row] = y;
+                else a.k_cache[(size_t) pos * a.kv_dim + (row - a.n_q)] = __float2half_rn(y);   // K post-RoPE as f16: llama.cpp:7849-7853
             } else {
-#pragma unroll 8
-                for (int l = lo; l < hi; l++)
-                    v = __fmaf_rn(__uint_as_float(stg[coef0 + l]), (float) (int) stg[val0 + l], v);
-            }
-            acc[0] = v;
-        }
-#pragma unroll
-        for (int cs = 1; cs < MAX_CHAIN_SLOTS; cs++) {
-            const int ch = cs * 32 + lane;
-            if (cs * 32 < n_chains && ch < n_chains) {
-                const int r = ch / C, kk = ch - r * C;
-                const int lo = max(r * nb, t * 32) - t * 32, hi = min(r * nb + nb, t * 32 + 32) - t * 32;
-                const int coef_row = kk < 8 ? 0 : 9;
-                const int val_row  = kk < 8 ? 1 + kk : 10 + (kk - 8);
-                float v = acc[cs];
-                if (type == T_Q5_K && kk == 8) {
-                    for (int l = lo; l < hi; l++)
-                        v = __fadd_rn(v, __fmul_rn(__uint_as_float(stg[9 * STG_STRIDE + l]), (float) (int) stg[10 * STG_STRIDE + l]));
-                } else {
-                    for (int l = lo; l < hi; l++)
-                        v = __fmaf_rn(__uint_as_float(stg[coef_row * STG_STRIDE + l]), (float) (int) stg[val_row * STG_STRIDE + l], v);
-                }
-                acc[cs] = v;
+                a.v_cache[(size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)] = __float2half_rn(val);
             }
         }
-        __syncwarp();
-        if (t != TU - 1) continue;
+    };
 
-        // ---- unit complete: publish chain results, finish one row per lane, epilogue on row pairs
-        float * fin = reinterpret_cast<float *>(stg);
-#pragma unroll
-        for (int cs = 0; cs < MAX_CHAIN_SLOTS; cs++) {
-            const int ch = cs * 32 + lane;
-            if (cs * 32 < n_chains && ch < n_chains) fin[ch] = acc[cs];
-        }
-        __syncwarp();
-        float val = 0.f;
-        if (lane < rows_unit) val = finish_row(type, fin + lane * C);
-        const float nxt = __shfl_down_sync(0xffffffffu, val, 1);
-        __syncwarp();
-        if (lane < rows_unit && (lane & 1) == 0) {
-            const float v0 = val, v1 = nxt;
-            const int row = ur.row_base + ur.u * rows_unit + lane;  // virtual row of v0; v1 is row + 1
-            if (EPI == EPI_STORE) {
-                a.out[row] = v0; a.out[row + 1] = v1;
-            } else if (EPI == EPI_RESID) {
-                // ggml_add(cur, inpSA) / ggml_add(cur, ffn_inp): cpp/src/llama.cpp:8865, 8901
-                a.out[row] = __fadd_rn(v0, a.resid[row]); a.out[row + 1] = __fadd_rn(v1, a.resid[row + 1]);
-            } else if (EPI == EPI_SILU) {
-                // rows (2r, 2r+1) = (gate r, up r): silu(gate) * up, cpp/src/llama.cpp:7960-8085
-                a.out[row >> 1] = __fmul_rn(silu_exact(v0), v1);
-            } else {  // EPI_QKV
-                const int pos = a.st->pos;
-                if (row < a.n_q + a.n_k) {
-                    // RoPE NORM mode on the pair (x0, x1): cpp/ggml/src/ggml.c:14121-14135
-                    const int i0 = row % a.head_dim;
-                    const float2 cs2 = a.rope[(size_t) pos * (a.head_dim / 2) + (i0 >> 1)];
-                    const float y0 = __fsub_rn(__fmul_rn(v0, cs2.x), __fmul_rn(v1, cs2.y));
-                    const float y1 = __fadd_rn(__fmul_rn(v0, cs2.y), __fmul_rn(v1, cs2.x));
-                    if (row < a.n_q) {
-                        a.q_out[row] = y0; a.q_out[row + 1] = y1;
-                    } else {
-                        // K stored post-RoPE as f16 at slot `pos`: llm_build_kv_store, cpp/src/llama.cpp:7849-7853
-                        *reinterpret_cast<__half2 *>(a.k_cache + (size_t) pos * a.kv_dim + (row - a.n_q)) =
-                            __halves2half2(__float2half_rn(y0), __float2half_rn(y1));
-                    }
-                } else {
-                    *reinterpret_cast<__half2 *>(a.v_cache + (size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)) =
-                        __halves2half2(__float2half_rn(v0), __float2half_rn(v1));
-                }
-            }
-        }
+    for (int i = 0; i < n_items; i += 2) {
+        if (i + 1 < n_items) prefetch(i + 1, rb);
+        process(i, ra);
+        if (i + 2 < n_items) prefetch(i + 2, ra);
+        if (i + 1 < n_items) process(i + 1, rb);
     }
-    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -650,10 +592,10 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
         for (int b = 0; b < nb; b++) {
             uint8_t * o = out + (size_t) b * 292;
             if (threadIdx.x == 0) *reinterpret_cast<float *>(o) = A.dx[b];
-            for (int e = threadIdx.x; e < 256; e += blockDim.x) o[4 + e] = (uint8_t) A.q[((size_t) ((e >> 4) * nb + b)) * 16 + (e & 15)];
+            for (int e = threadIdx.x; e < 256; e += blockDim.x) o[4 + e] = (uint8_t) A.q[(size_t) b * 256 + e];
             for (int i = threadIdx.x; i < 16; i += blockDim.x) {
                 int s = 0;
-                for (int e = 16 * i; e < 16 * i + 16; e++) s += A.q[((size_t) ((e >> 4) * nb + b)) * 16 + (e & 15)];
+                for (int e = 16 * i; e < 16 * i + 16; e++) s += A.q[(size_t) b * 256 + e];
                 o[260 + 2 * i] = (uint8_t) (s & 0xff); o[261 + 2 * i] = (uint8_t) ((s >> 8) & 0xff);
             }
         }
@@ -662,7 +604,7 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
         for (int b = threadIdx.x; b < nb32; b += blockDim.x) {
             uint8_t * o = out + (size_t) b * 34;
             *reinterpret_cast<__half *>(o) = __float2half_rn(A.dx[b]);     // dx is an exact f16 value; 34*b is even
-            for (int e = 0; e < 32; e++) o[2 + e] = (uint8_t) A.q[((size_t) ((e >> 4) * nb32 + b)) * 16 + (e & 15)];
+            for (int e = 0; e < 32; e++) o[2 + e] = (uint8_t) A.q[(size_t) b * 32 + e];
         }
     }
 }
