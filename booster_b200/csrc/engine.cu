@@ -61,33 +61,36 @@ __device__ __forceinline__ void copy16(uint8_t * dst, const uint8_t * src) {
     for (int j = 0; j < 16; j++) dst[j] = src[j];
 }
 __global__ void k_retile(int type, const uint8_t * __restrict__ src, int64_t n_rows, int nb, int vstride, int voff,
-                         uint8_t * p0, uint8_t * p1, uint8_t * p2, uint8_t * p3) {
+                         uint8_t * tiles) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;   // source block index = row*nb + bi
     if (i >= n_rows * nb) return;
     const int64_t row = i / nb, bi = i % nb;
     const int64_t vrow = row * vstride + voff;                            // destination (virtual) row
     const int64_t T = (vrow >> 5) * nb + bi; const int lane = (int) (vrow & 31);   // tile = block bi of 32 rows, one row per lane
+    uint8_t * p0 = tiles + (size_t) T * tile_bytes_of(type);    // the tile is one contiguous chunk; field offsets below
+    uint8_t * p1 = p0 + 4096, * p2 = p0 + 4608;
+    uint8_t * p3 = p0 + (type == T_Q6_K ? 6656 : 1024);
     if (type == T_Q4_K) {
         const uint8_t * b = src + i * 144;   // {half d, half dmin, u8 scales[12], u8 qs[128]}  ggml-common.h:267-277
-        for (int c = 0; c < 8; c++) copy16(p0 + T * 4096 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
-        for (int w = 0; w < 3; w++) for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) w * 32 + lane) * 4 + j] = b[4 + 4 * w + j];
-        for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) 3 * 32 + lane) * 4 + j] = b[j];
+        for (int c = 0; c < 8; c++) copy16(p0 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
+        for (int w = 0; w < 3; w++) for (int j = 0; j < 4; j++) p1[((size_t) w * 32 + lane) * 4 + j] = b[4 + 4 * w + j];
+        for (int j = 0; j < 4; j++) p1[((size_t) 3 * 32 + lane) * 4 + j] = b[j];
     } else if (type == T_Q5_K) {
         const uint8_t * b = src + i * 176;   // {half d, half dmin, u8 scales[12], u8 qh[32], u8 qs[128]}  :284-295
-        for (int c = 0; c < 8; c++) copy16(p0 + T * 4096 + ((size_t) c * 32 + lane) * 16, b + 48 + 16 * c);
-        for (int c = 0; c < 2; c++) copy16(p2 + T * 1024 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
-        for (int w = 0; w < 3; w++) for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) w * 32 + lane) * 4 + j] = b[4 + 4 * w + j];
-        for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) 3 * 32 + lane) * 4 + j] = b[j];
+        for (int c = 0; c < 8; c++) copy16(p0 + ((size_t) c * 32 + lane) * 16, b + 48 + 16 * c);
+        for (int c = 0; c < 2; c++) copy16(p2 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
+        for (int w = 0; w < 3; w++) for (int j = 0; j < 4; j++) p1[((size_t) w * 32 + lane) * 4 + j] = b[4 + 4 * w + j];
+        for (int j = 0; j < 4; j++) p1[((size_t) 3 * 32 + lane) * 4 + j] = b[j];
     } else if (type == T_Q6_K) {
         const uint8_t * b = src + i * 210;   // {u8 ql[128], u8 qh[64], i8 scales[16], half d}  :302-307
-        for (int c = 0; c < 8; c++) copy16(p0 + T * 4096 + ((size_t) c * 32 + lane) * 16, b + 16 * c);
-        for (int c = 0; c < 4; c++) copy16(p2 + T * 2048 + ((size_t) c * 32 + lane) * 16, b + 128 + 16 * c);
-        for (int w = 0; w < 4; w++) for (int j = 0; j < 4; j++) p1[T * 512 + ((size_t) w * 32 + lane) * 4 + j] = b[192 + 4 * w + j];
-        p3[T * 64 + lane * 2] = b[208]; p3[T * 64 + lane * 2 + 1] = b[209];
+        for (int c = 0; c < 8; c++) copy16(p0 + ((size_t) c * 32 + lane) * 16, b + 16 * c);
+        for (int c = 0; c < 4; c++) copy16(p2 + ((size_t) c * 32 + lane) * 16, b + 128 + 16 * c);
+        for (int w = 0; w < 4; w++) for (int j = 0; j < 4; j++) p1[((size_t) w * 32 + lane) * 4 + j] = b[192 + 4 * w + j];
+        p3[lane * 2] = b[208]; p3[lane * 2 + 1] = b[209];
     } else {                                 // T_Q8_0: {half d, i8 qs[32]}  :186-190
         const uint8_t * b = src + i * 34;
-        for (int c = 0; c < 2; c++) copy16(p0 + T * 1024 + ((size_t) c * 32 + lane) * 16, b + 2 + 16 * c);
-        p3[T * 64 + lane * 2] = b[0]; p3[T * 64 + lane * 2 + 1] = b[1];
+        for (int c = 0; c < 2; c++) copy16(p0 + ((size_t) c * 32 + lane) * 16, b + 2 + 16 * c);
+        p3[lane * 2] = b[0]; p3[lane * 2 + 1] = b[1];
     }
 }
 
@@ -113,12 +116,11 @@ static DevMat upload_tiled(const HostTensor * src, int n_src, cudaStream_t st) {
         if (src[i].type != type || src[i].k != k || src[i].rows != rows1) throw std::runtime_error("interleaved tensors must share type and shape");
     if (k % 256 != 0) throw std::runtime_error("matrix inner dimension must be a multiple of 256 (got " + std::to_string(k) + ")");
     int blk_bytes = 0, wpb = 256;
-    size_t tb[4] = {0, 0, 0, 0};   // bytes per tile of each plane
     switch (type) {
-        case T_Q4_K: blk_bytes = 144; tb[0] = 4096; tb[1] = 512; break;
-        case T_Q5_K: blk_bytes = 176; tb[0] = 4096; tb[1] = 512; tb[2] = 1024; break;
-        case T_Q6_K: blk_bytes = 210; tb[0] = 4096; tb[1] = 512; tb[2] = 2048; tb[3] = 64; break;
-        case T_Q8_0: blk_bytes = 34; wpb = 32; tb[0] = 1024; tb[3] = 64; break;
+        case T_Q4_K: blk_bytes = 144; break;
+        case T_Q5_K: blk_bytes = 176; break;
+        case T_Q6_K: blk_bytes = 210; break;
+        case T_Q8_0: blk_bytes = 34; wpb = 32; break;
         default: throw std::runtime_error("unsupported matrix type " + std::to_string(type) + " (supported: Q4_K, Q5_K, Q6_K, Q8_0)");
     }
     DevMat d;
@@ -130,23 +132,20 @@ static DevMat upload_tiled(const HostTensor * src, int n_src, cudaStream_t st) {
     const size_t n_tiles = (size_t) vrows * nb / 32;
     const size_t raw1 = (size_t) blk_bytes * nb * rows1;
     d.bytes = raw1 * n_src;
-    size_t off[4], total = 0;
-    for (int i = 0; i < 4; i++) { off[i] = total; total += align_up(tb[i] * n_tiles, 256); }
     uint8_t * base = nullptr;
-    CU(cudaMalloc(&base, total));
+    CU(cudaMalloc(&base, align_up((size_t) tile_bytes_of(type) * n_tiles, 256)));
     d.alloc = base;
-    uint8_t * p[4] = { base + off[0], base + off[1], base + off[2], base + off[3] };
     uint8_t * tmp = nullptr;
     CU(cudaMalloc(&tmp, raw1));
     for (int i = 0; i < n_src; i++) {
         CU(cudaMemcpyAsync(tmp, src[i].data, raw1, cudaMemcpyHostToDevice, st));
         const int64_t n_blocks = rows1 * nb;
-        k_retile<<<(unsigned) ((n_blocks + 127) / 128), 128, 0, st>>>(type, tmp, rows1, nb, n_src, i, p[0], p[1], p[2], p[3]);
+        k_retile<<<(unsigned) ((n_blocks + 127) / 128), 128, 0, st>>>(type, tmp, rows1, nb, n_src, i, base);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(st));
     }
     CU(cudaFree(tmp));
-    d.m.p0 = p[0]; d.m.p1 = tb[1] ? p[1] : nullptr; d.m.p2 = tb[2] ? p[2] : nullptr; d.m.p3 = tb[3] ? p[3] : nullptr;
+    d.m.p0 = base;
     return d;
 }
 static DevMat upload_matrix(int type, const void * host, int64_t n_rows, int64_t k, cudaStream_t st) {
@@ -473,15 +472,40 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     a.tiles_unit = a.seg[0].tiles_unit;
     for (int i = 0; i < a.n_seg; i++)
         if (a.seg[i].tiles_unit != a.tiles_unit) throw std::runtime_error("segments of one launch must share the unit shape");
-    // warps per 32-row unit: as many (4, 2, 1) as still leave every unit resident in ONE wave of sm_count x 12 warps
-    const int slots = c->sm_count * MV_WARPS;
-    a.group = a.n_units * 4 <= slots ? 4 : (a.n_units * 2 <= slots ? 2 : 1);
-    const size_t smem = act_smem_bytes(a.k, a.act_q8_0) + (size_t) (MV_WARPS / a.group) * HANDOFF_WORDS * 4;
+    int sb = 0;
+    for (int i = 0; i < a.n_seg; i++) sb = std::max(sb, tile_bytes_of(a.seg[i].type));
+    a.stage_bytes = (sb + 127) / 128 * 128;
+    // launch shape: W warps per CTA (one CTA per SM), S ring stages per warp, G warps per 32-row unit. Pick the
+    // combination with the most concurrently active warps (every unit resident in as few waves as possible),
+    // then the deepest ring that still fits the shared memory.
+    const size_t act_bytes = act_smem_bytes(a.k, a.act_q8_0);
+    const size_t budget = 227 * 1024 - 512;
+    int bestW = 0, bestG = 1, bestS = 0; double best = -1;
+    for (int W = MV_MAX_WARPS; W >= 4; W -= 2) {
+        for (int G = W; G >= 1; G--) {
+            if (W % G) continue;
+            if (G > 1 && (long long) a.n_units * G > (long long) c->sm_count * W) continue;   // sharing only within one wave
+            if (G > a.tiles_unit && G > 1) continue;
+            const size_t fixed = act_bytes + (G > 1 ? (size_t) (W / G) * HANDOFF_WORDS * 4 : 0) + (size_t) W * 4 * 8 + (size_t) W * 8;
+            if (fixed + (size_t) W * 2 * a.stage_bytes > budget) continue;
+            const int S = (int) std::min<size_t>(4, (budget - fixed) / ((size_t) W * a.stage_bytes));
+            const long long warps = (long long) a.n_units * G, slots = (long long) c->sm_count * W;
+            const long long waves = (warps + slots - 1) / slots;
+            const double active = (double) warps / (double) waves + 0.01 * S;   // average concurrently running warps
+            if (active > best) { best = active; bestW = W; bestG = G; bestS = S; }
+            break;   // largest feasible G for this W
+        }
+    }
+    if (bestW == 0) throw std::runtime_error("activation vector too long for the shared-memory budget");
+    a.group = bestG; a.stages = bestS;
+    const int W = bestW;
+    const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + (a.group > 1 ? (size_t) (W / a.group) * HANDOFF_WORDS * 4 : 0)
+                      + (size_t) W * a.stages * 8 + (size_t) W * 8;
     static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
     if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }
     const int grid = std::max(1, std::min(a.n_units, c->sm_count));
-    k_matvec<EPI><<<grid, MV_THREADS, smem, c->st>>>(a);
+    k_matvec<EPI><<<grid, W * 32, smem, c->st>>>(a);
     c->launches++;
 }
 
@@ -1001,7 +1025,7 @@ static int op_quantize(const float * x, int64_t k, void * out, int q80) {
         CU(cudaMemcpy(dx.p, x, (size_t) k * 4, cudaMemcpyHostToDevice));
         const size_t smem = act_smem_bytes((int) k, q80);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_quantize_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        k_quantize_export<<<1, MV_THREADS, smem>>>(dx.as<float>(), (int) k, q80, dout.as<uint8_t>());
+        k_quantize_export<<<1, 384, smem>>>(dx.as<float>(), (int) k, q80, dout.as<uint8_t>());
         CU(cudaGetLastError());
         CU(cudaMemcpy(out, dout.p, ob, cudaMemcpyDeviceToHost));
         return 0;

@@ -22,10 +22,11 @@
 // holds block b of 32 consecutive rows, ONE ROW PER LANE, every field transposed so that a warp-wide load of one
 // field is a dense 128/512-byte stream. A lane therefore walks the blocks of its own row in order and its fp32
 // fma chains never leave its registers:
-//   Q4_K: p0 qs uint4[8][32] (4096 B)  p1 u32[4][32] = 12 scale bytes + (d,dmin) (512 B)
-//   Q5_K: same + p2 qh uint4[2][32] (1024 B)
-//   Q6_K: p0 ql uint4[8][32]  p2 qh uint4[4][32] (2048 B)  p1 scales u32[4][32]  p3 d u16[32] (64 B)
-//   Q8_0: p0 qs uint4[2][32] (1024 B)  p3 d u16[32]      (blocks of 32 weights)
+// fma chains never leave its registers. A tile is ONE contiguous chunk (a single TMA bulk copy):
+//   Q4_K (4608 B): qs uint4[8][32] | u32[4][32] = 12 scale bytes + (d,dmin)
+//   Q5_K (5632 B): same | qh uint4[2][32]
+//   Q6_K (6720 B): ql uint4[8][32] | scales u32[4][32] | qh uint4[4][32] | d u16[32]
+//   Q8_0 (1088 B): qs uint4[2][32] | d u16[32]                 (blocks of 32 weights)
 // ffn_gate and ffn_up are interleaved row by row into one virtual matrix (row 2r = gate r, 2r+1 = up r).
 #pragma once
 #include <cuda_fp16.h>
@@ -43,11 +44,11 @@ struct TMat {
     int rows_unit = 32;   // a work unit = 32 rows (one per lane) x all nb blocks
     int tiles_unit = 0;   // = nb
     int n_units = 0;      // = n_rows/32
-    const uint8_t * p0 = nullptr;
-    const uint8_t * p1 = nullptr;
-    const uint8_t * p2 = nullptr;
-    const uint8_t * p3 = nullptr;
+    const uint8_t * p0 = nullptr;   // tiles, tile_bytes_of(type) each
 };
+__host__ __device__ __forceinline__ int tile_bytes_of(int type) {
+    return type == T_Q4_K ? 4608 : type == T_Q5_K ? 5632 : type == T_Q6_K ? 6720 : 1088;
+}
 
 // per-token scalars, device-resident so that one CUDA graph serves every token
 struct DecodeState {
@@ -70,7 +71,9 @@ struct MatvecArgs {
     float eps;
     int act_q8_0;              // 0: Q8_K activations, 1: Q8_0 activations
     int tiles_unit;            // identical for every segment of a launch (same K, same block width)
-    int group;                 // G = warps sharing one 32-row unit (1, 2 or 4): tile t is computed by warp t % G
+    int group;                 // G = warps sharing one 32-row unit (a divisor of the CTA's warp count)
+    int stages;                // tiles of shared-memory ring per warp (>= 2)
+    int stage_bytes;           // ring slot size = largest tile of the launch, 128-byte multiple
     // epilogue
     float * out;
     const float * resid;
@@ -83,8 +86,7 @@ struct MatvecArgs {
     const DecodeState * st;
 };
 
-static constexpr int MV_THREADS = 384;                      // one persistent CTA per SM
-static constexpr int MV_WARPS   = MV_THREADS / 32;
+static constexpr int MV_MAX_WARPS = 16;                     // one persistent CTA per SM, 8..16 warps (host picks)
 static constexpr int HANDOFF_WORDS = 12 * 32;               // chain state of one unit: 12 fp32 chains x 32 rows
 
 // ------------------------------------------------------------------------------------------------------------
@@ -236,6 +238,44 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
                                                   float eps, int k, int act_q8_0, const ActSmem & A, double * red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
+    if (norm_w != nullptr && k / 256 <= 2 * nwarp) {
+        // single pass: a warp keeps its (at most two) blocks of x and of the norm weight in registers, so x is read
+        // once and only one load latency sits in front of the mat-vec
+        float v[2][8], ww[2][8];
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = warp + u * nwarp;
+            if (b < k / 256) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(x + b * 256 + lane * 8);
+                const float4 a1 = *reinterpret_cast<const float4 *>(x + b * 256 + lane * 8 + 4);
+                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(norm_w + b * 256 + lane * 8));
+                const float4 w1 = __ldg(reinterpret_cast<const float4 *>(norm_w + b * 256 + lane * 8 + 4));
+                v[u][0] = a0.x; v[u][1] = a0.y; v[u][2] = a0.z; v[u][3] = a0.w; v[u][4] = a1.x; v[u][5] = a1.y; v[u][6] = a1.z; v[u][7] = a1.w;
+                ww[u][0] = w0.x; ww[u][1] = w0.y; ww[u][2] = w0.z; ww[u][3] = w0.w; ww[u][4] = w1.x; ww[u][5] = w1.y; ww[u][6] = w1.z; ww[u][7] = w1.w;
+#pragma unroll
+                for (int i = 0; i < 8; i++) s += (double) __fmul_rn(v[u][i], v[u][i]);
+            }
+        }
+        s = warp_sum_d(s);
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < nwarp; w++) tot += red[w];
+        const float mean = (float) (tot / (double) k);
+        const float sc = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = warp + u * nwarp;
+            if (b < k / 256) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], sc), ww[u][i]);
+                if (act_q8_0) q80_blocks_warp(v[u], lane, b, A);
+                else          q8k_block_warp(v[u], lane, b, A);
+            }
+        }
+        return;
+    }
     float scale = 1.f;
     if (norm_w != nullptr) {
         double s = 0.0;
@@ -290,60 +330,57 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// One lane = one ROW. A tile is block b of 32 rows; a lane streams its row's blocks through registers (coalesced
-// 16-byte loads thanks to the transposed tile layout; the next tile is in flight while this one is computed),
-// computes the block's exact integers — s[m] = the m-th int32 lane of the reference's AVX2 `sumi`, p[l] = the
-// l-th lane of its mins product — and advances its own 12 fp32 chains:
+// mbarrier / TMA bulk-copy wrappers (PTX; sm_90+ instructions, compiled for sm_100a)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (TMA engine, no registers, no per-lane addressing); completes `bytes` on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// One lane = one ROW. A tile is block b of 32 rows. Every warp streams ITS tiles through a private ring in shared
+// memory: lane 0 issues one TMA bulk copy per tile (`stages - 1` tiles ahead), completion lands on an mbarrier, and
+// each lane then reads its own row's fields with conflict-free 16-byte LDS. Per tile a lane computes the block's
+// exact integers — s[m] = the m-th int32 lane of the reference's AVX2 `sumi`, p[l] = the l-th lane of its mins
+// product — and advances its own 12 fp32 chains:
 //   acc[m] = fma(d_b, (float) s[m], acc[m])                      (ggml-quants.c:6972, 7556, 8216, 5376)
 //   Q4_K: acc[8+l] = fma(dmin_b, (float) p[l], acc[8+l])  (:6934)      Q5_K: acc[8] += dmin_b * (float) sum p  (:7516)
 // ------------------------------------------------------------------------------------------------------------
-struct TileRegs  { uint4 q[12]; uint32_t s[5]; };
 struct BlockInts { int s[8]; int p[4]; float d, dmin; };
 
-__device__ __forceinline__ void load_tile(const TMat & m, size_t T, int lane, TileRegs & r) {
-    switch (m.type) {
-        case T_Q4_K: case T_Q5_K: {
-            const uint8_t * q = m.p0 + T * 4096 + lane * 16;
-#pragma unroll
-            for (int c = 0; c < 8; c++) r.q[c] = ldg_stream_v4(q + c * 512);
-            const uint8_t * sd = m.p1 + T * 512 + lane * 4;
-#pragma unroll
-            for (int w = 0; w < 4; w++) r.s[w] = ldg_u32(sd + w * 128);
-            if (m.type == T_Q5_K) {
-                r.q[8] = ldg_stream_v4(m.p2 + T * 1024 + lane * 16);
-                r.q[9] = ldg_stream_v4(m.p2 + T * 1024 + 512 + lane * 16);
-            }
-        } break;
-        case T_Q6_K: {
-            const uint8_t * q = m.p0 + T * 4096 + lane * 16;
-#pragma unroll
-            for (int c = 0; c < 8; c++) r.q[c] = ldg_stream_v4(q + c * 512);
-            const uint8_t * h = m.p2 + T * 2048 + lane * 16;
-#pragma unroll
-            for (int c = 0; c < 4; c++) r.q[8 + c] = ldg_stream_v4(h + c * 512);
-            const uint8_t * sc = m.p1 + T * 512 + lane * 4;
-#pragma unroll
-            for (int w = 0; w < 4; w++) r.s[w] = ldg_u32(sc + w * 128);
-            r.s[4] = ldg_u16(m.p3 + T * 64 + lane * 2);
-        } break;
-        default: {
-            r.q[0] = ldg_stream_v4(m.p0 + T * 1024 + lane * 16);
-            r.q[1] = ldg_stream_v4(m.p0 + T * 1024 + 512 + lane * 16);
-            r.s[4] = ldg_u16(m.p3 + T * 64 + lane * 2);
-        } break;
-    }
-}
-
+__device__ __forceinline__ uint4    lds_u4(const uint8_t * p)  { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ uint32_t lds_u32(const uint8_t * p) { return *reinterpret_cast<const uint32_t *>(p); }
 // 16 activation bytes of the current block, same address in every lane (broadcast)
 __device__ __forceinline__ int4 act16(const int8_t * ab, int slot) { return *reinterpret_cast<const int4 *>(ab + slot * 16); }
 
+// `sl` = the tile in shared memory + lane*16 (qs chunks) ; `sw` = tile + 4096 + lane*4 (the u32 plane)
 template <bool Q5>
-__device__ __forceinline__ void ints_q45k(const TileRegs & r, const int8_t * ab, const int * bp, float yd, BlockInts & o) {
-    const uint32_t s0 = r.s[0], s1 = r.s[1], s2 = r.s[2], dmw = r.s[3];
+__device__ __forceinline__ void ints_q45k(const uint8_t * sl, const uint8_t * sw, const int8_t * ab, const int * bp, float yd, BlockInts & o) {
+    const uint32_t s0 = lds_u32(sw), s1 = lds_u32(sw + 128), s2 = lds_u32(sw + 256), dmw = lds_u32(sw + 384);
     // the 8 scale bytes and 8 min bytes (get_scale_min_k4 packing, cpp/ggml/src/ggml-quants.c:1891-1898)
     const uint32_t sc_a = s0 & 0x3f3f3f3fu, m_a = s1 & 0x3f3f3f3fu;
     const uint32_t sc_b = (s2 & 0x0f0f0f0fu) | (((s0 >> 6) & 0x03030303u) << 4);
     const uint32_t m_b  = ((s2 >> 4) & 0x0f0f0f0fu) | (((s1 >> 6) & 0x03030303u) << 4);
+    uint4 qh[2];
+    if (Q5) { qh[0] = lds_u4(sl + 4608); qh[1] = lds_u4(sl + 4608 + 512); }
     // s = s_lo + (s_hi16 >> 4): the high nibbles are multiplied IN PLACE (mask 0xf0 = 16 x value, unsigned dp4a);
     // their scaled sum is an exact multiple of 16, so the shift is exact
     int s_lo[8], s_hi[8];
@@ -355,7 +392,7 @@ __device__ __forceinline__ void ints_q45k(const TileRegs & r, const int8_t * ab,
         const int sc_lo = (int) ((scw >> ((j & 1) * 16)) & 0xff), sc_hi = (int) ((scw >> ((j & 1) * 16 + 8)) & 0xff);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const uint4 w = r.q[2 * j + h];
+            const uint4 w = lds_u4(sl + (2 * j + h) * 512);
             const int4 alo = act16(ab, 4 * j + h), ahi = act16(ab, 4 * j + 2 + h);
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
@@ -365,7 +402,7 @@ __device__ __forceinline__ void ints_q45k(const TileRegs & r, const int8_t * ab,
                     s_hi[4 * h + wi] += sc_hi * dp4a_us(W & 0xf0f0f0f0u, word_of(ahi, wi), 0);
                 } else {
                     // qh bit 2j -> +16 on the low-nibble weight, bit 2j+1 -> +16 on the high-nibble one
-                    const uint32_t H = word_of(r.q[8 + h], wi);
+                    const uint32_t H = word_of(qh[h], wi);
                     const uint32_t lo = (W & 0x0f0f0f0fu) | (((H >> (2 * j)) & 0x01010101u) << 4);
                     const uint32_t hi = ((W >> 4) & 0x0f0f0f0fu) | (((H >> (2 * j + 1)) & 0x01010101u) << 4);
                     s_lo[4 * h + wi] += sc_lo * __dp4a((int) lo, word_of(alo, wi), 0);
@@ -390,7 +427,10 @@ __device__ __forceinline__ void ints_q45k(const TileRegs & r, const int8_t * ab,
 // q (0..63 per byte) -> q - 32 as signed bytes, without inter-byte borrows
 __device__ __forceinline__ uint32_t sub32_bytes(uint32_t q) { return ((q | 0x80808080u) - 0x20202020u) ^ 0x80808080u; }
 
-__device__ __forceinline__ void ints_q6k(const TileRegs & r, const int8_t * ab, float yd, BlockInts & o) {
+__device__ __forceinline__ void ints_q6k(const uint8_t * sl, const uint8_t * sw, const uint8_t * tile, int lane, const int8_t * ab, float yd, BlockInts & o) {
+    uint32_t scw[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) scw[i] = lds_u32(sw + i * 128);
 #pragma unroll
     for (int i = 0; i < 8; i++) o.s[i] = 0;
     // layout of a super-block: dequantize_row_q6_K (cpp/ggml/src/ggml-quants.c:2970-3000); half n, group g of 32
@@ -399,15 +439,15 @@ __device__ __forceinline__ void ints_q6k(const TileRegs & r, const int8_t * ab, 
     for (int n = 0; n < 2; n++) {
 #pragma unroll
         for (int mq = 0; mq < 2; mq++) {
-            const uint4 qh = r.q[8 + 2 * n + mq];
+            const uint4 qh = lds_u4(sl + 4608 + (2 * n + mq) * 512);
 #pragma unroll
             for (int gl = 0; gl < 2; gl++) {                      // one ql chunk serves groups gl (low nibble) and gl+2 (high)
-                const uint4 ql = r.q[4 * n + 2 * gl + mq];
+                const uint4 ql = lds_u4(sl + (4 * n + 2 * gl + mq) * 512);
 #pragma unroll
                 for (int gh = 0; gh < 2; gh++) {
                     const int g = gl + 2 * gh;
                     const int si = 8 * n + 2 * g + mq;
-                    const int sc = (int) (int8_t) ((r.s[si >> 2] >> ((si & 3) * 8)) & 0xff);
+                    const int sc = (int) (int8_t) ((scw[si >> 2] >> ((si & 3) * 8)) & 0xff);
                     const int4 a = act16(ab, 8 * n + 2 * g + mq);
 #pragma unroll
                     for (int wi = 0; wi < 4; wi++) {
@@ -420,18 +460,21 @@ __device__ __forceinline__ void ints_q6k(const TileRegs & r, const int8_t * ab, 
             }
         }
     }
-    o.d = __fmul_rn(yd, h16_to_f32(r.s[4]));             // y[i].d * fp16(x[i].d)
+    const float dw = __half2float(*reinterpret_cast<const __half *>(tile + 6656 + lane * 2));
+    o.d = __fmul_rn(yd, dw);                              // y[i].d * fp16(x[i].d)
     o.dmin = 0.f;
 }
 
-__device__ __forceinline__ void ints_q80(const TileRegs & r, const int8_t * ab, float yd, BlockInts & o) {
+__device__ __forceinline__ void ints_q80(const uint8_t * sl, const uint8_t * tile, int lane, const int8_t * ab, float yd, BlockInts & o) {
+    const uint4 w0 = lds_u4(sl), w1 = lds_u4(sl + 512);
     const int4 a0 = act16(ab, 0), a1 = act16(ab, 1);
 #pragma unroll
     for (int wi = 0; wi < 4; wi++) {
-        o.s[wi]     = __dp4a((int) word_of(r.q[0], wi), word_of(a0, wi), 0);
-        o.s[4 + wi] = __dp4a((int) word_of(r.q[1], wi), word_of(a1, wi), 0);
+        o.s[wi]     = __dp4a((int) word_of(w0, wi), word_of(a0, wi), 0);
+        o.s[4 + wi] = __dp4a((int) word_of(w1, wi), word_of(a1, wi), 0);
     }
-    o.d = __fmul_rn(h16_to_f32(r.s[4]), yd);             // fp16(x.d) * fp16(y.d)
+    const float dw = __half2float(*reinterpret_cast<const __half *>(tile + 1024 + lane * 2));
+    o.d = __fmul_rn(dw, yd);                              // fp16(x.d) * fp16(y.d)
     o.dmin = 0.f;
 }
 
@@ -444,78 +487,116 @@ __device__ __forceinline__ float finish_row(int type, const float (&c)[12]) {
     return h;
 }
 
-struct UnitRef { int si; int u; int row_base; };
-__device__ __forceinline__ UnitRef locate_unit(const MatvecArgs & a, int unit) {
-    UnitRef r; r.si = 0; r.u = unit; r.row_base = 0;
-    if (a.n_seg > 1 && r.u >= a.seg[0].n_units) { r.u -= a.seg[0].n_units; r.row_base += a.seg[0].n_rows; r.si = 1;
-        if (a.n_seg > 2 && r.u >= a.seg[1].n_units) { r.u -= a.seg[1].n_units; r.row_base += a.seg[1].n_rows; r.si = 2; } }
-    return r;
+// a work unit resolved against the launch's segments: type, first tile in HBM, first output row
+struct UnitDesc { int type; int row0; const uint8_t * tiles; };
+__device__ __forceinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit) {
+    int si = 0, u = unit, row_base = 0;
+    if (a.n_seg > 1 && u >= a.seg[0].n_units) { u -= a.seg[0].n_units; row_base += a.seg[0].n_rows; si = 1;
+        if (a.n_seg > 2 && u >= a.seg[1].n_units) { u -= a.seg[1].n_units; row_base += a.seg[1].n_rows; si = 2; } }
+    UnitDesc d;
+    d.type  = si == 0 ? a.seg[0].type : (si == 1 ? a.seg[1].type : a.seg[2].type);
+    const uint8_t * base = si == 0 ? a.seg[0].p0 : (si == 1 ? a.seg[1].p0 : a.seg[2].p0);
+    d.tiles = base + (size_t) u * a.tiles_unit * tile_bytes_of(d.type);
+    d.row0  = row_base + u * 32;
+    return d;
 }
-__device__ __forceinline__ void bar_sync_n(int id, int n)   { asm volatile("bar.sync %0, %1;"   :: "r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------------------
 // The fused quantized mat-vec: [RMSNorm] + activation quant (prologue) -> exact W.x -> epilogue.
-// A work unit is 32 rows. G warps (1, 2 or 4 — chosen by the host so that matrices with few rows still occupy
-// every SM) share a unit: warp w computes the integers of tiles t = w, w+G, ... concurrently with the others,
-// while the 12 fp32 chains of each row advance strictly in block order, handed from warp to warp through shared
-// memory under named barriers (producer bar.arrive / consumer bar.sync on the edge w -> w+1).
+// A work unit is 32 rows. G warps (chosen by the host so that matrices with few rows still occupy every SM)
+// share a unit: the group's tiles form ONE sequence g = j*TU + t over its units j, warp w computes the integers of
+// g = w, w+G, ... concurrently with the others, while the 12 fp32 chains of each row advance strictly in block
+// order, handed from warp to warp through shared memory (producer mbarrier.arrive [release] on the consumer's
+// edge barrier, consumer try_wait [acquire]); the ring w -> w+1 -> ... -> w never has two hand-offs in flight.
 // ------------------------------------------------------------------------------------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const MatvecArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ double red_smem[MV_WARPS];
+__global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ double red_smem[MV_MAX_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int G = a.group, TU = a.tiles_unit, S = a.stages;
+    // shared memory: ring (128-byte aligned slots) | activations | hand-off buffers | mbarriers
+    uint8_t * ring = smem_raw + (size_t) warp * S * a.stage_bytes;
+    uint8_t * act_base = smem_raw + (size_t) W * S * a.stage_bytes;
     const size_t act_bytes = act_smem_bytes(a.k, a.act_q8_0);
-    const ActSmem A = act_smem_carve(smem_raw, a.k, a.act_q8_0);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int G = a.group, TU = a.tiles_unit;
+    const ActSmem A = act_smem_carve(act_base, a.k, a.act_q8_0);
     const int grp = warp / G, w = warp - grp * G;              // group inside the CTA, warp inside the group
-    float * handoff = reinterpret_cast<float *>(smem_raw + act_bytes) + (size_t) grp * HANDOFF_WORDS;
-    const int bar_in  = 1 + grp * G + (w + G - 1) % G;         // edge (w-1) -> w
-    const int bar_out = 1 + grp * G + w;                       // edge w -> (w+1)
+    float * handoff = reinterpret_cast<float *>(act_base + act_bytes) + (size_t) grp * HANDOFF_WORDS;
+    const size_t ho_bytes = G > 1 ? (size_t) (W / G) * HANDOFF_WORDS * 4 : 0;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(act_base + act_bytes + ho_bytes);
+    const uint32_t full0   = smem_u32(bars + warp * S);                            // my ring slots' "tile landed" barriers
+    const uint32_t edge_in  = smem_u32(bars + W * S + warp);                        // "chain state for me is published"
+    const uint32_t edge_out = smem_u32(bars + W * S + grp * G + (w + 1 == G ? 0 : w + 1));
+    const uint32_t ring_u32 = smem_u32(ring);
+
+    if (lane == 0) {
+        for (int s = 0; s < S; s++) mbar_init(full0 + 8 * s, 1);
+        mbar_init(edge_in, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
 
     // group-major mapping: unit u -> CTA u % grid, group (u / grid) % groups_per_cta, so that launches with few
     // units spread over every SM
-    const int groups_per_cta = MV_WARPS / G;
+    const int groups_per_cta = W / G;
     const int group_global = grp * gridDim.x + blockIdx.x;
     const int n_groups = gridDim.x * groups_per_cta;
     const int my_units = group_global < a.n_units ? (a.n_units - group_global + n_groups - 1) / n_groups : 0;
-    // the group's tiles form ONE sequence g = j*TU + t over its units j; warp w computes g = w, w+G, ... so the
-    // hand-off ring w -> w+1 -> ... -> w never produces twice on an edge before the consumer has taken the first
     const int total = my_units * TU;
     const int n_items = w < total ? (total - w + G - 1) / G : 0;
 
-    auto prefetch = [&](int i, TileRegs & r) {
-        const int g = w + i * G, j = g / TU, t = g - j * TU;
-        const UnitRef ur = locate_unit(a, group_global + j * n_groups);
-        const TMat & m = ur.si == 0 ? a.seg[0] : (ur.si == 1 ? a.seg[1] : a.seg[2]);
-        load_tile(m, (size_t) ur.u * TU + t, lane, r);
+    // ---- producer side: item pi = (unit pj, tile pt) goes to ring slot pi % S
+    int pi = 0, pj = 0, pt = w, ps = 0;
+    while (pt >= TU && TU > 0 && pi < n_items) { pt -= TU; pj++; }
+    UnitDesc pd = describe_unit(a, group_global + pj * n_groups);
+    auto issue_next = [&]() {
+        if (pi >= n_items) return;
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t) tile_bytes_of(pd.type);
+            mbar_expect_tx(full0 + 8 * ps, bytes);
+            bulk_g2s(ring_u32 + (uint32_t) ps * a.stage_bytes, pd.tiles + (size_t) pt * bytes, bytes, full0 + 8 * ps);
+        }
+        pi++; ps = ps + 1 == S ? 0 : ps + 1;
+        pt += G;
+        if (pt >= TU) {
+            do { pt -= TU; pj++; } while (pt >= TU);
+            if (pi < n_items) pd = describe_unit(a, group_global + pj * n_groups);
+        }
     };
-
-    TileRegs ra, rb;
-    if (n_items > 0) prefetch(0, ra);                          // weights do not depend on x: stream before the prologue
+    // weights do not depend on x: fill the ring before the prologue
+    for (int s = 0; s < S - 1; s++) issue_next();
 
     prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem);
-    __syncthreads();
+    __syncthreads();                                           // activations + every warp's barrier inits are visible
 
+    // ---- consumer side
     float acc[12];
 #pragma unroll
     for (int c = 0; c < 12; c++) acc[c] = 0.f;
-    auto process = [&](int i, const TileRegs & r) {
-        const int g = w + i * G, j = g / TU, t = g - j * TU;
-        const UnitRef ur = locate_unit(a, group_global + j * n_groups);
-        const int type = ur.si == 0 ? a.seg[0].type : (ur.si == 1 ? a.seg[1].type : a.seg[2].type);
+    int cj = 0, ct = w, cs = 0, cpar = 0, n_in = 0;
+    while (ct >= TU && n_items > 0) { ct -= TU; cj++; }
+    UnitDesc cd = describe_unit(a, group_global + cj * n_groups);
+    for (int i = 0; i < n_items; i++) {
+        const int g = w + i * G;
+        const int t = ct, type = cd.type;
+        issue_next();                                          // keeps S-1 tiles in flight (slot of item i-1 is free)
+        mbar_wait(full0 + 8 * cs, (uint32_t) cpar);
+        const uint8_t * tile = ring + (size_t) cs * a.stage_bytes;
+        const uint8_t * sl = tile + lane * 16;
         BlockInts bi;
 #pragma unroll
         for (int l = 0; l < 4; l++) bi.p[l] = 0;
         switch (type) {
-            case T_Q4_K: ints_q45k<false>(r, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi); break;
-            case T_Q5_K: ints_q45k<true>(r, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi); break;
-            case T_Q6_K: ints_q6k(r, A.q + (size_t) t * 256, A.dx[t], bi); break;
-            default:     ints_q80(r, A.q + (size_t) t * 32, A.dx[t], bi); break;
+            case T_Q4_K: ints_q45k<false>(sl, tile + 4096 + lane * 4, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi); break;
+            case T_Q5_K: ints_q45k<true>(sl, tile + 4096 + lane * 4, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi); break;
+            case T_Q6_K: ints_q6k(sl, tile + 4096 + lane * 4, tile, lane, A.q + (size_t) t * 256, A.dx[t], bi); break;
+            default:     ints_q80(sl, tile, lane, A.q + (size_t) t * 32, A.dx[t], bi); break;
         }
+        __syncwarp();                                          // every lane is done reading the slot before it is refilled
+        cs = cs + 1 == S ? 0 : cs + 1; if (cs == 0) cpar ^= 1;
         // ---- chain step, strictly in block order
-        if (G > 1 && g > 0) bar_sync_n(bar_in, 64);               // step g-1 is done (and its chain state published)
+        if (G > 1 && g > 0) { mbar_wait(edge_in, (uint32_t) (n_in & 1)); n_in++; }   // step g-1 is done, its state published
         if (t == 0) {
 #pragma unroll
             for (int c = 0; c < 12; c++) acc[c] = 0.f;
@@ -535,15 +616,22 @@ __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const MatvecArgs a) {
             if (t != TU - 1) {
 #pragma unroll
                 for (int c = 0; c < 12; c++) handoff[c * 32 + lane] = acc[c];
-                __threadfence_block();
             }
-            bar_arrive_n(bar_out, 64);
+            mbar_arrive(edge_out);                             // release: my lane's stores above are visible to the waiter
         }
-        if (t != TU - 1) return;
+        // advance to my next tile
+        const UnitDesc done = cd;
+        ct += G;
+        if (ct >= TU) {
+            do { ct -= TU; cj++; } while (ct >= TU);
+            if (i + 1 < n_items) cd = describe_unit(a, group_global + cj * n_groups);
+        }
+        if (t != TU - 1) continue;
+
         // ---- unit complete: this lane's row
         const float val = finish_row(type, acc);
         const float oth = __shfl_xor_sync(0xffffffffu, val, 1);    // partner row (2i <-> 2i+1)
-        const int row = ur.row_base + ur.u * 32 + lane;
+        const int row = done.row0 + lane;
         if (EPI == EPI_STORE) {
             a.out[row] = val;
         } else if (EPI == EPI_RESID) {
@@ -566,13 +654,6 @@ __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const MatvecArgs a) {
                 a.v_cache[(size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)] = __float2half_rn(val);
             }
         }
-    };
-
-    for (int i = 0; i < n_items; i += 2) {
-        if (i + 1 < n_items) prefetch(i + 1, rb);
-        process(i, ra);
-        if (i + 2 < n_items) prefetch(i + 2, ra);
-        if (i + 1 < n_items) process(i + 1, rb);
     }
 }
 
@@ -583,7 +664,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const MatvecArgs a) {
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q8_0, uint8_t * __restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ double red_smem[MV_WARPS];
+    __shared__ double red_smem[MV_MAX_WARPS];
     const ActSmem A = act_smem_carve(smem_raw, k, act_q8_0);
     prologue_quantize(x, nullptr, 0.f, k, act_q8_0, A, red_smem);
     __syncthreads();
