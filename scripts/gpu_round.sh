@@ -1,0 +1,25 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench line, ncu launch list, one ncu --set full capture of a layer's kernels.
+# usage (from the repo root, under gpurun): bash scripts/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export B200_TMP=/tmp/b200_models
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/smi.csv 2>&1
+nproc > $OUT/nproc.txt; lscpu | head -20 >> $OUT/nproc.txt
+if [ -z "$SKIP_TESTS" ]; then
+  ( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1
+  tail -5 $OUT/pytest_gpu.log
+fi
+( time timeout 900 python bench.py ) > $OUT/bench.json 2> $OUT/bench.err
+cat $OUT/bench.json
+if [ -z "$SKIP_NCU" ]; then
+  # every launch of 3 un-graphed tokens with its device time (cold-cache, serialised: shares, not absolutes)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:k_matvec|k_attn|k_embed|k_argmax' -c 600 \
+      --csv --log-file $OUT/launches.csv python scripts/ncu_token.py 3 > $OUT/ncu_launches.log 2>&1
+  # layer 0 of token 2: QKV, scores(+softmax), P.V, wo, gate/up, down
+  timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_matvec|k_attn' -s 193 -c 6 \
+      -f -o $OUT/prof_layer python scripts/ncu_token.py 2 > $OUT/ncu_full.log 2>&1
+  tail -3 $OUT/ncu_full.log
+fi
+ls -la $OUT
