@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (A/B runs of the GPU path only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -278,6 +279,8 @@ def main():
         line["kernel_ms_per_token"] = {k: round(v[0] / reps, 4) for k, v in acc.items()}
         # ---- the reference's CPU llama_decode on this host, bounded sample
         try:
+            if args.no_cpu:
+                raise RuntimeError("skipped (--no-cpu)")
             cpu_tps, info = cpu_reference_run(path, steps=2, warmup=1)
             line["cpu_baseline"] = dict(info, value=cpu_tps, unit="tokens/s")
         except Exception as e:  # the oracle library failing to load must not hide the GPU number

@@ -436,6 +436,7 @@ struct b200_ctx {
     cudaGraphExec_t g_logits = nullptr;   // H2D state -> forward -> D2H logits
     cudaGraphExec_t g_greedy = nullptr;   // forward -> argmax -> advance
     cudaGraphExec_t g_pipe = nullptr;     // pipeline stage step (recv -> forward -> send)
+    int64_t n_logits = 0, n_greedy = 0;   // kernels per replay of g_logits / g_greedy
     int sm_count = 148;
     bool taps = false;
     TapStore tapstore;
@@ -464,6 +465,26 @@ struct ProfScope {
     explicit ProfScope(b200_ctx * c_);
     ~ProfScope();
 };
+
+// Every kernel of the forward pass goes through here: cudaLaunchKernelEx with the programmatic-stream-serialization
+// attribute (PDL), so that inside the captured graph consecutive kernels are joined by programmatic edges — the next
+// kernel's CTAs start (barrier init, weight prefetch) while the previous one drains, and block in griddepcontrol.wait
+// until its results are visible. BOOSTER_B200_NO_PDL=1 falls back to plain stream order (A/B measurements).
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char * e = getenv("BOOSTER_B200_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+template <typename Arg>
+static void launch_fwd(void (*kern)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg & arg, bool pdl = true) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, kern, arg));
+}
 
 template <int EPI>
 static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
@@ -505,12 +526,42 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
     if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }
     const int grid = std::max(1, std::min(a.n_units, c->sm_count));
-    k_matvec<EPI><<<grid, W * 32, smem, c->st>>>(a);
+    launch_fwd(k_matvec<EPI>, dim3((unsigned) grid), dim3((unsigned) (W * 32)), smem, c->st, a);
     c->launches++;
+}
+
+// one launch per layer: cluster of ATT_CL CTAs per KV head (k_attn_fused); returns false when the context is too long
+// for its shared-memory layout (the three-kernel route below then takes over)
+template <int GQA>
+static bool launch_attention_fused(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
+    AttnArgs a = a_in;
+    const int ngrp = n_ctx_pad / 32;
+    a.kc_max = (ngrp + ATT_CL - 1) / ATT_CL * 32;
+    const size_t sc_bytes = (size_t) GQA * a.kc_max * 4;
+    const size_t budget = 200 * 1024;
+    if (sc_bytes + (size_t) PV_BATCH * (GQA * 4 + 32) > budget) return false;
+    int pch = (int) ((budget - sc_bytes) / (GQA * 4 + 32)) / PV_BATCH * PV_BATCH;
+    pch = std::min(pch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
+    a.p_chunk = pch;
+    const size_t smem = sc_bytes + (size_t) pch * (GQA * 4 + 32);
+    static size_t attr[64] = {0};
+    const int dv = c->device & 63;
+    if (smem > attr[dv]) { CU(cudaFuncSetAttribute(k_attn_fused<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr[dv] = smem; }
+    g_kind = KIND_ATTN; ProfScope ps(c);
+    launch_fwd(k_attn_fused<GQA>, dim3((unsigned) ATT_CL, (unsigned) a.n_head_kv), dim3(ATT_THREADS), smem, c->st, a);
+    c->launches += 1;
+    return true;
+}
+
+static bool attn_fused_enabled() {
+    static int v = -1;
+    if (v < 0) { const char * e = getenv("BOOSTER_B200_ATTN_SPLIT"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
 }
 
 template <int GQA>
 static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
+    if (attn_fused_enabled() && launch_attention_fused<GQA>(c, a_in, n_ctx_pad)) return;
     AttnArgs a = a_in;
     // P.V chunk: p rows (GQA x 4 B) + V rows (32 B) per position, up to ~200 KB of shared memory
     int pch = (200 * 1024) / (GQA * 4 + 32) / PV_BATCH * PV_BATCH;
@@ -536,6 +587,7 @@ static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pa
         const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PV_DIMS));
         k_attn_pv<GQA><<<gp, PV_DIMS * 16, pv_smem, c->st>>>(a);
     }
+    c->launches += a.fuse_softmax ? 2 : 3;
 }
 static void launch_attention(b200_ctx * c, const AttnArgs & a, int n_ctx_pad) {
     if (a.head_dim != 128) throw std::runtime_error("attention kernels are specialised for head_dim 128");
@@ -546,7 +598,6 @@ static void launch_attention(b200_ctx * c, const AttnArgs & a, int n_ctx_pad) {
         case 8: launch_attention_t<8>(c, a, n_ctx_pad); break;
         default: throw std::runtime_error("GQA ratio must be 1, 2, 4 or 8");
     }
-    c->launches += 2;
 }
 
 ProfScope::ProfScope(b200_ctx * c_) : c(c_) {
@@ -651,21 +702,18 @@ static void enqueue_argmax(b200_ctx * c, int advance) {
     c->launches += 2;
 }
 
-static cudaGraphExec_t capture(b200_ctx * c, const std::function<void()> & body) {
+static cudaGraphExec_t capture(b200_ctx * c, const std::function<void()> & body, int64_t * n_kernels) {
     cudaGraph_t g;
     const int64_t l0 = c->launches;
     CU(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
     body();
     CU(cudaStreamEndCapture(c->st, &g));
-    c->launches = l0;   // capture is not execution
+    *n_kernels = c->launches - l0;   // kernels one replay of this graph launches
+    c->launches = l0;                // capture is not execution
     cudaGraphExec_t ge;
     CU(cudaGraphInstantiate(&ge, g, 0));
     CU(cudaGraphDestroy(g));
     return ge;
-}
-static int64_t forward_launch_count(const b200_ctx * c) {
-    const b200_model & m = *c->m;
-    return (m.has_embd() ? 1 : 0) + (int64_t) m.layers.size() * 6 + (m.has_head() ? 1 : 0);
 }
 
 extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
@@ -791,10 +839,10 @@ extern "C" int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0
                     CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
                     enqueue_forward(c);
                     CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t) m.n_vocab * 4, cudaMemcpyDeviceToHost, c->st));
-                });
+                }, &c->n_logits);
             }
             CU(cudaGraphLaunch(c->g_logits, c->st));
-            c->launches += forward_launch_count(c);
+            c->launches += c->n_logits;
             CU(cudaStreamSynchronize(c->st));   // h_state is reused for the next token
             if (last && logits_out) std::memcpy(logits_out, c->h_logits, (size_t) m.n_vocab * 4);
         }
@@ -823,13 +871,13 @@ extern "C" int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0,
             c->g_greedy = capture(c, [&]() {
                 enqueue_forward(c);
                 enqueue_argmax(c, 1);
-            });
+            }, &c->n_greedy);
         }
         if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
         CU(cudaEventRecord(c->ev_t0, c->st));
         for (int s = 0; s < n_steps; s++) CU(cudaGraphLaunch(c->g_greedy, c->st));
         CU(cudaEventRecord(c->ev_t1, c->st));
-        c->launches += (forward_launch_count(c) + 2) * (int64_t) n_steps;
+        c->launches += c->n_greedy * (int64_t) n_steps;
         if (out_tokens) CU(cudaMemcpyAsync(out_tokens, c->d_out_tokens, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
         CU(cudaEventElapsedTime(&c->last_device_ms, c->ev_t0, c->ev_t1));

@@ -108,7 +108,7 @@ class Context:
         cnt = np.zeros(8, dtype=np.int32)
         check(self.L.b200_profile_token(self.h, token, pos, ms.ctypes.data_as(C.POINTER(C.c_float)),
                                         cnt.ctypes.data_as(C.POINTER(C.c_int32))), "b200_profile_token")
-        kinds = ["embed", "qkv", "attn_scores_softmax", "wo", "gate_up", "down", "head", "attn_pv"]
+        kinds = ["embed", "qkv", "attention", "wo", "gate_up", "down", "head", "attn_pv_split_route"]
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(kinds)}
 
     def kernel_launches(self) -> int:
