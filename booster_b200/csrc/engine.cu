@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -446,6 +447,11 @@ struct b200_ctx {
     cudaEvent_t ev_done = nullptr;     // in-process stage chain hand-off
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // device time of the last generate/decode call
     float last_device_ms = 0.f;
+    // phase trace (b200_trace_token): [launch][TRACE_CTAS][TRACE_PHASES] globaltimer stamps
+    unsigned long long * d_trace = nullptr;
+    bool tracing = false;
+    int trace_seq = 0;
+    std::vector<std::array<int, 3>> trace_meta;   // per launch: (kind, ctas, 0)
     // per-launch profiling (bench.py's live roofline): event pairs around every launch of one token
     bool prof = false;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_ev;   // (kind, (start, stop))
@@ -484,6 +490,14 @@ static void launch_fwd(void (*kern)(Arg), dim3 grid, dim3 block, size_t smem, cu
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
     CU(cudaLaunchKernelEx(&cfg, kern, arg));
+}
+
+static constexpr int TRACE_CTAS = 512, TRACE_MAX_LAUNCHES = 1024;
+static unsigned long long * trace_slot(b200_ctx * c, int ctas) {
+    if (!c->tracing) return nullptr;
+    if (ctas > TRACE_CTAS || c->trace_seq >= TRACE_MAX_LAUNCHES) throw std::runtime_error("trace buffer too small");
+    c->trace_meta.push_back({g_kind, ctas, 0});
+    return c->d_trace + (size_t) (c->trace_seq++) * TRACE_CTAS * TRACE_PHASES;
 }
 
 template <int EPI>
@@ -526,34 +540,44 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
     if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }
     const int grid = std::max(1, std::min(a.n_units, c->sm_count));
+    a.trace = trace_slot(c, grid);
     launch_fwd(k_matvec<EPI>, dim3((unsigned) grid), dim3((unsigned) (W * 32)), smem, c->st, a);
     c->launches++;
 }
 
-// one launch per layer: cluster of ATT_CL CTAs per KV head (k_attn_fused); returns false when the context is too long
-// for its shared-memory layout (the three-kernel route below then takes over)
+// two launches per layer: raw scores (k_attn_scores, every SM busy) then softmax + P.V (k_attn_softmax_pv); returns
+// false when the GQA score rows of the context do not fit the shared memory (the three-kernel route below takes over)
 template <int GQA>
-static bool launch_attention_fused(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
+static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
     AttnArgs a = a_in;
-    const int ngrp = n_ctx_pad / 32;
-    a.kc_max = (ngrp + ATT_CL - 1) / ATT_CL * 32;
-    const size_t sc_bytes = (size_t) GQA * a.kc_max * 4;
+    const size_t row_bytes = (size_t) GQA * n_ctx_pad * 4;
     const size_t budget = 200 * 1024;
-    if (sc_bytes + (size_t) PV_BATCH * (GQA * 4 + 32) > budget) return false;
-    int pch = (int) ((budget - sc_bytes) / (GQA * 4 + 32)) / PV_BATCH * PV_BATCH;
-    pch = std::min(pch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
-    a.p_chunk = pch;
-    const size_t smem = sc_bytes + (size_t) pch * (GQA * 4 + 32);
+    if (row_bytes + (size_t) PV_BATCH * 16 > budget) return false;
+    int vch = (int) ((budget - row_bytes) / 16) / PV_BATCH * PV_BATCH;
+    vch = std::min(vch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
+    a.p_chunk = vch;
+    a.fuse_softmax = 0;
+    const size_t smem = row_bytes + (size_t) vch * 16;
     static size_t attr[64] = {0};
     const int dv = c->device & 63;
-    if (smem > attr[dv]) { CU(cudaFuncSetAttribute(k_attn_fused<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr[dv] = smem; }
-    g_kind = KIND_ATTN; ProfScope ps(c);
-    launch_fwd(k_attn_fused<GQA>, dim3((unsigned) ATT_CL, (unsigned) a.n_head_kv), dim3(ATT_THREADS), smem, c->st, a);
-    c->launches += 1;
+    if (smem > attr[dv]) { CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr[dv] = smem; }
+    {
+        g_kind = KIND_ATTN; ProfScope ps(c);
+        const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
+        a.trace = trace_slot(c, (int) (gs.x * gs.y));
+        launch_fwd(k_attn_scores<GQA>, gs, dim3(ATT_THREADS), 0, c->st, a);
+    }
+    {
+        g_kind = KIND_ATTN_PV; ProfScope ps(c);
+        const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVS_DIMS));
+        a.trace = trace_slot(c, (int) (gp.x * gp.y));
+        launch_fwd(k_attn_softmax_pv<GQA>, gp, dim3((unsigned) (GQA * 16 * PVS_DIMS)), smem, c->st, a);
+    }
+    c->launches += 2;
     return true;
 }
 
-static bool attn_fused_enabled() {
+static bool attn_2k_enabled() {
     static int v = -1;
     if (v < 0) { const char * e = getenv("BOOSTER_B200_ATTN_SPLIT"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
@@ -561,7 +585,7 @@ static bool attn_fused_enabled() {
 
 template <int GQA>
 static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
-    if (attn_fused_enabled() && launch_attention_fused<GQA>(c, a_in, n_ctx_pad)) return;
+    if (attn_2k_enabled() && launch_attention_2k<GQA>(c, a_in, n_ctx_pad)) return;
     AttnArgs a = a_in;
     // P.V chunk: p rows (GQA x 4 B) + V rows (32 B) per position, up to ~200 KB of shared memory
     int pch = (200 * 1024) / (GQA * 4 + 32) / PV_BATCH * PV_BATCH;
@@ -781,6 +805,7 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     for (auto p : c->kc) cudaFree(p);
     for (auto p : c->vc) cudaFree(p);
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->logits);
+    cudaFree(c->d_trace);
     cudaFree(c->S); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits);
     cudaStreamDestroy(c->st);
@@ -916,6 +941,44 @@ extern "C" int b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms
         c->prof_ev.clear();
         return 0;
     } catch (const std::exception & e) { c->prof = false; return set_err(e.what()); }
+}
+
+// One token through a freshly captured graph whose kernels stamp %globaltimer at their phase boundaries (thread 0 of
+// every CTA). out = [n_launches][TRACE_CTAS=512][8] u64 (0 = not stamped), meta = [n_launches][2] (kind, ctas).
+// Phases: k_matvec 0 start | 1 ring filled, before griddepcontrol.wait | 2 after it | 3 prologue done | 4 end;
+//         k_attn_scores 0 start | 1 after wait | 2 scores written;
+//         k_attn_softmax_pv 0 start | 1 after wait | 2 score rows staged | 3 normalised | 4 P.V done.
+extern "C" int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int reps, uint64_t * out, int64_t cap_words, int32_t * meta, int64_t cap_meta) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        b200_model & m = *c->m;
+        if (pos < 0 || pos >= c->n_ctx || token < 0 || token >= m.n_vocab) throw std::runtime_error("bad token/pos");
+        CU(cudaSetDevice(m.device));
+        const size_t words = (size_t) TRACE_MAX_LAUNCHES * TRACE_CTAS * TRACE_PHASES;
+        if (!c->d_trace) CU(cudaMalloc(&c->d_trace, words * 8));
+        DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = 0; hs.step = 0;
+        c->tracing = true; c->trace_seq = 0; c->trace_meta.clear();
+        int64_t nk = 0;
+        cudaGraphExec_t ge = nullptr;
+        try {
+            ge = capture(c, [&]() { enqueue_forward(c); enqueue_argmax(c, 0); }, &nk);
+        } catch (...) { c->tracing = false; throw; }
+        c->tracing = false;
+        for (int r = 0; r < std::max(1, reps); r++) {
+            k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
+            CU(cudaMemsetAsync(c->d_trace, 0, words * 8, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            CU(cudaGraphLaunch(ge, c->st));
+            CU(cudaStreamSynchronize(c->st));
+        }
+        cudaGraphExecDestroy(ge);
+        const int64_t nl = c->trace_seq;
+        const int64_t need = nl * TRACE_CTAS * TRACE_PHASES;
+        if (out && cap_words >= need) CU(cudaMemcpy(out, c->d_trace, (size_t) need * 8, cudaMemcpyDeviceToHost));
+        if (meta) for (int64_t i = 0; i < nl && 2 * i + 1 < cap_meta; i++) { meta[2 * i] = c->trace_meta[(size_t) i][0]; meta[2 * i + 1] = c->trace_meta[(size_t) i][1]; }
+        return nl;
+    } catch (const std::exception & e) { c->tracing = false; set_err(e.what()); return -1; }
 }
 
 // ------------------------------------------------------------------------------------------------------------

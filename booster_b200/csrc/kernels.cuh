@@ -29,7 +29,6 @@
 //   Q8_0 (1088 B): qs uint4[2][32] | d u16[32]                 (blocks of 32 weights)
 // ffn_gate and ffn_up are interleaved row by row into one virtual matrix (row 2r = gate r, 2r+1 = up r).
 #pragma once
-#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -85,6 +84,7 @@ struct MatvecArgs {
     int n_q, n_k, head_dim, kv_dim;
     const float2 * rope;       // [n_ctx][head_dim/2] (cos, sin)
     const DecodeState * st;
+    unsigned long long * trace; // nullptr unless b200_trace_token is running
 };
 
 static constexpr int MV_MAX_WARPS = 16;                     // one persistent CTA per SM, 8..16 warps (host picks)
@@ -97,6 +97,15 @@ static constexpr int HANDOFF_WORDS = 12 * 32;               // chain state of on
 // prefetch); pdl_wait() blocks until the PREVIOUS kernel has completed and its memory is visible. Rule kept by
 // every kernel: no global read of anything a kernel writes, and no global write at all, before pdl_wait().
 // ------------------------------------------------------------------------------------------------------------
+// optional phase trace (b200_trace_token): thread 0 of every CTA stamps %globaltimer into tr[cta][phase]
+static constexpr int TRACE_PHASES = 8;
+__device__ __forceinline__ void trace_mark(unsigned long long * tr, int phase) {
+    if (tr != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        tr[(size_t) (blockIdx.y * gridDim.x + blockIdx.x) * TRACE_PHASES + phase] = t;
+    }
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -540,6 +549,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
     const uint32_t edge_out = smem_u32(bars + W * S + grp * G + (w + 1 == G ? 0 : w + 1));
     const uint32_t ring_u32 = smem_u32(ring);
 
+    trace_mark(a.trace, 0);
     pdl_launch_dependents();                                   // the next kernel may start its own weight prefetch
     if (lane == 0) {
         for (int s = 0; s < S; s++) mbar_init(full0 + 8 * s, 1);
@@ -579,10 +589,13 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
     // weights do not depend on x: fill the ring before the prologue
     for (int s = 0; s < S - 1; s++) issue_next();
 
+    trace_mark(a.trace, 1);
     pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
+    trace_mark(a.trace, 2);
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
     prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem);
     __syncthreads();                                           // activations + every warp's barrier inits are visible
+    trace_mark(a.trace, 3);
 
     // ---- consumer side
     float acc[12];
@@ -677,6 +690,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
             }
         }
     }
+    if (a.trace != nullptr) { __syncthreads(); trace_mark(a.trace, 4); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -823,7 +837,7 @@ struct AttnArgs {
     unsigned int * tickets;   // [n_head_kv] zero-initialised, self-resetting (last scores CTA of a KV head runs the softmax)
     int p_chunk;              // positions of p staged in shared memory by k_attn_pv (multiple of PV_BATCH)
     int fuse_softmax;         // 1: the last scores CTA of a KV head normalises its rows; 0: k_attn_softmax follows
-    int kc_max;               // k_attn_fused: capacity (keys) of one CTA's shared-memory score rows
+    unsigned long long * trace;
 };
 __device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1; }
 
@@ -863,6 +877,10 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     __shared__ double redd[GQA][8];
     __shared__ unsigned int s_ticket;
     const int g = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
+    trace_mark(a.trace, 0);
+    pdl_wait();                                               // q and this token's K row come from the QKV kernel
+    pdl_launch_dependents();                                  // AFTER the wait: the next kernel may touch K/V/q before ITS wait
+    trace_mark(a.trace, 1);
     const int n_kv = attn_n_kv(a);
     const int n_pad = (n_kv + 31) / 32 * 32;
     if (tile * ATT_TILE >= n_pad) return;
@@ -934,6 +952,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
                 a.S[(size_t) (g * GQA + h) * a.s_stride + t] = t < n_kv ? __fmul_rn(res[h], a.scale) : -INFINITY;
         }
     }
+    trace_mark(a.trace, 2);
     // ---- the last CTA of this KV head (atomic ticket) normalises the GQA rows: no separate softmax launch
     if (!a.fuse_softmax) return;
     __threadfence();
@@ -1053,223 +1072,115 @@ __global__ void __launch_bounds__(PV_DIMS * 16) k_attn_pv(const AttnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_attn_fused: the whole default-route attention of one layer in ONE launch, same arithmetic (and the same device
-// code for the chains) as k_attn_scores / k_attn_softmax / k_attn_pv above. One thread-block CLUSTER of ATT_CL CTAs
-// per KV head (hardware co-scheduled, so the three cluster barriers cannot dead-lock):
-//   0. every CTA starts the cp.async stream of ITS 16-dim slice of V (first p_chunk positions) — V does not depend
-//      on the scores, so it lands while the scores are computed;
-//   1. scores: CTA r owns a contiguous range of 32-key groups; K.q chains exactly as k_attn_scores; rows stay in
-//      shared memory;
-//   2. softmax: per-CTA max -> cluster barrier -> max over the CTAs (read through distributed shared memory) ->
-//      p = ggml_v_expf(s - max), per-16 float sums accumulated in double -> cluster barrier -> total in CTA order ->
-//      p *= (float)(1/sum), written to S (global, L2-resident) -> cluster barrier;
-//   3. P.V: CTA r owns dims [16r, 16r+16) of the KV head for ALL positions (the 16 tinyBLAS chains run over t in
-//      order, so positions cannot be split); p rows come back from L2 with cp.async.
+// k_attn_softmax_pv: soft_max_ext + P.V of one layer in ONE launch, no inter-CTA communication. A CTA owns
+// (KV head g, a slice of PVS_DIMS output dims) and ALL positions (the 16 tinyBLAS chains of an output element run
+// over t in order, so positions cannot be split). Every CTA of a KV head normalises the GQA score rows itself — the
+// exp work is repeated HD/PVS_DIMS times across CTAs, which is far cheaper than a grid-wide exchange of max and sum —
+// with exactly k_attn_softmax's arithmetic, on a shared-memory copy; then thread (h, c, dl) runs chain c of output
+// dim dl of head h. The CTA's V slice is independent of the scores and is put in flight BEFORE griddepcontrol.wait
+// (k_attn_scores waits for the QKV kernel before it lets this kernel launch, so K/V/q are already visible).
+//   grid (n_head_kv, HD / PVS_DIMS), block GQA * 16 * PVS_DIMS threads; shared: ps [GQA][n_pad] f32 | vs [v_chunk][8] f16
 // ------------------------------------------------------------------------------------------------------------
-static constexpr int ATT_CL = 8;             // CTAs per cluster (portable maximum); ATT_CL * PV_DIMS == head_dim
+static constexpr int PVS_DIMS = 8;            // dims per CTA: 8 halfs = one 16-byte cp.async per position
 
 template <int GQA>
-__global__ void __cluster_dims__(ATT_CL, 1, 1) __launch_bounds__(ATT_THREADS) k_attn_fused(const AttnArgs a) {
-    namespace cg = cooperative_groups;
+__global__ void __launch_bounds__(GQA * 16 * PVS_DIMS) k_attn_softmax_pv(const AttnArgs a) {
     constexpr int HD = 128;
-    constexpr int NT = ATT_THREADS;
-    constexpr int NW = 8 / GQA;                               // warps per head in the softmax (8 warps)
-    static_assert(ATT_CL * PV_DIMS == HD, "dim slices of the cluster must tile the head");
-    extern __shared__ __align__(16) uint8_t fz_dyn[];         // sc [GQA][kc_max] f32 | ps [GQA][p_chunk] f32 | vs [p_chunk][16] f16
-    __shared__ __align__(16) float qs[GQA][HD];
-    __shared__ float redf[GQA][8];
-    __shared__ double redd[GQA][8];
-    __shared__ float  cmax[GQA];                              // this CTA's row maxima (read by the peers)
-    __shared__ double csum[GQA];                              // this CTA's row sums   (read by the peers)
-    __shared__ float red[GQA][16][PV_DIMS + 1];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int r = (int) cluster.block_rank();
-    const int g = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int PCH = a.p_chunk, KC = a.kc_max;
-    float * sc = reinterpret_cast<float *>(fz_dyn);
-    float * ps = sc + (size_t) GQA * KC;
-    __half (*vs)[PV_DIMS] = reinterpret_cast<__half (*)[PV_DIMS]>(ps + (size_t) GQA * PCH);
+    constexpr int TH = 16 * PVS_DIMS;                          // threads per head (128 = 4 warps)
+    constexpr int NT = GQA * TH;
+    constexpr int NW = TH / 32;                                // warps per head
+    extern __shared__ __align__(16) uint8_t sp_dyn[];
+    __shared__ float  redf[GQA][NW];
+    __shared__ double redd[GQA][NW];
+    __shared__ float  red[GQA][16][PVS_DIMS + 1];
+    const int g = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int h = tid / TH, ht = tid % TH;                     // head of the group, thread within the head
+    const int c = ht / PVS_DIMS, dl = ht % PVS_DIMS;           // chain, dim
+    const int w = ht >> 5;                                     // warp within the head
 
+    trace_mark(a.trace, 0);
     pdl_launch_dependents();
-    pdl_wait();                                               // q, K, V of this token are written by the QKV kernel
-
-    const int n_kv = attn_n_kv(a);
+    const int n_kv = attn_n_kv(a);                             // DecodeState is written by the previous TOKEN's last kernel
     const int n_pad = (n_kv + 31) / 32 * 32;
-    const int ngrp = n_pad / 32;
-    const int t_begin = 32 * (int) (((long long) r * ngrp) / ATT_CL), t_end = 32 * (int) (((long long) (r + 1) * ngrp) / ATT_CL);
-    const int nloc = t_end - t_begin;                         // multiple of 32, <= kc_max
-    const int round_q = a.st ? a.st->round_q : a.round_q_override;
-    const __half * vbase = a.v_cache + g * HD + r * PV_DIMS;
-
-    // ---- 0. V slice of the first chunk in flight (rows at or beyond n_kv are never read: p == 0 there)
-    {
-        const int rows = min(PCH, n_kv);
-        for (int i = tid; i < rows * 2; i += NT)
-            cp_async16(&vs[i >> 1][(i & 1) * 8], vbase + (size_t) (i >> 1) * a.kv_dim + (i & 1) * 8);
+    const int VCH = a.p_chunk;                                 // positions of V staged at a time
+    float * ps = reinterpret_cast<float *>(sp_dyn);            // [GQA][n_pad]
+    __half (*vs)[PVS_DIMS] = reinterpret_cast<__half (*)[PVS_DIMS]>(sp_dyn + (size_t) GQA * n_pad * 4);
+    const __half * vbase = a.v_cache + g * HD + slice * PVS_DIMS;
+    {   // V rows of the first chunk (rows at or beyond n_kv are never read: p == 0 there)
+        const int rows = min(VCH, n_kv);
+        for (int i = tid; i < rows; i += NT) cp_async16(&vs[i][0], vbase + (size_t) i * a.kv_dim);
         cp_async_commit();
     }
-    for (int i = tid; i < GQA * HD; i += NT) {
-        float v = a.q[(size_t) (g * GQA) * HD + i];
-        if (round_q) v = __half2float(__float2half_rn(v));    // src1 converted to the vec_dot_type F16 (ggml.c:12345-12371)
-        (&qs[0][0])[i] = v;
-    }
-    __syncthreads();
-
-    // ---- 1. scores of keys [t_begin, t_end): 4 lanes per key, two 64-key passes of K loads in flight at a time
-    const int c4 = tid & 3;
-    for (int base = t_begin; base < t_end; base += 2 * ATT_TILE) {
-        uint2 kv[2][8];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int t = base + u * ATT_TILE + (tid >> 2);
-#pragma unroll
-            for (int s = 0; s < 8; s++) kv[u][s] = make_uint2(0u, 0u);
-            if (t < n_kv && t < t_end) {
-                const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
-#pragma unroll
-                for (int s = 0; s < 8; s++) kv[u][s] = __ldg(kr + s * 4);     // 4 halfs at element 16s + 4c4
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int t = base + u * ATT_TILE + (tid >> 2);
-            if (t >= t_end) continue;                         // t_end % 32 == 0: whole warps skip together
-            float kf[8][4];
-#pragma unroll
-            for (int s = 0; s < 8; s++) {
-                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[u][s].x));
-                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[u][s].y));
-                kf[s][0] = f0.x; kf[s][1] = f0.y; kf[s][2] = f1.x; kf[s][3] = f1.y;
-            }
-#pragma unroll
-            for (int h = 0; h < GQA; h++) {
-                float ch[4];
-                if (!round_q) {
-                    // tinyBLAS<16>: lane c: acc = fma(k[16s+c], q[16s+c], acc), s = 0..7
-#pragma unroll
-                    for (int e = 0; e < 4; e++) ch[e] = 0.f;
-#pragma unroll
-                    for (int s = 0; s < 8; s++) {
-                        const float4 qv = *reinterpret_cast<const float4 *>(&qs[h][16 * s + 4 * c4]);
-                        ch[0] = __fmaf_rn(kf[s][0], qv.x, ch[0]); ch[1] = __fmaf_rn(kf[s][1], qv.y, ch[1]);
-                        ch[2] = __fmaf_rn(kf[s][2], qv.z, ch[2]); ch[3] = __fmaf_rn(kf[s][3], qv.w, ch[3]);
-                    }
-                } else {
-                    // ggml_vec_dot_f16: sum[j][c] over i in {0, 64}: element i + 16j + c; then (0+2)+(1+3)
-                    float aj[4][4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float4 q0 = *reinterpret_cast<const float4 *>(&qs[h][16 * j + 4 * c4]);
-                        const float4 q1 = *reinterpret_cast<const float4 *>(&qs[h][64 + 16 * j + 4 * c4]);
-                        aj[j][0] = __fmaf_rn(kf[4 + j][0], q1.x, __fmul_rn(kf[j][0], q0.x));
-                        aj[j][1] = __fmaf_rn(kf[4 + j][1], q1.y, __fmul_rn(kf[j][1], q0.y));
-                        aj[j][2] = __fmaf_rn(kf[4 + j][2], q1.z, __fmul_rn(kf[j][2], q0.z));
-                        aj[j][3] = __fmaf_rn(kf[4 + j][3], q1.w, __fmul_rn(kf[j][3], q0.w));
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; e++) ch[e] = __fadd_rn(__fadd_rn(aj[0][e], aj[2][e]), __fadd_rn(aj[1][e], aj[3][e]));
-                }
-                // _mm512_reduce_add_ps over the 16 chains: lanes c4=0..3 hold chains 4c4..4c4+3
-                float t3[4], t6[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) t3[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, ch[e], 2), ch[e]);
-#pragma unroll
-                for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);
-                const float res = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
-                if (c4 == 0) sc[(size_t) h * KC + (t - t_begin)] = t < n_kv ? __fmul_rn(res, a.scale) : -INFINITY;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- 2. softmax over the cluster: warp -> (head hl, part w of NW)
-    const int hl = warp / NW, w = warp % NW;
-    float * row = sc + (size_t) hl * KC;
+    pdl_wait();                                               // the raw scores are complete
+    trace_mark(a.trace, 1);
+    float * row = ps + (size_t) h * n_pad;
     {
-        float mx = -INFINITY;
-        for (int i = w * 32 + lane; i < nloc; i += NW * 32) mx = fmaxf(mx, row[i]);
-        mx = warp_max(mx);
-        if (lane == 0) redf[hl][w] = mx;
+        const float * Sg = a.S + (size_t) (g * GQA + h) * a.s_stride;
+        for (int i = ht; i < n_pad / 4; i += TH) cp_async16(row + 4 * i, Sg + 4 * i);
+        cp_async_commit();
+        cp_async_wait<0>();                                    // (also completes this thread's V copies)
     }
-    __syncthreads();
-    if (tid < GQA) {
-        float m = redf[tid][0];
-        for (int j = 1; j < NW; j++) m = fmaxf(m, redf[tid][j]);
-        cmax[tid] = m;
-    }
-    cluster.sync();                                           // every CTA's cmax is published
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");   // the head's row is in shared memory
+    trace_mark(a.trace, 2);
+    // soft_max_ext of the head's row by its NW warps: see k_attn_softmax for the summation-order argument
     float mx = -INFINITY;
+    for (int i = ht; i < n_pad; i += TH) mx = fmaxf(mx, row[i]);
+    mx = warp_max(mx);
+    if (lane == 0) redf[h][w] = mx;
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");
+    mx = redf[h][0];
 #pragma unroll
-    for (int rr = 0; rr < ATT_CL; rr++) mx = fmaxf(mx, cluster.map_shared_rank(&cmax[0], rr)[hl]);
-    {
-        double part = 0.0;
-        for (int i = w * 32 + lane; i < nloc; i += NW * 32) {
-            const float p = v_expf(__fsub_rn(row[i], mx));
-            row[i] = p;
-            const float gs = reduce_add16_shfl(p);            // 16 consecutive, 16-aligned elements of the row
-            if ((lane & 15) == 0) part += (double) gs;
-        }
-        part = warp_sum_d(part);
-        if (lane == 0) redd[hl][w] = part;
+    for (int j = 1; j < NW; j++) mx = fmaxf(mx, redf[h][j]);
+    double part = 0.0;
+    for (int i = ht; i < n_pad; i += TH) {                     // n_pad % 32 == 0 and TH % 32 == 0: whole warps in or out
+        const float p = v_expf(__fsub_rn(row[i], mx));
+        row[i] = p;
+        const float gs = reduce_add16_shfl(p);                 // 16 consecutive, 16-aligned elements
+        if ((lane & 15) == 0) part += (double) gs;
     }
-    __syncthreads();
-    if (tid < GQA) {
-        double s = 0.0;
-        for (int j = 0; j < NW; j++) s += redd[tid][j];
-        csum[tid] = s;
-    }
-    cluster.sync();                                           // every CTA's csum is published
-    {
-        double sum = 0.0;
+    part = warp_sum_d(part);
+    if (lane == 0) redd[h][w] = part;
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");
+    double sum = 0.0;
 #pragma unroll
-        for (int rr = 0; rr < ATT_CL; rr++) sum += cluster.map_shared_rank(&csum[0], rr)[hl];
-        const float inv = (float) (1.0 / sum);
-        float * Sg = a.S + (size_t) (g * GQA + hl) * a.s_stride + t_begin;
-        for (int i = w * 32 + lane; i < nloc; i += NW * 32) Sg[i] = __fmul_rn(row[i], inv);
-    }
-    cluster.sync();                                           // all probabilities of this KV head are in S (release/acquire
-                                                              // at cluster scope); nobody reads remote shared memory after this
+    for (int j = 0; j < NW; j++) sum += redd[h][j];
+    const float inv = (float) (1.0 / sum);
+    for (int i = ht; i < n_pad; i += TH) row[i] = __fmul_rn(row[i], inv);   // own elements only
+    __syncthreads();                                           // all rows normalised, every thread's V copies landed
+    trace_mark(a.trace, 3);
 
-    // ---- 3. P.V for dims [16r, 16r+16): thread = (chain c, dim dl)
-    const int c = tid / PV_DIMS, dl = tid % PV_DIMS;
-    float acc[GQA];
-#pragma unroll
-    for (int h = 0; h < GQA; h++) acc[h] = 0.f;
-    for (int t0 = 0; t0 < n_pad; t0 += PCH) {
-        const int len = min(PCH, n_pad - t0), rows = min(len, n_kv - t0);
+    // P.V: chain c of (head h, dim dl): acc = fma(V[t][dl], p[t], acc) over t = c, c+16, ...
+    float acc = 0.f;
+    for (int t0 = 0; t0 < n_pad; t0 += VCH) {
+        const int len = min(VCH, n_pad - t0), rows = min(len, n_kv - t0);
         if (t0) {
             __syncthreads();
-            for (int i = tid; i < rows * 2; i += NT)
-                cp_async16(&vs[i >> 1][(i & 1) * 8], vbase + (size_t) (t0 + (i >> 1)) * a.kv_dim + (i & 1) * 8);
+            for (int i = tid; i < rows; i += NT) cp_async16(&vs[i][0], vbase + (size_t) (t0 + i) * a.kv_dim);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
         }
-        for (int i = tid; i < GQA * (len / 4); i += NT) {
-            const int h = i / (len / 4), j = i - h * (len / 4);
-            cp_async16(ps + (size_t) h * PCH + 4 * j, a.S + (size_t) (g * GQA + h) * a.s_stride + t0 + 4 * j);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
         const int steps = len / 16;
+        const float * pr = row + t0;
 #pragma unroll 8
         for (int s = 0; s < steps; s++) {
             const int tt = 16 * s + c;
             // slots at or beyond n_kv have p == 0 exactly; their V bytes were not loaded and must not be multiplied
             const float v = t0 + tt < n_kv ? __half2float(vs[tt][dl]) : 0.f;
-#pragma unroll
-            for (int h = 0; h < GQA; h++) acc[h] = __fmaf_rn(v, ps[(size_t) h * PCH + tt], acc[h]);
+            acc = __fmaf_rn(v, pr[tt], acc);
         }
     }
-#pragma unroll
-    for (int h = 0; h < GQA; h++) red[h][c][dl] = acc[h];
+    red[h][c][dl] = acc;
     __syncthreads();
-    for (int i = tid; i < GQA * PV_DIMS; i += NT) {
-        const int h = i / PV_DIMS, dd = i % PV_DIMS;
+    trace_mark(a.trace, 4);
+    if (tid < GQA * PVS_DIMS) {
+        const int hh = tid / PVS_DIMS, dd = tid % PVS_DIMS;
         float t3[8], t6[4];                                   // _mm512_reduce_add_ps over the 16 chains
 #pragma unroll
-        for (int j = 0; j < 8; j++) t3[j] = __fadd_rn(red[h][8 + j][dd], red[h][j][dd]);
+        for (int j = 0; j < 8; j++) t3[j] = __fadd_rn(red[hh][8 + j][dd], red[hh][j][dd]);
 #pragma unroll
         for (int j = 0; j < 4; j++) t6[j] = __fadd_rn(t3[4 + j], t3[j]);
-        a.out[(size_t) (g * GQA + h) * HD + r * PV_DIMS + dd] =
+        a.out[(size_t) (g * GQA + hh) * HD + slice * PVS_DIMS + dd] =
             __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));     // kqv_merged_cont layout: [n_head*hd]
     }
 }

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import B200Error, check
+from ._lib import B200Error, check, last_error
 
 INFO = ["n_vocab", "n_embd", "n_layer", "n_head", "n_head_kv", "n_ff", "head_dim", "n_ctx_train",
         "layer_begin", "layer_end", "ftype"]
@@ -110,6 +110,17 @@ class Context:
                                         cnt.ctypes.data_as(C.POINTER(C.c_int32))), "b200_profile_token")
         kinds = ["embed", "qkv", "attention", "wo", "gate_up", "down", "head", "attn_pv_split_route"]
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(kinds)}
+
+    def trace_token(self, token: int, pos: int, reps: int = 3):
+        """(stamps[n_launches, 512, 8] u64 ns, meta[n_launches, 2] = (kind, ctas)) of one graph-replayed token"""
+        cap_l = 1024
+        out = np.zeros((cap_l, 512, 8), dtype=np.uint64)
+        meta = np.zeros((cap_l, 2), dtype=np.int32)
+        n = int(self.L.b200_trace_token(self.h, token, pos, reps, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size,
+                                        meta.ctypes.data_as(C.POINTER(C.c_int32)), meta.size))
+        if n < 0:
+            raise B200Error(f"b200_trace_token: {last_error()}")
+        return out[:n], meta[:n]
 
     def kernel_launches(self) -> int:
         return int(self.L.b200_kernel_launches(self.h))

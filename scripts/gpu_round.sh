@@ -13,6 +13,9 @@ if [ -z "$SKIP_TESTS" ]; then
 fi
 ( time timeout 900 python bench.py ) > $OUT/bench.json 2> $OUT/bench.err
 cat $OUT/bench.json
+if [ -z "$SKIP_TRACE" ]; then
+  timeout 300 python scripts/trace_token.py 2000 $OUT/trace_token.txt > $OUT/trace_head.txt 2>&1; head -12 $OUT/trace_head.txt
+fi
 if [ -n "$AB" ]; then
   BOOSTER_B200_NO_PDL=1 timeout 900 python bench.py --no-cpu > $OUT/bench_nopdl.json 2>> $OUT/bench.err; cat $OUT/bench_nopdl.json
   BOOSTER_B200_ATTN_SPLIT=1 timeout 900 python bench.py --no-cpu > $OUT/bench_attnsplit.json 2>> $OUT/bench.err; cat $OUT/bench_attnsplit.json
@@ -21,8 +24,8 @@ if [ -z "$SKIP_NCU" ]; then
   # every launch of 3 un-graphed tokens with its device time (cold-cache, serialised: shares, not absolutes)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:k_matvec|k_attn|k_embed|k_argmax' -c 600 \
       --csv --log-file $OUT/launches.csv python scripts/ncu_token.py 3 > $OUT/ncu_launches.log 2>&1
-  # layer 0 of token 2: QKV, fused attention, wo, gate/up, down
-  timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_matvec|k_attn' -s 161 -c 5 \
+  # layer 0 of token 2: QKV, scores, softmax+P.V, wo, gate/up, down
+  timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_matvec|k_attn' -s 193 -c 6 \
       -f -o $OUT/prof_layer python scripts/ncu_token.py 2 > $OUT/ncu_full.log 2>&1
   tail -3 $OUT/ncu_full.log
 fi

@@ -1,8 +1,8 @@
 """Target for ncu: load the synthetic 8B Q4_K_M model and run a few UN-GRAPHED decode tokens at n_kv ~ 2000
 (stage API: plain kernel launches, no CUDA graph), so that `ncu -k regex:... -s ... -c ...` can pick launches.
-Launch order per token: [k_embed] + 32 x [k_matvec<QKV>, k_attn_fused, k_matvec<RESID> (wo),
+Launch order per token: [k_embed] + 32 x [k_matvec<QKV>, k_attn_scores, k_attn_softmax_pv, k_matvec<RESID> (wo),
 k_matvec<SILU> (gate/up), k_matvec<RESID> (down)] + k_matvec<STORE> (head) + k_argmax_partial + k_argmax_finish
-= 164 kernels, 129 of them k_matvec."""
+= 196 kernels, 129 of them k_matvec."""
 import ctypes as C
 import os
 import sys
