@@ -74,19 +74,19 @@ __global__ void k_retile(int type, const uint8_t * __restrict__ src, int64_t n_r
     if (type == T_Q4_K) {
         const uint8_t * b = src + i * 144;   // {half d, half dmin, u8 scales[12], u8 qs[128]}  ggml-common.h:267-277
         for (int c = 0; c < 8; c++) copy16(p0 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
-        for (int w = 0; w < 3; w++) for (int j = 0; j < 4; j++) p1[((size_t) w * 32 + lane) * 4 + j] = b[4 + 4 * w + j];
-        for (int j = 0; j < 4; j++) p1[((size_t) 3 * 32 + lane) * 4 + j] = b[j];
+        for (int j = 0; j < 12; j++) p1[(size_t) lane * 16 + j] = b[4 + j];        // sd: scales[12] | d | dmin
+        for (int j = 0; j < 4; j++) p1[(size_t) lane * 16 + 12 + j] = b[j];
     } else if (type == T_Q5_K) {
         const uint8_t * b = src + i * 176;   // {half d, half dmin, u8 scales[12], u8 qh[32], u8 qs[128]}  :284-295
         for (int c = 0; c < 8; c++) copy16(p0 + ((size_t) c * 32 + lane) * 16, b + 48 + 16 * c);
         for (int c = 0; c < 2; c++) copy16(p2 + ((size_t) c * 32 + lane) * 16, b + 16 + 16 * c);
-        for (int w = 0; w < 3; w++) for (int j = 0; j < 4; j++) p1[((size_t) w * 32 + lane) * 4 + j] = b[4 + 4 * w + j];
-        for (int j = 0; j < 4; j++) p1[((size_t) 3 * 32 + lane) * 4 + j] = b[j];
+        for (int j = 0; j < 12; j++) p1[(size_t) lane * 16 + j] = b[4 + j];
+        for (int j = 0; j < 4; j++) p1[(size_t) lane * 16 + 12 + j] = b[j];
     } else if (type == T_Q6_K) {
         const uint8_t * b = src + i * 210;   // {u8 ql[128], u8 qh[64], i8 scales[16], half d}  :302-307
         for (int c = 0; c < 8; c++) copy16(p0 + ((size_t) c * 32 + lane) * 16, b + 16 * c);
         for (int c = 0; c < 4; c++) copy16(p2 + ((size_t) c * 32 + lane) * 16, b + 128 + 16 * c);
-        for (int w = 0; w < 4; w++) for (int j = 0; j < 4; j++) p1[((size_t) w * 32 + lane) * 4 + j] = b[192 + 4 * w + j];
+        for (int j = 0; j < 16; j++) p1[(size_t) lane * 16 + j] = b[192 + j];
         p3[lane * 2] = b[208]; p3[lane * 2 + 1] = b[209];
     } else {                                 // T_Q8_0: {half d, i8 qs[32]}  :186-190
         const uint8_t * b = src + i * 34;
@@ -129,7 +129,7 @@ static DevMat upload_tiled(const HostTensor * src, int n_src, cudaStream_t st) {
     const int64_t vrows = rows1 * n_src;
     if (vrows % 32 != 0) throw std::runtime_error("row count " + std::to_string(vrows) + " is not a multiple of the work-unit height 32");
     d.m.type = type; d.m.n_rows = (int) vrows; d.m.nb = nb; d.m.rows_unit = 32;
-    d.m.tiles_unit = nb; d.m.n_units = (int) (vrows / 32);
+    d.m.tiles_unit = nb; d.m.n_units = (int) (vrows / 32); d.m.tile_bytes = tile_bytes_of(type);
     const size_t n_tiles = (size_t) vrows * nb / 32;
     const size_t raw1 = (size_t) blk_bytes * nb * rows1;
     d.bytes = raw1 * n_src;
@@ -520,7 +520,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
         for (int G = W; G >= 1; G--) {
             if (W % G) continue;
             if (G > 1 && (long long) a.n_units * G > (long long) c->sm_count * W) continue;   // sharing only within one wave
-            if (G > a.tiles_unit && G > 1) continue;
+            if (a.tiles_unit % G) continue;                                                   // warp w owns tiles w, w+G, ... of every unit
             const size_t fixed = act_bytes + (G > 1 ? (size_t) (W / G) * HANDOFF_WORDS * 4 : 0) + (size_t) W * 4 * 8 + (size_t) W * 8;
             if (fixed + (size_t) W * 2 * a.stage_bytes > budget) continue;
             const int S = (int) std::min<size_t>(4, (budget - fixed) / ((size_t) W * a.stage_bytes));
@@ -533,6 +533,9 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     }
     if (bestW == 0) throw std::runtime_error("activation vector too long for the shared-memory budget");
     a.group = bestG; a.stages = bestS;
+    static int prefill_env = -1;
+    if (prefill_env < 0) { const char * e = getenv("BOOSTER_B200_PREFILL"); prefill_env = e ? atoi(e) : 1; }
+    a.prefill = prefill_env;
     const int W = bestW;
     const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + (a.group > 1 ? (size_t) (W / a.group) * HANDOFF_WORDS * 4 : 0)
                       + (size_t) W * a.stages * 8 + (size_t) W * 8;
@@ -571,7 +574,7 @@ static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_p
         g_kind = KIND_ATTN_PV; ProfScope ps(c);
         const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVS_DIMS));
         a.trace = trace_slot(c, (int) (gp.x * gp.y));
-        launch_fwd(k_attn_softmax_pv<GQA>, gp, dim3((unsigned) (GQA * 16 * PVS_DIMS)), smem, c->st, a);
+        launch_fwd(k_attn_softmax_pv<GQA>, gp, dim3((unsigned) (GQA * PVS_TH)), smem, c->st, a);
     }
     c->launches += 2;
     return true;

@@ -44,6 +44,7 @@ struct TMat {
     int rows_unit = 32;   // a work unit = 32 rows (one per lane) x all nb blocks
     int tiles_unit = 0;   // = nb
     int n_units = 0;      // = n_rows/32
+    int tile_bytes = 0;   // = tile_bytes_of(type)
     const uint8_t * p0 = nullptr;   // tiles, tile_bytes_of(type) each
 };
 __host__ __device__ __forceinline__ int tile_bytes_of(int type) {
@@ -74,6 +75,7 @@ struct MatvecArgs {
     int group;                 // G = warps sharing one 32-row unit (a divisor of the CTA's warp count)
     int stages;                // tiles of shared-memory ring per warp (>= 2)
     int stage_bytes;           // ring slot size = largest tile of the launch, 128-byte multiple
+    int prefill;               // tiles per warp requested before griddepcontrol.wait (the rest follow the x loads)
     // epilogue
     float * out;
     const float * resid;
@@ -147,7 +149,20 @@ __device__ __forceinline__ float v_expf(float x) {
                                          __fmaf_rn(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)),
                               u, __fmaf_rn(0x1.ffffecp-1f, b, 1.0f));
     if (big) return n <= 0.f ? 0.f : INFINITY;
-    return ldexpf(j, (int) n);                                          // _mm512_scalef_ps: exact scaling by 2^n
+    // _mm512_scalef_ps: exact scaling by 2^n. j is in [0.70, 1.42], so for |n| <= 125 the result is a normal number
+    // and the scaling is an addition to the exponent field; the (very rare) sub-normal range goes through ldexpf.
+    const int ni = (int) n;
+    if (ni >= -125 && ni <= 125) return __int_as_float(__float_as_int(j) + (ni << 23));
+    return ldexpf(j, ni);
+}
+// _mm512_reduce_add_ps of 16 values held by one thread (same tree as reduce_add16_shfl)
+__device__ __forceinline__ float reduce_add16_regs(const float (&a)[16]) {
+    float t[8], u[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = __fadd_rn(a[8 + i], a[i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[i] = __fadd_rn(t[4 + i], t[i]);
+    return __fadd_rn(__fadd_rn(u[0], u[2]), __fadd_rn(u[1], u[3]));
 }
 // ggml_v_silu (cpp/ggml/src/ggml.c:2475-2482)
 __device__ __forceinline__ float silu_exact(float x) {
@@ -166,19 +181,21 @@ __device__ __forceinline__ float reduce_add16_shfl(float v) {
 // ------------------------------------------------------------------------------------------------------------
 // activation quantization (block-cooperative, result in shared memory in natural order: all lanes of a warp work
 // on the same block b of their own rows, so every activation read is a warp-wide broadcast)
-//   Q8_K: q[k] int8 | dx[nb] f32 | bp[nb][8] int = sums of the 8 sub-blocks of 32
+//   Q8_K: q[k] int8 | dx[nb] f32 | bp[nb][8] int = sums of the 8 sub-blocks of 32 | as[nb][64] int = -32 * (sum of
+//         the 4 quants of each 32-bit word): the "- 32" of Q6_K folded into the accumulator input of dp4a
 //   Q8_0: q[k] int8 | dx[k/32] f32 (already rounded through fp16)
 // ------------------------------------------------------------------------------------------------------------
 struct ActSmem {
     int8_t * q;
     float  * dx;
     int    * bp;
+    int    * as;
 };
 __host__ __device__ __forceinline__ size_t act_smem_bytes(int k, int act_q8_0) {
     size_t n = (size_t) k;
     n += (size_t) (act_q8_0 ? k / 32 : k / 256) * 4;
     n = (n + 15) / 16 * 16;
-    if (!act_q8_0) n += (size_t) (k / 256) * 32;
+    if (!act_q8_0) n += (size_t) (k / 256) * 32 + (size_t) k;
     return (n + 15) / 16 * 16;
 }
 __device__ __forceinline__ ActSmem act_smem_carve(uint8_t * base, int k, int act_q8_0) {
@@ -188,6 +205,7 @@ __device__ __forceinline__ ActSmem act_smem_carve(uint8_t * base, int k, int act
     size_t off = (size_t) k + (size_t) (act_q8_0 ? k / 32 : k / 256) * 4;
     off = (off + 15) / 16 * 16;
     a.bp = (int *) (base + off);
+    a.as = (int *) (base + off + (size_t) (k / 256) * 32);
     return a;
 }
 
@@ -210,7 +228,6 @@ __device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, in
         if (oa > amax || (oa == amax && oi < midx)) { amax = oa; mval = ov; midx = oi; }
     }
     uint32_t w0 = 0, w1 = 0;
-    int s8 = 0;
     float d = 0.f;
     if (amax != 0.f) {
         const float iscale = __fdiv_rn(-127.f, mval);
@@ -218,14 +235,16 @@ __device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, in
         for (int i = 0; i < 8; i++) {
             int qi = __float2int_rn(__fmul_rn(iscale, v[i]));
             qi = min(127, qi);
-            s8 += qi;
             if (i < 4) w0 |= ((uint32_t) (qi & 0xff)) << (8 * i);
             else       w1 |= ((uint32_t) (qi & 0xff)) << (8 * (i - 4));
         }
         d = __fdiv_rn(1.f, iscale);
     }
     *reinterpret_cast<uint2 *>(A.q + (size_t) b * 256 + lane * 8) = make_uint2(w0, w1);
-    int s32 = s8 + __shfl_xor_sync(0xffffffffu, s8, 1);
+    const int a0 = __dp4a((int) w0, 0x01010101, 0), a1 = __dp4a((int) w1, 0x01010101, 0);   // word sums
+    *reinterpret_cast<int2 *>(A.as + (size_t) b * 64 + lane * 2) = make_int2(-32 * a0, -32 * a1);
+    int s32 = a0 + a1;
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 1);
     s32 += __shfl_xor_sync(0xffffffffu, s32, 2);                 // sum of sub-block lane/4 (32 values)
     if ((lane & 3) == 0) A.bp[(size_t) b * 8 + (lane >> 2)] = s32;
     if (lane == 0) A.dx[b] = d;
@@ -251,28 +270,44 @@ __device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, i
     if ((lane & 3) == 0) A.dx[b256 * 8 + (lane >> 2)] = __half2float(__float2half_rn(d));
 }
 
+__device__ __forceinline__ void load8(const float * p, float (&v)[8]) {
+    const float4 a0 = *reinterpret_cast<const float4 *>(p), a1 = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+}
+__device__ __forceinline__ void ldg8(const float * p, float (&v)[8]) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(p)), a1 = __ldg(reinterpret_cast<const float4 *>(p + 4));
+    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+}
+
 // Block-cooperative prologue: optional RMSNorm(+weight) then activation quantization into shared memory.
 // RMSNorm = ggml_compute_forward_rms_norm_f32 (double sum of float x*x, scale = 1/sqrtf(mean+eps), y = x*scale)
 // followed by the separate ggml_mul with the norm weight (cpp/src/llama.cpp:7928-7958).
+// Warp w owns blocks w, w+W, ... ; PRO_U of them are handled per pass with all their loads issued up front.
+// `pre_w` (fast norm path): the caller already fetched the warp's norm weights (constants: before griddepcontrol.wait).
+// `after_loads` runs once, right after the first pass' x loads are in flight (the caller tops up its weight ring
+// there: the x loads must not queue behind those bulk copies).
+static constexpr int PRO_U = 4;
+template <typename F>
 __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, const float * __restrict__ norm_w,
-                                                  float eps, int k, int act_q8_0, const ActSmem & A, double * red) {
+                                                  float eps, int k, int act_q8_0, const ActSmem & A, double * red,
+                                                  const float (&pre_w)[2][8], bool fast_norm, F after_loads) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
-    if (norm_w != nullptr && k / 256 <= 2 * nwarp) {
-        // single pass: a warp keeps its (at most two) blocks of x and of the norm weight in registers, so x is read
-        // once and only one load latency sits in front of the mat-vec
-        float v[2][8], ww[2][8];
+    const int n256 = k / 256;
+    if (fast_norm) {
+        // single pass (n256 <= 2 * nwarp): x is read once, only one load latency sits in front of the mat-vec
+        float v[2][8];
         double s = 0.0;
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int b = warp + u * nwarp;
-            if (b < k / 256) {
-                const float4 a0 = *reinterpret_cast<const float4 *>(x + b * 256 + lane * 8);
-                const float4 a1 = *reinterpret_cast<const float4 *>(x + b * 256 + lane * 8 + 4);
-                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(norm_w + b * 256 + lane * 8));
-                const float4 w1 = __ldg(reinterpret_cast<const float4 *>(norm_w + b * 256 + lane * 8 + 4));
-                v[u][0] = a0.x; v[u][1] = a0.y; v[u][2] = a0.z; v[u][3] = a0.w; v[u][4] = a1.x; v[u][5] = a1.y; v[u][6] = a1.z; v[u][7] = a1.w;
-                ww[u][0] = w0.x; ww[u][1] = w0.y; ww[u][2] = w0.z; ww[u][3] = w0.w; ww[u][4] = w1.x; ww[u][5] = w1.y; ww[u][6] = w1.z; ww[u][7] = w1.w;
+            if (b < n256) load8(x + b * 256 + lane * 8, v[u]);
+        }
+        after_loads();
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = warp + u * nwarp;
+            if (b < n256) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) s += (double) __fmul_rn(v[u][i], v[u][i]);
             }
@@ -287,9 +322,9 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int b = warp + u * nwarp;
-            if (b < k / 256) {
+            if (b < n256) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], sc), ww[u][i]);
+                for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], sc), pre_w[u][i]);
                 if (act_q8_0) q80_blocks_warp(v[u], lane, b, A);
                 else          q8k_block_warp(v[u], lane, b, A);
             }
@@ -297,6 +332,7 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
         return;
     }
     float scale = 1.f;
+    bool ran_after = false;
     if (norm_w != nullptr) {
         double s = 0.0;
         for (int i = tid * 4; i < k; i += blockDim.x * 4) {
@@ -306,6 +342,7 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
             s += (double) __fmul_rn(v.z, v.z);
             s += (double) __fmul_rn(v.w, v.w);
         }
+        after_loads(); ran_after = true;
         s = warp_sum_d(s);
         if (lane == 0) red[warp] = s;
         __syncthreads();
@@ -314,22 +351,30 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
         const float mean = (float) (tot / (double) k);
         scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
     }
-    const int n256 = k / 256;
-    for (int b = warp; b < n256; b += nwarp) {
-        const float * xb = x + b * 256 + lane * 8;
-        const float4 a0 = *reinterpret_cast<const float4 *>(xb);
-        const float4 a1 = *reinterpret_cast<const float4 *>(xb + 4);
-        float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        if (norm_w != nullptr) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(norm_w + b * 256 + lane * 8);
-            const float4 w1 = *reinterpret_cast<const float4 *>(norm_w + b * 256 + lane * 8 + 4);
-            const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    for (int b0 = warp; b0 < n256; b0 += PRO_U * nwarp) {
+        float v[PRO_U][8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fmul_rn(v[i], scale), ww[i]);
+        for (int u = 0; u < PRO_U; u++) {
+            const int b = b0 + u * nwarp;
+            if (b < n256) load8(x + b * 256 + lane * 8, v[u]);
         }
-        if (act_q8_0) q80_blocks_warp(v, lane, b, A);
-        else          q8k_block_warp(v, lane, b, A);
+        if (!ran_after) { after_loads(); ran_after = true; }
+#pragma unroll
+        for (int u = 0; u < PRO_U; u++) {
+            const int b = b0 + u * nwarp;
+            if (b < n256) {
+                if (norm_w != nullptr) {
+                    float ww[8];
+                    ldg8(norm_w + b * 256 + lane * 8, ww);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], scale), ww[i]);
+                }
+                if (act_q8_0) q80_blocks_warp(v[u], lane, b, A);
+                else          q8k_block_warp(v[u], lane, b, A);
+            }
+        }
     }
+    if (!ran_after) after_loads();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -348,6 +393,8 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// byte i (compile-time) of a word, zero-extended: one PRMT
+template <int I> __device__ __forceinline__ int byte_of(uint32_t w) { return (int) __byte_perm(w, 0u, 0x4440u | (unsigned) I); }
 
 // ------------------------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy wrappers (PTX; sm_90+ instructions, compiled for sm_100a)
@@ -380,9 +427,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void * src, uint32_
 // memory: lane 0 issues one TMA bulk copy per tile (`stages - 1` tiles ahead), completion lands on an mbarrier, and
 // each lane then reads its own row's fields with conflict-free 16-byte LDS. Per tile a lane computes the block's
 // exact integers — s[m] = the m-th int32 lane of the reference's AVX2 `sumi`, p[l] = the l-th lane of its mins
-// product — and advances its own 12 fp32 chains:
+// product — and advances its own fp32 chains (12 for Q4_K, 9 for Q5_K, 8 for Q6_K / Q8_0):
 //   acc[m] = fma(d_b, (float) s[m], acc[m])                      (ggml-quants.c:6972, 7556, 8216, 5376)
 //   Q4_K: acc[8+l] = fma(dmin_b, (float) p[l], acc[8+l])  (:6934)      Q5_K: acc[8] += dmin_b * (float) sum p  (:7516)
+// Tile layouts (one contiguous chunk each; `c` = 16-byte chunk index, `l` = lane):
+//   Q4_K 4608 B: qs uint4[8][32] | sd uint4[32] = {scales[12], d, dmin} of the lane's block
+//   Q5_K 5632 B: the same | qh uint4[2][32]
+//   Q6_K 6720 B: ql uint4[8][32] | scales int8[16] as uint4[32] | qh uint4[4][32] | d u16[32]
+//   Q8_0 1088 B: qs uint4[2][32] | d u16[32]                        (blocks of 32 weights)
 // ------------------------------------------------------------------------------------------------------------
 struct BlockInts { int s[8]; int p[4]; float d, dmin; };
 
@@ -391,14 +443,20 @@ __device__ __forceinline__ uint32_t lds_u32(const uint8_t * p) { return *reinter
 // 16 activation bytes of the current block, same address in every lane (broadcast)
 __device__ __forceinline__ int4 act16(const int8_t * ab, int slot) { return *reinterpret_cast<const int4 *>(ab + slot * 16); }
 
-// `sl` = the tile in shared memory + lane*16 (qs chunks) ; `sw` = tile + 4096 + lane*4 (the u32 plane)
+template <int TYPE> struct TypeTag { static constexpr int value = TYPE; };
+template <int TYPE> __device__ __forceinline__ constexpr int n_chains() { return TYPE == T_Q4_K ? 12 : TYPE == T_Q5_K ? 9 : 8; }
+
+// `sl` = the tile in shared memory + lane*16
 template <bool Q5>
-__device__ __forceinline__ void ints_q45k(const uint8_t * sl, const uint8_t * sw, const int8_t * ab, const int * bp, float yd, BlockInts & o) {
-    const uint32_t s0 = lds_u32(sw), s1 = lds_u32(sw + 128), s2 = lds_u32(sw + 256), dmw = lds_u32(sw + 384);
+__device__ __forceinline__ void ints_q45k(const uint8_t * sl, const int8_t * ab, const int * bp, float yd, BlockInts & o) {
+    const uint4 sd = lds_u4(sl + 4096);
+    const uint32_t s0 = sd.x, s1 = sd.y, s2 = sd.z, dmw = sd.w;
     // the 8 scale bytes and 8 min bytes (get_scale_min_k4 packing, cpp/ggml/src/ggml-quants.c:1891-1898)
     const uint32_t sc_a = s0 & 0x3f3f3f3fu, m_a = s1 & 0x3f3f3f3fu;
-    const uint32_t sc_b = (s2 & 0x0f0f0f0fu) | (((s0 >> 6) & 0x03030303u) << 4);
-    const uint32_t m_b  = ((s2 >> 4) & 0x0f0f0f0fu) | (((s1 >> 6) & 0x03030303u) << 4);
+    const uint32_t sc_b = (s2 & 0x0f0f0f0fu) | ((s0 >> 2) & 0x30303030u);
+    const uint32_t m_b  = ((s2 >> 4) & 0x0f0f0f0fu) | ((s1 >> 2) & 0x30303030u);
+    const int sc[8] = { byte_of<0>(sc_a), byte_of<1>(sc_a), byte_of<2>(sc_a), byte_of<3>(sc_a),
+                        byte_of<0>(sc_b), byte_of<1>(sc_b), byte_of<2>(sc_b), byte_of<3>(sc_b) };
     uint4 qh[2];
     if (Q5) { qh[0] = lds_u4(sl + 4608); qh[1] = lds_u4(sl + 4608 + 512); }
     // s = s_lo + (s_hi16 >> 4): the high nibbles are multiplied IN PLACE (mask 0xf0 = 16 x value, unsigned dp4a);
@@ -408,8 +466,7 @@ __device__ __forceinline__ void ints_q45k(const uint8_t * sl, const uint8_t * sw
     for (int i = 0; i < 8; i++) { s_lo[i] = 0; s_hi[i] = 0; }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const uint32_t scw = j < 2 ? sc_a : sc_b;
-        const int sc_lo = (int) ((scw >> ((j & 1) * 16)) & 0xff), sc_hi = (int) ((scw >> ((j & 1) * 16 + 8)) & 0xff);
+        const int sc_lo = sc[2 * j], sc_hi = sc[2 * j + 1];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint4 w = lds_u4(sl + (2 * j + h) * 512);
@@ -435,22 +492,20 @@ __device__ __forceinline__ void ints_q45k(const uint8_t * sl, const uint8_t * sw
     for (int i = 0; i < 8; i++) o.s[i] = s_lo[i] + (s_hi[i] >> 4);
     // mins: lane l of the reference's _mm_madd_epi16(mins, q8s) = m[2l]*bsum[2l] + m[2l+1]*bsum[2l+1]
     const int4 bp0 = *reinterpret_cast<const int4 *>(bp), bp1 = *reinterpret_cast<const int4 *>(bp + 4);
-    o.p[0] = (int) (m_a & 0xff) * bp0.x + (int) ((m_a >> 8) & 0xff) * bp0.y;
-    o.p[1] = (int) ((m_a >> 16) & 0xff) * bp0.z + (int) (m_a >> 24) * bp0.w;
-    o.p[2] = (int) (m_b & 0xff) * bp1.x + (int) ((m_b >> 8) & 0xff) * bp1.y;
-    o.p[3] = (int) ((m_b >> 16) & 0xff) * bp1.z + (int) (m_b >> 24) * bp1.w;
+    o.p[0] = byte_of<0>(m_a) * bp0.x + byte_of<1>(m_a) * bp0.y;
+    o.p[1] = byte_of<2>(m_a) * bp0.z + byte_of<3>(m_a) * bp0.w;
+    o.p[2] = byte_of<0>(m_b) * bp1.x + byte_of<1>(m_b) * bp1.y;
+    o.p[3] = byte_of<2>(m_b) * bp1.z + byte_of<3>(m_b) * bp1.w;
     const __half2 dmh = *reinterpret_cast<const __half2 *>(&dmw);
     o.d    = __fmul_rn(yd, __low2float(dmh));            // y[i].d * fp16(x[i].d)
     o.dmin = __fmul_rn(-yd, __high2float(dmh));          // -y[i].d * fp16(x[i].dmin)
 }
 
-// q (0..63 per byte) -> q - 32 as signed bytes, without inter-byte borrows
-__device__ __forceinline__ uint32_t sub32_bytes(uint32_t q) { return ((q | 0x80808080u) - 0x20202020u) ^ 0x80808080u; }
-
-__device__ __forceinline__ void ints_q6k(const uint8_t * sl, const uint8_t * sw, const uint8_t * tile, int lane, const int8_t * ab, float yd, BlockInts & o) {
-    uint32_t scw[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) scw[i] = lds_u32(sw + i * 128);
+// Q6_K: the weight is q - 32 with q in 0..63; sum (q - 32) a = dp4a_u8(q, a) - 32 * sum(a), and the second term
+// (per 32-bit word of the activation block) comes pre-computed from the prologue as the accumulator input of dp4a
+__device__ __forceinline__ void ints_q6k(const uint8_t * sl, const uint8_t * tile, int lane, const int8_t * ab, const int * asb,
+                                         float yd, BlockInts & o) {
+    const uint4 scv = lds_u4(sl + 4096);
 #pragma unroll
     for (int i = 0; i < 8; i++) o.s[i] = 0;
     // layout of a super-block: dequantize_row_q6_K (cpp/ggml/src/ggml-quants.c:2970-3000); half n, group g of 32
@@ -467,14 +522,16 @@ __device__ __forceinline__ void ints_q6k(const uint8_t * sl, const uint8_t * sw,
                 for (int gh = 0; gh < 2; gh++) {
                     const int g = gl + 2 * gh;
                     const int si = 8 * n + 2 * g + mq;
-                    const int sc = (int) (int8_t) ((scw[si >> 2] >> ((si & 3) * 8)) & 0xff);
-                    const int4 a = act16(ab, 8 * n + 2 * g + mq);
+                    const int sc = (int) (int8_t) ((word_of(scv, si >> 2) >> ((si & 3) * 8)) & 0xff);
+                    const int4 a = act16(ab, si);
+                    const int4 c32 = *reinterpret_cast<const int4 *>(asb + 4 * si);
 #pragma unroll
                     for (int wi = 0; wi < 4; wi++) {
                         const uint32_t QL = word_of(ql, wi), QH = word_of(qh, wi);
                         const uint32_t lo = gh ? ((QL >> 4) & 0x0f0f0f0fu) : (QL & 0x0f0f0f0fu);
-                        const uint32_t q  = lo | (((QH >> (2 * g)) & 0x03030303u) << 4);
-                        o.s[4 * mq + wi] += sc * __dp4a((int) sub32_bytes(q), word_of(a, wi), 0);
+                        const uint32_t h2 = g == 0 ? (QH << 4) : g == 1 ? (QH << 2) : g == 2 ? QH : (QH >> 2);
+                        const uint32_t q  = lo | (h2 & 0x30303030u);
+                        o.s[4 * mq + wi] += sc * dp4a_us(q, word_of(a, wi), word_of(c32, wi));
                     }
                 }
             }
@@ -498,43 +555,55 @@ __device__ __forceinline__ void ints_q80(const uint8_t * sl, const uint8_t * til
     o.dmin = 0.f;
 }
 
-// hsum_float_8 (cpp/ggml/src/ggml-quants.c:47-53) + the type's tail, from the row's 12 chain values
-__device__ __forceinline__ float finish_row(int type, const float (&c)[12]) {
+template <int TYPE>
+__device__ __forceinline__ void tile_ints(const uint8_t * tile, int lane, int t, const ActSmem & A, BlockInts & bi) {
+    const uint8_t * sl = tile + lane * 16;
+    if (TYPE == T_Q4_K)      ints_q45k<false>(sl, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi);
+    else if (TYPE == T_Q5_K) ints_q45k<true>(sl, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi);
+    else if (TYPE == T_Q6_K) ints_q6k(sl, tile, lane, A.q + (size_t) t * 256, A.as + (size_t) t * 64, A.dx[t], bi);
+    else                     ints_q80(sl, tile, lane, A.q + (size_t) t * 32, A.dx[t], bi);
+}
+
+// hsum_float_8 (cpp/ggml/src/ggml-quants.c:47-53) + the type's tail, from the row's chain values
+template <int TYPE>
+__device__ __forceinline__ float finish_row(const float * c) {
     const float r0 = __fadd_rn(c[4], c[0]), r1 = __fadd_rn(c[5], c[1]), r2 = __fadd_rn(c[6], c[2]), r3 = __fadd_rn(c[7], c[3]);
     const float h = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
-    if (type == T_Q4_K) return __fadd_rn(h, __fadd_rn(__fadd_rn(c[8], c[10]), __fadd_rn(c[9], c[11])));   // + acc_m
-    if (type == T_Q5_K) return __fadd_rn(h, c[8]);                                                       // + summs
+    if (TYPE == T_Q4_K) return __fadd_rn(h, __fadd_rn(__fadd_rn(c[8], c[10]), __fadd_rn(c[9], c[11])));   // + acc_m
+    if (TYPE == T_Q5_K) return __fadd_rn(h, c[8]);                                                       // + summs
     return h;
 }
 
 // a work unit resolved against the launch's segments: type, first tile in HBM, first output row
-struct UnitDesc { int type; int row0; const uint8_t * tiles; };
+struct UnitDesc { int type; int row0; uint32_t bytes; const uint8_t * tiles; };
 __device__ __forceinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit) {
     int si = 0, u = unit, row_base = 0;
     if (a.n_seg > 1 && u >= a.seg[0].n_units) { u -= a.seg[0].n_units; row_base += a.seg[0].n_rows; si = 1;
         if (a.n_seg > 2 && u >= a.seg[1].n_units) { u -= a.seg[1].n_units; row_base += a.seg[1].n_rows; si = 2; } }
     UnitDesc d;
     d.type  = si == 0 ? a.seg[0].type : (si == 1 ? a.seg[1].type : a.seg[2].type);
+    d.bytes = (uint32_t) (si == 0 ? a.seg[0].tile_bytes : (si == 1 ? a.seg[1].tile_bytes : a.seg[2].tile_bytes));
     const uint8_t * base = si == 0 ? a.seg[0].p0 : (si == 1 ? a.seg[1].p0 : a.seg[2].p0);
-    d.tiles = base + (size_t) u * a.tiles_unit * tile_bytes_of(d.type);
+    d.tiles = base + (size_t) u * a.tiles_unit * d.bytes;
     d.row0  = row_base + u * 32;
     return d;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // The fused quantized mat-vec: [RMSNorm] + activation quant (prologue) -> exact W.x -> epilogue.
-// A work unit is 32 rows. G warps (chosen by the host so that matrices with few rows still occupy every SM)
-// share a unit: the group's tiles form ONE sequence g = j*TU + t over its units j, warp w computes the integers of
-// g = w, w+G, ... concurrently with the others, while the 12 fp32 chains of each row advance strictly in block
-// order, handed from warp to warp through shared memory (producer mbarrier.arrive [release] on the consumer's
-// edge barrier, consumer try_wait [acquire]); the ring w -> w+1 -> ... -> w never has two hand-offs in flight.
+// A work unit is 32 rows x all TU blocks of K. G warps (a divisor of TU chosen by the host so that matrices with few
+// rows still occupy every SM) share a unit: warp w of the group owns tiles t = w, w+G, ... of every unit of its
+// group and computes their integers concurrently with the others, while the fp32 chains of each row advance strictly
+// in block order, handed from warp to warp through shared memory (producer mbarrier.arrive [release] on the
+// consumer's edge barrier, consumer try_wait [acquire]); the ring w -> w+1 -> ... -> w never has two hand-offs in
+// flight. The code of a unit is specialised on the unit's block type.
 // ------------------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ double red_smem[MV_MAX_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int G = a.group, TU = a.tiles_unit, S = a.stages;
+    const int G = a.group, TU = a.tiles_unit, S = a.stages, KPW = TU / G;
     // shared memory: ring (128-byte aligned slots) | activations | hand-off buffers | mbarriers
     uint8_t * ring = smem_raw + (size_t) warp * S * a.stage_bytes;
     uint8_t * act_base = smem_raw + (size_t) W * S * a.stage_bytes;
@@ -565,129 +634,132 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
     const int group_global = grp * gridDim.x + blockIdx.x;
     const int n_groups = gridDim.x * groups_per_cta;
     const int my_units = group_global < a.n_units ? (a.n_units - group_global + n_groups - 1) / n_groups : 0;
-    const int total = my_units * TU;
-    const int n_items = w < total ? (total - w + G - 1) / G : 0;
+    const int n_items = my_units * KPW;
 
-    // ---- producer side: item pi = (unit pj, tile pt) goes to ring slot pi % S
-    int pi = 0, pj = 0, pt = w, ps = 0;
-    while (pt >= TU && TU > 0 && pi < n_items) { pt -= TU; pj++; }
-    UnitDesc pd = describe_unit(a, group_global + pj * n_groups);
+    // ---- producer side: item pi = (unit pj, tile w + G*pk) goes to ring slot pi % S
+    int pi = 0, pj = 0, pk = 0, ps = 0;
+    UnitDesc pd = describe_unit(a, my_units > 0 ? group_global : 0);
     auto issue_next = [&]() {
         if (pi >= n_items) return;
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t) tile_bytes_of(pd.type);
-            mbar_expect_tx(full0 + 8 * ps, bytes);
-            bulk_g2s(ring_u32 + (uint32_t) ps * a.stage_bytes, pd.tiles + (size_t) pt * bytes, bytes, full0 + 8 * ps);
+            mbar_expect_tx(full0 + 8 * ps, pd.bytes);
+            bulk_g2s(ring_u32 + (uint32_t) ps * a.stage_bytes, pd.tiles + (size_t) (w + G * pk) * pd.bytes, pd.bytes, full0 + 8 * ps);
         }
         pi++; ps = ps + 1 == S ? 0 : ps + 1;
-        pt += G;
-        if (pt >= TU) {
-            do { pt -= TU; pj++; } while (pt >= TU);
+        if (++pk == KPW) {
+            pk = 0; pj++;
             if (pi < n_items) pd = describe_unit(a, group_global + pj * n_groups);
         }
     };
-    // weights do not depend on x: fill the ring before the prologue
-    for (int s = 0; s < S - 1; s++) issue_next();
+    // weights do not depend on x: part of the ring is filled before the wait, the rest once the x loads are in flight
+    const int prefill = min(a.prefill, S - 1);
+    for (int s = 0; s < prefill; s++) issue_next();
+    // norm weights are constants too: the warp's (at most two) blocks, fast single-pass norm only
+    const bool fast_norm = a.norm_w != nullptr && a.k / 256 <= 2 * W;
+    float ww[2][8] = {};
+    if (fast_norm) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = warp + u * W;
+            if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, ww[u]);
+        }
+    }
 
     trace_mark(a.trace, 1);
     pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
     trace_mark(a.trace, 2);
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
-    prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem);
+    prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem, ww, fast_norm,
+                      [&]() { for (int s = prefill; s < S - 1; s++) issue_next(); });
     __syncthreads();                                           // activations + every warp's barrier inits are visible
     trace_mark(a.trace, 3);
 
     // ---- consumer side
-    float acc[12];
+    int cs = 0, cpar = 0, n_in = 0;
+    for (int j = 0; j < my_units; j++) {
+        const UnitDesc cd = describe_unit(a, group_global + j * n_groups);
+        auto unit_body = [&](auto tag) {
+            constexpr int TYPE = decltype(tag)::value;
+            constexpr int NCH = n_chains<TYPE>();
+            float acc[NCH];
 #pragma unroll
-    for (int c = 0; c < 12; c++) acc[c] = 0.f;
-    int cj = 0, ct = w, cs = 0, cpar = 0, n_in = 0;
-    while (ct >= TU && n_items > 0) { ct -= TU; cj++; }
-    UnitDesc cd = describe_unit(a, group_global + cj * n_groups);
-    for (int i = 0; i < n_items; i++) {
-        const int g = w + i * G;
-        const int t = ct, type = cd.type;
-        issue_next();                                          // keeps S-1 tiles in flight (slot of item i-1 is free)
-        // epilogue operands of a unit that completes with this tile: fetched now, used after the chain
-        float pre0 = 0.f, pre1 = 0.f;
-        if (t == TU - 1) {
-            const int prow = cd.row0 + lane;
-            if (EPI == EPI_RESID) pre0 = a.resid[prow];
-            if (EPI == EPI_QKV && prow < a.n_q + a.n_k) {
-                const float2 cs2 = a.rope[(size_t) pos * (a.head_dim / 2) + (((prow & ~1) % a.head_dim) >> 1)];
-                pre0 = cs2.x; pre1 = cs2.y;
-            }
-        }
-        mbar_wait(full0 + 8 * cs, (uint32_t) cpar);
-        const uint8_t * tile = ring + (size_t) cs * a.stage_bytes;
-        const uint8_t * sl = tile + lane * 16;
-        BlockInts bi;
+            for (int c = 0; c < NCH; c++) acc[c] = 0.f;
+            for (int k = 0; k < KPW; k++) {
+                const int t = w + G * k;
+                issue_next();                                  // keeps S-1 tiles in flight (slot of the previous item is free)
+                // epilogue operands of a unit that completes with this tile: fetched now, used after the chain
+                float pre0 = 0.f, pre1 = 0.f;
+                if (t == TU - 1) {
+                    const int prow = cd.row0 + lane;
+                    if (EPI == EPI_RESID) pre0 = a.resid[prow];
+                    if (EPI == EPI_QKV && prow < a.n_q + a.n_k) {
+                        const float2 cs2 = a.rope[(size_t) pos * (a.head_dim / 2) + (((prow & ~1) % a.head_dim) >> 1)];
+                        pre0 = cs2.x; pre1 = cs2.y;
+                    }
+                }
+                mbar_wait(full0 + 8 * cs, (uint32_t) cpar);
+                BlockInts bi;
+                tile_ints<TYPE>(ring + (size_t) cs * a.stage_bytes, lane, t, A, bi);
+                __syncwarp();                                  // every lane is done reading the slot before it is refilled
+                cs = cs + 1 == S ? 0 : cs + 1; if (cs == 0) cpar ^= 1;
+                // ---- chain step, strictly in block order
+                if (G > 1) {
+                    if (j > 0 || t > 0) { mbar_wait(edge_in, (uint32_t) (n_in & 1)); n_in++; }   // previous step done, state published
+                    if (t > 0) {
 #pragma unroll
-        for (int l = 0; l < 4; l++) bi.p[l] = 0;
-        switch (type) {
-            case T_Q4_K: ints_q45k<false>(sl, tile + 4096 + lane * 4, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi); break;
-            case T_Q5_K: ints_q45k<true>(sl, tile + 4096 + lane * 4, A.q + (size_t) t * 256, A.bp + (size_t) t * 8, A.dx[t], bi); break;
-            case T_Q6_K: ints_q6k(sl, tile + 4096 + lane * 4, tile, lane, A.q + (size_t) t * 256, A.dx[t], bi); break;
-            default:     ints_q80(sl, tile, lane, A.q + (size_t) t * 32, A.dx[t], bi); break;
-        }
-        __syncwarp();                                          // every lane is done reading the slot before it is refilled
-        cs = cs + 1 == S ? 0 : cs + 1; if (cs == 0) cpar ^= 1;
-        // ---- chain step, strictly in block order
-        if (G > 1 && g > 0) { mbar_wait(edge_in, (uint32_t) (n_in & 1)); n_in++; }   // step g-1 is done, its state published
-        if (t == 0) {
+                        for (int c = 0; c < NCH; c++) acc[c] = handoff[c * 32 + lane];
+                    } else {
 #pragma unroll
-            for (int c = 0; c < 12; c++) acc[c] = 0.f;
-        } else if (G > 1) {
+                        for (int c = 0; c < NCH; c++) acc[c] = 0.f;
+                    }
+                }
 #pragma unroll
-            for (int c = 0; c < 12; c++) acc[c] = handoff[c * 32 + lane];
-        }
+                for (int c = 0; c < 8; c++) acc[c] = __fmaf_rn(bi.d, (float) bi.s[c], acc[c]);
+                if (TYPE == T_Q4_K) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) acc[c] = __fmaf_rn(bi.d, (float) bi.s[c], acc[c]);
-        if (type == T_Q4_K) {
+                    for (int l = 0; l < 4; l++) acc[8 + l] = __fmaf_rn(bi.dmin, (float) bi.p[l], acc[8 + l]);
+                } else if (TYPE == T_Q5_K) {
+                    acc[8] = __fadd_rn(acc[8], __fmul_rn(bi.dmin, (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3])));
+                }
+                if (G > 1 && !(j == my_units - 1 && t == TU - 1)) {
+                    if (t != TU - 1) {
 #pragma unroll
-            for (int l = 0; l < 4; l++) acc[8 + l] = __fmaf_rn(bi.dmin, (float) bi.p[l], acc[8 + l]);
-        } else if (type == T_Q5_K) {
-            acc[8] = __fadd_rn(acc[8], __fmul_rn(bi.dmin, (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3])));
-        }
-        if (G > 1 && g != total - 1) {
-            if (t != TU - 1) {
-#pragma unroll
-                for (int c = 0; c < 12; c++) handoff[c * 32 + lane] = acc[c];
-            }
-            mbar_arrive(edge_out);                             // release: my lane's stores above are visible to the waiter
-        }
-        // advance to my next tile
-        const UnitDesc done = cd;
-        ct += G;
-        if (ct >= TU) {
-            do { ct -= TU; cj++; } while (ct >= TU);
-            if (i + 1 < n_items) cd = describe_unit(a, group_global + cj * n_groups);
-        }
-        if (t != TU - 1) continue;
+                        for (int c = 0; c < NCH; c++) handoff[c * 32 + lane] = acc[c];
+                    }
+                    mbar_arrive(edge_out);                     // release: my lane's stores above are visible to the waiter
+                }
+                if (t != TU - 1) continue;
 
-        // ---- unit complete: this lane's row
-        const float val = finish_row(type, acc);
-        const float oth = __shfl_xor_sync(0xffffffffu, val, 1);    // partner row (2i <-> 2i+1)
-        const int row = done.row0 + lane;
-        if (EPI == EPI_STORE) {
-            a.out[row] = val;
-        } else if (EPI == EPI_RESID) {
-            a.out[row] = __fadd_rn(val, pre0);                     // ggml_add(cur, inpSA / ffn_inp): llama.cpp:8865, 8901
-        } else if (EPI == EPI_SILU) {
-            // rows (2r, 2r+1) = (gate r, up r): silu(gate) * up, cpp/src/llama.cpp:7960-8085
-            if ((lane & 1) == 0) a.out[row >> 1] = __fmul_rn(silu_exact(val), oth);
-        } else {  // EPI_QKV
-            const float v0 = (lane & 1) ? oth : val, v1 = (lane & 1) ? val : oth;   // (x0, x1) of this row's RoPE pair
-            if (row < a.n_q + a.n_k) {
-                // RoPE NORM mode on the pair (x0, x1): cpp/ggml/src/ggml.c:14121-14135
-                const float2 cs2 = make_float2(pre0, pre1);
-                const float y = (lane & 1) ? __fadd_rn(__fmul_rn(v0, cs2.y), __fmul_rn(v1, cs2.x))
-                                           : __fsub_rn(__fmul_rn(v0, cs2.x), __fmul_rn(v1, cs2.y));
-                if (row < a.n_q) a.q_out[row] = y;
-                else a.k_cache[(size_t) pos * a.kv_dim + (row - a.n_q)] = __float2half_rn(y);   // K post-RoPE as f16: llama.cpp:7849-7853
-            } else {
-                a.v_cache[(size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)] = __float2half_rn(val);
+                // ---- unit complete: this lane's row
+                const float val = finish_row<TYPE>(acc);
+                const float oth = __shfl_xor_sync(0xffffffffu, val, 1);    // partner row (2i <-> 2i+1)
+                const int row = cd.row0 + lane;
+                if (EPI == EPI_STORE) {
+                    a.out[row] = val;
+                } else if (EPI == EPI_RESID) {
+                    a.out[row] = __fadd_rn(val, pre0);             // ggml_add(cur, inpSA / ffn_inp): llama.cpp:8865, 8901
+                } else if (EPI == EPI_SILU) {
+                    // rows (2r, 2r+1) = (gate r, up r): silu(gate) * up, cpp/src/llama.cpp:7960-8085
+                    if ((lane & 1) == 0) a.out[row >> 1] = __fmul_rn(silu_exact(val), oth);
+                } else {  // EPI_QKV
+                    const float v0 = (lane & 1) ? oth : val, v1 = (lane & 1) ? val : oth;   // (x0, x1) of this row's RoPE pair
+                    if (row < a.n_q + a.n_k) {
+                        // RoPE NORM mode on the pair (x0, x1): cpp/ggml/src/ggml.c:14121-14135
+                        const float y = (lane & 1) ? __fadd_rn(__fmul_rn(v0, pre1), __fmul_rn(v1, pre0))
+                                                   : __fsub_rn(__fmul_rn(v0, pre0), __fmul_rn(v1, pre1));
+                        if (row < a.n_q) a.q_out[row] = y;
+                        else a.k_cache[(size_t) pos * a.kv_dim + (row - a.n_q)] = __float2half_rn(y);   // K post-RoPE as f16: llama.cpp:7849-7853
+                    } else {
+                        a.v_cache[(size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)] = __float2half_rn(val);
+                    }
+                }
             }
+        };
+        switch (cd.type) {
+            case T_Q4_K: unit_body(TypeTag<T_Q4_K>{}); break;
+            case T_Q5_K: unit_body(TypeTag<T_Q5_K>{}); break;
+            case T_Q6_K: unit_body(TypeTag<T_Q6_K>{}); break;
+            default:     unit_body(TypeTag<T_Q8_0>{}); break;
         }
     }
     if (a.trace != nullptr) { __syncthreads(); trace_mark(a.trace, 4); }
@@ -702,7 +774,8 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ double red_smem[MV_MAX_WARPS];
     const ActSmem A = act_smem_carve(smem_raw, k, act_q8_0);
-    prologue_quantize(x, nullptr, 0.f, k, act_q8_0, A, red_smem);
+    const float no_w[2][8] = {};
+    prologue_quantize(x, nullptr, 0.f, k, act_q8_0, A, red_smem, no_w, false, []() {});
     __syncthreads();
     if (!act_q8_0) {
         const int nb = k / 256;
@@ -1079,38 +1152,44 @@ __global__ void __launch_bounds__(PV_DIMS * 16) k_attn_pv(const AttnArgs a) {
 // with exactly k_attn_softmax's arithmetic, on a shared-memory copy; then thread (h, c, dl) runs chain c of output
 // dim dl of head h. The CTA's V slice is independent of the scores and is put in flight BEFORE griddepcontrol.wait
 // (k_attn_scores waits for the QKV kernel before it lets this kernel launch, so K/V/q are already visible).
-//   grid (n_head_kv, HD / PVS_DIMS), block GQA * 16 * PVS_DIMS threads; shared: ps [GQA][n_pad] f32 | vs [v_chunk][8] f16
+//   grid (n_head_kv, HD / PVS_DIMS), block GQA * 64 threads (16 chains x 4 dim pairs per head); shared: ps [GQA][n_pad] f32 | vs [v_chunk][8] f16
 // ------------------------------------------------------------------------------------------------------------
 static constexpr int PVS_DIMS = 8;            // dims per CTA: 8 halfs = one 16-byte cp.async per position
+static constexpr int PVS_TH   = 16 * (PVS_DIMS / 2);   // threads per head: 16 chains x 4 dim pairs
 
 template <int GQA>
-__global__ void __launch_bounds__(GQA * 16 * PVS_DIMS) k_attn_softmax_pv(const AttnArgs a) {
+__global__ void __launch_bounds__(GQA * PVS_TH) k_attn_softmax_pv(const AttnArgs a) {
     constexpr int HD = 128;
-    constexpr int TH = 16 * PVS_DIMS;                          // threads per head (128 = 4 warps)
+    constexpr int TH = PVS_TH;                                 // 64 threads = 2 warps per head
     constexpr int NT = GQA * TH;
-    constexpr int NW = TH / 32;                                // warps per head
+    constexpr int NW = TH / 32;
     extern __shared__ __align__(16) uint8_t sp_dyn[];
     __shared__ float  redf[GQA][NW];
     __shared__ double redd[GQA][NW];
     __shared__ float  red[GQA][16][PVS_DIMS + 1];
     const int g = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int h = tid / TH, ht = tid % TH;                     // head of the group, thread within the head
-    const int c = ht / PVS_DIMS, dl = ht % PVS_DIMS;           // chain, dim
+    const int c = ht / (PVS_DIMS / 2), dp = ht % (PVS_DIMS / 2);   // chain, dim pair
     const int w = ht >> 5;                                     // warp within the head
 
     trace_mark(a.trace, 0);
     pdl_launch_dependents();
     const int n_kv = attn_n_kv(a);                             // DecodeState is written by the previous TOKEN's last kernel
     const int n_pad = (n_kv + 31) / 32 * 32;
-    const int VCH = a.p_chunk;                                 // positions of V staged at a time
+    const int VCH = a.p_chunk;                                 // positions of V staged at a time (multiple of 32)
     float * ps = reinterpret_cast<float *>(sp_dyn);            // [GQA][n_pad]
     __half (*vs)[PVS_DIMS] = reinterpret_cast<__half (*)[PVS_DIMS]>(sp_dyn + (size_t) GQA * n_pad * 4);
     const __half * vbase = a.v_cache + g * HD + slice * PVS_DIMS;
-    {   // V rows of the first chunk (rows at or beyond n_kv are never read: p == 0 there)
-        const int rows = min(VCH, n_kv);
-        for (int i = tid; i < rows; i += NT) cp_async16(&vs[i][0], vbase + (size_t) i * a.kv_dim);
+    // V rows of one chunk; rows in [n_kv, n_pad) are zero-filled: p == 0 there and the product must be 0, never NaN
+    auto stage_v = [&](int t0) {
+        const int len = min(VCH, n_pad - t0);
+        for (int i = tid; i < len; i += NT) {
+            if (t0 + i < n_kv) cp_async16(&vs[i][0], vbase + (size_t) (t0 + i) * a.kv_dim);
+            else *reinterpret_cast<uint4 *>(&vs[i][0]) = make_uint4(0u, 0u, 0u, 0u);
+        }
         cp_async_commit();
-    }
+    };
+    stage_v(0);
     pdl_wait();                                               // the raw scores are complete
     trace_mark(a.trace, 1);
     float * row = ps + (size_t) h * n_pad;
@@ -1122,9 +1201,16 @@ __global__ void __launch_bounds__(GQA * 16 * PVS_DIMS) k_attn_softmax_pv(const A
     }
     asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");   // the head's row is in shared memory
     trace_mark(a.trace, 2);
-    // soft_max_ext of the head's row by its NW warps: see k_attn_softmax for the summation-order argument
+    // soft_max_ext of the head's row (cpp/ggml/src/ggml.c:13682-13778): a thread owns whole 16-element vectors of the
+    // reference's loop, so the _mm512_reduce_add_ps tree is register arithmetic; the per-vector float sums are
+    // accumulated in double (order-insensitive here: see k_attn_softmax)
+    const int n16 = n_pad / 16;
     float mx = -INFINITY;
-    for (int i = ht; i < n_pad; i += TH) mx = fmaxf(mx, row[i]);
+    for (int gi = ht; gi < n16; gi += TH) {
+        const float4 * r4 = reinterpret_cast<const float4 *>(row + 16 * gi);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const float4 v = r4[q]; mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
+    }
     mx = warp_max(mx);
     if (lane == 0) redf[h][w] = mx;
     asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");
@@ -1132,11 +1218,17 @@ __global__ void __launch_bounds__(GQA * 16 * PVS_DIMS) k_attn_softmax_pv(const A
 #pragma unroll
     for (int j = 1; j < NW; j++) mx = fmaxf(mx, redf[h][j]);
     double part = 0.0;
-    for (int i = ht; i < n_pad; i += TH) {                     // n_pad % 32 == 0 and TH % 32 == 0: whole warps in or out
-        const float p = v_expf(__fsub_rn(row[i], mx));
-        row[i] = p;
-        const float gs = reduce_add16_shfl(p);                 // 16 consecutive, 16-aligned elements
-        if ((lane & 15) == 0) part += (double) gs;
+    for (int gi = ht; gi < n16; gi += TH) {
+        float4 * r4 = reinterpret_cast<float4 *>(row + 16 * gi);
+        float e[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 v = r4[q];
+            e[4 * q] = v_expf(__fsub_rn(v.x, mx)); e[4 * q + 1] = v_expf(__fsub_rn(v.y, mx));
+            e[4 * q + 2] = v_expf(__fsub_rn(v.z, mx)); e[4 * q + 3] = v_expf(__fsub_rn(v.w, mx));
+            r4[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+        }
+        part += (double) reduce_add16_regs(e);
     }
     part = warp_sum_d(part);
     if (lane == 0) redd[h][w] = part;
@@ -1145,32 +1237,40 @@ __global__ void __launch_bounds__(GQA * 16 * PVS_DIMS) k_attn_softmax_pv(const A
 #pragma unroll
     for (int j = 0; j < NW; j++) sum += redd[h][j];
     const float inv = (float) (1.0 / sum);
-    for (int i = ht; i < n_pad; i += TH) row[i] = __fmul_rn(row[i], inv);   // own elements only
+    for (int gi = ht; gi < n16; gi += TH) {                    // own vectors only
+        float4 * r4 = reinterpret_cast<float4 *>(row + 16 * gi);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float4 v = r4[q];
+            v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv); v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
+            r4[q] = v;
+        }
+    }
     __syncthreads();                                           // all rows normalised, every thread's V copies landed
     trace_mark(a.trace, 3);
 
-    // P.V: chain c of (head h, dim dl): acc = fma(V[t][dl], p[t], acc) over t = c, c+16, ...
-    float acc = 0.f;
+    // P.V: chain c of (head h, dims 2dp, 2dp+1): acc = fma(V[t][d], p[t], acc) over t = c, c+16, ...
+    float acc0 = 0.f, acc1 = 0.f;
     for (int t0 = 0; t0 < n_pad; t0 += VCH) {
-        const int len = min(VCH, n_pad - t0), rows = min(len, n_kv - t0);
+        const int len = min(VCH, n_pad - t0);
         if (t0) {
             __syncthreads();
-            for (int i = tid; i < rows; i += NT) cp_async16(&vs[i][0], vbase + (size_t) (t0 + i) * a.kv_dim);
-            cp_async_commit();
+            stage_v(t0);
             cp_async_wait<0>();
             __syncthreads();
         }
         const int steps = len / 16;
-        const float * pr = row + t0;
+        const float * pr = row + t0 + c;
+        const __half2 * vr = reinterpret_cast<const __half2 *>(&vs[c][2 * dp]);
 #pragma unroll 8
         for (int s = 0; s < steps; s++) {
-            const int tt = 16 * s + c;
-            // slots at or beyond n_kv have p == 0 exactly; their V bytes were not loaded and must not be multiplied
-            const float v = t0 + tt < n_kv ? __half2float(vs[tt][dl]) : 0.f;
-            acc = __fmaf_rn(v, pr[tt], acc);
+            const float2 v = __half22float2(vr[(size_t) s * 16 * (PVS_DIMS / 2)]);
+            const float p = pr[16 * s];
+            acc0 = __fmaf_rn(v.x, p, acc0);
+            acc1 = __fmaf_rn(v.y, p, acc1);
         }
     }
-    red[h][c][dl] = acc;
+    red[h][c][2 * dp] = acc0; red[h][c][2 * dp + 1] = acc1;
     __syncthreads();
     trace_mark(a.trace, 4);
     if (tid < GQA * PVS_DIMS) {
