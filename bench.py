@@ -170,7 +170,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from booster_b200 import engine
+    from booster_b200 import engine, pipeline
 
     if world > 1:
         torch.cuda.set_device(local_rank)
@@ -180,13 +180,11 @@ def main():
         dist.barrier()
         path = model_path()
     # stage = contiguous layer range (cpp/src/llama.cpp:5932-5968 with equal proportions)
-    lb, le = rank * cfg.n_layer // world, (rank + 1) * cfg.n_layer // world
+    lb, le = pipeline.stage_range(cfg.n_layer, rank, world)
     m = engine.Model(path, device=local_rank, layer_begin=lb, layer_end=le)
     c = engine.Context(m, CTX)
     if world > 1:
-        uid = [engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        c.comm_init(rank, world, uid[0])
+        c.comm_init(rank, world, pipeline.share_unique_id(dist, engine.comm_unique_id))
     gen = (lambda tok, pos, n: c.pipeline_generate_greedy(tok, pos, n)) if world > 1 else (lambda tok, pos, n: c.generate_greedy(tok, pos, n))
 
     # fill the KV cache with a real decode pass up to the burst start (untimed)
@@ -222,12 +220,8 @@ def main():
     # (events on one rank do not see the other stages), max over ranks
     elapsed = dev_ms / 1e3 if world == 1 else wall
     if world > 1:
-        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
+        elapsed = pipeline.max_over_ranks(dist, elapsed, device="cuda")
+        launches = pipeline.sum_over_ranks(dist, launches, device="cuda")
     tokens = args.steps * BURST
     tps = tokens / elapsed
 
