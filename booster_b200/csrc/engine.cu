@@ -510,6 +510,9 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     int sb = 0;
     for (int i = 0; i < a.n_seg; i++) sb = std::max(sb, tile_bytes_of(a.seg[i].type));
     a.stage_bytes = (sb + 127) / 128 * 128;
+    int nv = 0;
+    for (int i = 0; i < a.n_seg; i++) nv = std::max(nv, chain_values_of(a.seg[i].type));
+    a.nv = nv;
     // launch shape: W warps per CTA (one CTA per SM), S ring stages per warp, G warps per 32-row unit. Pick the
     // combination with the most concurrently active warps (every unit resident in as few waves as possible),
     // then the deepest ring that still fits the shared memory.
@@ -521,7 +524,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
             if (W % G) continue;
             if (G > 1 && (long long) a.n_units * G > (long long) c->sm_count * W) continue;   // sharing only within one wave
             if (a.tiles_unit % G) continue;                                                   // warp w owns tiles w, w+G, ... of every unit
-            const size_t fixed = act_bytes + (G > 1 ? (size_t) (W / G) * HANDOFF_WORDS * 4 : 0) + (size_t) W * 4 * 8 + (size_t) W * 8;
+            const size_t fixed = act_bytes + chain_smem_bytes(W, G, nv) + (size_t) W * 4 * 8;
             if (fixed + (size_t) W * 2 * a.stage_bytes > budget) continue;
             const int S = (int) std::min<size_t>(4, (budget - fixed) / ((size_t) W * a.stage_bytes));
             const long long warps = (long long) a.n_units * G, slots = (long long) c->sm_count * W;
@@ -537,8 +540,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     if (prefill_env < 0) { const char * e = getenv("BOOSTER_B200_PREFILL"); prefill_env = e ? atoi(e) : 1; }
     a.prefill = prefill_env;
     const int W = bestW;
-    const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + (a.group > 1 ? (size_t) (W / a.group) * HANDOFF_WORDS * 4 : 0)
-                      + (size_t) W * a.stages * 8 + (size_t) W * 8;
+    const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(W, a.group, nv) + (size_t) W * a.stages * 8;
     static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
     if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }

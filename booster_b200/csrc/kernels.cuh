@@ -76,6 +76,7 @@ struct MatvecArgs {
     int stages;                // tiles of shared-memory ring per warp (>= 2)
     int stage_bytes;           // ring slot size = largest tile of the launch, 128-byte multiple
     int prefill;               // tiles per warp requested before griddepcontrol.wait (the rest follow the x loads)
+    int nv;                    // chain values per tile (largest chain_values_of over the segments)
     // epilogue
     float * out;
     const float * resid;
@@ -90,7 +91,14 @@ struct MatvecArgs {
 };
 
 static constexpr int MV_MAX_WARPS = 16;                     // one persistent CTA per SM, 8..16 warps (host picks)
-static constexpr int HANDOFF_WORDS = 12 * 32;               // chain state of one unit: 12 fp32 chains x 32 rows
+static constexpr int HANDOFF_WORDS = 12 * 32;               // final chain values of one unit: 12 fp32 chains x 32 rows
+// values a tile publishes for the chain phase: s[8] (+ p[4] | sum p) as floats, d (+ dmin)
+__host__ __device__ __forceinline__ int chain_values_of(int type) { return type == 12 ? 14 : type == 13 ? 11 : 9; }
+// shared memory of the chain exchange when G > 1: per warp a double-buffered slot of `nv` x 32 floats, per group the
+// final values
+__host__ __device__ __forceinline__ size_t chain_smem_bytes(int W, int G, int nv) {
+    return G > 1 ? (size_t) W * 2 * nv * 128 + (size_t) (W / G) * HANDOFF_WORDS * 4 : 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // PDL (programmatic dependent launch): every kernel of the forward pass is launched with
@@ -290,7 +298,8 @@ static constexpr int PRO_U = 4;
 template <typename F>
 __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, const float * __restrict__ norm_w,
                                                   float eps, int k, int act_q8_0, const ActSmem & A, double * red,
-                                                  const float (&pre_w)[2][8], bool fast_norm, F after_loads) {
+                                                  const float (&pre_w)[2][8], bool fast_norm, F after_loads,
+                                                  unsigned long long * tr = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
     const int n256 = k / 256;
@@ -314,11 +323,13 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
         }
         s = warp_sum_d(s);
         if (lane == 0) red[warp] = s;
+        trace_mark(tr, 5);
         __syncthreads();
         double tot = 0.0;
         for (int w = 0; w < nwarp; w++) tot += red[w];
         const float mean = (float) (tot / (double) k);
         const float sc = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+        trace_mark(tr, 6);
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int b = warp + u * nwarp;
@@ -363,6 +374,7 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
         for (int u = 0; u < PRO_U; u++) {
             const int b = b0 + u * nwarp;
             if (b < n256) {
+                if (u == 1 && b0 == warp) trace_mark(tr, 5);       // first block of the warp quantized
                 if (norm_w != nullptr) {
                     float ww[8];
                     ldg8(norm_w + b * 256 + lane * 8, ww);
@@ -593,10 +605,12 @@ __device__ __forceinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit
 // The fused quantized mat-vec: [RMSNorm] + activation quant (prologue) -> exact W.x -> epilogue.
 // A work unit is 32 rows x all TU blocks of K. G warps (a divisor of TU chosen by the host so that matrices with few
 // rows still occupy every SM) share a unit: warp w of the group owns tiles t = w, w+G, ... of every unit of its
-// group and computes their integers concurrently with the others, while the fp32 chains of each row advance strictly
-// in block order, handed from warp to warp through shared memory (producer mbarrier.arrive [release] on the
-// consumer's edge barrier, consumer try_wait [acquire]); the ring w -> w+1 -> ... -> w never has two hand-offs in
-// flight. The code of a unit is specialised on the unit's block type.
+// group. G == 1: the row's fp32 chains live in the lane's registers. G > 1: the unit is processed in rounds of G
+// tiles; every warp computes the INTEGERS of its tile (order-free, exact) and publishes them as floats, one named
+// barrier, then the fp32 chains — which must run in block order — are advanced over the round's G tiles by the lanes
+// of the whole group in parallel: lane (row) of warp w owns chains c = w, w+G, ... of its row (32 x 12 independent
+// chains per unit). Nothing is serialised across warps any more; a chain step costs one LDS + one FMA.
+// The code of a unit is specialised on the unit's block type.
 // ------------------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArgs a) {
@@ -610,19 +624,19 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
     const size_t act_bytes = act_smem_bytes(a.k, a.act_q8_0);
     const ActSmem A = act_smem_carve(act_base, a.k, a.act_q8_0);
     const int grp = warp / G, w = warp - grp * G;              // group inside the CTA, warp inside the group
-    float * handoff = reinterpret_cast<float *>(act_base + act_bytes) + (size_t) grp * HANDOFF_WORDS;
-    const size_t ho_bytes = G > 1 ? (size_t) (W / G) * HANDOFF_WORDS * 4 : 0;
-    uint64_t * bars = reinterpret_cast<uint64_t *>(act_base + act_bytes + ho_bytes);
+    const int NV = a.nv;
+    // chain exchange (G > 1): cbuf[parity][warp of the CTA][value][lane] | fin[group][chain][lane]
+    float * cbuf = reinterpret_cast<float *>(act_base + act_bytes);
+    float * fin  = cbuf + (size_t) W * 2 * NV * 32 + (size_t) grp * HANDOFF_WORDS;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(act_base + act_bytes + chain_smem_bytes(W, G, NV));
     const uint32_t full0   = smem_u32(bars + warp * S);                            // my ring slots' "tile landed" barriers
-    const uint32_t edge_in  = smem_u32(bars + W * S + warp);                        // "chain state for me is published"
-    const uint32_t edge_out = smem_u32(bars + W * S + grp * G + (w + 1 == G ? 0 : w + 1));
     const uint32_t ring_u32 = smem_u32(ring);
+    const int bar_id = 1 + grp, bar_threads = G * 32;                              // the group's named barrier
 
     trace_mark(a.trace, 0);
     pdl_launch_dependents();                                   // the next kernel may start its own weight prefetch
     if (lane == 0) {
         for (int s = 0; s < S; s++) mbar_init(full0 + 8 * s, 1);
-        mbar_init(edge_in, 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -670,20 +684,21 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
     trace_mark(a.trace, 2);
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
     prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem, ww, fast_norm,
-                      [&]() { for (int s = prefill; s < S - 1; s++) issue_next(); });
+                      [&]() { for (int s = prefill; s < S - 1; s++) issue_next(); }, a.trace);
     __syncthreads();                                           // activations + every warp's barrier inits are visible
     trace_mark(a.trace, 3);
 
     // ---- consumer side
-    int cs = 0, cpar = 0, n_in = 0;
+    int cs = 0, cpar = 0, rnd = 0;
     for (int j = 0; j < my_units; j++) {
         const UnitDesc cd = describe_unit(a, group_global + j * n_groups);
         auto unit_body = [&](auto tag) {
             constexpr int TYPE = decltype(tag)::value;
             constexpr int NCH = n_chains<TYPE>();
-            float acc[NCH];
+            constexpr int CPW = 6;                             // chains per warp when G > 1: ceil(12 / 2)
+            float acc[12];                                     // G == 1: the row's chains; G > 1: [0, CPW) = chains w, w+G, ...
 #pragma unroll
-            for (int c = 0; c < NCH; c++) acc[c] = 0.f;
+            for (int c = 0; c < 12; c++) acc[c] = 0.f;
             for (int k = 0; k < KPW; k++) {
                 const int t = w + G * k;
                 issue_next();                                  // keeps S-1 tiles in flight (slot of the previous item is free)
@@ -702,36 +717,65 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
                 tile_ints<TYPE>(ring + (size_t) cs * a.stage_bytes, lane, t, A, bi);
                 __syncwarp();                                  // every lane is done reading the slot before it is refilled
                 cs = cs + 1 == S ? 0 : cs + 1; if (cs == 0) cpar ^= 1;
-                // ---- chain step, strictly in block order
-                if (G > 1) {
-                    if (j > 0 || t > 0) { mbar_wait(edge_in, (uint32_t) (n_in & 1)); n_in++; }   // previous step done, state published
-                    if (t > 0) {
+                float val;
+                if (G == 1) {
+                    // ---- chain step in registers, strictly in block order
 #pragma unroll
-                        for (int c = 0; c < NCH; c++) acc[c] = handoff[c * 32 + lane];
-                    } else {
+                    for (int c = 0; c < 8; c++) acc[c] = __fmaf_rn(bi.d, (float) bi.s[c], acc[c]);
+                    if (TYPE == T_Q4_K) {
 #pragma unroll
-                        for (int c = 0; c < NCH; c++) acc[c] = 0.f;
+                        for (int l = 0; l < 4; l++) acc[8 + l] = __fmaf_rn(bi.dmin, (float) bi.p[l], acc[8 + l]);
+                    } else if (TYPE == T_Q5_K) {
+                        acc[8] = __fadd_rn(acc[8], __fmul_rn(bi.dmin, (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3])));
                     }
-                }
+                    if (t != TU - 1) continue;
+                    val = finish_row<TYPE>(acc);
+                } else {
+                    // ---- publish this tile's integers (as exact floats) and scales
+                    float * cb = cbuf + ((size_t) ((rnd & 1) * W + warp) * NV) * 32 + lane;
 #pragma unroll
-                for (int c = 0; c < 8; c++) acc[c] = __fmaf_rn(bi.d, (float) bi.s[c], acc[c]);
-                if (TYPE == T_Q4_K) {
+                    for (int c = 0; c < 8; c++) cb[c * 32] = (float) bi.s[c];
+                    if (TYPE == T_Q4_K) {
 #pragma unroll
-                    for (int l = 0; l < 4; l++) acc[8 + l] = __fmaf_rn(bi.dmin, (float) bi.p[l], acc[8 + l]);
-                } else if (TYPE == T_Q5_K) {
-                    acc[8] = __fadd_rn(acc[8], __fmul_rn(bi.dmin, (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3])));
-                }
-                if (G > 1 && !(j == my_units - 1 && t == TU - 1)) {
-                    if (t != TU - 1) {
-#pragma unroll
-                        for (int c = 0; c < NCH; c++) handoff[c * 32 + lane] = acc[c];
+                        for (int l = 0; l < 4; l++) cb[(8 + l) * 32] = (float) bi.p[l];
+                    } else if (TYPE == T_Q5_K) {
+                        cb[8 * 32] = (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3]);
                     }
-                    mbar_arrive(edge_out);                     // release: my lane's stores above are visible to the waiter
+                    cb[NCH * 32] = bi.d;
+                    if (TYPE == T_Q4_K || TYPE == T_Q5_K) cb[(NCH + 1) * 32] = bi.dmin;
+                    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
+                    // ---- chain phase of the round: tiles t0 .. t0+G-1 in order, this lane's chains c = w + i*G
+                    const float * rb = cbuf + ((size_t) ((rnd & 1) * W + grp * G) * NV) * 32 + lane;
+                    rnd++;
+#pragma unroll 4
+                    for (int ww = 0; ww < G; ww++) {
+                        const float * tb = rb + (size_t) ww * NV * 32;
+#pragma unroll
+                        for (int i = 0; i < CPW; i++) {
+                            const int c = w + i * G;
+                            if (c < 8) acc[i] = __fmaf_rn(tb[NCH * 32], tb[c * 32], acc[i]);
+                            else if (c < NCH) {
+                                if (TYPE == T_Q4_K) acc[i] = __fmaf_rn(tb[(NCH + 1) * 32], tb[c * 32], acc[i]);
+                                else                acc[i] = __fadd_rn(acc[i], __fmul_rn(tb[(NCH + 1) * 32], tb[c * 32]));
+                            }
+                        }
+                    }
+                    if (k != KPW - 1) continue;
+                    // ---- unit complete: gather the row's chains
+#pragma unroll
+                    for (int i = 0; i < CPW; i++) {
+                        const int c = w + i * G;
+                        if (c < NCH) fin[c * 32 + lane] = acc[i];
+                    }
+                    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
+                    if (w != G - 1) continue;                  // the warp that fetched the epilogue operands finishes the rows
+                    float cv[NCH];
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) cv[c] = fin[c * 32 + lane];
+                    val = finish_row<TYPE>(cv);
                 }
-                if (t != TU - 1) continue;
 
-                // ---- unit complete: this lane's row
-                const float val = finish_row<TYPE>(acc);
+                // ---- this lane's row
                 const float oth = __shfl_xor_sync(0xffffffffu, val, 1);    // partner row (2i <-> 2i+1)
                 const int row = cd.row0 + lane;
                 if (EPI == EPI_STORE) {
@@ -1206,10 +1250,14 @@ __global__ void __launch_bounds__(GQA * PVS_TH) k_attn_softmax_pv(const AttnArgs
     // accumulated in double (order-insensitive here: see k_attn_softmax)
     const int n16 = n_pad / 16;
     float mx = -INFINITY;
+    // a thread visits the four float4 of its vector starting at (ht >> 1) & 3: the 8 lanes of a quarter-warp then hit 8
+    // different 16-byte bank groups. The reduce tree pairs float4 f with f+2 and adds the two halves — both
+    // commutative — so the rotation leaves every bit of the result unchanged.
+    const int rot = (ht >> 1) & 3;
     for (int gi = ht; gi < n16; gi += TH) {
         const float4 * r4 = reinterpret_cast<const float4 *>(row + 16 * gi);
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const float4 v = r4[q]; mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
+        for (int q = 0; q < 4; q++) { const float4 v = r4[(q + rot) & 3]; mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
     }
     mx = warp_max(mx);
     if (lane == 0) redf[h][w] = mx;
@@ -1223,10 +1271,10 @@ __global__ void __launch_bounds__(GQA * PVS_TH) k_attn_softmax_pv(const AttnArgs
         float e[16];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const float4 v = r4[q];
+            const float4 v = r4[(q + rot) & 3];
             e[4 * q] = v_expf(__fsub_rn(v.x, mx)); e[4 * q + 1] = v_expf(__fsub_rn(v.y, mx));
             e[4 * q + 2] = v_expf(__fsub_rn(v.z, mx)); e[4 * q + 3] = v_expf(__fsub_rn(v.w, mx));
-            r4[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+            r4[(q + rot) & 3] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
         }
         part += (double) reduce_add16_regs(e);
     }
@@ -1241,9 +1289,9 @@ __global__ void __launch_bounds__(GQA * PVS_TH) k_attn_softmax_pv(const AttnArgs
         float4 * r4 = reinterpret_cast<float4 *>(row + 16 * gi);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            float4 v = r4[q];
+            float4 v = r4[(q + rot) & 3];
             v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv); v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
-            r4[q] = v;
+            r4[(q + rot) & 3] = v;
         }
     }
     __syncthreads();                                           // all rows normalised, every thread's V copies landed

@@ -24,8 +24,13 @@ tot = {}
 for i in range(len(st)):
     kind, ctas = int(meta[i, 0]), int(meta[i, 1])
     s = st[i, :ctas, :].astype(np.int64)
-    nph = 3 if kind == 2 else 5
-    s = s[s[:, nph - 1] > 0]                     # CTAs that exited early (beyond n_kv) have no end stamp
+    # phase columns in time order: matvec 0 start,1 ring part-filled,2 after wait,5 x consumed,6 norm scale,3 prologue done,4 end
+    order = [0, 1, 2] if kind == 2 else ([0, 1, 2, 3, 4] if kind == 7 else [0, 1, 2, 5, 6, 3, 4])
+    nph = len(order)
+    s = s[s[:, order[-1]] > 0]                   # CTAs that exited early (beyond n_kv) have no end stamp
+    s = s[:, order]
+    for p in range(1, nph):                      # phases a kernel variant does not stamp: carry the previous one
+        s[:, p] = np.where(s[:, p] > 0, s[:, p], s[:, p - 1])
     start = s[:, 0]
     end = s[:, nph - 1]
     if t_first is None:
