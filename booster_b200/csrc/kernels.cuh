@@ -108,7 +108,7 @@ __host__ __device__ __forceinline__ size_t chain_smem_bytes(int W, int G, int nv
 // every kernel: no global read of anything a kernel writes, and no global write at all, before pdl_wait().
 // ------------------------------------------------------------------------------------------------------------
 // optional phase trace (b200_trace_token): thread 0 of every CTA stamps %globaltimer into tr[cta][phase]
-static constexpr int TRACE_PHASES = 8;
+static constexpr int TRACE_PHASES = 12;
 __device__ __forceinline__ void trace_mark(unsigned long long * tr, int phase) {
     if (tr != nullptr && threadIdx.x == 0) {
         unsigned long long t;
@@ -586,6 +586,30 @@ __device__ __forceinline__ float finish_row(const float * c) {
     return h;
 }
 
+// Chain phase of one round (G > 1): this lane advances its CPW chain slots over the round's G tiles in order. Slot i
+// owns chain c = w + i*G of the lane's row: value at voff[i], multiplier (d for c < 8, dmin above) at moff[i] of a
+// tile's published record. Slots beyond the type's chain count point at valid words and accumulate garbage that is
+// never read, so the loop has no branches; q5tail marks the slot holding Q5_K's summs chain (add of a product, not
+// an fma: ggml-quants.c:7516).
+template <int CPW, bool Q5>
+__device__ __forceinline__ void chain_round(const float * rb, int G, int tile_stride, const int (&voff)[6], const int (&moff)[6],
+                                            int q5slot, float (&acc)[12]) {
+#pragma unroll 4
+    for (int ww = 0; ww < G; ww++) {
+        const float * tb = rb + (size_t) ww * tile_stride;
+#pragma unroll
+        for (int i = 0; i < CPW; i++) {
+            const float v = tb[voff[i]], m = tb[moff[i]];
+            if (Q5) {
+                const float f = __fmaf_rn(m, v, acc[i]), g = __fadd_rn(acc[i], __fmul_rn(m, v));
+                acc[i] = i == q5slot ? g : f;
+            } else {
+                acc[i] = __fmaf_rn(m, v, acc[i]);
+            }
+        }
+    }
+}
+
 // a work unit resolved against the launch's segments: type, first tile in HBM, first output row
 struct UnitDesc { int type; int row0; uint32_t bytes; const uint8_t * tiles; };
 __device__ __forceinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit) {
@@ -695,10 +719,20 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
         auto unit_body = [&](auto tag) {
             constexpr int TYPE = decltype(tag)::value;
             constexpr int NCH = n_chains<TYPE>();
-            constexpr int CPW = 6;                             // chains per warp when G > 1: ceil(12 / 2)
+            constexpr int CPW = 6;                             // chain slots per lane when G > 1: ceil(12 / 2)
             float acc[12];                                     // G == 1: the row's chains; G > 1: [0, CPW) = chains w, w+G, ...
 #pragma unroll
             for (int c = 0; c < 12; c++) acc[c] = 0.f;
+            // G > 1: slot i of this lane = chain w + i*G (value and multiplier offsets inside a tile's record)
+            int voff[6], moff[6], q5slot = -1;
+            const int cpw = G >= 12 ? 1 : G >= 6 ? 2 : G >= 4 ? 3 : 6;
+#pragma unroll
+            for (int i = 0; i < CPW; i++) {
+                const int c = w + i * G;
+                voff[i] = (c < NCH ? c : 0) * 32;
+                moff[i] = (c < 8 || c >= NCH ? NCH : NCH + 1) * 32;
+                if (TYPE == T_Q5_K && c == 8) q5slot = i;
+            }
             for (int k = 0; k < KPW; k++) {
                 const int t = w + G * k;
                 issue_next();                                  // keeps S-1 tiles in flight (slot of the previous item is free)
@@ -713,9 +747,11 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
                     }
                 }
                 mbar_wait(full0 + 8 * cs, (uint32_t) cpar);
+                if (j == 0 && k == 0) trace_mark(a.trace, 7);  // first tile landed
                 BlockInts bi;
                 tile_ints<TYPE>(ring + (size_t) cs * a.stage_bytes, lane, t, A, bi);
                 __syncwarp();                                  // every lane is done reading the slot before it is refilled
+                if (j == 0 && k == 0) trace_mark(a.trace, 8);  // first tile's integers done
                 cs = cs + 1 == S ? 0 : cs + 1; if (cs == 0) cpar ^= 1;
                 float val;
                 if (G == 1) {
@@ -747,19 +783,14 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
                     // ---- chain phase of the round: tiles t0 .. t0+G-1 in order, this lane's chains c = w + i*G
                     const float * rb = cbuf + ((size_t) ((rnd & 1) * W + grp * G) * NV) * 32 + lane;
                     rnd++;
-#pragma unroll 4
-                    for (int ww = 0; ww < G; ww++) {
-                        const float * tb = rb + (size_t) ww * NV * 32;
-#pragma unroll
-                        for (int i = 0; i < CPW; i++) {
-                            const int c = w + i * G;
-                            if (c < 8) acc[i] = __fmaf_rn(tb[NCH * 32], tb[c * 32], acc[i]);
-                            else if (c < NCH) {
-                                if (TYPE == T_Q4_K) acc[i] = __fmaf_rn(tb[(NCH + 1) * 32], tb[c * 32], acc[i]);
-                                else                acc[i] = __fadd_rn(acc[i], __fmul_rn(tb[(NCH + 1) * 32], tb[c * 32]));
-                            }
-                        }
+                    if (j == 0 && k == 0) trace_mark(a.trace, 9);   // first round: every warp's integers published
+                    switch (cpw) {
+                        case 1:  chain_round<1, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
+                        case 2:  chain_round<2, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
+                        case 3:  chain_round<3, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
+                        default: chain_round<6, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
                     }
+                    if (j == 0 && k == 0) trace_mark(a.trace, 11);  // first round's chains advanced
                     if (k != KPW - 1) continue;
                     // ---- unit complete: gather the row's chains
 #pragma unroll
@@ -806,6 +837,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
             default:     unit_body(TypeTag<T_Q8_0>{}); break;
         }
     }
+    trace_mark(a.trace, 10);                                   // warp 0 out of work
     if (a.trace != nullptr) { __syncthreads(); trace_mark(a.trace, 4); }
 }
 

@@ -112,9 +112,9 @@ class Context:
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(kinds)}
 
     def trace_token(self, token: int, pos: int, reps: int = 3):
-        """(stamps[n_launches, 512, 8] u64 ns, meta[n_launches, 2] = (kind, ctas)) of one graph-replayed token"""
+        """(stamps[n_launches, 512, 12] u64 ns, meta[n_launches, 2] = (kind, ctas)) of one graph-replayed token"""
         cap_l = 1024
-        out = np.zeros((cap_l, 512, 8), dtype=np.uint64)
+        out = np.zeros((cap_l, 512, 12), dtype=np.uint64)
         meta = np.zeros((cap_l, 2), dtype=np.int32)
         n = int(self.L.b200_trace_token(self.h, token, pos, reps, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size,
                                         meta.ctypes.data_as(C.POINTER(C.c_int32)), meta.size))

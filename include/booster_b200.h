@@ -93,7 +93,7 @@ float   b200_last_device_ms(const b200_ctx * c);
  * per-kernel roofline of bench.py */
 int     b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms_by_kind[8], int32_t n_by_kind[8]);
 /* one token through a graph whose kernels stamp %globaltimer (ns) at their phase boundaries (thread 0 of every CTA):
- * out = [n_launches][512 CTAs][8 phases] u64 (0 = not stamped), meta = [n_launches][2] = (kind, CTAs). Returns the
+ * out = [n_launches][512 CTAs][12 phases] u64 (0 = not stamped), meta = [n_launches][2] = (kind, CTAs). Returns the
  * number of launches traced (-1 on error). Diagnostic companion of b200_profile_token: shows launch gaps, PDL overlap
  * and prologue/main-loop split inside the replayed graph, which ncu's serialised replays cannot. */
 int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int reps, uint64_t * out, int64_t cap_words,

@@ -11,8 +11,10 @@ if [ -z "$SKIP_TESTS" ]; then
   ( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1
   tail -5 $OUT/pytest_gpu.log
 fi
-( time timeout 900 python bench.py ) > $OUT/bench.json 2> $OUT/bench.err
-cat $OUT/bench.json
+if [ -z "$SKIP_BENCH" ]; then
+  ( time timeout 900 python bench.py $BENCH_ARGS ) > $OUT/bench.json 2> $OUT/bench.err
+  cat $OUT/bench.json
+fi
 if [ -z "$SKIP_TRACE" ]; then
   timeout 300 python scripts/trace_token.py 2000 $OUT/trace_token.txt > $OUT/trace_head.txt 2>&1; head -12 $OUT/trace_head.txt
 fi
