@@ -500,10 +500,10 @@ static unsigned long long * trace_slot(b200_ctx * c, int ctas) {
     return c->d_trace + (size_t) (c->trace_seq++) * TRACE_CTAS * TRACE_PHASES;
 }
 
-template <int EPI>
-static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
+static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     ProfScope ps(c);
     MatvecArgs a = a_in;
+    a.epi = epi;
     a.tiles_unit = a.seg[0].tiles_unit;
     for (int i = 0; i < a.n_seg; i++)
         if (a.seg[i].tiles_unit != a.tiles_unit) throw std::runtime_error("segments of one launch must share the unit shape");
@@ -524,6 +524,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
             if (W % G) continue;
             if (G > 1 && (long long) a.n_units * G > (long long) c->sm_count * W) continue;   // sharing only within one wave
             if (a.tiles_unit % G) continue;                                                   // warp w owns tiles w, w+G, ... of every unit
+            if (a.norm_w != nullptr && a.k / 256 > PRO_U * W) continue;                       // the normed vector is quantized in one pass
             const size_t fixed = act_bytes + chain_smem_bytes(W, G, nv) + (size_t) W * 4 * 8;
             if (fixed + (size_t) W * 2 * a.stage_bytes > budget) continue;
             const int S = (int) std::min<size_t>(4, (budget - fixed) / ((size_t) W * a.stage_bytes));
@@ -543,10 +544,10 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in) {
     const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(W, a.group, nv) + (size_t) W * a.stages * 8;
     static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
-    if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }
+    if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }
     const int grid = std::max(1, std::min(a.n_units, c->sm_count));
     a.trace = trace_slot(c, grid);
-    launch_fwd(k_matvec<EPI>, dim3((unsigned) grid), dim3((unsigned) (W * 32)), smem, c->st, a);
+    launch_fwd(k_matvec, dim3((unsigned) grid), dim3((unsigned) (W * 32)), smem, c->st, a);
     c->launches++;
 }
 
@@ -672,7 +673,7 @@ static void enqueue_forward(b200_ctx * c) {
             a.x = c->x; a.norm_w = L.attn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
             a.q_out = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
             a.n_q = QD; a.n_k = KVD; a.head_dim = HD; a.kv_dim = KVD; a.rope = c->rope; a.st = c->d_state;
-            launch_matvec<EPI_QKV>(c, a);
+            launch_matvec(c, a, EPI_QKV);
             tap(c, "Qcur", il, c->q, (size_t) QD);
         }
         {   // attention
@@ -692,7 +693,7 @@ static void enqueue_forward(b200_ctx * c) {
             a.seg[0] = L.wo.m; a.n_seg = 1; a.n_units = L.wo.m.n_units; a.k = QD;
             a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = q80;
             a.out = c->x; a.resid = c->x;
-            launch_matvec<EPI_RESID>(c, a);
+            launch_matvec(c, a, EPI_RESID);
             tap(c, "ffn_inp", il, c->x, (size_t) E);
         }
         {   // gate/up (interleaved virtual matrix) + SiLU*mul
@@ -701,7 +702,7 @@ static void enqueue_forward(b200_ctx * c) {
             a.seg[0] = L.gateup.m; a.n_seg = 1; a.n_units = L.gateup.m.n_units; a.k = E;
             a.x = c->x; a.norm_w = L.ffn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
             a.out = c->ffh;
-            launch_matvec<EPI_SILU>(c, a);
+            launch_matvec(c, a, EPI_SILU);
             tap(c, "ffn_gate_par", il, c->ffh, (size_t) FF);
         }
         {   // down + residual
@@ -710,7 +711,7 @@ static void enqueue_forward(b200_ctx * c) {
             a.seg[0] = L.down.m; a.n_seg = 1; a.n_units = L.down.m.n_units; a.k = FF;
             a.x = c->ffh; a.norm_w = nullptr; a.act_q8_0 = q80;
             a.out = c->x; a.resid = c->x;
-            launch_matvec<EPI_RESID>(c, a);
+            launch_matvec(c, a, EPI_RESID);
             tap(c, "l_out", il, c->x, (size_t) E);
         }
     }
@@ -720,7 +721,7 @@ static void enqueue_forward(b200_ctx * c) {
         a.seg[0] = m.output.m; a.n_seg = 1; a.n_units = m.output.m.n_units; a.k = E;
         a.x = c->x; a.norm_w = m.output_norm; a.eps = m.rms_eps; a.act_q8_0 = m.output.m.type == T_Q8_0;
         a.out = c->logits;
-        launch_matvec<EPI_STORE>(c, a);
+        launch_matvec(c, a, EPI_STORE);
         tap(c, "result_output", -1, c->logits, (size_t) m.n_vocab);
     }
 }
@@ -1190,7 +1191,7 @@ extern "C" int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int
         MatvecArgs a{};
         a.seg[0] = d.m; a.n_seg = 1; a.n_units = d.m.n_units; a.k = (int) k;
         a.x = dx.as<float>(); a.norm_w = nullptr; a.act_q8_0 = type == T_Q8_0; a.out = dy.as<float>();
-        launch_matvec<EPI_STORE>(&tmp, a);
+        launch_matvec(&tmp, a, EPI_STORE);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(y, dy.p, (size_t) n_rows * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -77,6 +77,7 @@ struct MatvecArgs {
     int stage_bytes;           // ring slot size = largest tile of the launch, 128-byte multiple
     int prefill;               // tiles per warp requested before griddepcontrol.wait (the rest follow the x loads)
     int nv;                    // chain values per tile (largest chain_values_of over the segments)
+    int epi;                   // EPI_*: ONE kernel serves every mat-vec of the layer, so its code stays in the instruction cache
     // epilogue
     float * out;
     const float * resid;
@@ -109,12 +110,15 @@ __host__ __device__ __forceinline__ size_t chain_smem_bytes(int W, int G, int nv
 // ------------------------------------------------------------------------------------------------------------
 // optional phase trace (b200_trace_token): thread 0 of every CTA stamps %globaltimer into tr[cta][phase]
 static constexpr int TRACE_PHASES = 12;
-__device__ __forceinline__ void trace_mark(unsigned long long * tr, int phase) {
-    if (tr != nullptr && threadIdx.x == 0) {
+__device__ __noinline__ void trace_stamp(unsigned long long * tr, int phase) {
+    {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         tr[(size_t) (blockIdx.y * gridDim.x + blockIdx.x) * TRACE_PHASES + phase] = t;
     }
+}
+__device__ __forceinline__ void trace_mark(unsigned long long * tr, int phase) {
+    if (tr != nullptr && threadIdx.x == 0) trace_stamp(tr, phase);
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -220,7 +224,10 @@ __device__ __forceinline__ ActSmem act_smem_carve(uint8_t * base, int k, int act
 // One warp quantizes 256 consecutive values (8 per lane) to Q8_K — quantize_row_q8_K_ref
 // (cpp/ggml/src/ggml-quants.c:3593-3630): `max` is the FIRST element of largest magnitude, iscale = -127/max,
 // q = min(127, round_half_even(iscale*x)), d = 1/iscale.
-__device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, int b, const ActSmem & A) {
+// (__noinline__ + by-value operands: ONE copy of this code in the kernel — these short kernels run with a cold
+// instruction cache, so code bytes are time; see DESIGN.md "instruction footprint")
+__device__ __noinline__ void q8k_block_warp(float4 va, float4 vb, int lane, int b, ActSmem A) {
+    const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
     float amax = 0.f, mval = 0.f;
     int   midx = 0;
 #pragma unroll
@@ -259,7 +266,8 @@ __device__ __forceinline__ void q8k_block_warp(const float (&v)[8], int lane, in
 }
 // One warp quantizes 256 consecutive values = 8 Q8_0 blocks of 32 — AVX path of quantize_row_q8_0
 // (cpp/ggml/src/ggml-quants.c:936-1000): d = amax/127 kept as fp16, id = 127/amax, q = round_half_even(x*id).
-__device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, int b256, const ActSmem & A) {
+__device__ __noinline__ void q80_blocks_warp(float4 va, float4 vb, int lane, int b256, ActSmem A) {
+    const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
     float amax = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
@@ -278,6 +286,11 @@ __device__ __forceinline__ void q80_blocks_warp(const float (&v)[8], int lane, i
     if ((lane & 3) == 0) A.dx[b256 * 8 + (lane >> 2)] = __half2float(__float2half_rn(d));
 }
 
+__device__ __forceinline__ void quantize_block(const float (&v)[8], int act_q8_0, int lane, int b, const ActSmem & A) {
+    const float4 va = make_float4(v[0], v[1], v[2], v[3]), vb = make_float4(v[4], v[5], v[6], v[7]);
+    if (act_q8_0) q80_blocks_warp(va, vb, lane, b, A);
+    else          q8k_block_warp(va, vb, lane, b, A);
+}
 __device__ __forceinline__ void load8(const float * p, float (&v)[8]) {
     const float4 a0 = *reinterpret_cast<const float4 *>(p), a1 = *reinterpret_cast<const float4 *>(p + 4);
     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
@@ -290,103 +303,65 @@ __device__ __forceinline__ void ldg8(const float * p, float (&v)[8]) {
 // Block-cooperative prologue: optional RMSNorm(+weight) then activation quantization into shared memory.
 // RMSNorm = ggml_compute_forward_rms_norm_f32 (double sum of float x*x, scale = 1/sqrtf(mean+eps), y = x*scale)
 // followed by the separate ggml_mul with the norm weight (cpp/src/llama.cpp:7928-7958).
-// Warp w owns blocks w, w+W, ... ; PRO_U of them are handled per pass with all their loads issued up front.
-// `pre_w` (fast norm path): the caller already fetched the warp's norm weights (constants: before griddepcontrol.wait).
-// `after_loads` runs once, right after the first pass' x loads are in flight (the caller tops up its weight ring
-// there: the x loads must not queue behind those bulk copies).
+// Warp w owns blocks w, w+W, ... ; PRO_U of them are handled per pass with all their loads issued up front. With a
+// norm the whole vector must fit ONE pass (k/256 <= PRO_U * W; the host checks), so x is read once and a single
+// load latency sits in front of the mat-vec; `pre_w` then holds the warp's norm weights, fetched by the caller
+// before griddepcontrol.wait (they are constants). `after_loads` runs once, right after the first pass' x loads are
+// in flight (the caller tops up its weight ring there: the x loads must not queue behind those bulk copies).
 static constexpr int PRO_U = 4;
+__device__ __noinline__ float rms_scale(double tot, int k, float eps) {
+    const float mean = (float) (tot / (double) k);
+    return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+}
 template <typename F>
-__device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, const float * __restrict__ norm_w,
-                                                  float eps, int k, int act_q8_0, const ActSmem & A, double * red,
-                                                  const float (&pre_w)[2][8], bool fast_norm, F after_loads,
+__device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, bool norm, float eps, int k, int act_q8_0,
+                                                  const ActSmem & A, double * red, const float (&pre_w)[PRO_U][8], F after_loads,
                                                   unsigned long long * tr = nullptr) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarp = blockDim.x >> 5;
     const int n256 = k / 256;
-    if (fast_norm) {
-        // single pass (n256 <= 2 * nwarp): x is read once, only one load latency sits in front of the mat-vec
-        float v[2][8];
-        double s = 0.0;
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int b = warp + u * nwarp;
-            if (b < n256) load8(x + b * 256 + lane * 8, v[u]);
-        }
-        after_loads();
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int b = warp + u * nwarp;
-            if (b < n256) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) s += (double) __fmul_rn(v[u][i], v[u][i]);
-            }
-        }
-        s = warp_sum_d(s);
-        if (lane == 0) red[warp] = s;
-        trace_mark(tr, 5);
-        __syncthreads();
-        double tot = 0.0;
-        for (int w = 0; w < nwarp; w++) tot += red[w];
-        const float mean = (float) (tot / (double) k);
-        const float sc = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
-        trace_mark(tr, 6);
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int b = warp + u * nwarp;
-            if (b < n256) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], sc), pre_w[u][i]);
-                if (act_q8_0) q80_blocks_warp(v[u], lane, b, A);
-                else          q8k_block_warp(v[u], lane, b, A);
-            }
-        }
-        return;
-    }
-    float scale = 1.f;
-    bool ran_after = false;
-    if (norm_w != nullptr) {
-        double s = 0.0;
-        for (int i = tid * 4; i < k; i += blockDim.x * 4) {
-            const float4 v = *reinterpret_cast<const float4 *>(x + i);
-            s += (double) __fmul_rn(v.x, v.x);
-            s += (double) __fmul_rn(v.y, v.y);
-            s += (double) __fmul_rn(v.z, v.z);
-            s += (double) __fmul_rn(v.w, v.w);
-        }
-        after_loads(); ran_after = true;
-        s = warp_sum_d(s);
-        if (lane == 0) red[warp] = s;
-        __syncthreads();
-        double tot = 0.0;
-        for (int w = 0; w < nwarp; w++) tot += red[w];
-        const float mean = (float) (tot / (double) k);
-        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
-    }
-    for (int b0 = warp; b0 < n256; b0 += PRO_U * nwarp) {
+    bool first = true;
+    for (int b0 = warp; b0 < n256 || first; b0 += PRO_U * nwarp) {
         float v[PRO_U][8];
 #pragma unroll
         for (int u = 0; u < PRO_U; u++) {
             const int b = b0 + u * nwarp;
             if (b < n256) load8(x + b * 256 + lane * 8, v[u]);
         }
-        if (!ran_after) { after_loads(); ran_after = true; }
+        if (first) after_loads();
+        float scale = 1.f;
+        if (norm && first) {
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < PRO_U; u++) {
+                const int b = b0 + u * nwarp;
+                if (b < n256) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) s += (double) __fmul_rn(v[u][i], v[u][i]);
+                }
+            }
+            s = warp_sum_d(s);
+            if (lane == 0) red[warp] = s;
+            trace_mark(tr, 5);
+            __syncthreads();
+            double tot = 0.0;
+            for (int w = 0; w < nwarp; w++) tot += red[w];
+            scale = rms_scale(tot, k, eps);
+            trace_mark(tr, 6);
+        }
+        first = false;
 #pragma unroll
         for (int u = 0; u < PRO_U; u++) {
             const int b = b0 + u * nwarp;
             if (b < n256) {
-                if (u == 1 && b0 == warp) trace_mark(tr, 5);       // first block of the warp quantized
-                if (norm_w != nullptr) {
-                    float ww[8];
-                    ldg8(norm_w + b * 256 + lane * 8, ww);
+                if (norm) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], scale), ww[i]);
+                    for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], scale), pre_w[u][i]);
                 }
-                if (act_q8_0) q80_blocks_warp(v[u], lane, b, A);
-                else          q8k_block_warp(v[u], lane, b, A);
+                quantize_block(v[u], act_q8_0, lane, b, A);
             }
         }
     }
-    if (!ran_after) after_loads();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -458,7 +433,8 @@ __device__ __forceinline__ int4 act16(const int8_t * ab, int slot) { return *rei
 template <int TYPE> struct TypeTag { static constexpr int value = TYPE; };
 template <int TYPE> __device__ __forceinline__ constexpr int n_chains() { return TYPE == T_Q4_K ? 12 : TYPE == T_Q5_K ? 9 : 8; }
 
-// `sl` = the tile in shared memory + lane*16
+// `sl` = the tile in shared memory + lane*16. The loops over the four 64-weight groups are deliberately NOT unrolled
+// (instruction footprint): their accumulators are indexed by (h, wi) only.
 template <bool Q5>
 __device__ __forceinline__ void ints_q45k(const uint8_t * sl, const int8_t * ab, const int * bp, float yd, BlockInts & o) {
     const uint4 sd = lds_u4(sl + 4096);
@@ -467,8 +443,6 @@ __device__ __forceinline__ void ints_q45k(const uint8_t * sl, const int8_t * ab,
     const uint32_t sc_a = s0 & 0x3f3f3f3fu, m_a = s1 & 0x3f3f3f3fu;
     const uint32_t sc_b = (s2 & 0x0f0f0f0fu) | ((s0 >> 2) & 0x30303030u);
     const uint32_t m_b  = ((s2 >> 4) & 0x0f0f0f0fu) | ((s1 >> 2) & 0x30303030u);
-    const int sc[8] = { byte_of<0>(sc_a), byte_of<1>(sc_a), byte_of<2>(sc_a), byte_of<3>(sc_a),
-                        byte_of<0>(sc_b), byte_of<1>(sc_b), byte_of<2>(sc_b), byte_of<3>(sc_b) };
     uint4 qh[2];
     if (Q5) { qh[0] = lds_u4(sl + 4608); qh[1] = lds_u4(sl + 4608 + 512); }
     // s = s_lo + (s_hi16 >> 4): the high nibbles are multiplied IN PLACE (mask 0xf0 = 16 x value, unsigned dp4a);
@@ -476,13 +450,17 @@ __device__ __forceinline__ void ints_q45k(const uint8_t * sl, const int8_t * ab,
     int s_lo[8], s_hi[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { s_lo[i] = 0; s_hi[i] = 0; }
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 4; j++) {
-        const int sc_lo = sc[2 * j], sc_hi = sc[2 * j + 1];
+        const uint32_t scw = (j & 2) ? sc_b : sc_a;
+        const int sh = (j & 1) * 16;
+        const int sc_lo = (int) ((scw >> sh) & 0xffu), sc_hi = (int) ((scw >> (sh + 8)) & 0xffu);
+        const uint8_t * q = sl + j * 1024;
+        const int8_t * aj = ab + j * 64;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const uint4 w = lds_u4(sl + (2 * j + h) * 512);
-            const int4 alo = act16(ab, 4 * j + h), ahi = act16(ab, 4 * j + 2 + h);
+            const uint4 w = lds_u4(q + h * 512);
+            const int4 alo = *reinterpret_cast<const int4 *>(aj + h * 16), ahi = *reinterpret_cast<const int4 *>(aj + 32 + h * 16);
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
                 const uint32_t W = word_of(w, wi);
@@ -491,9 +469,9 @@ __device__ __forceinline__ void ints_q45k(const uint8_t * sl, const int8_t * ab,
                     s_hi[4 * h + wi] += sc_hi * dp4a_us(W & 0xf0f0f0f0u, word_of(ahi, wi), 0);
                 } else {
                     // qh bit 2j -> +16 on the low-nibble weight, bit 2j+1 -> +16 on the high-nibble one
-                    const uint32_t H = word_of(qh[h], wi);
-                    const uint32_t lo = (W & 0x0f0f0f0fu) | (((H >> (2 * j)) & 0x01010101u) << 4);
-                    const uint32_t hi = ((W >> 4) & 0x0f0f0f0fu) | (((H >> (2 * j + 1)) & 0x01010101u) << 4);
+                    const uint32_t H = word_of(qh[h], wi) >> (2 * j);
+                    const uint32_t lo = (W & 0x0f0f0f0fu) | ((H & 0x01010101u) << 4);
+                    const uint32_t hi = ((W >> 4) & 0x0f0f0f0fu) | (((H >> 1) & 0x01010101u) << 4);
                     s_lo[4 * h + wi] += sc_lo * __dp4a((int) lo, word_of(alo, wi), 0);
                     s_hi[4 * h + wi] += 16 * sc_hi * __dp4a((int) hi, word_of(ahi, wi), 0);
                 }
@@ -514,7 +492,8 @@ __device__ __forceinline__ void ints_q45k(const uint8_t * sl, const int8_t * ab,
 }
 
 // Q6_K: the weight is q - 32 with q in 0..63; sum (q - 32) a = dp4a_u8(q, a) - 32 * sum(a), and the second term
-// (per 32-bit word of the activation block) comes pre-computed from the prologue as the accumulator input of dp4a
+// (per 32-bit word of the activation block) comes pre-computed from the prologue as the accumulator input of dp4a.
+// The loop over (half n, 16-byte column mq) is not unrolled; the four groups g inside it are.
 __device__ __forceinline__ void ints_q6k(const uint8_t * sl, const uint8_t * tile, int lane, const int8_t * ab, const int * asb,
                                          float yd, BlockInts & o) {
     const uint4 scv = lds_u4(sl + 4096);
@@ -522,11 +501,15 @@ __device__ __forceinline__ void ints_q6k(const uint8_t * sl, const uint8_t * til
     for (int i = 0; i < 8; i++) o.s[i] = 0;
     // layout of a super-block: dequantize_row_q6_K (cpp/ggml/src/ggml-quants.c:2970-3000); half n, group g of 32
     // weights: ql byte 64n + 32(g&1) + l, nibble g>>1; qh byte 32n + l, bits 2g..2g+1; scale 8n + 2g + l/16
-#pragma unroll
+#pragma unroll 1
     for (int n = 0; n < 2; n++) {
-#pragma unroll
+        // scales 8n .. 8n+7 = two words; scale of group g, column mq = byte 2g + mq of the pair
+        const uint32_t scw0 = n ? scv.z : scv.x, scw1 = n ? scv.w : scv.y;
+#pragma unroll 1
         for (int mq = 0; mq < 2; mq++) {
             const uint4 qh = lds_u4(sl + 4608 + (2 * n + mq) * 512);
+            const uint32_t sw0 = scw0 >> (8 * mq), sw1 = scw1 >> (8 * mq);
+            int part[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int gl = 0; gl < 2; gl++) {                      // one ql chunk serves groups gl (low nibble) and gl+2 (high)
                 const uint4 ql = lds_u4(sl + (4 * n + 2 * gl + mq) * 512);
@@ -534,7 +517,7 @@ __device__ __forceinline__ void ints_q6k(const uint8_t * sl, const uint8_t * til
                 for (int gh = 0; gh < 2; gh++) {
                     const int g = gl + 2 * gh;
                     const int si = 8 * n + 2 * g + mq;
-                    const int sc = (int) (int8_t) ((word_of(scv, si >> 2) >> ((si & 3) * 8)) & 0xff);
+                    const int sc = (int) (int8_t) (((g >> 1) ? sw1 : sw0) >> (16 * (g & 1)));
                     const int4 a = act16(ab, si);
                     const int4 c32 = *reinterpret_cast<const int4 *>(asb + 4 * si);
 #pragma unroll
@@ -543,10 +526,13 @@ __device__ __forceinline__ void ints_q6k(const uint8_t * sl, const uint8_t * til
                         const uint32_t lo = gh ? ((QL >> 4) & 0x0f0f0f0fu) : (QL & 0x0f0f0f0fu);
                         const uint32_t h2 = g == 0 ? (QH << 4) : g == 1 ? (QH << 2) : g == 2 ? QH : (QH >> 2);
                         const uint32_t q  = lo | (h2 & 0x30303030u);
-                        o.s[4 * mq + wi] += sc * dp4a_us(q, word_of(a, wi), word_of(c32, wi));
+                        part[wi] += sc * dp4a_us(q, word_of(a, wi), word_of(c32, wi));
                     }
                 }
             }
+            // o.s[4 mq + wi] += part[wi] without a dynamically indexed register array
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) { if (mq == 0) o.s[wi] += part[wi]; else o.s[4 + wi] += part[wi]; }
         }
     }
     const float dw = __half2float(*reinterpret_cast<const __half *>(tile + 6656 + lane * 2));
@@ -594,7 +580,7 @@ __device__ __forceinline__ float finish_row(const float * c) {
 template <int CPW, bool Q5>
 __device__ __forceinline__ void chain_round(const float * rb, int G, int tile_stride, const int (&voff)[6], const int (&moff)[6],
                                             int q5slot, float (&acc)[12]) {
-#pragma unroll 4
+#pragma unroll 1
     for (int ww = 0; ww < G; ww++) {
         const float * tb = rb + (size_t) ww * tile_stride;
 #pragma unroll
@@ -612,7 +598,7 @@ __device__ __forceinline__ void chain_round(const float * rb, int G, int tile_st
 
 // a work unit resolved against the launch's segments: type, first tile in HBM, first output row
 struct UnitDesc { int type; int row0; uint32_t bytes; const uint8_t * tiles; };
-__device__ __forceinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit) {
+__device__ __noinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit) {
     int si = 0, u = unit, row_base = 0;
     if (a.n_seg > 1 && u >= a.seg[0].n_units) { u -= a.seg[0].n_units; row_base += a.seg[0].n_rows; si = 1;
         if (a.n_seg > 2 && u >= a.seg[1].n_units) { u -= a.seg[1].n_units; row_base += a.seg[1].n_rows; si = 2; } }
@@ -636,8 +622,32 @@ __device__ __forceinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit
 // chains per unit). Nothing is serialised across warps any more; a chain step costs one LDS + one FMA.
 // The code of a unit is specialised on the unit's block type.
 // ------------------------------------------------------------------------------------------------------------
-template <int EPI>
-__global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArgs a) {
+// the row's epilogue (one call per unit; out of line: four block types share one copy)
+__device__ __noinline__ void matvec_epilogue(const MatvecArgs & a, float val, int row, int lane, float pre0, float pre1, int pos) {
+    const float oth = __shfl_xor_sync(0xffffffffu, val, 1);    // partner row (2i <-> 2i+1)
+    if (a.epi == EPI_STORE) {
+        a.out[row] = val;
+    } else if (a.epi == EPI_RESID) {
+        a.out[row] = __fadd_rn(val, pre0);                     // ggml_add(cur, inpSA / ffn_inp): llama.cpp:8865, 8901
+    } else if (a.epi == EPI_SILU) {
+        // rows (2r, 2r+1) = (gate r, up r): silu(gate) * up, cpp/src/llama.cpp:7960-8085
+        if ((lane & 1) == 0) a.out[row >> 1] = __fmul_rn(silu_exact(val), oth);
+    } else {  // EPI_QKV
+        const float v0 = (lane & 1) ? oth : val, v1 = (lane & 1) ? val : oth;   // (x0, x1) of this row's RoPE pair
+        if (row < a.n_q + a.n_k) {
+            // RoPE NORM mode on the pair (x0, x1): cpp/ggml/src/ggml.c:14121-14135
+            const float y = (lane & 1) ? __fadd_rn(__fmul_rn(v0, pre1), __fmul_rn(v1, pre0))
+                                       : __fsub_rn(__fmul_rn(v0, pre0), __fmul_rn(v1, pre1));
+            if (row < a.n_q) a.q_out[row] = y;
+            else a.k_cache[(size_t) pos * a.kv_dim + (row - a.n_q)] = __float2half_rn(y);   // K post-RoPE as f16: llama.cpp:7849-7853
+        } else {
+            a.v_cache[(size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)] = __float2half_rn(val);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_constant__ MatvecArgs a) {
+    const int EPI = a.epi;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ double red_smem[MV_MAX_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -692,12 +702,12 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
     // weights do not depend on x: part of the ring is filled before the wait, the rest once the x loads are in flight
     const int prefill = min(a.prefill, S - 1);
     for (int s = 0; s < prefill; s++) issue_next();
-    // norm weights are constants too: the warp's (at most two) blocks, fast single-pass norm only
-    const bool fast_norm = a.norm_w != nullptr && a.k / 256 <= 2 * W;
-    float ww[2][8] = {};
-    if (fast_norm) {
+    // norm weights are constants too: the warp's blocks (the host guarantees k/256 <= PRO_U * W when there is a norm)
+    const bool norm = a.norm_w != nullptr;
+    float ww[PRO_U][8] = {};
+    if (norm) {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < PRO_U; u++) {
             const int b = warp + u * W;
             if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, ww[u]);
         }
@@ -707,7 +717,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
     pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
     trace_mark(a.trace, 2);
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
-    prologue_quantize(a.x, a.norm_w, a.eps, a.k, a.act_q8_0, A, red_smem, ww, fast_norm,
+    prologue_quantize(a.x, norm, a.eps, a.k, a.act_q8_0, A, red_smem, ww,
                       [&]() { for (int s = prefill; s < S - 1; s++) issue_next(); }, a.trace);
     __syncthreads();                                           // activations + every warp's barrier inits are visible
     trace_mark(a.trace, 3);
@@ -806,28 +816,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const MatvecArg
                     val = finish_row<TYPE>(cv);
                 }
 
-                // ---- this lane's row
-                const float oth = __shfl_xor_sync(0xffffffffu, val, 1);    // partner row (2i <-> 2i+1)
-                const int row = cd.row0 + lane;
-                if (EPI == EPI_STORE) {
-                    a.out[row] = val;
-                } else if (EPI == EPI_RESID) {
-                    a.out[row] = __fadd_rn(val, pre0);             // ggml_add(cur, inpSA / ffn_inp): llama.cpp:8865, 8901
-                } else if (EPI == EPI_SILU) {
-                    // rows (2r, 2r+1) = (gate r, up r): silu(gate) * up, cpp/src/llama.cpp:7960-8085
-                    if ((lane & 1) == 0) a.out[row >> 1] = __fmul_rn(silu_exact(val), oth);
-                } else {  // EPI_QKV
-                    const float v0 = (lane & 1) ? oth : val, v1 = (lane & 1) ? val : oth;   // (x0, x1) of this row's RoPE pair
-                    if (row < a.n_q + a.n_k) {
-                        // RoPE NORM mode on the pair (x0, x1): cpp/ggml/src/ggml.c:14121-14135
-                        const float y = (lane & 1) ? __fadd_rn(__fmul_rn(v0, pre1), __fmul_rn(v1, pre0))
-                                                   : __fsub_rn(__fmul_rn(v0, pre0), __fmul_rn(v1, pre1));
-                        if (row < a.n_q) a.q_out[row] = y;
-                        else a.k_cache[(size_t) pos * a.kv_dim + (row - a.n_q)] = __float2half_rn(y);   // K post-RoPE as f16: llama.cpp:7849-7853
-                    } else {
-                        a.v_cache[(size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)] = __float2half_rn(val);
-                    }
-                }
+                matvec_epilogue(a, val, cd.row0 + lane, lane, pre0, pre1, pos);
             }
         };
         switch (cd.type) {
@@ -850,8 +839,8 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ double red_smem[MV_MAX_WARPS];
     const ActSmem A = act_smem_carve(smem_raw, k, act_q8_0);
-    const float no_w[2][8] = {};
-    prologue_quantize(x, nullptr, 0.f, k, act_q8_0, A, red_smem, no_w, false, []() {});
+    const float no_w[PRO_U][8] = {};
+    prologue_quantize(x, false, 0.f, k, act_q8_0, A, red_smem, no_w, []() {});
     __syncthreads();
     if (!act_q8_0) {
         const int nb = k / 256;
