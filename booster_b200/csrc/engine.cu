@@ -562,7 +562,6 @@ static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_p
     int vch = (int) ((budget - row_bytes) / 16) / PV_BATCH * PV_BATCH;
     vch = std::min(vch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
     a.p_chunk = vch;
-    a.fuse_softmax = 0;
     const size_t smem = row_bytes + (size_t) vch * 16;
     static size_t attr[64] = {0};
     const int dv = c->device & 63;
@@ -592,32 +591,27 @@ static bool attn_2k_enabled() {
 template <int GQA>
 static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
     if (attn_2k_enabled() && launch_attention_2k<GQA>(c, a_in, n_ctx_pad)) return;
+    // long-context route (the GQA score rows do not fit one CTA's shared memory): scores, softmax, chunked P.V
     AttnArgs a = a_in;
-    // P.V chunk: p rows (GQA x 4 B) + V rows (32 B) per position, up to ~200 KB of shared memory
     int pch = (200 * 1024) / (GQA * 4 + 32) / PV_BATCH * PV_BATCH;
     pch = std::min(pch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
     a.p_chunk = pch;
     const size_t pv_smem = (size_t) pch * (GQA * 4 + 32);
-    // fused softmax needs the GQA score rows in the shared memory of every scores CTA: only worth it (and only
-    // possible) for rows up to 64 KB; longer contexts run the stand-alone softmax kernel
-    a.fuse_softmax = (size_t) GQA * a.s_stride * 4 <= 64 * 1024;
-    const size_t sc_smem = a.fuse_softmax ? (size_t) GQA * a.s_stride * 4 : 0;
-    static size_t attr_pv[64] = {0}, attr_sc[64] = {0};   // per device (function attributes are per device)
+    static size_t attr_pv[64] = {0};   // per device (function attributes are per device)
     const int dv = c->device & 63;
     if (pv_smem > attr_pv[dv]) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_pv[dv] = pv_smem; }
-    if (sc_smem > attr_sc[dv]) { CU(cudaFuncSetAttribute(k_attn_scores<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc_smem)); attr_sc[dv] = sc_smem; }
     const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
     {
         g_kind = KIND_ATTN; ProfScope ps(c);
-        k_attn_scores<GQA><<<gs, ATT_THREADS, sc_smem, c->st>>>(a);    // + softmax in the last CTA of each KV head
-        if (!a.fuse_softmax) k_attn_softmax<<<a.n_head, 256, 0, c->st>>>(a);
+        launch_fwd(k_attn_scores<GQA>, gs, dim3(ATT_THREADS), 0, c->st, a);
+        k_attn_softmax<<<a.n_head, 256, 0, c->st>>>(a);
     }
     {
         g_kind = KIND_ATTN_PV; ProfScope ps(c);
         const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PV_DIMS));
         k_attn_pv<GQA><<<gp, PV_DIMS * 16, pv_smem, c->st>>>(a);
     }
-    c->launches += a.fuse_softmax ? 2 : 3;
+    c->launches += 3;
 }
 static void launch_attention(b200_ctx * c, const AttnArgs & a, int n_ctx_pad) {
     if (a.head_dim != 128) throw std::runtime_error("attention kernels are specialised for head_dim 128");
@@ -680,7 +674,7 @@ static void enqueue_forward(b200_ctx * c) {
             g_kind = KIND_ATTN;
             AttnArgs a{};
             a.q = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
-            a.S = c->S; a.s_stride = c->n_ctx; a.out = c->att; a.tickets = c->tickets;
+            a.S = c->S; a.s_stride = c->n_ctx; a.out = c->att;
             a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD;
             a.scale = 1.0f / sqrtf((float) HD);
             a.st = c->d_state; a.n_kv_override = 0; a.round_q_override = 0;
@@ -693,6 +687,10 @@ static void enqueue_forward(b200_ctx * c) {
             a.seg[0] = L.wo.m; a.n_seg = 1; a.n_units = L.wo.m.n_units; a.k = QD;
             a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = q80;
             a.out = c->x; a.resid = c->x;
+            static int dup = -1;   // diagnostic (BOOSTER_B200_DUP=1, tracing only): the wo launch twice in a row, the first into
+                                   // a scratch vector — does a kernel whose code was just executed start faster?
+            if (dup < 0) { const char * e = getenv("BOOSTER_B200_DUP"); dup = (e && e[0] == '1') ? 1 : 0; }
+            if (dup && c->tracing) { MatvecArgs d = a; d.out = c->ffh; launch_matvec(c, d, EPI_RESID); }
             launch_matvec(c, a, EPI_RESID);
             tap(c, "ffn_inp", il, c->x, (size_t) E);
         }
@@ -1255,7 +1253,7 @@ extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, cons
         CU(cudaMemcpyAsync(dv.p, v_cache, (size_t) n_kv * kvd * 2, cudaMemcpyHostToDevice, st));
         AttnArgs a{};
         a.q = dq.as<float>(); a.k_cache = dk.as<__half>(); a.v_cache = dv.as<__half>();
-        a.S = dS.as<float>(); a.s_stride = n_pad; a.out = dout.as<float>(); a.tickets = dT.as<unsigned int>();
+        a.S = dS.as<float>(); a.s_stride = n_pad; a.out = dout.as<float>();
         a.n_head = n_head; a.n_head_kv = n_head_kv; a.head_dim = head_dim; a.kv_dim = kvd;
         a.scale = scale; a.st = nullptr; a.n_kv_override = n_kv; a.round_q_override = round_q;
         launch_attention(&tmp, a, n_pad);

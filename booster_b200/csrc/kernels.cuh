@@ -150,6 +150,7 @@ __device__ __forceinline__ uint32_t word_of(const uint4 & v, int i) { return i =
 __device__ __forceinline__ int      word_of(const int4 & v, int i)  { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
 // ggml_v_expf, AVX-512 variant (cpp/ggml/src/ggml.c:2447-2472), one lane. All steps are element-wise IEEE ops.
+__device__ __noinline__ float scalef_slow(float j, int n) { return ldexpf(j, n); }   // sub-normal results: rare, out of line
 __device__ __forceinline__ float v_expf(float x) {
     const float r = 0x1.8p23f;
     const float z = __fmaf_rn(x, 0x1.715476p+0f, r);
@@ -165,7 +166,7 @@ __device__ __forceinline__ float v_expf(float x) {
     // and the scaling is an addition to the exponent field; the (very rare) sub-normal range goes through ldexpf.
     const int ni = (int) n;
     if (ni >= -125 && ni <= 125) return __int_as_float(__float_as_int(j) + (ni << 23));
-    return ldexpf(j, ni);
+    return scalef_slow(j, ni);
 }
 // _mm512_reduce_add_ps of 16 values held by one thread (same tree as reduce_add16_shfl)
 __device__ __forceinline__ float reduce_add16_regs(const float (&a)[16]) {
@@ -972,84 +973,55 @@ struct AttnArgs {
     const DecodeState * st;
     int n_kv_override;        // >0: use instead of st->pos+1 (operator-level test)
     int round_q_override;     // operator-level test of the batch>1 arithmetic
-    unsigned int * tickets;   // [n_head_kv] zero-initialised, self-resetting (last scores CTA of a KV head runs the softmax)
     int p_chunk;              // positions of p staged in shared memory by k_attn_pv (multiple of PV_BATCH)
-    int fuse_softmax;         // 1: the last scores CTA of a KV head normalises its rows; 0: k_attn_softmax follows
     unsigned long long * trace;
 };
 __device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1; }
 
-// soft_max_ext of one head row by `nw` cooperating warps (w = 0..nw-1) on a shared-memory copy `row` of the
-// scores; the normalised probabilities are written to S. See k_attn_softmax for the summation-order argument.
-__device__ __forceinline__ void softmax_row(float * row, float * S, int n_pad, int w, int nw, int lane, float * redf,
-                                            double * redd, int bar_id, int bar_threads) {
-    float mx = -INFINITY;
-    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) mx = fmaxf(mx, row[i]);
-    mx = warp_max(mx);
-    if (lane == 0) redf[w] = mx;
-    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
-    mx = redf[0];
-    for (int j = 1; j < nw; j++) mx = fmaxf(mx, redf[j]);
-    double part = 0.0;
-    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) {
-        const float p = v_expf(__fsub_rn(row[i], mx));
-        row[i] = p;
-        const float gs = reduce_add16_shfl(p);
-        if ((lane & 15) == 0) part += (double) gs;
-    }
-    part = warp_sum_d(part);
-    if (lane == 0) redd[w] = part;
-    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
-    double sum = 0.0;
-    for (int j = 0; j < nw; j++) sum += redd[j];
-    const float inv = (float) (1.0 / sum);
-    for (int i = w * 32 + lane; i < n_pad; i += nw * 32) S[i] = __fmul_rn(row[i], inv);   // own elements only
-}
-
 template <int GQA>
 __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     constexpr int HD = 128;
-    extern __shared__ __align__(16) float rows_dyn[];          // [GQA][s_stride] score rows, used by the last CTA only
     __shared__ __align__(16) float qs[GQA][HD];
-    __shared__ float redf[GQA][8];
-    __shared__ double redd[GQA][8];
-    __shared__ unsigned int s_ticket;
     const int g = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
     trace_mark(a.trace, 0);
+    const int n_kv = attn_n_kv(a);                            // DecodeState is written by the previous TOKEN's last kernel
+    const int n_pad = (n_kv + 31) / 32 * 32;
+    const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
+    // K rows of EARLIER positions were written by earlier tokens: their loads go out before griddepcontrol.wait
+    // (8 x 8-byte loads per lane in flight); only the row of the current position has to wait for the QKV kernel
+    uint2 kv[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) kv[s] = make_uint2(0u, 0u);
+    const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
+    if (t < n_kv - 1) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);            // 4 halfs at element 16s + 4c4
+    }
     pdl_wait();                                               // q and this token's K row come from the QKV kernel
     pdl_launch_dependents();                                  // AFTER the wait: the next kernel may touch K/V/q before ITS wait
     trace_mark(a.trace, 1);
-    const int n_kv = attn_n_kv(a);
-    const int n_pad = (n_kv + 31) / 32 * 32;
     if (tile * ATT_TILE >= n_pad) return;
     const int round_q = a.st ? a.st->round_q : a.round_q_override;
-    const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
-    // K first (it does not depend on q): 8 x 8-byte loads per lane in flight while q is fetched
-    float kf[8][4];
+    if (t == n_kv - 1) {
 #pragma unroll
-    for (int s = 0; s < 8; s++) { kf[s][0] = 0.f; kf[s][1] = 0.f; kf[s][2] = 0.f; kf[s][3] = 0.f; }
-    if (t < n_kv) {
-        const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
-        uint2 kv[8];
-#pragma unroll
-        for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);        // 4 halfs at element 16s + 4c4
-#pragma unroll
-        for (int s = 0; s < 8; s++) {
-            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].x));
-            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].y));
-            kf[s][0] = f0.x; kf[s][1] = f0.y; kf[s][2] = f1.x; kf[s][3] = f1.y;
-        }
+        for (int s = 0; s < 8; s++) kv[s] = kr[s * 4];                    // plain loads: written by the previous kernel
     }
     for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
         float v = a.q[(size_t) (g * GQA) * HD + i];
         if (round_q) v = __half2float(__float2half_rn(v));    // src1 converted to the vec_dot_type F16 (ggml.c:12345-12371)
         (&qs[0][0])[i] = v;
     }
+    float kf[8][4];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].y));
+        kf[s][0] = f0.x; kf[s][1] = f0.y; kf[s][2] = f1.x; kf[s][3] = f1.y;
+    }
     __syncthreads();
     if (t < n_pad) {                                          // n_pad % 32 == 0: whole warps take this branch together
-        float res[GQA];
-#pragma unroll
-        for (int h = 0; h < GQA; h++) {
+#pragma unroll 1
+        for (int h = 0; h < GQA; h++) {                       // rolled: instruction footprint
             float ch[4];
             if (!round_q) {
                 // tinyBLAS<16>: lane c: acc = fma(k[16s+c], q[16s+c], acc), s = 0..7
@@ -1082,37 +1054,11 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
             for (int e = 0; e < 4; e++) t3[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, ch[e], 2), ch[e]);   // a[8+i] + a[i] (valid in c4 = 0,1)
 #pragma unroll
             for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);   // t3[4+i] + t3[i] (valid in c4 = 0)
-            res[h] = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
-        }
-        if (c4 == 0) {
-#pragma unroll
-            for (int h = 0; h < GQA; h++)
-                a.S[(size_t) (g * GQA + h) * a.s_stride + t] = t < n_kv ? __fmul_rn(res[h], a.scale) : -INFINITY;
+            const float res = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
+            if (c4 == 0) a.S[(size_t) (g * GQA + h) * a.s_stride + t] = t < n_kv ? __fmul_rn(res, a.scale) : -INFINITY;
         }
     }
     trace_mark(a.trace, 2);
-    // ---- the last CTA of this KV head (atomic ticket) normalises the GQA rows: no separate softmax launch
-    if (!a.fuse_softmax) return;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&a.tickets[g], 1u);
-    __syncthreads();
-    const unsigned n_act = (unsigned) ((n_pad + ATT_TILE - 1) / ATT_TILE);
-    if (s_ticket != n_act - 1) return;
-    __threadfence();
-    if (tid == 0) a.tickets[g] = 0u;
-    // one memory round trip: the GQA score rows (written by the other CTAs of this KV head) -> shared memory
-    for (int i = tid; i < GQA * (n_pad / 4); i += ATT_THREADS) {
-        const int h = i / (n_pad / 4), j = i - h * (n_pad / 4);
-        cp_async16(rows_dyn + (size_t) h * a.s_stride + 4 * j, a.S + (size_t) (g * GQA + h) * a.s_stride + 4 * j);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    constexpr int NW = 8 / GQA;                               // warps per head (8 warps, GQA in {1,2,4,8})
-    const int warp = tid >> 5, lane = tid & 31, hl = warp / NW, w = warp % NW;
-    softmax_row(rows_dyn + (size_t) hl * a.s_stride, a.S + (size_t) (g * GQA + hl) * a.s_stride, n_pad, w, NW, lane,
-                redf[hl], redd[hl], 1 + hl, NW * 32);
 }
 
 __global__ void __launch_bounds__(256) k_attn_softmax(const AttnArgs a) {
