@@ -149,13 +149,75 @@ static DevMat upload_tiled(const HostTensor * src, int n_src, cudaStream_t st) {
     d.m.p0 = base;
     return d;
 }
+// n tensors with the same inner dimension stacked row-wise in ONE allocation; adjacent tensors of the same block type
+// form one segment (wq|wk always, wq|wk|wv when attn_v is not bumped to another type), so the kernel's unit lookup is
+// arithmetic on at most two segments
+struct DevStack {
+    void * alloc = nullptr;
+    size_t bytes = 0;          // algorithmic bytes
+    TMat seg[3];
+    int n_seg = 0;
+    int n_units = 0;
+};
+static DevStack upload_stack(const HostTensor * src, int n_src, cudaStream_t st) {
+    DevStack d;
+    const int64_t k = src[0].k;
+    size_t total = 0;
+    for (int i = 0; i < n_src; i++) {
+        if (src[i].k != k) throw std::runtime_error("stacked tensors must share the inner dimension");
+        if (src[i].rows % 32 != 0) throw std::runtime_error("row count is not a multiple of the work-unit height 32");
+        const int wpb = src[i].type == T_Q8_0 ? 32 : 256;
+        if (k % 256 != 0) throw std::runtime_error("matrix inner dimension must be a multiple of 256");
+        total += (size_t) tile_bytes_of(src[i].type) * (size_t) (src[i].rows / 32) * (size_t) (k / wpb);
+        if (i > 0 && ((src[i].type == T_Q8_0) != (src[0].type == T_Q8_0))) throw std::runtime_error("mixing Q8_0 and K-quant matrices inside one launch is not supported");
+    }
+    uint8_t * base = nullptr;
+    CU(cudaMalloc(&base, align_up(total, 256)));
+    d.alloc = base;
+    size_t off = 0;
+    for (int i = 0; i < n_src; i++) {
+        const int type = src[i].type;
+        int blk_bytes = 0, wpb = 256;
+        switch (type) {
+            case T_Q4_K: blk_bytes = 144; break;
+            case T_Q5_K: blk_bytes = 176; break;
+            case T_Q6_K: blk_bytes = 210; break;
+            case T_Q8_0: blk_bytes = 34; wpb = 32; break;
+            default: throw std::runtime_error("unsupported matrix type " + std::to_string(type) + " (supported: Q4_K, Q5_K, Q6_K, Q8_0)");
+        }
+        const int nb = (int) (k / wpb);
+        const size_t raw = (size_t) blk_bytes * nb * src[i].rows;
+        uint8_t * tmp = nullptr;
+        CU(cudaMalloc(&tmp, raw));
+        CU(cudaMemcpyAsync(tmp, src[i].data, raw, cudaMemcpyHostToDevice, st));
+        const int64_t n_blocks = src[i].rows * nb;
+        k_retile<<<(unsigned) ((n_blocks + 127) / 128), 128, 0, st>>>(type, tmp, src[i].rows, nb, 1, 0, base + off);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+        CU(cudaFree(tmp));
+        d.bytes += raw;
+        if (d.n_seg > 0 && d.seg[d.n_seg - 1].type == type) {
+            TMat & m = d.seg[d.n_seg - 1];
+            m.n_rows += (int) src[i].rows; m.n_units += (int) (src[i].rows / 32);
+        } else {
+            TMat & m = d.seg[d.n_seg++];
+            m.type = type; m.n_rows = (int) src[i].rows; m.nb = nb; m.rows_unit = 32; m.tiles_unit = nb;
+            m.n_units = (int) (src[i].rows / 32); m.tile_bytes = tile_bytes_of(type); m.p0 = base + off;
+        }
+        d.n_units += (int) (src[i].rows / 32);
+        off += (size_t) tile_bytes_of(type) * (size_t) (src[i].rows / 32) * nb;
+    }
+    return d;
+}
+
 static DevMat upload_matrix(int type, const void * host, int64_t n_rows, int64_t k, cudaStream_t st) {
     const HostTensor h{type, host, n_rows, k};
     return upload_tiled(&h, 1, st);
 }
 
 struct LayerW {
-    DevMat wq, wk, wv, wo, gateup, down;    // gateup = ffn_gate/ffn_up interleaved row by row
+    DevStack qkv;                           // attn_q | attn_k | attn_v stacked row-wise
+    DevMat wo, gateup, down;                // gateup = ffn_gate/ffn_up interleaved row by row
     float * attn_norm = nullptr;
     float * ffn_norm = nullptr;
 };
@@ -269,9 +331,18 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
             LayerW L;
             L.attn_norm = upload_f32(g.find(p + "attn_norm.weight"), E, st);
             L.ffn_norm  = upload_f32(g.find(p + "ffn_norm.weight"), E, st);
-            L.wq   = upload_named(g, p + "attn_q.weight", Q, E, st);
-            L.wk   = upload_named(g, p + "attn_k.weight", KV, E, st);
-            L.wv   = upload_named(g, p + "attn_v.weight", KV, E, st);
+            {
+                const char * nm[3] = { "attn_q.weight", "attn_k.weight", "attn_v.weight" };
+                const int64_t rows[3] = { Q, KV, KV };
+                HostTensor hs[3];
+                for (int i = 0; i < 3; i++) {
+                    const gguf_tensor * t = g.find(p + nm[i]);
+                    if (!t) throw std::runtime_error("missing tensor " + p + nm[i]);
+                    if ((int64_t) t->ne[0] != E || (int64_t) t->ne[1] != rows[i]) throw std::runtime_error("tensor " + p + nm[i] + " has an unexpected shape");
+                    hs[i] = HostTensor{(int) t->type, t->data, rows[i], E};
+                }
+                L.qkv = upload_stack(hs, 3, st);
+            }
             L.wo   = upload_named(g, p + "attn_output.weight", E, Q, st);
             {
                 const gguf_tensor * tg = g.find(p + "ffn_gate.weight"), * tu = g.find(p + "ffn_up.weight");
@@ -283,10 +354,10 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
                 L.gateup = upload_tiled(hs, 2, st);
             }
             L.down = upload_named(g, p + "ffn_down.weight", E, FF, st);
-            const bool q80 = L.wq.m.type == T_Q8_0;
-            for (const DevMat * d : { &L.wq, &L.wk, &L.wv, &L.wo, &L.gateup, &L.down })
+            const bool q80 = L.qkv.seg[0].type == T_Q8_0;
+            for (const DevMat * d : { &L.wo, &L.gateup, &L.down })
                 if ((d->m.type == T_Q8_0) != q80) throw std::runtime_error("mixing Q8_0 and K-quant matrices inside one layer is not supported");
-            wb += (int64_t) (L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.gateup.bytes + L.down.bytes) + 2 * (int64_t) E * 4;
+            wb += (int64_t) (L.qkv.bytes + L.wo.bytes + L.gateup.bytes + L.down.bytes) + 2 * (int64_t) E * 4;
             m->layers.push_back(L);
         }
         if (m->has_embd()) {
@@ -317,7 +388,8 @@ extern "C" void b200_model_free(b200_model * m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (auto & L : m->layers) {
-        for (DevMat * d : { &L.wq, &L.wk, &L.wv, &L.wo, &L.gateup, &L.down }) cudaFree(d->alloc);
+        cudaFree(L.qkv.alloc);
+        for (DevMat * d : { &L.wo, &L.gateup, &L.down }) cudaFree(d->alloc);
         cudaFree(L.attn_norm); cudaFree(L.ffn_norm);
     }
     cudaFree(m->embd_rows); cudaFree(m->output_norm); cudaFree(m->output.alloc);
@@ -525,7 +597,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
             if (G > 1 && (long long) a.n_units * G > (long long) c->sm_count * W) continue;   // sharing only within one wave
             if (a.tiles_unit % G) continue;                                                   // warp w owns tiles w, w+G, ... of every unit
             if (a.norm_w != nullptr && a.k / 256 > PRO_U * W) continue;                       // the normed vector is quantized in one pass
-            const size_t fixed = act_bytes + chain_smem_bytes(W, G, nv) + (size_t) W * 4 * 8;
+            const size_t fixed = act_bytes + chain_smem_bytes(W, G, nv) + (size_t) W * 4 * 8 + (size_t) W * 8;
             if (fixed + (size_t) W * 2 * a.stage_bytes > budget) continue;
             const int S = (int) std::min<size_t>(4, (budget - fixed) / ((size_t) W * a.stage_bytes));
             const long long warps = (long long) a.n_units * G, slots = (long long) c->sm_count * W;
@@ -541,7 +613,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     if (prefill_env < 0) { const char * e = getenv("BOOSTER_B200_PREFILL"); prefill_env = e ? atoi(e) : 1; }
     a.prefill = prefill_env;
     const int W = bestW;
-    const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(W, a.group, nv) + (size_t) W * a.stages * 8;
+    const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(W, a.group, nv) + (size_t) W * a.stages * 8 + (size_t) W * 8;
     static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
     if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }
@@ -576,7 +648,7 @@ static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_p
         g_kind = KIND_ATTN_PV; ProfScope ps(c);
         const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVS_DIMS));
         a.trace = trace_slot(c, (int) (gp.x * gp.y));
-        launch_fwd(k_attn_softmax_pv<GQA>, gp, dim3((unsigned) (GQA * PVS_TH)), smem, c->st, a);
+        launch_fwd(k_attn_softmax_pv<GQA>, gp, dim3((unsigned) (GQA * pvs_th(GQA))), smem, c->st, a);
     }
     c->launches += 2;
     return true;
@@ -658,12 +730,12 @@ static void enqueue_forward(b200_ctx * c) {
     for (int li = 0; li < (int) m.layers.size(); li++) {
         LayerW & L = m.layers[(size_t) li];
         const int il = m.layer_begin + li;
-        const int q80 = L.wq.m.type == T_Q8_0;
+        const int q80 = L.qkv.seg[0].type == T_Q8_0;
         {   // QKV
             g_kind = KIND_QKV;
             MatvecArgs a{};
-            a.seg[0] = L.wq.m; a.seg[1] = L.wk.m; a.seg[2] = L.wv.m; a.n_seg = 3;
-            a.n_units = L.wq.m.n_units + L.wk.m.n_units + L.wv.m.n_units; a.k = E;
+            for (int i = 0; i < L.qkv.n_seg; i++) a.seg[i] = L.qkv.seg[i];
+            a.n_seg = L.qkv.n_seg; a.n_units = L.qkv.n_units; a.k = E;
             a.x = c->x; a.norm_w = L.attn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
             a.q_out = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
             a.n_q = QD; a.n_k = KVD; a.head_dim = HD; a.kv_dim = KVD; a.rope = c->rope; a.st = c->d_state;

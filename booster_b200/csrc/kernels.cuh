@@ -97,8 +97,16 @@ static constexpr int HANDOFF_WORDS = 12 * 32;               // final chain value
 __host__ __device__ __forceinline__ int chain_values_of(int type) { return type == 12 ? 14 : type == 13 ? 11 : 9; }
 // shared memory of the chain exchange when G > 1: per warp a double-buffered slot of `nv` x 32 floats, per group the
 // final values
+// K-split modes: 0 = none (G == 1, chains in registers); 1 = hand-off (small G: the chain state walks from warp to warp
+// through a 1.5 KB buffer per group — the serial part is 12 FMAs per tile and the ring keeps its depth); 2 = exchange
+// (large G: integers published per round, chains advanced in parallel over (row, chain))
+enum { CHAIN_REGS = 0, CHAIN_HANDOFF = 1, CHAIN_EXCHANGE = 2 };
+__host__ __device__ __forceinline__ int chain_mode_of(int G) { return G == 1 ? CHAIN_REGS : G <= 4 ? CHAIN_HANDOFF : CHAIN_EXCHANGE; }
 __host__ __device__ __forceinline__ size_t chain_smem_bytes(int W, int G, int nv) {
-    return G > 1 ? (size_t) W * 2 * nv * 128 + (size_t) (W / G) * HANDOFF_WORDS * 4 : 0;
+    const int mode = chain_mode_of(G);
+    if (mode == CHAIN_REGS) return 0;
+    const size_t fin = (size_t) (W / G) * HANDOFF_WORDS * 4;
+    return mode == CHAIN_HANDOFF ? fin : (size_t) W * 2 * nv * 128 + fin;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -599,7 +607,7 @@ __device__ __forceinline__ void chain_round(const float * rb, int G, int tile_st
 
 // a work unit resolved against the launch's segments: type, first tile in HBM, first output row
 struct UnitDesc { int type; int row0; uint32_t bytes; const uint8_t * tiles; };
-__device__ __noinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit) {
+__device__ __forceinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit) {
     int si = 0, u = unit, row_base = 0;
     if (a.n_seg > 1 && u >= a.seg[0].n_units) { u -= a.seg[0].n_units; row_base += a.seg[0].n_rows; si = 1;
         if (a.n_seg > 2 && u >= a.seg[1].n_units) { u -= a.seg[1].n_units; row_base += a.seg[1].n_rows; si = 2; } }
@@ -660,22 +668,29 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
     const ActSmem A = act_smem_carve(act_base, a.k, a.act_q8_0);
     const int grp = warp / G, w = warp - grp * G;              // group inside the CTA, warp inside the group
     const int NV = a.nv;
-    // chain exchange (G > 1): cbuf[parity][warp of the CTA][value][lane] | fin[group][chain][lane]
+    const int mode = chain_mode_of(G);
+    // chain region: exchange: cbuf[parity][warp of the CTA][value][lane] | fin[group][chain][lane]; hand-off: fin only
     float * cbuf = reinterpret_cast<float *>(act_base + act_bytes);
-    float * fin  = cbuf + (size_t) W * 2 * NV * 32 + (size_t) grp * HANDOFF_WORDS;
+    float * fin  = cbuf + (mode == CHAIN_EXCHANGE ? (size_t) W * 2 * NV * 32 : 0) + (size_t) grp * HANDOFF_WORDS;
     uint64_t * bars = reinterpret_cast<uint64_t *>(act_base + act_bytes + chain_smem_bytes(W, G, NV));
     const uint32_t full0   = smem_u32(bars + warp * S);                            // my ring slots' "tile landed" barriers
+    const uint32_t edge_in  = smem_u32(bars + W * S + warp);                        // hand-off: "chain state for me is published"
+    const uint32_t edge_out = smem_u32(bars + W * S + grp * G + (w + 1 == G ? 0 : w + 1));
     const uint32_t ring_u32 = smem_u32(ring);
     const int bar_id = 1 + grp, bar_threads = G * 32;                              // the group's named barrier
 
     trace_mark(a.trace, 0);
     pdl_launch_dependents();                                   // the next kernel may start its own weight prefetch
-    if (lane == 0) {
-        for (int s = 0; s < S; s++) mbar_init(full0 + 8 * s, 1);
+    if (threadIdx.x == 0) {                                    // one thread, one fence: every barrier of the CTA
+        const uint32_t b0 = smem_u32(bars);
+#pragma unroll 1
+        for (int i = 0; i < W * S; i++) mbar_init(b0 + 8 * i, 1);
+#pragma unroll 1
+        for (int i = 0; i < W; i++) mbar_init(b0 + 8 * (W * S + i), 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncwarp();
+    __syncthreads();
 
     // group-major mapping: unit u -> CTA u % grid, group (u / grid) % groups_per_cta, so that launches with few
     // units spread over every SM
@@ -702,6 +717,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
     };
     // weights do not depend on x: part of the ring is filled before the wait, the rest once the x loads are in flight
     const int prefill = min(a.prefill, S - 1);
+#pragma unroll 1
     for (int s = 0; s < prefill; s++) issue_next();
     // norm weights are constants too: the warp's blocks (the host guarantees k/256 <= PRO_U * W when there is a norm)
     const bool norm = a.norm_w != nullptr;
@@ -719,12 +735,15 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
     trace_mark(a.trace, 2);
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
     prologue_quantize(a.x, norm, a.eps, a.k, a.act_q8_0, A, red_smem, ww,
-                      [&]() { for (int s = prefill; s < S - 1; s++) issue_next(); }, a.trace);
+                      [&]() {
+#pragma unroll 1
+                          for (int s = prefill; s < S - 1; s++) issue_next();
+                      }, a.trace);
     __syncthreads();                                           // activations + every warp's barrier inits are visible
     trace_mark(a.trace, 3);
 
     // ---- consumer side
-    int cs = 0, cpar = 0, rnd = 0;
+    int cs = 0, cpar = 0, rnd = 0, n_in = 0;
     for (int j = 0; j < my_units; j++) {
         const UnitDesc cd = describe_unit(a, group_global + j * n_groups);
         auto unit_body = [&](auto tag) {
@@ -765,7 +784,18 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
                 if (j == 0 && k == 0) trace_mark(a.trace, 8);  // first tile's integers done
                 cs = cs + 1 == S ? 0 : cs + 1; if (cs == 0) cpar ^= 1;
                 float val;
-                if (G == 1) {
+                if (mode != CHAIN_EXCHANGE) {
+                    if (mode == CHAIN_HANDOFF) {
+                        // the previous step of the group's tile sequence is done and its state published
+                        if (j > 0 || t > 0) { mbar_wait(edge_in, (uint32_t) (n_in & 1)); n_in++; }
+                        if (t > 0) {
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) acc[c] = fin[c * 32 + lane];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) acc[c] = 0.f;
+                        }
+                    }
                     // ---- chain step in registers, strictly in block order
 #pragma unroll
                     for (int c = 0; c < 8; c++) acc[c] = __fmaf_rn(bi.d, (float) bi.s[c], acc[c]);
@@ -774,6 +804,13 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
                         for (int l = 0; l < 4; l++) acc[8 + l] = __fmaf_rn(bi.dmin, (float) bi.p[l], acc[8 + l]);
                     } else if (TYPE == T_Q5_K) {
                         acc[8] = __fadd_rn(acc[8], __fmul_rn(bi.dmin, (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3])));
+                    }
+                    if (mode == CHAIN_HANDOFF && !(j == my_units - 1 && t == TU - 1)) {
+                        if (t != TU - 1) {
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) fin[c * 32 + lane] = acc[c];
+                        }
+                        mbar_arrive(edge_out);                 // release: my lane's stores above are visible to the waiter
                     }
                     if (t != TU - 1) continue;
                     val = finish_row<TYPE>(acc);
@@ -1163,15 +1200,18 @@ __global__ void __launch_bounds__(PV_DIMS * 16) k_attn_pv(const AttnArgs a) {
 // with exactly k_attn_softmax's arithmetic, on a shared-memory copy; then thread (h, c, dl) runs chain c of output
 // dim dl of head h. The CTA's V slice is independent of the scores and is put in flight BEFORE griddepcontrol.wait
 // (k_attn_scores waits for the QKV kernel before it lets this kernel launch, so K/V/q are already visible).
-//   grid (n_head_kv, HD / PVS_DIMS), block GQA * 64 threads (16 chains x 4 dim pairs per head); shared: ps [GQA][n_pad] f32 | vs [v_chunk][8] f16
+//   grid (n_head_kv, HD / PVS_DIMS), block GQA * pvs_th(GQA) threads (16 chains x dim groups per head); shared: ps [GQA][n_pad] f32 | vs [v_chunk][8] f16
 // ------------------------------------------------------------------------------------------------------------
 static constexpr int PVS_DIMS = 8;            // dims per CTA: 8 halfs = one 16-byte cp.async per position
-static constexpr int PVS_TH   = 16 * (PVS_DIMS / 2);   // threads per head: 16 chains x 4 dim pairs
+// dims per thread: 1 (128 threads per head) up to GQA 4, 2 (64 threads per head) for GQA 8 — at most 512 threads
+__host__ __device__ constexpr int pvs_dpt(int gqa) { return gqa >= 8 ? 2 : 1; }
+__host__ __device__ constexpr int pvs_th(int gqa) { return 16 * (PVS_DIMS / pvs_dpt(gqa)); }
 
 template <int GQA>
-__global__ void __launch_bounds__(GQA * PVS_TH) k_attn_softmax_pv(const AttnArgs a) {
+__global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const AttnArgs a) {
     constexpr int HD = 128;
-    constexpr int TH = PVS_TH;                                 // 64 threads = 2 warps per head
+    constexpr int DPT = pvs_dpt(GQA);
+    constexpr int TH = pvs_th(GQA);                            // threads per head: 16 chains x (8 / DPT) dim groups
     constexpr int NT = GQA * TH;
     constexpr int NW = TH / 32;
     extern __shared__ __align__(16) uint8_t sp_dyn[];
@@ -1180,7 +1220,7 @@ __global__ void __launch_bounds__(GQA * PVS_TH) k_attn_softmax_pv(const AttnArgs
     __shared__ float  red[GQA][16][PVS_DIMS + 1];
     const int g = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int h = tid / TH, ht = tid % TH;                     // head of the group, thread within the head
-    const int c = ht / (PVS_DIMS / 2), dp = ht % (PVS_DIMS / 2);   // chain, dim pair
+    const int c = ht / (PVS_DIMS / DPT), dp = ht % (PVS_DIMS / DPT);   // chain, dim group
     const int w = ht >> 5;                                     // warp within the head
 
     trace_mark(a.trace, 0);
@@ -1276,16 +1316,24 @@ __global__ void __launch_bounds__(GQA * PVS_TH) k_attn_softmax_pv(const AttnArgs
         }
         const int steps = len / 16;
         const float * pr = row + t0 + c;
-        const __half2 * vr = reinterpret_cast<const __half2 *>(&vs[c][2 * dp]);
+        if (DPT == 2) {
+            const __half2 * vr = reinterpret_cast<const __half2 *>(&vs[c][2 * dp]);
 #pragma unroll 8
-        for (int s = 0; s < steps; s++) {
-            const float2 v = __half22float2(vr[(size_t) s * 16 * (PVS_DIMS / 2)]);
-            const float p = pr[16 * s];
-            acc0 = __fmaf_rn(v.x, p, acc0);
-            acc1 = __fmaf_rn(v.y, p, acc1);
+            for (int s = 0; s < steps; s++) {
+                const float2 v = __half22float2(vr[(size_t) s * 16 * (PVS_DIMS / 2)]);
+                const float p = pr[16 * s];
+                acc0 = __fmaf_rn(v.x, p, acc0);
+                acc1 = __fmaf_rn(v.y, p, acc1);
+            }
+        } else {
+            const __half * vr = &vs[c][dp];
+#pragma unroll 8
+            for (int s = 0; s < steps; s++)
+                acc0 = __fmaf_rn(__half2float(vr[(size_t) s * 16 * PVS_DIMS]), pr[16 * s], acc0);
         }
     }
-    red[h][c][2 * dp] = acc0; red[h][c][2 * dp + 1] = acc1;
+    if (DPT == 2) { red[h][c][2 * dp] = acc0; red[h][c][2 * dp + 1] = acc1; }
+    else          red[h][c][dp] = acc0;
     __syncthreads();
     trace_mark(a.trace, 4);
     if (tid < GQA * PVS_DIMS) {
