@@ -634,7 +634,10 @@ static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_p
     int vch = (int) ((budget - row_bytes) / 16) / PV_BATCH * PV_BATCH;
     vch = std::min(vch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
     a.p_chunk = vch;
-    const size_t smem = row_bytes + (size_t) vch * 16;
+    size_t smem = row_bytes + (size_t) vch * 16;
+    // at most one CTA per SM: the block scheduler then spreads the (n_head_kv x 16) CTAs over distinct SMs even when
+    // they are launched early (PDL) next to the tail of the previous kernel
+    if ((int) a.n_head_kv * (128 / PVS_DIMS) <= c->sm_count) smem = std::max(smem, (size_t) 116 * 1024);
     static size_t attr[64] = {0};
     const int dv = c->device & 63;
     if (smem > attr[dv]) { CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr[dv] = smem; }

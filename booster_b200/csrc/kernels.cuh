@@ -244,13 +244,12 @@ __device__ __noinline__ void q8k_block_warp(float4 va, float4 vb, int lane, int 
         const float ax = fabsf(v[i]);
         if (ax > amax) { amax = ax; mval = v[i]; midx = lane * 8 + i; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
-        const float ov = __shfl_xor_sync(0xffffffffu, mval, o);
-        const int   oi = __shfl_xor_sync(0xffffffffu, midx, o);
-        if (oa > amax || (oa == amax && oi < midx)) { amax = oa; mval = ov; midx = oi; }
-    }
+    // first element of largest magnitude over the warp: two hardware warp reductions (redux.sync) and one shuffle.
+    // |x| >= 0, so the float bit patterns order like unsigned integers.
+    const unsigned amax_all = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+    const unsigned first = __reduce_min_sync(0xffffffffu, __float_as_uint(amax) == amax_all ? (unsigned) midx : 0xffffffffu);
+    mval = __shfl_sync(0xffffffffu, mval, (int) (first >> 3));
+    amax = __uint_as_float(amax_all);
     uint32_t w0 = 0, w1 = 0;
     float d = 0.f;
     if (amax != 0.f) {
@@ -318,7 +317,7 @@ __device__ __forceinline__ void ldg8(const float * p, float (&v)[8]) {
 // before griddepcontrol.wait (they are constants). `after_loads` runs once, right after the first pass' x loads are
 // in flight (the caller tops up its weight ring there: the x loads must not queue behind those bulk copies).
 static constexpr int PRO_U = 4;
-__device__ __noinline__ float rms_scale(double tot, int k, float eps) {
+__device__ __forceinline__ float rms_scale(double tot, int k, float eps) {
     const float mean = (float) (tot / (double) k);
     return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
 }
@@ -681,16 +680,15 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
 
     trace_mark(a.trace, 0);
     pdl_launch_dependents();                                   // the next kernel may start its own weight prefetch
-    if (threadIdx.x == 0) {                                    // one thread, one fence: every barrier of the CTA
-        const uint32_t b0 = smem_u32(bars);
+    if (lane == 0) {                                           // each warp: its own ring barriers and its edge barrier
 #pragma unroll 1
-        for (int i = 0; i < W * S; i++) mbar_init(b0 + 8 * i, 1);
-#pragma unroll 1
-        for (int i = 0; i < W; i++) mbar_init(b0 + 8 * (W * S + i), 32);
+        for (int s = 0; s < S; s++) mbar_init(full0 + 8 * s, 1);
+        mbar_init(edge_in, 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();                                              // (the edge barriers of OTHER warps are first used after the
+                                                               //  prologue's __syncthreads)
 
     // group-major mapping: unit u -> CTA u % grid, group (u / grid) % groups_per_cta, so that launches with few
     // units spread over every SM
