@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (A/B runs of the GPU path only)")
+    ap.add_argument("--value-only", action="store_true", help="A/B runs: device-resident value only (no e2e / roofline / cpu legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,7 +232,7 @@ def main():
             "config": config, "gpu_launches": launches, "clocks": clk,
             "wall_clock_tokens_per_s": tokens / wall}
 
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.value_only:
         peak, peak_src = peaks()
         # ---- end to end through the C-ABI with host buffers
         n_e2e = min(args.steps, 4) * BURST

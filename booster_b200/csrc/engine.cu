@@ -612,6 +612,9 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     static int prefill_env = -1;
     if (prefill_env < 0) { const char * e = getenv("BOOSTER_B200_PREFILL"); prefill_env = e ? atoi(e) : 1; }
     a.prefill = prefill_env;
+    static int ef_env = -1;
+    if (ef_env < 0) { const char * e = getenv("BOOSTER_B200_EVICT_FIRST"); ef_env = e ? atoi(e) : 1; }
+    a.evict_first = ef_env;
     const int W = bestW;
     const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(W, a.group, nv) + (size_t) W * a.stages * 8 + (size_t) W * 8;
     static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
@@ -718,6 +721,43 @@ static void tap(b200_ctx * c, const std::string & name, int il, const float * dp
     c->tapstore.v[name + "-" + std::to_string(il)] = std::move(h);
 }
 
+// L2 look-ahead plan (kernels.cuh PfRange): which later kernel's bytes each kernel of a layer prefetches into L2.
+//   QKV      -> this layer's K and V rows 0..pos, wo                      (consumed by scores, softmax+P.V, wo)
+//   scores   -> gate|up, first part        softmax+P.V -> gate|up, middle        wo -> gate|up, rest
+//   gate|up  -> down                       down        -> the next layer's QKV stack (or the head's first tiles)
+// The short kernels between two big mat-vecs are latency-bound and leave HBM idle; with the plan HBM streams the whole
+// time and the big mat-vecs find (most of) their tiles in L2. BOOSTER_B200_PF="kvwo,gu_scores,gu_pv,gu_wo,down,next"
+// (fractions of the consumer's bytes, 0 = off) tunes it; BOOSTER_B200_PF=0 disables the look-ahead.
+struct PfPlan { float kvwo = 1.f, gu_scores = 0.35f, gu_pv = 0.35f, gu_wo = 0.30f, down = 1.f, next = 1.f; };
+static const PfPlan & pf_plan() {
+    static PfPlan p; static bool init = false;
+    if (!init) {
+        init = true;
+        if (const char * e = getenv("BOOSTER_B200_PF")) {
+            float v[6] = {0, 0, 0, 0, 0, 0};
+            const int n = sscanf(e, "%f,%f,%f,%f,%f,%f", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+            if (n == 1 && v[0] == 0.f) { p = PfPlan{0, 0, 0, 0, 0, 0}; }
+            else if (n == 6) { p = PfPlan{v[0], v[1], v[2], v[3], v[4], v[5]}; }
+        }
+    }
+    return p;
+}
+static size_t tiled_bytes(const TMat & m) { return (size_t) m.n_units * m.tiles_unit * m.tile_bytes; }
+static size_t tiled_bytes(const DevStack & s) { size_t n = 0; for (int i = 0; i < s.n_seg; i++) n += tiled_bytes(s.seg[i]); return n; }
+// bytes [from, to) (fractions) of a tiled matrix as a look-ahead range, cut at tile-size-independent 16-byte multiples
+static PfRange pf_slice(const uint8_t * base, size_t total, double from, double to) {
+    PfRange r{nullptr, 0, 0};
+    from = std::min(1.0, std::max(0.0, from)); to = std::min(1.0, std::max(from, to));
+    const size_t b0 = (size_t) (total * from) / 8192 * 8192, b1 = to >= 1.0 ? total : (size_t) (total * to) / 8192 * 8192;
+    if (b1 <= b0) return r;
+    r.p = base + b0; r.bytes = (uint32_t) std::min<size_t>(b1 - b0, 0xfffffff0u);
+    return r;
+}
+static void pf_push(PfRange (&pf)[PF_RANGES], const PfRange & r) {
+    if (!r.bytes) return;
+    for (int i = 0; i < PF_RANGES; i++) if (!pf[i].bytes) { pf[i] = r; return; }
+}
+
 // enqueue the layers of this stage (+ embedding on the first stage, + head on the last) for ONE token whose
 // scalars are in c->d_state
 static void enqueue_forward(b200_ctx * c) {
@@ -730,10 +770,12 @@ static void enqueue_forward(b200_ctx * c) {
         k_embed<<<(E + thr - 1) / thr, thr, 0, c->st>>>(m.embd_type, m.embd_rows, m.embd_row_bytes, E, c->d_state, 0, c->x);
         c->launches++;
     }
+    const PfPlan & pp = pf_plan();
     for (int li = 0; li < (int) m.layers.size(); li++) {
         LayerW & L = m.layers[(size_t) li];
         const int il = m.layer_begin + li;
         const int q80 = L.qkv.seg[0].type == T_Q8_0;
+        const size_t gu_bytes = tiled_bytes(L.gateup.m);
         {   // QKV
             g_kind = KIND_QKV;
             MatvecArgs a{};
@@ -742,6 +784,12 @@ static void enqueue_forward(b200_ctx * c) {
             a.x = c->x; a.norm_w = L.attn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
             a.q_out = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
             a.n_q = QD; a.n_k = KVD; a.head_dim = HD; a.kv_dim = KVD; a.rope = c->rope; a.st = c->d_state;
+            if (pp.kvwo > 0.f) {
+                const uint32_t row = (uint32_t) KVD * 2, all = (uint32_t) std::min<size_t>((size_t) c->n_ctx * row, 0xfffffff0u);
+                pf_push(a.pf, PfRange{(const uint8_t *) c->kc[(size_t) li], all, row});
+                pf_push(a.pf, PfRange{(const uint8_t *) c->vc[(size_t) li], all, row});
+                pf_push(a.pf, pf_slice(L.wo.m.p0, tiled_bytes(L.wo.m), 0.0, pp.kvwo));
+            }
             launch_matvec(c, a, EPI_QKV);
             tap(c, "Qcur", il, c->q, (size_t) QD);
         }
@@ -753,6 +801,8 @@ static void enqueue_forward(b200_ctx * c) {
             a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD;
             a.scale = 1.0f / sqrtf((float) HD);
             a.st = c->d_state; a.n_kv_override = 0; a.round_q_override = 0;
+            pf_push(a.pf,  pf_slice(L.gateup.m.p0, gu_bytes, 0.0, pp.gu_scores));
+            pf_push(a.pf2, pf_slice(L.gateup.m.p0, gu_bytes, pp.gu_scores, pp.gu_scores + pp.gu_pv));
             launch_attention(c, a, c->n_ctx);
             tap(c, "kqv_merged_cont", il, c->att, (size_t) QD);
         }
@@ -761,7 +811,8 @@ static void enqueue_forward(b200_ctx * c) {
             MatvecArgs a{};
             a.seg[0] = L.wo.m; a.n_seg = 1; a.n_units = L.wo.m.n_units; a.k = QD;
             a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = q80;
-            a.out = c->x; a.resid = c->x;
+            a.out = c->x; a.resid = c->x; a.st = c->d_state;
+            pf_push(a.pf, pf_slice(L.gateup.m.p0, gu_bytes, pp.gu_scores + pp.gu_pv, pp.gu_scores + pp.gu_pv + pp.gu_wo));
             static int dup = -1;   // diagnostic (BOOSTER_B200_DUP=1, tracing only): the wo launch twice in a row, the first into
                                    // a scratch vector — does a kernel whose code was just executed start faster?
             if (dup < 0) { const char * e = getenv("BOOSTER_B200_DUP"); dup = (e && e[0] == '1') ? 1 : 0; }
@@ -774,7 +825,8 @@ static void enqueue_forward(b200_ctx * c) {
             MatvecArgs a{};
             a.seg[0] = L.gateup.m; a.n_seg = 1; a.n_units = L.gateup.m.n_units; a.k = E;
             a.x = c->x; a.norm_w = L.ffn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
-            a.out = c->ffh;
+            a.out = c->ffh; a.st = c->d_state;
+            pf_push(a.pf, pf_slice(L.down.m.p0, tiled_bytes(L.down.m), 0.0, pp.down));
             launch_matvec(c, a, EPI_SILU);
             tap(c, "ffn_gate_par", il, c->ffh, (size_t) FF);
         }
@@ -783,7 +835,15 @@ static void enqueue_forward(b200_ctx * c) {
             MatvecArgs a{};
             a.seg[0] = L.down.m; a.n_seg = 1; a.n_units = L.down.m.n_units; a.k = FF;
             a.x = c->ffh; a.norm_w = nullptr; a.act_q8_0 = q80;
-            a.out = c->x; a.resid = c->x;
+            a.out = c->x; a.resid = c->x; a.st = c->d_state;
+            if (li + 1 < (int) m.layers.size()) {
+                const DevStack & nq = m.layers[(size_t) li + 1].qkv;
+                pf_push(a.pf, pf_slice(nq.seg[0].p0, tiled_bytes(nq), 0.0, pp.next));
+            } else if (m.has_head()) {
+                // the head is 431 MB: only its first tiles (what the layer stack's look-ahead depth allows)
+                const size_t hb = tiled_bytes(m.output.m);
+                pf_push(a.pf, pf_slice(m.output.m.p0, hb, 0.0, pp.next * std::min(1.0, 32.0e6 / (double) hb)));
+            }
             launch_matvec(c, a, EPI_RESID);
             tap(c, "l_out", il, c->x, (size_t) E);
         }

@@ -61,6 +61,15 @@ struct DecodeState {
 
 enum { EPI_STORE = 0, EPI_RESID = 1, EPI_QKV = 2, EPI_SILU = 3 };
 
+// L2 look-ahead: a byte range of HBM that a LATER kernel of the token will stream (its weight tiles, this layer's K/V
+// rows). Every kernel of the forward pass carries up to PF_RANGES of them and turns them into bulk L2 prefetches in its
+// data-independent prologue, so that HBM keeps streaming while the (short, latency-bound) kernels in between wait on
+// each other; the consumer then finds its tiles in the 126 MB L2. per_pos != 0: the range grows with the position
+// (K/V rows 0..pos): bytes = min(bytes, (pos + 1) * per_pos).
+static constexpr int PF_RANGES = 3;
+static constexpr uint32_t PF_CHUNK = 8192;
+struct PfRange { const uint8_t * p; uint32_t bytes; uint32_t per_pos; };
+
 struct MatvecArgs {
     TMat seg[3];
     int n_seg;
@@ -88,6 +97,8 @@ struct MatvecArgs {
     int n_q, n_k, head_dim, kv_dim;
     const float2 * rope;       // [n_ctx][head_dim/2] (cos, sin)
     const DecodeState * st;
+    PfRange pf[PF_RANGES];     // L2 look-ahead for the kernels that follow (bytes == 0: unused)
+    int evict_first;           // weight tiles are copied with the L2 evict-first hint (they are dead after the copy)
     unsigned long long * trace; // nullptr unless b200_trace_token is running
 };
 
@@ -235,42 +246,75 @@ __device__ __forceinline__ ActSmem act_smem_carve(uint8_t * base, int k, int act
 // q = min(127, round_half_even(iscale*x)), d = 1/iscale.
 // (__noinline__ + by-value operands: ONE copy of this code in the kernel — these short kernels run with a cold
 // instruction cache, so code bytes are time; see DESIGN.md "instruction footprint")
-__device__ __noinline__ void q8k_block_warp(float4 va, float4 vb, int lane, int b, ActSmem A) {
-    const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-    float amax = 0.f, mval = 0.f;
-    int   midx = 0;
+// QB blocks (b, b + bstride, ...; the first `nvalid` of them exist, the others carry zeros and are not stored) go through
+// the steps TOGETHER: the arg-max reductions, the two divisions and the rounding of one block are a dependent chain
+// of several hundred cycles, and a warp that owns four blocks of a 14336-long vector (ffn_down's input) would
+// otherwise walk four such chains back to back.
+// Two copies: QB = 1 for the launches where a warp owns one block (k = 4096 with 16 warps), QB = 4 otherwise.
+template <int QB>
+__device__ __noinline__ void q8k_blocks_warp(float4 a0, float4 b0_, float4 a1, float4 b1_, float4 a2, float4 b2_, float4 a3, float4 b3_,
+                                             int lane, int b, int bstride, int nvalid, ActSmem A) {
+    const float4 va[4] = {a0, a1, a2, a3}, vb[4] = {b0_, b1_, b2_, b3_};
+    float v[QB][8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const float ax = fabsf(v[i]);
-        if (ax > amax) { amax = ax; mval = v[i]; midx = lane * 8 + i; }
+    for (int u = 0; u < QB; u++) {
+        v[u][0] = va[u].x; v[u][1] = va[u].y; v[u][2] = va[u].z; v[u][3] = va[u].w;
+        v[u][4] = vb[u].x; v[u][5] = vb[u].y; v[u][6] = vb[u].z; v[u][7] = vb[u].w;
+    }
+    float amax[QB], mval[QB];
+    int   midx[QB];
+#pragma unroll
+    for (int u = 0; u < QB; u++) {
+        amax[u] = 0.f; mval[u] = 0.f; midx[u] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float ax = fabsf(v[u][i]);
+            if (ax > amax[u]) { amax[u] = ax; mval[u] = v[u][i]; midx[u] = lane * 8 + i; }
+        }
     }
     // first element of largest magnitude over the warp: two hardware warp reductions (redux.sync) and one shuffle.
     // |x| >= 0, so the float bit patterns order like unsigned integers.
-    const unsigned amax_all = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
-    const unsigned first = __reduce_min_sync(0xffffffffu, __float_as_uint(amax) == amax_all ? (unsigned) midx : 0xffffffffu);
-    mval = __shfl_sync(0xffffffffu, mval, (int) (first >> 3));
-    amax = __uint_as_float(amax_all);
-    uint32_t w0 = 0, w1 = 0;
-    float d = 0.f;
-    if (amax != 0.f) {
-        const float iscale = __fdiv_rn(-127.f, mval);
+    unsigned amax_all[QB], first[QB];
+#pragma unroll
+    for (int u = 0; u < QB; u++) amax_all[u] = __reduce_max_sync(0xffffffffu, __float_as_uint(amax[u]));
+#pragma unroll
+    for (int u = 0; u < QB; u++) first[u] = __reduce_min_sync(0xffffffffu, __float_as_uint(amax[u]) == amax_all[u] ? (unsigned) midx[u] : 0xffffffffu);
+#pragma unroll
+    for (int u = 0; u < QB; u++) mval[u] = __shfl_sync(0xffffffffu, mval[u], (int) (first[u] >> 3));
+    float iscale[QB], d[QB];
+#pragma unroll
+    for (int u = 0; u < QB; u++) {
+        // an all-zero block keeps q = 0, d = 0 (cpp/ggml/src/ggml-quants.c:3607-3612): iscale 0 rounds every value to 0
+        const float is = __fdiv_rn(-127.f, mval[u]);
+        iscale[u] = amax_all[u] != 0u ? is : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < QB; u++) {
+        const float dd = __fdiv_rn(1.f, iscale[u]);
+        d[u] = amax_all[u] != 0u ? dd : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < QB; u++) {
+        uint32_t w0 = 0, w1 = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            int qi = __float2int_rn(__fmul_rn(iscale, v[i]));
+            int qi = __float2int_rn(__fmul_rn(iscale[u], v[u][i]));
             qi = min(127, qi);
             if (i < 4) w0 |= ((uint32_t) (qi & 0xff)) << (8 * i);
             else       w1 |= ((uint32_t) (qi & 0xff)) << (8 * (i - 4));
         }
-        d = __fdiv_rn(1.f, iscale);
+        const int a0s = __dp4a((int) w0, 0x01010101, 0), a1s = __dp4a((int) w1, 0x01010101, 0);   // word sums
+        int s32 = a0s + a1s;
+        s32 += __shfl_xor_sync(0xffffffffu, s32, 1);
+        s32 += __shfl_xor_sync(0xffffffffu, s32, 2);             // sum of sub-block lane/4 (32 values)
+        if (u < nvalid) {
+            const int bb = b + u * bstride;
+            *reinterpret_cast<uint2 *>(A.q + (size_t) bb * 256 + lane * 8) = make_uint2(w0, w1);
+            *reinterpret_cast<int2 *>(A.as + (size_t) bb * 64 + lane * 2) = make_int2(-32 * a0s, -32 * a1s);
+            if ((lane & 3) == 0) A.bp[(size_t) bb * 8 + (lane >> 2)] = s32;
+            if (lane == 0) A.dx[bb] = d[u];
+        }
     }
-    *reinterpret_cast<uint2 *>(A.q + (size_t) b * 256 + lane * 8) = make_uint2(w0, w1);
-    const int a0 = __dp4a((int) w0, 0x01010101, 0), a1 = __dp4a((int) w1, 0x01010101, 0);   // word sums
-    *reinterpret_cast<int2 *>(A.as + (size_t) b * 64 + lane * 2) = make_int2(-32 * a0, -32 * a1);
-    int s32 = a0 + a1;
-    s32 += __shfl_xor_sync(0xffffffffu, s32, 1);
-    s32 += __shfl_xor_sync(0xffffffffu, s32, 2);                 // sum of sub-block lane/4 (32 values)
-    if ((lane & 3) == 0) A.bp[(size_t) b * 8 + (lane >> 2)] = s32;
-    if (lane == 0) A.dx[b] = d;
 }
 // One warp quantizes 256 consecutive values = 8 Q8_0 blocks of 32 — AVX path of quantize_row_q8_0
 // (cpp/ggml/src/ggml-quants.c:936-1000): d = amax/127 kept as fp16, id = 127/amax, q = round_half_even(x*id).
@@ -294,11 +338,6 @@ __device__ __noinline__ void q80_blocks_warp(float4 va, float4 vb, int lane, int
     if ((lane & 3) == 0) A.dx[b256 * 8 + (lane >> 2)] = __half2float(__float2half_rn(d));
 }
 
-__device__ __forceinline__ void quantize_block(const float (&v)[8], int act_q8_0, int lane, int b, const ActSmem & A) {
-    const float4 va = make_float4(v[0], v[1], v[2], v[3]), vb = make_float4(v[4], v[5], v[6], v[7]);
-    if (act_q8_0) q80_blocks_warp(va, vb, lane, b, A);
-    else          q8k_block_warp(va, vb, lane, b, A);
-}
 __device__ __forceinline__ void load8(const float * p, float (&v)[8]) {
     const float4 a0 = *reinterpret_cast<const float4 *>(p), a1 = *reinterpret_cast<const float4 *>(p + 4);
     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
@@ -330,7 +369,7 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
     const int n256 = k / 256;
     bool first = true;
     for (int b0 = warp; b0 < n256 || first; b0 += PRO_U * nwarp) {
-        float v[PRO_U][8];
+        float v[PRO_U][8] = {};                     // blocks beyond the vector stay zero (quantized with the others, not stored)
 #pragma unroll
         for (int u = 0; u < PRO_U; u++) {
             const int b = b0 + u * nwarp;
@@ -358,16 +397,31 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
             trace_mark(tr, 6);
         }
         first = false;
+        if (norm) {
 #pragma unroll
-        for (int u = 0; u < PRO_U; u++) {
-            const int b = b0 + u * nwarp;
-            if (b < n256) {
-                if (norm) {
+            for (int u = 0; u < PRO_U; u++) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], scale), pre_w[u][i]);
-                }
-                quantize_block(v[u], act_q8_0, lane, b, A);
+                for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], scale), pre_w[u][i]);
             }
+        }
+        if (act_q8_0) {
+#pragma unroll
+            for (int u = 0; u < PRO_U; u++) {
+                const int b = b0 + u * nwarp;
+                if (b < n256) q80_blocks_warp(make_float4(v[u][0], v[u][1], v[u][2], v[u][3]), make_float4(v[u][4], v[u][5], v[u][6], v[u][7]), lane, b, A);
+            }
+        } else if (b0 < n256) {
+            const int nvalid = min(PRO_U, (n256 - b0 + nwarp - 1) / nwarp);
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (nvalid == 1)
+                q8k_blocks_warp<1>(make_float4(v[0][0], v[0][1], v[0][2], v[0][3]), make_float4(v[0][4], v[0][5], v[0][6], v[0][7]),
+                                   z4, z4, z4, z4, z4, z4, lane, b0, nwarp, 1, A);
+            else
+            q8k_blocks_warp<4>(make_float4(v[0][0], v[0][1], v[0][2], v[0][3]), make_float4(v[0][4], v[0][5], v[0][6], v[0][7]),
+                            make_float4(v[1][0], v[1][1], v[1][2], v[1][3]), make_float4(v[1][4], v[1][5], v[1][6], v[1][7]),
+                            make_float4(v[2][0], v[2][1], v[2][2], v[2][3]), make_float4(v[2][4], v[2][5], v[2][6], v[2][7]),
+                            make_float4(v[3][0], v[3][1], v[3][2], v[3][3]), make_float4(v[3][4], v[3][5], v[3][6], v[3][7]),
+                            lane, b0, nwarp, nvalid, A);
         }
     }
 }
@@ -415,6 +469,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// the same copy with an L2 evict-first hint: a tile is read exactly once per token, so after the copy its lines are the
+// preferred victims and the look-ahead data that has NOT been consumed yet stays resident
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+
+// L2 look-ahead (PfRange): lane 0 of warp `wid` (of `n_w` issuing warps in the whole grid) prefetches chunks wid,
+// wid + n_w, ... of every range — the ranges arrive front first, in the order their consumer walks them
+__device__ __forceinline__ void l2_prefetch_bulk(const void * p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void issue_l2_lookahead(const PfRange (&pf)[PF_RANGES], int wid, int n_w, int pos) {
+#pragma unroll 1
+    for (int r = 0; r < PF_RANGES; r++) {
+        uint32_t bytes = pf[r].bytes;
+        if (bytes == 0) continue;
+        if (pf[r].per_pos) bytes = min(bytes, (uint32_t) (pos + 1) * pf[r].per_pos);
+        bytes &= ~15u;
+#pragma unroll 1
+        for (uint32_t off = (uint32_t) wid * PF_CHUNK; off < bytes; off += (uint32_t) n_w * PF_CHUNK)
+            l2_prefetch_bulk(pf[r].p + off, min(PF_CHUNK, bytes - off));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -588,7 +672,9 @@ __device__ __forceinline__ float finish_row(const float * c) {
 template <int CPW, bool Q5>
 __device__ __forceinline__ void chain_round(const float * rb, int G, int tile_stride, const int (&voff)[6], const int (&moff)[6],
                                             int q5slot, float (&acc)[12]) {
-#pragma unroll 1
+    // (unrolled by 4 when a lane has one or two chains: the LDS of four tiles are in flight together and only the FMAs
+    //  are serial)
+#pragma unroll (CPW <= 2 ? 4 : 1)
     for (int ww = 0; ww < G; ww++) {
         const float * tb = rb + (size_t) ww * tile_stride;
 #pragma unroll
@@ -701,11 +787,15 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
     // ---- producer side: item pi = (unit pj, tile w + G*pk) goes to ring slot pi % S
     int pi = 0, pj = 0, pk = 0, ps = 0;
     UnitDesc pd = describe_unit(a, my_units > 0 ? group_global : 0);
+    const uint64_t pol = a.evict_first ? l2_policy_evict_first() : 0ull;
     auto issue_next = [&]() {
         if (pi >= n_items) return;
         if (lane == 0) {
             mbar_expect_tx(full0 + 8 * ps, pd.bytes);
-            bulk_g2s(ring_u32 + (uint32_t) ps * a.stage_bytes, pd.tiles + (size_t) (w + G * pk) * pd.bytes, pd.bytes, full0 + 8 * ps);
+            const uint32_t dst = ring_u32 + (uint32_t) ps * a.stage_bytes;
+            const uint8_t * src = pd.tiles + (size_t) (w + G * pk) * pd.bytes;
+            if (a.evict_first) bulk_g2s_hint(dst, src, pd.bytes, full0 + 8 * ps, pol);
+            else               bulk_g2s(dst, src, pd.bytes, full0 + 8 * ps);
         }
         pi++; ps = ps + 1 == S ? 0 : ps + 1;
         if (++pk == KPW) {
@@ -727,6 +817,10 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
             if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, ww[u]);
         }
     }
+
+    // L2 look-ahead for the kernels that follow (after this CTA's own first tiles are requested). DecodeState is
+    // written by the previous TOKEN's last kernel, so pos may be read before the wait.
+    if (lane == 0 && a.pf[0].bytes) issue_l2_lookahead(a.pf, warp * gridDim.x + blockIdx.x, W * gridDim.x, a.st ? a.st->pos : 0);
 
     trace_mark(a.trace, 1);
     pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
@@ -1009,6 +1103,8 @@ struct AttnArgs {
     int n_kv_override;        // >0: use instead of st->pos+1 (operator-level test)
     int round_q_override;     // operator-level test of the batch>1 arithmetic
     int p_chunk;              // positions of p staged in shared memory by k_attn_pv (multiple of PV_BATCH)
+    PfRange pf[PF_RANGES];    // L2 look-ahead issued by k_attn_scores
+    PfRange pf2[PF_RANGES];   // ... and by k_attn_softmax_pv
     unsigned long long * trace;
 };
 __device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1; }
@@ -1032,6 +1128,8 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
 #pragma unroll
         for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);            // 4 halfs at element 16s + 4c4
     }
+    if ((tid & 31) == 0 && a.pf[0].bytes)
+        issue_l2_lookahead(a.pf, (tid >> 5) * (gridDim.x * gridDim.y) + tile * gridDim.x + g, (ATT_THREADS / 32) * gridDim.x * gridDim.y, n_kv - 1);
     pdl_wait();                                               // q and this token's K row come from the QKV kernel
     pdl_launch_dependents();                                  // AFTER the wait: the next kernel may touch K/V/q before ITS wait
     trace_mark(a.trace, 1);
@@ -1239,6 +1337,8 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
         cp_async_commit();
     };
     stage_v(0);
+    if (lane == 0 && a.pf2[0].bytes)
+        issue_l2_lookahead(a.pf2, (tid >> 5) * (gridDim.x * gridDim.y) + slice * gridDim.x + g, (NT / 32) * gridDim.x * gridDim.y, n_kv - 1);
     pdl_wait();                                               // the raw scores are complete
     trace_mark(a.trace, 1);
     float * row = ps + (size_t) h * n_pad;
