@@ -212,14 +212,14 @@ def main():
     dev_ms = 0.0
     for _ in range(args.steps):
         gen(tok, pos0, BURST)
-        dev_ms += c.last_device_ms() if world == 1 else 0.0
+        dev_ms += c.last_device_ms()
     sync_all()
     wall = time.perf_counter() - t0
     clk = clocks.stop()
     launches = c.kernel_launches() - l0
-    # single GPU: device time from CUDA events on the engine's stream; multi-GPU: barrier-bracketed wall clock
-    # (events on one rank do not see the other stages), max over ranks
-    elapsed = dev_ms / 1e3 if world == 1 else wall
+    # device time from CUDA events on the engine's stream (every rank's span covers the whole burst: a stage's stream
+    # sits in ncclRecv while the other stages work), max over ranks; the barrier-bracketed wall clock is reported beside it
+    elapsed = dev_ms / 1e3
     if world > 1:
         elapsed = pipeline.max_over_ranks(dist, elapsed, device="cuda")
         launches = pipeline.sum_over_ranks(dist, launches, device="cuda")

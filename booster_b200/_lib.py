@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbooster_b200.so")
+# BOOSTER_B200_LIB: A/B builds of the SAME sources with different -D switches (scripts/gpu_variants.sh); never a fallback
+LIB_PATH = os.environ.get("BOOSTER_B200_LIB") or os.path.join(_HERE, "libbooster_b200.so")
 
 _lib = None
 

@@ -495,6 +495,7 @@ struct b200_ctx {
     float * q = nullptr;        // [n_head*hd]
     float * att = nullptr;      // kqv_merged_cont [n_head*hd]
     float * ffh = nullptr;      // silu(gate)*up [n_ff]
+    float * warm_x = nullptr;   // constant vector [max(n_ff, n_embd)] read by the prologue's dry run (B200_WARM)
     float * logits = nullptr;   // [n_vocab]
     float * S = nullptr;        // attention scores / probabilities [n_head][n_ctx]
     unsigned int * tickets = nullptr;
@@ -609,20 +610,29 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     }
     if (bestW == 0) throw std::runtime_error("activation vector too long for the shared-memory budget");
     a.group = bestG; a.stages = bestS;
+    a.chain_mode = chain_mode_of(bestG); a.act_bytes = (uint32_t) act_bytes; a.chain_bytes = (uint32_t) chain_smem_bytes(bestW, bestG, nv);
+    a.exch_words = a.chain_mode == CHAIN_EXCHANGE ? (uint32_t) bestW * 2 * (uint32_t) nv * 32 : 0;
+    a.kpw = a.tiles_unit / bestG; a.groups_per_cta = bestW / bestG; a.grp_magic = (uint32_t) (65536 / bestG + 1);
     static int prefill_env = -1;
     if (prefill_env < 0) { const char * e = getenv("BOOSTER_B200_PREFILL"); prefill_env = e ? atoi(e) : 1; }
     a.prefill = prefill_env;
-    static int ef_env = -1;
-    if (ef_env < 0) { const char * e = getenv("BOOSTER_B200_EVICT_FIRST"); ef_env = e ? atoi(e) : 1; }
-    a.evict_first = ef_env;
+#if B200_WARM
+    static int warm_env = -1;
+    if (warm_env < 0) { const char * e = getenv("BOOSTER_B200_WARM"); warm_env = e ? atoi(e) : 1; }
+    a.warm_x = warm_env ? c->warm_x : nullptr;
+#endif
     const int W = bestW;
     const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(W, a.group, nv) + (size_t) W * a.stages * 8 + (size_t) W * 8;
     static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
-    if (smem > attr_smem[c->device & 63]) { CU(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_smem[c->device & 63] = smem; }
+    if (smem > attr_smem[c->device & 63]) {
+        CU(cudaFuncSetAttribute(k_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CU(cudaFuncSetAttribute(k_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_smem[c->device & 63] = smem;
+    }
     const int grid = std::max(1, std::min(a.n_units, c->sm_count));
     a.trace = trace_slot(c, grid);
-    launch_fwd(k_matvec, dim3((unsigned) grid), dim3((unsigned) (W * 32)), smem, c->st, a);
+    launch_fwd(a.trace ? k_matvec<true> : k_matvec<false>, dim3((unsigned) grid), dim3((unsigned) (W * 32)), smem, c->st, a);
     c->launches++;
 }
 
@@ -643,18 +653,22 @@ static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_p
     if ((int) a.n_head_kv * (128 / PVS_DIMS) <= c->sm_count) smem = std::max(smem, (size_t) 116 * 1024);
     static size_t attr[64] = {0};
     const int dv = c->device & 63;
-    if (smem > attr[dv]) { CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr[dv] = smem; }
+    if (smem > attr[dv]) {
+        CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr[dv] = smem;
+    }
     {
         g_kind = KIND_ATTN; ProfScope ps(c);
         const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
         a.trace = trace_slot(c, (int) (gs.x * gs.y));
-        launch_fwd(k_attn_scores<GQA>, gs, dim3(ATT_THREADS), 0, c->st, a);
+        launch_fwd(a.trace ? k_attn_scores<GQA, true> : k_attn_scores<GQA, false>, gs, dim3(ATT_THREADS), 0, c->st, a);
     }
     {
         g_kind = KIND_ATTN_PV; ProfScope ps(c);
         const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVS_DIMS));
         a.trace = trace_slot(c, (int) (gp.x * gp.y));
-        launch_fwd(k_attn_softmax_pv<GQA>, gp, dim3((unsigned) (GQA * pvs_th(GQA))), smem, c->st, a);
+        launch_fwd(a.trace ? k_attn_softmax_pv<GQA, true> : k_attn_softmax_pv<GQA, false>, gp, dim3((unsigned) (GQA * pvs_th(GQA))), smem, c->st, a);
     }
     c->launches += 2;
     return true;
@@ -681,7 +695,7 @@ static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pa
     const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
     {
         g_kind = KIND_ATTN; ProfScope ps(c);
-        launch_fwd(k_attn_scores<GQA>, gs, dim3(ATT_THREADS), 0, c->st, a);
+        launch_fwd(k_attn_scores<GQA, false>, gs, dim3(ATT_THREADS), 0, c->st, a);
         k_attn_softmax<<<a.n_head, 256, 0, c->st>>>(a);
     }
     {
@@ -728,7 +742,7 @@ static void tap(b200_ctx * c, const std::string & name, int il, const float * dp
 // The short kernels between two big mat-vecs are latency-bound and leave HBM idle; with the plan HBM streams the whole
 // time and the big mat-vecs find (most of) their tiles in L2. BOOSTER_B200_PF="kvwo,gu_scores,gu_pv,gu_wo,down,next"
 // (fractions of the consumer's bytes, 0 = off) tunes it; BOOSTER_B200_PF=0 disables the look-ahead.
-struct PfPlan { float kvwo = 1.f, gu_scores = 0.35f, gu_pv = 0.35f, gu_wo = 0.30f, down = 1.f, next = 1.f; };
+struct PfPlan { float kvwo = 1.f, gu_scores = 0.f, gu_pv = 0.f, gu_wo = 0.f, down = 0.f, next = 1.f; };
 static const PfPlan & pf_plan() {
     static PfPlan p; static bool init = false;
     if (!init) {
@@ -784,12 +798,14 @@ static void enqueue_forward(b200_ctx * c) {
             a.x = c->x; a.norm_w = L.attn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
             a.q_out = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
             a.n_q = QD; a.n_k = KVD; a.head_dim = HD; a.kv_dim = KVD; a.rope = c->rope; a.st = c->d_state;
+#if B200_LOOKAHEAD
             if (pp.kvwo > 0.f) {
                 const uint32_t row = (uint32_t) KVD * 2, all = (uint32_t) std::min<size_t>((size_t) c->n_ctx * row, 0xfffffff0u);
                 pf_push(a.pf, PfRange{(const uint8_t *) c->kc[(size_t) li], all, row});
                 pf_push(a.pf, PfRange{(const uint8_t *) c->vc[(size_t) li], all, row});
                 pf_push(a.pf, pf_slice(L.wo.m.p0, tiled_bytes(L.wo.m), 0.0, pp.kvwo));
             }
+#endif
             launch_matvec(c, a, EPI_QKV);
             tap(c, "Qcur", il, c->q, (size_t) QD);
         }
@@ -898,6 +914,12 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         CU(cudaMalloc(&c->q, (size_t) QD * 4));
         CU(cudaMalloc(&c->att, (size_t) QD * 4));
         CU(cudaMalloc(&c->ffh, (size_t) m->n_ff * 4));
+        {
+            std::vector<float> w((size_t) std::max(m->n_ff, m->n_embd));
+            for (size_t i = 0; i < w.size(); i++) w[i] = 0.25f + 0.001f * (float) (i % 97);
+            CU(cudaMalloc(&c->warm_x, w.size() * 4));
+            CU(cudaMemcpy(c->warm_x, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&c->logits, (size_t) m->n_vocab * 4));
         CU(cudaMalloc(&c->S, (size_t) m->n_head * c->n_ctx * 4));
         CU(cudaMalloc(&c->tickets, (size_t) m->n_head_kv * 4));
@@ -943,7 +965,7 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (auto p : c->kc) cudaFree(p);
     for (auto p : c->vc) cudaFree(p);
-    cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->logits);
+    cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->warm_x); cudaFree(c->logits);
     cudaFree(c->d_trace);
     cudaFree(c->S); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits);
@@ -1167,7 +1189,12 @@ extern "C" int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, 
         CU(cudaSetDevice(m.device));
         c->h_state->token = first_token; c->h_state->pos = pos0; c->h_state->round_q = 0; c->h_state->step = 0;
         CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
+        // device time of the burst on THIS rank's stream (first stage step enqueued -> last one complete; a stage's
+        // stream idles inside ncclRecv while the other stages work, so every rank's span covers the whole burst)
+        if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
+        CU(cudaEventRecord(c->ev_t0, c->st));
         for (int s = 0; s < n_steps; s++) enqueue_stage_step(c, true);
+        CU(cudaEventRecord(c->ev_t1, c->st));
         // every rank gets the ids: last rank broadcasts point-to-point
         const bool last = c->rank == c->world - 1;
         NC(g_nccl.GroupStart());
@@ -1176,6 +1203,7 @@ extern "C" int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, 
         NC(g_nccl.GroupEnd());
         if (out_tokens) CU(cudaMemcpyAsync(out_tokens, c->d_out_tokens, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
+        CU(cudaEventElapsedTime(&c->last_device_ms, c->ev_t0, c->ev_t1));
         return 0;
     } catch (const std::exception & e) { return set_err(e.what()); }
 }

@@ -33,6 +33,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// build-time A/B switches (scripts/gpu_variants.sh builds one library per setting)
+#ifndef B200_CHAIN_UNROLL
+#define B200_CHAIN_UNROLL 1
+#endif
+#ifndef B200_QB
+#define B200_QB 1
+#endif
+#ifndef B200_LOOKAHEAD
+#define B200_LOOKAHEAD 0     // L2 look-ahead prefetches (PfRange): measured neutral-to-negative on B200, see DESIGN.md
+#endif
+#ifndef B200_WARM
+#define B200_WARM 0          // dry run of the prologue before griddepcontrol.wait (instruction-cache warm-up)
+#endif
+
 namespace b200 {
 
 enum { T_F32 = 0, T_F16 = 1, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
@@ -82,6 +96,13 @@ struct MatvecArgs {
     int act_q8_0;              // 0: Q8_K activations, 1: Q8_0 activations
     int tiles_unit;            // identical for every segment of a launch (same K, same block width)
     int group;                 // G = warps sharing one 32-row unit (a divisor of the CTA's warp count)
+    int kpw;                   // = tiles_unit / group   (host-computed: integer divisions are ~20 instructions each on
+    int groups_per_cta;        // = warps / group         the device, and these kernels are instruction-fetch bound)
+    uint32_t grp_magic;        // warp / group == (warp * grp_magic) >> 16 for warp < 32
+    int chain_mode;            // = chain_mode_of(group)
+    uint32_t act_bytes;        // = act_smem_bytes(k, act_q8_0)
+    uint32_t exch_words;       // floats of the exchange buffers in front of the hand-off region (0 unless CHAIN_EXCHANGE)
+    uint32_t chain_bytes;      // = chain_smem_bytes(warps, group, nv)
     int stages;                // tiles of shared-memory ring per warp (>= 2)
     int stage_bytes;           // ring slot size = largest tile of the launch, 128-byte multiple
     int prefill;               // tiles per warp requested before griddepcontrol.wait (the rest follow the x loads)
@@ -98,7 +119,7 @@ struct MatvecArgs {
     const float2 * rope;       // [n_ctx][head_dim/2] (cos, sin)
     const DecodeState * st;
     PfRange pf[PF_RANGES];     // L2 look-ahead for the kernels that follow (bytes == 0: unused)
-    int evict_first;           // weight tiles are copied with the L2 evict-first hint (they are dead after the copy)
+    const float * warm_x;      // B200_WARM: constant vector of k floats for the dry run of the prologue (nullptr: no dry run)
     unsigned long long * trace; // nullptr unless b200_trace_token is running
 };
 
@@ -136,8 +157,11 @@ __device__ __noinline__ void trace_stamp(unsigned long long * tr, int phase) {
         tr[(size_t) (blockIdx.y * gridDim.x + blockIdx.x) * TRACE_PHASES + phase] = t;
     }
 }
+// TR is a template parameter of every forward kernel: the production instantiation carries no trace code at all (these
+// kernels run with a cold instruction cache, so code bytes are time — DESIGN.md "instruction footprint")
+template <bool TR>
 __device__ __forceinline__ void trace_mark(unsigned long long * tr, int phase) {
-    if (tr != nullptr && threadIdx.x == 0) trace_stamp(tr, phase);
+    if (TR) { if (tr != nullptr && threadIdx.x == 0) trace_stamp(tr, phase); }
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -360,7 +384,7 @@ __device__ __forceinline__ float rms_scale(double tot, int k, float eps) {
     const float mean = (float) (tot / (double) k);
     return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
 }
-template <typename F>
+template <bool TR, typename F>
 __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, bool norm, float eps, int k, int act_q8_0,
                                                   const ActSmem & A, double * red, const float (&pre_w)[PRO_U][8], F after_loads,
                                                   unsigned long long * tr = nullptr) {
@@ -369,7 +393,11 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
     const int n256 = k / 256;
     bool first = true;
     for (int b0 = warp; b0 < n256 || first; b0 += PRO_U * nwarp) {
+#if B200_QB == 1
+        float v[PRO_U][8];
+#else
         float v[PRO_U][8] = {};                     // blocks beyond the vector stay zero (quantized with the others, not stored)
+#endif
 #pragma unroll
         for (int u = 0; u < PRO_U; u++) {
             const int b = b0 + u * nwarp;
@@ -389,12 +417,12 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
             }
             s = warp_sum_d(s);
             if (lane == 0) red[warp] = s;
-            trace_mark(tr, 5);
+            trace_mark<TR>(tr, 5);
             __syncthreads();
             double tot = 0.0;
             for (int w = 0; w < nwarp; w++) tot += red[w];
             scale = rms_scale(tot, k, eps);
-            trace_mark(tr, 6);
+            trace_mark<TR>(tr, 6);
         }
         first = false;
         if (norm) {
@@ -413,15 +441,23 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
         } else if (b0 < n256) {
             const int nvalid = min(PRO_U, (n256 - b0 + nwarp - 1) / nwarp);
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#if B200_QB == 1
+#pragma unroll
+            for (int u = 0; u < PRO_U; u++)
+                if (u < nvalid)
+                    q8k_blocks_warp<1>(make_float4(v[u][0], v[u][1], v[u][2], v[u][3]), make_float4(v[u][4], v[u][5], v[u][6], v[u][7]),
+                                       z4, z4, z4, z4, z4, z4, lane, b0 + u * nwarp, nwarp, 1, A);
+#else
             if (nvalid == 1)
                 q8k_blocks_warp<1>(make_float4(v[0][0], v[0][1], v[0][2], v[0][3]), make_float4(v[0][4], v[0][5], v[0][6], v[0][7]),
                                    z4, z4, z4, z4, z4, z4, lane, b0, nwarp, 1, A);
             else
-            q8k_blocks_warp<4>(make_float4(v[0][0], v[0][1], v[0][2], v[0][3]), make_float4(v[0][4], v[0][5], v[0][6], v[0][7]),
-                            make_float4(v[1][0], v[1][1], v[1][2], v[1][3]), make_float4(v[1][4], v[1][5], v[1][6], v[1][7]),
-                            make_float4(v[2][0], v[2][1], v[2][2], v[2][3]), make_float4(v[2][4], v[2][5], v[2][6], v[2][7]),
-                            make_float4(v[3][0], v[3][1], v[3][2], v[3][3]), make_float4(v[3][4], v[3][5], v[3][6], v[3][7]),
-                            lane, b0, nwarp, nvalid, A);
+                q8k_blocks_warp<4>(make_float4(v[0][0], v[0][1], v[0][2], v[0][3]), make_float4(v[0][4], v[0][5], v[0][6], v[0][7]),
+                                   make_float4(v[1][0], v[1][1], v[1][2], v[1][3]), make_float4(v[1][4], v[1][5], v[1][6], v[1][7]),
+                                   make_float4(v[2][0], v[2][1], v[2][2], v[2][3]), make_float4(v[2][4], v[2][5], v[2][6], v[2][7]),
+                                   make_float4(v[3][0], v[3][1], v[3][2], v[3][3]), make_float4(v[3][4], v[3][5], v[3][6], v[3][7]),
+                                   lane, b0, nwarp, nvalid, A);
+#endif
         }
     }
 }
@@ -674,7 +710,8 @@ __device__ __forceinline__ void chain_round(const float * rb, int G, int tile_st
                                             int q5slot, float (&acc)[12]) {
     // (unrolled by 4 when a lane has one or two chains: the LDS of four tiles are in flight together and only the FMAs
     //  are serial)
-#pragma unroll (CPW <= 2 ? 4 : 1)
+    constexpr int UNR = CPW <= 2 ? B200_CHAIN_UNROLL : 1;
+#pragma unroll UNR
     for (int ww = 0; ww < G; ww++) {
         const float * tb = rb + (size_t) ww * tile_stride;
 #pragma unroll
@@ -740,31 +777,32 @@ __device__ __noinline__ void matvec_epilogue(const MatvecArgs & a, float val, in
     }
 }
 
+template <bool TR>
 __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_constant__ MatvecArgs a) {
     const int EPI = a.epi;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ double red_smem[MV_MAX_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int G = a.group, TU = a.tiles_unit, S = a.stages, KPW = TU / G;
+    const int G = a.group, TU = a.tiles_unit, S = a.stages, KPW = a.kpw;
     // shared memory: ring (128-byte aligned slots) | activations | hand-off buffers | mbarriers
     uint8_t * ring = smem_raw + (size_t) warp * S * a.stage_bytes;
     uint8_t * act_base = smem_raw + (size_t) W * S * a.stage_bytes;
-    const size_t act_bytes = act_smem_bytes(a.k, a.act_q8_0);
+    const size_t act_bytes = a.act_bytes;
     const ActSmem A = act_smem_carve(act_base, a.k, a.act_q8_0);
-    const int grp = warp / G, w = warp - grp * G;              // group inside the CTA, warp inside the group
+    const int grp = (int) (((uint32_t) warp * a.grp_magic) >> 16), w = warp - grp * G;   // group inside the CTA, warp inside the group
     const int NV = a.nv;
-    const int mode = chain_mode_of(G);
+    const int mode = a.chain_mode;
     // chain region: exchange: cbuf[parity][warp of the CTA][value][lane] | fin[group][chain][lane]; hand-off: fin only
     float * cbuf = reinterpret_cast<float *>(act_base + act_bytes);
-    float * fin  = cbuf + (mode == CHAIN_EXCHANGE ? (size_t) W * 2 * NV * 32 : 0) + (size_t) grp * HANDOFF_WORDS;
-    uint64_t * bars = reinterpret_cast<uint64_t *>(act_base + act_bytes + chain_smem_bytes(W, G, NV));
+    float * fin  = cbuf + a.exch_words + (size_t) grp * HANDOFF_WORDS;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(act_base + act_bytes + a.chain_bytes);
     const uint32_t full0   = smem_u32(bars + warp * S);                            // my ring slots' "tile landed" barriers
     const uint32_t edge_in  = smem_u32(bars + W * S + warp);                        // hand-off: "chain state for me is published"
     const uint32_t edge_out = smem_u32(bars + W * S + grp * G + (w + 1 == G ? 0 : w + 1));
     const uint32_t ring_u32 = smem_u32(ring);
     const int bar_id = 1 + grp, bar_threads = G * 32;                              // the group's named barrier
 
-    trace_mark(a.trace, 0);
+    trace_mark<TR>(a.trace, 0);
     pdl_launch_dependents();                                   // the next kernel may start its own weight prefetch
     if (lane == 0) {                                           // each warp: its own ring barriers and its edge barrier
 #pragma unroll 1
@@ -778,7 +816,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
 
     // group-major mapping: unit u -> CTA u % grid, group (u / grid) % groups_per_cta, so that launches with few
     // units spread over every SM
-    const int groups_per_cta = W / G;
+    const int groups_per_cta = a.groups_per_cta;
     const int group_global = grp * gridDim.x + blockIdx.x;
     const int n_groups = gridDim.x * groups_per_cta;
     const int my_units = group_global < a.n_units ? (a.n_units - group_global + n_groups - 1) / n_groups : 0;
@@ -787,15 +825,14 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
     // ---- producer side: item pi = (unit pj, tile w + G*pk) goes to ring slot pi % S
     int pi = 0, pj = 0, pk = 0, ps = 0;
     UnitDesc pd = describe_unit(a, my_units > 0 ? group_global : 0);
-    const uint64_t pol = a.evict_first ? l2_policy_evict_first() : 0ull;
+    // weight tiles are read exactly once per token: the copies carry the L2 evict-first hint, so streaming 4.6 GB of
+    // them per token does not push the activations, the K/V rows and the kernels' own code out of L2
+    const uint64_t pol = l2_policy_evict_first();
     auto issue_next = [&]() {
         if (pi >= n_items) return;
         if (lane == 0) {
             mbar_expect_tx(full0 + 8 * ps, pd.bytes);
-            const uint32_t dst = ring_u32 + (uint32_t) ps * a.stage_bytes;
-            const uint8_t * src = pd.tiles + (size_t) (w + G * pk) * pd.bytes;
-            if (a.evict_first) bulk_g2s_hint(dst, src, pd.bytes, full0 + 8 * ps, pol);
-            else               bulk_g2s(dst, src, pd.bytes, full0 + 8 * ps);
+            bulk_g2s_hint(ring_u32 + (uint32_t) ps * a.stage_bytes, pd.tiles + (size_t) (w + G * pk) * pd.bytes, pd.bytes, full0 + 8 * ps, pol);
         }
         pi++; ps = ps + 1 == S ? 0 : ps + 1;
         if (++pk == KPW) {
@@ -820,19 +857,44 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
 
     // L2 look-ahead for the kernels that follow (after this CTA's own first tiles are requested). DecodeState is
     // written by the previous TOKEN's last kernel, so pos may be read before the wait.
+#if B200_LOOKAHEAD
     if (lane == 0 && a.pf[0].bytes) issue_l2_lookahead(a.pf, warp * gridDim.x + blockIdx.x, W * gridDim.x, a.st ? a.st->pos : 0);
+#endif
 
-    trace_mark(a.trace, 1);
+    trace_mark<TR>(a.trace, 1);
+#if B200_WARM
+    // Pass 0 (a.warm_x != nullptr): the SAME prologue instructions run once on a constant vector while this CTA would
+    // otherwise sit in griddepcontrol.wait — it reads only constants, writes only shared memory that pass 1 overwrites,
+    // and leaves the prologue's code in the instruction cache. Pass 1 is the real prologue.
+    int pos = 0;
+#pragma unroll 1
+    for (int pass = a.warm_x != nullptr ? 0 : 1; pass < 2; pass++) {
+        if (pass) {
+            pdl_wait();                                        // x (and everything else the previous kernels wrote) is visible
+            trace_mark<TR>(a.trace, 2);
+            pos = EPI == EPI_QKV ? a.st->pos : 0;              // in flight during the prologue
+        }
+        prologue_quantize<TR>(pass ? a.x : a.warm_x, norm, a.eps, a.k, a.act_q8_0, A, red_smem, ww,
+                          [&]() {
+                              if (pass) {
+#pragma unroll 1
+                                  for (int s = prefill; s < S - 1; s++) issue_next();
+                              }
+                          }, pass ? a.trace : nullptr);
+        __syncthreads();                                       // activations + every warp's barrier inits are visible
+    }
+#else
     pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
-    trace_mark(a.trace, 2);
+    trace_mark<TR>(a.trace, 2);
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
-    prologue_quantize(a.x, norm, a.eps, a.k, a.act_q8_0, A, red_smem, ww,
+    prologue_quantize<TR>(a.x, norm, a.eps, a.k, a.act_q8_0, A, red_smem, ww,
                       [&]() {
 #pragma unroll 1
                           for (int s = prefill; s < S - 1; s++) issue_next();
                       }, a.trace);
     __syncthreads();                                           // activations + every warp's barrier inits are visible
-    trace_mark(a.trace, 3);
+#endif
+    trace_mark<TR>(a.trace, 3);
 
     // ---- consumer side
     int cs = 0, cpar = 0, rnd = 0, n_in = 0;
@@ -864,16 +926,16 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
                     const int prow = cd.row0 + lane;
                     if (EPI == EPI_RESID) pre0 = a.resid[prow];
                     if (EPI == EPI_QKV && prow < a.n_q + a.n_k) {
-                        const float2 cs2 = a.rope[(size_t) pos * (a.head_dim / 2) + (((prow & ~1) % a.head_dim) >> 1)];
+                        const float2 cs2 = a.rope[(size_t) pos * (a.head_dim / 2) + (((prow & ~1) & (a.head_dim - 1)) >> 1)];
                         pre0 = cs2.x; pre1 = cs2.y;
                     }
                 }
                 mbar_wait(full0 + 8 * cs, (uint32_t) cpar);
-                if (j == 0 && k == 0) trace_mark(a.trace, 7);  // first tile landed
+                if (j == 0 && k == 0) trace_mark<TR>(a.trace, 7);  // first tile landed
                 BlockInts bi;
                 tile_ints<TYPE>(ring + (size_t) cs * a.stage_bytes, lane, t, A, bi);
                 __syncwarp();                                  // every lane is done reading the slot before it is refilled
-                if (j == 0 && k == 0) trace_mark(a.trace, 8);  // first tile's integers done
+                if (j == 0 && k == 0) trace_mark<TR>(a.trace, 8);  // first tile's integers done
                 cs = cs + 1 == S ? 0 : cs + 1; if (cs == 0) cpar ^= 1;
                 float val;
                 if (mode != CHAIN_EXCHANGE) {
@@ -923,14 +985,14 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
                     // ---- chain phase of the round: tiles t0 .. t0+G-1 in order, this lane's chains c = w + i*G
                     const float * rb = cbuf + ((size_t) ((rnd & 1) * W + grp * G) * NV) * 32 + lane;
                     rnd++;
-                    if (j == 0 && k == 0) trace_mark(a.trace, 9);   // first round: every warp's integers published
+                    if (j == 0 && k == 0) trace_mark<TR>(a.trace, 9);   // first round: every warp's integers published
                     switch (cpw) {
                         case 1:  chain_round<1, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
                         case 2:  chain_round<2, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
                         case 3:  chain_round<3, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
                         default: chain_round<6, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
                     }
-                    if (j == 0 && k == 0) trace_mark(a.trace, 11);  // first round's chains advanced
+                    if (j == 0 && k == 0) trace_mark<TR>(a.trace, 11);  // first round's chains advanced
                     if (k != KPW - 1) continue;
                     // ---- unit complete: gather the row's chains
 #pragma unroll
@@ -956,8 +1018,8 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
             default:     unit_body(TypeTag<T_Q8_0>{}); break;
         }
     }
-    trace_mark(a.trace, 10);                                   // warp 0 out of work
-    if (a.trace != nullptr) { __syncthreads(); trace_mark(a.trace, 4); }
+    trace_mark<TR>(a.trace, 10);                                   // warp 0 out of work
+    if (TR) { if (a.trace != nullptr) { __syncthreads(); trace_mark<TR>(a.trace, 4); } }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -970,7 +1032,7 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
     __shared__ double red_smem[MV_MAX_WARPS];
     const ActSmem A = act_smem_carve(smem_raw, k, act_q8_0);
     const float no_w[PRO_U][8] = {};
-    prologue_quantize(x, false, 0.f, k, act_q8_0, A, red_smem, no_w, []() {});
+    prologue_quantize<false>(x, false, 0.f, k, act_q8_0, A, red_smem, no_w, []() {});
     __syncthreads();
     if (!act_q8_0) {
         const int nb = k / 256;
@@ -1109,12 +1171,12 @@ struct AttnArgs {
 };
 __device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1; }
 
-template <int GQA>
+template <int GQA, bool TR>
 __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     constexpr int HD = 128;
     __shared__ __align__(16) float qs[GQA][HD];
     const int g = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
-    trace_mark(a.trace, 0);
+    trace_mark<TR>(a.trace, 0);
     const int n_kv = attn_n_kv(a);                            // DecodeState is written by the previous TOKEN's last kernel
     const int n_pad = (n_kv + 31) / 32 * 32;
     const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
@@ -1128,11 +1190,13 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
 #pragma unroll
         for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);            // 4 halfs at element 16s + 4c4
     }
+#if B200_LOOKAHEAD
     if ((tid & 31) == 0 && a.pf[0].bytes)
         issue_l2_lookahead(a.pf, (tid >> 5) * (gridDim.x * gridDim.y) + tile * gridDim.x + g, (ATT_THREADS / 32) * gridDim.x * gridDim.y, n_kv - 1);
+#endif
     pdl_wait();                                               // q and this token's K row come from the QKV kernel
     pdl_launch_dependents();                                  // AFTER the wait: the next kernel may touch K/V/q before ITS wait
-    trace_mark(a.trace, 1);
+    trace_mark<TR>(a.trace, 1);
     if (tile * ATT_TILE >= n_pad) return;
     const int round_q = a.st ? a.st->round_q : a.round_q_override;
     if (t == n_kv - 1) {
@@ -1191,7 +1255,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
             if (c4 == 0) a.S[(size_t) (g * GQA + h) * a.s_stride + t] = t < n_kv ? __fmul_rn(res, a.scale) : -INFINITY;
         }
     }
-    trace_mark(a.trace, 2);
+    trace_mark<TR>(a.trace, 2);
 }
 
 __global__ void __launch_bounds__(256) k_attn_softmax(const AttnArgs a) {
@@ -1303,7 +1367,7 @@ static constexpr int PVS_DIMS = 8;            // dims per CTA: 8 halfs = one 16-
 __host__ __device__ constexpr int pvs_dpt(int gqa) { return gqa >= 8 ? 2 : 1; }
 __host__ __device__ constexpr int pvs_th(int gqa) { return 16 * (PVS_DIMS / pvs_dpt(gqa)); }
 
-template <int GQA>
+template <int GQA, bool TR>
 __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const AttnArgs a) {
     constexpr int HD = 128;
     constexpr int DPT = pvs_dpt(GQA);
@@ -1319,7 +1383,7 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
     const int c = ht / (PVS_DIMS / DPT), dp = ht % (PVS_DIMS / DPT);   // chain, dim group
     const int w = ht >> 5;                                     // warp within the head
 
-    trace_mark(a.trace, 0);
+    trace_mark<TR>(a.trace, 0);
     pdl_launch_dependents();
     const int n_kv = attn_n_kv(a);                             // DecodeState is written by the previous TOKEN's last kernel
     const int n_pad = (n_kv + 31) / 32 * 32;
@@ -1337,10 +1401,12 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
         cp_async_commit();
     };
     stage_v(0);
+#if B200_LOOKAHEAD
     if (lane == 0 && a.pf2[0].bytes)
         issue_l2_lookahead(a.pf2, (tid >> 5) * (gridDim.x * gridDim.y) + slice * gridDim.x + g, (NT / 32) * gridDim.x * gridDim.y, n_kv - 1);
+#endif
     pdl_wait();                                               // the raw scores are complete
-    trace_mark(a.trace, 1);
+    trace_mark<TR>(a.trace, 1);
     float * row = ps + (size_t) h * n_pad;
     {
         const float * Sg = a.S + (size_t) (g * GQA + h) * a.s_stride;
@@ -1349,7 +1415,7 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
         cp_async_wait<0>();                                    // (also completes this thread's V copies)
     }
     asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");   // the head's row is in shared memory
-    trace_mark(a.trace, 2);
+    trace_mark<TR>(a.trace, 2);
     // soft_max_ext of the head's row (cpp/ggml/src/ggml.c:13682-13778): a thread owns whole 16-element vectors of the
     // reference's loop, so the _mm512_reduce_add_ps tree is register arithmetic; the per-vector float sums are
     // accumulated in double (order-insensitive here: see k_attn_softmax)
@@ -1373,15 +1439,23 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
     double part = 0.0;
     for (int gi = ht; gi < n16; gi += TH) {
         float4 * r4 = reinterpret_cast<float4 *>(row + 16 * gi);
-        float e[16];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float4 v = r4[(q + rot) & 3];
-            e[4 * q] = v_expf(__fsub_rn(v.x, mx)); e[4 * q + 1] = v_expf(__fsub_rn(v.y, mx));
-            e[4 * q + 2] = v_expf(__fsub_rn(v.z, mx)); e[4 * q + 3] = v_expf(__fsub_rn(v.w, mx));
-            r4[(q + rot) & 3] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+        // _mm512_reduce_add_ps of the vector's 16 exponentials: (a[8+i] + a[i]) pairs float4 f with f+2, so the vector is
+        // walked as two such pairs in a ROLLED loop (8 inlined ggml_v_expf instead of 16: instruction footprint)
+        float4 t[2];
+#pragma unroll 1
+        for (int pq = 0; pq < 2; pq++) {
+            const int f0 = (pq + rot) & 3, f1 = f0 ^ 2;
+            float4 lo = r4[f0], hi = r4[f1];
+            lo.x = v_expf(__fsub_rn(lo.x, mx)); lo.y = v_expf(__fsub_rn(lo.y, mx)); lo.z = v_expf(__fsub_rn(lo.z, mx)); lo.w = v_expf(__fsub_rn(lo.w, mx));
+            hi.x = v_expf(__fsub_rn(hi.x, mx)); hi.y = v_expf(__fsub_rn(hi.y, mx)); hi.z = v_expf(__fsub_rn(hi.z, mx)); hi.w = v_expf(__fsub_rn(hi.w, mx));
+            r4[f0] = lo; r4[f1] = hi;
+            // fp32 addition is commutative: which of the pair is the "upper" float4 does not change the sum
+            const float4 tt = make_float4(__fadd_rn(hi.x, lo.x), __fadd_rn(hi.y, lo.y), __fadd_rn(hi.z, lo.z), __fadd_rn(hi.w, lo.w));
+            // the pair {f, f+2} with f even is t[0..3] of the tree, the odd one is t[4..7]
+            if (f0 & 1) t[1] = tt; else t[0] = tt;
         }
-        part += (double) reduce_add16_regs(e);
+        const float u0 = __fadd_rn(t[1].x, t[0].x), u1 = __fadd_rn(t[1].y, t[0].y), u2 = __fadd_rn(t[1].z, t[0].z), u3 = __fadd_rn(t[1].w, t[0].w);
+        part += (double) __fadd_rn(__fadd_rn(u0, u2), __fadd_rn(u1, u3));
     }
     part = warp_sum_d(part);
     if (lane == 0) redd[h][w] = part;
@@ -1400,7 +1474,7 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
         }
     }
     __syncthreads();                                           // all rows normalised, every thread's V copies landed
-    trace_mark(a.trace, 3);
+    trace_mark<TR>(a.trace, 3);
 
     // P.V: chain c of (head h, dims 2dp, 2dp+1): acc = fma(V[t][d], p[t], acc) over t = c, c+16, ...
     float acc0 = 0.f, acc1 = 0.f;
@@ -1433,7 +1507,7 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
     if (DPT == 2) { red[h][c][2 * dp] = acc0; red[h][c][2 * dp + 1] = acc1; }
     else          red[h][c][dp] = acc0;
     __syncthreads();
-    trace_mark(a.trace, 4);
+    trace_mark<TR>(a.trace, 4);
     if (tid < GQA * PVS_DIMS) {
         const int hh = tid / PVS_DIMS, dd = tid % PVS_DIMS;
         float t3[8], t6[4];                                   // _mm512_reduce_add_ps over the 16 chains

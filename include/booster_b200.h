@@ -86,7 +86,8 @@ void b200_timings(b200_ctx * c, double * t_prompt_us, int64_t * n_prompt, double
 void b200_reset_timings(b200_ctx * c);
 /* number of kernels launched by this library's own code since the context was created */
 int64_t b200_kernel_launches(const b200_ctx * c);
-/* device time (CUDA events on the engine's stream) of the last b200_generate_greedy call, milliseconds */
+/* device time (CUDA events on the engine's stream) of the last b200_generate_greedy /
+ * b200_pipeline_generate_greedy call on this rank, milliseconds */
 float   b200_last_device_ms(const b200_ctx * c);
 /* one token, un-graphed, with an event pair around every launch: summed device ms and launch count per kernel
  * kind (0 embed, 1 qkv, 2 attention scores+softmax, 3 wo, 4 gate/up, 5 down, 6 head, 7 attention P.V) — the live
