@@ -269,6 +269,12 @@ def main():
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "peak_source": peak_src, "bytes_per_launch": float(gu_bytes), "ms_per_launch": gu_ms,
                             "share_of_token_time": acc["gate_up"][0] / reps / tot_ms}
+        # the same kernel outside the token's dependency chain: the gate|up launches of all 32 layers back to back
+        # (2.1 GB of distinct tiles), one event pair around the lot
+        iso_ms, iso_n = c.profile_kind("gate_up", pos0 + BURST // 2, reps=8)
+        line["roofline"]["isolated"] = {"ms_per_launch": iso_ms, "launches_timed": iso_n, "achieved": gu_bytes / (iso_ms * 1e-3) / 1e9,
+                                        "frac": gu_bytes / (iso_ms * 1e-3) / 1e9 / peak,
+                                        "what": "gate|up launches of every layer back to back (distinct weights per launch, PDL), one CUDA-event pair"}
         line["token_roofline"] = {"bytes_per_token": int(bytes_tok), "achieved_gbs": bytes_tok * tps / 1e9,
                                   "frac_of_peak": bytes_tok * tps / 1e9 / peak, "roofline_tokens_per_s": peak * 1e9 / bytes_tok}
         line["kernel_ms_per_token"] = {k: round(v[0] / reps, 4) for k, v in acc.items()}

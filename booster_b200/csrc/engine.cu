@@ -539,6 +539,8 @@ extern "C" int64_t b200_kernel_launches(const b200_ctx * c) { return c ? c->laun
 
 enum { KIND_EMBED = 0, KIND_QKV, KIND_ATTN, KIND_WO, KIND_GATEUP, KIND_DOWN, KIND_HEAD, KIND_ATTN_PV, KIND_COUNT };
 static int g_kind = KIND_EMBED;   // set by enqueue_forward before each launch group
+static int g_only_kind = -1;       // b200_profile_kind: enqueue_forward launches only this kind (-1: everything)
+static bool want(int kind) { return g_only_kind < 0 || g_only_kind == kind; }
 struct ProfScope {
     b200_ctx * c; cudaEvent_t a = nullptr, b = nullptr;
     explicit ProfScope(b200_ctx * c_);
@@ -610,6 +612,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     }
     if (bestW == 0) throw std::runtime_error("activation vector too long for the shared-memory budget");
     a.group = bestG; a.stages = bestS;
+    a.inv_k = (a.k & (a.k - 1)) == 0 ? 1.0 / (double) a.k : 0.0;
     a.chain_mode = chain_mode_of(bestG); a.act_bytes = (uint32_t) act_bytes; a.chain_bytes = (uint32_t) chain_smem_bytes(bestW, bestG, nv);
     a.exch_words = a.chain_mode == CHAIN_EXCHANGE ? (uint32_t) bestW * 2 * (uint32_t) nv * 32 : 0;
     a.kpw = a.tiles_unit / bestG; a.groups_per_cta = bestW / bestG; a.grp_magic = (uint32_t) (65536 / bestG + 1);
@@ -777,7 +780,7 @@ static void pf_push(PfRange (&pf)[PF_RANGES], const PfRange & r) {
 static void enqueue_forward(b200_ctx * c) {
     b200_model & m = *c->m;
     const int E = m.n_embd, HD = m.head_dim, KVD = m.n_head_kv * HD, QD = m.n_head * HD, FF = m.n_ff;
-    if (m.has_embd()) {
+    if (m.has_embd() && want(KIND_EMBED)) {
         const int thr = 256;
         g_kind = KIND_EMBED;
         ProfScope ps(c);
@@ -790,7 +793,7 @@ static void enqueue_forward(b200_ctx * c) {
         const int il = m.layer_begin + li;
         const int q80 = L.qkv.seg[0].type == T_Q8_0;
         const size_t gu_bytes = tiled_bytes(L.gateup.m);
-        {   // QKV
+        if (want(KIND_QKV)) {   // QKV
             g_kind = KIND_QKV;
             MatvecArgs a{};
             for (int i = 0; i < L.qkv.n_seg; i++) a.seg[i] = L.qkv.seg[i];
@@ -809,7 +812,7 @@ static void enqueue_forward(b200_ctx * c) {
             launch_matvec(c, a, EPI_QKV);
             tap(c, "Qcur", il, c->q, (size_t) QD);
         }
-        {   // attention
+        if (want(KIND_ATTN) || want(KIND_ATTN_PV)) {   // attention
             g_kind = KIND_ATTN;
             AttnArgs a{};
             a.q = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
@@ -822,7 +825,7 @@ static void enqueue_forward(b200_ctx * c) {
             launch_attention(c, a, c->n_ctx);
             tap(c, "kqv_merged_cont", il, c->att, (size_t) QD);
         }
-        {   // wo + residual
+        if (want(KIND_WO)) {   // wo + residual
             g_kind = KIND_WO;
             MatvecArgs a{};
             a.seg[0] = L.wo.m; a.n_seg = 1; a.n_units = L.wo.m.n_units; a.k = QD;
@@ -836,7 +839,7 @@ static void enqueue_forward(b200_ctx * c) {
             launch_matvec(c, a, EPI_RESID);
             tap(c, "ffn_inp", il, c->x, (size_t) E);
         }
-        {   // gate/up (interleaved virtual matrix) + SiLU*mul
+        if (want(KIND_GATEUP)) {   // gate/up (interleaved virtual matrix) + SiLU*mul
             g_kind = KIND_GATEUP;
             MatvecArgs a{};
             a.seg[0] = L.gateup.m; a.n_seg = 1; a.n_units = L.gateup.m.n_units; a.k = E;
@@ -846,7 +849,7 @@ static void enqueue_forward(b200_ctx * c) {
             launch_matvec(c, a, EPI_SILU);
             tap(c, "ffn_gate_par", il, c->ffh, (size_t) FF);
         }
-        {   // down + residual
+        if (want(KIND_DOWN)) {   // down + residual
             g_kind = KIND_DOWN;
             MatvecArgs a{};
             a.seg[0] = L.down.m; a.n_seg = 1; a.n_units = L.down.m.n_units; a.k = FF;
@@ -864,7 +867,7 @@ static void enqueue_forward(b200_ctx * c) {
             tap(c, "l_out", il, c->x, (size_t) E);
         }
     }
-    if (m.has_head()) {
+    if (m.has_head() && want(KIND_HEAD)) {
         g_kind = KIND_HEAD;
         MatvecArgs a{};
         a.seg[0] = m.output.m; a.n_seg = 1; a.n_units = m.output.m.n_units; a.k = E;
@@ -1102,6 +1105,38 @@ extern "C" int b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms
         c->prof_ev.clear();
         return 0;
     } catch (const std::exception & e) { c->prof = false; return set_err(e.what()); }
+}
+
+// Kernel-in-isolation timing: the launches of ONE kind (e.g. the gate|up mat-vec) of every layer of this stage, back to
+// back on the engine's stream (each layer has its own weights, so nothing is re-read from L2), `reps` times, between ONE
+// pair of CUDA events. ms_total / n_launches is the kernel's steady-state launch-to-launch time without the token's
+// dependency chain around it (the next launch's weight prefetch overlaps the previous one's tail, as in the token).
+extern "C" int b200_profile_kind(b200_ctx * c, int kind, int pos, int reps, float * ms_total, int32_t * n_launches) {
+    try {
+        require_gpu();
+        if (!c || kind < 0 || kind >= KIND_COUNT || reps <= 0) throw std::runtime_error("bad arguments");
+        b200_model & m = *c->m;
+        if (pos < 0 || pos >= c->n_ctx) throw std::runtime_error("bad pos");
+        CU(cudaSetDevice(m.device));
+        DecodeState hs; hs.token = 0; hs.pos = pos; hs.round_q = 0; hs.step = 0;
+        k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
+        if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
+        const int64_t l0 = c->launches;
+        g_only_kind = kind;
+        try {
+            enqueue_forward(c);                                  // warm-up round
+            CU(cudaEventRecord(c->ev_t0, c->st));
+            const int64_t l1 = c->launches;
+            for (int r = 0; r < reps; r++) enqueue_forward(c);
+            CU(cudaEventRecord(c->ev_t1, c->st));
+            *n_launches = (int32_t) (c->launches - l1);
+        } catch (...) { g_only_kind = -1; throw; }
+        g_only_kind = -1;
+        (void) l0;
+        CU(cudaStreamSynchronize(c->st));
+        CU(cudaEventElapsedTime(ms_total, c->ev_t0, c->ev_t1));
+        return 0;
+    } catch (const std::exception & e) { g_only_kind = -1; return set_err(e.what()); }
 }
 
 // One token through a freshly captured graph whose kernels stamp %globaltimer at their phase boundaries (thread 0 of

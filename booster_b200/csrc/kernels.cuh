@@ -37,9 +37,6 @@
 #ifndef B200_CHAIN_UNROLL
 #define B200_CHAIN_UNROLL 1
 #endif
-#ifndef B200_QB
-#define B200_QB 1
-#endif
 #ifndef B200_LOOKAHEAD
 #define B200_LOOKAHEAD 0     // L2 look-ahead prefetches (PfRange): measured neutral-to-negative on B200, see DESIGN.md
 #endif
@@ -93,6 +90,7 @@ struct MatvecArgs {
     const float * x;
     const float * norm_w;
     float eps;
+    double inv_k;              // 1.0 / k if k is a power of two, else 0 (rms_scale)
     int act_q8_0;              // 0: Q8_K activations, 1: Q8_0 activations
     int tiles_unit;            // identical for every segment of a launch (same K, same block width)
     int group;                 // G = warps sharing one 32-row unit (a divisor of the CTA's warp count)
@@ -274,7 +272,8 @@ __device__ __forceinline__ ActSmem act_smem_carve(uint8_t * base, int k, int act
 // the steps TOGETHER: the arg-max reductions, the two divisions and the rounding of one block are a dependent chain
 // of several hundred cycles, and a warp that owns four blocks of a 14336-long vector (ffn_down's input) would
 // otherwise walk four such chains back to back.
-// Two copies: QB = 1 for the launches where a warp owns one block (k = 4096 with 16 warps), QB = 4 otherwise.
+// Only QB = 1 is instantiated: running a warp's four blocks of a 14336-long vector through the steps together
+// (QB = 4) shortens ffn_down's prologue by 1.3 us but the extra 600 instructions cost more than that (r01n/r01q A/B).
 template <int QB>
 __device__ __noinline__ void q8k_blocks_warp(float4 a0, float4 b0_, float4 a1, float4 b1_, float4 a2, float4 b2_, float4 a3, float4 b3_,
                                              int lane, int b, int bstride, int nvalid, ActSmem A) {
@@ -380,12 +379,14 @@ __device__ __forceinline__ void ldg8(const float * p, float (&v)[8]) {
 // before griddepcontrol.wait (they are constants). `after_loads` runs once, right after the first pass' x loads are
 // in flight (the caller tops up its weight ring there: the x loads must not queue behind those bulk copies).
 static constexpr int PRO_U = 4;
-__device__ __forceinline__ float rms_scale(double tot, int k, float eps) {
-    const float mean = (float) (tot / (double) k);
+// inv_k = 1.0 / k when k is a power of two (the multiplication is then exactly the division and the ~100-instruction
+// double-precision division routine is never fetched), else 0
+__device__ __forceinline__ float rms_scale(double tot, int k, double inv_k, float eps) {
+    const float mean = inv_k != 0.0 ? (float) (tot * inv_k) : (float) (tot / (double) k);
     return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
 }
 template <bool TR, typename F>
-__device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, bool norm, float eps, int k, int act_q8_0,
+__device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, bool norm, float eps, int k, double inv_k, int act_q8_0,
                                                   const ActSmem & A, double * red, const float (&pre_w)[PRO_U][8], F after_loads,
                                                   unsigned long long * tr = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -393,11 +394,7 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
     const int n256 = k / 256;
     bool first = true;
     for (int b0 = warp; b0 < n256 || first; b0 += PRO_U * nwarp) {
-#if B200_QB == 1
         float v[PRO_U][8];
-#else
-        float v[PRO_U][8] = {};                     // blocks beyond the vector stay zero (quantized with the others, not stored)
-#endif
 #pragma unroll
         for (int u = 0; u < PRO_U; u++) {
             const int b = b0 + u * nwarp;
@@ -421,15 +418,17 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
             __syncthreads();
             double tot = 0.0;
             for (int w = 0; w < nwarp; w++) tot += red[w];
-            scale = rms_scale(tot, k, eps);
+            scale = rms_scale(tot, k, inv_k, eps);
             trace_mark<TR>(tr, 6);
         }
         first = false;
         if (norm) {
 #pragma unroll
             for (int u = 0; u < PRO_U; u++) {
+                if (b0 + u * nwarp < n256) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], scale), pre_w[u][i]);
+                    for (int i = 0; i < 8; i++) v[u][i] = __fmul_rn(__fmul_rn(v[u][i], scale), pre_w[u][i]);
+                }
             }
         }
         if (act_q8_0) {
@@ -438,26 +437,13 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
                 const int b = b0 + u * nwarp;
                 if (b < n256) q80_blocks_warp(make_float4(v[u][0], v[u][1], v[u][2], v[u][3]), make_float4(v[u][4], v[u][5], v[u][6], v[u][7]), lane, b, A);
             }
-        } else if (b0 < n256) {
-            const int nvalid = min(PRO_U, (n256 - b0 + nwarp - 1) / nwarp);
+        } else {
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#if B200_QB == 1
 #pragma unroll
             for (int u = 0; u < PRO_U; u++)
-                if (u < nvalid)
+                if (b0 + u * nwarp < n256)
                     q8k_blocks_warp<1>(make_float4(v[u][0], v[u][1], v[u][2], v[u][3]), make_float4(v[u][4], v[u][5], v[u][6], v[u][7]),
                                        z4, z4, z4, z4, z4, z4, lane, b0 + u * nwarp, nwarp, 1, A);
-#else
-            if (nvalid == 1)
-                q8k_blocks_warp<1>(make_float4(v[0][0], v[0][1], v[0][2], v[0][3]), make_float4(v[0][4], v[0][5], v[0][6], v[0][7]),
-                                   z4, z4, z4, z4, z4, z4, lane, b0, nwarp, 1, A);
-            else
-                q8k_blocks_warp<4>(make_float4(v[0][0], v[0][1], v[0][2], v[0][3]), make_float4(v[0][4], v[0][5], v[0][6], v[0][7]),
-                                   make_float4(v[1][0], v[1][1], v[1][2], v[1][3]), make_float4(v[1][4], v[1][5], v[1][6], v[1][7]),
-                                   make_float4(v[2][0], v[2][1], v[2][2], v[2][3]), make_float4(v[2][4], v[2][5], v[2][6], v[2][7]),
-                                   make_float4(v[3][0], v[3][1], v[3][2], v[3][3]), make_float4(v[3][4], v[3][5], v[3][6], v[3][7]),
-                                   lane, b0, nwarp, nvalid, A);
-#endif
         }
     }
 }
@@ -874,7 +860,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
             trace_mark<TR>(a.trace, 2);
             pos = EPI == EPI_QKV ? a.st->pos : 0;              // in flight during the prologue
         }
-        prologue_quantize<TR>(pass ? a.x : a.warm_x, norm, a.eps, a.k, a.act_q8_0, A, red_smem, ww,
+        prologue_quantize<TR>(pass ? a.x : a.warm_x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, ww,
                           [&]() {
                               if (pass) {
 #pragma unroll 1
@@ -887,7 +873,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
     pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
     trace_mark<TR>(a.trace, 2);
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
-    prologue_quantize<TR>(a.x, norm, a.eps, a.k, a.act_q8_0, A, red_smem, ww,
+    prologue_quantize<TR>(a.x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, ww,
                       [&]() {
 #pragma unroll 1
                           for (int s = prefill; s < S - 1; s++) issue_next();
@@ -1032,7 +1018,7 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
     __shared__ double red_smem[MV_MAX_WARPS];
     const ActSmem A = act_smem_carve(smem_raw, k, act_q8_0);
     const float no_w[PRO_U][8] = {};
-    prologue_quantize<false>(x, false, 0.f, k, act_q8_0, A, red_smem, no_w, []() {});
+    prologue_quantize<false>(x, false, 0.f, k, 0.0, act_q8_0, A, red_smem, no_w, []() {});
     __syncthreads();
     if (!act_q8_0) {
         const int nb = k / 256;

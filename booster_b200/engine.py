@@ -111,6 +111,15 @@ class Context:
         kinds = ["embed", "qkv", "attention", "wo", "gate_up", "down", "head", "attn_pv_split_route"]
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(kinds)}
 
+    KINDS = ["embed", "qkv", "attention", "wo", "gate_up", "down", "head", "attn_pv_split_route"]
+
+    def profile_kind(self, kind: str, pos: int, reps: int = 4):
+        """(ms per launch, launches) of ONE kernel kind launched back to back over every layer, `reps` times"""
+        ms = C.c_float(0.0)
+        n = C.c_int32(0)
+        check(self.L.b200_profile_kind(self.h, self.KINDS.index(kind), pos, reps, C.byref(ms), C.byref(n)), "b200_profile_kind")
+        return float(ms.value) / max(1, n.value), int(n.value)
+
     def trace_token(self, token: int, pos: int, reps: int = 3):
         """(stamps[n_launches, 512, 12] u64 ns, meta[n_launches, 2] = (kind, ctas)) of one graph-replayed token"""
         cap_l = 1024

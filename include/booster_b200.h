@@ -93,6 +93,10 @@ float   b200_last_device_ms(const b200_ctx * c);
  * kind (0 embed, 1 qkv, 2 attention scores+softmax, 3 wo, 4 gate/up, 5 down, 6 head, 7 attention P.V) — the live
  * per-kernel roofline of bench.py */
 int     b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms_by_kind[8], int32_t n_by_kind[8]);
+/* the launches of ONE kernel kind (numbering as above) of every layer, back to back, `reps` times, between one pair of
+ * CUDA events on the engine's stream: ms_total / n_launches = that kernel's steady-state time outside the token's
+ * dependency chain (each layer has its own weights: nothing is served from L2) */
+int     b200_profile_kind(b200_ctx * c, int kind, int pos, int reps, float * ms_total, int32_t * n_launches);
 /* one token through a graph whose kernels stamp %globaltimer (ns) at their phase boundaries (thread 0 of every CTA):
  * out = [n_launches][512 CTAs][12 phases] u64 (0 = not stamped), meta = [n_launches][2] = (kind, CTAs). Returns the
  * number of launches traced (-1 on error). Diagnostic companion of b200_profile_token: shows launch gaps, PDL overlap
