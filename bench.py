@@ -265,8 +265,17 @@ def main():
         n_kv_mean = pos0 + BURST / 2
         bytes_tok = m.weight_bytes + G.kv_bytes_per_token(cfg, int(n_kv_mean))
         tot_ms = sum(v[0] for v in acc.values()) / reps
+        # DRAM traffic of one gate|up launch from the committed ncu --set full capture (profiles/traffic.json, written by
+        # scripts/ncu_summary.py): dram__bytes_read.sum + dram__bytes_write.sum
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)["gate_up"]
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         line["roofline"] = {"bound": "hbm", "kernel": "k_matvec<EPI_SILU> (ffn gate|up, fused RMSNorm + Q8_K quant + SiLU*mul)",
-                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                             "peak_source": peak_src, "bytes_per_launch": float(gu_bytes), "ms_per_launch": gu_ms,
                             "share_of_token_time": acc["gate_up"][0] / reps / tot_ms}
         # the same kernel outside the token's dependency chain: the gate|up launches of all 32 layers back to back

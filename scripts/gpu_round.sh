@@ -14,6 +14,8 @@ fi
 if [ -z "$SKIP_BENCH" ]; then
   ( time timeout 900 python bench.py $BENCH_ARGS ) > $OUT/bench.json 2> $OUT/bench.err
   cat $OUT/bench.json
+  ( time timeout 600 python bench.py --impl reference --steps 2 --warmup 1 ) > $OUT/bench_reference.json 2>> $OUT/bench.err
+  cut -c1-400 $OUT/bench_reference.json
 fi
 if [ -z "$SKIP_TRACE" ]; then
   timeout 300 python scripts/trace_token.py 2000 $OUT/trace_token.txt > $OUT/trace_head.txt 2>&1; head -12 $OUT/trace_head.txt
@@ -30,5 +32,6 @@ if [ -z "$SKIP_NCU" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_matvec|k_attn' -s 193 -c 6 \
       -f -o $OUT/prof_layer python scripts/ncu_token.py 2 > $OUT/ncu_full.log 2>&1
   tail -3 $OUT/ncu_full.log
+  python scripts/launch_summary.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1 || true
 fi
 ls -la $OUT

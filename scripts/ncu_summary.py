@@ -28,3 +28,17 @@ for row in rows[2:]:
         if w in hdr:
             i = hdr.index(w)
             print(f'{w:82s} {row[i]:>24s} {units[i]}')
+
+# optional: python scripts/ncu_summary.py file.ncu-rep traffic.json — per-kernel DRAM traffic of the captured layer
+# (launch order: qkv, scores, softmax+P.V, wo, gate_up, down), read by bench.py for roofline.traffic
+if len(sys.argv) > 2:
+    import json
+    names = ["qkv", "attn_scores", "attn_softmax_pv", "wo", "gate_up", "down"]
+    ir, iw, it = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out_j = {}
+    for name, row in zip(names, rows[2:]):
+        out_j[name] = {"kernel": row[hdr.index('Kernel Name')], "dram_bytes_read": float(row[ir]) * scale[units[ir]],
+                       "dram_bytes_write": float(row[iw]) * scale[units[iw]], "ncu_duration_us": float(row[it]),
+                       "source": sys.argv[1]}
+    json.dump(out_j, open(sys.argv[2], "w"), indent=1)
