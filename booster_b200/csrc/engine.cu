@@ -510,7 +510,9 @@ struct b200_ctx {
     cudaGraphExec_t g_logits = nullptr;   // H2D state -> forward -> D2H logits
     cudaGraphExec_t g_greedy = nullptr;   // forward -> argmax -> advance
     cudaGraphExec_t g_pipe = nullptr;     // pipeline stage step (recv -> forward -> send)
-    int64_t n_logits = 0, n_greedy = 0;   // kernels per replay of g_logits / g_greedy
+    int64_t n_logits = 0, n_greedy = 0, n_pipe = 0;   // kernels per replay of g_logits / g_greedy / g_pipe
+    int pipe_calls = 0;                   // b200_pipeline_generate_greedy calls so far (the first one runs un-graphed: NCCL connects lazily)
+    bool pipe_graph_failed = false;
     int sm_count = 148;
     bool taps = false;
     TapStore tapstore;
@@ -1227,8 +1229,33 @@ extern "C" int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, 
         // device time of the burst on THIS rank's stream (first stage step enqueued -> last one complete; a stage's
         // stream idles inside ncclRecv while the other stages work, so every rank's span covers the whole burst)
         if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
+        // One stage step = [ncclRecv x] -> this stage's kernels -> [ncclSend x] -> arg-max / advance (+ token hand-back),
+        // captured ONCE into a CUDA graph (NCCL point-to-point calls are capturable) and replayed per token, like the
+        // single-GPU loop. The first burst runs un-graphed so that NCCL sets up its peer connections outside a capture;
+        // BOOSTER_B200_PIPE_GRAPH=0 keeps it that way. A failed capture falls back to plain launches, never to another path.
+        static int pipe_graph = -1;
+        if (pipe_graph < 0) { const char * e = getenv("BOOSTER_B200_PIPE_GRAPH"); pipe_graph = e ? atoi(e) : 1; }
+        if (pipe_graph && c->pipe_calls >= 1 && !c->g_pipe && !c->pipe_graph_failed) {
+            const int64_t l0 = c->launches;
+            try {
+                c->g_pipe = capture(c, [&]() { enqueue_stage_step(c, true); }, &c->n_pipe);
+            } catch (const std::exception & e) {
+                cudaGraph_t junk = nullptr;
+                cudaStreamEndCapture(c->st, &junk);            // leave capture mode whatever state it is in
+                if (junk) cudaGraphDestroy(junk);
+                cudaGetLastError();
+                c->launches = l0; c->g_pipe = nullptr; c->pipe_graph_failed = true;
+                fprintf(stderr, "booster_b200: pipeline stage graph capture failed (%s); using plain launches\n", e.what());
+            }
+        }
+        c->pipe_calls++;
         CU(cudaEventRecord(c->ev_t0, c->st));
-        for (int s = 0; s < n_steps; s++) enqueue_stage_step(c, true);
+        if (c->g_pipe) {
+            for (int s = 0; s < n_steps; s++) CU(cudaGraphLaunch(c->g_pipe, c->st));
+            c->launches += c->n_pipe * (int64_t) n_steps;
+        } else {
+            for (int s = 0; s < n_steps; s++) enqueue_stage_step(c, true);
+        }
         CU(cudaEventRecord(c->ev_t1, c->st));
         // every rank gets the ids: last rank broadcasts point-to-point
         const bool last = c->rank == c->world - 1;
