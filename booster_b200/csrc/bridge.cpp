@@ -178,7 +178,8 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
     { std::lock_guard<std::mutex> lk(g_mu); Job & j = g_jobs[job]; j = Job(); j.seed = seed; }
 
     std::vector<int32_t> inp;
-    if (!p.tok->tokenize(text, inp)) return 0;
+    // llama_tokenize(model, prompt, add_special = false, parse_special = true): cpp/bridge.cpp:275-278
+    if (!p.tok->tokenize(text, false, true, inp)) return 0;
     { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].prompt_tokens = (int64_t) inp.size(); }
     const int max_embd = p.n_ctx - 4;
     if ((int) inp.size() > max_embd || inp.empty()) {     // cpp/bridge.cpp:382-386
@@ -208,7 +209,7 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
         if (n > 1) { t_p_us += dt; n_p_eval += (int64_t) n; } else { t_e_us += dt; n_eval += 1; }
         n_past += (int) n;
         std::string pieces;
-        for (size_t i = 0; i < n; i++) pieces += p.tok->piece(inp[consumed + i]);
+        for (size_t i = 0; i < n; i++) pieces += p.tok->piece(inp[consumed + i], true);
         { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += pieces; }
         consumed += n;
     }
@@ -219,7 +220,7 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
         const double t0 = now_us();
         if (b200_stage_argmax(last, &id) != 0) return 1;
         --n_remain;
-        { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += p.tok->piece(id); }
+        { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += p.tok->piece(id, true); }
         if (p.tok->is_eog(id)) break;                      // cpp/bridge.cpp:640
         if (n_remain == 0 || n_past >= max_embd) break;
         if (run_token(p, id, n_past, 0) != 0) return 1;

@@ -16,6 +16,7 @@
 // There is no CPU fallback: every entry point fails with an error when no CUDA device is present.
 #include "../../include/booster_b200.h"
 #include "gguf.hpp"
+#include "tokenizer.hpp"
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -619,7 +620,7 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     a.exch_words = a.chain_mode == CHAIN_EXCHANGE ? (uint32_t) bestW * 2 * (uint32_t) nv * 32 : 0;
     a.kpw = a.tiles_unit / bestG; a.groups_per_cta = bestW / bestG; a.grp_magic = (uint32_t) (65536 / bestG + 1);
     static int prefill_env = -1;
-    if (prefill_env < 0) { const char * e = getenv("BOOSTER_B200_PREFILL"); prefill_env = e ? atoi(e) : 1; }
+    if (prefill_env < 0) { const char * e = getenv("BOOSTER_B200_PREFILL"); prefill_env = e ? atoi(e) : 0; }
     a.prefill = prefill_env;
 #if B200_WARM
     static int warm_env = -1;
@@ -1343,6 +1344,44 @@ extern "C" int b200_stage_argmax(b200_ctx * c, int32_t * token_out) {
         return 0;
     } catch (const std::exception & e) { return set_err(e.what()); }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// tokenizer entry points (host side): llama_tokenize / llama_token_to_piece / llama_token_is_eog
+// ------------------------------------------------------------------------------------------------------------
+struct b200_tokenizer { std::unique_ptr<b200::Tokenizer> t; };
+extern "C" b200_tokenizer * b200_tokenizer_load(const char * gguf_path) {
+    try {
+        if (!gguf_path) throw std::runtime_error("null path");
+        std::string err;
+        auto t = b200::make_tokenizer(gguf_path, err);
+        if (!t) throw std::runtime_error(err);
+        auto * h = new b200_tokenizer();
+        h->t = std::move(t);
+        return h;
+    } catch (const std::exception & e) { set_err(e.what()); return nullptr; }
+}
+extern "C" void b200_tokenizer_free(b200_tokenizer * h) { delete h; }
+extern "C" int32_t b200_tokenizer_n_vocab(const b200_tokenizer * h) { return h ? h->t->n_vocab() : 0; }
+extern "C" int32_t b200_tokenize(const b200_tokenizer * h, const char * text, int32_t text_len, int32_t * tokens, int32_t n_max,
+                                 int add_special, int parse_special) {
+    try {
+        if (!h || !text || text_len < 0) throw std::runtime_error("bad arguments");
+        std::vector<int32_t> out;
+        if (!h->t->tokenize(std::string(text, (size_t) text_len), add_special != 0, parse_special != 0, out))
+            throw std::runtime_error("text cannot be tokenized (malformed UTF-8, a byte without a token, or ids out of range)");
+        if ((int64_t) out.size() > (int64_t) n_max) return -(int32_t) out.size();      // llama_tokenize_impl: cpp/src/llama-vocab.cpp:1497-1516
+        for (size_t i = 0; i < out.size(); i++) tokens[i] = out[i];
+        return (int32_t) out.size();
+    } catch (const std::exception & e) { set_err(e.what()); return INT32_MIN; }
+}
+extern "C" int32_t b200_token_to_piece(const b200_tokenizer * h, int32_t token, char * buf, int32_t length, int special) {
+    if (!h) return 0;
+    const std::string p = h->t->piece(token, special != 0);
+    if ((int64_t) p.size() > (int64_t) length) return -(int32_t) p.size();
+    std::memcpy(buf, p.data(), p.size());
+    return (int32_t) p.size();
+}
+extern "C" int b200_token_is_eog(const b200_tokenizer * h, int32_t token) { return h && h->t->is_eog(token) ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------------------
 // operator-level entry points (tests): host in, host out, SAME kernels

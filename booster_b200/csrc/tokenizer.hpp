@@ -1,11 +1,16 @@
-// tokenizer.hpp — host-side text <-> token-id interface used by bridge.cpp.
+// tokenizer.hpp — host-side text <-> token-id interface used by bridge.cpp (SURVEY.md §8 row f-1).
 // Replaces the reference's llama_tokenize / llama_token_to_piece / llama_token_is_eog calls
-// (cpp/bridge.cpp:275-278, 630, 640; implementation cpp/src/llama-vocab.cpp).
+// (cpp/bridge.cpp:275-278, 630, 640; implementation cpp/src/llama-vocab.cpp, cpp/src/unicode.cpp; vocabulary
+// loading cpp/src/llama.cpp:5250-5760).
 //
-// Round 1 ships the "no_vocab" tokenizer only (tokenizer.ggml.model == "no_vocab",
-// cpp/src/llama.cpp:5267-5268): the reference cannot tokenize text for such models at all, so the
-// bridge defines the prompt as white-space separated decimal token ids and a piece as "<id> ".
-// BPE / SPM are SURVEY.md §8 row f-1 ("next"); make_tokenizer fails loudly for them.
+// Three vocabularies, chosen by tokenizer.ggml.model:
+//   "no_vocab" — the reference cannot tokenize text for such models at all (cpp/src/llama.cpp:5267-5268); the
+//                bridge defines the prompt as white-space separated decimal token ids and a piece as "<id> ";
+//   "llama"    — SentencePiece-style score-driven merges with byte fallback (LLaMA-2, Mistral);
+//   "gpt2"     — byte-level BPE with merge ranks and the LLaMA-3 pre-tokenizer (tokenizer.ggml.pre = llama3 |
+//                llama-v3 | llama-bpe). Other pre-tokenizers fail loudly at load.
+// Results are pinned token for token against the reference's own tokenizer (oracle/_ref) on synthetic
+// vocabularies: tests/test_tokenizer.py, tests/golden/tokenizer_*.json.
 #pragma once
 #include <cstdint>
 #include <memory>
@@ -16,10 +21,19 @@ namespace b200 {
 
 struct Tokenizer {
     virtual ~Tokenizer() = default;
-    virtual bool tokenize(const std::string & text, std::vector<int32_t> & out) const = 0;
-    virtual std::string piece(int32_t id) const = 0;
+    // llama_tokenize(model, text, add_special, parse_special): false when the text cannot be tokenized
+    // (ids out of range for no_vocab, invalid UTF-8 or a byte without a token for the text vocabularies)
+    virtual bool tokenize(const std::string & text, bool add_special, bool parse_special, std::vector<int32_t> & out) const = 0;
+    // llama_token_to_piece(ctx, id, special)
+    virtual std::string piece(int32_t id, bool special) const = 0;
     virtual bool is_eog(int32_t id) const = 0;
+    virtual int32_t n_vocab() const = 0;
+    virtual int32_t bos() const { return -1; }
+    virtual int32_t eos() const { return -1; }
 };
+
+// bit 0 \p{L}, bit 1 \p{N}, bit 2 \s of a codepoint (unicode_tables.hpp)
+int codepoint_class(uint32_t cp);
 
 // reads tokenizer.* metadata from the GGUF; returns nullptr and sets err when the model's tokenizer
 // is not implemented

@@ -220,3 +220,39 @@ def op_attention(q, k_cache_f16, v_cache_f16, n_kv: int, n_head: int, n_head_kv:
                                        v.ctypes.data_as(C.POINTER(C.c_uint16)), n_kv, n_head, n_head_kv, head_dim, scale, int(round_q),
                                        out.ctypes.data_as(C.POINTER(C.c_float))), "op_attention")
     return out
+
+
+class Tokenizer:
+    """llama_tokenize / llama_token_to_piece / llama_token_is_eog of a GGUF's vocabulary (include/booster_b200.h)."""
+
+    def __init__(self, path: str):
+        self.L = _lib.lib()
+        self.h = self.L.b200_tokenizer_load(path.encode())
+        if not self.h:
+            raise B200Error(f"b200_tokenizer_load({path}): {_lib.last_error()}")
+        self.n_vocab = int(self.L.b200_tokenizer_n_vocab(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.b200_tokenizer_free(self.h)
+            self.h = None
+
+    def tokenize(self, text: bytes, add_special: bool = False, parse_special: bool = True) -> List[int]:
+        cap = len(text) + 16
+        buf = (C.c_int32 * cap)()
+        n = self.L.b200_tokenize(self.h, text, len(text), buf, cap, int(add_special), int(parse_special))
+        if n == -2**31:
+            raise B200Error(f"b200_tokenize: {_lib.last_error()}")
+        if n < 0:
+            raise B200Error("token buffer too small")
+        return list(buf[:n])
+
+    def piece(self, token: int, special: bool = True) -> bytes:
+        buf = C.create_string_buffer(512)
+        n = self.L.b200_token_to_piece(self.h, token, buf, 512, int(special))
+        if n < 0:
+            raise B200Error("piece buffer too small")
+        return buf.raw[:n]
+
+    def is_eog(self, token: int) -> bool:
+        return bool(self.L.b200_token_is_eog(self.h, token))

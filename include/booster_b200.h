@@ -133,6 +133,29 @@ int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batch_gt1, b200
 int b200_stage_logits(b200_ctx * c, float * logits_out);
 int b200_stage_argmax(b200_ctx * c, int32_t * token_out);
 
+/* ---- tokenizer (host side) ----------------------------------------------------------------------
+ * The vocabulary of a GGUF (tokenizer.ggml.model = "llama" (SPM), "gpt2" (byte-level BPE, LLaMA-3 pre-tokenizer) or
+ * "no_vocab" (prompts are decimal ids)), loaded without the weights.
+ * b200_tokenize        == llama_tokenize(model, text, text_len, tokens, n_max, add_special, parse_special)
+ *                         (cpp/include/llama.h; cpp/src/llama-vocab.cpp:1243-1392,1497-1516): number of tokens, or minus
+ *                         that number when n_max is too small; INT32_MIN when the text cannot be tokenized.
+ * b200_token_to_piece  == llama_token_to_piece(model, token, buf, length, 0, special) (cpp/src/llama-vocab.cpp:1539-1608):
+ *                         bytes written (no terminator), or minus the size needed.
+ * b200_token_is_eog    == llama_token_is_eog (cpp/src/llama-vocab.cpp:1433-1439).
+ * The bridge (doInference / status) uses exactly these with add_special = 0, parse_special = 1, special = 1
+ * (cpp/bridge.cpp:275-278, 630, 640). */
+typedef struct b200_tokenizer b200_tokenizer;
+b200_tokenizer * b200_tokenizer_load(const char * gguf_path);
+void    b200_tokenizer_free(b200_tokenizer * t);
+int32_t b200_tokenizer_n_vocab(const b200_tokenizer * t);
+int32_t b200_tokenize(const b200_tokenizer * t, const char * text, int32_t text_len, int32_t * tokens, int32_t n_max,
+                      int add_special, int parse_special);
+int32_t b200_token_to_piece(const b200_tokenizer * t, int32_t token, char * buf, int32_t length, int special);
+int     b200_token_is_eog(const b200_tokenizer * t, int32_t token);
+/* codepoint classes of the LLaMA-3 pre-tokenizer regex: bit 0 \p{L}, bit 1 \p{N}, bit 2 \s (cpp/src/unicode.h:8-46,
+ * cpp/src/unicode-data.cpp) */
+int     b200_cpt_class(uint32_t cp);
+
 /* ---- operator-level entry points (parity tests; host pointers, compute on the GPU with the SAME kernels
  * the engine launches) ----------------------------------------------------------------------------------- */
 /* quantize_row_q8_K (cpp/ggml/src/ggml-quants.c:3593-3630): out = block_q8_K[k/256] in ggml layout (292 B each) */

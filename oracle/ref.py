@@ -102,8 +102,64 @@ def lib() -> C.CDLL:
         fn.restype = None
     L.ggml_quantize_chunk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
     L.ggml_quantize_chunk.restype = C.c_size_t
+    # tokenizer oracle (may be absent from a library built before the tokenizer shim existed)
+    if hasattr(L, "refshim_vocab_load"):
+        L.refshim_vocab_load.argtypes = [C.c_char_p]
+        L.refshim_vocab_load.restype = C.c_void_p
+        L.refshim_vocab_free.argtypes = [C.c_void_p]
+        L.refshim_tokenize.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int]
+        L.refshim_tokenize.restype = C.c_int
+        L.refshim_token_to_piece.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int, C.c_int]
+        L.refshim_token_to_piece.restype = C.c_int
+        L.refshim_token_is_eog.argtypes = [C.c_void_p, C.c_int32]
+        L.refshim_token_is_eog.restype = C.c_int
+        L.refshim_cpt_flags.argtypes = [C.c_uint32]
+        L.refshim_cpt_flags.restype = C.c_uint16
     L.refshim_init(1)
     return L
+
+
+def has_tokenizer() -> bool:
+    return available() and hasattr(lib(), "refshim_vocab_load")
+
+
+class RefVocab:
+    """the reference's tokenizer on a vocab-only load of a GGUF: llama_tokenize / llama_token_to_piece /
+    llama_token_is_eog (cpp/src/llama-vocab.cpp), the calls cpp/bridge.cpp:275-278, 630, 640 make"""
+
+    def __init__(self, path: str):
+        self.L = lib()
+        self.h = self.L.refshim_vocab_load(path.encode())
+        if not self.h:
+            raise RuntimeError(f"reference could not load the vocabulary of {path}")
+
+    def close(self):
+        if self.h:
+            self.L.refshim_vocab_free(self.h)
+            self.h = None
+
+    def tokenize(self, text: bytes, add_special: bool = False, parse_special: bool = True) -> List[int]:
+        cap = len(text) + 16
+        buf = (C.c_int32 * cap)()
+        n = self.L.refshim_tokenize(self.h, text, len(text), buf, cap, int(add_special), int(parse_special))
+        if n < 0:
+            raise RuntimeError("token buffer too small")
+        return list(buf[:n])
+
+    def piece(self, token: int, special: bool = True) -> bytes:
+        buf = C.create_string_buffer(512)
+        n = self.L.refshim_token_to_piece(self.h, token, buf, 512, int(special))
+        if n < 0:
+            raise RuntimeError("piece buffer too small")
+        return buf.raw[:n]
+
+    def is_eog(self, token: int) -> bool:
+        return bool(self.L.refshim_token_is_eog(self.h, token))
+
+
+def cpt_flags(cp: int) -> int:
+    """codepoint_flags of the reference's Unicode tables (cpp/src/unicode.h:8-46) as the raw uint16"""
+    return int(lib().refshim_cpt_flags(cp))
 
 
 def quantize_model(f_in: str, f_out: str, ftype: int, nthread: int = 0) -> None:

@@ -13,6 +13,8 @@
 //   decode loop:                   cpp/bridge.cpp:549-560 (llama_decode + llama_batch_get_one)
 //   logits:                        cpp/janus.cpp:224 (llama_get_logits)
 //   node tap:                      cpp/include/llama.h:324-325 (cb_eval), cpp/src/llama.cpp:14707
+//   tokenizer (vocab-only load):   cpp/bridge.cpp:275-278 (llama_tokenize, add_special=false, parse_special=true),
+//                                  cpp/bridge.cpp:630 (llama_token_to_piece), :640 (llama_token_is_eog)
 
 #include "llama.h"
 #include "ggml.h"
@@ -171,4 +173,26 @@ void refshim_timings(void * hv, double * t_p_eval_ms, int * n_p_eval, double * t
     *t_eval_ms   = t.t_eval_ms;   *n_eval   = t.n_eval;
 }
 
+// ---- tokenizer oracle: the reference's own llama_tokenize / llama_token_to_piece / llama_token_is_eog on a
+// vocab-only load of a GGUF (llama_model_params.vocab_only, cpp/include/llama.h)
+void * refshim_vocab_load(const char * path) {
+    llama_model_params mp = llama_model_default_params();
+    mp.vocab_only = true;
+    mp.n_gpu_layers = 0;
+    return llama_load_model_from_file(path, mp);
+}
+void refshim_vocab_free(void * m) { if (m) llama_free_model(static_cast<llama_model *>(m)); }
+int refshim_tokenize(void * m, const char * text, int text_len, int32_t * out, int cap, int add_special, int parse_special) {
+    return llama_tokenize(static_cast<llama_model *>(m), text, text_len, out, cap, add_special != 0, parse_special != 0);
+}
+int refshim_token_to_piece(void * m, int32_t token, char * buf, int cap, int special) {
+    return llama_token_to_piece(static_cast<llama_model *>(m), token, buf, cap, 0, special != 0);
+}
+int refshim_token_is_eog(void * m, int32_t token) { return llama_token_is_eog(static_cast<llama_model *>(m), token) ? 1 : 0; }
+
 }  // extern "C"
+
+// codepoint category flags of the reference's tables (cpp/src/unicode.h:8-46, unicode-data.cpp), for the test that pins
+// booster_b200/csrc/unicode_tables.hpp
+#include "unicode.h"
+extern "C" uint16_t refshim_cpt_flags(uint32_t cp) { return unicode_cpt_flags(cp).as_uint(); }

@@ -77,3 +77,43 @@ def test_bad_model_path_returns_null():
     L.init(b"", b"")
     assert not L.initContext(3, b"/nonexistent.gguf", 1, 0, 100, 0, 0, 0, 64, 8, 0, 0.0, 0.0, 0.0, 1, 1.0, 1.0, 1.0,
                              0, 1, 200, 1.0, 1.0, 1.0, 42, b"")
+
+
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_do_inference_with_text_prompt(kind, tmp_path):
+    """text in, text out through the nine symbols with a real vocabulary: the prompt is tokenized as
+    llama_tokenize(model, prompt, add_special=false, parse_special=true) (cpp/bridge.cpp:275-278), status() is the
+    concatenation of llama_token_to_piece of prompt and generated tokens (cpp/bridge.cpp:628-632), generation stops at
+    an end-of-generation token (cpp/bridge.cpp:640)."""
+    import dataclasses
+
+    import tokenizer_fixtures as F
+    from booster_b200 import engine, gguf_io as G
+    extra = F.vocab_kv(kind, pad_to=32)
+    n_vocab = extra["llama.vocab_size"][1]
+    cfg = dataclasses.replace(G.CONFIGS["tiny"], n_vocab=n_vocab)
+    path = str(tmp_path / f"tiny_{kind}.gguf")
+    G.synth_llama(path, cfg, "Q4_K_M", seed=5, extra_kv=extra)
+    tok = engine.Tokenizer(path)
+    prompt = "Hello world, it's 42 tokens<|user|>ok" if kind == "spm" else "Hello world, it's 42 tokens<|eot_id|>ok"
+    ids = tok.tokenize(prompt.encode(), add_special=False, parse_special=True)
+    assert 8 < len(ids) < 40
+    # the same ids through the token-level API give the generated continuation
+    m = engine.Model(path); c = engine.Context(m, 64)
+    gen, _ = c.greedy(ids, 6)
+    c.close(); m.close()
+    idx = 2 if kind == "spm" else 3
+    L, ctx = _init(path, n_ctx=64, predict=6, idx=idx)
+    assert ctx
+    job = f"job-text-{kind}".encode()
+    n = L.doInference(idx, ctx, job, b"", prompt.encode())
+    assert L.getPromptTokenCount(job) == len(ids)
+    out = L.status(job)
+    expect_ids = list(ids)
+    for g in gen:
+        expect_ids.append(g)
+        if tok.is_eog(g):
+            break
+    assert out == b"".join(tok.piece(i, True) for i in expect_ids)
+    assert n >= len(ids)
+    tok.close()

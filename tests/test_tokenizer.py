@@ -1,0 +1,122 @@
+"""Tokenizer parity: booster_b200's llama_tokenize / llama_token_to_piece / llama_token_is_eog against
+the reference's own tokenizer on synthetic SPM and byte-level-BPE (LLaMA-3 pre-tokenizer) vocabularies — token-id exact.
+Host-side code: no GPU needed. Golden vectors come from oracle/_ref (tests/golden/make_tokenizer_golden.py); where the
+reference library is present the comparison is also made live on further random strings, and the codepoint classes behind
+the pre-tokenizer regex are checked for all 0x110000 codepoints."""
+import base64
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import tokenizer_fixtures as F
+from booster_b200 import _lib, engine
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _ref():
+    try:
+        from oracle import ref
+        return ref if ref.has_tokenizer() else None
+    except Exception:
+        return None
+
+
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_golden_tokenize_bit_exact(kind):
+    g = json.load(open(os.path.join(GOLDEN, f"tokenizer_{kind}.json")))
+    t = engine.Tokenizer(os.path.join(GOLDEN, f"vocab_{kind}.gguf"))
+    n_tok = 0
+    for case in g["cases"]:
+        text = base64.b64decode(case["text_b64"])
+        for key, ids in case["ids"].items():
+            ours = t.tokenize(text, add_special=key[0] == "1", parse_special=key[1] == "1")
+            assert ours == ids, (text, key)
+            n_tok += len(ids)
+    assert n_tok > 10000                       # the fixture is not trivially empty
+    t.close()
+
+
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_golden_pieces_and_eog(kind):
+    g = json.load(open(os.path.join(GOLDEN, f"tokenizer_{kind}.json")))
+    t = engine.Tokenizer(os.path.join(GOLDEN, f"vocab_{kind}.gguf"))
+    assert t.n_vocab == len(g["pieces"])
+    for i, (sp, nosp, eog) in enumerate(g["pieces"]):
+        assert t.piece(i, True) == base64.b64decode(sp), i
+        assert t.piece(i, False) == base64.b64decode(nosp), i
+        assert t.is_eog(i) == bool(eog), i
+    assert sum(e for _, _, e in g["pieces"]) >= 1
+    t.close()
+
+
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_round_trip_through_pieces(kind):
+    """detokenizing the ids gives the text back (SPM: with the space the add_space_prefix rule inserted)"""
+    t = engine.Tokenizer(os.path.join(GOLDEN, f"vocab_{kind}.gguf"))
+    for s in ["Hello world, it's 12345 tokens.", "naïve café 日本語 😀", "a\n\n  b\t c "]:
+        ids = t.tokenize(s.encode(), False, False)
+        back = b"".join(t.piece(i, True) for i in ids)
+        assert back == ((b" " if kind == "spm" else b"") + s.encode())
+    t.close()
+
+
+def test_malformed_utf8_and_unknown_models_fail_loudly(tmp_path):
+    t = engine.Tokenizer(os.path.join(GOLDEN, "vocab_bpe.gguf"))
+    with pytest.raises(engine.B200Error):
+        t.tokenize(b"ok \xff\xfe broken", False, True)
+    t.close()
+    s = engine.Tokenizer(os.path.join(GOLDEN, "vocab_spm.gguf"))          # SPM works on bytes: byte fallback, no failure
+    assert len(s.tokenize(b"ok \xff\xfe", False, True)) >= 3
+    s.close()
+    from booster_b200 import gguf_io as G
+    kv = G.llama_kv(G.CONFIGS["tiny"], "F32", F.vocab_kv("bpe"))
+    kv["tokenizer.ggml.pre"] = ("str", "qwen2")
+    p = str(tmp_path / "other_pre.gguf")
+    G.write_gguf(p, kv, [])
+    with pytest.raises(engine.B200Error, match="not implemented"):
+        engine.Tokenizer(p)
+
+
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_live_against_reference_random_strings(kind, tmp_path):
+    ref = _ref()
+    if ref is None:
+        pytest.skip("oracle/_ref with the tokenizer shim is not available")
+    path = str(tmp_path / f"vocab_{kind}.gguf")
+    F.write_vocab_gguf(path, kind)
+    rv, t = ref.RefVocab(path), engine.Tokenizer(path)
+    for s in F.test_strings(seed=2024, n_random=400):
+        b = s.encode("utf-8")
+        for add_special in (False, True):
+            for parse_special in (False, True):
+                assert t.tokenize(b, add_special, parse_special) == rv.tokenize(b, add_special, parse_special), (s, add_special, parse_special)
+    for i in range(t.n_vocab):
+        assert t.piece(i, True) == rv.piece(i, True) and t.piece(i, False) == rv.piece(i, False) and t.is_eog(i) == rv.is_eog(i)
+    rv.close(); t.close()
+
+
+def test_codepoint_classes_equal_reference_tables():
+    """\\p{L}, \\p{N}, \\s of every codepoint (booster_b200/csrc/unicode_tables.hpp, generated from unicodedata) against the
+    reference's tables (cpp/src/unicode-data.cpp through unicode_cpt_flags)"""
+    ref = _ref()
+    if ref is None:
+        pytest.skip("oracle/_ref with the tokenizer shim is not available")
+    L, R = _lib.lib(), ref.lib()
+    LETTER, NUMBER, WHITESPACE = 0x0004, 0x0002, 0x0100          # cpp/src/unicode.h:8-36
+    bad = []
+    for cp in range(0x110000):
+        f = R.refshim_cpt_flags(cp)
+        want = (1 if f & LETTER else 0) | (2 if f & NUMBER else 0) | (4 if f & WHITESPACE else 0)
+        if L.b200_cpt_class(cp) != want:
+            bad.append(hex(cp))
+    assert not bad, bad[:20]
+    # the contraction rule lower-cases with the full Unicode map in the reference and with ASCII here: no non-ASCII
+    # codepoint lower-cases to one of the letters the rule looks at
+    tolower = getattr(R, "_Z15unicode_tolowerj")
+    tolower.restype, tolower.argtypes = C.c_uint32, [C.c_uint32]
+    hits = [hex(cp) for cp in range(128, 0x110000) if tolower(cp) in [ord(c) for c in "stmdrevl"]]
+    assert not hits, hits
