@@ -28,6 +28,7 @@
 #include <dlfcn.h>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -541,8 +542,12 @@ extern "C" int b200_n_ctx(const b200_ctx * c) { return c ? c->n_ctx : 0; }
 extern "C" int64_t b200_kernel_launches(const b200_ctx * c) { return c ? c->launches : 0; }
 
 enum { KIND_EMBED = 0, KIND_QKV, KIND_ATTN, KIND_WO, KIND_GATEUP, KIND_DOWN, KIND_HEAD, KIND_ATTN_PV, KIND_COUNT };
-static int g_kind = KIND_EMBED;   // set by enqueue_forward before each launch group
-static int g_only_kind = -1;       // b200_profile_kind: enqueue_forward launches only this kind (-1: everything)
+// (thread_local: up to 8 pods run doInference concurrently, each on its own OS thread — SURVEY §8b threading)
+static thread_local int g_kind = KIND_EMBED;   // set by enqueue_forward before each launch group
+static thread_local int g_only_kind = -1;       // b200_profile_kind: enqueue_forward launches only this kind (-1: everything)
+// function attributes (dynamic shared-memory opt-in) are raised lazily, per device, from whichever pod's thread gets
+// there first
+static std::mutex g_attr_mu;
 static bool want(int kind) { return g_only_kind < 0 || g_only_kind == kind; }
 struct ProfScope {
     b200_ctx * c; cudaEvent_t a = nullptr, b = nullptr;
@@ -631,10 +636,13 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(W, a.group, nv) + (size_t) W * a.stages * 8 + (size_t) W * 8;
     static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
     if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
-    if (smem > attr_smem[c->device & 63]) {
-        CU(cudaFuncSetAttribute(k_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        CU(cudaFuncSetAttribute(k_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attr_smem[c->device & 63] = smem;
+    {
+        std::lock_guard<std::mutex> attr_lock(g_attr_mu);
+        if (smem > attr_smem[c->device & 63]) {
+            CU(cudaFuncSetAttribute(k_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            CU(cudaFuncSetAttribute(k_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            attr_smem[c->device & 63] = smem;
+        }
     }
     const int grid = std::max(1, std::min(a.n_units, c->sm_count));
     a.trace = trace_slot(c, grid);
@@ -659,11 +667,13 @@ static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_p
     if ((int) a.n_head_kv * (128 / PVS_DIMS) <= c->sm_count) smem = std::max(smem, (size_t) 116 * 1024);
     static size_t attr[64] = {0};
     const int dv = c->device & 63;
+    std::unique_lock<std::mutex> attr_lock(g_attr_mu);
     if (smem > attr[dv]) {
         CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr[dv] = smem;
     }
+    attr_lock.unlock();
     {
         g_kind = KIND_ATTN; ProfScope ps(c);
         const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
@@ -697,7 +707,10 @@ static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pa
     const size_t pv_smem = (size_t) pch * (GQA * 4 + 32);
     static size_t attr_pv[64] = {0};   // per device (function attributes are per device)
     const int dv = c->device & 63;
-    if (pv_smem > attr_pv[dv]) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_pv[dv] = pv_smem; }
+    {
+        std::lock_guard<std::mutex> attr_lock(g_attr_mu);
+        if (pv_smem > attr_pv[dv]) { CU(cudaFuncSetAttribute(k_attn_pv<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pv_smem)); attr_pv[dv] = pv_smem; }
+    }
     const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
     {
         g_kind = KIND_ATTN; ProfScope ps(c);

@@ -117,3 +117,32 @@ def test_do_inference_with_text_prompt(kind, tmp_path):
     assert out == b"".join(tok.piece(i, True) for i in expect_ids)
     assert n >= len(ids)
     tok.close()
+
+
+def test_two_pods_concurrently_equal_sequential(golden_dir):
+    """the Go server runs one doInference per pod, up to 8 pods at once, each on its own OS thread:
+    two pods decoding at the same time on one GPU give exactly what each gives alone"""
+    path = os.path.join(golden_dir, "tiny_Q4_K_M.gguf")
+    g = np.load(os.path.join(golden_dir, "tiny_Q4_K_M.npz"))
+    prompt = " ".join(str(t) for t in g["prompt"].tolist()).encode()
+    L = _lib.lib()
+    ctxs = []
+    for idx in (4, 5):
+        _, ctx = _init(path, n_ctx=64, predict=8, idx=idx)
+        assert ctx
+        ctxs.append((idx, ctx))
+    results = {}
+
+    def run(idx, ctx, rounds):
+        for r in range(rounds):
+            job = f"pod{idx}-r{r}".encode()
+            L.doInference(idx, ctx, job, b"", prompt)
+            results[job] = L.status(job).decode()
+
+    ths = [threading.Thread(target=run, args=(idx, ctx, 6)) for idx, ctx in ctxs]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    expect = g["prompt"].tolist() + g["ids"].tolist()
+    assert len(results) == 12
+    for job, text in results.items():
+        assert [int(x) for x in text.split()] == expect, job
