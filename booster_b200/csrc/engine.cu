@@ -107,7 +107,6 @@ struct DevMat {
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-static int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
 
 struct HostTensor { int type; const void * data; int64_t rows; int64_t k; };
 
@@ -848,10 +847,6 @@ static void enqueue_forward(b200_ctx * c) {
             a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = q80;
             a.out = c->x; a.resid = c->x; a.st = c->d_state;
             pf_push(a.pf, pf_slice(L.gateup.m.p0, gu_bytes, pp.gu_scores + pp.gu_pv, pp.gu_scores + pp.gu_pv + pp.gu_wo));
-            static int dup = -1;   // diagnostic (BOOSTER_B200_DUP=1, tracing only): the wo launch twice in a row, the first into
-                                   // a scratch vector — does a kernel whose code was just executed start faster?
-            if (dup < 0) { const char * e = getenv("BOOSTER_B200_DUP"); dup = (e && e[0] == '1') ? 1 : 0; }
-            if (dup && c->tracing) { MatvecArgs d = a; d.out = c->ffh; launch_matvec(c, d, EPI_RESID); }
             launch_matvec(c, a, EPI_RESID);
             tap(c, "ffn_inp", il, c->x, (size_t) E);
         }
