@@ -19,7 +19,7 @@ BRIDGE_SYMBOLS = ["init", "initContext", "doInference", "stopInference", "status
                   "getPromptTokenCount", "timing", "getSeed"]
 B200_SYMBOLS = ["b200_last_error", "b200_device_count", "b200_version", "b200_model_load", "b200_model_free",
                 "b200_model_info", "b200_model_weight_bytes", "b200_ctx_new", "b200_ctx_free", "b200_n_ctx",
-                "b200_kv_clear", "b200_decode", "b200_generate_greedy", "b200_set_taps", "b200_get_tap",
+                "b200_kv_clear", "b200_decode", "b200_generate_greedy", "b200_step_greedy", "b200_set_taps", "b200_get_tap",
                 "b200_timings", "b200_reset_timings", "b200_kernel_launches", "b200_last_device_ms", "b200_profile_token", "b200_profile_kind", "b200_trace_token", "b200_job_timing_us", "b200_comm_unique_id",
                 "b200_comm_init", "b200_pipeline_generate_greedy", "b200_pipeline_decode", "b200_stage_forward",
                 "b200_stage_logits", "b200_stage_argmax", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     sig("b200_reset_timings", None, [vp])
     sig("b200_kernel_launches", C.c_int64, [vp])
     sig("b200_last_device_ms", C.c_float, [vp])
+    sig("b200_step_greedy", C.c_int, [vp, C.c_int32, C.c_int, i32p])
     sig("b200_tokenizer_load", vp, [cp])
     sig("b200_tokenizer_free", None, [vp])
     sig("b200_tokenizer_n_vocab", C.c_int32, [vp])

@@ -214,18 +214,31 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
         consumed += n;
     }
 
-    // ---- generation: sample (greedy, on device) then decode the sampled token (cpp/bridge.cpp:586-646)
+    // ---- generation: sample (greedy, on device) then decode the sampled token (cpp/bridge.cpp:586-646).
+    // A pod on one GPU replays one CUDA graph per token (b200_step_greedy: decode + arg-max + 4-byte read-back); a
+    // layer-split pod chains its stages with plain launches and peer copies.
+    static const bool graph_ok = [] { const char * e = std::getenv("BOOSTER_B200_BRIDGE_GRAPH"); return !(e && e[0] == '0'); }();   // A/B switch
+    const bool single = p.stages.size() == 1 && graph_ok;
+    int32_t id = 0;
+    bool have_id = false;
     while (n_remain != 0 && n_past < max_embd && !g_stop[idx].load()) {
-        int32_t id = 0;
         const double t0 = now_us();
-        if (b200_stage_argmax(last, &id) != 0) return 1;
+        if (!have_id) { if (b200_stage_argmax(last, &id) != 0) return 1; }
+        have_id = false;
         --n_remain;
         { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += p.tok->piece(id, true); }
         if (p.tok->is_eog(id)) break;                      // cpp/bridge.cpp:640
         if (n_remain == 0 || n_past >= max_embd) break;
-        if (run_token(p, id, n_past, 0) != 0) return 1;
+        if (single) {
+            int32_t next = 0;
+            if (b200_step_greedy(last, id, n_past, &next) != 0) return 1;
+            id = next; have_id = true;
+        } else {
+            if (run_token(p, id, n_past, 0) != 0) return 1;
+        }
         n_past += 1;
-        // launches are asynchronous: the interval that ends at the NEXT arg-max's sync is what one token costs
+        // single stage: the step is synchronous; layer split: launches are asynchronous and the interval that ends at
+        // the NEXT arg-max's sync is what one token costs
         t_e_us += now_us() - t0; n_eval += 1;
     }
     // per-token timings, integer milliseconds like the reference (cpp/bridge.cpp:650-655)

@@ -511,6 +511,9 @@ struct b200_ctx {
     cudaGraphExec_t g_logits = nullptr;   // H2D state -> forward -> D2H logits
     cudaGraphExec_t g_greedy = nullptr;   // forward -> argmax -> advance
     cudaGraphExec_t g_pipe = nullptr;     // pipeline stage step (recv -> forward -> send)
+    cudaGraphExec_t g_step = nullptr;     // H2D state -> forward -> arg-max -> D2H token (b200_step_greedy)
+    int64_t n_step = 0;
+    int32_t * h_tok = nullptr;            // pinned: the token b200_step_greedy hands back
     int64_t n_logits = 0, n_greedy = 0, n_pipe = 0;   // kernels per replay of g_logits / g_greedy / g_pipe
     int pipe_calls = 0;                   // b200_pipeline_generate_greedy calls so far (the first one runs un-graphed: NCCL connects lazily)
     bool pipe_graph_failed = false;
@@ -958,6 +961,7 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         CU(cudaMemsetAsync(c->d_state, 0, sizeof(DecodeState), c->st));
         CU(cudaMallocHost(&c->h_state, sizeof(DecodeState)));
         CU(cudaMallocHost(&c->h_logits, (size_t) m->n_vocab * 4));
+        CU(cudaMallocHost(&c->h_tok, sizeof(int32_t)));
         c->out_tokens_cap = c->n_ctx + 8;
         CU(cudaMalloc(&c->d_out_tokens, (size_t) c->out_tokens_cap * 4));
         CU(cudaStreamSynchronize(c->st));
@@ -982,7 +986,8 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->warm_x); cudaFree(c->logits);
     cudaFree(c->d_trace);
     cudaFree(c->S); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
-    cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits);
+    cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits); cudaFreeHost(c->h_tok);
+    if (c->g_step) cudaGraphExecDestroy(c->g_step);
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -1086,6 +1091,43 @@ extern "C" int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0,
     } catch (const std::exception & e) {
         return set_err(e.what());
     }
+}
+
+// One generated token through a single-stage context, the way the bridge's generation loop needs it: decode `token`
+// at `pos` (batch-1 arithmetic) and hand back the arg-max of its logits — llama_decode + sample_top_token
+// (cpp/bridge.cpp:549-560, 962-981) as ONE CUDA-graph replay (state H2D -> forward -> arg-max -> 4-byte D2H) and one
+// synchronisation, instead of ~195 plain launches per token.
+extern "C" int b200_step_greedy(b200_ctx * c, int32_t token, int pos, int32_t * next_token) {
+    try {
+        require_gpu();
+        if (!c || !next_token) throw std::runtime_error("bad arguments");
+        b200_model & m = *c->m;
+        if (!m.has_embd() || !m.has_head()) throw std::runtime_error("b200_step_greedy needs a single-stage context (use b200_stage_forward for layer splits)");
+        if (pos < 0 || pos >= c->n_ctx) throw std::runtime_error("position exceeds n_ctx");
+        if (token < 0 || token >= m.n_vocab) throw std::runtime_error("token id out of range");
+        CU(cudaSetDevice(m.device));
+        c->h_state->token = token; c->h_state->pos = pos; c->h_state->round_q = 0; c->h_state->step = 0;
+        if (c->taps) {                                         // taps need the un-graphed path
+            CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
+            enqueue_forward(c);
+            enqueue_argmax(c, 0);
+            CU(cudaMemcpyAsync(c->h_tok, c->d_out_tokens, 4, cudaMemcpyDeviceToHost, c->st));
+        } else {
+            if (!c->g_step) {
+                c->g_step = capture(c, [&]() {
+                    CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
+                    enqueue_forward(c);
+                    enqueue_argmax(c, 0);
+                    CU(cudaMemcpyAsync(c->h_tok, c->d_out_tokens, 4, cudaMemcpyDeviceToHost, c->st));
+                }, &c->n_step);
+            }
+            CU(cudaGraphLaunch(c->g_step, c->st));
+            c->launches += c->n_step;
+        }
+        CU(cudaStreamSynchronize(c->st));
+        *next_token = *c->h_tok;
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
 }
 
 extern "C" float b200_last_device_ms(const b200_ctx * c) { return c ? c->last_device_ms : 0.f; }

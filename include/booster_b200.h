@@ -74,6 +74,10 @@ int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, float * l
  * argmax sampling (cpp/bridge.cpp:962-981 sample_top_token). out_tokens[n_steps] receives the sampled ids. */
 int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0, int n_steps, int32_t * out_tokens);
 
+/* One generated token of the bridge's loop on a single-stage context: llama_decode of `token` at `pos` followed by the
+ * arg-max of its logits (cpp/bridge.cpp:549-560, 962-981), as one CUDA-graph replay and one synchronisation. */
+int b200_step_greedy(b200_ctx * c, int32_t token, int pos, int32_t * next_token);
+
 /* Per-node taps for layer-wise parity (the counterpart of llama_context_params.cb_eval,
  * cpp/include/llama.h:324-325; node names cpp/src/llama.cpp:13812-13817). When enabled, b200_decode runs
  * un-graphed and keeps host copies of: "Qcur" (post-RoPE), "kqv_merged_cont", "ffn_inp", "ffn_gate_par",
