@@ -1080,9 +1080,17 @@ extern "C" int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0,
         }
         if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
         CU(cudaEventRecord(c->ev_t0, c->st));
-        for (int s = 0; s < n_steps; s++) CU(cudaGraphLaunch(c->g_greedy, c->st));
+        // BOOSTER_B200_NO_GRAPH=1 (A/B): the same kernels as plain stream launches — the token's scalars live in device
+        // memory, so nothing but the launch mechanism changes
+        static int no_graph = -1;
+        if (no_graph < 0) { const char * e = getenv("BOOSTER_B200_NO_GRAPH"); no_graph = (e && e[0] == '1') ? 1 : 0; }
+        if (no_graph) {
+            for (int s = 0; s < n_steps; s++) { enqueue_forward(c); enqueue_argmax(c, 1); }
+        } else {
+            for (int s = 0; s < n_steps; s++) CU(cudaGraphLaunch(c->g_greedy, c->st));
+            c->launches += c->n_greedy * (int64_t) n_steps;
+        }
         CU(cudaEventRecord(c->ev_t1, c->st));
-        c->launches += c->n_greedy * (int64_t) n_steps;
         if (out_tokens) CU(cudaMemcpyAsync(out_tokens, c->d_out_tokens, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
         CU(cudaEventElapsedTime(&c->last_device_ms, c->ev_t0, c->ev_t1));
