@@ -120,3 +120,31 @@ def test_codepoint_classes_equal_reference_tables():
     tolower.restype, tolower.argtypes = C.c_uint32, [C.c_uint32]
     hits = [hex(cp) for cp in range(128, 0x110000) if tolower(cp) in [ord(c) for c in "stmdrevl"]]
     assert not hits, hits
+
+
+def test_truncated_and_corrupted_gguf_fail_without_crashing(tmp_path):
+    """the container parser (booster_b200/csrc/gguf.cpp) bounds-checks every read: a cut or damaged file is an error
+    message, never a crash (the reference aborts on most of these)"""
+    data = open(os.path.join(GOLDEN, "vocab_bpe.gguf"), "rb").read()
+    rng = np.random.default_rng(3)
+    cuts = [0, 3, 4, 12, 24, 100, 5000, len(data) - 1] + [int(c) for c in rng.integers(0, len(data), size=12)]
+    for i, c in enumerate(cuts):
+        p = str(tmp_path / f"cut{i}.gguf")
+        open(p, "wb").write(data[:c])
+        try:
+            t = engine.Tokenizer(p)          # a cut inside the padding after the last key still loads
+            t.close()
+        except engine.B200Error:
+            pass
+    for i in range(12):
+        b = bytearray(data)
+        for pos in rng.integers(0, len(data), size=3):
+            b[int(pos)] = int(rng.integers(0, 256))
+        p = str(tmp_path / f"flip{i}.gguf")
+        open(p, "wb").write(bytes(b))
+        try:
+            t = engine.Tokenizer(p)
+            t.tokenize(b"hello world 123", False, True)
+            t.close()
+        except engine.B200Error:
+            pass
