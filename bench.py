@@ -94,8 +94,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(path, steps, warmup, sample_tokens=8, n_prompt=64):
-    """the reference's own CPU llama_decode on the host cores; returns (tokens/s, info)"""
+def cpu_reference_run(path, steps, warmup, sample_tokens=None, n_prompt=64):
+    """the reference's own CPU llama_decode on the host cores; returns (tokens/s, info). A step is `sample_tokens` greedy
+    decode tokens (default: up to 32, capped so that the whole run stays inside ctx 512 — BASELINE.md §2: 64-token prompt,
+    then >= 128 decode steps when the step count allows)"""
+    if sample_tokens is None:
+        sample_tokens = max(1, min(32, 400 // max(1, steps)))
     from oracle import ref
     cores = os.cpu_count() or 1
     best = None
@@ -133,7 +137,7 @@ def cpu_reference_run(path, steps, warmup, sample_tokens=8, n_prompt=64):
     tm = r.timings()
     r.close()
     lib_tps = 1e3 * tm["n_eval"] / tm["t_eval_ms"] if tm["t_eval_ms"] > 0 else None
-    return n / dt, {"cores": th, "host_cores": cores, "kind": "reference", "variant": ref.variant(),
+    return n / dt, {"cores": th, "host_cores": cores, "kind": "reference", "variant": ref.variant(), "tokens_per_step": sample_tokens,
                     "sample": f"{n} greedy decode steps (batch 1, n_kv {n_prompt}..{pos}) after a {n_prompt}-token prefill, ctx 512, "
                               f"threads={th} (best of {cands})", "llama_timings_tok_s": lib_tps}
 
@@ -163,7 +167,7 @@ def main():
         path = model_path()
         tps, info = cpu_reference_run(path, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "decode tokens/sec", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 8 / tps, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["tokens_per_step"] / tps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "q4_K x q8_K int8 dot, f32 accumulate", "data": "synthetic",
                 "config": config, "cpu_baseline": dict(info, value=tps, unit="tokens/s"),
                 "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -295,7 +299,7 @@ def main():
         try:
             if args.no_cpu:
                 raise RuntimeError("skipped (--no-cpu)")
-            cpu_tps, info = cpu_reference_run(path, steps=2, warmup=1)
+            cpu_tps, info = cpu_reference_run(path, steps=4, warmup=1)
             line["cpu_baseline"] = dict(info, value=cpu_tps, unit="tokens/s")
         except Exception as e:  # the oracle library failing to load must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
