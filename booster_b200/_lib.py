@@ -25,7 +25,7 @@ B200_SYMBOLS = ["b200_last_error", "b200_device_count", "b200_version", "b200_mo
                 "b200_stage_logits", "b200_stage_argmax", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
                 "b200_op_dequantize_row", "b200_op_mul_mat_vec", "b200_op_rms_norm", "b200_op_rope",
                 "b200_op_attention", "b200_tokenizer_load", "b200_tokenizer_free", "b200_tokenizer_n_vocab", "b200_tokenize",
-                "b200_token_to_piece", "b200_token_is_eog", "b200_cpt_class"]
+                "b200_token_to_piece", "b200_token_is_eog", "b200_cpt_class", "b200_op_launch_shape"]
 
 
 def lib() -> C.CDLL:
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     sig("b200_token_to_piece", C.c_int32, [vp, C.c_int32, C.c_char_p, C.c_int32, C.c_int])
     sig("b200_token_is_eog", C.c_int, [vp, C.c_int32])
     sig("b200_cpt_class", C.c_int, [C.c_uint32])
+    sig("b200_op_launch_shape", C.c_int, [i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, i32p])
     sig("b200_profile_token", C.c_int, [vp, C.c_int32, C.c_int, f32p, i32p])
     sig("b200_profile_kind", C.c_int, [vp, C.c_int, C.c_int, C.c_int, f32p, i32p])
     sig("b200_trace_token", C.c_int64, [vp, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int64, i32p, C.c_int64])

@@ -585,6 +585,44 @@ static unsigned long long * trace_slot(b200_ctx * c, int ctas) {
     return c->d_trace + (size_t) (c->trace_seq++) * TRACE_CTAS * TRACE_PHASES;
 }
 
+// launch shape of one mat-vec: W warps per CTA (one CTA per SM), S ring stages per warp, G warps per 32-row unit. Pick the
+// combination with the most concurrently active warps (every unit resident in as few waves as possible), then the
+// deepest ring that still fits the shared memory. Pure host arithmetic (b200_op_launch_shape exposes it to the tests).
+static void pick_launch_shape(int n_units, int tiles_unit, int k, bool norm, int act_q8_0, int stage_bytes, int nv, int sm_count,
+                              int & bestW, int & bestG, int & bestS) {
+    const size_t act_bytes = act_smem_bytes(k, act_q8_0);
+    const size_t budget = 227 * 1024 - 512;
+    bestW = 0; bestG = 1; bestS = 0;
+    double best = -1;
+    for (int W = MV_MAX_WARPS; W >= 4; W -= 2) {
+        for (int G = W; G >= 1; G--) {
+            if (W % G) continue;
+            if (G > 1 && (long long) n_units * G > (long long) sm_count * W) continue;   // sharing only within one wave
+            if (tiles_unit % G) continue;                                               // warp w owns tiles w, w+G, ... of every unit
+            if (norm && k / 256 > PRO_U * W) continue;                                  // the normed vector is quantized in one pass
+            const size_t fixed = act_bytes + chain_smem_bytes(W, G, nv) + (size_t) W * 4 * 8 + (size_t) W * 8;
+            if (fixed + (size_t) W * 2 * stage_bytes > budget) continue;
+            const int S = (int) std::min<size_t>(4, (budget - fixed) / ((size_t) W * stage_bytes));
+            const long long warps = (long long) n_units * G, slots = (long long) sm_count * W;
+            const long long waves = (warps + slots - 1) / slots;
+            const double active = (double) warps / (double) waves + 0.01 * S;   // average concurrently running warps
+            if (active > best) { best = active; bestW = W; bestG = G; bestS = S; }
+            break;   // largest feasible G for this W
+        }
+    }
+}
+// (W, G, S) the engine would launch a mat-vec with: `types` = block types of the launch's segments, n_units = rows / 32
+extern "C" int b200_op_launch_shape(const int32_t * types, int n_types, int64_t n_units, int64_t k, int norm, int sm_count, int32_t wgs[3]) {
+    if (!types || n_types <= 0 || !wgs || k <= 0 || k % 256) return set_err("bad arguments");
+    int sb = 0, nv = 0;
+    for (int i = 0; i < n_types; i++) { sb = std::max(sb, tile_bytes_of(types[i])); nv = std::max(nv, chain_values_of(types[i])); }
+    const int q80 = types[0] == T_Q8_0;
+    int W, G, S;
+    pick_launch_shape((int) n_units, (int) (k / (q80 ? 32 : 256)), (int) k, norm != 0, q80, (sb + 127) / 128 * 128, nv, sm_count, W, G, S);
+    wgs[0] = W; wgs[1] = G; wgs[2] = S;
+    return W == 0 ? set_err("activation vector too long for the shared-memory budget") : 0;
+}
+
 static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     ProfScope ps(c);
     MatvecArgs a = a_in;
@@ -598,28 +636,9 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     int nv = 0;
     for (int i = 0; i < a.n_seg; i++) nv = std::max(nv, chain_values_of(a.seg[i].type));
     a.nv = nv;
-    // launch shape: W warps per CTA (one CTA per SM), S ring stages per warp, G warps per 32-row unit. Pick the
-    // combination with the most concurrently active warps (every unit resident in as few waves as possible),
-    // then the deepest ring that still fits the shared memory.
     const size_t act_bytes = act_smem_bytes(a.k, a.act_q8_0);
-    const size_t budget = 227 * 1024 - 512;
-    int bestW = 0, bestG = 1, bestS = 0; double best = -1;
-    for (int W = MV_MAX_WARPS; W >= 4; W -= 2) {
-        for (int G = W; G >= 1; G--) {
-            if (W % G) continue;
-            if (G > 1 && (long long) a.n_units * G > (long long) c->sm_count * W) continue;   // sharing only within one wave
-            if (a.tiles_unit % G) continue;                                                   // warp w owns tiles w, w+G, ... of every unit
-            if (a.norm_w != nullptr && a.k / 256 > PRO_U * W) continue;                       // the normed vector is quantized in one pass
-            const size_t fixed = act_bytes + chain_smem_bytes(W, G, nv) + (size_t) W * 4 * 8 + (size_t) W * 8;
-            if (fixed + (size_t) W * 2 * a.stage_bytes > budget) continue;
-            const int S = (int) std::min<size_t>(4, (budget - fixed) / ((size_t) W * a.stage_bytes));
-            const long long warps = (long long) a.n_units * G, slots = (long long) c->sm_count * W;
-            const long long waves = (warps + slots - 1) / slots;
-            const double active = (double) warps / (double) waves + 0.01 * S;   // average concurrently running warps
-            if (active > best) { best = active; bestW = W; bestG = G; bestS = S; }
-            break;   // largest feasible G for this W
-        }
-    }
+    int bestW = 0, bestG = 1, bestS = 0;
+    pick_launch_shape(a.n_units, a.tiles_unit, a.k, a.norm_w != nullptr, a.act_q8_0, a.stage_bytes, nv, c->sm_count, bestW, bestG, bestS);
     if (bestW == 0) throw std::runtime_error("activation vector too long for the shared-memory budget");
     a.group = bestG; a.stages = bestS;
     a.inv_k = (a.k & (a.k - 1)) == 0 ? 1.0 / (double) a.k : 0.0;

@@ -137,6 +137,10 @@ int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batch_gt1, b200
 int b200_stage_logits(b200_ctx * c, float * logits_out);
 int b200_stage_argmax(b200_ctx * c, int32_t * token_out);
 
+/* launch shape (warps per CTA, warps sharing a 32-row unit, ring stages per warp) the engine picks for a mat-vec whose
+ * segments have the given block types: pure host arithmetic, exposed so that tests pin the shapes */
+int b200_op_launch_shape(const int32_t * types, int n_types, int64_t n_units, int64_t k, int norm, int sm_count, int32_t wgs[3]);
+
 /* ---- tokenizer (host side) ----------------------------------------------------------------------
  * The vocabulary of a GGUF (tokenizer.ggml.model = "llama" (SPM), "gpt2" (byte-level BPE, LLaMA-3 pre-tokenizer) or
  * "no_vocab" (prompts are decimal ids)), loaded without the weights.
