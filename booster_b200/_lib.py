@@ -22,7 +22,7 @@ B200_SYMBOLS = ["b200_last_error", "b200_device_count", "b200_version", "b200_mo
                 "b200_kv_clear", "b200_decode", "b200_generate_greedy", "b200_step_greedy", "b200_set_taps", "b200_get_tap",
                 "b200_timings", "b200_reset_timings", "b200_kernel_launches", "b200_last_device_ms", "b200_profile_token", "b200_profile_kind", "b200_trace_token", "b200_job_timing_us", "b200_comm_unique_id",
                 "b200_comm_init", "b200_pipeline_generate_greedy", "b200_pipeline_decode", "b200_stage_forward",
-                "b200_stage_logits", "b200_stage_argmax", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
+                "b200_stage_logits", "b200_stage_argmax", "b200_stage_sync", "b200_kv_write", "b200_kv_read", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
                 "b200_op_dequantize_row", "b200_op_mul_mat_vec", "b200_op_rms_norm", "b200_op_rope",
                 "b200_op_attention", "b200_tokenizer_load", "b200_tokenizer_free", "b200_tokenizer_n_vocab", "b200_tokenize",
                 "b200_token_to_piece", "b200_token_is_eog", "b200_cpt_class", "b200_op_launch_shape"]
@@ -95,6 +95,9 @@ def lib() -> C.CDLL:
     sig("b200_stage_forward", C.c_int, [vp, C.c_int32, C.c_int, C.c_int, vp])
     sig("b200_stage_logits", C.c_int, [vp, f32p])
     sig("b200_stage_argmax", C.c_int, [vp, i32p])
+    sig("b200_stage_sync", C.c_int, [vp])
+    sig("b200_kv_write", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)])
+    sig("b200_kv_read", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)])
     sig("b200_op_quantize_q8_K", C.c_int, [f32p, C.c_int64, vp])
     sig("b200_op_quantize_q8_0", C.c_int, [f32p, C.c_int64, vp])
     sig("b200_op_dequantize_row", C.c_int, [C.c_int, vp, C.c_int64, f32p])

@@ -39,6 +39,12 @@ struct Pod {
     std::vector<b200_ctx *>   stages;
     std::unique_ptr<b200::Tokenizer> tok;
     int n_vocab = 0;
+    // contexts first, then the models they point into
+    void release() {
+        for (b200_ctx * c : stages) b200_ctx_free(c);
+        for (b200_model * m : models) b200_model_free(m);
+        stages.clear(); models.clear(); tok.reset();
+    }
 };
 
 Pod               g_pods[MAX_PODS];
@@ -111,6 +117,7 @@ void * initContext(
     (void) scale; (void) hi; (void) lo; (void) debug;
     if (idx < 0 || idx >= MAX_PODS || !modelName) return nullptr;
     Pod & p = g_pods[idx];
+    p.release();                          // re-initialising a pod frees its previous weights and KV cache
     p = Pod();
     p.model_path = modelName;
     p.seed = seed;
@@ -149,10 +156,11 @@ void * initContext(
     for (int il = 0; il < n_layer;) {
         int e = il; while (e < n_layer && dev[(size_t) e] == dev[(size_t) il]) e++;
         b200_model * m = b200_model_load(modelName, dev[(size_t) il], il, e);
-        if (!m) { std::fprintf(stderr, "initContext: %s\n", b200_last_error()); return nullptr; }
+        if (!m) { std::fprintf(stderr, "initContext: %s\n", b200_last_error()); p.release(); return nullptr; }
+        p.models.push_back(m);
         b200_ctx * c = b200_ctx_new(m, n_ctx);
-        if (!c) { std::fprintf(stderr, "initContext: %s\n", b200_last_error()); return nullptr; }
-        p.models.push_back(m); p.stages.push_back(c);
+        if (!c) { std::fprintf(stderr, "initContext: %s\n", b200_last_error()); p.release(); return nullptr; }
+        p.stages.push_back(c);
         il = e;
     }
     p.n_ctx = b200_n_ctx(p.stages[0]);
@@ -161,7 +169,7 @@ void * initContext(
     p.n_batch = (batch_size > 0 && batch_size <= p.n_ctx) ? batch_size : 512;
     std::string terr;
     p.tok = b200::make_tokenizer(modelName, terr);
-    if (!p.tok) { std::fprintf(stderr, "initContext: %s\n", terr.c_str()); return nullptr; }
+    if (!p.tok) { std::fprintf(stderr, "initContext: %s\n", terr.c_str()); p.release(); return nullptr; }
     return (void *) &p;
 }
 
@@ -202,9 +210,9 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
         for (size_t i = 0; i < n; i++) {
             if (run_token(p, inp[consumed + i], n_past + (int) i, n > 1 ? 1 : 0) != 0) return 1;   // llama_decode failed: bridge.cpp:556-558
         }
-        // synchronise the chain end so that the chunk time is real (the last chunk is synchronised by the
-        // first arg-max of the generation loop)
-        if (consumed + n != inp.size()) { int32_t t; if (b200_stage_argmax(last, &t) != 0) return 1; }
+        // every chunk is a blocking llama_decode in the reference (cpp/bridge.cpp:549-560): synchronise the chain end so
+        // that the chunk's time is the prompt's and not the first generated token's
+        if (b200_stage_sync(last) != 0) return 1;
         const double dt = now_us() - t0;
         if (n > 1) { t_p_us += dt; n_p_eval += (int64_t) n; } else { t_e_us += dt; n_eval += 1; }
         n_past += (int) n;

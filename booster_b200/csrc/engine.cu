@@ -138,14 +138,16 @@ static DevMat upload_tiled(const HostTensor * src, int n_src, cudaStream_t st) {
     CU(cudaMalloc(&base, align_up((size_t) tile_bytes_of(type) * n_tiles, 256)));
     d.alloc = base;
     uint8_t * tmp = nullptr;
-    CU(cudaMalloc(&tmp, raw1));
-    for (int i = 0; i < n_src; i++) {
-        CU(cudaMemcpyAsync(tmp, src[i].data, raw1, cudaMemcpyHostToDevice, st));
-        const int64_t n_blocks = rows1 * nb;
-        k_retile<<<(unsigned) ((n_blocks + 127) / 128), 128, 0, st>>>(type, tmp, rows1, nb, n_src, i, base);
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(st));
-    }
+    try {
+        CU(cudaMalloc(&tmp, raw1));
+        for (int i = 0; i < n_src; i++) {
+            CU(cudaMemcpyAsync(tmp, src[i].data, raw1, cudaMemcpyHostToDevice, st));
+            const int64_t n_blocks = rows1 * nb;
+            k_retile<<<(unsigned) ((n_blocks + 127) / 128), 128, 0, st>>>(type, tmp, rows1, nb, n_src, i, base);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(st));
+        }
+    } catch (...) { cudaFree(tmp); cudaFree(base); throw; }
     CU(cudaFree(tmp));
     d.m.p0 = base;
     return d;
@@ -176,6 +178,8 @@ static DevStack upload_stack(const HostTensor * src, int n_src, cudaStream_t st)
     CU(cudaMalloc(&base, align_up(total, 256)));
     d.alloc = base;
     size_t off = 0;
+    uint8_t * tmp = nullptr;
+    try {
     for (int i = 0; i < n_src; i++) {
         const int type = src[i].type;
         int blk_bytes = 0, wpb = 256;
@@ -188,7 +192,6 @@ static DevStack upload_stack(const HostTensor * src, int n_src, cudaStream_t st)
         }
         const int nb = (int) (k / wpb);
         const size_t raw = (size_t) blk_bytes * nb * src[i].rows;
-        uint8_t * tmp = nullptr;
         CU(cudaMalloc(&tmp, raw));
         CU(cudaMemcpyAsync(tmp, src[i].data, raw, cudaMemcpyHostToDevice, st));
         const int64_t n_blocks = src[i].rows * nb;
@@ -196,6 +199,7 @@ static DevStack upload_stack(const HostTensor * src, int n_src, cudaStream_t st)
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(st));
         CU(cudaFree(tmp));
+        tmp = nullptr;
         d.bytes += raw;
         if (d.n_seg > 0 && d.seg[d.n_seg - 1].type == type) {
             TMat & m = d.seg[d.n_seg - 1];
@@ -208,6 +212,7 @@ static DevStack upload_stack(const HostTensor * src, int n_src, cudaStream_t st)
         d.n_units += (int) (src[i].rows / 32);
         off += (size_t) tile_bytes_of(type) * (size_t) (src[i].rows / 32) * nb;
     }
+    } catch (...) { cudaFree(tmp); cudaFree(base); throw; }
     return d;
 }
 
@@ -270,7 +275,10 @@ static DevMat upload_named(const gguf_file & g, const std::string & name, int64_
     return upload_matrix((int) t->type, t->data, rows, k, st);
 }
 
+extern "C" void b200_model_free(b200_model * m);
 extern "C" b200_model * b200_model_load(const char * path, int device, int layer_begin, int layer_end) {
+    std::unique_ptr<b200_model> m;
+    cudaStream_t st = nullptr;
     try {
         require_gpu();
         gguf_file g;
@@ -278,7 +286,7 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
         if (!err.empty()) throw std::runtime_error(err);
         const std::string arch = g.get_s("general.architecture", "");
         if (arch != "llama") throw std::runtime_error("unsupported architecture '" + arch + "' (this path covers LLM_ARCH_LLAMA only)");
-        auto m = std::make_unique<b200_model>();
+        m = std::make_unique<b200_model>();
         m->device = device;
         CU(cudaSetDevice(device));
         // hparams: cpp/src/llama.cpp:4571-4700
@@ -319,7 +327,6 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
         m->tok_eos = (int32_t) g.get_u("tokenizer.ggml.eos_token_id", (uint64_t) -1);
         m->tok_bos = (int32_t) g.get_u("tokenizer.ggml.bos_token_id", (uint64_t) -1);
 
-        cudaStream_t st;
         CU(cudaStreamCreate(&st));
         const int E = m->n_embd, HD = m->head_dim, KV = m->n_head_kv * HD, Q = m->n_head * HD, FF = m->n_ff;
         if (const gguf_tensor * rf = g.find("rope_freqs.weight")) {
@@ -329,7 +336,8 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
         int64_t wb = 0;
         for (int il = layer_begin; il < layer_end; il++) {
             const std::string p = "blk." + std::to_string(il) + ".";
-            LayerW L;
+            m->layers.emplace_back();          // registered first: a failure below frees what this layer already uploaded
+            LayerW & L = m->layers.back();
             L.attn_norm = upload_f32(g.find(p + "attn_norm.weight"), E, st);
             L.ffn_norm  = upload_f32(g.find(p + "ffn_norm.weight"), E, st);
             {
@@ -359,7 +367,6 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
             for (const DevMat * d : { &L.wo, &L.gateup, &L.down })
                 if ((d->m.type == T_Q8_0) != q80) throw std::runtime_error("mixing Q8_0 and K-quant matrices inside one layer is not supported");
             wb += (int64_t) (L.qkv.bytes + L.wo.bytes + L.gateup.bytes + L.down.bytes) + 2 * (int64_t) E * 4;
-            m->layers.push_back(L);
         }
         if (m->has_embd()) {
             m->embd_type = (int) te->type;
@@ -377,10 +384,15 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
         }
         CU(cudaStreamSynchronize(st));
         CU(cudaStreamDestroy(st));
+        st = nullptr;
         m->weight_bytes = wb;
         return m.release();
     } catch (const std::exception & e) {
         set_err(e.what());
+        // a failed load (out of memory, bad tensor) must not keep the layers it already uploaded
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        if (m) b200_model_free(m.release());
+        cudaGetLastError();
         return nullptr;
     }
 }
@@ -523,7 +535,9 @@ struct b200_ctx {
     // pipeline
     void * comm = nullptr;
     int rank = 0, world = 1;
-    cudaEvent_t ev_done = nullptr;     // in-process stage chain hand-off
+    cudaEvent_t ev_done = nullptr;     // in-process stage chain hand-off: this stage's l_out is complete
+    cudaEvent_t ev_taken = nullptr;    // ... and the NEXT stage has copied it out of c->x (recorded on the consumer's stream)
+    bool taken_pending = false;        // ev_taken was recorded since this stage last waited on it
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // device time of the last generate/decode call
     float last_device_ms = 0.f;
     // phase trace (b200_trace_token): [launch][TRACE_CTAS][TRACE_PHASES] globaltimer stamps
@@ -931,11 +945,13 @@ static cudaGraphExec_t capture(b200_ctx * c, const std::function<void()> & body,
     return ge;
 }
 
+extern "C" void b200_ctx_free(b200_ctx * c);
 extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
+    std::unique_ptr<b200_ctx> c;
     try {
         require_gpu();
         if (!m) throw std::runtime_error("null model");
-        auto c = std::make_unique<b200_ctx>();
+        c = std::make_unique<b200_ctx>();
         c->m = m;
         c->device = m->device;
         CU(cudaSetDevice(m->device));
@@ -988,6 +1004,8 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         return c.release();
     } catch (const std::exception & e) {
         set_err(e.what());
+        if (c) b200_ctx_free(c.release());     // whatever was allocated so far (cudaFree(nullptr) is a no-op)
+        cudaGetLastError();
         return nullptr;
     }
 }
@@ -995,7 +1013,7 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
 extern "C" void b200_ctx_free(b200_ctx * c) {
     if (!c) return;
     cudaSetDevice(c->m->device);
-    cudaStreamSynchronize(c->st);
+    if (c->st) cudaStreamSynchronize(c->st);
     if (c->g_logits) cudaGraphExecDestroy(c->g_logits);
     if (c->g_greedy) cudaGraphExecDestroy(c->g_greedy);
     if (c->g_pipe)   cudaGraphExecDestroy(c->g_pipe);
@@ -1007,7 +1025,10 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     cudaFree(c->S); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits); cudaFreeHost(c->h_tok);
     if (c->g_step) cudaGraphExecDestroy(c->g_step);
-    cudaStreamDestroy(c->st);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
+    if (c->ev_taken) cudaEventDestroy(c->ev_taken);
+    if (c->ev_t0) { cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1); }
+    if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
 
@@ -1016,6 +1037,40 @@ extern "C" void b200_kv_clear(b200_ctx * c) {
     // the cache is addressed by position and attention only reads slots [0, pos]; clearing is a reset of counters
     cudaSetDevice(c->m->device);
     cudaStreamSynchronize(c->st);
+}
+
+// Rows [pos0, pos0 + n) of one local layer's K (post-RoPE) and V cache, f16 bits [n][n_head_kv * head_dim] — the view
+// llama_kv_cache exposes through k_l / v_l (cpp/src/llama.cpp:2495-2539; V returned position-major). Tests use the pair
+// to start both sides of a parity check from the same cache at n_kv in the thousands, and to check the K-shift.
+extern "C" int b200_kv_write(b200_ctx * c, int layer, int pos0, int n, const uint16_t * k_rows, const uint16_t * v_rows) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        const int li = layer - c->m->layer_begin;
+        if (li < 0 || li >= (int) c->kc.size()) throw std::runtime_error("layer is not on this stage");
+        if (pos0 < 0 || n < 0 || pos0 + n > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");
+        const size_t row = (size_t) c->m->n_head_kv * c->m->head_dim * 2;
+        CU(cudaSetDevice(c->m->device));
+        if (k_rows) CU(cudaMemcpyAsync((uint8_t *) c->kc[(size_t) li] + pos0 * row, k_rows, n * row, cudaMemcpyHostToDevice, c->st));
+        if (v_rows) CU(cudaMemcpyAsync((uint8_t *) c->vc[(size_t) li] + pos0 * row, v_rows, n * row, cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+extern "C" int b200_kv_read(b200_ctx * c, int layer, int pos0, int n, uint16_t * k_rows, uint16_t * v_rows) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        const int li = layer - c->m->layer_begin;
+        if (li < 0 || li >= (int) c->kc.size()) throw std::runtime_error("layer is not on this stage");
+        if (pos0 < 0 || n < 0 || pos0 + n > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");
+        const size_t row = (size_t) c->m->n_head_kv * c->m->head_dim * 2;
+        CU(cudaSetDevice(c->m->device));
+        if (k_rows) CU(cudaMemcpyAsync(k_rows, (const uint8_t *) c->kc[(size_t) li] + pos0 * row, n * row, cudaMemcpyDeviceToHost, c->st));
+        if (v_rows) CU(cudaMemcpyAsync(v_rows, (const uint8_t *) c->vc[(size_t) li] + pos0 * row, n * row, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
 }
 
 extern "C" void b200_set_taps(b200_ctx * c, int enable) { if (c) { c->taps = enable != 0; c->tapstore.v.clear(); } }
@@ -1086,6 +1141,7 @@ extern "C" int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0,
         if (!m.has_embd() || !m.has_head()) throw std::runtime_error("single-stage model required; use b200_pipeline_generate_greedy");
         if (pos0 < 0 || pos0 + n_steps > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");
         if (n_steps > c->out_tokens_cap) throw std::runtime_error("n_steps too large");
+        if (first_token < 0 || first_token >= m.n_vocab) throw std::runtime_error("token id out of range");
         CU(cudaSetDevice(m.device));
         const double t0 = now_us();
         c->h_state->token = first_token; c->h_state->pos = pos0; c->h_state->round_q = 0; c->h_state->step = 0;
@@ -1301,6 +1357,11 @@ extern "C" int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, 
         if (c->world == 1) return b200_generate_greedy(c, first_token, pos0, n_steps, out_tokens);
         if (!c->comm) throw std::runtime_error("b200_comm_init not called");
         b200_model & m = *c->m;
+        // the same validation as b200_generate_greedy, identical on EVERY rank (all ranks see the same arguments), so that
+        // no rank blocks in ncclRecv while another one returns an error
+        if (pos0 < 0 || pos0 + n_steps > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");
+        if (n_steps > c->out_tokens_cap) throw std::runtime_error("n_steps too large");
+        if (first_token < 0 || first_token >= m.n_vocab) throw std::runtime_error("token id out of range");
         CU(cudaSetDevice(m.device));
         c->h_state->token = first_token; c->h_state->pos = pos0; c->h_state->round_q = 0; c->h_state->step = 0;
         CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
@@ -1355,6 +1416,8 @@ extern "C" int b200_pipeline_decode(b200_ctx * c, const int32_t * tokens, int n,
         if (c->world == 1) return b200_decode(c, tokens, n, pos0, logits_out);
         if (!c->comm) throw std::runtime_error("b200_comm_init not called");
         b200_model & m = *c->m;
+        if (pos0 < 0 || pos0 + n > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");
+        for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= m.n_vocab) throw std::runtime_error("token id out of range");
         CU(cudaSetDevice(m.device));
         const int round_q = n > 1 ? 1 : 0;
         for (int i = 0; i < n; i++) {
@@ -1381,20 +1444,38 @@ extern "C" int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batc
         if (m.has_embd() && (token < 0 || token >= m.n_vocab)) throw std::runtime_error("token id out of range");
         if (m.has_embd() != (prev == nullptr)) throw std::runtime_error("stage chain mismatch: only the first stage has no predecessor");
         CU(cudaSetDevice(m.device));
+        // back edge of the hand-off: this stage's kernels overwrite c->x, which the NEXT stage may still be copying for
+        // the previous token (prompt tokens are enqueued back to back without a host sync) — wait until it has been taken
+        if (c->taken_pending) { CU(cudaStreamWaitEvent(c->st, c->ev_taken, 0)); c->taken_pending = false; }
         if (prev) {
             // hand-off of the residual stream l_out -> next device (cf. cpp/ggml/src/ggml-cuda.cu:2386-2407)
             if (!prev->ev_done) { CU(cudaSetDevice(prev->m->device)); CU(cudaEventCreateWithFlags(&prev->ev_done, cudaEventDisableTiming)); CU(cudaSetDevice(m.device)); }
+            // (an event is recorded on a stream of ITS device: ev_taken belongs to the consumer's device)
+            if (!prev->ev_taken) CU(cudaEventCreateWithFlags(&prev->ev_taken, cudaEventDisableTiming));
             CU(cudaSetDevice(prev->m->device));
             CU(cudaEventRecord(prev->ev_done, prev->st));
             CU(cudaSetDevice(m.device));
             CU(cudaStreamWaitEvent(c->st, prev->ev_done, 0));
             CU(cudaMemcpyPeerAsync(c->x, m.device, prev->x, prev->m->device, (size_t) m.n_embd * 4, c->st));
+            CU(cudaEventRecord(prev->ev_taken, c->st));
+            prev->taken_pending = true;
         }
         DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = batch_gt1 ? 1 : 0; hs.step = 0;
         k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
         c->launches++;
         enqueue_forward(c);
         CU(cudaGetLastError());
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+// block until everything enqueued on this stage's stream has completed (the bridge brackets each prompt chunk with it,
+// as the reference brackets each blocking llama_decode with its timer: cpp/bridge.cpp:549-560)
+extern "C" int b200_stage_sync(b200_ctx * c) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        CU(cudaSetDevice(c->m->device));
+        CU(cudaStreamSynchronize(c->st));
         return 0;
     } catch (const std::exception & e) { return set_err(e.what()); }
 }

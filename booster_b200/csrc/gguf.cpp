@@ -1,7 +1,9 @@
 // gguf.cpp — see gguf.hpp. Host-only, no CUDA.
 #include "gguf.hpp"
 
+#include <algorithm>
 #include <cstring>
+#include <stdexcept>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -17,14 +19,14 @@ struct cursor {
     bool ok = true;
     template <typename T> T rd() {
         T v{};
-        if (p + sizeof(T) > end) { ok = false; return v; }
+        if (!ok || sizeof(T) > (size_t) (end - p)) { ok = false; return v; }
         std::memcpy(&v, p, sizeof(T));
         p += sizeof(T);
         return v;
     }
     std::string str() {
         const uint64_t n = rd<uint64_t>();
-        if (!ok || p + n > end) { ok = false; return {}; }
+        if (!ok || n > (uint64_t) (end - p)) { ok = false; return {}; }     // (no pointer arithmetic on an untrusted 64-bit length)
         std::string s((const char *) p, (size_t) n);
         p += n;
         return s;
@@ -65,12 +67,30 @@ uint64_t ggml_row_bytes(uint32_t type, uint64_t k) {
     }
 }
 
+uint64_t ggml_block_elems(uint32_t type) {
+    switch (type) {
+        case 0: case 1: case 30: return 1;
+        case 8: return 32;
+        case 12: case 13: case 14: return 256;
+        default: return 0;
+    }
+}
+
 gguf_file::~gguf_file() {
     if (base) munmap((void *) base, size);
     if (fd >= 0) close(fd);
 }
 
+// a damaged file is an error string, never an exception or a crash (the callers sit behind extern "C" entry points)
 std::string gguf_file::open(const std::string & path) {
+    try {
+        return open_impl(path);
+    } catch (const std::exception & e) {
+        return std::string("corrupt GGUF (") + e.what() + "): " + path;
+    }
+}
+
+std::string gguf_file::open_impl(const std::string & path) {
     fd = ::open(path.c_str(), O_RDONLY);
     if (fd < 0) return "cannot open " + path;
     struct stat st;
@@ -87,6 +107,9 @@ std::string gguf_file::open(const std::string & path) {
     if (version < 2 || version > 3) return "unsupported GGUF version " + std::to_string(version);
     const uint64_t n_tensors = c.rd<uint64_t>();
     const uint64_t n_kv      = c.rd<uint64_t>();
+    // every kv pair / tensor record / array element occupies at least one byte of the file: counts beyond the
+    // remaining bytes are corrupt (and must never reach reserve())
+    if (!c.ok || n_kv > size || n_tensors > size) return "corrupt GGUF header (counts exceed the file size)";
 
     for (uint64_t i = 0; i < n_kv && c.ok; i++) {
         std::string key = c.str();
@@ -95,11 +118,12 @@ std::string gguf_file::open(const std::string & path) {
         if (v.type == GV_ARR) {
             v.arr_type = c.rd<uint32_t>();
             v.arr_n    = c.rd<uint64_t>();
+            if (!c.ok || v.arr_n > (uint64_t) (c.end - c.p)) return "corrupt GGUF array length in key " + key;
             if (v.arr_type == GV_STR) {
-                v.arr_s.reserve((size_t) v.arr_n);
+                v.arr_s.reserve((size_t) std::min<uint64_t>(v.arr_n, 1u << 20));   // (grows on demand: arr_n is untrusted)
                 for (uint64_t j = 0; j < v.arr_n && c.ok; j++) v.arr_s.push_back(c.str());
             } else {
-                v.arr_f.reserve((size_t) v.arr_n);
+                v.arr_f.reserve((size_t) std::min<uint64_t>(v.arr_n, 1u << 20));
                 for (uint64_t j = 0; j < v.arr_n && c.ok; j++) {
                     gguf_value e;
                     if (!read_scalar(c, v.arr_type, e)) return "bad array element type in key " + key;
@@ -121,20 +145,32 @@ std::string gguf_file::open(const std::string & path) {
         for (uint32_t d = 0; d < t.n_dims; d++) t.ne[d] = c.rd<uint64_t>();
         t.type   = c.rd<uint32_t>();
         t.offset = c.rd<uint64_t>();
+        if (!c.ok) break;
         tensor_order.push_back(t.name);
         tensors[t.name] = t;
     }
     if (!c.ok) return "truncated GGUF tensor table";
 
     alignment = get_u("general.alignment", 32);
+    if (alignment == 0 || (alignment & (alignment - 1)) != 0 || alignment > (1u << 20))
+        return "bad general.alignment " + std::to_string(alignment) + " (must be a power of two)";
     const uint64_t meta = (uint64_t) (c.p - base);
     data_off = (meta + alignment - 1) / alignment * alignment;
+    if (data_off > size) return "truncated GGUF (no data section)";
+    const uint64_t data_size = size - data_off;
 
     for (auto & it : tensors) {
         gguf_tensor & t = it.second;
-        const uint64_t rb = ggml_row_bytes(t.type, t.ne[0]);
-        t.nbytes = rb * t.ne[1] * t.ne[2] * t.ne[3];
-        if (data_off + t.offset + t.nbytes > size && rb != 0) return "tensor " + t.name + " exceeds file size";
+        const uint64_t blk = ggml_block_elems(t.type);
+        if (blk == 0) { t.nbytes = 0; t.data = nullptr; continue; }      // a type this path never reads: no data pointer
+        if (t.ne[0] % blk != 0) return "tensor " + t.name + ": row length is not a multiple of its block size";
+        // checked arithmetic: ne[] and offset are untrusted 64-bit values
+        uint64_t nb = 0;
+        if (__builtin_mul_overflow(t.ne[0] / blk, ggml_row_bytes(t.type, blk), &nb)) return "tensor " + t.name + ": size overflow";
+        for (int d = 1; d < 4; d++)
+            if (__builtin_mul_overflow(nb, t.ne[d], &nb)) return "tensor " + t.name + ": size overflow";
+        t.nbytes = nb;
+        if (t.offset > data_size || nb > data_size - t.offset) return "tensor " + t.name + " exceeds file size";
         t.data = base + data_off + t.offset;
     }
     return {};

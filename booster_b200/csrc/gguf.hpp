@@ -52,6 +52,7 @@ struct gguf_file {
     ~gguf_file();
     // returns empty string on success, else an error message
     std::string open(const std::string & path);
+    std::string open_impl(const std::string & path);
 
     bool has(const std::string & k) const { return kv.count(k) > 0; }
     uint64_t    get_u(const std::string & k, uint64_t def) const;
@@ -62,5 +63,7 @@ struct gguf_file {
 
 // bytes of one row of `k` elements in ggml block layout; 0 if the type is not one we handle
 uint64_t ggml_row_bytes(uint32_t type, uint64_t k);
+// elements per block of a type this path handles (1 for F32/F16/BF16); 0 for any other type
+uint64_t ggml_block_elems(uint32_t type);
 
 }  // namespace b200

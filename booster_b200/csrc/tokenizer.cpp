@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <queue>
+#include <stdexcept>
 #include <unordered_map>
 
 namespace b200 {
@@ -510,7 +511,17 @@ std::unique_ptr<Tokenizer> load_text_tokenizer(const gguf_file & g, const std::s
 
 int codepoint_class(uint32_t cp) { return (int) cpt_class(cp); }
 
+static std::unique_ptr<Tokenizer> make_tokenizer_impl(const std::string & gguf_path, std::string & err);
+// never throws: the callers are extern "C" entry points reached from cgo (initContext)
 std::unique_ptr<Tokenizer> make_tokenizer(const std::string & gguf_path, std::string & err) {
+    try {
+        return make_tokenizer_impl(gguf_path, err);
+    } catch (const std::exception & e) {
+        err = std::string("tokenizer load failed: ") + e.what();
+        return nullptr;
+    }
+}
+static std::unique_ptr<Tokenizer> make_tokenizer_impl(const std::string & gguf_path, std::string & err) {
     gguf_file g;
     err = g.open(gguf_path);
     if (!err.empty()) return nullptr;

@@ -60,6 +60,21 @@ class Context:
     def kv_clear(self):
         self.L.b200_kv_clear(self.h)
 
+    def kv_write(self, layer: int, pos0: int, k_rows, v_rows):
+        """rows [pos0, pos0+n) of one layer's K / V cache from f16 arrays [n, n_head_kv*head_dim] (test support)"""
+        k = np.ascontiguousarray(k_rows, dtype=np.float16).view(np.uint16)
+        v = np.ascontiguousarray(v_rows, dtype=np.float16).view(np.uint16)
+        u16p = C.POINTER(C.c_uint16)
+        check(self.L.b200_kv_write(self.h, layer, pos0, k.shape[0], k.ctypes.data_as(u16p), v.ctypes.data_as(u16p)), "b200_kv_write")
+
+    def kv_read(self, layer: int, pos0: int, n: int):
+        kvd = self.model.n_head_kv * self.model.head_dim
+        k = np.empty((n, kvd), dtype=np.uint16)
+        v = np.empty((n, kvd), dtype=np.uint16)
+        u16p = C.POINTER(C.c_uint16)
+        check(self.L.b200_kv_read(self.h, layer, pos0, n, k.ctypes.data_as(u16p), v.ctypes.data_as(u16p)), "b200_kv_read")
+        return k.view(np.float16), v.view(np.float16)
+
     def decode(self, tokens: Sequence[int], pos0: int, want_logits: bool = True) -> Optional[np.ndarray]:
         """llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0)) then llama_get_logits (last token's row)."""
         toks = np.ascontiguousarray(tokens, dtype=np.int32)

@@ -61,6 +61,12 @@ void       b200_ctx_free(b200_ctx * c);
 int        b200_n_ctx(const b200_ctx * c);
 void       b200_kv_clear(b200_ctx * c);               /* llama_kv_cache_clear (cpp/bridge.cpp:459) */
 
+/* Rows [pos0, pos0 + n) of one layer's K (post-RoPE) and V cache as f16 bits [n][n_head_kv * head_dim]: the cells of
+ * struct llama_kv_cache (cpp/src/llama.cpp:2495-2539), position-major on both sides. Either pointer may be NULL.
+ * For parity tests (both sides start from one cache at n_kv in the thousands; K-shift checks), not for serving. */
+int b200_kv_write(b200_ctx * c, int layer, int pos0, int n, const uint16_t * k_rows, const uint16_t * v_rows);
+int b200_kv_read(b200_ctx * c, int layer, int pos0, int n, uint16_t * k_rows, uint16_t * v_rows);
+
 /* ---- the hot path ------------------------------------------------------------------------------------------
  * b200_decode == llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0))  (cpp/bridge.cpp:549-560,
  *                cpp/src/llama.cpp:18517 → llama_decode_internal :14537-14840) followed by
@@ -134,6 +140,7 @@ int b200_pipeline_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, 
  * batch_gt1 != 0 selects the reference's batch>1 arithmetic (q rounded to f16 before K.q).
  * b200_stage_logits / b200_stage_argmax synchronise and read the LAST stage's result.                       */
 int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batch_gt1, b200_ctx * prev);
+int b200_stage_sync(b200_ctx * c);    /* wait for everything enqueued on this stage (llama_synchronize, cpp/src/llama.cpp:18536) */
 int b200_stage_logits(b200_ctx * c, float * logits_out);
 int b200_stage_argmax(b200_ctx * c, int32_t * token_out);
 

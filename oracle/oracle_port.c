@@ -19,6 +19,7 @@
  * against oracle/_ref live). Compile with -ffp-contract=off: contraction is written explicitly with fmaf where the
  * reference uses FMA.
  */
+#define _GNU_SOURCE   /* M_PI under -std=c11 */
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -282,23 +283,50 @@ void port_rms_norm(const float * x, const float * w, int64_t k, float eps, float
     for (int64_t i = 0; i < k; i++) { const float v = x[i] * scale; y[i] = w ? v * w[i] : v; }
 }
 
-/* ggml_rope_cache_init + rope_yarn (ext_factor = 0 branch) + NORM-mode rotation
- * (cpp/ggml/src/ggml.c:13994-14031, 14121-14135): theta starts at pos, multiplied by theta_scale per pair */
-void port_rope(float * x, int n_heads, int head_dim, int pos, float freq_base, float freq_scale, const float * ff) {
+/* ggml_rope_yarn_corr_dim(s) (cpp/ggml/src/ggml.c:14011-14041) */
+static float yarn_corr_dim(int n_dims, int n_ctx_orig, float n_rot, float base) {
+    return n_dims * logf(n_ctx_orig / (n_rot * 2 * (float) M_PI)) / (2 * logf(base));
+}
+/* ggml_rope_cache_init + rope_yarn + NORM-mode rotation (cpp/ggml/src/ggml.c:13987-14031, 14121-14135): theta starts
+ * at pos and is multiplied by theta_scale per pair; with ext_factor != 0 the angle is the YaRN mix of the interpolated
+ * and the extrapolated one and the magnitude gets the 0.1*ln(1/freq_scale) correction; cos/sin carry attn_factor.
+ * beta_fast = 32, beta_slow = 1 are the context defaults (cpp/src/llama.cpp:16441-16442). */
+void port_rope_ext(float * x, int n_heads, int head_dim, int pos, float freq_base, float freq_scale, const float * ff,
+                   float ext_factor, float attn_factor, int n_ctx_orig) {
     const float theta_scale = powf(freq_base, -2.0f / head_dim);
+    float corr[2];
+    {
+        const float start = floorf(yarn_corr_dim(head_dim, n_ctx_orig, 32.0f, freq_base));
+        const float end   = ceilf(yarn_corr_dim(head_dim, n_ctx_orig, 1.0f, freq_base));
+        corr[0] = start > 0 ? start : 0;
+        corr[1] = end < head_dim - 1 ? end : head_dim - 1;
+    }
     for (int h = 0; h < n_heads; h++) {
         float theta = (float) pos;
         float * p = x + (int64_t) h * head_dim;
         for (int i0 = 0; i0 < head_dim; i0 += 2) {
             const float f = ff ? ff[i0 / 2] : 1.0f;
-            const float th = freq_scale * (theta / f);
-            const float c = cosf(th), s = sinf(th);
+            const float theta_extrap = theta / f;
+            const float theta_interp = freq_scale * theta_extrap;
+            float th = theta_interp, mscale = attn_factor;
+            if (ext_factor != 0.0f) {
+                const float hl = corr[1] - corr[0];
+                const float y = (i0 / 2 - corr[0]) / (0.001f > hl ? 0.001f : hl);
+                const float y01 = y < 0 ? 0 : (y > 1 ? 1 : y);          /* MIN(1, MAX(0, y)) */
+                const float ramp_mix = (1 - y01) * ext_factor;
+                th = theta_interp * (1 - ramp_mix) + theta_extrap * ramp_mix;
+                mscale *= 1.0f + 0.1f * logf(1.0f / freq_scale);
+            }
+            const float c = cosf(th) * mscale, s = sinf(th) * mscale;
             const float x0 = p[i0], x1 = p[i0 + 1];
             p[i0] = x0 * c - x1 * s;
             p[i0 + 1] = x0 * s + x1 * c;
             theta *= theta_scale;
         }
     }
+}
+void port_rope(float * x, int n_heads, int head_dim, int pos, float freq_base, float freq_scale, const float * ff) {
+    port_rope_ext(x, n_heads, head_dim, pos, freq_base, freq_scale, ff, 0.0f, 1.0f, 4096);
 }
 
 /* ---- the reference's SIMD exp/silu, lane-exact -------------------------------------------------------------
@@ -339,7 +367,9 @@ typedef struct {
 } port_layer;
 typedef struct {
     int32_t n_layer, n_embd, n_head, n_head_kv, head_dim, n_ff, n_vocab, n_ctx;
-    float rms_eps, rope_freq_base, rope_freq_scale, pad;
+    float rms_eps, rope_freq_base, rope_freq_scale;
+    float yarn_ext_factor, yarn_attn_factor;   /* cparams.yarn_* (cpp/src/llama.cpp:16686-16690); 0 and 1 without YaRN */
+    int32_t n_ctx_orig;
     const float * rope_freq_factors;
     port_mat tok_embd, output;
     const float * output_norm;
@@ -439,8 +469,10 @@ int port_decode(const port_model * M, const int32_t * tokens, int n, int pos0, f
             port_mul_mat_vec(L->wq.type, L->wq.data, QD, E, nx, q);
             port_mul_mat_vec(L->wk.type, L->wk.data, KVD, E, nx, kk);
             port_mul_mat_vec(L->wv.type, L->wv.data, KVD, E, nx, vv);
-            port_rope(q, M->n_head, hd, pos, M->rope_freq_base, M->rope_freq_scale, M->rope_freq_factors);
-            port_rope(kk, M->n_head_kv, hd, pos, M->rope_freq_base, M->rope_freq_scale, M->rope_freq_factors);
+            port_rope_ext(q, M->n_head, hd, pos, M->rope_freq_base, M->rope_freq_scale, M->rope_freq_factors,
+                          M->yarn_ext_factor, M->yarn_attn_factor, M->n_ctx_orig);
+            port_rope_ext(kk, M->n_head_kv, hd, pos, M->rope_freq_base, M->rope_freq_scale, M->rope_freq_factors,
+                          M->yarn_ext_factor, M->yarn_attn_factor, M->n_ctx_orig);
             uint16_t * kc = M->k_cache + ((int64_t) il * M->n_ctx + pos) * KVD;
             uint16_t * vc = M->v_cache + ((int64_t) il * M->n_ctx + pos) * KVD;
             for (int i = 0; i < KVD; i++) { kc[i] = f2h(kk[i]); vc[i] = f2h(vv[i]); }

@@ -29,7 +29,8 @@ class PortLayer(C.Structure):
 
 class PortModel(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_layer", "n_embd", "n_head", "n_head_kv", "head_dim", "n_ff", "n_vocab", "n_ctx")] + \
-               [(n, C.c_float) for n in ("rms_eps", "rope_freq_base", "rope_freq_scale", "pad")] + \
+               [(n, C.c_float) for n in ("rms_eps", "rope_freq_base", "rope_freq_scale", "yarn_ext_factor", "yarn_attn_factor")] + \
+               [("n_ctx_orig", C.c_int32)] + \
                [("rope_freq_factors", C.c_void_p), ("tok_embd", PortMat), ("output", PortMat), ("output_norm", C.c_void_p),
                 ("layers", C.POINTER(PortLayer)), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
                 ("tap_l_out", C.c_void_p), ("tap_q", C.c_void_p), ("tap_kqv", C.c_void_p)]
@@ -135,6 +136,10 @@ class PortModelRunner:
         M.rope_freq_base = float(kv.get("llama.rope.freq_base", 10000.0))
         sf = float(kv.get("llama.rope.scaling.factor", 0.0))
         M.rope_freq_scale = 1.0 if sf == 0.0 or kv.get("llama.rope.scaling.type", "linear") == "none" else 1.0 / sf
+        # cparams.yarn_ext_factor / yarn_attn_factor / n_ctx_orig_yarn (cpp/src/llama.cpp:16670-16690)
+        M.yarn_ext_factor = 1.0 if kv.get("llama.rope.scaling.type", "linear") == "yarn" else 0.0
+        M.yarn_attn_factor = float(kv.get("llama.rope.scaling.attn_factor", 1.0))
+        M.n_ctx_orig = int(kv.get("llama.rope.scaling.original_context_length", kv.get("llama.context_length", 4096)))
 
         def mat(name) -> PortMat:
             t = self.f.tensors[name]

@@ -29,15 +29,25 @@ from oracle import ref  # noqa: E402
 PROMPT = [5, 9, 200, 17, 3, 99, 42, 7, 11, 300, 1, 2]
 N_GEN = 8
 MODELS = [("tiny", "Q4_K_M", 15), ("tiny", "Q5_K_M", 17), ("tiny", "Q8_0", 7), ("tiny-gqa4", "Q4_K_M", 15)]
+# YaRN rope scaling with ext_factor = 1 (llama.rope.scaling.type = "yarn": cpp/src/llama.cpp:16686-16690), a prompt that
+# runs past the original context so that the interpolation / extrapolation ramp and the attention factor all matter
+YARN_KV = {"llama.rope.scaling.type": ("str", "yarn"), "llama.rope.scaling.factor": ("f32", 4.0),
+           "llama.rope.scaling.original_context_length": ("u32", 32), "llama.rope.scaling.attn_factor": ("f32", 1.25)}
+YARN_PROMPT = [int(t) for t in np.random.default_rng(7).integers(0, 512, size=48)]
 
 
-def make_models():
-    for cfg_name, ftype, code in MODELS:
-        cfg = G.CONFIGS[cfg_name]
+def make_models(only=None):
+    for cfg_name, ftype, code in MODELS + [("tiny-gqa4+yarn", "Q4_K_M", 15)]:
+        yarn = cfg_name.endswith("+yarn")
+        PROMPT = YARN_PROMPT if yarn else globals()["PROMPT"]
+        cfg = G.CONFIGS[cfg_name.split("+")[0]]
+        cfg_name = cfg_name.replace("+", "-")
+        if only and cfg_name not in only:
+            continue
         out = os.path.join(HERE, f"{cfg_name}_{ftype}.gguf")
         with tempfile.TemporaryDirectory() as td:
             f32 = os.path.join(td, "f32.gguf")
-            G.synth_llama(f32, cfg, seed=1234, source="f32")
+            G.synth_llama(f32, cfg, seed=1234, source="f32", extra_kv=YARN_KV if yarn else None)
             ref.quantize_model(f32, out, code, nthread=4)
         r = ref.RefModel(out, n_ctx=64, n_threads=4)
         names = [f"l_out-{i}" for i in range(cfg.n_layer)] + [f"Qcur-{i}" for i in range(cfg.n_layer)] + \
@@ -90,5 +100,7 @@ if __name__ == "__main__":
     if not ref.available():
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` in the build container")
     print("reference variant:", ref.variant())
-    make_ops()
-    make_models()
+    only = sys.argv[1:]            # e.g. `make_golden.py tiny-gqa4-yarn`: (re)generate only the named models
+    if not only:
+        make_ops()
+    make_models(only)

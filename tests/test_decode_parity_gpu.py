@@ -32,7 +32,8 @@ def _synth(model_dir, cfg, ftype, seed=7):
     return p
 
 
-@pytest.mark.parametrize("model", ["tiny_Q4_K_M", "tiny_Q5_K_M", "tiny_Q8_0", "tiny-gqa4_Q4_K_M"])
+# tiny-gqa4-yarn: YaRN rope scaling with ext_factor = 1, attn_factor 1.25, a 48-token prompt past the original context of 32
+@pytest.mark.parametrize("model", ["tiny_Q4_K_M", "tiny_Q5_K_M", "tiny_Q8_0", "tiny-gqa4_Q4_K_M", "tiny-gqa4-yarn_Q4_K_M"])
 def test_golden_models_bitwise(golden_dir, model):
     g = np.load(os.path.join(golden_dir, model + ".npz"))
     m = engine.Model(os.path.join(golden_dir, model + ".gguf"))
@@ -116,6 +117,40 @@ def test_long_context_bitwise(model_dir):
     c.close(); m.close()
 
 
+@pytest.mark.parametrize("cfg,ftype,n_ctx,n_kv0", [
+    ("llama3-8b-2l", "Q4_K_M", 2048, 2040),      # BASELINE config 2: 8B shapes at the end of ctx 2048
+    ("llama3-8b-2l", "Q5_K_M", 8192, 8186),      # config 4: Mistral-7B shapes (same as 8B, GQA 4), Q5_K_M, ctx 8192
+    ("llama3-8b-2l", "Q8_0", 1536, 1530),        # config 3: Q8_0 after 512 prefill + 1K generated
+    ("llama3-70b-1l", "Q4_K_M", 4096, 4090),     # config 5: 70B shapes (GQA 8), ctx 4096
+])
+def test_fullshape_decode_at_full_context_vs_port_bitwise(model_dir, cfg, ftype, n_ctx, n_kv0):
+    """the real per-layer shapes decoding at the END of each BASELINE config's context. Both sides start from the same
+    KV cache (N(0,1) f16 rows for positions < n_kv0, injected through b200_kv_write / the port's cache arrays — a
+    prefill of thousands of tokens through the scalar port would take minutes) and then decode real tokens: the new
+    K/V rows, the attention over all n_kv0+ positions and the logits must be bit-identical, and stay so token after token."""
+    path = _synth(model_dir, cfg, ftype)
+    conf = G.CONFIGS[cfg]
+    kvd = conf.n_head_kv * conf.head_dim
+    rng = np.random.default_rng(n_kv0)
+    p = port.PortModelRunner(path, n_ctx=n_ctx)
+    m = engine.Model(path)
+    c = engine.Context(m, n_ctx)
+    for il in range(conf.n_layer):
+        k = rng.standard_normal((n_kv0, kvd)).astype(np.float16)
+        v = rng.standard_normal((n_kv0, kvd)).astype(np.float16)
+        p.kc[il, :n_kv0] = k.view(np.uint16); p.vc[il, :n_kv0] = v.view(np.uint16)
+        c.kv_write(il, 0, k, v)
+    tok = 17
+    for i in range(min(4, n_ctx - n_kv0)):
+        a, b = c.decode([tok], n_kv0 + i), p.decode([tok], n_kv0 + i)
+        _same(a, b, f"decode at n_kv {n_kv0 + i + 1}")
+        tok = int(np.argmax(b))
+    for il in range(conf.n_layer):                 # the rows this run appended to the cache
+        k, v = c.kv_read(il, n_kv0, 2)
+        assert np.array_equal(k.view(np.uint16), p.kc[il, n_kv0:n_kv0 + 2]) and np.array_equal(v.view(np.uint16), p.vc[il, n_kv0:n_kv0 + 2])
+    c.close(); m.close()
+
+
 def test_device_greedy_equals_host_greedy_and_is_deterministic(model_dir):
     path = _synth(model_dir, "llama3-8b-2l", "Q4_K_M")
     m = engine.Model(path)
@@ -154,6 +189,39 @@ def test_position_bounds_and_bad_tokens(golden_dir):
     with pytest.raises(engine.B200Error):
         c.decode([1], 32)
     c.close(); m.close()
+
+
+def test_in_process_stage_split_prompt_back_to_back(golden_dir):
+    """a 12-token prompt enqueued back to back through two stages (no host sync between tokens, as the bridge's prompt
+    loop does): the consumer's copy of token i's l_out must not race with the producer's token i+1 (back edge event) —
+    logits and the greedy continuation equal the single-stage run. Uses two devices when the box has them."""
+    import ctypes as C
+    path = os.path.join(golden_dir, "tiny-gqa4_Q4_K_M.gguf")
+    g = np.load(os.path.join(golden_dir, "tiny-gqa4_Q4_K_M.npz"))
+    prompt = g["prompt"].tolist()
+    d1 = 1 if engine.device_count() > 1 else 0
+    m0 = engine.Model(path, 0, 0, 1); m1 = engine.Model(path, d1, 1, 3)
+    c0 = engine.Context(m0, 64); c1 = engine.Context(m1, 64)
+    L = m0.L
+    out = np.empty(m0.n_vocab, dtype=np.float32)
+    for rep in range(3):
+        for i, t in enumerate(prompt):
+            assert L.b200_stage_forward(c0.h, t, i, 1, None) == 0
+            assert L.b200_stage_forward(c1.h, t, i, 1, c0.h) == 0
+        assert L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+        _same(out, g["logits"][0], f"prefill through 2 stages (rep {rep})")
+    pos = len(prompt)
+    for i, t in enumerate(g["ids"].tolist()[:4]):
+        assert int(np.argmax(out)) == t
+        assert L.b200_stage_forward(c0.h, t, pos, 0, None) == 0
+        assert L.b200_stage_forward(c1.h, t, pos, 0, c0.h) == 0
+        assert L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+        _same(out, g["logits"][i + 1], f"step {i} through 2 stages")
+        pos += 1
+    for x in (c0, c1):
+        x.close()
+    for x in (m0, m1):
+        x.close()
 
 
 def test_in_process_stage_split_equals_single_stage(golden_dir):

@@ -98,7 +98,11 @@ def test_rope(pos, base):
     assert np.array_equal(engine.op_rope(x, 8, 128, pos, base, 0.5, ff), port.rope(x, 8, 128, pos, base, 0.5, ff))
 
 
-@pytest.mark.parametrize("cfg", [(4, 1, 1), (4, 1, 33), (32, 8, 257), (32, 8, 2048), (64, 8, 700), (8, 8, 64), (2, 1, 5), (32, 8, 3000)])
+# (n_head, n_head_kv, n_kv): GQA 1/2/4/8; the contexts of the BASELINE configs (2048, 4096, 8192 and one position short of
+# them); (64, 8, 8192) exceeds one CTA's shared memory for the GQA score rows and takes the long-context route
+@pytest.mark.parametrize("cfg", [(4, 1, 1), (4, 1, 33), (32, 8, 257), (32, 8, 2048), (64, 8, 700), (8, 8, 64), (2, 1, 5), (32, 8, 3000),
+                                 (16, 8, 1000), (32, 8, 4096), (32, 8, 8191), (32, 8, 8192), (64, 8, 4095), (64, 8, 4096), (64, 8, 8192),
+                                 (8, 1, 12000)])
 @pytest.mark.parametrize("round_q", [False, True])
 def test_attention_bit_exact(cfg, round_q):
     n_head, n_head_kv, n_kv = cfg

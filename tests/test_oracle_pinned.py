@@ -50,7 +50,7 @@ def test_vec_dot_bit_exact(ops, name):
 # logits are BIT-IDENTICAL to the reference's, step after step. Bitwise equality is the criterion: with quantized
 # activations anything weaker is meaningless, because a 1-ulp upstream difference eventually flips an int8 of a
 # Q8_K block and the deviation cascades to ~1e-2 and persists through the KV cache (DESIGN.md "why bit-exact").
-@pytest.mark.parametrize("model", ["tiny_Q4_K_M", "tiny_Q5_K_M", "tiny_Q8_0", "tiny-gqa4_Q4_K_M"])
+@pytest.mark.parametrize("model", ["tiny_Q4_K_M", "tiny_Q5_K_M", "tiny_Q8_0", "tiny-gqa4_Q4_K_M", "tiny-gqa4-yarn_Q4_K_M"])
 def test_model_logits_vs_golden_bitwise(golden_dir, model):
     g = np.load(os.path.join(golden_dir, model + ".npz"))
     m = port.PortModelRunner(os.path.join(golden_dir, model + ".gguf"), n_ctx=64)

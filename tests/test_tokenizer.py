@@ -148,3 +148,37 @@ def test_truncated_and_corrupted_gguf_fail_without_crashing(tmp_path):
             t.close()
         except engine.B200Error:
             pass
+
+
+def test_crafted_gguf_headers_are_errors_not_crashes(tmp_path):
+    """the four crafted failures of the round-1 review: a 2^64-1 string length (pointer wrap), a huge array count
+    (reserve -> length_error / bad_alloc), general.alignment = 0 (SIGFPE) and tensor sizes / offsets that overflow 64 bits"""
+    import struct
+
+    def s(b):
+        return struct.pack("<Q", len(b)) + b
+
+    def header(n_t, n_kv):
+        return b"GGUF" + struct.pack("<IQQ", 3, n_t, n_kv)
+
+    kv_arch = s(b"general.architecture") + struct.pack("<I", 8) + s(b"llama")
+    cases = {
+        "strlen_wrap": header(0, 1) + struct.pack("<Q", 2**64 - 1) + b"x" * 64,
+        "count_wrap": header(2**63, 2**63) + b"\0" * 64,
+        "arr_huge_str": header(0, 1) + s(b"tokenizer.ggml.tokens") + struct.pack("<IIQ", 9, 8, 2**62) + b"\0" * 64,
+        "arr_huge_num": header(0, 1) + s(b"tokenizer.ggml.scores") + struct.pack("<IIQ", 9, 6, 2**62) + b"\0" * 64,
+        "align_zero": header(0, 2) + kv_arch + s(b"general.alignment") + struct.pack("<II", 4, 0) + b"\0" * 64,
+        "align_odd": header(0, 2) + kv_arch + s(b"general.alignment") + struct.pack("<II", 4, 48) + b"\0" * 64,
+        "ne_overflow": header(1, 1) + kv_arch + s(b"token_embd.weight") + struct.pack("<IQQIQ", 2, 2**40, 2**40, 0, 0) + b"\0" * 256,
+        "ne_overflow_q": header(1, 1) + kv_arch + s(b"token_embd.weight") + struct.pack("<IQQIQ", 2, 2**62, 2**10, 12, 0) + b"\0" * 256,
+        "offset_wrap": header(1, 1) + kv_arch + s(b"token_embd.weight") + struct.pack("<IQQIQ", 2, 256, 4, 0, 2**64 - 64) + b"\0" * 8192,
+        "row_not_block_multiple": header(1, 1) + kv_arch + s(b"token_embd.weight") + struct.pack("<IQQIQ", 2, 100, 4, 12, 0) + b"\0" * 8192,
+    }
+    L = engine._lib.lib()
+    for name, blob in cases.items():
+        p = str(tmp_path / f"{name}.gguf")
+        open(p, "wb").write(blob)
+        with pytest.raises(engine.B200Error):
+            engine.Tokenizer(p)
+        # the model loader goes through the same parser (and fails earlier without a GPU): an error either way
+        assert not L.b200_model_load(p.encode(), 0, 0, -1), name
