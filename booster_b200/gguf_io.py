@@ -71,11 +71,20 @@ def write_gguf(path: str, kv: Dict[str, tuple], tensors: List[Tuple[str, Tuple[i
     infos = []
     off = 0
     sizes = []
-    for name, ne, t, _ in tensors:
+    where = {}
+    for name, ne, t, data in tensors:
         n_rows = int(np.prod(ne[1:])) if len(ne) > 1 else 1
         nbytes = row_bytes(t, ne[0]) * n_rows
-        infos.append((name, ne, t, off))
         sizes.append(nbytes)
+        if isinstance(data, tuple) and data[0] == "alias":
+            # the tensor shares the file bytes of an earlier tensor of the same type and shape (synthetic benchmark
+            # files: every consumer still gets its own copy in HBM, the FILE just does not store it twice)
+            o, nb0 = where[data[1]]
+            assert nb0 == nbytes, f"{name}: alias of {data[1]} with a different size"
+            infos.append((name, ne, t, o))
+            continue
+        where[name] = (off, nbytes)
+        infos.append((name, ne, t, off))
         off += (nbytes + ALIGN - 1) // ALIGN * ALIGN
     with open(path, "wb") as f:
         f.write(GGUF_MAGIC + struct.pack("<IQQ", 3, len(tensors), len(kv)))
@@ -87,6 +96,8 @@ def write_gguf(path: str, kv: Dict[str, tuple], tensors: List[Tuple[str, Tuple[i
         pos = f.tell()
         f.write(b"\0" * ((pos + ALIGN - 1) // ALIGN * ALIGN - pos))
         for (name, ne, t, data), nbytes in zip(tensors, sizes):
+            if isinstance(data, tuple) and data[0] == "alias":
+                continue
             arr = data() if callable(data) else data
             raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
             assert raw.size == nbytes, f"{name}: have {raw.size} bytes, expected {nbytes}"
@@ -276,9 +287,12 @@ def llama_kv(cfg: LlamaConfig, ftype: str, extra_kv: Dict[str, tuple] | None = N
 
 
 def synth_llama(path: str, cfg: LlamaConfig, ftype: str = "Q4_K_M", seed: int = 1234, source: str = "blocks",
-                extra_kv: Dict[str, tuple] | None = None, rope_freqs: np.ndarray | None = None) -> None:
+                extra_kv: Dict[str, tuple] | None = None, rope_freqs: np.ndarray | None = None, share_period: int = 0) -> None:
     """Write a synthetic LLaMA-architecture GGUF. source="blocks": random quantized blocks in the reference's
-    type mixture for `ftype`; source="f32": F32 weights ~ N(0, 0.02^2) (norms ~ 1 +- 0.1), ftype ignored."""
+    type mixture for `ftype`; source="f32": F32 weights ~ N(0, 0.02^2) (norms ~ 1 +- 0.1), ftype ignored.
+    share_period > 0 (blocks only): a layer's matrix re-uses the FILE bytes of the same matrix of an earlier layer with the
+    same block type (at most `share_period` distinct copies per (matrix, type)) — a 42 GB 70B-shaped file becomes ~3 GB on
+    disk while every layer still has its own tiles in HBM, so timing is unaffected. Never used for parity fixtures."""
     rng = np.random.default_rng(seed)
     E, KV, FF, V = cfg.n_embd, cfg.n_head_kv * cfg.head_dim, cfg.n_ff, cfg.n_vocab
     shapes = [("token_embd.weight", (E, V)), ("output_norm.weight", (E,)), ("output.weight", (E, V))]
@@ -291,6 +305,7 @@ def synth_llama(path: str, cfg: LlamaConfig, ftype: str = "Q4_K_M", seed: int = 
         shapes.append(("rope_freqs.weight", (cfg.head_dim // 2,)))
     types = tensor_types(cfg, ftype) if source == "blocks" else {}
     tensors = []
+    shared: Dict[tuple, List[str]] = {}
     for name, ne in shapes:
         if name == "rope_freqs.weight":
             tensors.append((name, ne, F32, np.asarray(rope_freqs, dtype=np.float32)))
@@ -300,6 +315,13 @@ def synth_llama(path: str, cfg: LlamaConfig, ftype: str = "Q4_K_M", seed: int = 
             t = types[name]
             # lazy: generated when written, so only one tensor is in memory at a time
             sub = np.random.default_rng(rng.integers(0, 2**63))
+            if share_period > 0 and name.startswith("blk."):
+                key = (name.split(".", 2)[2], t)
+                have = shared.setdefault(key, [])
+                if len(have) >= share_period:
+                    tensors.append((name, ne, t, ("alias", have[int(name.split(".")[1]) % share_period])))
+                    continue
+                have.append(name)
             tensors.append((name, ne, t, (lambda s=sub, t=t, ne=ne: random_blocks(s, t, ne[1], ne[0]))))
         else:
             sub = np.random.default_rng(rng.integers(0, 2**63))
