@@ -237,6 +237,11 @@ def op_attention(q, k_cache_f16, v_cache_f16, n_kv: int, n_head: int, n_head_kv:
     return out
 
 
+def set_attention_route(route: int) -> None:
+    """0: automatic (cluster kernel when it fits), 1: always the long-context three-kernel route"""
+    _lib.lib().b200_set_attention_route(route)
+
+
 class Tokenizer:
     """llama_tokenize / llama_token_to_piece / llama_token_is_eog of a GGUF's vocabulary (include/booster_b200.h)."""
 

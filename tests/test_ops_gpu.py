@@ -102,9 +102,25 @@ def test_rope(pos, base):
 # them); (64, 8, 8192) exceeds one CTA's shared memory for the GQA score rows and takes the long-context route
 @pytest.mark.parametrize("cfg", [(4, 1, 1), (4, 1, 33), (32, 8, 257), (32, 8, 2048), (64, 8, 700), (8, 8, 64), (2, 1, 5), (32, 8, 3000),
                                  (16, 8, 1000), (32, 8, 4096), (32, 8, 8191), (32, 8, 8192), (64, 8, 4095), (64, 8, 4096), (64, 8, 8192),
-                                 (8, 1, 12000)])
+                                 (8, 1, 12000), (8, 1, 70000)])
 @pytest.mark.parametrize("round_q", [False, True])
 def test_attention_bit_exact(cfg, round_q):
+    _attention_case(cfg, round_q)
+
+
+# the long-context three-kernel route (taken automatically only when a CTA's share of the context exceeds its shared
+# memory, e.g. (8, 1, 70000) above) forced at ordinary sizes too
+@pytest.mark.parametrize("cfg", [(4, 1, 33), (32, 8, 2048), (64, 8, 4095), (64, 8, 8192), (2, 1, 5), (16, 8, 1000)])
+@pytest.mark.parametrize("round_q", [False, True])
+def test_attention_long_context_route_bit_exact(cfg, round_q):
+    engine.set_attention_route(1)
+    try:
+        _attention_case(cfg, round_q)
+    finally:
+        engine.set_attention_route(0)
+
+
+def _attention_case(cfg, round_q):
     n_head, n_head_kv, n_kv = cfg
     hd = 128
     rng = np.random.default_rng(n_kv)
