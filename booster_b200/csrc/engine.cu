@@ -685,64 +685,60 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     c->launches++;
 }
 
-// attention route: 0 = automatic (the cluster kernel when it fits, else the long-context route), 1 = force the
-// long-context three-kernel route (tests keep both covered)
+// two launches per layer: raw scores (k_attn_scores, every SM busy) then softmax + P.V (k_attn_softmax_pv); returns
+// false when the GQA score rows of the context do not fit the shared memory (the three-kernel route below takes over)
+template <int GQA>
+static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
+    AttnArgs a = a_in;
+    const size_t row_bytes = (size_t) GQA * n_ctx_pad * 4;
+    const size_t budget = 200 * 1024;
+    if (row_bytes + (size_t) PV_BATCH * 16 > budget) return false;
+    int vch = (int) ((budget - row_bytes) / 16) / PV_BATCH * PV_BATCH;
+    vch = std::min(vch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);
+    a.p_chunk = vch;
+    size_t smem = row_bytes + (size_t) vch * 16;
+    // at most one CTA per SM: the block scheduler then spreads the (n_head_kv x 16) CTAs over distinct SMs even when
+    // they are launched early (PDL) next to the tail of the previous kernel
+    if ((int) a.n_head_kv * (128 / PVS_DIMS) <= c->sm_count) smem = std::max(smem, (size_t) 116 * 1024);
+    static size_t attr[64] = {0};
+    const int dv = c->device & 63;
+    std::unique_lock<std::mutex> attr_lock(g_attr_mu);
+    if (smem > attr[dv]) {
+        CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CU(cudaFuncSetAttribute(k_attn_softmax_pv<GQA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr[dv] = smem;
+    }
+    attr_lock.unlock();
+    {
+        g_kind = KIND_ATTN; ProfScope ps(c);
+        const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
+        a.trace = trace_slot(c, (int) (gs.x * gs.y));
+        launch_fwd(a.trace ? k_attn_scores<GQA, true> : k_attn_scores<GQA, false>, gs, dim3(ATT_THREADS), 0, c->st, a);
+    }
+    {
+        g_kind = KIND_ATTN_PV; ProfScope ps(c);
+        const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVS_DIMS));
+        a.trace = trace_slot(c, (int) (gp.x * gp.y));
+        launch_fwd(a.trace ? k_attn_softmax_pv<GQA, true> : k_attn_softmax_pv<GQA, false>, gp, dim3((unsigned) (GQA * pvs_th(GQA))), smem, c->st, a);
+    }
+    c->launches += 2;
+    return true;
+}
+
+// attention route: 0 = automatic (two launches when the GQA score rows fit one CTA's shared memory, else the
+// long-context three-kernel route), 1 = always the long-context route (tests keep both covered at every size)
 static int g_attn_route = 0;
 extern "C" void b200_set_attention_route(int route) { g_attn_route = route; }
-
-// one launch per layer: k_attn_cluster, a 16-CTA cluster per KV head. Returns false when the per-CTA shared memory (score
-// slice + probabilities of the chain + a useful V stage) exceeds the budget — contexts of several ten thousand positions —
-// or when the device cannot co-schedule a 16-CTA cluster; the three-kernel route below takes over.
-template <int GQA>
-static bool launch_attention_cluster(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
-    if (g_attn_route == 1) return false;
-    AttnCArgs a{};
-    a.q = a_in.q; a.k_cache = a_in.k_cache; a.v_cache = a_in.v_cache; a.out = a_in.out; a.kv_dim = a_in.kv_dim; a.scale = a_in.scale;
-    a.st = a_in.st; a.n_kv_override = a_in.n_kv_override; a.round_q_override = a_in.round_q_override;
-    a.n16_max = n_ctx_pad / 16;
-    a.vpc_max = (a.n16_max + ATC_CS - 1) / ATC_CS;
-    const size_t sbuf = (size_t) GQA * a.vpc_max * 16 * 4, pbuf = (size_t) GQA * a.n16_max * 4;
-    const size_t budget = 200 * 1024;
-    if (sbuf + pbuf + 64 * 256 > budget) return false;
-    a.v_rows = (int) std::min<size_t>((size_t) a.n16_max, (budget - sbuf - pbuf) / 256);
-    const size_t smem = (size_t) a.v_rows * 256 + sbuf + pbuf;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(ATC_CS, (unsigned) a_in.n_head_kv); cfg.blockDim = dim3(ATC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = c->st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = ATC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    static size_t attr[64] = {0};
-    static int feasible[64] = {0};                 // per device: 0 unknown, 1 yes, -1 no
-    const int dv = c->device & 63;
-    {
-        std::lock_guard<std::mutex> attr_lock(g_attr_mu);
-        if (smem > attr[dv] || feasible[dv] == 0) {
-            for (auto kern : { k_attn_cluster<GQA, false>, k_attn_cluster<GQA, true> }) {
-                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max(smem, attr[dv])));
-            }
-            attr[dv] = std::max(smem, attr[dv]);
-            int n_clusters = 0;
-            cudaLaunchConfig_t q = cfg; q.numAttrs = 1;
-            if (cudaOccupancyMaxActiveClusters(&n_clusters, k_attn_cluster<GQA, false>, &q) != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
-            feasible[dv] = n_clusters >= 1 ? 1 : -1;
-        }
-        if (feasible[dv] < 0) return false;
-    }
-    g_kind = KIND_ATTN; ProfScope ps(c);
-    a.trace = trace_slot(c, (int) (cfg.gridDim.x * cfg.gridDim.y));
-    CU(cudaLaunchKernelEx(&cfg, a.trace ? k_attn_cluster<GQA, true> : k_attn_cluster<GQA, false>, a));
-    c->launches += 1;
-    return true;
+static bool attn_2k_enabled() {
+    static int v = -1;
+    if (v < 0) { const char * e = getenv("BOOSTER_B200_ATTN_SPLIT"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1 && g_attn_route != 1;
 }
 
 template <int GQA>
 static void launch_attention_t(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
-    if (launch_attention_cluster<GQA>(c, a_in, n_ctx_pad)) return;
-    // long-context route (a CTA's share of the score rows does not fit its shared memory): scores, softmax, chunked P.V
+    if (attn_2k_enabled() && launch_attention_2k<GQA>(c, a_in, n_ctx_pad)) return;
+    // long-context route (the GQA score rows do not fit one CTA's shared memory): scores, softmax, chunked P.V
     AttnArgs a = a_in;
     int pch = (200 * 1024) / (GQA * 4 + 32) / PV_BATCH * PV_BATCH;
     pch = std::min(pch, (n_ctx_pad + PV_BATCH - 1) / PV_BATCH * PV_BATCH);

@@ -1339,325 +1339,171 @@ __global__ void __launch_bounds__(PV_DIMS * 16) k_attn_pv(const AttnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_attn_cluster: the whole default-route attention of one layer (scores, soft_max_ext, P.V) in ONE launch. A thread-block
-// CLUSTER of 16 CTAs owns one KV head (all GQA query heads that share it); the three steps are joined by cluster barriers
-// and small distributed-shared-memory exchanges instead of kernel boundaries and a round trip of the score rows
-// through global memory. The work split follows the structure of the reference's arithmetic:
-//   * scores / exponentials / per-vector sums: CTA r owns a CONTIGUOUS run of 16-position vectors (the reference sums
-//     the exponentials of 16 consecutive positions with _mm512_reduce_add_ps before the double accumulation,
-//     cpp/ggml/src/ggml.c:2619-2640) — every vector sum is local; only the per-head maxima (before) and the per-head
-//     partial sums in double (after) cross the cluster, as 16 x GQA scalars each.
-//   * P.V: tinyBLAS<16> keeps 16 independent fma chains per output element, chain c over positions t = c, c+16, ...
-//     (cpp/ggml/src/llamafile/sgemm.cpp:408-430). CTA r runs chain r for all 128 dims and all GQA heads: it reads V rows
-//     t = r (mod 16) only — whole 256-byte rows, fetched into shared memory BEFORE griddepcontrol.wait — and needs the
-//     probabilities of exactly those positions, which their owners scatter to it (one remote 4-byte store per value).
-//     The 16 chain values of an output element then meet in the CTA that owns its dims for the _mm512_reduce_add_ps tree.
-// Nothing is computed twice (the two-kernel route repeated each soft-max in 16 CTAs) and every K / V byte is read once.
-//   grid (16, n_head_kv), cluster (16, 1, 1), 512 threads.
-//   dynamic shared memory: vbuf f16 [v_rows][128] | sbuf f32 [GQA][16 vpc_max] | pbuf f32 [GQA][n16_max]
+// k_attn_softmax_pv: soft_max_ext + P.V of one layer in ONE launch, no inter-CTA communication. A CTA owns
+// (KV head g, a slice of PVS_DIMS output dims) and ALL positions (the 16 tinyBLAS chains of an output element run
+// over t in order, so positions cannot be split). Every CTA of a KV head normalises the GQA score rows itself — the
+// exp work is repeated HD/PVS_DIMS times across CTAs, which is far cheaper than a grid-wide exchange of max and sum —
+// with exactly k_attn_softmax's arithmetic, on a shared-memory copy; then thread (h, c, dl) runs chain c of output
+// dim dl of head h. The CTA's V slice is independent of the scores and is put in flight BEFORE griddepcontrol.wait
+// (k_attn_scores waits for the QKV kernel before it lets this kernel launch, so K/V/q are already visible).
+//   grid (n_head_kv, HD / PVS_DIMS), block GQA * pvs_th(GQA) threads (16 chains x dim groups per head); shared: ps [GQA][n_pad] f32 | vs [v_chunk][8] f16
 // ------------------------------------------------------------------------------------------------------------
-static constexpr int ATC_CS = 16;              // CTAs per cluster == tinyBLAS chains
-static constexpr int ATC_THREADS = 512;
-static constexpr int ATC_PASS = ATC_THREADS / 4;   // key positions per scores pass (4 lanes per key row)
-
-struct AttnCArgs {
-    const float * q;          // [n_head][128] post-RoPE
-    const __half * k_cache;   // [n_ctx][kv_dim]
-    const __half * v_cache;
-    float * out;              // [n_head*128]  (kqv_merged_cont)
-    int kv_dim;
-    float scale;
-    const DecodeState * st;
-    int n_kv_override;        // >0: use instead of st->pos+1 (operator-level test)
-    int round_q_override;
-    int vpc_max;              // 16-position vectors per CTA at n_ctx (sizes sbuf)
-    int n16_max;              // 16-position vectors at n_ctx (sizes pbuf)
-    int v_rows;               // rows of the V stage in shared memory (>= 1)
-    unsigned long long * trace;
-};
-
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acquire()   { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-// address of the same shared-memory variable in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
-    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v)  { asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(addr), "d"(v) : "memory"); }
+static constexpr int PVS_DIMS = 8;            // dims per CTA: 8 halfs = one 16-byte cp.async per position
+// dims per thread: 1 (128 threads per head) up to GQA 4, 2 (64 threads per head) for GQA 8 — at most 512 threads
+__host__ __device__ constexpr int pvs_dpt(int gqa) { return gqa >= 8 ? 2 : 1; }
+__host__ __device__ constexpr int pvs_th(int gqa) { return 16 * (PVS_DIMS / pvs_dpt(gqa)); }
 
 template <int GQA, bool TR>
-__global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_cluster(const AttnCArgs a) {
+__global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const AttnArgs a) {
     constexpr int HD = 128;
-    constexpr int TH = ATC_THREADS / GQA;          // threads per head in the soft-max steps
-    constexpr int NH = GQA > 4 ? GQA / 4 : 1;      // heads per thread in the P.V step (thread = (head slot, dim))
-    extern __shared__ __align__(16) uint8_t atc_dyn[];
-    __shared__ __align__(16) float qs[GQA][HD];
-    __shared__ float  wmax[ATC_THREADS / 32];
-    __shared__ float  lmaxs[GQA], gmaxs[GQA], invs[GQA];
-    __shared__ float  mbuf[ATC_CS][GQA];           // received: every CTA's per-head maximum
-    __shared__ double dsum[ATC_CS][GQA];           // received: every CTA's per-head partial sum
-    __shared__ float  obuf[GQA][8][ATC_CS + 1];    // received: the 16 chain values of my 8 dims
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r = (int) cluster_ctarank(), g = blockIdx.y;
+    constexpr int DPT = pvs_dpt(GQA);
+    constexpr int TH = pvs_th(GQA);                            // threads per head: 16 chains x (8 / DPT) dim groups
+    constexpr int NT = GQA * TH;
+    constexpr int NW = TH / 32;
+    extern __shared__ __align__(16) uint8_t sp_dyn[];
+    __shared__ float  redf[GQA][NW];
+    __shared__ double redd[GQA][NW];
+    __shared__ float  red[GQA][16][PVS_DIMS + 1];
+    const int g = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int h = tid / TH, ht = tid % TH;                     // head of the group, thread within the head
+    const int c = ht / (PVS_DIMS / DPT), dp = ht % (PVS_DIMS / DPT);   // chain, dim group
+    const int w = ht >> 5;                                     // warp within the head
 
     trace_mark<TR>(a.trace, 0);
-    cluster_arrive_relaxed();                                  // #0: "this CTA runs" — waited on before the first remote store
-    pdl_launch_dependents();                                   // the wo mat-vec may start its weight prefetch
-    const int n_kv = a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1;   // DecodeState: written by the previous TOKEN
+    pdl_launch_dependents();
+    const int n_kv = attn_n_kv(a);                             // DecodeState is written by the previous TOKEN's last kernel
     const int n_pad = (n_kv + 31) / 32 * 32;
-    const int n16 = n_pad / 16;
-    const int vpc = (n16 + ATC_CS - 1) / ATC_CS;               // vectors per CTA
-    const int v0 = min(n16, r * vpc), v1 = min(n16, v0 + vpc); // my vectors [v0, v1): positions [16 v0, 16 v1)
-    const int npos = (v1 - v0) * 16;
-    __half * vbuf = reinterpret_cast<__half *>(atc_dyn);
-    float * sbuf = reinterpret_cast<float *>(atc_dyn + (size_t) a.v_rows * HD * 2);
-    float * pbuf = sbuf + (size_t) GQA * a.vpc_max * 16;
-    const int s_stride = a.vpc_max * 16, p_stride = a.n16_max;
-
-    // ---- V rows of chain r: t = 16 j + r. Rows of earlier positions were written by earlier tokens: they are put in
-    // flight before griddepcontrol.wait; the current position's row (written by the QKV kernel) follows after it.
-    const __half * vbase = a.v_cache + g * HD;
-    auto stage_v = [&](int j0, bool before_wait) {
-        const int rows = min(a.v_rows, n16 - j0);
-        for (int i = tid; i < rows * 16; i += ATC_THREADS) {
-            const int j = i >> 4, seg = i & 15, t = 16 * (j0 + j) + r;
-            __half * dst = vbuf + (size_t) j * HD + seg * 8;
-            if (t < n_kv - 1 || (!before_wait && t == n_kv - 1)) cp_async16(dst, vbase + (size_t) t * a.kv_dim + seg * 8);
-            else if (t >= n_kv) *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);   // p == 0 there: the product must be 0
+    const int VCH = a.p_chunk;                                 // positions of V staged at a time (multiple of 32)
+    float * ps = reinterpret_cast<float *>(sp_dyn);            // [GQA][n_pad]
+    __half (*vs)[PVS_DIMS] = reinterpret_cast<__half (*)[PVS_DIMS]>(sp_dyn + (size_t) GQA * n_pad * 4);
+    const __half * vbase = a.v_cache + g * HD + slice * PVS_DIMS;
+    // V rows of one chunk; rows in [n_kv, n_pad) are zero-filled: p == 0 there and the product must be 0, never NaN
+    auto stage_v = [&](int t0) {
+        const int len = min(VCH, n_pad - t0);
+        for (int i = tid; i < len; i += NT) {
+            if (t0 + i < n_kv) cp_async16(&vs[i][0], vbase + (size_t) (t0 + i) * a.kv_dim);
+            else *reinterpret_cast<uint4 *>(&vs[i][0]) = make_uint4(0u, 0u, 0u, 0u);
         }
         cp_async_commit();
     };
-    stage_v(0, true);
-
-    // ---- K rows of the first scores pass (4 lanes per key row, lane c4 owns the tinyBLAS chains 4c4..4c4+3)
-    const int tl = tid >> 2, c4 = tid & 3;
-    auto k_ptr = [&](int t) { return reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4); };
-    uint2 kv[8];
-#pragma unroll
-    for (int s = 0; s < 8; s++) kv[s] = make_uint2(0u, 0u);
-    {
-        const int t = 16 * v0 + tl;
-        if (tl < npos && t < n_kv - 1) {
-            const uint2 * kr = k_ptr(t);
-#pragma unroll
-            for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);            // 4 halfs at element 16s + 4c4
-        }
-    }
+    stage_v(0);
+#if B200_LOOKAHEAD
+    if (lane == 0 && a.pf2[0].bytes)
+        issue_l2_lookahead(a.pf2, (tid >> 5) * (gridDim.x * gridDim.y) + slice * gridDim.x + g, (NT / 32) * gridDim.x * gridDim.y, n_kv - 1);
+#endif
+    pdl_wait();                                               // the raw scores are complete
     trace_mark<TR>(a.trace, 1);
-    pdl_wait();                                                // q and this token's K / V rows come from the QKV kernel
-    trace_mark<TR>(a.trace, 2);
-    const int round_q = a.st ? a.st->round_q : a.round_q_override;
-    for (int i = tid; i < GQA * HD; i += ATC_THREADS) {
-        float v = a.q[(size_t) (g * GQA) * HD + i];
-        if (round_q) v = __half2float(__float2half_rn(v));     // src1 converted to the vec_dot_type F16 (ggml.c:12345-12371)
-        (&qs[0][0])[i] = v;
-    }
-    {   // the current position's V row, if it is in chain r and in the first stage
-        const int t = n_kv - 1, j = t >> 4;
-        if ((t & 15) == r && j < a.v_rows && tid < 16) cp_async16(vbuf + (size_t) j * HD + tid * 8, vbase + (size_t) t * a.kv_dim + tid * 8);
+    float * row = ps + (size_t) h * n_pad;
+    {
+        const float * Sg = a.S + (size_t) (g * GQA + h) * a.s_stride;
+        for (int i = ht; i < n_pad / 4; i += TH) cp_async16(row + 4 * i, Sg + 4 * i);
         cp_async_commit();
+        cp_async_wait<0>();                                    // (also completes this thread's V copies)
     }
-    __syncthreads();
-
-    // ---- raw scores of my positions into sbuf[h][position - 16 v0]  (k_attn_scores' arithmetic)
-    for (int p0 = 0; p0 < npos; p0 += ATC_PASS) {
-        const int lp = p0 + tl, t = 16 * v0 + lp;
-        if (lp < npos && t == n_kv - 1) {
-            const uint2 * kr = k_ptr(t);
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");   // the head's row is in shared memory
+    trace_mark<TR>(a.trace, 2);
+    // soft_max_ext of the head's row (cpp/ggml/src/ggml.c:13682-13778): a thread owns whole 16-element vectors of the
+    // reference's loop, so the _mm512_reduce_add_ps tree is register arithmetic; the per-vector float sums are
+    // accumulated in double (order-insensitive here: see k_attn_softmax)
+    const int n16 = n_pad / 16;
+    float mx = -INFINITY;
+    // a thread visits the four float4 of its vector starting at (ht >> 1) & 3: the 8 lanes of a quarter-warp then hit 8
+    // different 16-byte bank groups. The reduce tree pairs float4 f with f+2 and adds the two halves — both
+    // commutative — so the rotation leaves every bit of the result unchanged.
+    const int rot = (ht >> 1) & 3;
+    for (int gi = ht; gi < n16; gi += TH) {
+        const float4 * r4 = reinterpret_cast<const float4 *>(row + 16 * gi);
 #pragma unroll
-            for (int s = 0; s < 8; s++) kv[s] = kr[s * 4];                    // plain loads: written by the previous kernel
-        }
-        float kf[8][4];
+        for (int q = 0; q < 4; q++) { const float4 v = r4[(q + rot) & 3]; mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) redf[h][w] = mx;
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");
+    mx = redf[h][0];
 #pragma unroll
-        for (int s = 0; s < 8; s++) {
-            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].x));
-            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].y));
-            kf[s][0] = f0.x; kf[s][1] = f0.y; kf[s][2] = f1.x; kf[s][3] = f1.y;
-        }
-        // the next pass' rows are requested before this pass' arithmetic
-        {
-            const int lpn = lp + ATC_PASS, tn = 16 * v0 + lpn;
-#pragma unroll
-            for (int s = 0; s < 8; s++) kv[s] = make_uint2(0u, 0u);
-            if (lpn < npos && tn < n_kv - 1) {
-                const uint2 * kr = k_ptr(tn);
-#pragma unroll
-                for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);
-            }
-        }
-        if (lp < npos) {                                       // npos % 16 == 0: groups of 4 lanes take the branch together
+    for (int j = 1; j < NW; j++) mx = fmaxf(mx, redf[h][j]);
+    double part = 0.0;
+    for (int gi = ht; gi < n16; gi += TH) {
+        float4 * r4 = reinterpret_cast<float4 *>(row + 16 * gi);
+        // _mm512_reduce_add_ps of the vector's 16 exponentials: (a[8+i] + a[i]) pairs float4 f with f+2, so the vector is
+        // walked as two such pairs in a ROLLED loop (8 inlined ggml_v_expf instead of 16: instruction footprint)
+        float4 t[2];
 #pragma unroll 1
-            for (int h = 0; h < GQA; h++) {                    // rolled: instruction footprint
-                float ch[4];
-                if (!round_q) {
-                    // tinyBLAS<16>: lane c: acc = fma(k[16s+c], q[16s+c], acc), s = 0..7
+        for (int pq = 0; pq < 2; pq++) {
+            const int f0 = (pq + rot) & 3, f1 = f0 ^ 2;
+            float4 lo = r4[f0], hi = r4[f1];
+            lo.x = v_expf(__fsub_rn(lo.x, mx)); lo.y = v_expf(__fsub_rn(lo.y, mx)); lo.z = v_expf(__fsub_rn(lo.z, mx)); lo.w = v_expf(__fsub_rn(lo.w, mx));
+            hi.x = v_expf(__fsub_rn(hi.x, mx)); hi.y = v_expf(__fsub_rn(hi.y, mx)); hi.z = v_expf(__fsub_rn(hi.z, mx)); hi.w = v_expf(__fsub_rn(hi.w, mx));
+            r4[f0] = lo; r4[f1] = hi;
+            // fp32 addition is commutative: which of the pair is the "upper" float4 does not change the sum
+            const float4 tt = make_float4(__fadd_rn(hi.x, lo.x), __fadd_rn(hi.y, lo.y), __fadd_rn(hi.z, lo.z), __fadd_rn(hi.w, lo.w));
+            // the pair {f, f+2} with f even is t[0..3] of the tree, the odd one is t[4..7]
+            if (f0 & 1) t[1] = tt; else t[0] = tt;
+        }
+        const float u0 = __fadd_rn(t[1].x, t[0].x), u1 = __fadd_rn(t[1].y, t[0].y), u2 = __fadd_rn(t[1].z, t[0].z), u3 = __fadd_rn(t[1].w, t[0].w);
+        part += (double) __fadd_rn(__fadd_rn(u0, u2), __fadd_rn(u1, u3));
+    }
+    part = warp_sum_d(part);
+    if (lane == 0) redd[h][w] = part;
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + h), "r"(TH) : "memory");
+    double sum = 0.0;
 #pragma unroll
-                    for (int e = 0; e < 4; e++) ch[e] = 0.f;
+    for (int j = 0; j < NW; j++) sum += redd[h][j];
+    const float inv = (float) (1.0 / sum);
+    for (int gi = ht; gi < n16; gi += TH) {                    // own vectors only
+        float4 * r4 = reinterpret_cast<float4 *>(row + 16 * gi);
 #pragma unroll
-                    for (int s = 0; s < 8; s++) {
-                        const float4 qv = *reinterpret_cast<const float4 *>(&qs[h][16 * s + 4 * c4]);
-                        ch[0] = __fmaf_rn(kf[s][0], qv.x, ch[0]); ch[1] = __fmaf_rn(kf[s][1], qv.y, ch[1]);
-                        ch[2] = __fmaf_rn(kf[s][2], qv.z, ch[2]); ch[3] = __fmaf_rn(kf[s][3], qv.w, ch[3]);
-                    }
-                } else {
-                    // ggml_vec_dot_f16: sum[j][c] over i in {0, 64}: element i + 16j + c; then (0+2)+(1+3)
-                    float aj[4][4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float4 q0 = *reinterpret_cast<const float4 *>(&qs[h][16 * j + 4 * c4]);
-                        const float4 q1 = *reinterpret_cast<const float4 *>(&qs[h][64 + 16 * j + 4 * c4]);
-                        aj[j][0] = __fmaf_rn(kf[4 + j][0], q1.x, __fmul_rn(kf[j][0], q0.x));
-                        aj[j][1] = __fmaf_rn(kf[4 + j][1], q1.y, __fmul_rn(kf[j][1], q0.y));
-                        aj[j][2] = __fmaf_rn(kf[4 + j][2], q1.z, __fmul_rn(kf[j][2], q0.z));
-                        aj[j][3] = __fmaf_rn(kf[4 + j][3], q1.w, __fmul_rn(kf[j][3], q0.w));
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; e++) ch[e] = __fadd_rn(__fadd_rn(aj[0][e], aj[2][e]), __fadd_rn(aj[1][e], aj[3][e]));
-                }
-                // _mm512_reduce_add_ps over the 16 chains (fp32 addition is commutative, so after the two exchanges every
-                // one of the 4 lanes holds the same tree result)
-                float t3[4], t6[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) t3[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, ch[e], 2), ch[e]);   // a[8+i] + a[i]
-#pragma unroll
-                for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);   // t3[4+i] + t3[i]
-                const float res = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
-                if ((h & 3) == c4) sbuf[(size_t) h * s_stride + lp] = t < n_kv ? __fmul_rn(res, a.scale) : -INFINITY;
-            }
+        for (int q = 0; q < 4; q++) {
+            float4 v = r4[(q + rot) & 3];
+            v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv); v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
+            r4[(q + rot) & 3] = v;
         }
     }
-    __syncthreads();
+    __syncthreads();                                           // all rows normalised, every thread's V copies landed
     trace_mark<TR>(a.trace, 3);
 
-    // ---- per-head maximum: local, then across the cluster
-    const int h = tid / TH, ht = tid % TH;                     // head of the soft-max steps, thread within the head
-    {
-        float mx = -INFINITY;
-        const float * row = sbuf + (size_t) h * s_stride;
-        for (int i = ht; i < npos; i += TH) mx = fmaxf(mx, row[i]);
-        mx = warp_max(mx);
-        if (lane == 0) wmax[warp] = mx;
-        __syncthreads();
-        if (tid < GQA) {
-            constexpr int WPH = TH / 32;                       // warps per head
-            float m = wmax[tid * WPH];
-#pragma unroll
-            for (int w = 1; w < WPH; w++) m = fmaxf(m, wmax[tid * WPH + w]);
-            lmaxs[tid] = m;
+    // P.V: chain c of (head h, dims 2dp, 2dp+1): acc = fma(V[t][d], p[t], acc) over t = c, c+16, ...
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int t0 = 0; t0 < n_pad; t0 += VCH) {
+        const int len = min(VCH, n_pad - t0);
+        if (t0) {
+            __syncthreads();
+            stage_v(t0);
+            cp_async_wait<0>();
+            __syncthreads();
         }
-        __syncthreads();
+        const int steps = len / 16;
+        const float * pr = row + t0 + c;
+        if (DPT == 2) {
+            const __half2 * vr = reinterpret_cast<const __half2 *>(&vs[c][2 * dp]);
+#pragma unroll 8
+            for (int s = 0; s < steps; s++) {
+                const float2 v = __half22float2(vr[(size_t) s * 16 * (PVS_DIMS / 2)]);
+                const float p = pr[16 * s];
+                acc0 = __fmaf_rn(v.x, p, acc0);
+                acc1 = __fmaf_rn(v.y, p, acc1);
+            }
+        } else {
+            const __half * vr = &vs[c][dp];
+#pragma unroll 8
+            for (int s = 0; s < steps; s++)
+                acc0 = __fmaf_rn(__half2float(vr[(size_t) s * 16 * PVS_DIMS]), pr[16 * s], acc0);
+        }
     }
-    cluster_wait_acquire();                                    // #0: every CTA of the cluster has started
-    if (tid < ATC_CS * GQA) {
-        const int hh = tid / ATC_CS, dst = tid % ATC_CS;
-        st_cluster_f32(mapa_u32(smem_u32(&mbuf[r][hh]), (uint32_t) dst), lmaxs[hh]);
-    }
-    cluster_arrive_release();                                  // #1
-    cluster_wait_acquire();
-    if (tid < GQA) {
-        float m = mbuf[0][tid];
-#pragma unroll
-        for (int rr = 1; rr < ATC_CS; rr++) m = fmaxf(m, mbuf[rr][tid]);
-        gmaxs[tid] = m;
-    }
+    if (DPT == 2) { red[h][c][2 * dp] = acc0; red[h][c][2 * dp + 1] = acc1; }
+    else          red[h][c][dp] = acc0;
     __syncthreads();
     trace_mark<TR>(a.trace, 4);
-
-    // ---- p = ggml_v_expf(s - max) of my positions: kept for the vector sums, and scattered to the CTA that runs the
-    // P.V chain of the position (t mod 16), slot t / 16
-    {
-        const float mx = gmaxs[h];
-        float * row = sbuf + (size_t) h * s_stride;
-        for (int i = ht; i < npos; i += TH) {
-            const float e = v_expf(__fsub_rn(row[i], mx));
-            row[i] = e;
-            const int t = 16 * v0 + i;
-            st_cluster_f32(mapa_u32(smem_u32(pbuf + (size_t) h * p_stride + (t >> 4)), (uint32_t) (t & 15)), e);
-        }
-    }
-    __syncthreads();
-    // per-vector float sums (_mm512_reduce_add_ps tree) accumulated in double (cpp/ggml/src/ggml.c:2619-2640); double
-    // addition of these few hundred floats is order-insensitive after the final cast (see k_attn_softmax)
-    if (warp < GQA) {
-        const float * row = sbuf + (size_t) warp * s_stride;
-        double part = 0.0;
-        for (int v = lane; v < v1 - v0; v += 32) {
-            float e16[16];
+    if (tid < GQA * PVS_DIMS) {
+        const int hh = tid / PVS_DIMS, dd = tid % PVS_DIMS;
+        float t3[8], t6[4];                                   // _mm512_reduce_add_ps over the 16 chains
 #pragma unroll
-            for (int q4 = 0; q4 < 4; q4++) {
-                const float4 x = *reinterpret_cast<const float4 *>(row + 16 * v + 4 * q4);
-                e16[4 * q4] = x.x; e16[4 * q4 + 1] = x.y; e16[4 * q4 + 2] = x.z; e16[4 * q4 + 3] = x.w;
-            }
-            part += (double) reduce_add16_regs(e16);
-        }
-        part = warp_sum_d(part);
-        if (lane < ATC_CS) st_cluster_f64(mapa_u32(smem_u32(&dsum[r][warp]), (uint32_t) lane), part);
-    }
-    cluster_arrive_release();                                  // #2: exponentials and partial sums delivered
-    cluster_wait_acquire();
-    if (tid < GQA) {
-        double sum = 0.0;
-#pragma unroll
-        for (int rr = 0; rr < ATC_CS; rr++) sum += dsum[rr][tid];
-        invs[tid] = (float) (1.0 / sum);
-    }
-    cp_async_wait<0>();
-    __syncthreads();                                           // invs, and every thread's V copies
-    trace_mark<TR>(a.trace, 5);
-
-    // ---- P.V, chain r: thread = (head slot hs, dim d): acc = fma(V[16j + r][d], p[16j + r], acc) over j in order
-    {
-        const int d = tid & (HD - 1), hs = tid >> 7;
-        float acc[NH], inv[NH];
-        const float * pr[NH];
-#pragma unroll
-        for (int u = 0; u < NH; u++) {
-            const int hh = min(hs + 4 * u, GQA - 1);
-            acc[u] = 0.f; inv[u] = invs[hh]; pr[u] = pbuf + (size_t) hh * p_stride;
-        }
-        const bool active = hs < GQA;
-        for (int j0 = 0; j0 < n16; j0 += a.v_rows) {
-            const int rows = min(a.v_rows, n16 - j0);
-            if (j0) {                                          // contexts whose chain rows exceed the stage: next chunk
-                __syncthreads();
-                stage_v(j0, false);
-                cp_async_wait<0>();
-                __syncthreads();
-            }
-            if (active) {
-                const __half * vr = vbuf + d;
-#pragma unroll 8
-                for (int j = 0; j < rows; j++) {
-                    const float v = __half2float(vr[(size_t) j * HD]);
-#pragma unroll
-                    for (int u = 0; u < NH; u++) acc[u] = __fmaf_rn(v, __fmul_rn(pr[u][j0 + j], inv[u]), acc[u]);
-                }
-            }
-        }
-        // the chain value of (head, dim) goes to the CTA that owns the dim (d / 8)
-        if (active) {
-#pragma unroll
-            for (int u = 0; u < NH; u++)
-                if (hs + 4 * u < GQA)
-                    st_cluster_f32(mapa_u32(smem_u32(&obuf[hs + 4 * u][d & 7][r]), (uint32_t) (d >> 3)), acc[u]);
-        }
-    }
-    cluster_arrive_release();                                  // #3: chain values delivered
-    cluster_wait_acquire();
-    trace_mark<TR>(a.trace, 6);
-    if (tid < GQA * 8) {
-        const int hh = tid >> 3, dl = tid & 7;
-        float t3[8], t6[4];                                    // _mm512_reduce_add_ps over the 16 chains
-#pragma unroll
-        for (int j = 0; j < 8; j++) t3[j] = __fadd_rn(obuf[hh][dl][8 + j], obuf[hh][dl][j]);
+        for (int j = 0; j < 8; j++) t3[j] = __fadd_rn(red[hh][8 + j][dd], red[hh][j][dd]);
 #pragma unroll
         for (int j = 0; j < 4; j++) t6[j] = __fadd_rn(t3[4 + j], t3[j]);
-        a.out[(size_t) (g * GQA + hh) * HD + r * 8 + dl] =
+        a.out[(size_t) (g * GQA + hh) * HD + slice * PVS_DIMS + dd] =
             __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));     // kqv_merged_cont layout: [n_head*hd]
     }
-    trace_mark<TR>(a.trace, 7);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -196,8 +196,8 @@ int b200_op_rope(float * x, int n_heads, int head_dim, int pos, float freq_base,
  * round_q = 0: batch-1 arithmetic (tinyBLAS F16xF32); 1: batch>1 (q rounded to f16, ggml_vec_dot_f16). */
 int b200_op_attention(const float * q, const uint16_t * k_cache, const uint16_t * v_cache, int n_kv,
                       int n_head, int n_head_kv, int head_dim, float scale, int round_q, float * out);
-/* which kernels run the attention: 0 = automatic (one 16-CTA-cluster launch per layer when a CTA's share of the context
- * fits its shared memory, else the three-launch long-context route), 1 = always the long-context route. Process-wide;
+/* which kernels run the attention: 0 = automatic (scores + fused softmax/P.V when the GQA score rows of the context fit
+ * one CTA's shared memory, else the three-launch long-context route), 1 = always the long-context route. Process-wide;
  * exists so that tests cover both routes at every size. */
 void b200_set_attention_route(int route);
 

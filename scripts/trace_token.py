@@ -26,8 +26,7 @@ for i in range(len(st)):
     s = st[i, :ctas, :].astype(np.int64)
     # phase columns in time order: matvec 0 start,1 ring part-filled,2 after wait,5 x consumed,6 norm scale,3 prologue done,4 end
     #   7 first tile landed, 8 its integers done, 9 first round published (G>1), 11 first round's chains done, 10 warp 0 out of work
-    # k_attn_cluster: 0 start, 1 K/V requested, 2 after wait, 3 scores, 4 cluster max, 5 soft-max done, 6 chains exchanged, 7 end
-    order = list(range(8)) if kind == 2 else ([0, 1, 2, 3, 4] if kind == 7 else [0, 1, 2, 5, 6, 3, 7, 8, 9, 11, 10, 4])
+    order = [0, 1, 2] if kind == 2 else ([0, 1, 2, 3, 4] if kind == 7 else [0, 1, 2, 5, 6, 3, 7, 8, 9, 11, 10, 4])
     nph = len(order)
     s = s[s[:, order[-1]] > 0]                   # CTAs that exited early (beyond n_kv) have no end stamp
     s = s[:, order]
