@@ -18,6 +18,7 @@
 #include "gguf.hpp"
 #include "tokenizer.hpp"
 #include "kernels.cuh"
+#include "token_kernel.cuh"
 
 #include <algorithm>
 #include <array>
@@ -532,6 +533,15 @@ struct b200_ctx {
     int sm_count = 148;
     bool taps = false;
     TapStore tapstore;
+    // persistent per-token kernel (token_kernel.cuh): phase list in device memory, grid-barrier counter, transposed scores
+    Phase * d_plan = nullptr;
+    int n_phases = 0;
+    size_t token_smem = 0;
+    unsigned long long * d_bar = nullptr;
+    float * S_T = nullptr;
+    int token_state = 0;               // 0: not built yet, 1: usable, -1: not usable for this model / context
+    unsigned long long * d_ttrace = nullptr;   // b200_trace_phases
+    bool ttracing = false;
     // pipeline
     void * comm = nullptr;
     int rank = 0, world = 1;
@@ -602,10 +612,10 @@ static unsigned long long * trace_slot(b200_ctx * c, int ctas) {
 // launch shape of one mat-vec: W warps per CTA (one CTA per SM), S ring stages per warp, G warps per 32-row unit. Pick the
 // combination with the most concurrently active warps (every unit resident in as few waves as possible), then the
 // deepest ring that still fits the shared memory. Pure host arithmetic (b200_op_launch_shape exposes it to the tests).
+static constexpr size_t MV_SMEM_BUDGET = 227 * 1024 - 512;    // dynamic shared memory of k_matvec
 static void pick_launch_shape(int n_units, int tiles_unit, int k, bool norm, int act_q8_0, int stage_bytes, int nv, int sm_count,
-                              int & bestW, int & bestG, int & bestS) {
+                              int & bestW, int & bestG, int & bestS, size_t budget = MV_SMEM_BUDGET) {
     const size_t act_bytes = act_smem_bytes(k, act_q8_0);
-    const size_t budget = 227 * 1024 - 512;
     bestW = 0; bestG = 1; bestS = 0;
     double best = -1;
     for (int W = MV_MAX_WARPS; W >= 4; W -= 2) {
@@ -637,9 +647,8 @@ extern "C" int b200_op_launch_shape(const int32_t * types, int n_types, int64_t 
     return W == 0 ? set_err("activation vector too long for the shared-memory budget") : 0;
 }
 
-static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
-    ProfScope ps(c);
-    MatvecArgs a = a_in;
+// derived fields of a mat-vec (launch shape, shared-memory layout); returns the dynamic shared memory it needs
+static size_t shape_matvec(MatvecArgs & a, int epi, int sm_count, size_t budget) {
     a.epi = epi;
     a.tiles_unit = a.seg[0].tiles_unit;
     for (int i = 0; i < a.n_seg; i++)
@@ -652,25 +661,27 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
     a.nv = nv;
     const size_t act_bytes = act_smem_bytes(a.k, a.act_q8_0);
     int bestW = 0, bestG = 1, bestS = 0;
-    pick_launch_shape(a.n_units, a.tiles_unit, a.k, a.norm_w != nullptr, a.act_q8_0, a.stage_bytes, nv, c->sm_count, bestW, bestG, bestS);
+    pick_launch_shape(a.n_units, a.tiles_unit, a.k, a.norm_w != nullptr, a.act_q8_0, a.stage_bytes, nv, sm_count, bestW, bestG, bestS, budget);
     if (bestW == 0) throw std::runtime_error("activation vector too long for the shared-memory budget");
-    a.group = bestG; a.stages = bestS;
+    a.group = bestG; a.stages = bestS; a.warps = bestW;
     a.inv_k = (a.k & (a.k - 1)) == 0 ? 1.0 / (double) a.k : 0.0;
     a.chain_mode = chain_mode_of(bestG); a.act_bytes = (uint32_t) act_bytes; a.chain_bytes = (uint32_t) chain_smem_bytes(bestW, bestG, nv);
     a.exch_words = a.chain_mode == CHAIN_EXCHANGE ? (uint32_t) bestW * 2 * (uint32_t) nv * 32 : 0;
     a.kpw = a.tiles_unit / bestG; a.groups_per_cta = bestW / bestG; a.grp_magic = (uint32_t) (65536 / bestG + 1);
+    const size_t smem = (size_t) bestW * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(bestW, a.group, nv) + (size_t) bestW * a.stages * 8 + (size_t) bestW * 8;
+    if (smem > budget + 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
+    return smem;
+}
+
+static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
+    ProfScope ps(c);
+    MatvecArgs a = a_in;
+    const size_t smem = shape_matvec(a, epi, c->sm_count, MV_SMEM_BUDGET);
     static int prefill_env = -1;
     if (prefill_env < 0) { const char * e = getenv("BOOSTER_B200_PREFILL"); prefill_env = e ? atoi(e) : 0; }
     a.prefill = prefill_env;
-#if B200_WARM
-    static int warm_env = -1;
-    if (warm_env < 0) { const char * e = getenv("BOOSTER_B200_WARM"); warm_env = e ? atoi(e) : 1; }
-    a.warm_x = warm_env ? c->warm_x : nullptr;
-#endif
-    const int W = bestW;
-    const size_t smem = (size_t) W * a.stages * a.stage_bytes + act_bytes + chain_smem_bytes(W, a.group, nv) + (size_t) W * a.stages * 8 + (size_t) W * 8;
+    const int W = a.warps;
     static size_t attr_smem[64] = {0};   // per device (function attributes are per device)
-    if (smem > 227 * 1024 - 256) throw std::runtime_error("activation vector too long for the shared-memory budget");
     {
         std::lock_guard<std::mutex> attr_lock(g_attr_mu);
         if (smem > attr_smem[c->device & 63]) {
@@ -830,6 +841,140 @@ static void pf_push(PfRange (&pf)[PF_RANGES], const PfRange & r) {
     for (int i = 0; i < PF_RANGES; i++) if (!pf[i].bytes) { pf[i] = r; return; }
 }
 
+// arguments of the mat-vecs of one layer / of the head (shared by the per-kernel path and the persistent kernel's plan)
+static MatvecArgs args_qkv(b200_ctx * c, int li) {
+    b200_model & m = *c->m; LayerW & L = m.layers[(size_t) li];
+    const int E = m.n_embd, HD = m.head_dim, KVD = m.n_head_kv * HD, QD = m.n_head * HD;
+    MatvecArgs a{};
+    for (int i = 0; i < L.qkv.n_seg; i++) a.seg[i] = L.qkv.seg[i];
+    a.n_seg = L.qkv.n_seg; a.n_units = L.qkv.n_units; a.k = E;
+    a.x = c->x; a.norm_w = L.attn_norm; a.eps = m.rms_eps; a.act_q8_0 = L.qkv.seg[0].type == T_Q8_0;
+    a.q_out = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
+    a.n_q = QD; a.n_k = KVD; a.head_dim = HD; a.kv_dim = KVD; a.rope = c->rope; a.st = c->d_state;
+    return a;
+}
+static MatvecArgs args_wo(b200_ctx * c, int li) {
+    b200_model & m = *c->m; LayerW & L = m.layers[(size_t) li];
+    MatvecArgs a{};
+    a.seg[0] = L.wo.m; a.n_seg = 1; a.n_units = L.wo.m.n_units; a.k = m.n_head * m.head_dim;
+    a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = L.qkv.seg[0].type == T_Q8_0;
+    a.out = c->x; a.resid = c->x; a.st = c->d_state;
+    return a;
+}
+static MatvecArgs args_gateup(b200_ctx * c, int li) {
+    b200_model & m = *c->m; LayerW & L = m.layers[(size_t) li];
+    MatvecArgs a{};
+    a.seg[0] = L.gateup.m; a.n_seg = 1; a.n_units = L.gateup.m.n_units; a.k = m.n_embd;
+    a.x = c->x; a.norm_w = L.ffn_norm; a.eps = m.rms_eps; a.act_q8_0 = L.qkv.seg[0].type == T_Q8_0;
+    a.out = c->ffh; a.st = c->d_state;
+    return a;
+}
+static MatvecArgs args_down(b200_ctx * c, int li) {
+    b200_model & m = *c->m; LayerW & L = m.layers[(size_t) li];
+    MatvecArgs a{};
+    a.seg[0] = L.down.m; a.n_seg = 1; a.n_units = L.down.m.n_units; a.k = m.n_ff;
+    a.x = c->ffh; a.norm_w = nullptr; a.act_q8_0 = L.qkv.seg[0].type == T_Q8_0;
+    a.out = c->x; a.resid = c->x; a.st = c->d_state;
+    return a;
+}
+static MatvecArgs args_head(b200_ctx * c) {
+    b200_model & m = *c->m;
+    MatvecArgs a{};
+    a.seg[0] = m.output.m; a.n_seg = 1; a.n_units = m.output.m.n_units; a.k = m.n_embd;
+    a.x = c->x; a.norm_w = m.output_norm; a.eps = m.rms_eps; a.act_q8_0 = m.output.m.type == T_Q8_0;
+    a.out = c->logits;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// persistent per-token kernel (token_kernel.cuh): phase list of this stage, built once per context
+// ------------------------------------------------------------------------------------------------------------
+static constexpr size_t TK_SMEM_BUDGET = 208 * 1024;          // dynamic; the kernel's static shared memory is ~14 KB
+template <int GQA>
+static void token_kernel_prepare(b200_ctx * c, size_t smem) {
+    for (auto kern : { k_token<GQA, false>, k_token<GQA, true> })
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_token<GQA, false>, TK_THREADS, smem));
+    if (nb < 1) throw std::runtime_error("the per-token kernel does not fit one SM");
+}
+static bool token_kernel_enabled() {
+    static int v = -1;
+    if (v < 0) { const char * e = getenv("BOOSTER_B200_TOKEN_KERNEL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+// returns false (and remembers it) when this model / context cannot use the persistent kernel; the per-kernel path runs then
+static bool token_kernel_build(b200_ctx * c) {
+    if (c->token_state != 0) return c->token_state > 0;
+    c->token_state = -1;
+    b200_model & m = *c->m;
+    const int HD = m.head_dim, KVD = m.n_head_kv * HD, gqa = m.n_head / m.n_head_kv;
+    if (HD != 128 || (gqa != 1 && gqa != 2 && gqa != 4 && gqa != 8) || m.layers.empty()) return false;
+    try {
+        const int rs = (c->n_ctx / 16 + 3) / 4 * 4;
+        const size_t ps_bytes = (size_t) gqa * 16 * rs * 4;
+        if (ps_bytes + 64 * 16 > TK_SMEM_BUDGET) return false;            // the GQA score rows of the context must fit one CTA
+        int v_chunk = (int) std::min<size_t>((size_t) (c->n_ctx + 63) / 64 * 64, (TK_SMEM_BUDGET - ps_bytes) / 16 / 64 * 64);
+        size_t smem = ps_bytes + (size_t) v_chunk * 16;
+        std::vector<Phase> plan;
+        auto push_mv = [&](MatvecArgs a, int epi) {
+            Phase P{};
+            P.kind = PH_MATVEC;
+            smem = std::max(smem, shape_matvec(a, epi, c->sm_count, TK_SMEM_BUDGET));
+            P.mv = a;
+            plan.push_back(P);
+        };
+        for (int li = 0; li < (int) m.layers.size(); li++) {
+            push_mv(args_qkv(c, li), EPI_QKV);
+            Phase P{};
+            P.at.q = c->q; P.at.k_cache = c->kc[(size_t) li]; P.at.v_cache = c->vc[(size_t) li];
+            P.at.rs = rs; P.at.out = c->att; P.at.n_head_kv = m.n_head_kv; P.at.kv_dim = KVD;
+            P.at.scale = 1.0f / sqrtf((float) HD); P.at.st = c->d_state; P.at.v_chunk = v_chunk;
+            P.kind = PH_SCORES; plan.push_back(P);
+            P.kind = PH_SOFTMAX_PV; plan.push_back(P);
+            push_mv(args_wo(c, li), EPI_RESID);
+            push_mv(args_gateup(c, li), EPI_SILU);
+            push_mv(args_down(c, li), EPI_RESID);
+        }
+        if (m.has_head()) push_mv(args_head(c), EPI_STORE);
+        CU(cudaMalloc(&c->S_T, (size_t) m.n_head * 16 * rs * 4));
+        for (auto & P : plan) P.at.S = c->S_T;
+        CU(cudaMalloc(&c->d_plan, plan.size() * sizeof(Phase)));
+        CU(cudaMemcpy(c->d_plan, plan.data(), plan.size() * sizeof(Phase), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_bar, 8));
+        CU(cudaMemset(c->d_bar, 0, 8));
+        c->n_phases = (int) plan.size();
+        c->token_smem = smem;
+        {
+            std::lock_guard<std::mutex> attr_lock(g_attr_mu);
+            switch (gqa) {
+                case 1: token_kernel_prepare<1>(c, smem); break;
+                case 2: token_kernel_prepare<2>(c, smem); break;
+                case 4: token_kernel_prepare<4>(c, smem); break;
+                default: token_kernel_prepare<8>(c, smem); break;
+            }
+        }
+        c->token_state = 1;
+        return true;
+    } catch (const std::exception & e) {
+        fprintf(stderr, "booster_b200: per-token kernel not usable (%s); using one kernel per operator\n", e.what());
+        cudaGetLastError();
+        return false;
+    }
+}
+template <int GQA>
+static void token_kernel_launch(b200_ctx * c) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned) c->sm_count); cfg.blockDim = dim3(TK_THREADS); cfg.dynamicSmemBytes = c->token_smem; cfg.stream = c->st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;                 // all CTAs co-resident, or the launch fails: the grid barrier needs it
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    unsigned long long * tr = c->ttracing ? c->d_ttrace : nullptr;
+    CU(cudaLaunchKernelEx(&cfg, tr ? k_token<GQA, true> : k_token<GQA, false>, (const Phase *) c->d_plan, c->n_phases, c->d_bar, tr));
+    c->launches++;
+}
+
 // enqueue the layers of this stage (+ embedding on the first stage, + head on the last) for ONE token whose
 // scalars are in c->d_state
 static void enqueue_forward(b200_ctx * c) {
@@ -842,20 +987,26 @@ static void enqueue_forward(b200_ctx * c) {
         k_embed<<<(E + thr - 1) / thr, thr, 0, c->st>>>(m.embd_type, m.embd_rows, m.embd_row_bytes, E, c->d_state, 0, c->x);
         c->launches++;
     }
+    // the persistent kernel runs everything after the embedding row; taps, per-launch profiling and the per-kernel phase
+    // trace need the one-kernel-per-operator path
+    if (token_kernel_enabled() && !c->taps && !c->prof && !c->tracing && g_only_kind < 0 && token_kernel_build(c)) {
+        switch (m.n_head / m.n_head_kv) {
+            case 1: token_kernel_launch<1>(c); break;
+            case 2: token_kernel_launch<2>(c); break;
+            case 4: token_kernel_launch<4>(c); break;
+            default: token_kernel_launch<8>(c); break;
+        }
+        return;
+    }
     const PfPlan & pp = pf_plan();
     for (int li = 0; li < (int) m.layers.size(); li++) {
         LayerW & L = m.layers[(size_t) li];
         const int il = m.layer_begin + li;
-        const int q80 = L.qkv.seg[0].type == T_Q8_0;
         const size_t gu_bytes = tiled_bytes(L.gateup.m);
+        (void) pp; (void) gu_bytes;
         if (want(KIND_QKV)) {   // QKV
             g_kind = KIND_QKV;
-            MatvecArgs a{};
-            for (int i = 0; i < L.qkv.n_seg; i++) a.seg[i] = L.qkv.seg[i];
-            a.n_seg = L.qkv.n_seg; a.n_units = L.qkv.n_units; a.k = E;
-            a.x = c->x; a.norm_w = L.attn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
-            a.q_out = c->q; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
-            a.n_q = QD; a.n_k = KVD; a.head_dim = HD; a.kv_dim = KVD; a.rope = c->rope; a.st = c->d_state;
+            MatvecArgs a = args_qkv(c, li);
 #if B200_LOOKAHEAD
             if (pp.kvwo > 0.f) {
                 const uint32_t row = (uint32_t) KVD * 2, all = (uint32_t) std::min<size_t>((size_t) c->n_ctx * row, 0xfffffff0u);
@@ -875,37 +1026,35 @@ static void enqueue_forward(b200_ctx * c) {
             a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD;
             a.scale = 1.0f / sqrtf((float) HD);
             a.st = c->d_state; a.n_kv_override = 0; a.round_q_override = 0;
+#if B200_LOOKAHEAD
             pf_push(a.pf,  pf_slice(L.gateup.m.p0, gu_bytes, 0.0, pp.gu_scores));
             pf_push(a.pf2, pf_slice(L.gateup.m.p0, gu_bytes, pp.gu_scores, pp.gu_scores + pp.gu_pv));
+#endif
             launch_attention(c, a, c->n_ctx);
             tap(c, "kqv_merged_cont", il, c->att, (size_t) QD);
         }
         if (want(KIND_WO)) {   // wo + residual
             g_kind = KIND_WO;
-            MatvecArgs a{};
-            a.seg[0] = L.wo.m; a.n_seg = 1; a.n_units = L.wo.m.n_units; a.k = QD;
-            a.x = c->att; a.norm_w = nullptr; a.act_q8_0 = q80;
-            a.out = c->x; a.resid = c->x; a.st = c->d_state;
+            MatvecArgs a = args_wo(c, li);
+#if B200_LOOKAHEAD
             pf_push(a.pf, pf_slice(L.gateup.m.p0, gu_bytes, pp.gu_scores + pp.gu_pv, pp.gu_scores + pp.gu_pv + pp.gu_wo));
+#endif
             launch_matvec(c, a, EPI_RESID);
             tap(c, "ffn_inp", il, c->x, (size_t) E);
         }
         if (want(KIND_GATEUP)) {   // gate/up (interleaved virtual matrix) + SiLU*mul
             g_kind = KIND_GATEUP;
-            MatvecArgs a{};
-            a.seg[0] = L.gateup.m; a.n_seg = 1; a.n_units = L.gateup.m.n_units; a.k = E;
-            a.x = c->x; a.norm_w = L.ffn_norm; a.eps = m.rms_eps; a.act_q8_0 = q80;
-            a.out = c->ffh; a.st = c->d_state;
+            MatvecArgs a = args_gateup(c, li);
+#if B200_LOOKAHEAD
             pf_push(a.pf, pf_slice(L.down.m.p0, tiled_bytes(L.down.m), 0.0, pp.down));
+#endif
             launch_matvec(c, a, EPI_SILU);
             tap(c, "ffn_gate_par", il, c->ffh, (size_t) FF);
         }
         if (want(KIND_DOWN)) {   // down + residual
             g_kind = KIND_DOWN;
-            MatvecArgs a{};
-            a.seg[0] = L.down.m; a.n_seg = 1; a.n_units = L.down.m.n_units; a.k = FF;
-            a.x = c->ffh; a.norm_w = nullptr; a.act_q8_0 = q80;
-            a.out = c->x; a.resid = c->x; a.st = c->d_state;
+            MatvecArgs a = args_down(c, li);
+#if B200_LOOKAHEAD
             if (li + 1 < (int) m.layers.size()) {
                 const DevStack & nq = m.layers[(size_t) li + 1].qkv;
                 pf_push(a.pf, pf_slice(nq.seg[0].p0, tiled_bytes(nq), 0.0, pp.next));
@@ -914,16 +1063,14 @@ static void enqueue_forward(b200_ctx * c) {
                 const size_t hb = tiled_bytes(m.output.m);
                 pf_push(a.pf, pf_slice(m.output.m.p0, hb, 0.0, pp.next * std::min(1.0, 32.0e6 / (double) hb)));
             }
+#endif
             launch_matvec(c, a, EPI_RESID);
             tap(c, "l_out", il, c->x, (size_t) E);
         }
     }
     if (m.has_head() && want(KIND_HEAD)) {
         g_kind = KIND_HEAD;
-        MatvecArgs a{};
-        a.seg[0] = m.output.m; a.n_seg = 1; a.n_units = m.output.m.n_units; a.k = E;
-        a.x = c->x; a.norm_w = m.output_norm; a.eps = m.rms_eps; a.act_q8_0 = m.output.m.type == T_Q8_0;
-        a.out = c->logits;
+        MatvecArgs a = args_head(c);
         launch_matvec(c, a, EPI_STORE);
         tap(c, "result_output", -1, c->logits, (size_t) m.n_vocab);
     }
@@ -1025,7 +1172,7 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     for (auto p : c->kc) cudaFree(p);
     for (auto p : c->vc) cudaFree(p);
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->warm_x); cudaFree(c->logits);
-    cudaFree(c->d_trace);
+    cudaFree(c->d_trace); cudaFree(c->d_plan); cudaFree(c->d_bar); cudaFree(c->S_T); cudaFree(c->d_ttrace);
     cudaFree(c->S); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits); cudaFreeHost(c->h_tok);
     if (c->g_step) cudaGraphExecDestroy(c->g_step);

@@ -93,7 +93,8 @@ struct MatvecArgs {
     double inv_k;              // 1.0 / k if k is a power of two, else 0 (rms_scale)
     int act_q8_0;              // 0: Q8_K activations, 1: Q8_0 activations
     int tiles_unit;            // identical for every segment of a launch (same K, same block width)
-    int group;                 // G = warps sharing one 32-row unit (a divisor of the CTA's warp count)
+    int warps;                 // W = warps of the CTA that work on this mat-vec (all of them in k_matvec)
+    int group;                 // G = warps sharing one 32-row unit (a divisor of W)
     int kpw;                   // = tiles_unit / group   (host-computed: integer divisions are ~20 instructions each on
     int groups_per_cta;        // = warps / group         the device, and these kernels are instruction-fetch bound)
     uint32_t grp_magic;        // warp / group == (warp * grp_magic) >> 16 for warp < 32
@@ -385,12 +386,14 @@ __device__ __forceinline__ float rms_scale(double tot, int k, double inv_k, floa
     const float mean = inv_k != 0.0 ? (float) (tot * inv_k) : (float) (tot / (double) k);
     return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
 }
+// barrier of the first `nwarp` warps of the CTA (a mat-vec phase of the persistent kernel may run on fewer warps than the
+// CTA has; barrier 15 is reserved for it, 1..8 are the K-split groups')
+__device__ __forceinline__ void sync_warps(int nwarp) { asm volatile("bar.sync 15, %0;" :: "r"(nwarp * 32) : "memory"); }
 template <bool TR, typename F>
 __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, bool norm, float eps, int k, double inv_k, int act_q8_0,
                                                   const ActSmem & A, double * red, const float (&pre_w)[PRO_U][8], F after_loads,
-                                                  unsigned long long * tr = nullptr) {
+                                                  int nwarp, unsigned long long * tr = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarp = blockDim.x >> 5;
     const int n256 = k / 256;
     bool first = true;
     for (int b0 = warp; b0 < n256 || first; b0 += PRO_U * nwarp) {
@@ -415,7 +418,7 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
             s = warp_sum_d(s);
             if (lane == 0) red[warp] = s;
             trace_mark<TR>(tr, 5);
-            __syncthreads();
+            sync_warps(nwarp);
             double tot = 0.0;
             for (int w = 0; w < nwarp; w++) tot += red[w];
             scale = rms_scale(tot, k, inv_k, eps);
@@ -763,75 +766,100 @@ __device__ __noinline__ void matvec_epilogue(const MatvecArgs & a, float val, in
     }
 }
 
-template <bool TR>
-__global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_constant__ MatvecArgs a) {
-    const int EPI = a.epi;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ double red_smem[MV_MAX_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int G = a.group, TU = a.tiles_unit, S = a.stages, KPW = a.kpw;
-    // shared memory: ring (128-byte aligned slots) | activations | hand-off buffers | mbarriers
-    uint8_t * ring = smem_raw + (size_t) warp * S * a.stage_bytes;
-    uint8_t * act_base = smem_raw + (size_t) W * S * a.stage_bytes;
-    const size_t act_bytes = a.act_bytes;
-    const ActSmem A = act_smem_carve(act_base, a.k, a.act_q8_0);
-    const int grp = (int) (((uint32_t) warp * a.grp_magic) >> 16), w = warp - grp * G;   // group inside the CTA, warp inside the group
-    const int NV = a.nv;
-    const int mode = a.chain_mode;
-    // chain region: exchange: cbuf[parity][warp of the CTA][value][lane] | fin[group][chain][lane]; hand-off: fin only
-    float * cbuf = reinterpret_cast<float *>(act_base + act_bytes);
-    float * fin  = cbuf + a.exch_words + (size_t) grp * HANDOFF_WORDS;
-    uint64_t * bars = reinterpret_cast<uint64_t *>(act_base + act_bytes + a.chain_bytes);
-    const uint32_t full0   = smem_u32(bars + warp * S);                            // my ring slots' "tile landed" barriers
-    const uint32_t edge_in  = smem_u32(bars + W * S + warp);                        // hand-off: "chain state for me is published"
-    const uint32_t edge_out = smem_u32(bars + W * S + grp * G + (w + 1 == G ? 0 : w + 1));
-    const uint32_t ring_u32 = smem_u32(ring);
-    const int bar_id = 1 + grp, bar_threads = G * 32;                              // the group's named barrier
+// per-thread state of one mat-vec between its two halves: mv_begin (everything that does not depend on the input vector:
+// shared-memory carve-up, barrier init, work split, the first weight tiles requested, norm weights) and mv_run (prologue on
+// x, the tile loop, epilogues). k_matvec runs them around griddepcontrol.wait; the persistent per-token kernel runs
+// mv_begin of the NEXT phase before it waits at the grid barrier, so HBM streams through the barrier.
+struct MvState {
+    uint8_t * ring; uint8_t * act_base;
+    ActSmem A;
+    float * cbuf; float * fin;
+    uint32_t full0, edge_in, edge_out, ring_u32;
+    int grp, w, bar_id, bar_threads;
+    int group_global, n_groups, my_units, n_items;
+    int pi, pj, pk, ps;
+    UnitDesc pd;
+    uint64_t pol;
+};
 
-    trace_mark<TR>(a.trace, 0);
-    pdl_launch_dependents();                                   // the next kernel may start its own weight prefetch
+// producer side: item pi = (unit pj, tile w + G*pk) goes to ring slot pi % S
+__device__ __forceinline__ void mv_issue_next(const MatvecArgs & a, MvState & s, int lane) {
+    if (s.pi >= s.n_items) return;
+    if (lane == 0) {
+        mbar_expect_tx(s.full0 + 8 * s.ps, s.pd.bytes);
+        bulk_g2s_hint(s.ring_u32 + (uint32_t) s.ps * a.stage_bytes, s.pd.tiles + (size_t) (s.w + a.group * s.pk) * s.pd.bytes, s.pd.bytes,
+                      s.full0 + 8 * s.ps, s.pol);
+    }
+    s.pi++; s.ps = s.ps + 1 == a.stages ? 0 : s.ps + 1;
+    if (++s.pk == a.kpw) {
+        s.pk = 0; s.pj++;
+        if (s.pi < s.n_items) s.pd = describe_unit(a, s.group_global + s.pj * s.n_groups);
+    }
+}
+
+// cta / n_cta: this CTA's index and the number of CTAs that share the mat-vec; n_prefill: tiles per warp requested now
+template <bool TR>
+__device__ __forceinline__ void mv_begin(const MatvecArgs & a, uint8_t * smem_raw, int cta, int n_cta, int n_prefill, MvState & s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = a.warps;
+    const int G = a.group, S = a.stages;
+    // shared memory: ring (128-byte aligned slots) | activations | hand-off buffers | mbarriers
+    s.ring = smem_raw + (size_t) warp * S * a.stage_bytes;
+    s.act_base = smem_raw + (size_t) W * S * a.stage_bytes;
+    const size_t act_bytes = a.act_bytes;
+    s.A = act_smem_carve(s.act_base, a.k, a.act_q8_0);
+    s.grp = (int) (((uint32_t) warp * a.grp_magic) >> 16); s.w = warp - s.grp * G;   // group inside the CTA, warp inside the group
+    // chain region: exchange: cbuf[parity][warp of the CTA][value][lane] | fin[group][chain][lane]; hand-off: fin only
+    s.cbuf = reinterpret_cast<float *>(s.act_base + act_bytes);
+    s.fin  = s.cbuf + a.exch_words + (size_t) s.grp * HANDOFF_WORDS;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(s.act_base + act_bytes + a.chain_bytes);
+    s.full0    = smem_u32(bars + warp * S);                            // my ring slots' "tile landed" barriers
+    s.edge_in  = smem_u32(bars + W * S + warp);                        // hand-off: "chain state for me is published"
+    s.edge_out = smem_u32(bars + W * S + s.grp * G + (s.w + 1 == G ? 0 : s.w + 1));
+    s.ring_u32 = smem_u32(s.ring);
+    s.bar_id = 1 + s.grp; s.bar_threads = G * 32;                      // the group's named barrier
     if (lane == 0) {                                           // each warp: its own ring barriers and its edge barrier
 #pragma unroll 1
-        for (int s = 0; s < S; s++) mbar_init(full0 + 8 * s, 1);
-        mbar_init(edge_in, 32);
+        for (int st = 0; st < S; st++) mbar_init(s.full0 + 8 * st, 1);
+        mbar_init(s.edge_in, 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();                                              // (the edge barriers of OTHER warps are first used after the
-                                                               //  prologue's __syncthreads)
-
-    // group-major mapping: unit u -> CTA u % grid, group (u / grid) % groups_per_cta, so that launches with few
+                                                               //  prologue's barrier)
+    // group-major mapping: unit u -> CTA u % n_cta, group (u / n_cta) % groups_per_cta, so that mat-vecs with few
     // units spread over every SM
-    const int groups_per_cta = a.groups_per_cta;
-    const int group_global = grp * gridDim.x + blockIdx.x;
-    const int n_groups = gridDim.x * groups_per_cta;
-    const int my_units = group_global < a.n_units ? (a.n_units - group_global + n_groups - 1) / n_groups : 0;
-    const int n_items = my_units * KPW;
-
-    // ---- producer side: item pi = (unit pj, tile w + G*pk) goes to ring slot pi % S
-    int pi = 0, pj = 0, pk = 0, ps = 0;
-    UnitDesc pd = describe_unit(a, my_units > 0 ? group_global : 0);
+    s.group_global = s.grp * n_cta + cta;
+    s.n_groups = n_cta * a.groups_per_cta;
+    s.my_units = s.group_global < a.n_units ? (a.n_units - s.group_global + s.n_groups - 1) / s.n_groups : 0;
+    s.n_items = s.my_units * a.kpw;
+    s.pi = 0; s.pj = 0; s.pk = 0; s.ps = 0;
+    s.pd = describe_unit(a, s.my_units > 0 ? s.group_global : 0);
     // weight tiles are read exactly once per token: the copies carry the L2 evict-first hint, so streaming 4.6 GB of
     // them per token does not push the activations, the K/V rows and the kernels' own code out of L2
-    const uint64_t pol = l2_policy_evict_first();
-    auto issue_next = [&]() {
-        if (pi >= n_items) return;
-        if (lane == 0) {
-            mbar_expect_tx(full0 + 8 * ps, pd.bytes);
-            bulk_g2s_hint(ring_u32 + (uint32_t) ps * a.stage_bytes, pd.tiles + (size_t) (w + G * pk) * pd.bytes, pd.bytes, full0 + 8 * ps, pol);
-        }
-        pi++; ps = ps + 1 == S ? 0 : ps + 1;
-        if (++pk == KPW) {
-            pk = 0; pj++;
-            if (pi < n_items) pd = describe_unit(a, group_global + pj * n_groups);
-        }
-    };
-    // weights do not depend on x: part of the ring is filled before the wait, the rest once the x loads are in flight
-    const int prefill = min(a.prefill, S - 1);
+    s.pol = l2_policy_evict_first();
+    // weights do not depend on x: (part of) the ring is filled before the input exists
+    const int prefill = min(n_prefill, S - 1);
 #pragma unroll 1
-    for (int s = 0; s < prefill; s++) issue_next();
-    // norm weights are constants too: the warp's blocks (the host guarantees k/256 <= PRO_U * W when there is a norm)
+    for (int st = 0; st < prefill; st++) mv_issue_next(a, s, lane);
+}
+
+template <bool TR>
+__device__ __forceinline__ void mv_run(const MatvecArgs & a, double * red_smem, int n_prefilled, MvState & s) {
+    const int EPI = a.epi;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = a.warps;
+    const int G = a.group, TU = a.tiles_unit, S = a.stages, KPW = a.kpw;
+    const int NV = a.nv, mode = a.chain_mode;
+    const int grp = s.grp, w = s.w;
+    uint8_t * const ring = s.ring;
+    const ActSmem A = s.A;
+    float * const cbuf = s.cbuf; float * const fin = s.fin;
+    const uint32_t full0 = s.full0, edge_in = s.edge_in, edge_out = s.edge_out;
+    const int bar_id = s.bar_id, bar_threads = s.bar_threads;
+    const int group_global = s.group_global, n_groups = s.n_groups, my_units = s.my_units;
     const bool norm = a.norm_w != nullptr;
+    const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
+    // norm weights: the warp's blocks (the host guarantees k/256 <= PRO_U * W when there is a norm); constants, requested
+    // together with x
     float ww[PRO_U][8] = {};
     if (norm) {
 #pragma unroll
@@ -840,46 +868,12 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
             if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, ww[u]);
         }
     }
-
-    // L2 look-ahead for the kernels that follow (after this CTA's own first tiles are requested). DecodeState is
-    // written by the previous TOKEN's last kernel, so pos may be read before the wait.
-#if B200_LOOKAHEAD
-    if (lane == 0 && a.pf[0].bytes) issue_l2_lookahead(a.pf, warp * gridDim.x + blockIdx.x, W * gridDim.x, a.st ? a.st->pos : 0);
-#endif
-
-    trace_mark<TR>(a.trace, 1);
-#if B200_WARM
-    // Pass 0 (a.warm_x != nullptr): the SAME prologue instructions run once on a constant vector while this CTA would
-    // otherwise sit in griddepcontrol.wait — it reads only constants, writes only shared memory that pass 1 overwrites,
-    // and leaves the prologue's code in the instruction cache. Pass 1 is the real prologue.
-    int pos = 0;
-#pragma unroll 1
-    for (int pass = a.warm_x != nullptr ? 0 : 1; pass < 2; pass++) {
-        if (pass) {
-            pdl_wait();                                        // x (and everything else the previous kernels wrote) is visible
-            trace_mark<TR>(a.trace, 2);
-            pos = EPI == EPI_QKV ? a.st->pos : 0;              // in flight during the prologue
-        }
-        prologue_quantize<TR>(pass ? a.x : a.warm_x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, ww,
-                          [&]() {
-                              if (pass) {
-#pragma unroll 1
-                                  for (int s = prefill; s < S - 1; s++) issue_next();
-                              }
-                          }, pass ? a.trace : nullptr);
-        __syncthreads();                                       // activations + every warp's barrier inits are visible
-    }
-#else
-    pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
-    trace_mark<TR>(a.trace, 2);
-    const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
     prologue_quantize<TR>(a.x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, ww,
                       [&]() {
 #pragma unroll 1
-                          for (int s = prefill; s < S - 1; s++) issue_next();
-                      }, a.trace);
-    __syncthreads();                                           // activations + every warp's barrier inits are visible
-#endif
+                          for (int st = n_prefilled; st < S - 1; st++) mv_issue_next(a, s, lane);
+                      }, W, a.trace);
+    sync_warps(W);                                             // activations + every warp's barrier inits are visible
     trace_mark<TR>(a.trace, 3);
 
     // ---- consumer side
@@ -905,7 +899,7 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
             }
             for (int k = 0; k < KPW; k++) {
                 const int t = w + G * k;
-                issue_next();                                  // keeps S-1 tiles in flight (slot of the previous item is free)
+                mv_issue_next(a, s, lane);                     // keeps S-1 tiles in flight (slot of the previous item is free)
                 // epilogue operands of a unit that completes with this tile: fetched now, used after the chain
                 float pre0 = 0.f, pre1 = 0.f;
                 if (t == TU - 1) {
@@ -1005,6 +999,27 @@ __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_co
         }
     }
     trace_mark<TR>(a.trace, 10);                                   // warp 0 out of work
+}
+
+template <bool TR>
+__global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_constant__ MatvecArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ double red_smem[MV_MAX_WARPS];
+    trace_mark<TR>(a.trace, 0);
+    pdl_launch_dependents();                                   // the next kernel may start its own weight prefetch
+    MvState s;
+    const int prefill = min(a.prefill, a.stages - 1);
+    mv_begin<TR>(a, smem_raw, (int) blockIdx.x, (int) gridDim.x, prefill, s);
+    // L2 look-ahead for the kernels that follow (after this CTA's own first tiles are requested). DecodeState is
+    // written by the previous TOKEN's last kernel, so pos may be read before the wait.
+#if B200_LOOKAHEAD
+    if ((threadIdx.x & 31) == 0 && a.pf[0].bytes)
+        issue_l2_lookahead(a.pf, (int) (threadIdx.x >> 5) * gridDim.x + blockIdx.x, a.warps * gridDim.x, a.st ? a.st->pos : 0);
+#endif
+    trace_mark<TR>(a.trace, 1);
+    pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
+    trace_mark<TR>(a.trace, 2);
+    mv_run<TR>(a, red_smem, prefill, s);
     if (TR) { if (a.trace != nullptr) { __syncthreads(); trace_mark<TR>(a.trace, 4); } }
 }
 
@@ -1018,7 +1033,7 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
     __shared__ double red_smem[MV_MAX_WARPS];
     const ActSmem A = act_smem_carve(smem_raw, k, act_q8_0);
     const float no_w[PRO_U][8] = {};
-    prologue_quantize<false>(x, false, 0.f, k, 0.0, act_q8_0, A, red_smem, no_w, []() {});
+    prologue_quantize<false>(x, false, 0.f, k, 0.0, act_q8_0, A, red_smem, no_w, []() {}, (int) (blockDim.x >> 5));
     __syncthreads();
     if (!act_q8_0) {
         const int nb = k / 256;
