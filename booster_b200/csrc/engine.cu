@@ -921,6 +921,10 @@ static bool token_kernel_build(b200_ctx * c) {
             Phase P{};
             P.kind = PH_MATVEC;
             smem = std::max(smem, shape_matvec(a, epi, c->sm_count, TK_SMEM_BUDGET));
+            // tiles per warp requested before the grid barrier (the whole ring but one slot); BOOSTER_B200_TK_PREFILL overrides (A/B)
+            static int pf_env = -2;
+            if (pf_env == -2) { const char * e = getenv("BOOSTER_B200_TK_PREFILL"); pf_env = e ? atoi(e) : -1; }
+            a.prefill = pf_env >= 0 ? std::min(pf_env, a.stages - 1) : a.stages - 1;
             P.mv = a;
             plan.push_back(P);
         };
@@ -1152,6 +1156,8 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         CU(cudaMalloc(&c->d_out_tokens, (size_t) c->out_tokens_cap * 4));
         CU(cudaStreamSynchronize(c->st));
         CU(cudaDeviceSynchronize());
+        // the persistent kernel's phase list is built now: it allocates, and the first decode may already be a capture
+        if (token_kernel_enabled()) token_kernel_build(c.get());
         return c.release();
     } catch (const std::exception & e) {
         set_err(e.what());
@@ -1462,6 +1468,41 @@ extern "C" int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int re
         if (meta) for (int64_t i = 0; i < nl && 2 * i + 1 < cap_meta; i++) { meta[2 * i] = c->trace_meta[(size_t) i][0]; meta[2 * i + 1] = c->trace_meta[(size_t) i][1]; }
         return nl;
     } catch (const std::exception & e) { c->tracing = false; set_err(e.what()); return -1; }
+}
+
+// One token through the persistent kernel's tracing instantiation: out = [n_phases][n_ctas][4] globaltimer stamps (ns):
+// 0 the phase's dependent half starts | 1 it is done | 2 arrived at the grid barrier and the next phase's independent half
+// issued | 3 barrier passed. kinds[n_phases] = 0 mat-vec, 1 attention scores, 2 soft-max + P.V. Returns n_phases (-1: error,
+// 0: the persistent kernel is not in use for this context).
+extern "C" int64_t b200_trace_phases(b200_ctx * c, int32_t token, int pos, int reps, uint64_t * out, int64_t cap_words, int32_t * kinds,
+                                     int64_t cap_kinds, int32_t * n_ctas) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        b200_model & m = *c->m;
+        if (pos < 0 || pos >= c->n_ctx || token < 0 || token >= m.n_vocab) throw std::runtime_error("bad token/pos");
+        CU(cudaSetDevice(m.device));
+        if (!token_kernel_enabled() || !token_kernel_build(c)) return 0;
+        const size_t words = (size_t) c->n_phases * c->sm_count * TK_TRACE_SLOTS;
+        if (!c->d_ttrace) CU(cudaMalloc(&c->d_ttrace, words * 8));
+        DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = 0; hs.step = 0;
+        for (int r = 0; r < std::max(1, reps); r++) {
+            k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
+            CU(cudaMemsetAsync(c->d_ttrace, 0, words * 8, c->st));
+            c->ttracing = true;
+            try { enqueue_forward(c); } catch (...) { c->ttracing = false; throw; }
+            c->ttracing = false;
+            CU(cudaStreamSynchronize(c->st));
+        }
+        if (out && cap_words >= (int64_t) words) CU(cudaMemcpy(out, c->d_ttrace, words * 8, cudaMemcpyDeviceToHost));
+        if (kinds) {
+            std::vector<Phase> plan((size_t) c->n_phases);
+            CU(cudaMemcpy(plan.data(), c->d_plan, plan.size() * sizeof(Phase), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < c->n_phases && i < cap_kinds; i++) kinds[i] = plan[(size_t) i].kind == PH_MATVEC ? 10 + plan[(size_t) i].mv.epi : plan[(size_t) i].kind;
+        }
+        if (n_ctas) *n_ctas = c->sm_count;
+        return c->n_phases;
+    } catch (const std::exception & e) { set_err(e.what()); return -1; }
 }
 
 // ------------------------------------------------------------------------------------------------------------

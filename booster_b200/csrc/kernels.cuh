@@ -32,6 +32,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 // build-time A/B switches (scripts/gpu_variants.sh builds one library per setting)
 #ifndef B200_CHAIN_UNROLL
@@ -483,11 +484,33 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+#ifndef B200_HANG_DEBUG
+#define B200_HANG_DEBUG 0    // 1: mbarrier waits report and trap after ~2 s instead of spinning for ever (debug builds)
+#endif
+#if B200_HANG_DEBUG
+__device__ int g_dbg_phase[256];     // phase each CTA is in (token kernel), for the timeout report
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if B200_HANG_DEBUG
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+#endif
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#if B200_HANG_DEBUG
+        if (!ok && (++spins & 255u) == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) {
+                if ((threadIdx.x & 31) == 0)
+                    printf("booster_b200: mbarrier timeout: CTA %d warp %d bar 0x%x parity %u phase %d\n", (int) blockIdx.x, (int) threadIdx.x >> 5, bar, parity,
+                           g_dbg_phase[blockIdx.x & 255]);
+                __trap();
+            }
+        }
+#endif
     } while (!ok);
 }
 // global -> shared bulk copy (TMA engine, no registers, no per-lane addressing); completes `bytes` on `bar`
@@ -794,6 +817,17 @@ __device__ __forceinline__ void mv_issue_next(const MatvecArgs & a, MvState & s,
     if (++s.pk == a.kpw) {
         s.pk = 0; s.pj++;
         if (s.pi < s.n_items) s.pd = describe_unit(a, s.group_global + s.pj * s.n_groups);
+    }
+}
+
+// end of a mat-vec inside the persistent kernel: the warp's mbarriers are invalidated before their shared memory is
+// re-used by the next phase (initialising a location that still holds a valid mbarrier object is undefined — measured: a
+// later phase with the same layout then waits for ever on its first tile). Call after a barrier of the mat-vec's warps.
+__device__ __forceinline__ void mv_end(const MatvecArgs & a, const MvState & s) {
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll 1
+        for (int st = 0; st < a.stages; st++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(s.full0 + 8 * st) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(s.edge_in) : "memory");
     }
 }
 

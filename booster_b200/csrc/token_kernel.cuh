@@ -17,6 +17,7 @@
 // k_attn_scores / k_attn_softmax_pv), so every result is bit-identical to them and to the reference.
 #pragma once
 #include "kernels.cuh"
+#include <cstdio>
 
 namespace b200 {
 
@@ -60,8 +61,25 @@ __device__ __forceinline__ void grid_arrive(unsigned long long * ctr) {      // 
     __threadfence();
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(ctr), "l"(1ull) : "memory");
 }
-__device__ __forceinline__ void grid_wait(const unsigned long long * ctr, unsigned long long target) {
-    while (ld_acquire_u64(ctr) < target) { }
+// A grid that never gathers (a CTA that died, a launch that was not co-resident) must not hang the process: after
+// GRID_WAIT_NS of spinning the waiter reports where it stands and traps — the host sees a launch failure.
+static constexpr unsigned long long GRID_WAIT_NS = 4000000000ull;
+__device__ __noinline__ void grid_wait_timeout(const unsigned long long * ctr, unsigned long long target, int phase) {
+    printf("booster_b200: grid barrier timeout: CTA %d phase %d counter %llu target %llu\n", (int) blockIdx.x, phase, ld_acquire_u64(ctr), target);
+    __trap();
+}
+__device__ __forceinline__ void grid_wait(const unsigned long long * ctr, unsigned long long target, int phase) {
+    if (ld_acquire_u64(ctr) < target) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
+        while (ld_acquire_u64(ctr) < target) {
+            if ((++spins & 1023u) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > GRID_WAIT_NS) grid_wait_timeout(ctr, target, phase);
+            }
+        }
+    }
     __threadfence();
 }
 __device__ __forceinline__ void cp_async16_cg(void * smem_dst, const void * gsrc) { cp_async16(smem_dst, gsrc); }
@@ -363,7 +381,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_token(const Phase * __restric
     MvState ms;
     ScState ss;
     auto begin = [&](const Phase & P) {
-        if (P.kind == PH_MATVEC) { if (warp < P.mv.warps) mv_begin<false>(P.mv, smem_raw, cta, n_cta, P.mv.stages - 1, ms); }
+        if (P.kind == PH_MATVEC) { if (warp < P.mv.warps) mv_begin<false>(P.mv, smem_raw, cta, n_cta, P.mv.prefill, ms); }
         else if (P.kind == PH_SCORES) scores_begin(P.at, cta, ss);
         else pv_begin<GQA>(P.at, cta, smem_raw);
     };
@@ -385,17 +403,21 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_token(const Phase * __restric
             cp_async_commit();
         }
         stamp(p, 0);
-        if (P.kind == PH_MATVEC) { if (warp < P.mv.warps) mv_run<false>(P.mv, red_smem, P.mv.stages - 1, ms); }
+#if B200_HANG_DEBUG
+        if (tid == 0) g_dbg_phase[cta & 255] = p;
+#endif
+        if (P.kind == PH_MATVEC) { if (warp < P.mv.warps) mv_run<false>(P.mv, red_smem, P.mv.prefill, ms); }
         else if (P.kind == PH_SCORES) scores_run<GQA>(P.at, cta, n_cta, qs, ss);
         else pv_run<GQA>(P.at, cta, n_cta, smem_raw, redf, redd, red);
         cp_async_wait<0>();
         __syncthreads();                                       // the phase's shared memory is free, its global writes are issued
+        if (P.kind == PH_MATVEC && warp < P.mv.warps) mv_end(P.mv, ms);
         stamp(p, 1);
         if (p + 1 < n_phases) {
             if (tid == 0) grid_arrive(bar);
             begin(ph[(p + 1) & 1]);                            // HBM streams while the grid gathers
             stamp(p, 2);
-            if (tid == 0) grid_wait(bar, bar_base + (unsigned long long) (p + 1) * (unsigned long long) n_cta);
+            if (tid == 0) grid_wait(bar, bar_base + (unsigned long long) (p + 1) * (unsigned long long) n_cta, p);
             __syncthreads();
             stamp(p, 3);
         }

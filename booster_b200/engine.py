@@ -146,6 +146,20 @@ class Context:
             raise B200Error(f"b200_trace_token: {last_error()}")
         return out[:n], meta[:n]
 
+    def trace_phases(self, token: int, pos: int, reps: int = 3):
+        """(stamps[n_phases, n_ctas, 4] u64 ns, kinds[n_phases]) of one token through the persistent kernel; None if not in use"""
+        cap_p, cap_c = 1024, 256
+        out = np.zeros(cap_p * cap_c * 4, dtype=np.uint64)
+        kinds = np.zeros(cap_p, dtype=np.int32)
+        nc = C.c_int32(0)
+        n = int(self.L.b200_trace_phases(self.h, token, pos, reps, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size,
+                                         kinds.ctypes.data_as(C.POINTER(C.c_int32)), kinds.size, C.byref(nc)))
+        if n < 0:
+            raise B200Error(f"b200_trace_phases: {last_error()}")
+        if n == 0:
+            return None
+        return out[:n * nc.value * 4].reshape(n, nc.value, 4), kinds[:n]
+
     def kernel_launches(self) -> int:
         return int(self.L.b200_kernel_launches(self.h))
 

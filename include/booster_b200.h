@@ -114,6 +114,14 @@ int     b200_profile_kind(b200_ctx * c, int kind, int pos, int reps, float * ms_
 int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int reps, uint64_t * out, int64_t cap_words,
                          int32_t * meta, int64_t cap_meta);
 
+/* one token through the persistent per-token kernel with %globaltimer stamps (ns) at its phase boundaries:
+ * out = [n_phases][n_ctas][4]: 0 the phase's dependent half starts | 1 it is done | 2 arrived at the grid barrier, next
+ * phase's independent half issued | 3 barrier passed. kinds[i] = 1 attention scores, 2 soft-max + P.V, 10 + EPI for a mat-vec
+ * (10 head/store, 11 +residual (wo, down), 12 QKV, 13 gate|up). Returns n_phases; 0 if the context runs one kernel per
+ * operator; -1 on error. */
+int64_t b200_trace_phases(b200_ctx * c, int32_t token, int pos, int reps, uint64_t * out, int64_t cap_words, int32_t * kinds,
+                          int64_t cap_kinds, int32_t * n_ctas);
+
 /* µs-resolution per-token timings of a finished bridge job (additive companion of promptEval()/timing(),
  * whose integer-millisecond values read 0 on a B200) */
 int b200_job_timing_us(const char * jobID, double * prompt_us_per_token, double * gen_us_per_token);

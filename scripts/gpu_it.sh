@@ -6,7 +6,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 export B200_TMP=/tmp/b200_models
 if [ -n "$KEXPR" ]; then
-  ( time timeout ${TEST_TIMEOUT:-900} python -m pytest tests -m gpu -x -q -k "$KEXPR" ) > $OUT/pytest.log 2>&1
+  ( time timeout ${TEST_TIMEOUT:-900} python -m pytest tests -m gpu -x -q --timeout ${PER_TEST_TIMEOUT:-180} --timeout-method=thread -k "$KEXPR" ) > $OUT/pytest.log 2>&1
   tail -12 $OUT/pytest.log
 fi
 i=0
