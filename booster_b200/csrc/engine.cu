@@ -889,11 +889,33 @@ static MatvecArgs args_head(b200_ctx * c) {
 // ------------------------------------------------------------------------------------------------------------
 // persistent per-token kernel (token_kernel.cuh): phase list of this stage, built once per context
 // ------------------------------------------------------------------------------------------------------------
-static constexpr size_t TK_SMEM_BUDGET = 208 * 1024;          // dynamic; the kernel's static shared memory is ~14 KB
+// shared memory the kernel's own __shared__ variables take (phase descriptors, attention scratch): the dynamic budget is
+// what is left of the 227 KB a CTA may have
+template <int GQA>
+static size_t token_kernel_static_smem() {
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, k_token<GQA, true>));
+    return fa.sharedSizeBytes;
+}
+static size_t token_kernel_budget(int gqa) {
+    size_t st = 0;
+    switch (gqa) {
+        case 1: st = token_kernel_static_smem<1>(); break;
+        case 2: st = token_kernel_static_smem<2>(); break;
+        case 4: st = token_kernel_static_smem<4>(); break;
+        default: st = token_kernel_static_smem<8>(); break;
+    }
+    return 227 * 1024 - (st + 127) / 128 * 128 - 256;
+}
 template <int GQA>
 static void token_kernel_prepare(b200_ctx * c, size_t smem) {
-    for (auto kern : { k_token<GQA, false>, k_token<GQA, true> })
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    static size_t attr[64] = {0};      // per device; the attribute only ever grows (other contexts keep launching with theirs)
+    const int dv = c->device & 63;
+    if (smem > attr[dv]) {
+        for (auto kern : { k_token<GQA, false>, k_token<GQA, true> })
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr[dv] = smem;
+    }
     int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_token<GQA, false>, TK_THREADS, smem));
     if (nb < 1) throw std::runtime_error("the per-token kernel does not fit one SM");
@@ -911,6 +933,7 @@ static bool token_kernel_build(b200_ctx * c) {
     const int HD = m.head_dim, KVD = m.n_head_kv * HD, gqa = m.n_head / m.n_head_kv;
     if (HD != 128 || (gqa != 1 && gqa != 2 && gqa != 4 && gqa != 8) || m.layers.empty()) return false;
     try {
+        const size_t TK_SMEM_BUDGET = token_kernel_budget(gqa);
         const int rs = (c->n_ctx / 16 + 3) / 4 * 4;
         const size_t ps_bytes = (size_t) gqa * 16 * rs * 4;
         if (ps_bytes + 64 * 16 > TK_SMEM_BUDGET) return false;            // the GQA score rows of the context must fit one CTA

@@ -57,8 +57,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void grid_arrive(unsigned long long * ctr) {      // one thread, after a CTA-wide barrier
-    __threadfence();
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long * p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread, after a CTA-wide barrier: the release is cumulative over the CTA's writes that the barrier ordered before it
+__device__ __forceinline__ void grid_arrive(unsigned long long * ctr) {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(ctr), "l"(1ull) : "memory");
 }
 // A grid that never gathers (a CTA that died, a launch that was not co-resident) must not hang the process: after
@@ -69,11 +74,12 @@ __device__ __noinline__ void grid_wait_timeout(const unsigned long long * ctr, u
     __trap();
 }
 __device__ __forceinline__ void grid_wait(const unsigned long long * ctr, unsigned long long target, int phase) {
-    if (ld_acquire_u64(ctr) < target) {
+    // relaxed polls (no fence per poll), ONE acquire fence once the grid has gathered
+    if (ld_relaxed_u64(ctr) < target) {
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         unsigned spins = 0;
-        while (ld_acquire_u64(ctr) < target) {
+        while (ld_relaxed_u64(ctr) < target) {
             if ((++spins & 1023u) == 0) {
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                 if (t1 - t0 > GRID_WAIT_NS) grid_wait_timeout(ctr, target, phase);

@@ -206,16 +206,16 @@ def test_in_process_stage_split_prompt_back_to_back(golden_dir):
     out = np.empty(m0.n_vocab, dtype=np.float32)
     for rep in range(3):
         for i, t in enumerate(prompt):
-            assert L.b200_stage_forward(c0.h, t, i, 1, None) == 0
-            assert L.b200_stage_forward(c1.h, t, i, 1, c0.h) == 0
-        assert L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+            engine.check(L.b200_stage_forward(c0.h, t, i, 1, None), "stage 0")
+            engine.check(L.b200_stage_forward(c1.h, t, i, 1, c0.h), "stage 1")
+        engine.check(L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))), "logits")
         _same(out, g["logits"][0], f"prefill through 2 stages (rep {rep})")
     pos = len(prompt)
     for i, t in enumerate(g["ids"].tolist()[:4]):
         assert int(np.argmax(out)) == t
-        assert L.b200_stage_forward(c0.h, t, pos, 0, None) == 0
-        assert L.b200_stage_forward(c1.h, t, pos, 0, c0.h) == 0
-        assert L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+        engine.check(L.b200_stage_forward(c0.h, t, pos, 0, None), "stage 0")
+        engine.check(L.b200_stage_forward(c1.h, t, pos, 0, c0.h), "stage 1")
+        engine.check(L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))), "logits")
         _same(out, g["logits"][i + 1], f"step {i} through 2 stages")
         pos += 1
     for x in (c0, c1):
@@ -233,10 +233,10 @@ def test_in_process_stage_split_equals_single_stage(golden_dir):
     c0 = engine.Context(m0, 64); c1 = engine.Context(m1, 64)
     L = m.L
     import ctypes as C
-    assert L.b200_stage_forward(c0.h, 5, 0, 0, None) == 0
-    assert L.b200_stage_forward(c1.h, 5, 0, 0, c0.h) == 0
+    engine.check(L.b200_stage_forward(c0.h, 5, 0, 0, None), "stage 0")
+    engine.check(L.b200_stage_forward(c1.h, 5, 0, 0, c0.h), "stage 1")
     out = np.empty(m.n_vocab, dtype=np.float32)
-    assert L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    engine.check(L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))), "logits")
     assert np.array_equal(out, full)
     for x in (c, c0, c1):
         x.close()
