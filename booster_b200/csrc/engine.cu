@@ -920,10 +920,15 @@ static void token_kernel_prepare(b200_ctx * c, size_t smem) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_token<GQA, false>, TK_THREADS, smem));
     if (nb < 1) throw std::runtime_error("the per-token kernel does not fit one SM");
 }
+// Which path decodes a token: 0 = one kernel per operator joined by programmatic dependent launch (default: measured
+// faster, 546 vs 371 tok/s on the 8B Q4_K_M config — the grid barrier costs 3 us against ~2 us for a PDL kernel boundary
+// and does not overlap the way the next kernel's early CTAs do), 1 = the persistent per-token kernel.
+// BOOSTER_B200_TOKEN_KERNEL=1 or b200_set_token_kernel(1) selects it for contexts created afterwards.
+static int g_token_kernel = -1;
+extern "C" void b200_set_token_kernel(int on) { g_token_kernel = on ? 1 : 0; }
 static bool token_kernel_enabled() {
-    static int v = -1;
-    if (v < 0) { const char * e = getenv("BOOSTER_B200_TOKEN_KERNEL"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
+    if (g_token_kernel < 0) { const char * e = getenv("BOOSTER_B200_TOKEN_KERNEL"); g_token_kernel = (e && e[0] == '1') ? 1 : 0; }
+    return g_token_kernel == 1;
 }
 // returns false (and remembers it) when this model / context cannot use the persistent kernel; the per-kernel path runs then
 static bool token_kernel_build(b200_ctx * c) {
@@ -1016,7 +1021,7 @@ static void enqueue_forward(b200_ctx * c) {
     }
     // the persistent kernel runs everything after the embedding row; taps, per-launch profiling and the per-kernel phase
     // trace need the one-kernel-per-operator path
-    if (token_kernel_enabled() && !c->taps && !c->prof && !c->tracing && g_only_kind < 0 && token_kernel_build(c)) {
+    if (c->token_state > 0 && !c->taps && !c->prof && !c->tracing && g_only_kind < 0) {
         switch (m.n_head / m.n_head_kv) {
             case 1: token_kernel_launch<1>(c); break;
             case 2: token_kernel_launch<2>(c); break;
@@ -1505,7 +1510,7 @@ extern "C" int64_t b200_trace_phases(b200_ctx * c, int32_t token, int pos, int r
         b200_model & m = *c->m;
         if (pos < 0 || pos >= c->n_ctx || token < 0 || token >= m.n_vocab) throw std::runtime_error("bad token/pos");
         CU(cudaSetDevice(m.device));
-        if (!token_kernel_enabled() || !token_kernel_build(c)) return 0;
+        if (c->token_state <= 0) return 0;
         const size_t words = (size_t) c->n_phases * c->sm_count * TK_TRACE_SLOTS;
         if (!c->d_ttrace) CU(cudaMalloc(&c->d_ttrace, words * 8));
         DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = 0; hs.step = 0;

@@ -251,6 +251,11 @@ def op_attention(q, k_cache_f16, v_cache_f16, n_kv: int, n_head: int, n_head_kv:
     return out
 
 
+def set_token_kernel(on: bool) -> None:
+    """contexts created afterwards decode with the persistent per-token kernel (True) or one kernel per operator (False)"""
+    _lib.lib().b200_set_token_kernel(int(on))
+
+
 def set_attention_route(route: int) -> None:
     """0: automatic (cluster kernel when it fits), 1: always the long-context three-kernel route"""
     _lib.lib().b200_set_attention_route(route)

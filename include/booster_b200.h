@@ -114,6 +114,10 @@ int     b200_profile_kind(b200_ctx * c, int kind, int pos, int reps, float * ms_
 int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int reps, uint64_t * out, int64_t cap_words,
                          int32_t * meta, int64_t cap_meta);
 
+/* Decode path of contexts created AFTER the call: 0 (default) = one kernel per operator joined by programmatic dependent
+ * launch, 1 = ONE persistent kernel per token (token_kernel.cuh: phase list + grid barriers; same arithmetic, bit-identical
+ * results; measured slower on B200, kept selectable: DESIGN.md §4). Env BOOSTER_B200_TOKEN_KERNEL=1 sets the initial value. */
+void b200_set_token_kernel(int on);
 /* one token through the persistent per-token kernel with %globaltimer stamps (ns) at its phase boundaries:
  * out = [n_phases][n_ctas][4]: 0 the phase's dependent half starts | 1 it is done | 2 arrived at the grid barrier, next
  * phase's independent half issued | 3 barrier passed. kinds[i] = 1 attention scores, 2 soft-max + P.V, 10 + EPI for a mat-vec
