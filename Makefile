@@ -6,15 +6,15 @@ CSRC      := booster_b200/csrc
 OBJDIR    := build
 LIB       := booster_b200/libbooster_b200.so
 
-OBJS := $(OBJDIR)/engine.o $(OBJDIR)/gguf.o $(OBJDIR)/bridge.o $(OBJDIR)/tokenizer.o
+OBJS := $(OBJDIR)/engine.o $(OBJDIR)/gguf.o $(OBJDIR)/bridge.o $(OBJDIR)/tokenizer.o $(OBJDIR)/janus.o
 
 all: $(LIB)
 
-$(OBJDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.cuh $(CSRC)/gguf.hpp $(CSRC)/tokenizer.hpp include/booster_b200.h
+$(OBJDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.cuh $(CSRC)/token_kernel.cuh $(CSRC)/gguf.hpp $(CSRC)/tokenizer.hpp include/booster_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/engine.ptxas.log || (cat $(OBJDIR)/engine.ptxas.log; false)
 
-$(OBJDIR)/%.o: $(CSRC)/%.cpp $(CSRC)/gguf.hpp $(CSRC)/tokenizer.hpp $(CSRC)/unicode_tables.hpp include/bridge.h include/booster_b200.h
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(CSRC)/gguf.hpp $(CSRC)/tokenizer.hpp $(CSRC)/janus.hpp $(CSRC)/unicode_tables.hpp include/bridge.h include/booster_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(ARCH) -O2 -std=c++17 -Xcompiler -fPIC,-Wall -c $< -o $@
 

@@ -5,7 +5,9 @@
 // (cpp/bridge.cpp:175-658: tokenize -> reject if > n_ctx-4 -> clear KV -> prompt in n_batch chunks ->
 // sample/decode one token at a time until EOG / n_predict / n_ctx-4 / stop flag -> per-token timings), but every
 // llama_decode is the CUDA engine. Differences, all documented in DESIGN.md / INTEGRATION.md:
-//   * sampler: greedy arg-max on the device (the Janus sampler is SURVEY.md §8 row f-2, "next");
+//   * sampler: the reference's Janus sampler restated on the host (janus.hpp; logits come back once per token), or — with
+//     janus = 0, a setting the reference ignores — the standard chain; temperature <= 0 / top_k = 1 there is greedy
+//     arg-max on the device;
 //   * tokenizer: models with tokenizer.ggml.model == "no_vocab" take prompts that are white-space separated
 //     token ids and render pieces as "<id> "; text tokenizers (BPE/SPM) are row f-1, see tokenizer.hpp;
 //   * context shift / Self-Extend (cpp/bridge.cpp:487-524) are row f-3: generation stops at n_ctx-4 instead;
@@ -14,6 +16,7 @@
 #include "../../include/bridge.h"
 #include "../../include/booster_b200.h"
 #include "tokenizer.hpp"
+#include "janus.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -39,6 +42,11 @@ struct Pod {
     std::vector<b200_ctx *>   stages;
     std::unique_ptr<b200::Tokenizer> tok;
     int n_vocab = 0;
+    // samplers (cpp/bridge.cpp:746-761 stores the same parameters per pod)
+    b200::JanusParams jparams;
+    b200::StandardParams sparams;
+    b200::JanusSampler janus;           // scales / types tables: initJanus, once per pod (the reference redoes it per job)
+    std::vector<float> logits;          // host copy of the last token's logits
     // contexts first, then the models they point into
     void release() {
         for (b200_ctx * c : stages) b200_ctx_free(c);
@@ -112,9 +120,11 @@ void * initContext(
     float repetition_penalty, int penalty_last_n,
     int32_t janus, int32_t depth, float scale, float hi, float lo,
     uint32_t seed, char * debug) {
-    (void) threads; (void) mirostat; (void) mirostat_tau; (void) mirostat_eta; (void) temperature; (void) top_k;
-    (void) top_p; (void) typical_p; (void) repetition_penalty; (void) penalty_last_n; (void) janus; (void) depth;
-    (void) scale; (void) hi; (void) lo; (void) debug;
+    (void) threads; (void) debug;
+    // mirostat and typical-p belong to the standard chain the reference keeps commented out; not implemented here either
+    if (mirostat != 0 || (typical_p > 0.f && typical_p < 1.f))
+        std::fprintf(stderr, "initContext: mirostat / typical_p are ignored (the reference's bridge never applies them: cpp/bridge.cpp:586-596)\n");
+    (void) mirostat_tau; (void) mirostat_eta;
     if (idx < 0 || idx >= MAX_PODS || !modelName) return nullptr;
     Pod & p = g_pods[idx];
     p.release();                          // re-initialising a pod frees its previous weights and KV cache
@@ -170,6 +180,12 @@ void * initContext(
     std::string terr;
     p.tok = b200::make_tokenizer(modelName, terr);
     if (!p.tok) { std::fprintf(stderr, "initContext: %s\n", terr.c_str()); p.release(); return nullptr; }
+    // sampler parameters (cpp/bridge.cpp:746-761)
+    p.jparams.janus = janus; p.jparams.depth = depth; p.jparams.scale = scale; p.jparams.hi = hi; p.jparams.lo = lo;
+    p.sparams.temp = temperature; p.sparams.top_k = top_k; p.sparams.top_p = top_p;
+    p.sparams.penalty_repeat = repetition_penalty; p.sparams.penalty_last_n = penalty_last_n;
+    if (janus != 0) p.janus.init(*p.tok, p.jparams, 0);
+    p.logits.resize((size_t) p.n_vocab);
     return (void *) &p;
 }
 
@@ -222,31 +238,58 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
         consumed += n;
     }
 
-    // ---- generation: sample (greedy, on device) then decode the sampled token (cpp/bridge.cpp:586-646).
-    // A pod on one GPU replays one CUDA graph per token (b200_step_greedy: decode + arg-max + 4-byte read-back); a
-    // layer-split pod chains its stages with plain launches and peer copies.
+    // ---- generation: sample, then decode the sampled token (cpp/bridge.cpp:586-646).
+    //   janus != 0 (what the reference always does): the logits come to the host once per token and the Janus sampler picks;
+    //   janus == 0: the standard chain; when that is greedy, the arg-max stays on the device and a pod on one GPU replays
+    //   one CUDA graph per token (decode + arg-max + 4-byte read-back).
+    // A layer-split pod chains its stages with plain launches and peer copies.
     static const bool graph_ok = [] { const char * e = std::getenv("BOOSTER_B200_BRIDGE_GRAPH"); return !(e && e[0] == '0'); }();   // A/B switch
+    static const bool force_greedy = [] { const char * e = std::getenv("BOOSTER_B200_SAMPLER"); return e && std::strcmp(e, "greedy") == 0; }();
     const bool single = p.stages.size() == 1 && graph_ok;
+    const bool use_janus = p.jparams.janus != 0 && !force_greedy;
+    b200::StandardSampler std_sampler;
+    std_sampler.init(p.sparams, seed);
+    const bool device_argmax = !use_janus && (force_greedy || std_sampler.greedy());
+    if (use_janus) p.janus.rng.seed(seed);                 // llama_set_rng_seed(ctx, seed): cpp/bridge.cpp:216-217
+    std::vector<int32_t> last_tokens((size_t) p.n_ctx, 0); // cpp/bridge.cpp:437-438: only generated tokens enter
+    std::vector<int32_t> history(inp);                     // prompt + generated: the standard chain's penalty window
     int32_t id = 0;
-    bool have_id = false;
+    bool have_next = false;                                // device arg-max path: the next id came back with the decode
+    bool have_logits = false;                              // host path: p.logits holds the logits of the last decoded token
     while (n_remain != 0 && n_past < max_embd && !g_stop[idx].load()) {
         const double t0 = now_us();
-        if (!have_id) { if (b200_stage_argmax(last, &id) != 0) return 1; }
-        have_id = false;
+        if (device_argmax) {
+            if (!have_next) { if (b200_stage_argmax(last, &id) != 0) return 1; }
+            have_next = false;
+        } else {
+            if (!have_logits) { if (b200_stage_logits(last, p.logits.data()) != 0) return 1; }
+            have_logits = false;
+            if (use_janus) {
+                id = p.janus.sample(p.logits.data(), last_tokens, inp.size(), (size_t) n_past, (size_t) p.n_predict);
+                last_tokens.erase(last_tokens.begin());    // cpp/bridge.cpp:602-603
+                last_tokens.push_back(id);
+            } else {
+                id = std_sampler.sample(p.logits.data(), p.n_vocab, history);
+            }
+        }
+        history.push_back(id);
         --n_remain;
         { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += p.tok->piece(id, true); }
         if (p.tok->is_eog(id)) break;                      // cpp/bridge.cpp:640
         if (n_remain == 0 || n_past >= max_embd) break;
-        if (single) {
+        if (single && device_argmax) {
             int32_t next = 0;
             if (b200_step_greedy(last, id, n_past, &next) != 0) return 1;
-            id = next; have_id = true;
+            id = next; have_next = true;
+        } else if (single) {
+            if (b200_decode(last, &id, 1, n_past, p.logits.data()) != 0) return 1;   // one graph: state in, forward, logits out
+            have_logits = true;
         } else {
             if (run_token(p, id, n_past, 0) != 0) return 1;
         }
         n_past += 1;
         // single stage: the step is synchronous; layer split: launches are asynchronous and the interval that ends at
-        // the NEXT arg-max's sync is what one token costs
+        // the NEXT read-back's sync is what one token costs
         t_e_us += now_us() - t0; n_eval += 1;
     }
     // per-token timings, integer milliseconds like the reference (cpp/bridge.cpp:650-655)

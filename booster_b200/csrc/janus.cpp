@@ -1,0 +1,319 @@
+// janus.cpp — see janus.hpp. Host-only, no CUDA.
+#include "janus.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+namespace b200 {
+
+namespace {
+
+// token types (cpp/janus.h:27-37)
+constexpr int LANG_ZERO = 0, LANG_EN = 2, SPACE_EN = 20, LANG_RU = 3, SPACE_RU = 30, LANG_OTHER = 4, SPACE_OTHER = 40;
+constexpr int EOS = 2, NL = 13;    // cpp/janus.h:23-24: fixed ids, whatever the model
+
+// tokType (cpp/janus.cpp:724-829): byte-level classification of the piece
+int tok_type(const std::string & in) {
+    int en = 0, ru = 0, other = 0;
+    const size_t n = in.size();
+    const bool space = n > 0 && (unsigned char) in[0] == 0x20;
+    for (size_t i = 0; i < n; i++) {
+        const unsigned char b = (unsigned char) in[i];
+        if ((b >= 0x41 && b <= 0x5A) || (b >= 0x61 && b <= 0x7A)) { en++; continue; }
+        if (b < 0x80) continue;
+        if (b == 0xD0 && i + 1 < n) {
+            i++;
+            const unsigned char c = (unsigned char) in[i];
+            if ((c >= 0x90 && c <= 0xBF) || c == 0x81) ru++; else other++;
+            continue;
+        }
+        if (b == 0xD1 && i + 1 < n) {
+            i++;
+            const unsigned char c = (unsigned char) in[i];
+            if ((c >= 0x80 && c <= 0x8F) || c == 0x91) ru++; else other++;
+            continue;
+        }
+        if (b >= 0xC3 && b < 0xE3) { i++; other++; continue; }
+        if (b >= 0xE3 && b < 0xF0) { i += 2; other++; continue; }
+        if (b >= 0xF0) { i += 3; continue; }
+    }
+    if (space) {
+        if (other) return SPACE_OTHER;
+        if (en) return SPACE_EN;
+        if (ru) return SPACE_RU;
+    }
+    if (other) return LANG_OTHER;
+    if (en) return LANG_EN;
+    if (ru) return LANG_RU;
+    return LANG_ZERO;
+}
+
+// isLower (cpp/janus.cpp:832-865)
+bool is_lower(const std::string & in) {
+    if (in.empty()) return false;
+    const unsigned char b0 = (unsigned char) in[0];
+    if (b0 >= 0x61 && b0 <= 0x7A) return true;
+    if (in.size() >= 2) {
+        const unsigned char b1 = (unsigned char) in[1];
+        if (b0 == 0xD0 && b1 >= 0xB0 && b1 <= 0xBF) return true;
+        if (b0 == 0xD1 && ((b1 >= 0x80 && b1 <= 0x8F) || b1 == 0x91)) return true;
+    }
+    return false;
+}
+
+// isPedantic (cpp/janus.cpp:378-401)
+bool is_pedantic(const std::string & token) {
+    char * end = nullptr;
+    strtol(token.c_str(), &end, 10);
+    if (*end == 0) return true;            // numbers (and the empty piece)
+    if (token == " *" || token == " =" || token == " -" || token == " +") return true;
+    if (token == "{" || token == "}" || token == "[" || token == "]") return true;
+    if (token == " {" || token == " }" || token == " [" || token == " ]") return true;
+    if (token == "<|end_of_text|>" || token == "```") return true;
+    return false;
+}
+
+}  // namespace
+
+void JanusSampler::init(const Tokenizer & tok, const JanusParams & params, uint32_t seed) {
+    p = params;
+    rng.seed(seed);
+    n_vocab = tok.n_vocab();
+    scales.assign((size_t) n_vocab, 0.f);
+    types.assign((size_t) n_vocab, 0.f);
+    pedantic.assign((size_t) n_vocab, 0);
+    // safe defaults (cpp/janus.cpp:437-441) — they change the caller's parameters, as the reference does
+    if (p.depth <= 0) p.depth = 200;
+    if (p.scale <= 0.0 || p.scale > 1.0) p.scale = 0.97f;
+    if (p.hi <= 0.0 || p.hi > 1.0) p.hi = 0.99f;
+    if (p.lo <= 0.0 || p.lo > 1.0) p.lo = 0.96f;
+    const float scale = p.scale;
+    static const float probes[20] = { 0.20f, 0.22f, 0.25f, 0.28f, 0.30f, 0.32f, 0.33f, 0.35f, 0.36f, 0.38f,
+                                      0.40f, 0.42f, 0.44f, 0.45f, 0.46f, 0.48f, 0.50f, 0.52f, 0.53f, 0.55f };
+    static bool warned = false;
+    auto probe = [&](size_t i) {
+        if (i >= 20) {
+            if (!warned) { warned = true; std::fprintf(stderr, "booster_b200: Janus: token longer than the reference's 20-entry length table; clamped (the reference reads out of bounds there)\n"); }
+            i = 19;
+        }
+        return probes[i];
+    };
+    std::vector<std::string> piece((size_t) n_vocab);
+    for (int32_t id = 0; id < n_vocab; id++) piece[(size_t) id] = tok.piece(id, true);   // llama_token_to_piece(ctx, id): special = true
+    for (int32_t id = 0; id < n_vocab; id++) {
+        const std::string & s = piece[(size_t) id];
+        const int type = tok_type(s);
+        const bool lower = is_lower(s);
+        const size_t len = s.size();
+        types[(size_t) id] = (float) type;
+        pedantic[(size_t) id] = is_pedantic(s) ? 1 : 0;
+        // every expression below is evaluated in double and stored as float, as in the reference (1.0 is a double literal)
+        if (pedantic[(size_t) id]) { scales[(size_t) id] = (float) (1.0 - (1.0 - scale) * 0.20); continue; }
+        if (type == LANG_RU && lower) { scales[(size_t) id] = (float) (1.0 - (1.0 - scale) * probe(len / 2)); continue; }
+        if (type == LANG_EN && lower) { scales[(size_t) id] = (float) (1.0 - (1.0 - scale) * probe(len)); continue; }
+        scales[(size_t) id] = scale;
+    }
+    auto set = [&](int64_t id, double v) { if (id >= 0 && id < n_vocab) scales[(size_t) id] = (float) v; };
+    set(0, 1.0);
+    set(tok.eos(), scale);
+    set(tok.eot(), scale);
+    // "LLaMA v2/v3 and Mistral": llama_model_desc starts with the architecture name, "llama" for every model on this path
+    if (n_vocab > 128000) {                 // LLaMA-3 (cpp/janus.cpp:536-624): by piece text and id range
+        for (int32_t id = 0; id < n_vocab; id++) {
+            const std::string & t = piece[(size_t) id];
+            const int type = (int) types[(size_t) id];
+            if (t == "\n" || t == "\n\n") { set(id, 1.0 - (1.0 - scale) * 0.10); continue; }
+            if (t == "  " || t == "    ") { set(id, 1.0 - (1.0 - scale) * 0.20); continue; }
+            if (t == " " || t == "," || t == ".") { set(id, 1.0 - (1.0 - scale) * 0.10); continue; }
+            if (t == " \xE2\x80\x94" || t == "-" || t == ":" || t == ";") { set(id, 1.0 - (1.0 - scale) * 0.30); continue; }
+            if (t == " (" || t == ")." || t == " )" || t == ")" || t == "(") { set(id, 1.0 - (1.0 - scale) * 0.30); continue; }
+            if (id < 20000 && type == SPACE_RU) { set(id, 1.0 - (1.0 - scale) * 0.30); continue; }
+            if (id >= 20000 && id < 35000 && type == SPACE_RU) { set(id, 1.0 - (1.0 - scale) * 0.40); continue; }
+            if (id >= 35000 && id < 50000 && type == SPACE_RU) { set(id, 1.0 - (1.0 - scale) * 0.50); continue; }
+            if (id < 500 && type == SPACE_EN) { set(id, 1.0 - (1.0 - scale) * 0.30); continue; }
+            if (id >= 500 && id < 800 && type == SPACE_EN) { set(id, 1.0 - (1.0 - scale) * 0.40); continue; }
+            if (id >= 800 && id < 1100 && type == SPACE_EN) { set(id, 1.0 - (1.0 - scale) * 0.50); continue; }
+        }
+    } else {                                // LLaMA-2 (cpp/janus.cpp:626-693): fixed token ids
+        set(0, 1.0);
+        set(EOS, scale);
+        set(NL, 1.0 - (1.0 - scale) * 0.10);
+        static const struct { int id; double f; } fixed[] = {
+            {259, 0.20}, {268, 0.20}, {29871, 0.10}, {29892, 0.10}, {29889, 0.20}, {813, 0.30}, {29899, 0.30}, {29901, 0.30}, {29936, 0.30},
+            {313, 0.30}, {467, 0.30}, {1723, 0.30}, {29897, 0.30}, {29898, 0.30},
+            {490, 0.30}, {531, 0.30}, {606, 0.30}, {614, 0.30}, {665, 0.35}, {733, 0.35}, {863, 0.35}, {1077, 0.40}, {1097, 0.40}, {1186, 0.40},
+            {1447, 0.45}, {1538, 0.45}, {1604, 0.45}, {1685, 0.45}, {4281, 0.50}, {857, 0.50}, {939, 0.50}, {1651, 0.50},
+            {263, 0.30}, {278, 0.30}, {297, 0.30}, {304, 0.30}, {310, 0.30}, {322, 0.30}, {363, 0.35}, {372, 0.35}, {373, 0.35}, {385, 0.35},
+            {393, 0.35}, {408, 0.35}, {411, 0.35}, {470, 0.40}, {472, 0.40}, {526, 0.40}, {319, 0.50},
+        };
+        for (const auto & f : fixed) set(f.id, 1.0 - (1.0 - scale) * f.f);
+    }
+}
+
+int32_t JanusSampler::sample(float * logits, const std::vector<int32_t> & last_tokens, size_t prompt_len, size_t pos, size_t max) {
+    const size_t ctx_size = last_tokens.size();
+    const int32_t last_token = last_tokens[ctx_size - 1];
+    const float last_type = types[(size_t) last_token];
+    // boost <EOS> when we are closer to the limit (cpp/janus.cpp:235): double arithmetic, stored back as float
+    if (EOS < n_vocab) logits[EOS] = (float) ((double) logits[EOS] * (1.0 + std::log(1.0 + (double) ((float) (pos - prompt_len) / (float) max)) * 0.05));
+    // pessimization of repeated tokens among the generated ones (cpp/janus.cpp:240-267)
+    const size_t depth = std::min((size_t) p.depth, pos - prompt_len);
+    for (size_t i = 0; i < depth; i++) {
+        const int32_t id = last_tokens[ctx_size - 1 - i];
+        const float cur_type = types[(size_t) id];
+        if ((last_type == SPACE_RU || last_type == LANG_RU) && cur_type == LANG_RU) {
+            logits[id] = (float) ((double) logits[id] * (1.0 - (1.0 - (double) scales[(size_t) id]) * 0.20));
+            continue;
+        }
+        logits[id] *= scales[(size_t) id];
+    }
+    // double down incompatible tokens (cpp/janus.cpp:271-285)
+    if (last_type == SPACE_RU || last_type == LANG_RU) {
+        for (int32_t id = 0; id < n_vocab; id++) {
+            const float t = types[(size_t) id];
+            if (t == LANG_EN || t == LANG_OTHER) logits[id] = (float) ((double) logits[id] * 0.5);
+        }
+    }
+    // The reference sorts all candidates by logit (descending) and cuts the list at the first one whose ratio to the top
+    // logit is below the cutoff (cpp/janus.cpp:289-324). For a positive top logit the ratio falls along the sorted order,
+    // so the short list is exactly the candidates whose ratio is not below the cutoff — found in one pass, no full sort.
+    int32_t top = 0;
+    for (int32_t id = 1; id < n_vocab; id++) if (logits[id] > logits[top]) top = id;
+    const float top_logit = logits[top];
+    float cutoff = p.lo;
+    const float top_type = types[(size_t) top];
+    if (pedantic[(size_t) top] || top_type == LANG_RU || top_type == LANG_EN) cutoff = p.hi;
+    struct Cand { int32_t id; float logit; float p; };
+    std::vector<Cand> cand;
+    const auto by_logit = [](const Cand & a, const Cand & b) { return a.logit > b.logit; };
+    if (top_logit > 0.f) {
+        for (int32_t id = 0; id < n_vocab; id++) if (!(logits[id] / top_logit < cutoff)) cand.push_back({id, logits[id], 0.f});
+        std::sort(cand.begin(), cand.end(), by_logit);
+    } else {
+        // top logit <= 0 (or NaN somewhere): the ratio does not fall along the order; walk the fully sorted list as the
+        // reference does (the whole vocabulary survives when every logit is negative)
+        cand.reserve((size_t) n_vocab);
+        for (int32_t id = 0; id < n_vocab; id++) cand.push_back({id, logits[id], 0.f});
+        std::sort(cand.begin(), cand.end(), by_logit);
+        for (size_t i = 1; i < cand.size(); i++) if (cand[i].logit / cand[0].logit < cutoff) { cand.resize(i); break; }
+    }
+    // llama_sample_token: softmax over the short list, then one draw (cpp/src/llama-sampling.cpp:32-59, 610-631)
+    const float max_l = cand[0].logit;
+    float cum = 0.f;
+    for (auto & c : cand) { c.p = expf(c.logit - max_l); cum += c.p; }
+    std::vector<float> probs;
+    probs.reserve(cand.size());
+    for (auto & c : cand) { c.p /= cum; probs.push_back(c.p); }
+    std::discrete_distribution<> dist(probs.begin(), probs.end());
+    return cand[(size_t) dist(rng)].id;
+}
+
+// llama_sampling_sample's default chain (cpp/common/sampling.cpp llama_sampling_prepare + sampler_queue "kfypmt"):
+// repetition penalty over the last penalty_last_n tokens (llama_sample_repetition_penalties_impl), top-k, (tail-free z = 1
+// and typical p = 1 are no-ops), top-p, min-p, temperature, softmax draw
+int32_t StandardSampler::sample(const float * logits_in, int32_t n_vocab, const std::vector<int32_t> & prev) {
+    struct Cand { int32_t id; float logit; float p; };
+    std::vector<Cand> cand((size_t) n_vocab);
+    for (int32_t id = 0; id < n_vocab; id++) cand[(size_t) id] = {id, logits_in[id], 0.f};
+    if (p.penalty_repeat != 1.0f && p.penalty_last_n != 0 && !prev.empty()) {
+        const size_t n = p.penalty_last_n < 0 ? prev.size() : std::min(prev.size(), (size_t) p.penalty_last_n);
+        std::vector<uint8_t> seen((size_t) n_vocab, 0);
+        for (size_t i = prev.size() - n; i < prev.size(); i++) if (prev[i] >= 0 && prev[i] < n_vocab) seen[(size_t) prev[i]] = 1;
+        for (auto & c : cand) if (seen[(size_t) c.id]) c.logit = c.logit <= 0 ? c.logit * p.penalty_repeat : c.logit / p.penalty_repeat;
+    }
+    const auto by_logit = [](const Cand & a, const Cand & b) { return a.logit > b.logit; };
+    if (p.temp <= 0.f) return std::max_element(cand.begin(), cand.end(), [](const Cand & a, const Cand & b) { return a.logit < b.logit; })->id;
+    size_t k = p.top_k <= 0 ? cand.size() : std::min(cand.size(), (size_t) p.top_k);
+    std::partial_sort(cand.begin(), cand.begin() + (long) k, cand.end(), by_logit);
+    cand.resize(k);
+    auto softmax = [&]() {
+        const float mx = cand[0].logit;
+        float cum = 0.f;
+        for (auto & c : cand) { c.p = expf(c.logit - mx); cum += c.p; }
+        for (auto & c : cand) c.p /= cum;
+    };
+    if (p.top_p < 1.0f) {
+        softmax();
+        float cum = 0.f;
+        size_t last = cand.size();
+        for (size_t i = 0; i < cand.size(); i++) { cum += cand[i].p; if (cum >= p.top_p) { last = i + 1; break; } }
+        cand.resize(std::max<size_t>(1, last));
+    }
+    if (p.min_p > 0.0f) {
+        softmax();
+        const float thr = cand[0].p * p.min_p;
+        size_t keep = 1;
+        while (keep < cand.size() && cand[keep].p >= thr) keep++;
+        cand.resize(keep);
+    }
+    for (auto & c : cand) c.logit /= p.temp;
+    softmax();
+    std::vector<float> probs;
+    for (auto & c : cand) probs.push_back(c.p);
+    std::discrete_distribution<> dist(probs.begin(), probs.end());
+    return cand[(size_t) dist(rng)].id;
+}
+
+}  // namespace b200
+
+// ------------------------------------------------------------------------------------------------------------
+// C-ABI of the samplers alone (include/booster_b200.h): the parity tests feed them the REFERENCE's logits step by step
+// and compare the ids with the reference's own sample_janus_token — no GPU involved
+// ------------------------------------------------------------------------------------------------------------
+#include "../../include/booster_b200.h"
+
+struct b200_sampler {
+    std::unique_ptr<b200::Tokenizer> tok;
+    b200::JanusSampler janus;
+    b200::StandardSampler standard;
+    bool use_janus = true;
+    std::vector<int32_t> last_tokens, history;
+    size_t n_prompt = 0;
+};
+
+extern "C" b200_sampler * b200_sampler_new(const char * gguf_path, int n_ctx, int32_t janus, int32_t depth, float scale, float hi, float lo,
+                                           float temperature, int top_k, float top_p, float repetition_penalty, int penalty_last_n) {
+    try {
+        if (!gguf_path || n_ctx <= 0) return nullptr;
+        std::string err;
+        auto s = std::make_unique<b200_sampler>();
+        s->tok = b200::make_tokenizer(gguf_path, err);
+        if (!s->tok) return nullptr;
+        b200::JanusParams jp; jp.janus = janus; jp.depth = depth; jp.scale = scale; jp.hi = hi; jp.lo = lo;
+        b200::StandardParams sp; sp.temp = temperature; sp.top_k = top_k; sp.top_p = top_p; sp.penalty_repeat = repetition_penalty; sp.penalty_last_n = penalty_last_n;
+        s->use_janus = janus != 0;
+        if (s->use_janus) s->janus.init(*s->tok, jp, 0);
+        s->standard.init(sp, 0);
+        s->last_tokens.assign((size_t) n_ctx, 0);
+        return s.release();
+    } catch (const std::exception &) { return nullptr; }
+}
+extern "C" void b200_sampler_free(b200_sampler * s) { delete s; }
+// a new job: the prompt's ids (the standard chain's penalty window; Janus only needs their count) and the rng seed
+extern "C" void b200_sampler_reset(b200_sampler * s, const int32_t * prompt, int32_t n_prompt, uint32_t seed) {
+    if (!s) return;
+    std::fill(s->last_tokens.begin(), s->last_tokens.end(), 0);
+    s->history.assign(prompt, prompt + n_prompt);
+    s->n_prompt = (size_t) n_prompt;
+    s->janus.rng.seed(seed);
+    s->standard.rng.seed(seed);
+}
+// one token from logits[n_vocab] (modified in place by Janus, as the reference modifies the context's logits) at position
+// pos = tokens decoded so far; n_predict as passed to initContext
+extern "C" int32_t b200_sampler_sample(b200_sampler * s, float * logits, int32_t pos, int32_t n_predict) {
+    if (!s || !logits) return -1;
+    int32_t id;
+    if (s->use_janus) {
+        id = s->janus.sample(logits, s->last_tokens, s->n_prompt, (size_t) pos, (size_t) n_predict);
+        s->last_tokens.erase(s->last_tokens.begin());
+        s->last_tokens.push_back(id);
+    } else {
+        id = s->standard.sample(logits, s->tok->n_vocab(), s->history);
+    }
+    s->history.push_back(id);
+    return id;
+}

@@ -1,0 +1,70 @@
+// janus.hpp — host-side samplers behind doInference.
+//
+// The reference's bridge samples EVERY token with its "Janus" sampler (cpp/bridge.cpp:586-596; the standard sampling
+// chain is commented out there): per-token repetition scales derived from the token TEXT (cpp/janus.cpp initJanus
+// :405-700), an <EOS> boost, language heuristics, a cut of the sorted candidates at a ratio to the top logit and a
+// softmax draw from the short list (sample_janus_token :191-331). JanusSampler restates that arithmetic on the host —
+// the logits come back from the GPU once per token — so that with the same seed the drop-in library generates the
+// same token ids as the reference. Pinned against the reference's own janus.cpp (compiled unmodified into oracle/_ref):
+// tests/golden/janus_*.json, tests/test_sampler.py.
+//
+// Where the reference's arithmetic is undefined, this file is defined and says so:
+//   * initJanus indexes a 20-entry table with the token's byte length (cpp/janus.cpp:474-492): tokens of 20 bytes or more
+//     (40 for Cyrillic) read past the table. Here the index is clamped to the last entry; warned once per process.
+//   * scales[llama_token_eot(model)] is written even when the model has no EOT token (index -1), and the LLaMA-2 branch
+//     writes fixed token ids regardless of the vocabulary size (:616-693). Here both are bounds-checked.
+//   * candidates whose logits tie exactly may be ordered differently by the reference's std::sort of the whole vocabulary.
+//
+// StandardSampler is the chain the reference keeps commented out (llama_sampling_sample: repetition penalty, top-k,
+// top-p, min-p, temperature; cpp/common/sampling.cpp), selected with janus = 0: additive, the reference never runs it.
+#pragma once
+#include <cstdint>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "tokenizer.hpp"
+
+namespace b200 {
+
+struct JanusParams {       // cpp/janus.h:13-19
+    int32_t janus = 1;
+    int32_t depth = 200;
+    float   scale = 0.96f;
+    float   hi    = 0.99f;
+    float   lo    = 0.96f;
+};
+
+struct JanusSampler {
+    JanusParams p;
+    std::vector<float> scales, types;      // per token id (cpp/janus.cpp ::scales, ::types)
+    std::vector<uint8_t> pedantic;         // isPedantic(id), cached (the reference re-derives it from the piece per call)
+    std::mt19937 rng;                      // llama_context's sampling rng (cpp/src/llama.cpp:18610 llama_set_rng_seed)
+    int32_t n_vocab = 0;
+
+    // initJanus(ctx, params, debug) (cpp/bridge.cpp:196) + llama_set_rng_seed(ctx, seed) (cpp/bridge.cpp:216-217)
+    void init(const Tokenizer & tok, const JanusParams & params, uint32_t seed);
+    // sample_janus_token (cpp/janus.cpp:191-331). logits[n_vocab] is modified in place, as the reference modifies the
+    // context's logits. last_tokens: n_ctx entries, zeros, then the generated tokens (cpp/bridge.cpp:437-438, 602-603).
+    int32_t sample(float * logits, const std::vector<int32_t> & last_tokens, size_t prompt_len, size_t pos, size_t max);
+};
+
+struct StandardParams {    // llama_sampling_params (cpp/common/sampling.h) — the fields initContext carries
+    float   temp = 0.8f;
+    int32_t top_k = 40;
+    float   top_p = 0.95f;
+    float   min_p = 0.05f;            // not in initContext's signature: the reference's default
+    float   penalty_repeat = 1.0f;
+    int32_t penalty_last_n = 64;
+};
+
+struct StandardSampler {
+    StandardParams p;
+    std::mt19937 rng;
+    void init(const StandardParams & params, uint32_t seed) { p = params; rng.seed(seed); }
+    bool greedy() const { return p.temp <= 0.f || p.top_k == 1; }
+    // penalties -> top-k -> top-p -> min-p -> temperature -> draw; prev = every token so far (prompt + generated)
+    int32_t sample(const float * logits, int32_t n_vocab, const std::vector<int32_t> & prev);
+};
+
+}  // namespace b200

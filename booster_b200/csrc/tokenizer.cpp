@@ -40,6 +40,7 @@ struct IdTokenizer final : Tokenizer {
     bool is_eog(int32_t id) const override { return id >= 0 && (id == eos_id || id == eot_id); }
     int32_t n_vocab() const override { return nv; }
     int32_t eos() const override { return eos_id; }
+    int32_t eot() const override { return eot_id; }
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -157,6 +158,7 @@ struct TextTokenizer final : Tokenizer {
     int32_t n_vocab() const override { return (int32_t) text.size(); }
     int32_t bos() const override { return bos_id; }
     int32_t eos() const override { return eos_id; }
+    int32_t eot() const override { return eot_id; }
     bool is_eog(int32_t id) const override { return id != -1 && (id == eos_id || id == eot_id || id == eom_id); }   // llama-vocab.cpp:1433-1439
 
     bool is_special_kind(int32_t id) const { return kind[(size_t) id] == TT_UNKNOWN || kind[(size_t) id] == TT_CONTROL; }

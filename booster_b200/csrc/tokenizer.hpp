@@ -30,6 +30,7 @@ struct Tokenizer {
     virtual int32_t n_vocab() const = 0;
     virtual int32_t bos() const { return -1; }
     virtual int32_t eos() const { return -1; }
+    virtual int32_t eot() const { return -1; }   // llama_token_eot (cpp/src/llama-vocab.cpp:1489-1491)
 };
 
 // bit 0 \p{L}, bit 1 \p{N}, bit 2 \s of a codepoint (unicode_tables.hpp)

@@ -261,6 +261,30 @@ def set_attention_route(route: int) -> None:
     _lib.lib().b200_set_attention_route(route)
 
 
+class Sampler:
+    """doInference's sampler on its own (include/booster_b200.h b200_sampler_*): Janus (janus != 0) or the standard chain"""
+
+    def __init__(self, path: str, n_ctx: int, janus: int = 1, depth: int = 200, scale: float = 0.96, hi: float = 0.99, lo: float = 0.96,
+                 temperature: float = 0.8, top_k: int = 40, top_p: float = 0.95, repetition_penalty: float = 1.0, penalty_last_n: int = 64):
+        self.L = _lib.lib()
+        self.h = self.L.b200_sampler_new(path.encode(), n_ctx, janus, depth, scale, hi, lo, temperature, top_k, top_p, repetition_penalty, penalty_last_n)
+        if not self.h:
+            raise B200Error(f"b200_sampler_new({path}) failed")
+
+    def close(self):
+        if self.h:
+            self.L.b200_sampler_free(self.h)
+            self.h = None
+
+    def reset(self, prompt: Sequence[int], seed: int):
+        toks = np.ascontiguousarray(prompt, dtype=np.int32)
+        self.L.b200_sampler_reset(self.h, toks.ctypes.data_as(C.POINTER(C.c_int32)), len(toks), seed)
+
+    def sample(self, logits: np.ndarray, pos: int, n_predict: int = -1) -> int:
+        lg = np.ascontiguousarray(logits, dtype=np.float32).copy()
+        return int(self.L.b200_sampler_sample(self.h, lg.ctypes.data_as(C.POINTER(C.c_float)), pos, n_predict))
+
+
 class Tokenizer:
     """llama_tokenize / llama_token_to_piece / llama_token_is_eog of a GGUF's vocabulary (include/booster_b200.h)."""
 

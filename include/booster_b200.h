@@ -179,6 +179,20 @@ int32_t b200_tokenize(const b200_tokenizer * t, const char * text, int32_t text_
                       int add_special, int parse_special);
 int32_t b200_token_to_piece(const b200_tokenizer * t, int32_t token, char * buf, int32_t length, int special);
 int     b200_token_is_eog(const b200_tokenizer * t, int32_t token);
+/* ---- samplers (host side) ----------------------------------------------------------------------------
+ * What doInference does with the logits of every token, exposed on its own so that it can be pinned against the reference's
+ * sampler on the reference's logits (no GPU involved): janus != 0 -> sample_janus_token (cpp/janus.cpp:191-331) with the
+ * tables of initJanus (:405-700) built from the GGUF's vocabulary; janus == 0 -> llama_sampling_sample's default chain
+ * (repetition penalty, top-k, top-p, min-p 0.05, temperature; cpp/common/sampling.cpp), which the reference's bridge keeps
+ * commented out. b200_sampler_reset starts a job (prompt ids, rng seed = llama_set_rng_seed); b200_sampler_sample draws the next
+ * token from logits[n_vocab] (Janus modifies them in place) at position pos = number of tokens decoded so far. */
+typedef struct b200_sampler b200_sampler;
+b200_sampler * b200_sampler_new(const char * gguf_path, int n_ctx, int32_t janus, int32_t depth, float scale, float hi, float lo,
+                                float temperature, int top_k, float top_p, float repetition_penalty, int penalty_last_n);
+void    b200_sampler_free(b200_sampler * s);
+void    b200_sampler_reset(b200_sampler * s, const int32_t * prompt, int32_t n_prompt, uint32_t seed);
+int32_t b200_sampler_sample(b200_sampler * s, float * logits, int32_t pos, int32_t n_predict);
+
 /* codepoint classes of the LLaMA-3 pre-tokenizer regex: bit 0 \p{L}, bit 1 \p{N}, bit 2 \s (cpp/src/unicode.h:8-46,
  * cpp/src/unicode-data.cpp) */
 int     b200_cpt_class(uint32_t cp);

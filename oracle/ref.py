@@ -115,6 +115,12 @@ def lib() -> C.CDLL:
         L.refshim_token_is_eog.restype = C.c_int
         L.refshim_cpt_flags.argtypes = [C.c_uint32]
         L.refshim_cpt_flags.restype = C.c_uint16
+    if hasattr(L, "refshim_janus_generate"):
+        L.refshim_kv_seq_rm.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.refshim_kv_seq_add.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.refshim_janus_generate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                             C.c_uint32, C.c_int, C.POINTER(C.c_int32)]
+        L.refshim_janus_generate.restype = C.c_int
     L.refshim_init(1)
     return L
 
@@ -230,6 +236,25 @@ class RefModel:
             logits = self.decode([t], pos)
             pos += 1
         return ids, all_logits
+
+    def kv_seq_rm(self, p0: int, p1: int):
+        """llama_kv_cache_seq_rm(ctx, 0, p0, p1) (cpp/bridge.cpp:500)"""
+        self.L.refshim_kv_seq_rm(self.h, p0, p1)
+
+    def kv_seq_add(self, p0: int, p1: int, delta: int):
+        """llama_kv_cache_seq_add(ctx, 0, p0, p1, delta) (cpp/bridge.cpp:501); the K-shift runs inside the next decode"""
+        self.L.refshim_kv_seq_add(self.h, p0, p1, delta)
+
+    def janus_generate(self, prompt: Sequence[int], n_gen: int, depth: int, scale: float, hi: float, lo: float, seed: int,
+                       n_predict: int = -1) -> List[int]:
+        """the bridge's generation loop with the reference's own initJanus / sample_janus_token (cpp/janus.cpp)"""
+        toks = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.empty(n_gen, dtype=np.int32)
+        n = self.L.refshim_janus_generate(self.h, toks.ctypes.data_as(C.POINTER(C.c_int32)), len(toks), n_gen, depth, scale, hi, lo,
+                                          seed, n_predict, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        if n < 0:
+            raise RuntimeError("llama_decode failed")
+        return out[:n].tolist()
 
     def reset_timings(self):
         self.L.refshim_reset_timings(self.h)

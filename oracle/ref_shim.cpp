@@ -15,10 +15,15 @@
 //   node tap:                      cpp/include/llama.h:324-325 (cb_eval), cpp/src/llama.cpp:14707
 //   tokenizer (vocab-only load):   cpp/bridge.cpp:275-278 (llama_tokenize, add_special=false, parse_special=true),
 //                                  cpp/bridge.cpp:630 (llama_token_to_piece), :640 (llama_token_is_eog)
+//   sampler:                       cpp/bridge.cpp:196 (initJanus), :437-438, :586-603 (sample_janus_token + last_tokens)
+//   context shift:                 cpp/bridge.cpp:500-503 (llama_kv_cache_seq_rm / llama_kv_cache_seq_add)
 
 #include "llama.h"
 #include "ggml.h"
 #include "ggml-backend.h"
+#include "common.h"
+#include "sampling.h"
+#include "janus.h"
 
 #include <cstdint>
 #include <cstring>
@@ -171,6 +176,41 @@ void refshim_timings(void * hv, double * t_p_eval_ms, int * n_p_eval, double * t
     const llama_timings t = llama_get_timings(static_cast<ref_handle *>(hv)->ctx);
     *t_p_eval_ms = t.t_p_eval_ms; *n_p_eval = t.n_p_eval;
     *t_eval_ms   = t.t_eval_ms;   *n_eval   = t.n_eval;
+}
+
+// ---- context shift: the two calls of cpp/bridge.cpp:500-503; the K-shift itself runs inside the next llama_decode
+// (llama_kv_cache_update -> build_k_shift, cpp/src/llama.cpp:8482-8510)
+void refshim_kv_seq_rm(void * hv, int p0, int p1)             { llama_kv_cache_seq_rm(static_cast<ref_handle *>(hv)->ctx, 0, p0, p1); }
+void refshim_kv_seq_add(void * hv, int p0, int p1, int delta) { llama_kv_cache_seq_add(static_cast<ref_handle *>(hv)->ctx, 0, p0, p1, delta); }
+
+// ---- sampler oracle: the generation loop of cpp/bridge.cpp with the reference's own initJanus / sample_janus_token
+// (cpp/janus.cpp, compiled unmodified): clear the cache, decode the prompt as one batch, then n_gen times
+// { id = sample_janus_token(...); shift last_tokens; decode id } — last_tokens is n_ctx zeros that only GENERATED tokens
+// enter (cpp/bridge.cpp:437-438, 602-603); the rng is seeded like cpp/bridge.cpp:216-217 but with the caller's seed.
+// Stops after an end-of-generation token (cpp/bridge.cpp:640). Returns the number of ids written.
+int refshim_janus_generate(void * hv, const int32_t * prompt, int n_prompt, int n_gen, int depth, float scale, float hi, float lo,
+                           uint32_t seed, int n_predict, int32_t * out_ids) {
+    auto * h = static_cast<ref_handle *>(hv);
+    janus_params jp;
+    jp.janus = 1; jp.depth = depth; jp.scale = scale; jp.hi = hi; jp.lo = lo;
+    llama_sampling_params sp;
+    initJanus(h->ctx, jp, nullptr);
+    llama_set_rng_seed(h->ctx, seed);
+    llama_kv_cache_clear(h->ctx);
+    std::vector<llama_token> toks(prompt, prompt + n_prompt);
+    if (llama_decode(h->ctx, llama_batch_get_one(toks.data(), n_prompt, 0, 0))) return -1;
+    std::vector<llama_token> last_tokens((size_t) llama_n_ctx(h->ctx), 0);
+    int n_past = n_prompt, n = 0;
+    for (int i = 0; i < n_gen; i++) {
+        llama_token id = sample_janus_token(h->ctx, sp, jp, last_tokens, (size_t) n_prompt, (size_t) n_past, (size_t) n_predict);
+        last_tokens.erase(last_tokens.begin());
+        last_tokens.push_back(id);
+        out_ids[n++] = id;
+        if (llama_token_is_eog(h->model, id)) break;
+        if (llama_decode(h->ctx, llama_batch_get_one(&id, 1, n_past, 0))) return -1;
+        n_past += 1;
+    }
+    return n;
 }
 
 // ---- tokenizer oracle: the reference's own llama_tokenize / llama_token_to_piece / llama_token_is_eog on a

@@ -96,11 +96,45 @@ def make_ops():
     print("ops.npz written")
 
 
+def make_janus():
+    """tests/golden/janus.json: token ids the reference's bridge loop generates with its own Janus sampler (unmodified
+    cpp/janus.cpp through refshim_janus_generate) on tiny models with the padded synthetic vocabularies, for fixed seeds.
+    The models are rebuilt by the tests with the same deterministic generator (tests/test_sampler.py::_model)."""
+    import dataclasses
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import tokenizer_fixtures as F
+    from booster_b200 import engine
+    out = []
+    for kind in ("spm", "bpe"):
+        extra = F.vocab_kv(kind, pad_to=30016 if kind == "spm" else 128256)
+        cfg = dataclasses.replace(G.CONFIGS["tiny"], n_vocab=extra["llama.vocab_size"][1])
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, f"tiny_{kind}.gguf")
+            G.synth_llama(path, cfg, "Q4_K_M", seed=5, extra_kv=extra)
+            tok = engine.Tokenizer(path)
+            r = ref.RefModel(path, n_ctx=64, n_threads=2)
+            for text in ("Hello world, it's 42 tokens", "русский язык и ещё"):
+                prompt = tok.tokenize(text.encode(), False, True)
+                for depth, scale, hi, lo in ((200, 1.0, 1.0, 1.0), (200, 0.96, 0.99, 0.96), (8, 0.9, 0.7, 0.5)):
+                    for seed in (7, 4242):
+                        ids = r.janus_generate(prompt, 20, depth, scale, hi, lo, seed, n_predict=20)
+                        out.append({"kind": kind, "text": text, "prompt": prompt, "depth": depth, "scale": scale, "hi": hi, "lo": lo,
+                                    "seed": seed, "n_predict": 20, "ids": ids})
+            r.close(); tok.close()
+    json.dump(out, open(os.path.join(HERE, "janus.json"), "w"), indent=0)
+    print(f"janus.json: {len(out)} cases")
+
+
 if __name__ == "__main__":
     if not ref.available():
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` in the build container")
     print("reference variant:", ref.variant())
     only = sys.argv[1:]            # e.g. `make_golden.py tiny-gqa4-yarn`: (re)generate only the named models
+    if only == ["janus"]:
+        make_janus()
+        sys.exit(0)
     if not only:
         make_ops()
+        make_janus()
     make_models(only)

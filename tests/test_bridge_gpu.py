@@ -146,3 +146,32 @@ def test_two_pods_concurrently_equal_sequential(golden_dir):
     assert len(results) == 12
     for job, text in results.items():
         assert [int(x) for x in text.split()] == expect, job
+
+
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_do_inference_janus_sampler_equals_reference_golden(kind, tmp_path, golden_dir):
+    """SURVEY §8 f-2 through the nine symbols: with the seed fixed, doInference generates the token ids the reference's own
+    bridge loop generates with its Janus sampler (tests/golden/janus.json, made by the unmodified cpp/janus.cpp) — logits
+    bit-identical, sampler arithmetic identical, same std::mt19937 draws. Three settings: the reference's deterministic one,
+    its defaults, and a wide short list (real random draws)."""
+    import json
+
+    import test_sampler
+    from booster_b200 import engine
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "janus.json"))) if c["kind"] == kind]
+    assert len(cases) >= 12
+    path = test_sampler._model(tmp_path, kind)
+    tok = engine.Tokenizer(path)
+    L = _lib.lib()
+    L.init(b"", b"")
+    idx = 6
+    for i, c in enumerate(cases):
+        ctx = L.initContext(idx, path.encode(), 1, 0, 100, 0, 0, 0, 64, c["n_predict"], 0, 0.0, 0.0, 0.8, 40, 0.95, 1.0, 1.0, 64,
+                            1, c["depth"], c["scale"], c["hi"], c["lo"], c["seed"], b"")
+        assert ctx
+        job = f"janus-{kind}-{i}".encode()
+        L.doInference(idx, ctx, job, b"", c["text"].encode())
+        assert L.getSeed(job) == c["seed"]
+        want = b"".join(tok.piece(t, True) for t in c["prompt"] + c["ids"])
+        assert L.status(job) == want, (c["depth"], c["scale"], c["hi"], c["lo"], c["seed"])
+    tok.close()
