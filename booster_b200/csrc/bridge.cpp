@@ -10,7 +10,9 @@
 //     arg-max on the device;
 //   * tokenizer: models with tokenizer.ggml.model == "no_vocab" take prompts that are white-space separated
 //     token ids and render pieces as "<id> "; text tokenizers (BPE/SPM) are row f-1, see tokenizer.hpp;
-//   * context shift / Self-Extend (cpp/bridge.cpp:487-524) are row f-3: generation stops at n_ctx-4 instead;
+//   * context shift (cpp/bridge.cpp:487-507): same branch, same unreachability (the loop ends at n_ctx - 4 first); the KV
+//     operations behind it are b200_kv_seq_rm / b200_kv_seq_add (engine.cu), bit-exact against the reference. Self-Extend
+//     (ga_n > 1, :509-524) cannot be switched on through initContext in the reference either and is not built;
 //   * status() returns a per-thread snapshot instead of a pointer into a string another thread appends to
 //     (the reference race).
 #include "../../include/bridge.h"
@@ -277,6 +279,17 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
         { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += p.tok->piece(id, true); }
         if (p.tok->is_eog(id)) break;                      // cpp/bridge.cpp:640
         if (n_remain == 0 || n_past >= max_embd) break;
+        // infinite text generation via context shifting (cpp/bridge.cpp:487-507, n_keep = 0: gpt_params' default): keep the
+        // first n_keep tokens, drop half of the rest, move the tail down. As in the reference the loop condition above
+        // (n_past < n_ctx - 4) ends the job before n_past + 1 can exceed n_ctx, so the branch only documents the behaviour —
+        // the operation itself is b200_kv_seq_rm / b200_kv_seq_add, tested against the reference on their own.
+        if (n_past + 1 > p.n_ctx) {
+            const int n_keep = 0, n_left = n_past - n_keep, n_discard = n_left / 2;
+            for (b200_ctx * c : p.stages) {
+                if (b200_kv_seq_rm(c, n_keep, n_keep + n_discard) != 0 || b200_kv_seq_add(c, n_keep + n_discard, n_past, -n_discard) != 0) return 1;
+            }
+            n_past -= n_discard;
+        }
         if (single && device_argmax) {
             int32_t next = 0;
             if (b200_step_greedy(last, id, n_past, &next) != 0) return 1;

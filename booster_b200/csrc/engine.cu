@@ -429,7 +429,14 @@ extern "C" int64_t b200_model_weight_bytes(const b200_model * m) { return m ? m-
 static float yarn_corr_dim(int n_dims, int n_ctx_orig, float n_rot, float base) {
     return n_dims * logf(n_ctx_orig / (n_rot * 2 * (float) M_PI)) / (2 * logf(base));
 }
+// (cos, sin) of the hd/2 pairs for position p — ggml_rope_cache_init; p may be negative (the K-shift rotates by a delta)
+static void build_rope_row(const b200_model & m, int p, float2 * row);
 static void build_rope_table(const b200_model & m, int n_ctx, std::vector<float2> & tab) {
+    const int hd = m.head_dim;
+    tab.resize((size_t) n_ctx * (hd / 2));
+    for (int p = 0; p < n_ctx; p++) build_rope_row(m, p, tab.data() + (size_t) p * (hd / 2));
+}
+static void build_rope_row(const b200_model & m, int p, float2 * row) {
     const int hd = m.head_dim;
     const float theta_scale = powf(m.rope_freq_base, -2.0f / hd);
     float corr[2];
@@ -439,8 +446,7 @@ static void build_rope_table(const b200_model & m, int n_ctx, std::vector<float2
         corr[0] = std::max(0.f, start);
         corr[1] = std::min((float) (hd - 1), end);
     }
-    tab.resize((size_t) n_ctx * (hd / 2));
-    for (int p = 0; p < n_ctx; p++) {
+    {
         float theta = (float) p;
         for (int i0 = 0; i0 < hd; i0 += 2) {
             const float ff = m.rope_freq_factors.empty() ? 1.0f : m.rope_freq_factors[(size_t) (i0 / 2)];
@@ -454,7 +460,7 @@ static void build_rope_table(const b200_model & m, int n_ctx, std::vector<float2
                 th = theta_interp * (1 - ramp_mix) + theta_extrap * ramp_mix;
                 mscale *= 1.0f + 0.1f * logf(1.0f / m.rope_freq_scale);
             }
-            tab[(size_t) p * (hd / 2) + i0 / 2] = make_float2(cosf(th) * mscale, sinf(th) * mscale);
+            row[i0 / 2] = make_float2(cosf(th) * mscale, sinf(th) * mscale);
             theta *= theta_scale;
         }
     }
@@ -533,6 +539,17 @@ struct b200_ctx {
     int sm_count = 148;
     bool taps = false;
     TapStore tapstore;
+    // KV cells (struct llama_kv_cache, cpp/src/llama.cpp:2495-2539). Until the first llama_kv_cache_seq_rm / seq_add a sequence
+    // only grows and cell == position (n_hi positions written so far); afterwards the cells are managed like the reference's:
+    // find_slot from `head`, positions and pending K-shift deltas per cell, attention masked by cell_pos on the device.
+    struct KvCells {
+        bool managed = false;
+        int n_hi = 0;                      // identity mode: highest position written + 1
+        std::vector<int32_t> pos, delta;   // managed mode, per cell
+        int head = 0, used = 0;
+        bool has_shift = false;
+    } cells;
+    int32_t * d_cell_pos = nullptr;        // [n_ctx] device copy of cells.pos
     // persistent per-token kernel (token_kernel.cuh): phase list in device memory, grid-barrier counter, transposed scores
     Phase * d_plan = nullptr;
     int n_phases = 0;
@@ -961,7 +978,7 @@ static bool token_kernel_build(b200_ctx * c) {
             Phase P{};
             P.at.q = c->q; P.at.k_cache = c->kc[(size_t) li]; P.at.v_cache = c->vc[(size_t) li];
             P.at.rs = rs; P.at.out = c->att; P.at.n_head_kv = m.n_head_kv; P.at.kv_dim = KVD;
-            P.at.scale = 1.0f / sqrtf((float) HD); P.at.st = c->d_state; P.at.v_chunk = v_chunk;
+            P.at.scale = 1.0f / sqrtf((float) HD); P.at.st = c->d_state; P.at.v_chunk = v_chunk; P.at.cell_pos = c->d_cell_pos;
             P.kind = PH_SCORES; plan.push_back(P);
             P.kind = PH_SOFTMAX_PV; plan.push_back(P);
             push_mv(args_wo(c, li), EPI_RESID);
@@ -1057,7 +1074,7 @@ static void enqueue_forward(b200_ctx * c) {
             a.S = c->S; a.s_stride = c->n_ctx; a.out = c->att;
             a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD;
             a.scale = 1.0f / sqrtf((float) HD);
-            a.st = c->d_state; a.n_kv_override = 0; a.round_q_override = 0;
+            a.st = c->d_state; a.n_kv_override = 0; a.round_q_override = 0; a.cell_pos = c->d_cell_pos;
 #if B200_LOOKAHEAD
             pf_push(a.pf,  pf_slice(L.gateup.m.p0, gu_bytes, 0.0, pp.gu_scores));
             pf_push(a.pf2, pf_slice(L.gateup.m.p0, gu_bytes, pp.gu_scores, pp.gu_scores + pp.gu_pv));
@@ -1159,6 +1176,8 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         CU(cudaMalloc(&c->S, (size_t) m->n_head * c->n_ctx * 4));
         CU(cudaMalloc(&c->tickets, (size_t) m->n_head_kv * 4));
         CU(cudaMemsetAsync(c->tickets, 0, (size_t) m->n_head_kv * 4, c->st));
+        CU(cudaMalloc(&c->d_cell_pos, (size_t) c->n_ctx * 4));
+        CU(cudaMemsetAsync(c->d_cell_pos, 0xff, (size_t) c->n_ctx * 4, c->st));
         CU(cudaMalloc(&c->amax_key, 8));
         CU(cudaMemsetAsync(c->amax_key, 0, 8, c->st));
         if (HD != 128) throw std::runtime_error("attention kernels are specialised for head_dim 128");
@@ -1206,6 +1225,7 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     for (auto p : c->kc) cudaFree(p);
     for (auto p : c->vc) cudaFree(p);
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->warm_x); cudaFree(c->logits);
+    cudaFree(c->d_cell_pos);
     cudaFree(c->d_trace); cudaFree(c->d_plan); cudaFree(c->d_bar); cudaFree(c->S_T); cudaFree(c->d_ttrace);
     cudaFree(c->S); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits); cudaFreeHost(c->h_tok);
@@ -1219,9 +1239,200 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
 
 extern "C" void b200_kv_clear(b200_ctx * c) {
     if (!c) return;
-    // the cache is addressed by position and attention only reads slots [0, pos]; clearing is a reset of counters
+    // llama_kv_cache_clear (cpp/src/llama.cpp:3135-3152): every cell empty, head 0. Attention only reads cells that hold a
+    // position, so the rows themselves need no clearing.
     cudaSetDevice(c->m->device);
     cudaStreamSynchronize(c->st);
+    c->cells = b200_ctx::KvCells();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// KV cells: find_slot / seq_rm / seq_add / K-shift (cpp/src/llama.cpp:3028-3125, 3154-3206, 3268-3314, 8482-8510, 15245-15277)
+// ------------------------------------------------------------------------------------------------------------
+// K-shift: the cached (post-RoPE) K rows of cells whose position changed are rotated by the accumulated delta, in place, as
+// ggml_rope_ext_inplace on the f16 cache does (ggml_compute_forward_rope_f16, cpp/ggml/src/ggml.c:14169-14291): f16 -> f32,
+// x0*cos - x1*sin / x0*sin + x1*cos (un-fused), f32 -> f16. row_of[cell] selects the (cos, sin) row of the cell's delta
+// (-1: untouched — delta 0 is the identity unless the model scales cos/sin by an attention factor, then row 0 holds it).
+__global__ void k_kshift(__half * k_cache, int n_cells, int kv_dim, int head_dim, const int32_t * __restrict__ row_of,
+                         const float2 * __restrict__ rows) {
+    const int half_dim = head_dim / 2, pairs = kv_dim / 2;
+    const int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t) n_cells * pairs) return;
+    const int cell = (int) (idx / pairs), pr = (int) (idx % pairs);
+    const int r = row_of[cell];
+    if (r < 0) return;
+    const float2 cs = rows[(size_t) r * half_dim + (pr % half_dim)];
+    __half * p = k_cache + (size_t) cell * kv_dim + 2 * pr;
+    const float x0 = __half2float(p[0]), x1 = __half2float(p[1]);
+    p[0] = __float2half_rn(__fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y)));
+    p[1] = __float2half_rn(__fadd_rn(__fmul_rn(x0, cs.y), __fmul_rn(x1, cs.x)));
+}
+
+static void kv_enter_managed(b200_ctx * c) {
+    auto & k = c->cells;
+    if (k.managed) return;
+    k.managed = true;
+    k.pos.assign((size_t) c->n_ctx, -1);
+    k.delta.assign((size_t) c->n_ctx, 0);
+    for (int i = 0; i < k.n_hi && i < c->n_ctx; i++) k.pos[(size_t) i] = i;
+    k.used = std::min(k.n_hi, c->n_ctx);
+    k.head = k.used >= c->n_ctx ? 0 : k.used;       // cpp/src/llama.cpp:14821-14826: head += n_tokens, wrapped
+    k.has_shift = false;
+    CU(cudaMemcpyAsync(c->d_cell_pos, k.pos.data(), (size_t) c->n_ctx * 4, cudaMemcpyHostToDevice, c->st));
+    CU(cudaStreamSynchronize(c->st));
+}
+static int kv_cell_max(const b200_ctx * c) {            // llama_kv_cache_cell_max (cpp/src/llama.cpp:3397-3407)
+    for (int i = c->n_ctx; i > 0; i--) if (c->cells.pos[(size_t) i - 1] >= 0) return i;
+    return 0;
+}
+// llama_kv_cache_update_internal: apply the pending K-shift to every local layer, then clear the deltas
+static void kv_apply_shift(b200_ctx * c) {
+    auto & k = c->cells;
+    if (!k.managed || !k.has_shift) return;
+    b200_model & m = *c->m;
+    const int hd = m.head_dim;
+    // the reference rotates EVERY cell by its delta; delta 0 is the identity only when cos(0) * mscale == 1
+    float2 probe[128];
+    std::vector<float2> row0((size_t) hd / 2);
+    build_rope_row(m, 0, row0.data());
+    (void) probe;
+    const bool identity0 = row0[0].x == 1.0f && row0[0].y == 0.0f;
+    std::vector<int32_t> deltas;                        // distinct deltas -> table rows
+    std::vector<int32_t> row_of((size_t) c->n_ctx, -1);
+    for (int i = 0; i < c->n_ctx; i++) {
+        const int d = k.delta[(size_t) i];
+        if (d == 0 && identity0) continue;
+        size_t r = 0;
+        while (r < deltas.size() && deltas[r] != d) r++;
+        if (r == deltas.size()) deltas.push_back(d);
+        row_of[(size_t) i] = (int32_t) r;
+    }
+    if (!deltas.empty()) {
+        std::vector<float2> rows(deltas.size() * (size_t) (hd / 2));
+        for (size_t r = 0; r < deltas.size(); r++) build_rope_row(m, deltas[r], rows.data() + r * (size_t) (hd / 2));
+        int32_t * d_row_of = nullptr; float2 * d_rows = nullptr;
+        CU(cudaMalloc(&d_row_of, row_of.size() * 4));
+        CU(cudaMalloc(&d_rows, rows.size() * sizeof(float2)));
+        CU(cudaMemcpyAsync(d_row_of, row_of.data(), row_of.size() * 4, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
+        const int kvd = m.n_head_kv * hd;
+        const int64_t n = (int64_t) c->n_ctx * (kvd / 2);
+        for (size_t li = 0; li < c->kc.size(); li++) {
+            k_kshift<<<(unsigned) ((n + 255) / 256), 256, 0, c->st>>>(c->kc[li], c->n_ctx, kvd, hd, d_row_of, d_rows);
+            c->launches++;
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->st));
+        cudaFree(d_row_of); cudaFree(d_rows);
+    }
+    k.has_shift = false;
+    std::fill(k.delta.begin(), k.delta.end(), 0);
+}
+// llama_kv_cache_find_slot for n tokens of sequence 0 at positions pos0..; returns the first cell (-1: no room), and the
+// number of cells to attend. Updates the device copy of the cells' positions.
+static int kv_find_slot(b200_ctx * c, int pos0, int n, int * n_kv) {
+    auto & k = c->cells;
+    const int size = c->n_ctx;
+    if (n > size) return -1;
+    if (k.head > k.used + 2 * n) k.head = 0;            // cpp/src/llama.cpp:14684-14688
+    int n_tested = 0;
+    while (true) {
+        if (k.head + n > size) { n_tested += size - k.head; k.head = 0; continue; }
+        bool found = true;
+        for (int i = 0; i < n; i++) {
+            if (k.pos[(size_t) (k.head + i)] >= 0) { found = false; k.head += i + 1; n_tested += i + 1; break; }
+        }
+        if (found) break;
+        if (n_tested >= size) return -1;
+    }
+    for (int i = 0; i < n; i++) k.pos[(size_t) (k.head + i)] = pos0 + i;
+    k.used += n;
+    const int first = k.head;
+    CU(cudaMemcpyAsync(c->d_cell_pos + first, k.pos.data() + first, (size_t) n * 4, cudaMemcpyHostToDevice, c->st));
+    *n_kv = kv_cell_max(c);
+    k.head += n;                                         // cpp/src/llama.cpp:14821-14826 (after the graph ran)
+    if (k.head >= size) k.head = 0;
+    return first;
+}
+// the per-token scalars of token `pos` (cell and attention length included) for a context whose cache was never shifted
+static DecodeState identity_state(b200_ctx * c, int32_t token, int pos, int round_q) {
+    if (c->cells.managed) throw std::runtime_error("this entry point does not support a context-shifted KV cache; use b200_decode / b200_step_greedy");
+    DecodeState hs{};
+    hs.token = token; hs.pos = pos; hs.round_q = round_q; hs.step = 0; hs.cell = pos; hs.n_kv = pos + 1; hs.managed = 0;
+    return hs;
+}
+// state of token i of a batch of n at positions pos0.. : cells from find_slot once the cache is managed
+struct BatchPlace { int first = -1, n_kv = 0; };
+static BatchPlace place_batch(b200_ctx * c, int pos0, int n) {
+    BatchPlace b;
+    if (!c->cells.managed) return b;
+    kv_apply_shift(c);
+    b.first = kv_find_slot(c, pos0, n, &b.n_kv);
+    if (b.first < 0) throw std::runtime_error("no free KV cells for the batch");   // llama_decode returns 1: cpp/src/llama.cpp:14690
+    return b;
+}
+static DecodeState token_state(b200_ctx * c, const BatchPlace & b, int i, int32_t token, int pos, int round_q) {
+    if (!c->cells.managed) return identity_state(c, token, pos, round_q);
+    DecodeState hs{};
+    hs.token = token; hs.pos = pos; hs.round_q = round_q; hs.step = 0; hs.cell = b.first + i; hs.n_kv = b.n_kv; hs.managed = 1;
+    return hs;
+}
+static void note_positions(b200_ctx * c, int pos_end) { if (!c->cells.managed) c->cells.n_hi = std::max(c->cells.n_hi, pos_end); }
+
+// llama_kv_cache_seq_rm(ctx, 0, p0, p1) (cpp/bridge.cpp:500; cpp/src/llama.cpp:3154-3206)
+extern "C" int b200_kv_seq_rm(b200_ctx * c, int p0, int p1) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        CU(cudaSetDevice(c->m->device));
+        kv_enter_managed(c);
+        auto & k = c->cells;
+        if (p0 < 0) p0 = 0;
+        if (p1 < 0) p1 = INT32_MAX;
+        int new_head = c->n_ctx;
+        for (int i = 0; i < c->n_ctx; i++) {
+            if (k.pos[(size_t) i] >= p0 && k.pos[(size_t) i] < p1) {
+                k.used--;
+                k.pos[(size_t) i] = -1;
+                if (new_head == c->n_ctx) new_head = i;
+            }
+        }
+        if (new_head != c->n_ctx && new_head < k.head) k.head = new_head;
+        CU(cudaMemcpyAsync(c->d_cell_pos, k.pos.data(), (size_t) c->n_ctx * 4, cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+// llama_kv_cache_seq_add(ctx, 0, p0, p1, delta) (cpp/bridge.cpp:501; cpp/src/llama.cpp:3268-3314): positions move now, the K
+// rows are re-rotated by the accumulated delta at the next decode (llama_kv_cache_update)
+extern "C" int b200_kv_seq_add(b200_ctx * c, int p0, int p1, int delta) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        CU(cudaSetDevice(c->m->device));
+        kv_enter_managed(c);
+        auto & k = c->cells;
+        if (p0 < 0) p0 = 0;
+        if (p1 < 0) p1 = INT32_MAX;
+        if (p0 == p1) return 0;
+        int new_head = c->n_ctx;
+        for (int i = 0; i < c->n_ctx; i++) {
+            if (k.pos[(size_t) i] >= p0 && k.pos[(size_t) i] < p1) {
+                k.has_shift = true;
+                k.pos[(size_t) i] += delta;
+                k.delta[(size_t) i] += delta;
+                if (k.pos[(size_t) i] < 0) {
+                    k.used--;
+                    k.pos[(size_t) i] = -1;
+                    if (new_head == c->n_ctx) new_head = i;
+                }
+            }
+        }
+        k.head = new_head != c->n_ctx ? new_head : 0;
+        CU(cudaMemcpyAsync(c->d_cell_pos, k.pos.data(), (size_t) c->n_ctx * 4, cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
 }
 
 // Rows [pos0, pos0 + n) of one local layer's K (post-RoPE) and V cache, f16 bits [n][n_head_kv * head_dim] — the view
@@ -1236,6 +1447,8 @@ extern "C" int b200_kv_write(b200_ctx * c, int layer, int pos0, int n, const uin
         if (pos0 < 0 || n < 0 || pos0 + n > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");
         const size_t row = (size_t) c->m->n_head_kv * c->m->head_dim * 2;
         CU(cudaSetDevice(c->m->device));
+        if (c->cells.managed) throw std::runtime_error("b200_kv_write addresses rows by position: not available after a context shift");
+        note_positions(c, pos0 + n);
         if (k_rows) CU(cudaMemcpyAsync((uint8_t *) c->kc[(size_t) li] + pos0 * row, k_rows, n * row, cudaMemcpyHostToDevice, c->st));
         if (v_rows) CU(cudaMemcpyAsync((uint8_t *) c->vc[(size_t) li] + pos0 * row, v_rows, n * row, cudaMemcpyHostToDevice, c->st));
         CU(cudaStreamSynchronize(c->st));
@@ -1288,9 +1501,11 @@ extern "C" int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0
         const double t0 = now_us();
         // reference semantics for batch > 1: q is rounded to f16 before K.q (cpp/ggml/src/ggml.c:12345-12371)
         const int round_q = n > 1 ? 1 : 0;
+        const BatchPlace place = place_batch(c, pos0, n);
+        note_positions(c, pos0 + n);
         for (int i = 0; i < n; i++) {
             const bool last = i == n - 1;
-            c->h_state->token = tokens[i]; c->h_state->pos = pos0 + i; c->h_state->round_q = round_q; c->h_state->step = 0;
+            *c->h_state = token_state(c, place, i, tokens[i], pos0 + i, round_q);
             if (c->taps) {
                 CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
                 enqueue_forward(c);
@@ -1329,7 +1544,8 @@ extern "C" int b200_generate_greedy(b200_ctx * c, int32_t first_token, int pos0,
         if (first_token < 0 || first_token >= m.n_vocab) throw std::runtime_error("token id out of range");
         CU(cudaSetDevice(m.device));
         const double t0 = now_us();
-        c->h_state->token = first_token; c->h_state->pos = pos0; c->h_state->round_q = 0; c->h_state->step = 0;
+        *c->h_state = identity_state(c, first_token, pos0, 0);
+        note_positions(c, pos0 + n_steps);
         CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
         if (!c->g_greedy) {
             CU(cudaStreamSynchronize(c->st));
@@ -1374,7 +1590,9 @@ extern "C" int b200_step_greedy(b200_ctx * c, int32_t token, int pos, int32_t * 
         if (pos < 0 || pos >= c->n_ctx) throw std::runtime_error("position exceeds n_ctx");
         if (token < 0 || token >= m.n_vocab) throw std::runtime_error("token id out of range");
         CU(cudaSetDevice(m.device));
-        c->h_state->token = token; c->h_state->pos = pos; c->h_state->round_q = 0; c->h_state->step = 0;
+        const BatchPlace place = place_batch(c, pos, 1);
+        note_positions(c, pos + 1);
+        *c->h_state = token_state(c, place, 0, token, pos, 0);
         if (c->taps) {                                         // taps need the un-graphed path
             CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
             enqueue_forward(c);
@@ -1410,7 +1628,7 @@ extern "C" int b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms
         b200_model & m = *c->m;
         if (pos < 0 || pos >= c->n_ctx || token < 0 || token >= m.n_vocab) throw std::runtime_error("bad token/pos");
         CU(cudaSetDevice(m.device));
-        DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = 0; hs.step = 0;
+        const DecodeState hs = identity_state(c, token, pos, 0);
         k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
         c->prof = true; c->prof_ev.clear();
         enqueue_forward(c);
@@ -1439,7 +1657,7 @@ extern "C" int b200_profile_kind(b200_ctx * c, int kind, int pos, int reps, floa
         b200_model & m = *c->m;
         if (pos < 0 || pos >= c->n_ctx) throw std::runtime_error("bad pos");
         CU(cudaSetDevice(m.device));
-        DecodeState hs; hs.token = 0; hs.pos = pos; hs.round_q = 0; hs.step = 0;
+        const DecodeState hs = identity_state(c, 0, pos, 0);
         k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
         if (!c->ev_t0) { CU(cudaEventCreate(&c->ev_t0)); CU(cudaEventCreate(&c->ev_t1)); }
         const int64_t l0 = c->launches;
@@ -1474,7 +1692,7 @@ extern "C" int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int re
         CU(cudaSetDevice(m.device));
         const size_t words = (size_t) TRACE_MAX_LAUNCHES * TRACE_CTAS * TRACE_PHASES;
         if (!c->d_trace) CU(cudaMalloc(&c->d_trace, words * 8));
-        DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = 0; hs.step = 0;
+        const DecodeState hs = identity_state(c, token, pos, 0);
         c->tracing = true; c->trace_seq = 0; c->trace_meta.clear();
         int64_t nk = 0;
         cudaGraphExec_t ge = nullptr;
@@ -1513,7 +1731,7 @@ extern "C" int64_t b200_trace_phases(b200_ctx * c, int32_t token, int pos, int r
         if (c->token_state <= 0) return 0;
         const size_t words = (size_t) c->n_phases * c->sm_count * TK_TRACE_SLOTS;
         if (!c->d_ttrace) CU(cudaMalloc(&c->d_ttrace, words * 8));
-        DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = 0; hs.step = 0;
+        const DecodeState hs = identity_state(c, token, pos, 0);
         for (int r = 0; r < std::max(1, reps); r++) {
             k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
             CU(cudaMemsetAsync(c->d_ttrace, 0, words * 8, c->st));
@@ -1583,7 +1801,8 @@ extern "C" int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, 
         if (n_steps > c->out_tokens_cap) throw std::runtime_error("n_steps too large");
         if (first_token < 0 || first_token >= m.n_vocab) throw std::runtime_error("token id out of range");
         CU(cudaSetDevice(m.device));
-        c->h_state->token = first_token; c->h_state->pos = pos0; c->h_state->round_q = 0; c->h_state->step = 0;
+        *c->h_state = identity_state(c, first_token, pos0, 0);
+        note_positions(c, pos0 + n_steps);
         CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
         // device time of the burst on THIS rank's stream (first stage step enqueued -> last one complete; a stage's
         // stream idles inside ncclRecv while the other stages work, so every rank's span covers the whole burst)
@@ -1641,7 +1860,8 @@ extern "C" int b200_pipeline_decode(b200_ctx * c, const int32_t * tokens, int n,
         CU(cudaSetDevice(m.device));
         const int round_q = n > 1 ? 1 : 0;
         for (int i = 0; i < n; i++) {
-            c->h_state->token = tokens[i]; c->h_state->pos = pos0 + i; c->h_state->round_q = round_q; c->h_state->step = 0;
+            *c->h_state = identity_state(c, tokens[i], pos0 + i, round_q);
+            note_positions(c, pos0 + i + 1);
             CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(DecodeState), cudaMemcpyHostToDevice, c->st));
             enqueue_stage_step(c, false);
             CU(cudaStreamSynchronize(c->st));
@@ -1680,7 +1900,9 @@ extern "C" int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batc
             CU(cudaEventRecord(prev->ev_taken, c->st));
             prev->taken_pending = true;
         }
-        DecodeState hs; hs.token = token; hs.pos = pos; hs.round_q = batch_gt1 ? 1 : 0; hs.step = 0;
+        const BatchPlace place = place_batch(c, pos, 1);
+        note_positions(c, pos + 1);
+        const DecodeState hs = token_state(c, place, 0, token, pos, batch_gt1 ? 1 : 0);
         k_set_state<<<1, 1, 0, c->st>>>(c->d_state, hs);
         c->launches++;
         enqueue_forward(c);
@@ -1897,7 +2119,7 @@ extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, cons
         a.q = dq.as<float>(); a.k_cache = dk.as<__half>(); a.v_cache = dv.as<__half>();
         a.S = dS.as<float>(); a.s_stride = n_pad; a.out = dout.as<float>();
         a.n_head = n_head; a.n_head_kv = n_head_kv; a.head_dim = head_dim; a.kv_dim = kvd;
-        a.scale = scale; a.st = nullptr; a.n_kv_override = n_kv; a.round_q_override = round_q;
+        a.scale = scale; a.st = nullptr; a.n_kv_override = n_kv; a.round_q_override = round_q; a.cell_pos = nullptr;
         launch_attention(&tmp, a, n_pad);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out, dout.p, (size_t) qd * 4, cudaMemcpyDeviceToHost, st));

@@ -66,9 +66,16 @@ __host__ __device__ __forceinline__ int tile_bytes_of(int type) {
 // per-token scalars, device-resident so that one CUDA graph serves every token
 struct DecodeState {
     int32_t token;     // input token id of this step
-    int32_t pos;       // its position == KV slot it is written to
+    int32_t pos;       // its position
     int32_t round_q;   // 1: batch > 1 arithmetic for K.q (q rounded to f16, ggml_vec_dot_f16 order)
     int32_t step;      // greedy loop: index into out_tokens
+    // KV cells (struct llama_kv_cache, cpp/src/llama.cpp:2495-2539). Until a context shift cell == pos and n_kv == pos + 1
+    // (what llama_kv_cache_find_slot gives a sequence that only ever grows); after llama_kv_cache_seq_rm / seq_add the cells
+    // keep their places, freed cells are re-used by new tokens, and attention masks by the cells' positions (managed != 0).
+    int32_t cell;      // KV cell this token's K / V rows are written to
+    int32_t n_kv;      // cells attended: highest used cell + 1 (the kernels pad it to 32 like the reference, :14698)
+    int32_t managed;   // 0: cell t holds position t for t < n_kv; 1: positions come from cell_pos[]
+    int32_t pad_;
 };
 
 enum { EPI_STORE = 0, EPI_RESID = 1, EPI_QKV = 2, EPI_SILU = 3 };
@@ -766,7 +773,7 @@ __device__ __forceinline__ UnitDesc describe_unit(const MatvecArgs & a, int unit
 // The code of a unit is specialised on the unit's block type.
 // ------------------------------------------------------------------------------------------------------------
 // the row's epilogue (one call per unit; out of line: four block types share one copy)
-__device__ __noinline__ void matvec_epilogue(const MatvecArgs & a, float val, int row, int lane, float pre0, float pre1, int pos) {
+__device__ __noinline__ void matvec_epilogue(const MatvecArgs & a, float val, int row, int lane, float pre0, float pre1, int cell) {
     const float oth = __shfl_xor_sync(0xffffffffu, val, 1);    // partner row (2i <-> 2i+1)
     if (a.epi == EPI_STORE) {
         a.out[row] = val;
@@ -782,9 +789,9 @@ __device__ __noinline__ void matvec_epilogue(const MatvecArgs & a, float val, in
             const float y = (lane & 1) ? __fadd_rn(__fmul_rn(v0, pre1), __fmul_rn(v1, pre0))
                                        : __fsub_rn(__fmul_rn(v0, pre0), __fmul_rn(v1, pre1));
             if (row < a.n_q) a.q_out[row] = y;
-            else a.k_cache[(size_t) pos * a.kv_dim + (row - a.n_q)] = __float2half_rn(y);   // K post-RoPE as f16: llama.cpp:7849-7853
+            else a.k_cache[(size_t) cell * a.kv_dim + (row - a.n_q)] = __float2half_rn(y);   // K post-RoPE as f16: llama.cpp:7849-7853
         } else {
-            a.v_cache[(size_t) pos * a.kv_dim + (row - a.n_q - a.n_k)] = __float2half_rn(val);
+            a.v_cache[(size_t) cell * a.kv_dim + (row - a.n_q - a.n_k)] = __float2half_rn(val);
         }
     }
 }
@@ -803,6 +810,7 @@ struct MvState {
     int pi, pj, pk, ps;
     UnitDesc pd;
     uint64_t pol;
+    float ww[PRO_U][8];        // the warp's norm weights (constants: requested before the input exists)
 };
 
 // producer side: item pi = (unit pj, tile w + G*pk) goes to ring slot pi % S
@@ -875,6 +883,19 @@ __device__ __forceinline__ void mv_begin(const MatvecArgs & a, uint8_t * smem_ra
     const int prefill = min(n_prefill, S - 1);
 #pragma unroll 1
     for (int st = 0; st < prefill; st++) mv_issue_next(a, s, lane);
+    // norm weights are constants too: the warp's blocks (the host guarantees k/256 <= PRO_U * W when there is a norm)
+#pragma unroll
+    for (int u = 0; u < PRO_U; u++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) s.ww[u][i] = 0.f;
+    }
+    if (a.norm_w != nullptr) {
+#pragma unroll
+        for (int u = 0; u < PRO_U; u++) {
+            const int b = warp + u * W;
+            if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, s.ww[u]);
+        }
+    }
 }
 
 template <bool TR>
@@ -892,17 +913,8 @@ __device__ __forceinline__ void mv_run(const MatvecArgs & a, double * red_smem, 
     const int group_global = s.group_global, n_groups = s.n_groups, my_units = s.my_units;
     const bool norm = a.norm_w != nullptr;
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
-    // norm weights: the warp's blocks (the host guarantees k/256 <= PRO_U * W when there is a norm); constants, requested
-    // together with x
-    float ww[PRO_U][8] = {};
-    if (norm) {
-#pragma unroll
-        for (int u = 0; u < PRO_U; u++) {
-            const int b = warp + u * W;
-            if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, ww[u]);
-        }
-    }
-    prologue_quantize<TR>(a.x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, ww,
+    const int cell = EPI == EPI_QKV ? a.st->cell : 0;
+    prologue_quantize<TR>(a.x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, s.ww,
                       [&]() {
 #pragma unroll 1
                           for (int st = n_prefilled; st < S - 1; st++) mv_issue_next(a, s, lane);
@@ -1022,7 +1034,7 @@ __device__ __forceinline__ void mv_run(const MatvecArgs & a, double * red_smem, 
                     val = finish_row<TYPE>(cv);
                 }
 
-                matvec_epilogue(a, val, cd.row0 + lane, lane, pre0, pre1, pos);
+                matvec_epilogue(a, val, cd.row0 + lane, lane, pre0, pre1, cell);
             }
         };
         switch (cd.type) {
@@ -1202,9 +1214,20 @@ struct AttnArgs {
     int p_chunk;              // positions of p staged in shared memory by k_attn_pv (multiple of PV_BATCH)
     PfRange pf[PF_RANGES];    // L2 look-ahead issued by k_attn_scores
     PfRange pf2[PF_RANGES];   // ... and by k_attn_softmax_pv
+    const int32_t * cell_pos; // [n_ctx] position held by each KV cell (-1: empty); read only when st->managed
     unsigned long long * trace;
 };
-__device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->pos + 1; }
+__device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->n_kv; }
+// the cell this token's K / V rows were just written to (by the QKV kernel; every other cell is older)
+__device__ __forceinline__ int attn_cur_cell(const AttnArgs & a, int n_kv) { return a.n_kv_override > 0 ? n_kv - 1 : a.st->cell; }
+// the KQ mask (cpp/src/llama.cpp:14132-14200): cell t is attended iff it holds a position of the sequence that is <= the
+// token's. Without a context shift cell t holds position t and the test is t < n_kv.
+__device__ __forceinline__ bool attn_cell_visible(const DecodeState * st, const int32_t * cell_pos, int t, int n_kv) {
+    if (t >= n_kv) return false;
+    if (st == nullptr || !st->managed) return true;
+    const int p = cell_pos[t];
+    return p >= 0 && p <= st->pos;
+}
 
 template <int GQA, bool TR>
 __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
@@ -1221,7 +1244,8 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
 #pragma unroll
     for (int s = 0; s < 8; s++) kv[s] = make_uint2(0u, 0u);
     const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
-    if (t < n_kv - 1) {
+    const int cur = attn_cur_cell(a, n_kv);
+    if (t < n_kv && t != cur) {
 #pragma unroll
         for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);            // 4 halfs at element 16s + 4c4
     }
@@ -1234,10 +1258,11 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     trace_mark<TR>(a.trace, 1);
     if (tile * ATT_TILE >= n_pad) return;
     const int round_q = a.st ? a.st->round_q : a.round_q_override;
-    if (t == n_kv - 1) {
+    if (t == cur) {
 #pragma unroll
         for (int s = 0; s < 8; s++) kv[s] = kr[s * 4];                    // plain loads: written by the previous kernel
     }
+    const bool visible = attn_cell_visible(a.st, a.cell_pos, t, n_kv);
     for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
         float v = a.q[(size_t) (g * GQA) * HD + i];
         if (round_q) v = __half2float(__float2half_rn(v));    // src1 converted to the vec_dot_type F16 (ggml.c:12345-12371)
@@ -1287,7 +1312,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
 #pragma unroll
             for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);   // t3[4+i] + t3[i] (valid in c4 = 0)
             const float res = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
-            if (c4 == 0) a.S[(size_t) (g * GQA + h) * a.s_stride + t] = t < n_kv ? __fmul_rn(res, a.scale) : -INFINITY;
+            if (c4 == 0) a.S[(size_t) (g * GQA + h) * a.s_stride + t] = visible ? __fmul_rn(res, a.scale) : -INFINITY;
         }
     }
     trace_mark<TR>(a.trace, 2);
@@ -1592,7 +1617,7 @@ __global__ void k_argmax_finish(unsigned long long * key, DecodeState * st, int3
     *key = 0ull;
     if (advance) {
         if (out_tokens) out_tokens[st->step] = idx;
-        st->token = idx; st->pos += 1; st->step += 1;
+        st->token = idx; st->pos += 1; st->step += 1; st->cell += 1; st->n_kv += 1;   // (device loop: only without a context shift)
     } else {
         out_tokens[0] = idx;
     }
@@ -1602,7 +1627,7 @@ __global__ void k_set_state(DecodeState * st, const DecodeState v) { *st = v; }
 
 // advance (pos, step) on stages that do not sample (pipeline stages other than the last)
 __global__ void k_advance(DecodeState * st) {
-    if (threadIdx.x == 0) { st->pos += 1; st->step += 1; }
+    if (threadIdx.x == 0) { st->pos += 1; st->step += 1; st->cell += 1; st->n_kv += 1; }
 }
 
 // RoPE on a [n_heads][head_dim] f32 buffer in place (operator-level test; engine fuses it into EPI_QKV)

@@ -37,6 +37,7 @@ struct AttnPhase {
     int n_head_kv, kv_dim;
     float scale;
     const DecodeState * st;
+    const int32_t * cell_pos; // position held by each KV cell (read only when st->managed)
     int v_chunk;              // positions of V staged in shared memory at a time (multiple of 64)
 };
 
@@ -103,14 +104,14 @@ __device__ __forceinline__ void sc_load_k(const AttnPhase & a, int vb, int n_blo
     if (vb >= n_blocks) return;
     const int g = vb % a.n_head_kv, tile = vb / a.n_head_kv;
     const int t = tile * TK_SC_TILE + (tid >> 2), c4 = tid & 3;
-    if (t < n_kv - 1) {
+    if (t < n_kv && t != a.st->cell) {
         const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * 128 + 4 * c4);
 #pragma unroll
         for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);            // 4 halfs at element 16s + 4c4 (row of an earlier token)
     }
 }
 __device__ __forceinline__ void scores_begin(const AttnPhase & a, int cta, ScState & s) {
-    const int n_kv = a.st->pos + 1;                            // DecodeState is not written during the token
+    const int n_kv = a.st->n_kv;                               // DecodeState is not written during the token
     const int n_pad = (n_kv + 31) / 32 * 32;
     const int n_blocks = a.n_head_kv * ((n_pad + TK_SC_TILE - 1) / TK_SC_TILE);
     sc_load_k(a, cta, n_blocks, n_kv, threadIdx.x, s.kv);
@@ -119,7 +120,7 @@ template <int GQA>
 __device__ __forceinline__ void scores_run(const AttnPhase & a, int cta, int n_cta, float (*qs)[128], ScState & s) {
     constexpr int HD = 128;
     const int tid = threadIdx.x, tl = tid >> 2, c4 = tid & 3;
-    const int n_kv = a.st->pos + 1;
+    const int n_kv = a.st->n_kv;
     const int n_pad = (n_kv + 31) / 32 * 32;
     const int n_blocks = a.n_head_kv * ((n_pad + TK_SC_TILE - 1) / TK_SC_TILE);
     const int round_q = a.st->round_q;
@@ -137,7 +138,8 @@ __device__ __forceinline__ void scores_run(const AttnPhase & a, int cta, int n_c
             g_staged = g;
             __syncthreads();
         }
-        if (t == n_kv - 1) {                                   // this token's row: written by the QKV phase (plain loads)
+        const bool visible = attn_cell_visible(a.st, a.cell_pos, t, n_kv);
+        if (t == a.st->cell) {                                 // this token's row: written by the QKV phase (plain loads)
             const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
 #pragma unroll
             for (int e = 0; e < 8; e++) s.kv[e] = kr[e * 4];
@@ -187,7 +189,7 @@ __device__ __forceinline__ void scores_run(const AttnPhase & a, int cta, int n_c
                 for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);   // t3[4+i] + t3[i] (valid in c4 = 0)
                 const float res = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
                 if (c4 == 0)
-                    a.S[((size_t) (g * GQA + h) * 16 + (t & 15)) * a.rs + (t >> 4)] = t < n_kv ? __fmul_rn(res, a.scale) : -INFINITY;
+                    a.S[((size_t) (g * GQA + h) * 16 + (t & 15)) * a.rs + (t >> 4)] = visible ? __fmul_rn(res, a.scale) : -INFINITY;
             }
         }
     }
@@ -208,14 +210,14 @@ __device__ __forceinline__ void pv_stage_v(const AttnPhase & a, int g, int slice
     const int len = min(a.v_chunk, n_pad - t0);
     for (int i = threadIdx.x; i < len; i += TK_THREADS) {
         const int t = t0 + i;
-        if (t < n_kv - 1 || (cur_row_too && t == n_kv - 1)) cp_async16(&vs[i][0], vbase + (size_t) t * a.kv_dim);
+        if (t < n_kv && (cur_row_too || t != a.st->cell)) cp_async16(&vs[i][0], vbase + (size_t) t * a.kv_dim);
         else if (t >= n_kv) *reinterpret_cast<uint4 *>(&vs[i][0]) = make_uint4(0u, 0u, 0u, 0u);   // p == 0 there: the product must be 0, never NaN
     }
     cp_async_commit();
 }
 template <int GQA>
 __device__ __forceinline__ void pv_begin(const AttnPhase & a, int cta, uint8_t * dyn) {
-    const int n_kv = a.st->pos + 1;
+    const int n_kv = a.st->n_kv;
     const int n_pad = (n_kv + 31) / 32 * 32;
     if (cta >= a.n_head_kv * (128 / TK_PV_DIMS)) return;
     __half (*vs)[TK_PV_DIMS] = reinterpret_cast<__half (*)[TK_PV_DIMS]>(dyn + (size_t) GQA * 16 * a.rs * 4);
@@ -229,7 +231,7 @@ __device__ __forceinline__ void pv_run(const AttnPhase & a, int cta, int n_cta, 
     constexpr int NW = TH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = tid / TH, ht = tid % TH, w = ht >> 5;
-    const int n_kv = a.st->pos + 1;
+    const int n_kv = a.st->n_kv;
     const int n_pad = (n_kv + 31) / 32 * 32;
     const int n16 = n_pad / 16, rs = a.rs;
     float * ps = reinterpret_cast<float *>(dyn);
@@ -240,9 +242,9 @@ __device__ __forceinline__ void pv_run(const AttnPhase & a, int cta, int n_cta, 
         if (vb != cta) {
             __syncthreads();                                   // the previous block is done with ps / vs
             pv_stage_v(a, g, slice, 0, n_kv, n_pad, true, vs);
-        } else if (n_kv - 1 < a.v_chunk && tid == 0) {
+        } else if (a.st->cell < a.v_chunk && tid == 0) {
             // the first block's earlier rows were requested in pv_begin; this token's row is written by the QKV phase
-            cp_async16(&vs[n_kv - 1][0], a.v_cache + g * HD + slice * TK_PV_DIMS + (size_t) (n_kv - 1) * a.kv_dim);
+            cp_async16(&vs[a.st->cell][0], a.v_cache + g * HD + slice * TK_PV_DIMS + (size_t) a.st->cell * a.kv_dim);
         }
         // the GQA x 16 score rows of the KV head, n16 floats each (16-byte copies: the rows are padded to 4 floats)
         {

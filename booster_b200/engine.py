@@ -75,6 +75,14 @@ class Context:
         check(self.L.b200_kv_read(self.h, layer, pos0, n, k.ctypes.data_as(u16p), v.ctypes.data_as(u16p)), "b200_kv_read")
         return k.view(np.float16), v.view(np.float16)
 
+    def kv_seq_rm(self, p0: int, p1: int):
+        """llama_kv_cache_seq_rm(ctx, 0, p0, p1)"""
+        check(self.L.b200_kv_seq_rm(self.h, p0, p1), "b200_kv_seq_rm")
+
+    def kv_seq_add(self, p0: int, p1: int, delta: int):
+        """llama_kv_cache_seq_add(ctx, 0, p0, p1, delta); the K-shift runs inside the next decode"""
+        check(self.L.b200_kv_seq_add(self.h, p0, p1, delta), "b200_kv_seq_add")
+
     def decode(self, tokens: Sequence[int], pos0: int, want_logits: bool = True) -> Optional[np.ndarray]:
         """llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0)) then llama_get_logits (last token's row)."""
         toks = np.ascontiguousarray(tokens, dtype=np.int32)

@@ -67,6 +67,15 @@ void       b200_kv_clear(b200_ctx * c);               /* llama_kv_cache_clear (c
 int b200_kv_write(b200_ctx * c, int layer, int pos0, int n, const uint16_t * k_rows, const uint16_t * v_rows);
 int b200_kv_read(b200_ctx * c, int layer, int pos0, int n, uint16_t * k_rows, uint16_t * v_rows);
 
+/* Context shift: llama_kv_cache_seq_rm(ctx, 0, p0, p1) and llama_kv_cache_seq_add(ctx, 0, p0, p1, delta)
+ * (cpp/bridge.cpp:500-501; cpp/src/llama.cpp:3154-3206, 3268-3314). Cells keep their places, freed cells are re-used by the
+ * next tokens (llama_kv_cache_find_slot, :3028-3125), attention masks by the cells' positions, and the cached K rows of the
+ * moved cells are re-rotated by the accumulated delta at the next decode (build_k_shift, :8482-8510) — the same cell order
+ * and arithmetic as the reference, so logits stay bit-identical after a shift. Afterwards decode with b200_decode /
+ * b200_step_greedy / b200_stage_forward (the device-resident greedy loop and b200_kv_write need an unshifted cache). */
+int b200_kv_seq_rm(b200_ctx * c, int p0, int p1);
+int b200_kv_seq_add(b200_ctx * c, int p0, int p1, int delta);
+
 /* ---- the hot path ------------------------------------------------------------------------------------------
  * b200_decode == llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0))  (cpp/bridge.cpp:549-560,
  *                cpp/src/llama.cpp:18517 → llama_decode_internal :14537-14840) followed by

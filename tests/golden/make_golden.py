@@ -96,6 +96,20 @@ def make_ops():
     print("ops.npz written")
 
 
+def make_kvshift():
+    """tests/golden/kvshift_<model>.npz: logits of every step of tests/kvshift_script.py run by the reference (context shift:
+    llama_kv_cache_seq_rm / seq_add, K-shift inside the next llama_decode, freed cells re-used)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import kvshift_script
+    for model in ("tiny-gqa4_Q4_K_M", "tiny-gqa4-yarn_Q4_K_M"):
+        r = ref.RefModel(os.path.join(HERE, model + ".gguf"), n_ctx=64, n_threads=4)
+        prompt = [int(t) for t in np.random.default_rng(11).integers(0, 512, size=30)]
+        lg = kvshift_script.run(r, prompt)
+        np.savez_compressed(os.path.join(HERE, f"kvshift_{model}.npz"), prompt=np.array(prompt, dtype=np.int32), logits=lg)
+        print(f"kvshift_{model}.npz: {lg.shape[0]} steps")
+        r.close()
+
+
 def make_janus():
     """tests/golden/janus.json: token ids the reference's bridge loop generates with its own Janus sampler (unmodified
     cpp/janus.cpp through refshim_janus_generate) on tiny models with the padded synthetic vocabularies, for fixed seeds.
@@ -134,7 +148,11 @@ if __name__ == "__main__":
     if only == ["janus"]:
         make_janus()
         sys.exit(0)
+    if only == ["kvshift"]:
+        make_kvshift()
+        sys.exit(0)
     if not only:
         make_ops()
         make_janus()
+        make_kvshift()
     make_models(only)

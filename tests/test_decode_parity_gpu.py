@@ -151,6 +151,28 @@ def test_fullshape_decode_at_full_context_vs_port_bitwise(model_dir, cfg, ftype,
     c.close(); m.close()
 
 
+@pytest.mark.parametrize("model", ["tiny-gqa4_Q4_K_M", "tiny-gqa4-yarn_Q4_K_M"])
+def test_context_shift_bitwise_golden(golden_dir, model):
+    """llama_kv_cache_seq_rm + seq_add (cpp/bridge.cpp:487-507), the K-shift re-rotation of the cached K rows
+    (build_k_shift, cpp/src/llama.cpp:8482-8510) and the reference's cell bookkeeping (find_slot re-uses the freed cells in the
+    middle of the cache) — every logit of the scenario in tests/kvshift_script.py equals the reference's, bit for bit.
+    The YaRN model scales cos/sin by the attention factor, so its K-shift touches every cell (as the reference's does)."""
+    import kvshift_script
+    g = np.load(os.path.join(golden_dir, f"kvshift_{model}.npz"))
+    m = engine.Model(os.path.join(golden_dir, model + ".gguf"))
+    c = engine.Context(m, 64)
+    lg = kvshift_script.run(c, g["prompt"].tolist())
+    assert lg.shape == g["logits"].shape
+    for i in range(lg.shape[0]):
+        _same(lg[i], g["logits"][i], f"step {i}")
+    # the device-resident greedy loop addresses cells by position: refused after a shift instead of computing something else
+    with pytest.raises(engine.B200Error):
+        c.generate_greedy(1, 40, 2)
+    c.kv_clear()                                   # llama_kv_cache_clear: back to an unshifted cache
+    assert c.generate_greedy(1, 0, 2).shape == (2,)
+    c.close(); m.close()
+
+
 def test_device_greedy_equals_host_greedy_and_is_deterministic(model_dir):
     path = _synth(model_dir, "llama3-8b-2l", "Q4_K_M")
     m = engine.Model(path)
