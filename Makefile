@@ -16,7 +16,7 @@ $(OBJDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.cuh $(CSRC)/token_kernel.c
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(CSRC)/gguf.hpp $(CSRC)/tokenizer.hpp $(CSRC)/janus.hpp $(CSRC)/unicode_tables.hpp include/bridge.h include/booster_b200.h
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(ARCH) -O2 -std=c++17 -Xcompiler -fPIC,-Wall -c $< -o $@
+	$(NVCC) $(ARCH) -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-O3 -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -ldl

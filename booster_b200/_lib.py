@@ -22,7 +22,7 @@ B200_SYMBOLS = ["b200_last_error", "b200_device_count", "b200_version", "b200_mo
                 "b200_kv_clear", "b200_decode", "b200_generate_greedy", "b200_step_greedy", "b200_set_taps", "b200_get_tap",
                 "b200_timings", "b200_reset_timings", "b200_kernel_launches", "b200_last_device_ms", "b200_profile_token", "b200_profile_kind", "b200_trace_token", "b200_trace_phases", "b200_set_token_kernel", "b200_job_timing_us", "b200_comm_unique_id",
                 "b200_comm_init", "b200_pipeline_generate_greedy", "b200_pipeline_decode", "b200_stage_forward",
-                "b200_stage_logits", "b200_stage_argmax", "b200_stage_sync", "b200_kv_write", "b200_kv_read", "b200_kv_seq_rm", "b200_kv_seq_add", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
+                "b200_stage_logits", "b200_stage_argmax", "b200_stage_logits_view", "b200_decode_view", "b200_stage_sync", "b200_kv_write", "b200_kv_read", "b200_kv_seq_rm", "b200_kv_seq_add", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
                 "b200_op_dequantize_row", "b200_op_mul_mat_vec", "b200_op_rms_norm", "b200_op_rope",
                 "b200_op_attention", "b200_set_attention_route", "b200_tokenizer_load", "b200_tokenizer_free", "b200_tokenizer_n_vocab", "b200_tokenize",
                 "b200_token_to_piece", "b200_token_is_eog", "b200_cpt_class", "b200_op_launch_shape",
@@ -41,8 +41,11 @@ def lib() -> C.CDLL:
     vp, cp = C.c_void_p, C.c_char_p
 
     def sig(name, res, args):
-        fn = getattr(L, name)
-        fn.restype, fn.argtypes = res, args
+        # (an A/B library built from an older revision lacks the newest entry points: tests/test_cabi_surface.py is what
+        #  guarantees that the shipped library exports every symbol the headers declare)
+        fn = getattr(L, name, None)
+        if fn is not None:
+            fn.restype, fn.argtypes = res, args
 
     # include/bridge.h
     sig("init", None, [cp, cp])
@@ -97,6 +100,8 @@ def lib() -> C.CDLL:
     sig("b200_stage_logits", C.c_int, [vp, f32p])
     sig("b200_stage_argmax", C.c_int, [vp, i32p])
     sig("b200_stage_sync", C.c_int, [vp])
+    sig("b200_stage_logits_view", f32p, [vp])
+    sig("b200_decode_view", f32p, [vp, C.c_int32, C.c_int])
     sig("b200_kv_write", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)])
     sig("b200_kv_read", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)])
     sig("b200_op_quantize_q8_K", C.c_int, [f32p, C.c_int64, vp])

@@ -48,7 +48,6 @@ struct Pod {
     b200::JanusParams jparams;
     b200::StandardParams sparams;
     b200::JanusSampler janus;           // scales / types tables: initJanus, once per pod (the reference redoes it per job)
-    std::vector<float> logits;          // host copy of the last token's logits
     // contexts first, then the models they point into
     void release() {
         for (b200_ctx * c : stages) b200_ctx_free(c);
@@ -187,7 +186,6 @@ void * initContext(
     p.sparams.temp = temperature; p.sparams.top_k = top_k; p.sparams.top_p = top_p;
     p.sparams.penalty_repeat = repetition_penalty; p.sparams.penalty_last_n = penalty_last_n;
     if (janus != 0) p.janus.init(*p.tok, p.jparams, 0);
-    p.logits.resize((size_t) p.n_vocab);
     return (void *) &p;
 }
 
@@ -257,22 +255,22 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
     std::vector<int32_t> history(inp);                     // prompt + generated: the standard chain's penalty window
     int32_t id = 0;
     bool have_next = false;                                // device arg-max path: the next id came back with the decode
-    bool have_logits = false;                              // host path: p.logits holds the logits of the last decoded token
+    float * lg = nullptr;                                  // host path: the logits of the last decoded token (the engine's pinned buffer)
     while (n_remain != 0 && n_past < max_embd && !g_stop[idx].load()) {
         const double t0 = now_us();
         if (device_argmax) {
             if (!have_next) { if (b200_stage_argmax(last, &id) != 0) return 1; }
             have_next = false;
         } else {
-            if (!have_logits) { if (b200_stage_logits(last, p.logits.data()) != 0) return 1; }
-            have_logits = false;
+            if (!lg) { lg = b200_stage_logits_view(last); if (!lg) return 1; }
             if (use_janus) {
-                id = p.janus.sample(p.logits.data(), last_tokens, inp.size(), (size_t) n_past, (size_t) p.n_predict);
+                id = p.janus.sample(lg, last_tokens, inp.size(), (size_t) n_past, (size_t) p.n_predict);
                 last_tokens.erase(last_tokens.begin());    // cpp/bridge.cpp:602-603
                 last_tokens.push_back(id);
             } else {
-                id = std_sampler.sample(p.logits.data(), p.n_vocab, history);
+                id = std_sampler.sample(lg, p.n_vocab, history);
             }
+            lg = nullptr;
         }
         history.push_back(id);
         --n_remain;
@@ -295,8 +293,8 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
             if (b200_step_greedy(last, id, n_past, &next) != 0) return 1;
             id = next; have_next = true;
         } else if (single) {
-            if (b200_decode(last, &id, 1, n_past, p.logits.data()) != 0) return 1;   // one graph: state in, forward, logits out
-            have_logits = true;
+            lg = b200_decode_view(last, id, n_past);       // one graph: state in, forward, logits out (pinned, no second copy)
+            if (!lg) return 1;
         } else {
             if (run_token(p, id, n_past, 0) != 0) return 1;
         }

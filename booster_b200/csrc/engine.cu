@@ -18,6 +18,9 @@
 #include "gguf.hpp"
 #include "tokenizer.hpp"
 #include "kernels.cuh"
+#ifndef B200_TOKEN_KERNEL
+#define B200_TOKEN_KERNEL 1      // 0: build without the persistent per-token kernel (A/B: code size of the module)
+#endif
 #include "token_kernel.cuh"
 
 #include <algorithm>
@@ -906,6 +909,7 @@ static MatvecArgs args_head(b200_ctx * c) {
 // ------------------------------------------------------------------------------------------------------------
 // persistent per-token kernel (token_kernel.cuh): phase list of this stage, built once per context
 // ------------------------------------------------------------------------------------------------------------
+#if B200_TOKEN_KERNEL
 // shared memory the kernel's own __shared__ variables take (phase descriptors, attention scratch): the dynamic budget is
 // what is left of the 227 KB a CTA may have
 template <int GQA>
@@ -1024,6 +1028,12 @@ static void token_kernel_launch(b200_ctx * c) {
     c->launches++;
 }
 
+#else
+extern "C" void b200_set_token_kernel(int) {}
+static bool token_kernel_enabled() { return false; }
+static bool token_kernel_build(b200_ctx *) { return false; }
+template <int GQA> static void token_kernel_launch(b200_ctx *) { throw std::runtime_error("built without the per-token kernel"); }
+#endif
 // enqueue the layers of this stage (+ embedding on the first stage, + head on the last) for ONE token whose
 // scalars are in c->d_state
 static void enqueue_forward(b200_ctx * c) {
@@ -1931,6 +1941,24 @@ extern "C" int b200_stage_logits(b200_ctx * c, float * logits_out) {
         std::memcpy(logits_out, c->h_logits, (size_t) c->m->n_vocab * 4);
         return 0;
     } catch (const std::exception & e) { return set_err(e.what()); }
+}
+// the last stage's logits in the context's own pinned host buffer (valid until the next call on this context; the caller may
+// modify them — the bridge's sampler does, as the reference's sampler modifies llama_get_logits' buffer): no second copy
+extern "C" float * b200_stage_logits_view(b200_ctx * c) {
+    try {
+        require_gpu();
+        if (!c || !c->m->has_head()) throw std::runtime_error("not the last stage");
+        CU(cudaSetDevice(c->m->device));
+        CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t) c->m->n_vocab * 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        return c->h_logits;
+    } catch (const std::exception & e) { set_err(e.what()); return nullptr; }
+}
+// llama_decode of one token on a single-stage context + llama_get_logits, as ONE graph replay (state in, forward, logits out
+// to the pinned buffer) and one synchronisation; returns the pinned buffer (see b200_stage_logits_view)
+extern "C" float * b200_decode_view(b200_ctx * c, int32_t token, int pos) {
+    if (b200_decode(c, &token, 1, pos, nullptr) != 0) return nullptr;
+    return c->taps ? nullptr : c->h_logits;
 }
 extern "C" int b200_stage_argmax(b200_ctx * c, int32_t * token_out) {
     try {

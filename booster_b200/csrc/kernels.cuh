@@ -64,7 +64,7 @@ __host__ __device__ __forceinline__ int tile_bytes_of(int type) {
 }
 
 // per-token scalars, device-resident so that one CUDA graph serves every token
-struct DecodeState {
+struct alignas(16) DecodeState {
     int32_t token;     // input token id of this step
     int32_t pos;       // its position
     int32_t round_q;   // 1: batch > 1 arithmetic for K.q (q rounded to f16, ggml_vec_dot_f16 order)
@@ -397,7 +397,8 @@ __device__ __forceinline__ float rms_scale(double tot, int k, double inv_k, floa
 // barrier of the first `nwarp` warps of the CTA (a mat-vec phase of the persistent kernel may run on fewer warps than the
 // CTA has; barrier 15 is reserved for it, 1..8 are the K-split groups')
 __device__ __forceinline__ void sync_warps(int nwarp) { asm volatile("bar.sync 15, %0;" :: "r"(nwarp * 32) : "memory"); }
-template <bool TR, typename F>
+// WHOLE_CTA: every warp of the CTA takes part (the stand-alone kernels): the barrier is a plain __syncthreads()
+template <bool TR, bool WHOLE_CTA, typename F>
 __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, bool norm, float eps, int k, double inv_k, int act_q8_0,
                                                   const ActSmem & A, double * red, const float (&pre_w)[PRO_U][8], F after_loads,
                                                   int nwarp, unsigned long long * tr = nullptr) {
@@ -426,7 +427,7 @@ __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, 
             s = warp_sum_d(s);
             if (lane == 0) red[warp] = s;
             trace_mark<TR>(tr, 5);
-            sync_warps(nwarp);
+            if (WHOLE_CTA) __syncthreads(); else sync_warps(nwarp);
             double tot = 0.0;
             for (int w = 0; w < nwarp; w++) tot += red[w];
             scale = rms_scale(tot, k, inv_k, eps);
@@ -914,7 +915,7 @@ __device__ __forceinline__ void mv_run(const MatvecArgs & a, double * red_smem, 
     const bool norm = a.norm_w != nullptr;
     const int pos = EPI == EPI_QKV ? a.st->pos : 0;            // in flight during the prologue
     const int cell = EPI == EPI_QKV ? a.st->cell : 0;
-    prologue_quantize<TR>(a.x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, s.ww,
+    prologue_quantize<TR, false>(a.x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, s.ww,
                       [&]() {
 #pragma unroll 1
                           for (int st = n_prefilled; st < S - 1; st++) mv_issue_next(a, s, lane);
@@ -1047,25 +1048,233 @@ __device__ __forceinline__ void mv_run(const MatvecArgs & a, double * red_smem, 
     trace_mark<TR>(a.trace, 10);                                   // warp 0 out of work
 }
 
+// The stand-alone kernel keeps its own copy of the body (the one the round-1 measurements were made with): expressed through
+// mv_begin / mv_run it compiles to the same register count but measures 2.4 % slower per token on the same box
+// (548 -> 535 tok/s, gpurun_out/r2k) — ptxas schedules the monolithic body better than the state-struct version.
 template <bool TR>
 __global__ void __launch_bounds__(MV_MAX_WARPS * 32, 1) k_matvec(const __grid_constant__ MatvecArgs a) {
+    const int EPI = a.epi;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ double red_smem[MV_MAX_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int G = a.group, TU = a.tiles_unit, S = a.stages, KPW = a.kpw;
+    // shared memory: ring (128-byte aligned slots) | activations | hand-off buffers | mbarriers
+    uint8_t * ring = smem_raw + (size_t) warp * S * a.stage_bytes;
+    uint8_t * act_base = smem_raw + (size_t) W * S * a.stage_bytes;
+    const size_t act_bytes = a.act_bytes;
+    const ActSmem A = act_smem_carve(act_base, a.k, a.act_q8_0);
+    const int grp = (int) (((uint32_t) warp * a.grp_magic) >> 16), w = warp - grp * G;   // group inside the CTA, warp inside the group
+    const int NV = a.nv;
+    const int mode = a.chain_mode;
+    // chain region: exchange: cbuf[parity][warp of the CTA][value][lane] | fin[group][chain][lane]; hand-off: fin only
+    float * cbuf = reinterpret_cast<float *>(act_base + act_bytes);
+    float * fin  = cbuf + a.exch_words + (size_t) grp * HANDOFF_WORDS;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(act_base + act_bytes + a.chain_bytes);
+    const uint32_t full0   = smem_u32(bars + warp * S);                            // my ring slots' "tile landed" barriers
+    const uint32_t edge_in  = smem_u32(bars + W * S + warp);                        // hand-off: "chain state for me is published"
+    const uint32_t edge_out = smem_u32(bars + W * S + grp * G + (w + 1 == G ? 0 : w + 1));
+    const uint32_t ring_u32 = smem_u32(ring);
+    const int bar_id = 1 + grp, bar_threads = G * 32;                              // the group's named barrier
+
     trace_mark<TR>(a.trace, 0);
     pdl_launch_dependents();                                   // the next kernel may start its own weight prefetch
-    MvState s;
-    const int prefill = min(a.prefill, a.stages - 1);
-    mv_begin<TR>(a, smem_raw, (int) blockIdx.x, (int) gridDim.x, prefill, s);
+    if (lane == 0) {                                           // each warp: its own ring barriers and its edge barrier
+#pragma unroll 1
+        for (int s = 0; s < S; s++) mbar_init(full0 + 8 * s, 1);
+        mbar_init(edge_in, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();                                              // (the edge barriers of OTHER warps are first used after the
+                                                               //  prologue's __syncthreads)
+
+    // group-major mapping: unit u -> CTA u % grid, group (u / grid) % groups_per_cta, so that launches with few
+    // units spread over every SM
+    const int groups_per_cta = a.groups_per_cta;
+    const int group_global = grp * gridDim.x + blockIdx.x;
+    const int n_groups = gridDim.x * groups_per_cta;
+    const int my_units = group_global < a.n_units ? (a.n_units - group_global + n_groups - 1) / n_groups : 0;
+    const int n_items = my_units * KPW;
+
+    // ---- producer side: item pi = (unit pj, tile w + G*pk) goes to ring slot pi % S
+    int pi = 0, pj = 0, pk = 0, ps = 0;
+    UnitDesc pd = describe_unit(a, my_units > 0 ? group_global : 0);
+    // weight tiles are read exactly once per token: the copies carry the L2 evict-first hint, so streaming 4.6 GB of
+    // them per token does not push the activations, the K/V rows and the kernels' own code out of L2
+    const uint64_t pol = l2_policy_evict_first();
+    auto issue_next = [&]() {
+        if (pi >= n_items) return;
+        if (lane == 0) {
+            mbar_expect_tx(full0 + 8 * ps, pd.bytes);
+            bulk_g2s_hint(ring_u32 + (uint32_t) ps * a.stage_bytes, pd.tiles + (size_t) (w + G * pk) * pd.bytes, pd.bytes, full0 + 8 * ps, pol);
+        }
+        pi++; ps = ps + 1 == S ? 0 : ps + 1;
+        if (++pk == KPW) {
+            pk = 0; pj++;
+            if (pi < n_items) pd = describe_unit(a, group_global + pj * n_groups);
+        }
+    };
+    // weights do not depend on x: part of the ring is filled before the wait, the rest once the x loads are in flight
+    const int prefill = min(a.prefill, S - 1);
+#pragma unroll 1
+    for (int s = 0; s < prefill; s++) issue_next();
+    // norm weights are constants too: the warp's blocks (the host guarantees k/256 <= PRO_U * W when there is a norm)
+    const bool norm = a.norm_w != nullptr;
+    float ww[PRO_U][8] = {};
+    if (norm) {
+#pragma unroll
+        for (int u = 0; u < PRO_U; u++) {
+            const int b = warp + u * W;
+            if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, ww[u]);
+        }
+    }
+
     // L2 look-ahead for the kernels that follow (after this CTA's own first tiles are requested). DecodeState is
     // written by the previous TOKEN's last kernel, so pos may be read before the wait.
 #if B200_LOOKAHEAD
-    if ((threadIdx.x & 31) == 0 && a.pf[0].bytes)
-        issue_l2_lookahead(a.pf, (int) (threadIdx.x >> 5) * gridDim.x + blockIdx.x, a.warps * gridDim.x, a.st ? a.st->pos : 0);
+    if (lane == 0 && a.pf[0].bytes) issue_l2_lookahead(a.pf, warp * gridDim.x + blockIdx.x, W * gridDim.x, a.st ? a.st->pos : 0);
 #endif
+
     trace_mark<TR>(a.trace, 1);
     pdl_wait();                                                // x (and everything else the previous kernels wrote) is visible
     trace_mark<TR>(a.trace, 2);
-    mv_run<TR>(a, red_smem, prefill, s);
+    // (pos, ...) and (cell, ...) as two 16-byte loads of the DecodeState, in flight during the prologue
+    int pos = 0, cell = 0;
+    if (EPI == EPI_QKV) {
+        const int4 s0 = *reinterpret_cast<const int4 *>(a.st), s1 = *(reinterpret_cast<const int4 *>(a.st) + 1);
+        pos = s0.y; cell = s1.x;
+    }
+    prologue_quantize<TR, true>(a.x, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, ww,
+                      [&]() {
+#pragma unroll 1
+                          for (int s = prefill; s < S - 1; s++) issue_next();
+                      }, W, a.trace);
+    __syncthreads();                                           // activations + every warp's barrier inits are visible
+    trace_mark<TR>(a.trace, 3);
+
+    // ---- consumer side
+    int cs = 0, cpar = 0, rnd = 0, n_in = 0;
+    for (int j = 0; j < my_units; j++) {
+        const UnitDesc cd = describe_unit(a, group_global + j * n_groups);
+        auto unit_body = [&](auto tag) {
+            constexpr int TYPE = decltype(tag)::value;
+            constexpr int NCH = n_chains<TYPE>();
+            constexpr int CPW = 6;                             // chain slots per lane when G > 1: ceil(12 / 2)
+            float acc[12];                                     // G == 1: the row's chains; G > 1: [0, CPW) = chains w, w+G, ...
+#pragma unroll
+            for (int c = 0; c < 12; c++) acc[c] = 0.f;
+            // G > 1: slot i of this lane = chain w + i*G (value and multiplier offsets inside a tile's record)
+            int voff[6], moff[6], q5slot = -1;
+            const int cpw = G >= 12 ? 1 : G >= 6 ? 2 : G >= 4 ? 3 : 6;
+#pragma unroll
+            for (int i = 0; i < CPW; i++) {
+                const int c = w + i * G;
+                voff[i] = (c < NCH ? c : 0) * 32;
+                moff[i] = (c < 8 || c >= NCH ? NCH : NCH + 1) * 32;
+                if (TYPE == T_Q5_K && c == 8) q5slot = i;
+            }
+            for (int k = 0; k < KPW; k++) {
+                const int t = w + G * k;
+                issue_next();                                  // keeps S-1 tiles in flight (slot of the previous item is free)
+                // epilogue operands of a unit that completes with this tile: fetched now, used after the chain
+                float pre0 = 0.f, pre1 = 0.f;
+                if (t == TU - 1) {
+                    const int prow = cd.row0 + lane;
+                    if (EPI == EPI_RESID) pre0 = a.resid[prow];
+                    if (EPI == EPI_QKV && prow < a.n_q + a.n_k) {
+                        const float2 cs2 = a.rope[(size_t) pos * (a.head_dim / 2) + (((prow & ~1) & (a.head_dim - 1)) >> 1)];
+                        pre0 = cs2.x; pre1 = cs2.y;
+                    }
+                }
+                mbar_wait(full0 + 8 * cs, (uint32_t) cpar);
+                if (j == 0 && k == 0) trace_mark<TR>(a.trace, 7);  // first tile landed
+                BlockInts bi;
+                tile_ints<TYPE>(ring + (size_t) cs * a.stage_bytes, lane, t, A, bi);
+                __syncwarp();                                  // every lane is done reading the slot before it is refilled
+                if (j == 0 && k == 0) trace_mark<TR>(a.trace, 8);  // first tile's integers done
+                cs = cs + 1 == S ? 0 : cs + 1; if (cs == 0) cpar ^= 1;
+                float val;
+                if (mode != CHAIN_EXCHANGE) {
+                    if (mode == CHAIN_HANDOFF) {
+                        // the previous step of the group's tile sequence is done and its state published
+                        if (j > 0 || t > 0) { mbar_wait(edge_in, (uint32_t) (n_in & 1)); n_in++; }
+                        if (t > 0) {
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) acc[c] = fin[c * 32 + lane];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) acc[c] = 0.f;
+                        }
+                    }
+                    // ---- chain step in registers, strictly in block order
+#pragma unroll
+                    for (int c = 0; c < 8; c++) acc[c] = __fmaf_rn(bi.d, (float) bi.s[c], acc[c]);
+                    if (TYPE == T_Q4_K) {
+#pragma unroll
+                        for (int l = 0; l < 4; l++) acc[8 + l] = __fmaf_rn(bi.dmin, (float) bi.p[l], acc[8 + l]);
+                    } else if (TYPE == T_Q5_K) {
+                        acc[8] = __fadd_rn(acc[8], __fmul_rn(bi.dmin, (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3])));
+                    }
+                    if (mode == CHAIN_HANDOFF && !(j == my_units - 1 && t == TU - 1)) {
+                        if (t != TU - 1) {
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) fin[c * 32 + lane] = acc[c];
+                        }
+                        mbar_arrive(edge_out);                 // release: my lane's stores above are visible to the waiter
+                    }
+                    if (t != TU - 1) continue;
+                    val = finish_row<TYPE>(acc);
+                } else {
+                    // ---- publish this tile's integers (as exact floats) and scales
+                    float * cb = cbuf + ((size_t) ((rnd & 1) * W + warp) * NV) * 32 + lane;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) cb[c * 32] = (float) bi.s[c];
+                    if (TYPE == T_Q4_K) {
+#pragma unroll
+                        for (int l = 0; l < 4; l++) cb[(8 + l) * 32] = (float) bi.p[l];
+                    } else if (TYPE == T_Q5_K) {
+                        cb[8 * 32] = (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3]);
+                    }
+                    cb[NCH * 32] = bi.d;
+                    if (TYPE == T_Q4_K || TYPE == T_Q5_K) cb[(NCH + 1) * 32] = bi.dmin;
+                    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
+                    // ---- chain phase of the round: tiles t0 .. t0+G-1 in order, this lane's chains c = w + i*G
+                    const float * rb = cbuf + ((size_t) ((rnd & 1) * W + grp * G) * NV) * 32 + lane;
+                    rnd++;
+                    if (j == 0 && k == 0) trace_mark<TR>(a.trace, 9);   // first round: every warp's integers published
+                    switch (cpw) {
+                        case 1:  chain_round<1, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
+                        case 2:  chain_round<2, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
+                        case 3:  chain_round<3, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
+                        default: chain_round<6, TYPE == T_Q5_K>(rb, G, NV * 32, voff, moff, q5slot, acc); break;
+                    }
+                    if (j == 0 && k == 0) trace_mark<TR>(a.trace, 11);  // first round's chains advanced
+                    if (k != KPW - 1) continue;
+                    // ---- unit complete: gather the row's chains
+#pragma unroll
+                    for (int i = 0; i < CPW; i++) {
+                        const int c = w + i * G;
+                        if (c < NCH) fin[c * 32 + lane] = acc[i];
+                    }
+                    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
+                    if (w != G - 1) continue;                  // the warp that fetched the epilogue operands finishes the rows
+                    float cv[NCH];
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) cv[c] = fin[c * 32 + lane];
+                    val = finish_row<TYPE>(cv);
+                }
+
+                matvec_epilogue(a, val, cd.row0 + lane, lane, pre0, pre1, cell);
+            }
+        };
+        switch (cd.type) {
+            case T_Q4_K: unit_body(TypeTag<T_Q4_K>{}); break;
+            case T_Q5_K: unit_body(TypeTag<T_Q5_K>{}); break;
+            case T_Q6_K: unit_body(TypeTag<T_Q6_K>{}); break;
+            default:     unit_body(TypeTag<T_Q8_0>{}); break;
+        }
+    }
+    trace_mark<TR>(a.trace, 10);                                   // warp 0 out of work
     if (TR) { if (a.trace != nullptr) { __syncthreads(); trace_mark<TR>(a.trace, 4); } }
 }
 
@@ -1079,7 +1288,7 @@ __global__ void k_quantize_export(const float * __restrict__ x, int k, int act_q
     __shared__ double red_smem[MV_MAX_WARPS];
     const ActSmem A = act_smem_carve(smem_raw, k, act_q8_0);
     const float no_w[PRO_U][8] = {};
-    prologue_quantize<false>(x, false, 0.f, k, 0.0, act_q8_0, A, red_smem, no_w, []() {}, (int) (blockDim.x >> 5));
+    prologue_quantize<false, true>(x, false, 0.f, k, 0.0, act_q8_0, A, red_smem, no_w, []() {}, (int) (blockDim.x >> 5));
     __syncthreads();
     if (!act_q8_0) {
         const int nb = k / 256;
@@ -1235,7 +1444,10 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     __shared__ __align__(16) float qs[GQA][HD];
     const int g = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
     trace_mark<TR>(a.trace, 0);
-    const int n_kv = attn_n_kv(a);                            // DecodeState is written by the previous TOKEN's last kernel
+    // (cell, n_kv, managed) in ONE 16-byte load: DecodeState is written by the previous TOKEN's last kernel
+    int n_kv, cur, managed = 0;
+    if (a.n_kv_override > 0) { n_kv = a.n_kv_override; cur = n_kv - 1; }
+    else { const int4 s1 = *(reinterpret_cast<const int4 *>(a.st) + 1); cur = s1.x; n_kv = s1.y; managed = s1.z; }
     const int n_pad = (n_kv + 31) / 32 * 32;
     const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
     // K rows of EARLIER positions were written by earlier tokens: their loads go out before griddepcontrol.wait
@@ -1244,7 +1456,6 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
 #pragma unroll
     for (int s = 0; s < 8; s++) kv[s] = make_uint2(0u, 0u);
     const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
-    const int cur = attn_cur_cell(a, n_kv);
     if (t < n_kv && t != cur) {
 #pragma unroll
         for (int s = 0; s < 8; s++) kv[s] = __ldg(kr + s * 4);            // 4 halfs at element 16s + 4c4
@@ -1257,12 +1468,15 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     pdl_launch_dependents();                                  // AFTER the wait: the next kernel may touch K/V/q before ITS wait
     trace_mark<TR>(a.trace, 1);
     if (tile * ATT_TILE >= n_pad) return;
-    const int round_q = a.st ? a.st->round_q : a.round_q_override;
+    int round_q = a.round_q_override, pos = 0;
+    if (a.st) { const int4 s0 = *reinterpret_cast<const int4 *>(a.st); pos = s0.y; round_q = s0.z; }
     if (t == cur) {
 #pragma unroll
         for (int s = 0; s < 8; s++) kv[s] = kr[s * 4];                    // plain loads: written by the previous kernel
     }
-    const bool visible = attn_cell_visible(a.st, a.cell_pos, t, n_kv);
+    // the KQ mask (cpp/src/llama.cpp:14132-14200): without a context shift cell t holds position t and the test is t < n_kv
+    bool visible = t < n_kv;
+    if (managed && visible) { const int p = a.cell_pos[t]; visible = p >= 0 && p <= pos; }
     for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
         float v = a.q[(size_t) (g * GQA) * HD + i];
         if (round_q) v = __half2float(__float2half_rn(v));    // src1 converted to the vec_dot_type F16 (ggml.c:12345-12371)

@@ -164,6 +164,11 @@ int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batch_gt1, b200
 int b200_stage_sync(b200_ctx * c);    /* wait for everything enqueued on this stage (llama_synchronize, cpp/src/llama.cpp:18536) */
 int b200_stage_logits(b200_ctx * c, float * logits_out);
 int b200_stage_argmax(b200_ctx * c, int32_t * token_out);
+/* llama_get_logits without a second copy: the logits in the context's own pinned host buffer, valid (and writable — the
+ * sampler modifies them in place like the reference's, cpp/janus.cpp:224-283) until the next call on the context.
+ * b200_decode_view = llama_decode of one token on a single-stage context (one CUDA-graph replay) + that view. NULL on error. */
+float * b200_stage_logits_view(b200_ctx * c);
+float * b200_decode_view(b200_ctx * c, int32_t token, int pos);
 
 /* launch shape (warps per CTA, warps sharing a 32-row unit, ring stages per warp) the engine picks for a mat-vec whose
  * segments have the given block types: pure host arithmetic, exposed so that tests pin the shapes */
