@@ -223,8 +223,13 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
     while (consumed < inp.size() && !g_stop[idx].load()) {
         const size_t n = std::min((size_t) p.n_batch, inp.size() - consumed);
         const double t0 = now_us();
-        for (size_t i = 0; i < n; i++) {
-            if (run_token(p, inp[consumed + i], n_past + (int) i, n > 1 ? 1 : 0) != 0) return 1;   // llama_decode failed: bridge.cpp:556-558
+        if (p.stages.size() == 1) {
+            // one llama_decode of the chunk (cpp/bridge.cpp:549-560): the batched prompt kernels on a pod that sits on one GPU
+            if (b200_decode(last, inp.data() + consumed, (int) n, n_past, nullptr) != 0) return 1;
+        } else {
+            for (size_t i = 0; i < n; i++) {
+                if (run_token(p, inp[consumed + i], n_past + (int) i, n > 1 ? 1 : 0) != 0) return 1;   // llama_decode failed: bridge.cpp:556-558
+            }
         }
         // every chunk is a blocking llama_decode in the reference (cpp/bridge.cpp:549-560): synchronise the chain end so
         // that the chunk's time is the prompt's and not the first generated token's

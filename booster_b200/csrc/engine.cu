@@ -22,6 +22,7 @@
 #define B200_TOKEN_KERNEL 1      // 0: build without the persistent per-token kernel (A/B: code size of the module)
 #endif
 #include "token_kernel.cuh"
+#include "prefill.cuh"
 
 #include <algorithm>
 #include <array>
@@ -553,6 +554,13 @@ struct b200_ctx {
         bool has_shift = false;
     } cells;
     int32_t * d_cell_pos = nullptr;        // [n_ctx] device copy of cells.pos
+    // prompt batches (prefill.cuh): activations of up to pb_cap tokens, allocated at the first batch
+    struct PrefillBufs {
+        int cap = 0;
+        float * X = nullptr, * Q = nullptr, * ATT = nullptr, * FFH = nullptr, * S = nullptr;
+        uint8_t * rec = nullptr;
+        int32_t * tokens = nullptr;
+    } pb;
     // persistent per-token kernel (token_kernel.cuh): phase list in device memory, grid-barrier counter, transposed scores
     Phase * d_plan = nullptr;
     int n_phases = 0;
@@ -719,7 +727,9 @@ static void launch_matvec(b200_ctx * c, const MatvecArgs & a_in, int epi) {
 // two launches per layer: raw scores (k_attn_scores, every SM busy) then softmax + P.V (k_attn_softmax_pv); returns
 // false when the GQA score rows of the context do not fit the shared memory (the three-kernel route below takes over)
 template <int GQA>
-static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad) {
+// nz > 1: a prompt batch, token z of it in blockIdx.z (plain stream order then: the batch's own K / V rows come from the
+// kernel just before, and the scores kernel reads older rows ahead of its dependency wait)
+static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_pad, int nz = 1) {
     AttnArgs a = a_in;
     const size_t row_bytes = (size_t) GQA * n_ctx_pad * 4;
     const size_t budget = 200 * 1024;
@@ -742,15 +752,15 @@ static bool launch_attention_2k(b200_ctx * c, const AttnArgs & a_in, int n_ctx_p
     attr_lock.unlock();
     {
         g_kind = KIND_ATTN; ProfScope ps(c);
-        const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE));
-        a.trace = trace_slot(c, (int) (gs.x * gs.y));
-        launch_fwd(a.trace ? k_attn_scores<GQA, true> : k_attn_scores<GQA, false>, gs, dim3(ATT_THREADS), 0, c->st, a);
+        const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_ctx_pad + ATT_TILE - 1) / ATT_TILE), (unsigned) nz);
+        a.trace = nz == 1 ? trace_slot(c, (int) (gs.x * gs.y)) : nullptr;
+        launch_fwd(a.trace ? k_attn_scores<GQA, true> : k_attn_scores<GQA, false>, gs, dim3(ATT_THREADS), 0, c->st, a, nz == 1);
     }
     {
         g_kind = KIND_ATTN_PV; ProfScope ps(c);
-        const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVS_DIMS));
-        a.trace = trace_slot(c, (int) (gp.x * gp.y));
-        launch_fwd(a.trace ? k_attn_softmax_pv<GQA, true> : k_attn_softmax_pv<GQA, false>, gp, dim3((unsigned) (GQA * pvs_th(GQA))), smem, c->st, a);
+        const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVS_DIMS), (unsigned) nz);
+        a.trace = nz == 1 ? trace_slot(c, (int) (gp.x * gp.y)) : nullptr;
+        launch_fwd(a.trace ? k_attn_softmax_pv<GQA, true> : k_attn_softmax_pv<GQA, false>, gp, dim3((unsigned) (GQA * pvs_th(GQA))), smem, c->st, a, nz == 1);
     }
     c->launches += 2;
     return true;
@@ -1236,6 +1246,7 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     for (auto p : c->vc) cudaFree(p);
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->warm_x); cudaFree(c->logits);
     cudaFree(c->d_cell_pos);
+    cudaFree(c->pb.X); cudaFree(c->pb.Q); cudaFree(c->pb.ATT); cudaFree(c->pb.FFH); cudaFree(c->pb.S); cudaFree(c->pb.rec); cudaFree(c->pb.tokens);
     cudaFree(c->d_trace); cudaFree(c->d_plan); cudaFree(c->d_bar); cudaFree(c->S_T); cudaFree(c->d_ttrace);
     cudaFree(c->S); cudaFree(c->tickets); cudaFree(c->amax_key); cudaFree(c->rope); cudaFree(c->d_state); cudaFree(c->d_out_tokens);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_logits); cudaFreeHost(c->h_tok);
@@ -1499,6 +1510,136 @@ static double now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// prompt batches (prefill.cuh): llama_decode with n_tokens > 1 as batched kernels — every weight tile is fetched once per 64
+// tokens. Same arithmetic as the token-by-token path (same device functions), so the logits are bit-identical to it.
+// ------------------------------------------------------------------------------------------------------------
+static constexpr int PB_MAX_T = 512;               // tokens per pass (the reference's n_ubatch: cpp/common/common.h:81)
+static constexpr int PB_ATT_Z = 64;                // tokens per attention launch group (bounds the score buffer)
+static int g_prefill_batch = -1;       // 1: prompt batches run the batched kernels (default), 0: token by token (A/B, tests)
+extern "C" void b200_set_prefill_batch(int on) { g_prefill_batch = on ? 1 : 0; }
+static bool prefill_batch_enabled() {
+    if (g_prefill_batch < 0) { const char * e = getenv("BOOSTER_B200_PREFILL_BATCH"); g_prefill_batch = (e && e[0] == '0') ? 0 : 1; }
+    return g_prefill_batch == 1;
+}
+static bool prefill_batch_usable(const b200_ctx * c, int n) {
+    const b200_model & m = *c->m;
+    if (!prefill_batch_enabled() || n < 8 || c->taps || c->cells.managed || !m.has_embd() || !m.has_head() || m.head_dim != 128) return false;
+    const int gqa = m.n_head / m.n_head_kv;
+    if (gqa != 1 && gqa != 2 && gqa != 4 && gqa != 8) return false;
+    if ((size_t) gqa * c->n_ctx * 4 + (size_t) PV_BATCH * 16 > 200 * 1024) return false;   // the two-launch attention must fit
+    if (m.n_ff % 256 || m.n_embd % 256 || std::max(m.n_ff, m.n_embd) / 256 > 4 * 16 * 4) return false;
+    return true;
+}
+static void prefill_alloc(b200_ctx * c) {
+    if (c->pb.cap) return;
+    const b200_model & m = *c->m;
+    const int T = PB_MAX_T, QD = m.n_head * m.head_dim;
+    const size_t kmax = (size_t) std::max(std::max(m.n_ff, m.n_embd), QD);
+    CU(cudaMalloc(&c->pb.X, (size_t) T * m.n_embd * 4));
+    CU(cudaMalloc(&c->pb.Q, (size_t) T * QD * 4));
+    CU(cudaMalloc(&c->pb.ATT, (size_t) T * QD * 4));
+    CU(cudaMalloc(&c->pb.FFH, (size_t) T * m.n_ff * 4));
+    CU(cudaMalloc(&c->pb.S, (size_t) PB_ATT_Z * m.n_head * c->n_ctx * 4));
+    const size_t rec_bytes = (size_t) (T / PB_CHUNK) * (kmax / 256) * PB_CHUNK * pb_record_bytes(0, 1);
+    CU(cudaMalloc(&c->pb.rec, rec_bytes));
+    CU(cudaMemset(c->pb.rec, 0, rec_bytes));       // records of tokens beyond a partial last chunk are read (and discarded)
+    CU(cudaMalloc(&c->pb.tokens, (size_t) T * 4));
+    c->pb.cap = T;
+}
+static bool has_q6k(const TMat * seg, int n_seg) { for (int i = 0; i < n_seg; i++) if (seg[i].type == T_Q6_K) return true; return false; }
+static void pb_quant(b200_ctx * c, const float * X, int k, int T, const float * norm_w, int act_q8_0, int with_as) {
+    QuantBatchArgs a{};
+    a.X = X; a.k = k; a.T = T; a.norm_w = norm_w; a.eps = c->m->rms_eps; a.inv_k = (k & (k - 1)) == 0 ? 1.0 / (double) k : 0.0;
+    a.act_q8_0 = act_q8_0; a.with_as = with_as; a.rec = c->pb.rec;
+    const size_t smem = act_smem_bytes(k, act_q8_0);
+    static size_t attr[64] = {0};
+    if (smem > 48 * 1024 && smem > attr[c->device & 63]) {
+        std::lock_guard<std::mutex> lk(g_attr_mu);
+        CU(cudaFuncSetAttribute(k_quant_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr[c->device & 63] = smem;
+    }
+    if (norm_w && k / 256 > PRO_U * 16) throw std::runtime_error("normed vector too long for the batched quantizer");
+    k_quant_batch<<<(unsigned) T, 512, smem, c->st>>>(a);
+    c->launches++;
+}
+static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int pos0, float * out, int out_stride, const float * resid, int with_as) {
+    MatmulBatchArgs a{};
+    for (int i = 0; i < mv.n_seg; i++) a.seg[i] = mv.seg[i];
+    a.n_seg = mv.n_seg; a.n_units = mv.n_units; a.k = mv.k; a.tiles_unit = mv.seg[0].tiles_unit;
+    a.act_q8_0 = mv.act_q8_0; a.with_as = with_as; a.rec = c->pb.rec; a.T = T; a.epi = epi;
+    a.out = out; a.out_stride = out_stride; a.resid = resid; a.resid_stride = out_stride;
+    a.q_out = c->pb.Q; a.q_stride = mv.n_q; a.k_cache = mv.k_cache; a.v_cache = mv.v_cache;
+    a.n_q = mv.n_q; a.n_k = mv.n_k; a.head_dim = mv.head_dim; a.kv_dim = mv.kv_dim; a.rope = mv.rope; a.pos0 = pos0;
+    int sb = 0;
+    for (int i = 0; i < mv.n_seg; i++) sb = std::max(sb, tile_bytes_of(mv.seg[i].type));
+    const size_t smem = PB_STAGES * pb_stage_bytes(sb, a.act_q8_0, with_as);
+    static size_t attr[64] = {0};
+    if (smem > attr[c->device & 63]) {
+        std::lock_guard<std::mutex> lk(g_attr_mu);
+        CU(cudaFuncSetAttribute(k_matmul_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr[c->device & 63] = smem;
+    }
+    const dim3 grid((unsigned) ((T + PB_CHUNK - 1) / PB_CHUNK), (unsigned) a.n_units);
+    k_matmul_batch<<<grid, PB_WARPS * 32, smem, c->st>>>(a, sb);
+    c->launches++;
+}
+template <int GQA>
+static void pb_attention(b200_ctx * c, int li, int T, int pos0) {
+    const b200_model & m = *c->m;
+    const int HD = m.head_dim, KVD = m.n_head_kv * HD, QD = m.n_head * HD;
+    for (int z0 = 0; z0 < T; z0 += PB_ATT_Z) {
+        const int nz = std::min(PB_ATT_Z, T - z0);
+        AttnArgs a{};
+        a.q = c->pb.Q + (size_t) z0 * QD; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
+        a.S = c->pb.S; a.s_stride = c->n_ctx; a.out = c->pb.ATT + (size_t) z0 * QD;
+        a.n_head = m.n_head; a.n_head_kv = m.n_head_kv; a.head_dim = HD; a.kv_dim = KVD;
+        a.scale = 1.0f / sqrtf((float) HD);
+        a.st = nullptr; a.n_kv_override = pos0 + z0 + 1; a.round_q_override = 1; a.cell_pos = nullptr;   // batch > 1: q rounded to f16
+        a.zq = QD; a.zs = m.n_head * c->n_ctx;
+        const int n_pad_max = (pos0 + z0 + nz + 31) / 32 * 32;
+        if (!launch_attention_2k<GQA>(c, a, std::min(n_pad_max, c->n_ctx), nz)) throw std::runtime_error("batched attention does not fit");
+    }
+}
+// tokens[0..n) at positions pos0..: the whole prompt batch through every layer; leaves the LAST token's residual stream in c->x
+static void prefill_batch(b200_ctx * c, const int32_t * tokens, int n, int pos0) {
+    b200_model & m = *c->m;
+    prefill_alloc(c);
+    const int E = m.n_embd, FF = m.n_ff, QD = m.n_head * m.head_dim;
+    for (int t0 = 0; t0 < n; t0 += PB_MAX_T) {
+        const int T = std::min(PB_MAX_T, n - t0), p0 = pos0 + t0;
+        CU(cudaMemcpyAsync(c->pb.tokens, tokens + t0, (size_t) T * 4, cudaMemcpyHostToDevice, c->st));
+        k_embed_batch<<<dim3((unsigned) ((E + 255) / 256), (unsigned) T), 256, 0, c->st>>>(m.embd_type, m.embd_rows, m.embd_row_bytes, E, c->pb.tokens, c->pb.X);
+        c->launches++;
+        for (int li = 0; li < (int) m.layers.size(); li++) {
+            LayerW & L = m.layers[(size_t) li];
+            const int q80 = L.qkv.seg[0].type == T_Q8_0;
+            const MatvecArgs aq = args_qkv(c, li), ao = args_wo(c, li), ag = args_gateup(c, li), ad = args_down(c, li);
+            int was = has_q6k(aq.seg, aq.n_seg);
+            pb_quant(c, c->pb.X, E, T, L.attn_norm, q80, was);
+            pb_matmul(c, aq, EPI_QKV, T, p0, nullptr, 0, nullptr, was);
+            switch (m.n_head / m.n_head_kv) {
+                case 1: pb_attention<1>(c, li, T, p0); break;
+                case 2: pb_attention<2>(c, li, T, p0); break;
+                case 4: pb_attention<4>(c, li, T, p0); break;
+                default: pb_attention<8>(c, li, T, p0); break;
+            }
+            was = has_q6k(ao.seg, 1);
+            pb_quant(c, c->pb.ATT, QD, T, nullptr, q80, was);
+            pb_matmul(c, ao, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
+            was = has_q6k(ag.seg, 1);
+            pb_quant(c, c->pb.X, E, T, L.ffn_norm, q80, was);
+            pb_matmul(c, ag, EPI_SILU, T, p0, c->pb.FFH, FF, nullptr, was);
+            was = has_q6k(ad.seg, 1);
+            pb_quant(c, c->pb.FFH, FF, T, nullptr, q80, was);
+            pb_matmul(c, ad, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
+        }
+        CU(cudaGetLastError());
+    }
+    const int last = (n - 1) % PB_MAX_T;
+    CU(cudaMemcpyAsync(c->x, c->pb.X + (size_t) last * E, (size_t) E * 4, cudaMemcpyDeviceToDevice, c->st));
+}
+
 extern "C" int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, float * logits_out) {
     try {
         require_gpu();
@@ -1511,6 +1652,19 @@ extern "C" int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0
         const double t0 = now_us();
         // reference semantics for batch > 1: q is rounded to f16 before K.q (cpp/ggml/src/ggml.c:12345-12371)
         const int round_q = n > 1 ? 1 : 0;
+        if (prefill_batch_usable(c, n)) {
+            // the prompt batch through the batched kernels, then the head on the last token's residual stream
+            note_positions(c, pos0 + n);
+            prefill_batch(c, tokens, n, pos0);
+            g_only_kind = KIND_HEAD;
+            try { enqueue_forward(c); } catch (...) { g_only_kind = -1; throw; }
+            g_only_kind = -1;
+            if (logits_out) CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t) m.n_vocab * 4, cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            if (logits_out) std::memcpy(logits_out, c->h_logits, (size_t) m.n_vocab * 4);
+            c->t_prompt_us += now_us() - t0; c->n_prompt += n;
+            return 0;
+        }
         const BatchPlace place = place_batch(c, pos0, n);
         note_positions(c, pos0 + n);
         for (int i = 0; i < n; i++) {

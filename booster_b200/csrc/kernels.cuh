@@ -1424,9 +1424,12 @@ struct AttnArgs {
     PfRange pf[PF_RANGES];    // L2 look-ahead issued by k_attn_scores
     PfRange pf2[PF_RANGES];   // ... and by k_attn_softmax_pv
     const int32_t * cell_pos; // [n_ctx] position held by each KV cell (-1: empty); read only when st->managed
+    // prompt batches: blockIdx.z = token of the batch; token z uses q + z*zq, S + z*zs, out + z*zq and attends
+    // n_kv_override + z cells (its own position included). All zero for a single token.
+    int zq, zs;
     unsigned long long * trace;
 };
-__device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override : a.st->n_kv; }
+__device__ __forceinline__ int attn_n_kv(const AttnArgs & a) { return a.n_kv_override > 0 ? a.n_kv_override + (int) blockIdx.z : a.st->n_kv; }
 // the cell this token's K / V rows were just written to (by the QKV kernel; every other cell is older)
 __device__ __forceinline__ int attn_cur_cell(const AttnArgs & a, int n_kv) { return a.n_kv_override > 0 ? n_kv - 1 : a.st->cell; }
 // the KQ mask (cpp/src/llama.cpp:14132-14200): cell t is attended iff it holds a position of the sequence that is <= the
@@ -1446,7 +1449,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     trace_mark<TR>(a.trace, 0);
     // (cell, n_kv, managed) in ONE 16-byte load: DecodeState is written by the previous TOKEN's last kernel
     int n_kv, cur, managed = 0;
-    if (a.n_kv_override > 0) { n_kv = a.n_kv_override; cur = n_kv - 1; }
+    if (a.n_kv_override > 0) { n_kv = a.n_kv_override + (int) blockIdx.z; cur = n_kv - 1; }
     else { const int4 s1 = *(reinterpret_cast<const int4 *>(a.st) + 1); cur = s1.x; n_kv = s1.y; managed = s1.z; }
     const int n_pad = (n_kv + 31) / 32 * 32;
     const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
@@ -1478,7 +1481,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
     bool visible = t < n_kv;
     if (managed && visible) { const int p = a.cell_pos[t]; visible = p >= 0 && p <= pos; }
     for (int i = tid; i < GQA * HD; i += ATT_THREADS) {
-        float v = a.q[(size_t) (g * GQA) * HD + i];
+        float v = a.q[(size_t) blockIdx.z * a.zq + (size_t) (g * GQA) * HD + i];
         if (round_q) v = __half2float(__float2half_rn(v));    // src1 converted to the vec_dot_type F16 (ggml.c:12345-12371)
         (&qs[0][0])[i] = v;
     }
@@ -1526,7 +1529,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_scores(const AttnArgs a) {
 #pragma unroll
             for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);   // t3[4+i] + t3[i] (valid in c4 = 0)
             const float res = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
-            if (c4 == 0) a.S[(size_t) (g * GQA + h) * a.s_stride + t] = visible ? __fmul_rn(res, a.scale) : -INFINITY;
+            if (c4 == 0) a.S[(size_t) blockIdx.z * a.zs + (size_t) (g * GQA + h) * a.s_stride + t] = visible ? __fmul_rn(res, a.scale) : -INFINITY;
         }
     }
     trace_mark<TR>(a.trace, 2);
@@ -1683,7 +1686,7 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
     trace_mark<TR>(a.trace, 1);
     float * row = ps + (size_t) h * n_pad;
     {
-        const float * Sg = a.S + (size_t) (g * GQA + h) * a.s_stride;
+        const float * Sg = a.S + (size_t) blockIdx.z * a.zs + (size_t) (g * GQA + h) * a.s_stride;
         for (int i = ht; i < n_pad / 4; i += TH) cp_async16(row + 4 * i, Sg + 4 * i);
         cp_async_commit();
         cp_async_wait<0>();                                    // (also completes this thread's V copies)
@@ -1789,7 +1792,7 @@ __global__ void __launch_bounds__(GQA * pvs_th(GQA)) k_attn_softmax_pv(const Att
         for (int j = 0; j < 8; j++) t3[j] = __fadd_rn(red[hh][8 + j][dd], red[hh][j][dd]);
 #pragma unroll
         for (int j = 0; j < 4; j++) t6[j] = __fadd_rn(t3[4 + j], t3[j]);
-        a.out[(size_t) (g * GQA + hh) * HD + slice * PVS_DIMS + dd] =
+        a.out[(size_t) blockIdx.z * a.zq + (size_t) (g * GQA + hh) * HD + slice * PVS_DIMS + dd] =
             __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));     // kqv_merged_cont layout: [n_head*hd]
     }
 }

@@ -264,6 +264,11 @@ def set_token_kernel(on: bool) -> None:
     _lib.lib().b200_set_token_kernel(int(on))
 
 
+def set_prefill_batch(on: bool) -> None:
+    """prompt batches through the batched kernels (True, default) or token by token (False)"""
+    _lib.lib().b200_set_prefill_batch(int(on))
+
+
 def set_attention_route(route: int) -> None:
     """0: automatic (cluster kernel when it fits), 1: always the long-context three-kernel route"""
     _lib.lib().b200_set_attention_route(route)

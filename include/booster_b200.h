@@ -123,6 +123,10 @@ int     b200_profile_kind(b200_ctx * c, int kind, int pos, int reps, float * ms_
 int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int reps, uint64_t * out, int64_t cap_words,
                          int32_t * meta, int64_t cap_meta);
 
+/* Prompt batches (b200_decode with n >= 8 on a single-stage context): 1 (default) = the batched kernels of prefill.cuh (every
+ * weight tile fetched once per 64 tokens), 0 = token by token through the decode kernels. Same arithmetic, bit-identical
+ * logits; the switch exists for A/B measurements and for the test that compares the two. Env BOOSTER_B200_PREFILL_BATCH=0. */
+void b200_set_prefill_batch(int on);
 /* Decode path of contexts created AFTER the call: 0 (default) = one kernel per operator joined by programmatic dependent
  * launch, 1 = ONE persistent kernel per token (token_kernel.cuh: phase list + grid barriers; same arithmetic, bit-identical
  * results; measured slower on B200, kept selectable: DESIGN.md §4). Env BOOSTER_B200_TOKEN_KERNEL=1 sets the initial value. */

@@ -173,6 +173,40 @@ def test_context_shift_bitwise_golden(golden_dir, model):
     c.close(); m.close()
 
 
+@pytest.mark.parametrize("cfg,ftype,n_prompt", [("llama3-8b-2l", "Q4_K_M", 200), ("llama3-8b-2l", "Q8_0", 130), ("llama3-8b-2l", "Q5_K_M", 70),
+                                                ("llama3-70b-1l", "Q4_K_M", 65), ("tiny-gqa4", "Q4_K_M", 450)])
+def test_prompt_batch_kernels_equal_token_by_token_bitwise(model_dir, cfg, ftype, n_prompt):
+    """a prompt batch through the batched kernels (prefill.cuh: weight tiles fetched once per 64 tokens,
+    attention with the token in blockIdx.z) gives the logits AND the KV cache of the token-by-token path, bit for bit —
+    partial last chunks of 64, two passes of 512 for the long prompt, every block type, GQA 4 and 8, then decode continues
+    on the cache the batch wrote."""
+    path = _synth(model_dir, cfg, ftype)
+    conf = G.CONFIGS[cfg]
+    prompt = np.random.default_rng(n_prompt).integers(0, conf.n_vocab, size=n_prompt).tolist()
+    m = engine.Model(path)
+    out = {}
+    for batch in (False, True):
+        engine.set_prefill_batch(batch)
+        try:
+            c = engine.Context(m, 512)
+            l0 = c.kernel_launches()
+            lg = [c.decode(prompt, 0)]
+            n_launch = c.kernel_launches() - l0
+            lg.append(c.decode([int(np.argmax(lg[0]))], n_prompt))
+            lg.append(c.decode([7, 8, 9, 10, 11, 12, 13, 14, 15], n_prompt + 1))     # a second, short batch on top
+            kv = [c.kv_read(il, 0, n_prompt + 10) for il in range(conf.n_layer)]
+            out[batch] = (lg, kv, n_launch)
+            c.close()
+        finally:
+            engine.set_prefill_batch(True)
+    assert out[True][2] < out[False][2] / 4, "the batched kernels were not used"
+    for a, b in zip(out[True][0], out[False][0]):
+        _same(a, b, "logits")
+    for (ka, va), (kb, vb) in zip(out[True][1], out[False][1]):
+        assert np.array_equal(ka.view(np.uint16), kb.view(np.uint16)) and np.array_equal(va.view(np.uint16), vb.view(np.uint16))
+    m.close()
+
+
 def test_device_greedy_equals_host_greedy_and_is_deterministic(model_dir):
     path = _synth(model_dir, "llama3-8b-2l", "Q4_K_M")
     m = engine.Model(path)
