@@ -270,8 +270,15 @@ def main():
     lb, le = pipeline.stage_range(cfg.n_layer, rank, world)
     m = engine.Model(path, device=local_rank, layer_begin=lb, layer_end=le)
     c = engine.Context(m, ctx)
+    handoff = "single GPU"
     if world > 1:
         c.comm_init(rank, world, pipeline.share_unique_id(dist, engine.comm_unique_id))
+        handoff = "ncclSend/ncclRecv per stage boundary"
+        if os.environ.get("BOOSTER_B200_P2P", "1") != "0":
+            # direct NVLink stores into the next stage's inbox (CUDA IPC) instead of NCCL point-to-point
+            nxt, first = pipeline.exchange_inbox_handles(dist, c.p2p_handle())
+            c.p2p_connect(rank, world, nxt, first)
+            handoff = "peer stores over NVLink into the next stage's inbox (CUDA IPC) + sequence flag, per stage boundary"
     gen = (lambda tok, pos, n: c.pipeline_generate_greedy(tok, pos, n)) if world > 1 else (lambda tok, pos, n: c.generate_greedy(tok, pos, n))
 
     def sync_all():
@@ -312,7 +319,7 @@ def main():
             return gen(tok, pos0, burst)
 
     config = {"workload": workload, "name": args.config, "n_layer": cfg.n_layer, "n_embd": cfg.n_embd, "n_vocab": cfg.n_vocab,
-              "ctx": ctx, "burst": burst, "parallelism": f"layer-split pp{world}" if world > 1 else "single GPU",
+              "ctx": ctx, "burst": burst, "parallelism": f"layer-split pp{world}" if world > 1 else "single GPU", "hand_off": handoff,
               "l2": f"inputs larger than L2 ({m.weight_bytes / 1e9:.1f} GB of weights streamed per token on this rank vs 126 MB L2)"}
     for _ in range(args.warmup):
         one_step()

@@ -571,6 +571,13 @@ struct b200_ctx {
     unsigned long long * d_ttrace = nullptr;   // b200_trace_phases
     bool ttracing = false;
     // pipeline
+    // direct NVLink hand-off between the stage processes (b200_p2p_*): this rank's inbox (device memory, exported through CUDA
+    // IPC), the next rank's inbox and rank 0's inbox mapped into this process, and the per-direction message counters
+    struct P2PInbox * inbox = nullptr;          // mine
+    struct P2PInbox * next_inbox = nullptr;     // rank + 1's (x hand-off)
+    struct P2PInbox * first_inbox = nullptr;    // rank 0's (token hand-back; only on the last rank)
+    unsigned long long * p2p_counts = nullptr;  // device: [0] x sent, [1] x received, [2] tokens sent, [3] tokens received
+    bool p2p = false;
     void * comm = nullptr;
     int rank = 0, world = 1;
     cudaEvent_t ev_done = nullptr;     // in-process stage chain hand-off: this stage's l_out is complete
@@ -1242,6 +1249,9 @@ extern "C" void b200_ctx_free(b200_ctx * c) {
     if (c->g_greedy) cudaGraphExecDestroy(c->g_greedy);
     if (c->g_pipe)   cudaGraphExecDestroy(c->g_pipe);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->next_inbox) cudaIpcCloseMemHandle(c->next_inbox);
+    if (c->first_inbox) cudaIpcCloseMemHandle(c->first_inbox);
+    cudaFree(c->inbox); cudaFree(c->p2p_counts);
     for (auto p : c->kc) cudaFree(p);
     for (auto p : c->vc) cudaFree(p);
     cudaFree(c->x); cudaFree(c->q); cudaFree(c->att); cudaFree(c->ffh); cudaFree(c->warm_x); cudaFree(c->logits);
@@ -1933,10 +1943,134 @@ extern "C" int b200_comm_init(b200_ctx * c, int rank, int world, const uint8_t i
     } catch (const std::exception & e) { return set_err(e.what()); }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// direct peer hand-off (replaces the ncclSend / ncclRecv pair of a stage boundary, which costs ~20 us of launch + proxy
+// latency for a 16 KiB message that NVLink moves in well under a microsecond): the producer's last step is a small kernel
+// that STORES the residual stream into the consumer's inbox over NVLink and then publishes a sequence number
+// (st.release.sys); the consumer's first step spins on that number (ld.acquire.sys) and copies the vector out.
+// The inboxes are device allocations exported through CUDA IPC (one process per GPU). Message i of a direction carries
+// sequence number i: both ends count in device memory, so the kernels are captured once into the stage's CUDA graph.
+// ------------------------------------------------------------------------------------------------------------
+static constexpr int P2P_MAX_EMBD = 16384;
+struct P2PInbox {
+    float x[P2P_MAX_EMBD];
+    unsigned long long seq_x;           // number of residual vectors delivered
+    unsigned long long seq_tok;         // number of tokens delivered
+    int32_t token;
+    int32_t pad_[3];
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long * p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long * p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __noinline__ void p2p_timeout(const char * what, unsigned long long have, unsigned long long want) {
+    printf("booster_b200: peer hand-off timeout waiting for %s: have %llu want %llu\n", what, have, want);
+    __trap();
+}
+__device__ __forceinline__ void p2p_spin(const unsigned long long * seq, unsigned long long want, const char * what) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+    while (ld_acquire_sys_u64(seq) < want) {
+        if ((++spins & 4095u) == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 30000000000ull) p2p_timeout(what, ld_acquire_sys_u64(seq), want);     // 30 s: a peer died
+        }
+    }
+}
+__global__ void k_p2p_send_x(const float * __restrict__ x, int n, P2PInbox * peer, unsigned long long * counts) {
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) reinterpret_cast<float4 *>(peer->x)[i] = reinterpret_cast<const float4 *>(x)[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { const unsigned long long s = ++counts[0]; st_release_sys_u64(&peer->seq_x, s); }
+}
+__global__ void k_p2p_recv_x(float * __restrict__ x, int n, const P2PInbox * mine, unsigned long long * counts) {
+    __shared__ unsigned long long want;
+    if (threadIdx.x == 0) { want = ++counts[1]; p2p_spin(&mine->seq_x, want, "the residual stream"); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) reinterpret_cast<float4 *>(x)[i] = reinterpret_cast<const float4 *>(mine->x)[i];
+}
+__global__ void k_p2p_send_token(const DecodeState * st, P2PInbox * peer, unsigned long long * counts) {
+    if (threadIdx.x != 0) return;
+    peer->token = st->token;
+    __threadfence_system();
+    const unsigned long long s = ++counts[2];
+    st_release_sys_u64(&peer->seq_tok, s);
+}
+__global__ void k_p2p_recv_token(DecodeState * st, const P2PInbox * mine, unsigned long long * counts) {
+    if (threadIdx.x != 0) return;
+    const unsigned long long want = ++counts[3];
+    p2p_spin(&mine->seq_tok, want, "the sampled token");
+    st->token = *reinterpret_cast<const volatile int32_t *>(&mine->token);
+}
+
+// this rank's inbox as a 64-byte CUDA IPC handle (allocates it on first use)
+extern "C" int b200_p2p_handle(b200_ctx * c, uint8_t handle[64]) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        if (c->m->n_embd > P2P_MAX_EMBD || c->m->n_embd % 4) throw std::runtime_error("n_embd not supported by the peer hand-off");
+        CU(cudaSetDevice(c->m->device));
+        if (!c->inbox) {
+            CU(cudaMalloc(&c->inbox, sizeof(P2PInbox)));
+            CU(cudaMemset(c->inbox, 0, sizeof(P2PInbox)));
+            CU(cudaMalloc(&c->p2p_counts, 4 * sizeof(unsigned long long)));
+            CU(cudaMemset(c->p2p_counts, 0, 4 * sizeof(unsigned long long)));
+        }
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, c->inbox));
+        std::memcpy(handle, &h, 64);
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+// map the inboxes this rank writes to: rank + 1's (next_handle; ignored on the last rank) and rank 0's (first_handle; used by
+// the last rank only). After this call b200_pipeline_* hands off over NVLink stores instead of NCCL.
+extern "C" int b200_p2p_connect(b200_ctx * c, int rank, int world, const uint8_t next_handle[64], const uint8_t first_handle[64]) {
+    try {
+        require_gpu();
+        if (!c || !c->inbox) throw std::runtime_error("b200_p2p_handle must be called first");
+        CU(cudaSetDevice(c->m->device));
+        c->rank = rank; c->world = world;
+        auto open = [&](const uint8_t * hb) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, hb, 64);
+            void * p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            return (P2PInbox *) p;
+        };
+        if (rank + 1 < world) c->next_inbox = open(next_handle);
+        if (rank == world - 1 && world > 1) c->first_inbox = open(first_handle);
+        c->p2p = true;
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
 // one token through this rank's stage: [recv x] -> forward -> [send x] ; last stage: argmax -> token to stage 0
 static void enqueue_stage_step(b200_ctx * c, bool greedy) {
     b200_model & m = *c->m;
     const bool first = c->rank == 0, last = c->rank == c->world - 1;
+    if (c->p2p) {
+        if (!first) { k_p2p_recv_x<<<1, 256, 0, c->st>>>(c->x, m.n_embd, c->inbox, c->p2p_counts); c->launches++; }
+        enqueue_forward(c);
+        if (!last) { k_p2p_send_x<<<1, 256, 0, c->st>>>(c->x, m.n_embd, c->next_inbox, c->p2p_counts); c->launches++; }
+        if (greedy) {
+            if (last) {
+                enqueue_argmax(c, 1);
+                if (c->world > 1) { k_p2p_send_token<<<1, 32, 0, c->st>>>(c->d_state, c->first_inbox, c->p2p_counts); c->launches++; }
+            } else {
+                k_advance<<<1, 32, 0, c->st>>>(c->d_state);
+                if (first) { k_p2p_recv_token<<<1, 32, 0, c->st>>>(c->d_state, c->inbox, c->p2p_counts); c->launches++; }
+            }
+            c->launches++;
+        }
+        CU(cudaGetLastError());
+        return;
+    }
     if (!first) NC(g_nccl.Recv(c->x, (size_t) m.n_embd, NCCL_FLOAT32, c->rank - 1, c->comm, c->st));
     enqueue_forward(c);
     if (!last) NC(g_nccl.Send(c->x, (size_t) m.n_embd, NCCL_FLOAT32, c->rank + 1, c->comm, c->st));

@@ -176,6 +176,17 @@ class Context:
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         check(self.L.b200_comm_init(self.h, rank, world, buf), "b200_comm_init")
 
+    def p2p_handle(self) -> bytes:
+        """this rank's inbox as a 64-byte CUDA IPC handle"""
+        buf = (C.c_uint8 * 64)()
+        check(self.L.b200_p2p_handle(self.h, buf), "b200_p2p_handle")
+        return bytes(buf)
+
+    def p2p_connect(self, rank: int, world: int, next_handle: bytes, first_handle: bytes):
+        nh = (C.c_uint8 * 64).from_buffer_copy(next_handle)
+        fh = (C.c_uint8 * 64).from_buffer_copy(first_handle)
+        check(self.L.b200_p2p_connect(self.h, rank, world, nh, fh), "b200_p2p_connect")
+
     def pipeline_generate_greedy(self, first_token: int, pos0: int, n_steps: int) -> np.ndarray:
         out = np.empty(n_steps, dtype=np.int32)
         check(self.L.b200_pipeline_generate_greedy(self.h, first_token, pos0, n_steps,

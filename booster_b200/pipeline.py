@@ -65,3 +65,16 @@ def sum_over_ranks(dist, n: int, device=None) -> int:
     t = torch.tensor([n], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return int(t.item())
+
+
+def exchange_inbox_handles(dist, my_handle: bytes) -> Tuple[bytes, bytes]:
+    """every rank contributes its 64-byte inbox handle (b200_p2p_handle); returns (the next rank's, rank 0's) — what
+    b200_p2p_connect needs. The last rank's `next` is its own handle (unused)."""
+    if len(my_handle) != 64:
+        raise RuntimeError("an inbox handle is 64 bytes")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    handles = [None] * world
+    dist.all_gather_object(handles, my_handle)
+    if any(not isinstance(h, (bytes, bytearray)) or len(h) != 64 for h in handles):
+        raise RuntimeError("bad inbox handle from a peer")
+    return bytes(handles[min(rank + 1, world - 1)]), bytes(handles[0])

@@ -150,6 +150,14 @@ int b200_job_timing_us(const char * jobID, double * prompt_us_per_token, double 
  * stage 0 with one more 4-byte send/recv (greedy) or the logits stay on the last rank.                      */
 int b200_comm_unique_id(uint8_t id[128]);
 int b200_comm_init(b200_ctx * c, int rank, int world, const uint8_t id[128]);
+/* Direct NVLink hand-off instead of ncclSend / ncclRecv at the stage boundaries (same protocol: one message of f32[n_embd] per
+ * boundary per token + the 4-byte token hand-back, cf. cpp/ggml/src/ggml-cuda.cu:2386-2407): the producer's last step stores
+ * the vector into the consumer's inbox over NVLink and publishes a sequence number, the consumer's first step spins on it.
+ * b200_p2p_handle returns this rank's inbox as a CUDA IPC handle (64 bytes) to be passed to its neighbours through the
+ * host-side process group; b200_p2p_connect maps rank + 1's inbox (next_handle; unused on the last rank) and rank 0's
+ * (first_handle; used by the last rank). b200_comm_init is still required (the ids of a burst are broadcast with NCCL). */
+int b200_p2p_handle(b200_ctx * c, uint8_t handle[64]);
+int b200_p2p_connect(b200_ctx * c, int rank, int world, const uint8_t next_handle[64], const uint8_t first_handle[64]);
 /* All ranks call this collectively: run n_steps greedy tokens through the pipeline, starting from
  * first_token at position pos0. Every rank receives the token ids in out_tokens. */
 int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, int pos0, int n_steps, int32_t * out_tokens);

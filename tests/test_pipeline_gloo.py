@@ -56,8 +56,10 @@ def _worker(rank, world, port, q):
             dist.send(x, dst=1)
         else:
             dist.recv(x, src=0)
+        # inbox handles of the direct NVLink hand-off: every rank learns its successor's and rank 0's
+        nxt, first = P.exchange_inbox_handles(dist, bytes([rank]) * 64)
         dist.barrier()
-        q.put((rank, uid, lb, le, slowest, launches, float(x[0])))
+        q.put((rank, uid, lb, le, slowest, launches, float(x[0]), nxt[0], first[0]))
     finally:
         dist.destroy_process_group()
 
@@ -80,3 +82,4 @@ def test_world2_gloo():
     assert all(r[4] == 2.0 for r in res)                           # slowest rank's time everywhere
     assert all(r[5] == 300 for r in res)
     assert res[1][6] == 0.0                                        # stage 1 received stage 0's stream
+    assert [(r[7], r[8]) for r in res] == [(1, 0), (1, 0)]         # next rank's handle (the last rank: its own), rank 0's handle
