@@ -93,7 +93,9 @@ def lib() -> C.CDLL:
     sig("b200_profile_kind", C.c_int, [vp, C.c_int, C.c_int, C.c_int, f32p, i32p])
     sig("b200_trace_token", C.c_int64, [vp, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int64, i32p, C.c_int64])
     sig("b200_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)])
-    sig("b200_comm_init", "b200_p2p_handle", "b200_p2p_connect", C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)])
+    sig("b200_comm_init", C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)])
+    sig("b200_p2p_handle", C.c_int, [vp, C.POINTER(C.c_uint8)])
+    sig("b200_p2p_connect", C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)])
     sig("b200_pipeline_generate_greedy", C.c_int, [vp, C.c_int32, C.c_int, C.c_int, i32p])
     sig("b200_pipeline_decode", C.c_int, [vp, i32p, C.c_int, C.c_int, f32p])
     sig("b200_stage_forward", C.c_int, [vp, C.c_int32, C.c_int, C.c_int, vp])
