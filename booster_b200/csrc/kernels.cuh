@@ -401,8 +401,11 @@ __device__ __forceinline__ void sync_warps(int nwarp) { asm volatile("bar.sync 1
 template <bool TR, bool WHOLE_CTA, typename F>
 __device__ __forceinline__ void prologue_quantize(const float * __restrict__ x, bool norm, float eps, int k, double inv_k, int act_q8_0,
                                                   const ActSmem & A, double * red, const float (&pre_w)[PRO_U][8], F after_loads,
-                                                  int nwarp, unsigned long long * tr = nullptr) {
+                                                  int nwarp_arg, unsigned long long * tr = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // (the stand-alone kernels derive the count from blockDim as the measured round-1 code did: ptxas unrolls the cross-warp
+    //  reduction below differently when the count is a run-time argument)
+    const int nwarp = WHOLE_CTA ? (int) (blockDim.x >> 5) : nwarp_arg;
     const int n256 = k / 256;
     bool first = true;
     for (int b0 = warp; b0 < n256 || first; b0 += PRO_U * nwarp) {
