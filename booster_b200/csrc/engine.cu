@@ -23,6 +23,7 @@
 #endif
 #include "token_kernel.cuh"
 #include "prefill.cuh"
+#include "prefill_mma.cuh"
 
 #include <algorithm>
 #include <array>
@@ -1551,16 +1552,29 @@ static void prefill_alloc(b200_ctx * c) {
     CU(cudaMalloc(&c->pb.ATT, (size_t) T * QD * 4));
     CU(cudaMalloc(&c->pb.FFH, (size_t) T * m.n_ff * 4));
     CU(cudaMalloc(&c->pb.S, (size_t) PB_ATT_Z * m.n_head * c->n_ctx * 4));
-    const size_t rec_bytes = (size_t) (T / PB_CHUNK) * (kmax / 256) * PB_CHUNK * pb_record_bytes(0, 1);
+    const size_t rec_bytes = std::max((size_t) (T / PB_CHUNK) * (kmax / 256) * PB_CHUNK * pb_record_bytes(0, 1),
+                                      (size_t) (T / MB_NT) * (kmax / 256) * MB_REC_BYTES);
     CU(cudaMalloc(&c->pb.rec, rec_bytes));
     CU(cudaMemset(c->pb.rec, 0, rec_bytes));       // records of tokens beyond a partial last chunk are read (and discarded)
     CU(cudaMalloc(&c->pb.tokens, (size_t) T * 4));
     c->pb.cap = T;
 }
 static bool has_q6k(const TMat * seg, int n_seg) { for (int i = 0; i < n_seg; i++) if (seg[i].type == T_Q6_K) return true; return false; }
-static void pb_quant(b200_ctx * c, const float * X, int k, int T, const float * norm_w, int act_q8_0, int with_as) {
+// K-quant launches run on the tensor cores (prefill_mma.cuh) when every segment has an even number of 32-row units
+static int g_prefill_mma = -1;         // 1 (default): k_mma_batch for K-quant matrices, 0: the dp4a kernel (A/B, tests)
+extern "C" void b200_set_prefill_mma(int on) { g_prefill_mma = on ? 1 : 0; }
+static bool pb_use_mma(const MatvecArgs & mv) {
+    if (g_prefill_mma < 0) { const char * e = getenv("BOOSTER_B200_PREFILL_MMA"); g_prefill_mma = (e && e[0] == '0') ? 0 : 1; }
+    if (g_prefill_mma != 1 || mv.act_q8_0) return false;
+    for (int i = 0; i < mv.n_seg; i++) {
+        const int t = mv.seg[i].type;
+        if ((t != T_Q4_K && t != T_Q5_K && t != T_Q6_K) || (mv.seg[i].n_units & 1)) return false;
+    }
+    return true;
+}
+static void pb_quant(b200_ctx * c, const float * X, int k, int T, const float * norm_w, int act_q8_0, int with_as, bool mma = false) {
     QuantBatchArgs a{};
-    a.X = X; a.k = k; a.T = T; a.norm_w = norm_w; a.eps = c->m->rms_eps; a.inv_k = (k & (k - 1)) == 0 ? 1.0 / (double) k : 0.0;
+    a.X = X; a.k = k; a.T = T; a.norm_w = norm_w; a.eps = norm_w ? c->m->rms_eps : 0.f; a.inv_k = (k & (k - 1)) == 0 ? 1.0 / (double) k : 0.0;
     a.act_q8_0 = act_q8_0; a.with_as = with_as; a.rec = c->pb.rec;
     const size_t smem = act_smem_bytes(k, act_q8_0);
     static size_t attr[64] = {0};
@@ -1570,7 +1584,17 @@ static void pb_quant(b200_ctx * c, const float * X, int k, int T, const float * 
         attr[c->device & 63] = smem;
     }
     if (norm_w && k / 256 > PRO_U * 16) throw std::runtime_error("normed vector too long for the batched quantizer");
-    k_quant_batch<<<(unsigned) T, 512, smem, c->st>>>(a);
+    if (mma) {
+        static size_t attr_m[64] = {0};
+        if (smem > 48 * 1024 && smem > attr_m[c->device & 63]) {
+            std::lock_guard<std::mutex> lk(g_attr_mu);
+            CU(cudaFuncSetAttribute(k_quant_batch_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            attr_m[c->device & 63] = smem;
+        }
+        k_quant_batch_mma<<<(unsigned) T, 512, smem, c->st>>>(a);
+    } else {
+        k_quant_batch<<<(unsigned) T, 512, smem, c->st>>>(a);
+    }
     c->launches++;
 }
 static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int pos0, float * out, int out_stride, const float * resid, int with_as) {
@@ -1583,6 +1607,28 @@ static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int p
     a.n_q = mv.n_q; a.n_k = mv.n_k; a.head_dim = mv.head_dim; a.kv_dim = mv.kv_dim; a.rope = mv.rope; a.pos0 = pos0;
     int sb = 0;
     for (int i = 0; i < mv.n_seg; i++) sb = std::max(sb, tile_bytes_of(mv.seg[i].type));
+    if (pb_use_mma(mv)) {
+        bool q4 = false, q5 = false, q6 = false;
+        for (int i = 0; i < mv.n_seg; i++) { q4 |= mv.seg[i].type == T_Q4_K; q5 |= mv.seg[i].type == T_Q5_K; q6 |= mv.seg[i].type == T_Q6_K; }
+        a.mb_a_bytes = (uint32_t) mb_a_bytes(q6);
+        a.mb_raw_stride = (uint32_t) ((sb + 127) / 128 * 128);
+        a.mb_rec_copy = (uint32_t) mb_rec_copy_bytes(q4, q5);
+        a.mb_stage_bytes = 2 * a.mb_raw_stride + (a.mb_rec_copy + 127) / 128 * 128;
+        const size_t budget = 226 * 1024;
+        a.mb_stages = (int) std::min<size_t>(MB_MAX_STAGES, (budget - a.mb_a_bytes) / a.mb_stage_bytes);
+        if (a.mb_stages < 2) throw std::runtime_error("k_mma_batch: shared memory layout does not fit");
+        const size_t smem_m = std::max((size_t) a.mb_a_bytes + (size_t) a.mb_stages * a.mb_stage_bytes, (size_t) MB_CHAIN_BYTES);
+        static size_t attr_m[64] = {0};
+        if (smem_m > attr_m[c->device & 63]) {
+            std::lock_guard<std::mutex> lk(g_attr_mu);
+            CU(cudaFuncSetAttribute(k_mma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_m));
+            attr_m[c->device & 63] = smem_m;
+        }
+        const dim3 grid_m((unsigned) ((T + MB_NT - 1) / MB_NT), (unsigned) (a.n_units / 2));
+        k_mma_batch<<<grid_m, MB_WARPS * 32, smem_m, c->st>>>(a);
+        c->launches++;
+        return;
+    }
     const size_t smem = PB_STAGES * pb_stage_bytes(sb, a.act_q8_0, with_as);
     static size_t attr[64] = {0};
     if (smem > attr[c->device & 63]) {
@@ -1626,7 +1672,7 @@ static void prefill_batch(b200_ctx * c, const int32_t * tokens, int n, int pos0)
             const int q80 = L.qkv.seg[0].type == T_Q8_0;
             const MatvecArgs aq = args_qkv(c, li), ao = args_wo(c, li), ag = args_gateup(c, li), ad = args_down(c, li);
             int was = has_q6k(aq.seg, aq.n_seg);
-            pb_quant(c, c->pb.X, E, T, L.attn_norm, q80, was);
+            pb_quant(c, c->pb.X, E, T, L.attn_norm, q80, was, pb_use_mma(aq));
             pb_matmul(c, aq, EPI_QKV, T, p0, nullptr, 0, nullptr, was);
             switch (m.n_head / m.n_head_kv) {
                 case 1: pb_attention<1>(c, li, T, p0); break;
@@ -1635,13 +1681,13 @@ static void prefill_batch(b200_ctx * c, const int32_t * tokens, int n, int pos0)
                 default: pb_attention<8>(c, li, T, p0); break;
             }
             was = has_q6k(ao.seg, 1);
-            pb_quant(c, c->pb.ATT, QD, T, nullptr, q80, was);
+            pb_quant(c, c->pb.ATT, QD, T, nullptr, q80, was, pb_use_mma(ao));
             pb_matmul(c, ao, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
             was = has_q6k(ag.seg, 1);
-            pb_quant(c, c->pb.X, E, T, L.ffn_norm, q80, was);
+            pb_quant(c, c->pb.X, E, T, L.ffn_norm, q80, was, pb_use_mma(ag));
             pb_matmul(c, ag, EPI_SILU, T, p0, c->pb.FFH, FF, nullptr, was);
             was = has_q6k(ad.seg, 1);
-            pb_quant(c, c->pb.FFH, FF, T, nullptr, q80, was);
+            pb_quant(c, c->pb.FFH, FF, T, nullptr, q80, was, pb_use_mma(ad));
             pb_matmul(c, ad, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
         }
         CU(cudaGetLastError());
@@ -2373,6 +2419,50 @@ extern "C" int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(y, dy.p, (size_t) n_rows * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        cudaFree(d.alloc);
+        CU(cudaStreamDestroy(st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
+// the batched mat-mul of a prompt batch as an operator: y[T][n_rows] = W x[t] for T <= 512 tokens, through k_quant_batch(_mma) +
+// k_mma_batch / k_matmul_batch exactly as prefill_batch() launches them (tests: worst-case magnitudes, ragged T)
+extern "C" int b200_op_mul_mat(int type, const void * w, int64_t n_rows, int64_t k, const float * x, int64_t T, float * y) {
+    try {
+        require_gpu();
+        if (T <= 0 || T > PB_MAX_T) throw std::runtime_error("b200_op_mul_mat: 1..512 tokens");
+        cudaStream_t st;
+        CU(cudaStreamCreate(&st));
+        const int64_t rows_pad = (n_rows + 63) / 64 * 64;
+        std::vector<uint8_t> padded;
+        if (rows_pad != n_rows) {
+            const size_t rb = ggml_row_bytes(type, k);
+            padded.assign((size_t) rows_pad * rb, 0);
+            memcpy(padded.data(), w, (size_t) n_rows * rb);
+            w = padded.data();
+        }
+        DevMat d = upload_matrix(type, w, rows_pad, k, st);
+        const size_t rec_bytes = std::max((size_t) ((T + PB_CHUNK - 1) / PB_CHUNK) * (k / 256) * PB_CHUNK * pb_record_bytes(0, 1),
+                                          (size_t) ((T + MB_NT - 1) / MB_NT) * (k / 256) * MB_REC_BYTES);
+        DBuf dx((size_t) T * k * 4), dy((size_t) T * rows_pad * 4), drec(rec_bytes);
+        CU(cudaMemsetAsync(drec.p, 0, rec_bytes, st));
+        CU(cudaMemcpyAsync(dx.p, x, (size_t) T * k * 4, cudaMemcpyHostToDevice, st));
+        b200_ctx tmp;
+        tmp.st = st;
+        int dev = 0; CU(cudaGetDevice(&dev));
+        tmp.device = dev;
+        tmp.pb.rec = drec.as<uint8_t>();
+        MatvecArgs a{};
+        a.seg[0] = d.m; a.n_seg = 1; a.n_units = d.m.n_units; a.k = (int) k; a.act_q8_0 = type == T_Q8_0;
+        const int was = type == T_Q6_K;
+        pb_quant(&tmp, dx.as<float>(), (int) k, (int) T, nullptr, a.act_q8_0, was, pb_use_mma(a));
+        pb_matmul(&tmp, a, EPI_STORE, (int) T, 0, dy.as<float>(), (int) rows_pad, nullptr, was);
+        CU(cudaGetLastError());
+        std::vector<float> hy((size_t) T * rows_pad);
+        CU(cudaMemcpyAsync(hy.data(), dy.p, hy.size() * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int64_t t = 0; t < T; t++) memcpy(y + t * n_rows, hy.data() + t * rows_pad, (size_t) n_rows * 4);
+        tmp.pb.rec = nullptr;
         cudaFree(d.alloc);
         CU(cudaStreamDestroy(st));
         return 0;

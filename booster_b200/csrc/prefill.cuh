@@ -101,6 +101,9 @@ struct MatmulBatchArgs {
     int n_q, n_k, head_dim, kv_dim;
     const float2 * rope;
     int pos0;                 // position (== KV cell) of token 0 of the batch
+    // k_mma_batch (prefill_mma.cuh): shared-memory layout chosen on the host
+    uint32_t mb_a_bytes, mb_raw_stride, mb_stage_bytes, mb_rec_copy;
+    int mb_stages;
 };
 
 // resolve a unit against the segments (same rule as describe_unit)

@@ -242,6 +242,17 @@ def op_mul_mat_vec(t: int, w_raw, n_rows: int, k: int, x) -> np.ndarray:
     return y
 
 
+def op_mul_mat(t: int, w_raw, n_rows: int, k: int, x) -> np.ndarray:
+    """x[T][k] -> y[T][n_rows] through the prompt-batch kernels (T <= 512)"""
+    w_raw = np.ascontiguousarray(w_raw, dtype=np.uint8)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    T = x.shape[0]
+    y = np.empty((T, n_rows), dtype=np.float32)
+    check(_lib.lib().b200_op_mul_mat(t, w_raw.ctypes.data, n_rows, k, x.ctypes.data_as(C.POINTER(C.c_float)), T,
+                                     y.ctypes.data_as(C.POINTER(C.c_float))), "op_mul_mat")
+    return y
+
+
 def op_rms_norm(x, w, eps: float) -> np.ndarray:
     x = _f32(x)
     y = np.empty_like(x)
@@ -278,6 +289,11 @@ def set_token_kernel(on: bool) -> None:
 def set_prefill_batch(on: bool) -> None:
     """prompt batches through the batched kernels (True, default) or token by token (False)"""
     _lib.lib().b200_set_prefill_batch(int(on))
+
+
+def set_prefill_mma(on: bool) -> None:
+    """K-quant prompt batches on the tensor cores (True, default) or through the dp4a batch kernel (False)"""
+    _lib.lib().b200_set_prefill_mma(int(on))
 
 
 def set_attention_route(route: int) -> None:

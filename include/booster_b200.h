@@ -127,6 +127,8 @@ int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int reps, uint64_
  * weight tile fetched once per 64 tokens), 0 = token by token through the decode kernels. Same arithmetic, bit-identical
  * logits; the switch exists for A/B measurements and for the test that compares the two. Env BOOSTER_B200_PREFILL_BATCH=0. */
 void b200_set_prefill_batch(int on);
+/* 1 (default): K-quant prompt batches run on the tensor cores (k_mma_batch, exact fp16 HMMA); 0: the dp4a batch kernel */
+void b200_set_prefill_mma(int on);
 /* Decode path of contexts created AFTER the call: 0 (default) = one kernel per operator joined by programmatic dependent
  * launch, 1 = ONE persistent kernel per token (token_kernel.cuh: phase list + grid barriers; same arithmetic, bit-identical
  * results; measured slower on B200, kept selectable: DESIGN.md §4). Env BOOSTER_B200_TOKEN_KERNEL=1 sets the initial value. */
@@ -236,6 +238,9 @@ int b200_op_dequantize_row(int type, const void * w, int64_t k, float * y);
  * q8_0_q8_0 (cpp/ggml/src/ggml-quants.c:6832,7400,8037,5227): y[n_rows] = W[n_rows x k] . x[k];
  * w = n_rows rows of blocks in ggml row-major layout */
 int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int64_t k, const float * x, float * y);
+/* batch > 1 (ggml_compute_forward_mul_mat with ne11 = T, cpp/ggml/src/ggml.c:12277): y[T][n_rows] for x[T][k], T <= 512, through the
+   prompt-batch kernels */
+int b200_op_mul_mat(int type, const void * w, int64_t n_rows, int64_t k, const float * x, int64_t T, float * y);
 /* ggml_compute_forward_rms_norm_f32 then ggml_mul by the weight (cpp/ggml/src/ggml.c:11850-11896,
  * cpp/src/llama.cpp:7928-7958). w may be NULL. */
 int b200_op_rms_norm(const float * x, const float * w, int64_t k, float eps, float * y);

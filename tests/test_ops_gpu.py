@@ -131,3 +131,77 @@ def _attention_case(cfg, round_q):
     y = engine.op_attention(q, k, v, n_kv, n_head, n_head_kv, hd, scale, round_q)
     yr = port.attention(q, k, v, n_kv, n_head, n_head_kv, hd, scale, round_q)
     assert np.array_equal(y, yr), f"max abs diff {np.abs(y - yr).max()} rel {rel_err(y, yr)}"
+
+
+# ---- batch > 1 mat-mul (prompt batches): k_mma_batch on the tensor cores for K-quants, k_matmul_batch (dp4a) for Q8_0 ----
+@pytest.mark.parametrize("name", list(TYPES))
+@pytest.mark.parametrize("shape", [(64, 256, 8), (128, 768, 33), (1024, 4096, 70), (96, 14336, 31), (320, 4096, 512)])
+def test_mul_mat_batch_vs_port(name, shape):
+    """x[T][k] through the prompt-batch kernels equals the reference arithmetic token by token (ragged T, rows that are not
+    a multiple of 64, one K step and 56 of them)"""
+    n, k, T = shape
+    t = TYPES[name]
+    rng = np.random.default_rng(n * 7 + k + T)
+    w = G.random_blocks(rng, t, n, k)
+    x = (rng.standard_normal((T, k)) * rng.choice([0.01, 1.0, 30.0], size=(T, 1))).astype(np.float32)
+    x[min(3, T - 1), :256] = 0.0
+    y = engine.op_mul_mat(t, w, n, k, x)
+    for i in sorted(set([0, 1, T // 2, T - 2, T - 1])):
+        yr = port.mul_mat_vec(t, w, n, k, x[i])
+        assert np.array_equal(y[i], yr), f"token {i}: max abs diff {np.abs(y[i] - yr).max()} rel {rel_err(y[i], yr)}"
+
+
+def _extreme_blocks(name, n, k, rng):
+    """rows of worst-case magnitudes for the exact-fp16 argument of prefill_mma.cuh: largest quants x largest sub-block
+    scales (Q4_K 15*63, Q5_K 31*63, Q6_K -32*-128 and 31*127), mixed with random rows"""
+    t = TYPES[name]
+    w = G.random_blocks(rng, t, n, k).reshape(n, -1).copy()
+    nb = k // 256
+    if name == "Q4_K":
+        blk = np.full(144, 0xFF, np.uint8); blk[0:4] = np.array([1.0, 0.5], np.float16).view(np.uint8)
+    elif name == "Q5_K":
+        blk = np.full(176, 0xFF, np.uint8); blk[0:4] = np.array([1.0, 0.5], np.float16).view(np.uint8)
+    elif name == "Q6_K":
+        blk = np.zeros(210, np.uint8); blk[192:208] = 0x80; blk[208:210] = np.array([1.0], np.float16).view(np.uint8)
+    else:
+        blk = np.full(34, 0x81, np.uint8); blk[0:2] = np.array([1.0], np.float16).view(np.uint8)
+    per = blk.size
+    reps = w.shape[1] // per
+    w[0::4] = np.tile(blk, reps)
+    if name == "Q6_K":   # q = 63 (w = +31, odd), scale +127
+        b2 = np.full(210, 0xFF, np.uint8); b2[192:208] = 0x7F; b2[208:210] = np.array([1.0], np.float16).view(np.uint8)
+        w[1::4] = np.tile(b2, nb)
+    return w.reshape(-1)
+
+
+@pytest.mark.parametrize("name", list(TYPES))
+def test_mul_mat_batch_extremes(name):
+    """every quant at +-127 against the largest weights: the integer sums reach their bounds (Q6_K: 32 * 4096 * 127 < 2^24)
+    and must still come out of the fp16 tensor-core contraction exactly"""
+    rng = np.random.default_rng(11)
+    n, k, T = 64, 1024, 40
+    w = _extreme_blocks(name, n, k, rng)
+    x = rng.standard_normal((T, k)).astype(np.float32)
+    x[0] = 3.0; x[1] = -3.0                          # every quant -127 / +127
+    x[2] = np.where(np.arange(k) % 2 == 0, 5.0, -5.0)
+    x[3, :] = 0.0; x[3, ::256] = 1.0                 # a single non-zero per block
+    y = engine.op_mul_mat(TYPES[name], w, n, k, x)
+    for i in range(T if name != "Q8_0" else 8):
+        yr = port.mul_mat_vec(TYPES[name], w, n, k, x[i])
+        assert np.array_equal(y[i], yr), f"token {i}: max abs diff {np.abs(y[i] - yr).max()}"
+
+
+def test_mul_mat_batch_mma_equals_dp4a():
+    """the tensor-core kernel and the dp4a batch kernel give the same bits (A/B switch b200_set_prefill_mma)"""
+    rng = np.random.default_rng(3)
+    n, k, T = 192, 2048, 100
+    x = rng.standard_normal((T, k)).astype(np.float32)
+    for name in ("Q4_K", "Q5_K", "Q6_K"):
+        w = G.random_blocks(rng, TYPES[name], n, k)
+        ya = engine.op_mul_mat(TYPES[name], w, n, k, x)
+        engine.set_prefill_mma(False)
+        try:
+            yb = engine.op_mul_mat(TYPES[name], w, n, k, x)
+        finally:
+            engine.set_prefill_mma(True)
+        assert np.array_equal(ya, yb), name
