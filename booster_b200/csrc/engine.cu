@@ -1533,12 +1533,14 @@ static bool prefill_batch_enabled() {
     if (g_prefill_batch < 0) { const char * e = getenv("BOOSTER_B200_PREFILL_BATCH"); g_prefill_batch = (e && e[0] == '0') ? 0 : 1; }
     return g_prefill_batch == 1;
 }
+static int g_prefill_attn_batch = 1;   // 1: k_attn_softmax_rows + k_attn_pv_batch, 0: the per-token attention kernels over blockIdx.z
+extern "C" void b200_set_prefill_attn_batch(int on) { g_prefill_attn_batch = on ? 1 : 0; }
 static bool prefill_batch_usable(const b200_ctx * c, int n) {
     const b200_model & m = *c->m;
     if (!prefill_batch_enabled() || n < 8 || c->taps || c->cells.managed || !m.has_embd() || !m.has_head() || m.head_dim != 128) return false;
     const int gqa = m.n_head / m.n_head_kv;
     if (gqa != 1 && gqa != 2 && gqa != 4 && gqa != 8) return false;
-    if ((size_t) gqa * c->n_ctx * 4 + (size_t) PV_BATCH * 16 > 200 * 1024) return false;   // the two-launch attention must fit
+    if (g_prefill_attn_batch == 0 && (size_t) gqa * c->n_ctx * 4 + (size_t) PV_BATCH * 16 > 200 * 1024) return false;   // the two-launch attention must fit
     if (m.n_ff % 256 || m.n_embd % 256 || std::max(m.n_ff, m.n_embd) / 256 > 4 * 16 * 4) return false;
     return true;
 }
@@ -1653,8 +1655,24 @@ static void pb_attention(b200_ctx * c, int li, int T, int pos0) {
         a.scale = 1.0f / sqrtf((float) HD);
         a.st = nullptr; a.n_kv_override = pos0 + z0 + 1; a.round_q_override = 1; a.cell_pos = nullptr;   // batch > 1: q rounded to f16
         a.zq = QD; a.zs = m.n_head * c->n_ctx;
-        const int n_pad_max = (pos0 + z0 + nz + 31) / 32 * 32;
-        if (!launch_attention_2k<GQA>(c, a, std::min(n_pad_max, c->n_ctx), nz)) throw std::runtime_error("batched attention does not fit");
+        const int n_pad_max = std::min((pos0 + z0 + nz + 31) / 32 * 32, c->n_ctx);
+        if (g_prefill_attn_batch == 0) {   // A/B: the per-token kernels with the token in blockIdx.z
+            if (!launch_attention_2k<GQA>(c, a, n_pad_max, nz)) throw std::runtime_error("batched attention does not fit");
+            continue;
+        }
+        const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_pad_max + ATT_TILE - 1) / ATT_TILE), (unsigned) nz);
+        launch_fwd(k_attn_scores<GQA, false>, gs, dim3(ATT_THREADS), 0, c->st, a, false);
+        k_attn_softmax_rows<<<(unsigned) ((nz * a.n_head + 7) / 8), 256, 0, c->st>>>(a, nz);
+        static bool attr_done[64] = {false};
+        if (!attr_done[c->device & 63]) {
+            std::lock_guard<std::mutex> lk(g_attr_mu);
+            CU(cudaFuncSetAttribute(k_attn_pv_batch<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pvb_smem_bytes()));
+            attr_done[c->device & 63] = true;
+        }
+        constexpr int TQ = PVB_ROWS / GQA;
+        const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVB_DIMS), (unsigned) ((nz + TQ - 1) / TQ));
+        k_attn_pv_batch<GQA><<<gp, 256, pvb_smem_bytes(), c->st>>>(a, nz);
+        c->launches += 3;
     }
 }
 // tokens[0..n) at positions pos0..: the whole prompt batch through every layer; leaves the LAST token's residual stream in c->x

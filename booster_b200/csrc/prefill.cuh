@@ -86,6 +86,124 @@ __global__ void __launch_bounds__(512) k_quant_batch(const QuantBatchArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// attention of a prompt batch: k_attn_scores (kernels.cuh, token in blockIdx.z) writes the raw score rows, then
+//   k_attn_softmax_rows  one warp per (token, head) row, in place: k_attn_softmax's arithmetic (max, ggml_v_expf, per-16
+//                        _mm512_reduce_add_ps sums accumulated in double, * (float)(1/sum)), each row normalised ONCE
+//   k_attn_pv_batch      CTA = (KV head, 16 output dims, 32 / GQA tokens): every V chunk is staged once for the 32 (token,
+//                        head) rows of the CTA; thread (chain c, dim) advances the 32 rows' tinyBLAS chains t = c, c+16, ...
+//                        A token's probabilities end at its own padded length; beyond it p = 0 and fma(v, 0, acc) == acc,
+//                        which is what the reference's masked (-inf -> 0) columns contribute (cpp/src/llama.cpp:14132-14200).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_attn_softmax_rows(const AttnArgs a, int nz) {
+    const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= nz * a.n_head) return;
+    const int z = row / a.n_head, h = row - z * a.n_head;
+    const int n_pad = (a.n_kv_override + z + 31) / 32 * 32, n16 = n_pad / 16;
+    float * S = a.S + (size_t) z * a.zs + (size_t) h * a.s_stride;
+    float mx = -INFINITY;
+    for (int gi = lane; gi < n16; gi += 32) {
+        const float4 * r4 = reinterpret_cast<const float4 *>(S + 16 * gi);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const float4 v = r4[q]; mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
+    }
+    mx = warp_max(mx);
+    double part = 0.0;
+    for (int gi = lane; gi < n16; gi += 32) {
+        float4 * r4 = reinterpret_cast<float4 *>(S + 16 * gi);
+        float4 t[2];
+#pragma unroll 1
+        for (int pq = 0; pq < 2; pq++) {                       // float4 pairs {0, 2} and {1, 3}: a[8+i] + a[i]
+            float4 lo = r4[pq], hi = r4[pq + 2];
+            lo.x = v_expf(__fsub_rn(lo.x, mx)); lo.y = v_expf(__fsub_rn(lo.y, mx)); lo.z = v_expf(__fsub_rn(lo.z, mx)); lo.w = v_expf(__fsub_rn(lo.w, mx));
+            hi.x = v_expf(__fsub_rn(hi.x, mx)); hi.y = v_expf(__fsub_rn(hi.y, mx)); hi.z = v_expf(__fsub_rn(hi.z, mx)); hi.w = v_expf(__fsub_rn(hi.w, mx));
+            r4[pq] = lo; r4[pq + 2] = hi;
+            const float4 tt = make_float4(__fadd_rn(hi.x, lo.x), __fadd_rn(hi.y, lo.y), __fadd_rn(hi.z, lo.z), __fadd_rn(hi.w, lo.w));
+            if (pq) t[1] = tt; else t[0] = tt;
+        }
+        const float u0 = __fadd_rn(t[1].x, t[0].x), u1 = __fadd_rn(t[1].y, t[0].y), u2 = __fadd_rn(t[1].z, t[0].z), u3 = __fadd_rn(t[1].w, t[0].w);
+        part += (double) __fadd_rn(__fadd_rn(u0, u2), __fadd_rn(u1, u3));
+    }
+    const double sum = warp_sum_d(part);
+    const float inv = (float) (1.0 / sum);
+    for (int gi = lane; gi < n16; gi += 32) {
+        float4 * r4 = reinterpret_cast<float4 *>(S + 16 * gi);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float4 v = r4[q];
+            v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv); v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
+            r4[q] = v;
+        }
+    }
+}
+
+static constexpr int PVB_ROWS = 32;            // (token, head) rows per CTA: 32 / GQA tokens x GQA heads
+static constexpr int PVB_CHUNK = 256;          // positions staged at a time
+static constexpr int PVB_DIMS = 16;
+__host__ __device__ constexpr size_t pvb_smem_bytes() {
+    return (size_t) PVB_ROWS * PVB_CHUNK * 4 + (size_t) PVB_CHUNK * PVB_DIMS * 2 > (size_t) PVB_ROWS * 16 * (PVB_DIMS + 1) * 4
+               ? (size_t) PVB_ROWS * PVB_CHUNK * 4 + (size_t) PVB_CHUNK * PVB_DIMS * 2 : (size_t) PVB_ROWS * 16 * (PVB_DIMS + 1) * 4;
+}
+template <int GQA>
+__global__ void __launch_bounds__(256) k_attn_pv_batch(const AttnArgs a, int nz) {
+    constexpr int HD = 128, TQ = PVB_ROWS / GQA;
+    extern __shared__ __align__(16) uint8_t pvb_dyn[];
+    float * ps = reinterpret_cast<float *>(pvb_dyn);                                        // [32 rows][PVB_CHUNK]
+    __half (*vs)[PVB_DIMS] = reinterpret_cast<__half (*)[PVB_DIMS]>(pvb_dyn + (size_t) PVB_ROWS * PVB_CHUNK * 4);
+    const int g = blockIdx.x, slice = blockIdx.y, z0 = blockIdx.z * TQ, tid = threadIdx.x;
+    const int c = tid / PVB_DIMS, dl = tid % PVB_DIMS;
+    const int ntok = min(TQ, nz - z0);
+    const int n_kv_last = a.n_kv_override + z0 + ntok - 1;     // cells attended by the CTA's last token
+    const int n_max = (n_kv_last + 31) / 32 * 32;
+    const __half * vbase = a.v_cache + g * HD + slice * PVB_DIMS;
+    float acc[PVB_ROWS];
+#pragma unroll
+    for (int r = 0; r < PVB_ROWS; r++) acc[r] = 0.f;
+    for (int t0 = 0; t0 < n_max; t0 += PVB_CHUNK) {
+        const int len = min(PVB_CHUNK, n_max - t0);
+        if (t0) __syncthreads();
+        for (int i = tid; i < len * 2; i += 256) {             // V rows: 2 x 16 bytes; rows beyond the last cell are zero
+            const int t = t0 + (i >> 1);
+            if (t < n_kv_last) cp_async16(&vs[i >> 1][(i & 1) * 8], vbase + (size_t) t * a.kv_dim + (i & 1) * 8);
+            else *reinterpret_cast<uint4 *>(&vs[i >> 1][(i & 1) * 8]) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int i = tid; i < PVB_ROWS * (len / 4); i += 256) {
+            const int r = i / (len / 4), j = i - r * (len / 4), tok = r / GQA, h = r - tok * GQA, t = t0 + 4 * j;
+            const int n_pad_z = (a.n_kv_override + z0 + tok + 31) / 32 * 32;
+            float * dst = ps + (size_t) r * PVB_CHUNK + 4 * j;
+            if (tok < ntok && t < n_pad_z) cp_async16(dst, a.S + (size_t) (z0 + tok) * a.zs + (size_t) (g * GQA + h) * a.s_stride + t);
+            else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        const int steps = len / 16;
+#pragma unroll 2
+        for (int s = 0; s < steps; s++) {
+            const int tt = 16 * s + c;
+            const float v = __half2float(vs[tt][dl]);
+#pragma unroll
+            for (int r = 0; r < PVB_ROWS; r++) acc[r] = __fmaf_rn(v, ps[(size_t) r * PVB_CHUNK + tt], acc[r]);
+        }
+    }
+    __syncthreads();
+    float (*red)[16][PVB_DIMS + 1] = reinterpret_cast<float (*)[16][PVB_DIMS + 1]>(pvb_dyn);
+#pragma unroll
+    for (int r = 0; r < PVB_ROWS; r++) red[r][c][dl] = acc[r];
+    __syncthreads();
+    for (int i = tid; i < PVB_ROWS * PVB_DIMS; i += 256) {
+        const int r = i / PVB_DIMS, dd = i % PVB_DIMS, tok = r / GQA, h = r - tok * GQA;
+        if (tok >= ntok) continue;
+        float t3[8], t6[4];                                   // _mm512_reduce_add_ps over the 16 chains
+#pragma unroll
+        for (int j = 0; j < 8; j++) t3[j] = __fadd_rn(red[r][8 + j][dd], red[r][j][dd]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) t6[j] = __fadd_rn(t3[4 + j], t3[j]);
+        a.out[(size_t) (z0 + tok) * a.zq + (size_t) (g * GQA + h) * HD + slice * PVB_DIMS + dd] =
+            __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
+    }
+}
+
 struct MatmulBatchArgs {
     TMat seg[3];
     int n_seg, n_units, k, tiles_unit;
