@@ -10,7 +10,7 @@ OBJS := $(OBJDIR)/engine.o $(OBJDIR)/gguf.o $(OBJDIR)/bridge.o $(OBJDIR)/tokeniz
 
 all: $(LIB)
 
-$(OBJDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.cuh $(CSRC)/token_kernel.cuh $(CSRC)/prefill.cuh $(CSRC)/prefill_mma.cuh $(CSRC)/gguf.hpp $(CSRC)/tokenizer.hpp include/booster_b200.h
+$(OBJDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.cuh $(CSRC)/token_kernel.cuh $(CSRC)/prefill.cuh $(CSRC)/prefill_mma.cuh $(CSRC)/prefill_umma.cuh $(CSRC)/gguf.hpp $(CSRC)/tokenizer.hpp include/booster_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/engine.ptxas.log || (cat $(OBJDIR)/engine.ptxas.log; false)
 

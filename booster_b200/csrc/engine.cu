@@ -24,6 +24,7 @@
 #include "token_kernel.cuh"
 #include "prefill.cuh"
 #include "prefill_mma.cuh"
+#include "prefill_umma.cuh"
 
 #include <algorithm>
 #include <array>
@@ -1555,7 +1556,7 @@ static void prefill_alloc(b200_ctx * c) {
     CU(cudaMalloc(&c->pb.FFH, (size_t) T * m.n_ff * 4));
     CU(cudaMalloc(&c->pb.S, (size_t) PB_ATT_Z * m.n_head * c->n_ctx * 4));
     const size_t rec_bytes = std::max((size_t) (T / PB_CHUNK) * (kmax / 256) * PB_CHUNK * pb_record_bytes(0, 1),
-                                      (size_t) (T / MB_NT) * (kmax / 256) * MB_REC_BYTES);
+                                      std::max((size_t) (T / MB_NT) * (kmax / 256) * MB_REC_BYTES, (size_t) (T / UM_NT) * (kmax / 256) * UM_REC_BYTES));
     CU(cudaMalloc(&c->pb.rec, rec_bytes));
     CU(cudaMemset(c->pb.rec, 0, rec_bytes));       // records of tokens beyond a partial last chunk are read (and discarded)
     CU(cudaMalloc(&c->pb.tokens, (size_t) T * 4));
@@ -1563,21 +1564,26 @@ static void prefill_alloc(b200_ctx * c) {
 }
 static bool has_q6k(const TMat * seg, int n_seg) { for (int i = 0; i < n_seg; i++) if (seg[i].type == T_Q6_K) return true; return false; }
 // K-quant launches run on the tensor cores (prefill_mma.cuh) when every segment has an even number of 32-row units
-static int g_prefill_mma = -1;         // 1 (default): k_mma_batch for K-quant matrices, 0: the dp4a kernel (A/B, tests)
-extern "C" void b200_set_prefill_mma(int on) { g_prefill_mma = on ? 1 : 0; }
-static bool pb_use_mma(const MatvecArgs & mv) {
-    if (g_prefill_mma < 0) { const char * e = getenv("BOOSTER_B200_PREFILL_MMA"); g_prefill_mma = (e && e[0] == '0') ? 0 : 1; }
-    if (g_prefill_mma != 1 || mv.act_q8_0) return false;
+static int g_prefill_mma = -1;         // 2 (default): tcgen05 (k_umma_batch), 1: mma.sync (k_mma_batch), 0: the dp4a kernel (A/B, tests)
+extern "C" void b200_set_prefill_mma(int mode) { g_prefill_mma = mode < 0 ? 0 : mode > 2 ? 2 : mode; }
+// record layout / kernel of a K-quant launch: 2 = k_umma_batch (segments of a multiple of 4 units), 1 = k_mma_batch (even), 0 = dp4a
+static int pb_mma_mode(const MatvecArgs & mv) {
+    if (g_prefill_mma < 0) { const char * e = getenv("BOOSTER_B200_PREFILL_MMA"); g_prefill_mma = e ? std::max(0, std::min(2, atoi(e))) : 2; }
+    if (g_prefill_mma == 0 || mv.act_q8_0) return 0;
+    int mode = g_prefill_mma;
     for (int i = 0; i < mv.n_seg; i++) {
         const int t = mv.seg[i].type;
-        if ((t != T_Q4_K && t != T_Q5_K && t != T_Q6_K) || (mv.seg[i].n_units & 1)) return false;
+        if (t != T_Q4_K && t != T_Q5_K && t != T_Q6_K) return 0;
+        if (mv.seg[i].n_units & 1) return 0;
+        if (mv.seg[i].n_units & 3) mode = 1;
     }
-    return true;
+    return mode;
 }
-static void pb_quant(b200_ctx * c, const float * X, int k, int T, const float * norm_w, int act_q8_0, int with_as, bool mma = false) {
+static bool pb_use_mma(const MatvecArgs & mv) { return pb_mma_mode(mv) != 0; }
+static void pb_quant(b200_ctx * c, const float * X, int k, int T, const float * norm_w, int act_q8_0, int with_as, int mma = 0) {
     QuantBatchArgs a{};
     a.X = X; a.k = k; a.T = T; a.norm_w = norm_w; a.eps = norm_w ? c->m->rms_eps : 0.f; a.inv_k = (k & (k - 1)) == 0 ? 1.0 / (double) k : 0.0;
-    a.act_q8_0 = act_q8_0; a.with_as = with_as; a.rec = c->pb.rec;
+    a.act_q8_0 = act_q8_0; a.with_as = with_as; a.rec = c->pb.rec; a.layout = mma;
     const size_t smem = act_smem_bytes(k, act_q8_0);
     static size_t attr[64] = {0};
     if (smem > 48 * 1024 && smem > attr[c->device & 63]) {
@@ -1609,9 +1615,30 @@ static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int p
     a.n_q = mv.n_q; a.n_k = mv.n_k; a.head_dim = mv.head_dim; a.kv_dim = mv.kv_dim; a.rope = mv.rope; a.pos0 = pos0;
     int sb = 0;
     for (int i = 0; i < mv.n_seg; i++) sb = std::max(sb, tile_bytes_of(mv.seg[i].type));
-    if (pb_use_mma(mv)) {
-        bool q4 = false, q5 = false, q6 = false;
-        for (int i = 0; i < mv.n_seg; i++) { q4 |= mv.seg[i].type == T_Q4_K; q5 |= mv.seg[i].type == T_Q5_K; q6 |= mv.seg[i].type == T_Q6_K; }
+    const int mma_mode = pb_mma_mode(mv);
+    bool q4 = false, q5 = false, q6 = false;
+    for (int i = 0; i < mv.n_seg; i++) { q4 |= mv.seg[i].type == T_Q4_K; q5 |= mv.seg[i].type == T_Q5_K; q6 |= mv.seg[i].type == T_Q6_K; }
+    if (mma_mode == 2) {
+        a.mb_a_bytes = (uint32_t) um_a_bytes(q6);
+        a.mb_raw_stride = (uint32_t) ((sb + 127) / 128 * 128);
+        a.mb_rec_copy = (uint32_t) um_rec_copy_bytes(q4, q5);
+        a.mb_stage_bytes = 4 * a.mb_raw_stride + (a.mb_rec_copy + 127) / 128 * 128;
+        const size_t budget = 226 * 1024;
+        a.mb_stages = (int) std::min<size_t>(UM_MAX_STAGES, (budget - a.mb_a_bytes) / a.mb_stage_bytes);
+        if (a.mb_stages < 2) throw std::runtime_error("k_umma_batch: shared memory layout does not fit");
+        const size_t smem_u = std::max((size_t) a.mb_a_bytes + (size_t) a.mb_stages * a.mb_stage_bytes, (size_t) 120 * 1024);   // one CTA per SM (TMEM)
+        static size_t attr_u[64] = {0};
+        if (smem_u > attr_u[c->device & 63]) {
+            std::lock_guard<std::mutex> lk(g_attr_mu);
+            CU(cudaFuncSetAttribute(k_umma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_u));
+            attr_u[c->device & 63] = smem_u;
+        }
+        const dim3 grid_u((unsigned) ((T + UM_NT - 1) / UM_NT), (unsigned) (a.n_units / 4));
+        k_umma_batch<<<grid_u, UM_WARPS * 32, smem_u, c->st>>>(a);
+        c->launches++;
+        return;
+    }
+    if (mma_mode == 1) {
         a.mb_a_bytes = (uint32_t) mb_a_bytes(q6);
         a.mb_raw_stride = (uint32_t) ((sb + 127) / 128 * 128);
         a.mb_rec_copy = (uint32_t) mb_rec_copy_bytes(q4, q5);
@@ -1690,7 +1717,7 @@ static void prefill_batch(b200_ctx * c, const int32_t * tokens, int n, int pos0)
             const int q80 = L.qkv.seg[0].type == T_Q8_0;
             const MatvecArgs aq = args_qkv(c, li), ao = args_wo(c, li), ag = args_gateup(c, li), ad = args_down(c, li);
             int was = has_q6k(aq.seg, aq.n_seg);
-            pb_quant(c, c->pb.X, E, T, L.attn_norm, q80, was, pb_use_mma(aq));
+            pb_quant(c, c->pb.X, E, T, L.attn_norm, q80, was, pb_mma_mode(aq));
             pb_matmul(c, aq, EPI_QKV, T, p0, nullptr, 0, nullptr, was);
             switch (m.n_head / m.n_head_kv) {
                 case 1: pb_attention<1>(c, li, T, p0); break;
@@ -1699,13 +1726,13 @@ static void prefill_batch(b200_ctx * c, const int32_t * tokens, int n, int pos0)
                 default: pb_attention<8>(c, li, T, p0); break;
             }
             was = has_q6k(ao.seg, 1);
-            pb_quant(c, c->pb.ATT, QD, T, nullptr, q80, was, pb_use_mma(ao));
+            pb_quant(c, c->pb.ATT, QD, T, nullptr, q80, was, pb_mma_mode(ao));
             pb_matmul(c, ao, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
             was = has_q6k(ag.seg, 1);
-            pb_quant(c, c->pb.X, E, T, L.ffn_norm, q80, was, pb_use_mma(ag));
+            pb_quant(c, c->pb.X, E, T, L.ffn_norm, q80, was, pb_mma_mode(ag));
             pb_matmul(c, ag, EPI_SILU, T, p0, c->pb.FFH, FF, nullptr, was);
             was = has_q6k(ad.seg, 1);
-            pb_quant(c, c->pb.FFH, FF, T, nullptr, q80, was, pb_use_mma(ad));
+            pb_quant(c, c->pb.FFH, FF, T, nullptr, q80, was, pb_mma_mode(ad));
             pb_matmul(c, ad, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
         }
         CU(cudaGetLastError());
@@ -2461,7 +2488,7 @@ extern "C" int b200_op_mul_mat(int type, const void * w, int64_t n_rows, int64_t
         }
         DevMat d = upload_matrix(type, w, rows_pad, k, st);
         const size_t rec_bytes = std::max((size_t) ((T + PB_CHUNK - 1) / PB_CHUNK) * (k / 256) * PB_CHUNK * pb_record_bytes(0, 1),
-                                          (size_t) ((T + MB_NT - 1) / MB_NT) * (k / 256) * MB_REC_BYTES);
+                                          std::max((size_t) ((T + MB_NT - 1) / MB_NT) * (k / 256) * MB_REC_BYTES, (size_t) ((T + UM_NT - 1) / UM_NT) * (k / 256) * UM_REC_BYTES));
         DBuf dx((size_t) T * k * 4), dy((size_t) T * rows_pad * 4), drec(rec_bytes);
         CU(cudaMemsetAsync(drec.p, 0, rec_bytes, st));
         CU(cudaMemcpyAsync(dx.p, x, (size_t) T * k * 4, cudaMemcpyHostToDevice, st));
@@ -2473,7 +2500,7 @@ extern "C" int b200_op_mul_mat(int type, const void * w, int64_t n_rows, int64_t
         MatvecArgs a{};
         a.seg[0] = d.m; a.n_seg = 1; a.n_units = d.m.n_units; a.k = (int) k; a.act_q8_0 = type == T_Q8_0;
         const int was = type == T_Q6_K;
-        pb_quant(&tmp, dx.as<float>(), (int) k, (int) T, nullptr, a.act_q8_0, was, pb_use_mma(a));
+        pb_quant(&tmp, dx.as<float>(), (int) k, (int) T, nullptr, a.act_q8_0, was, pb_mma_mode(a));
         pb_matmul(&tmp, a, EPI_STORE, (int) T, 0, dy.as<float>(), (int) rows_pad, nullptr, was);
         CU(cudaGetLastError());
         std::vector<float> hy((size_t) T * rows_pad);

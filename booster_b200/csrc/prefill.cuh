@@ -51,6 +51,7 @@ struct QuantBatchArgs {
     double inv_k;
     int act_q8_0, with_as;
     uint8_t * rec;            // [ceil(T/64)][k/256][64][record]
+    int layout;               // 0: records above (k_matmul_batch), 1: k_mma_batch blocks, 2: k_umma_batch blocks
 };
 
 // one CTA per token: the decode path's prologue (RMSNorm + quantization into shared memory), then the image is written out

@@ -116,26 +116,6 @@ __device__ __forceinline__ void mb_write_records(const ActSmem & A, int n256, ui
     }
 }
 
-// k_quant_batch with the MMA record layout (one CTA per token: the decode path's prologue, then the image is written out)
-__global__ void __launch_bounds__(512) k_quant_batch_mma(const QuantBatchArgs a) {
-    extern __shared__ __align__(16) uint8_t qb_smem[];
-    __shared__ double red_smem[MV_MAX_WARPS];
-    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const ActSmem A = act_smem_carve(qb_smem, a.k, 0);
-    const bool norm = a.norm_w != nullptr;
-    float ww[PRO_U][8] = {};
-    if (norm) {
-#pragma unroll
-        for (int u = 0; u < PRO_U; u++) {
-            const int b = warp + u * W;
-            if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, ww[u]);
-        }
-    }
-    prologue_quantize<false, true>(a.X + (size_t) t * a.k, norm, a.eps, a.k, a.inv_k, 0, A, red_smem, ww, []() {}, W);
-    __syncthreads();
-    mb_write_records(A, a.k / 256, a.rec, t, lane, warp, W);
-}
-
 // raw tiles of the CTA's two units -> fp16 A operand. warp = (unit u, 16-byte chunk c of the quants); lane = row of the unit
 template <int TYPE>
 __device__ __forceinline__ void mb_expand(const uint8_t * raw, uint32_t raw_stride, uint8_t * As, uint32_t mins_off, int warp, int lane) {

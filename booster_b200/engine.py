@@ -291,9 +291,9 @@ def set_prefill_batch(on: bool) -> None:
     _lib.lib().b200_set_prefill_batch(int(on))
 
 
-def set_prefill_mma(on: bool) -> None:
-    """K-quant prompt batches on the tensor cores (True, default) or through the dp4a batch kernel (False)"""
-    _lib.lib().b200_set_prefill_mma(int(on))
+def set_prefill_mma(mode: int) -> None:
+    """K-quant prompt batches: 2 = tcgen05 / TMEM kernel (default), 1 = mma.sync kernel, 0 = dp4a batch kernel"""
+    _lib.lib().b200_set_prefill_mma(int(mode))
 
 
 def set_attention_route(route: int) -> None:

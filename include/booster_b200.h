@@ -127,8 +127,11 @@ int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int reps, uint64_
  * weight tile fetched once per 64 tokens), 0 = token by token through the decode kernels. Same arithmetic, bit-identical
  * logits; the switch exists for A/B measurements and for the test that compares the two. Env BOOSTER_B200_PREFILL_BATCH=0. */
 void b200_set_prefill_batch(int on);
-/* 1 (default): K-quant prompt batches run on the tensor cores (k_mma_batch, exact fp16 HMMA); 0: the dp4a batch kernel */
-void b200_set_prefill_mma(int on);
+/* K-quant prompt batches: 2 (default) = tcgen05.mma with TMEM accumulators (k_umma_batch), 1 = mma.sync (k_mma_batch),
+   0 = the dp4a batch kernel; all three are bit-identical */
+void b200_set_prefill_mma(int mode);
+/* 1 (default): prompt-batch attention through k_attn_softmax_rows + k_attn_pv_batch; 0: the per-token kernels over blockIdx.z */
+void b200_set_prefill_attn_batch(int on);
 /* Decode path of contexts created AFTER the call: 0 (default) = one kernel per operator joined by programmatic dependent
  * launch, 1 = ONE persistent kernel per token (token_kernel.cuh: phase list + grid barriers; same arithmetic, bit-identical
  * results; measured slower on B200, kept selectable: DESIGN.md §4). Env BOOSTER_B200_TOKEN_KERNEL=1 sets the initial value. */

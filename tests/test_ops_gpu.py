@@ -191,17 +191,21 @@ def test_mul_mat_batch_extremes(name):
         assert np.array_equal(y[i], yr), f"token {i}: max abs diff {np.abs(y[i] - yr).max()}"
 
 
-def test_mul_mat_batch_mma_equals_dp4a():
-    """the tensor-core kernel and the dp4a batch kernel give the same bits (A/B switch b200_set_prefill_mma)"""
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("name", ["Q4_K", "Q5_K", "Q6_K"])
+def test_mul_mat_batch_kernel_variants(name, mode):
+    """the three batch kernels — tcgen05 (2, default), mma.sync (1), dp4a (0): A/B switch b200_set_prefill_mma — give the
+    reference's bits, on random blocks and on the worst-case magnitudes"""
     rng = np.random.default_rng(3)
-    n, k, T = 192, 2048, 100
+    n, k, T = 256, 2048, 100
     x = rng.standard_normal((T, k)).astype(np.float32)
-    for name in ("Q4_K", "Q5_K", "Q6_K"):
-        w = G.random_blocks(rng, TYPES[name], n, k)
-        ya = engine.op_mul_mat(TYPES[name], w, n, k, x)
-        engine.set_prefill_mma(False)
-        try:
-            yb = engine.op_mul_mat(TYPES[name], w, n, k, x)
-        finally:
-            engine.set_prefill_mma(True)
-        assert np.array_equal(ya, yb), name
+    x[0] = 3.0; x[1] = -3.0
+    w = _extreme_blocks(name, n, k, rng)
+    engine.set_prefill_mma(mode)
+    try:
+        y = engine.op_mul_mat(TYPES[name], w, n, k, x)
+    finally:
+        engine.set_prefill_mma(2)
+    for i in (0, 1, 2, 50, 99):
+        yr = port.mul_mat_vec(TYPES[name], w, n, k, x[i])
+        assert np.array_equal(y[i], yr), f"mode {mode} token {i}: max abs diff {np.abs(y[i] - yr).max()}"
