@@ -124,7 +124,8 @@ def lib() -> C.CDLL:
     sig("b200_sampler_sample", C.c_int32, [vp, f32p, C.c_int32, C.c_int32])
     sig("b200_set_token_kernel", None, [C.c_int])
     sig("b200_set_prefill_batch", None, [C.c_int])
-    sig("b200_set_prefill_mma", "b200_set_prefill_attn_batch", None, [C.c_int])
+    sig("b200_set_prefill_mma", None, [C.c_int])
+    sig("b200_set_prefill_attn_batch", None, [C.c_int])
     sig("b200_trace_phases", C.c_int64, [vp, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int64, i32p, C.c_int64, i32p])
     _lib = L
     return L
