@@ -376,6 +376,26 @@ def main():
 
     if rank == 0 and world == 1 and not args.value_only:
         tok1 = int(ids[-1])
+        # ---- prompt batch (llama_decode with n_tokens = 512): its own context, the reference's n_ubatch in one call
+        try:
+            pc = engine.Context(m, 1024)
+            pp = np.random.default_rng(7).integers(0, cfg.n_vocab, size=512).tolist()
+            pms = []
+            for _ in range(3):
+                pc.kv_clear()
+                t0 = time.perf_counter()
+                pc.decode(pp, 0, want_logits=False)
+                torch.cuda.synchronize()
+                pms.append(1e3 * (time.perf_counter() - t0))
+            pc.close()
+            pm = float(np.mean(pms[1:]))
+            line["prompt_batch"] = {"tokens": 512, "ms": pm, "tokens_per_s": 512e3 / pm,
+                                    "kernels": ("k_quant_batch + k_matmul_batch (dp4a: Q8_0 lane sums are 4-byte contractions)" if ftype == "Q8_0" else
+                                                "k_quant_batch_mma + k_mma_batch (exact fp16 HMMA per AVX2 lane-slice)") +
+                                               " + k_attn_scores / k_attn_softmax_rows / k_attn_pv_batch",
+                                    "what": "b200_decode of one 512-token batch at positions 0..511, wall clock incl. the final synchronisation"}
+        except Exception as e:
+            line["prompt_batch"] = {"error": str(e)}
         # ---- end to end, additive token-level seam: host token in, host logits out, host arg-max
         n_e2e = min(args.steps, 4) * min(burst, 64)
         lg = c.decode([tok1], pos0)

@@ -1564,11 +1564,11 @@ static void prefill_alloc(b200_ctx * c) {
 }
 static bool has_q6k(const TMat * seg, int n_seg) { for (int i = 0; i < n_seg; i++) if (seg[i].type == T_Q6_K) return true; return false; }
 // K-quant launches run on the tensor cores (prefill_mma.cuh) when every segment has an even number of 32-row units
-static int g_prefill_mma = -1;         // 2 (default): tcgen05 (k_umma_batch), 1: mma.sync (k_mma_batch), 0: the dp4a kernel (A/B, tests)
+static int g_prefill_mma = -1;         // 1 (default, the fastest measured): mma.sync (k_mma_batch), 2: tcgen05 (k_umma_batch), 0: the dp4a kernel
 extern "C" void b200_set_prefill_mma(int mode) { g_prefill_mma = mode < 0 ? 0 : mode > 2 ? 2 : mode; }
 // record layout / kernel of a K-quant launch: 2 = k_umma_batch (segments of a multiple of 4 units), 1 = k_mma_batch (even), 0 = dp4a
 static int pb_mma_mode(const MatvecArgs & mv) {
-    if (g_prefill_mma < 0) { const char * e = getenv("BOOSTER_B200_PREFILL_MMA"); g_prefill_mma = e ? std::max(0, std::min(2, atoi(e))) : 2; }
+    if (g_prefill_mma < 0) { const char * e = getenv("BOOSTER_B200_PREFILL_MMA"); g_prefill_mma = e ? std::max(0, std::min(2, atoi(e))) : 1; }
     if (g_prefill_mma == 0 || mv.act_q8_0) return 0;
     int mode = g_prefill_mma;
     for (int i = 0; i < mv.n_seg; i++) {

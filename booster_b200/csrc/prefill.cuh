@@ -312,15 +312,39 @@ __global__ void __launch_bounds__(PB_WARPS * 32, 1) k_matmul_batch(const __grid_
             const uint32_t par = (uint32_t) ((step / PB_STAGES) & 1);
             mbar_wait(full0 + 8 * s, par);
             const uint8_t * stage = pb_smem + (size_t) s * stage_bytes;
+            if (TYPE == T_Q8_0) {
+                // eight 32-weight blocks per step; a block's weights are read once for the warp's four tokens. The lane sums
+                // come out of dp4a already as floats: the accumulator input 0x4B400000 is the bit pattern of 1.5 * 2^23, and
+                // adding an integer |v| < 2^22 to it gives the bit pattern of 12582912.0 + v — one exact FADD instead of an
+                // I2F on the quarter-rate conversion pipe (|v| <= 4 * 127 * 127)
+#pragma unroll 1
+                for (int tt = 0; tt < 8; tt++) {
+                    const uint8_t * tile = stage + (size_t) tt * ud.bytes, * sl = tile + lane * 16;
+                    const uint4 w0 = lds_u4(sl), w1 = lds_u4(sl + 512);
+                    const float dw = __half2float(*reinterpret_cast<const __half *>(tile + 1024 + lane * 2));
+#pragma unroll
+                    for (int j = 0; j < PB_TOK; j++) {
+                        const uint8_t * r = stage + w_bytes + (size_t) (warp * PB_TOK + j) * rb;
+                        const int4 a0 = *reinterpret_cast<const int4 *>(r + tt * 32), a1 = *reinterpret_cast<const int4 *>(r + tt * 32 + 16);
+                        const float d = __fmul_rn(dw, *reinterpret_cast<const float *>(r + 256 + tt * 4));      // fp16(x.d) * fp16(y.d)
+#pragma unroll
+                        for (int wi = 0; wi < 4; wi++) {
+                            const float f0 = __fsub_rn(__int_as_float(__dp4a((int) word_of(w0, wi), word_of(a0, wi), 0x4B400000)), 12582912.f);
+                            const float f1 = __fsub_rn(__int_as_float(__dp4a((int) word_of(w1, wi), word_of(a1, wi), 0x4B400000)), 12582912.f);
+                            acc[j][wi]     = __fmaf_rn(d, f0, acc[j][wi]);
+                            acc[j][4 + wi] = __fmaf_rn(d, f1, acc[j][4 + wi]);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < PB_TOK; j++) {                 // (unrolled: acc[j] stays in registers)
                 const uint8_t * r = stage + w_bytes + (size_t) (warp * PB_TOK + j) * rb;
                 ActSmem A;
                 A.q = (int8_t *) r; A.dx = (float *) (r + 256); A.bp = (int *) (r + 272); A.as = (int *) (r + 304);
-#pragma unroll 1
-                for (int tt = 0; tt < (TYPE == T_Q8_0 ? 8 : 1); tt++) {
+                {
                     BlockInts bi;
-                    tile_ints<TYPE>(stage + (size_t) tt * ud.bytes, lane, TYPE == T_Q8_0 ? tt : 0, A, bi);
+                    tile_ints<TYPE>(stage, lane, 0, A, bi);
                     // chain step in registers, strictly in block order (the per-token kernel's CHAIN_REGS arithmetic)
 #pragma unroll
                     for (int c = 0; c < 8; c++) acc[j][c] = __fmaf_rn(bi.d, (float) bi.s[c], acc[j][c]);
@@ -331,6 +355,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32, 1) k_matmul_batch(const __grid_
                         acc[j][8] = __fadd_rn(acc[j][8], __fmul_rn(bi.dmin, (float) (bi.p[0] + bi.p[1] + bi.p[2] + bi.p[3])));
                     }
                 }
+            }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);        // this warp is done with the stage

@@ -292,7 +292,7 @@ def set_prefill_batch(on: bool) -> None:
 
 
 def set_prefill_mma(mode: int) -> None:
-    """K-quant prompt batches: 2 = tcgen05 / TMEM kernel (default), 1 = mma.sync kernel, 0 = dp4a batch kernel"""
+    """K-quant prompt batches: 1 = mma.sync kernel (default), 2 = tcgen05 / TMEM kernel, 0 = dp4a batch kernel"""
     _lib.lib().b200_set_prefill_mma(int(mode))
 
 

@@ -127,8 +127,8 @@ int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int reps, uint64_
  * weight tile fetched once per 64 tokens), 0 = token by token through the decode kernels. Same arithmetic, bit-identical
  * logits; the switch exists for A/B measurements and for the test that compares the two. Env BOOSTER_B200_PREFILL_BATCH=0. */
 void b200_set_prefill_batch(int on);
-/* K-quant prompt batches: 2 (default) = tcgen05.mma with TMEM accumulators (k_umma_batch), 1 = mma.sync (k_mma_batch),
-   0 = the dp4a batch kernel; all three are bit-identical */
+/* K-quant prompt batches: 1 (default, the fastest measured) = mma.sync HMMA (k_mma_batch), 2 = tcgen05.mma with TMEM
+   accumulators (k_umma_batch), 0 = the dp4a batch kernel; all three are bit-identical */
 void b200_set_prefill_mma(int mode);
 /* 1 (default): prompt-batch attention through k_attn_softmax_rows + k_attn_pv_batch; 0: the per-token kernels over blockIdx.z */
 void b200_set_prefill_attn_batch(int on);

@@ -13,7 +13,7 @@ for cfg in $CFGS; do
   timeout 600 python scripts/prefill_speed.py $cfg 512 3 2>> $OUT/err.txt | tee -a $OUT/speed.txt
   if [ -n "$AB_ENV" ]; then env $AB_ENV timeout 600 python scripts/prefill_speed.py $cfg 512 3 2>> $OUT/err.txt | sed "s/^/[$AB_ENV] /" | tee -a $OUT/speed.txt; fi
   if [ -z "$SKIP_NCU" ]; then
-    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:k_quant_batch|k_matmul_batch|k_mma_batch|k_attn|k_embed_batch' -c ${NCU_C:-80} --csv --log-file $OUT/launches_$cfg.csv \
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:k_quant_batch|k_matmul_batch|k_mma_batch|k_umma_batch|k_attn|k_embed_batch' -c ${NCU_C:-80} --csv --log-file $OUT/launches_$cfg.csv \
         python scripts/ncu_prefill.py $cfg > $OUT/ncu_$cfg.log 2>&1
     python scripts/launch_summary.py $OUT/launches_$cfg.csv | tee $OUT/launches_${cfg}_summary.txt
   fi
