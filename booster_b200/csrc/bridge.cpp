@@ -227,8 +227,23 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
             // one llama_decode of the chunk (cpp/bridge.cpp:549-560): the batched prompt kernels on a pod that sits on one GPU
             if (b200_decode(last, inp.data() + consumed, (int) n, n_past, nullptr) != 0) return 1;
         } else {
-            for (size_t i = 0; i < n; i++) {
-                if (run_token(p, inp[consumed + i], n_past + (int) i, n > 1 ? 1 : 0) != 0) return 1;   // llama_decode failed: bridge.cpp:556-558
+            // a pod split over several GPUs: the chunk goes through every stage's batched kernels in pieces of <= 512 tokens
+            // (one peer copy of the residual streams per stage boundary); token by token where they cannot run
+            for (size_t i0 = 0; i0 < n; ) {
+                const size_t nn = std::min((size_t) 512, n - i0);
+                bool batch = true;
+                for (b200_ctx * c : p.stages) batch = batch && b200_stage_batch_usable(c, (int) nn) == 1;
+                if (batch) {
+                    b200_ctx * prev = nullptr;
+                    for (b200_ctx * c : p.stages) {
+                        if (b200_stage_forward_batch(c, inp.data() + consumed + i0, (int) nn, n_past + (int) i0, prev) != 0) return 1;
+                        prev = c;
+                    }
+                } else {
+                    for (size_t i = i0; i < i0 + nn; i++)
+                        if (run_token(p, inp[consumed + i], n_past + (int) i, n > 1 ? 1 : 0) != 0) return 1;   // llama_decode failed: bridge.cpp:556-558
+                }
+                i0 += nn;
             }
         }
         // every chunk is a blocking llama_decode in the reference (cpp/bridge.cpp:549-560): synchronise the chain end so

@@ -1538,7 +1538,7 @@ static int g_prefill_attn_batch = 1;   // 1: k_attn_softmax_rows + k_attn_pv_bat
 extern "C" void b200_set_prefill_attn_batch(int on) { g_prefill_attn_batch = on ? 1 : 0; }
 static bool prefill_batch_usable(const b200_ctx * c, int n) {
     const b200_model & m = *c->m;
-    if (!prefill_batch_enabled() || n < 8 || c->taps || c->cells.managed || !m.has_embd() || !m.has_head() || m.head_dim != 128) return false;
+    if (!prefill_batch_enabled() || n < 8 || c->taps || c->cells.managed || m.head_dim != 128) return false;   // (stages too: b200_stage_forward_batch)
     const int gqa = m.n_head / m.n_head_kv;
     if (gqa != 1 && gqa != 2 && gqa != 4 && gqa != 8) return false;
     if (g_prefill_attn_batch == 0 && (size_t) gqa * c->n_ctx * 4 + (size_t) PV_BATCH * 16 > 200 * 1024) return false;   // the two-launch attention must fit
@@ -1702,43 +1702,96 @@ static void pb_attention(b200_ctx * c, int li, int T, int pos0) {
         c->launches += 3;
     }
 }
+// the context's layers (a stage's share of them) over the residual streams c->pb.X[T][n_embd] of T tokens at positions p0..
+static void prefill_layers(b200_ctx * c, int T, int p0) {
+    b200_model & m = *c->m;
+    const int E = m.n_embd, FF = m.n_ff, QD = m.n_head * m.head_dim;
+    for (int li = 0; li < (int) m.layers.size(); li++) {
+        LayerW & L = m.layers[(size_t) li];
+        const int q80 = L.qkv.seg[0].type == T_Q8_0;
+        const MatvecArgs aq = args_qkv(c, li), ao = args_wo(c, li), ag = args_gateup(c, li), ad = args_down(c, li);
+        int was = has_q6k(aq.seg, aq.n_seg);
+        pb_quant(c, c->pb.X, E, T, L.attn_norm, q80, was, pb_mma_mode(aq));
+        pb_matmul(c, aq, EPI_QKV, T, p0, nullptr, 0, nullptr, was);
+        switch (m.n_head / m.n_head_kv) {
+            case 1: pb_attention<1>(c, li, T, p0); break;
+            case 2: pb_attention<2>(c, li, T, p0); break;
+            case 4: pb_attention<4>(c, li, T, p0); break;
+            default: pb_attention<8>(c, li, T, p0); break;
+        }
+        was = has_q6k(ao.seg, 1);
+        pb_quant(c, c->pb.ATT, QD, T, nullptr, q80, was, pb_mma_mode(ao));
+        pb_matmul(c, ao, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
+        was = has_q6k(ag.seg, 1);
+        pb_quant(c, c->pb.X, E, T, L.ffn_norm, q80, was, pb_mma_mode(ag));
+        pb_matmul(c, ag, EPI_SILU, T, p0, c->pb.FFH, FF, nullptr, was);
+        was = has_q6k(ad.seg, 1);
+        pb_quant(c, c->pb.FFH, FF, T, nullptr, q80, was, pb_mma_mode(ad));
+        pb_matmul(c, ad, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
+    }
+    CU(cudaGetLastError());
+}
+static void prefill_embed(b200_ctx * c, const int32_t * tokens, int T) {
+    b200_model & m = *c->m;
+    CU(cudaMemcpyAsync(c->pb.tokens, tokens, (size_t) T * 4, cudaMemcpyHostToDevice, c->st));
+    k_embed_batch<<<dim3((unsigned) ((m.n_embd + 255) / 256), (unsigned) T), 256, 0, c->st>>>(m.embd_type, m.embd_rows, m.embd_row_bytes, m.n_embd, c->pb.tokens, c->pb.X);
+    c->launches++;
+}
 // tokens[0..n) at positions pos0..: the whole prompt batch through every layer; leaves the LAST token's residual stream in c->x
 static void prefill_batch(b200_ctx * c, const int32_t * tokens, int n, int pos0) {
     b200_model & m = *c->m;
     prefill_alloc(c);
-    const int E = m.n_embd, FF = m.n_ff, QD = m.n_head * m.head_dim;
     for (int t0 = 0; t0 < n; t0 += PB_MAX_T) {
-        const int T = std::min(PB_MAX_T, n - t0), p0 = pos0 + t0;
-        CU(cudaMemcpyAsync(c->pb.tokens, tokens + t0, (size_t) T * 4, cudaMemcpyHostToDevice, c->st));
-        k_embed_batch<<<dim3((unsigned) ((E + 255) / 256), (unsigned) T), 256, 0, c->st>>>(m.embd_type, m.embd_rows, m.embd_row_bytes, E, c->pb.tokens, c->pb.X);
-        c->launches++;
-        for (int li = 0; li < (int) m.layers.size(); li++) {
-            LayerW & L = m.layers[(size_t) li];
-            const int q80 = L.qkv.seg[0].type == T_Q8_0;
-            const MatvecArgs aq = args_qkv(c, li), ao = args_wo(c, li), ag = args_gateup(c, li), ad = args_down(c, li);
-            int was = has_q6k(aq.seg, aq.n_seg);
-            pb_quant(c, c->pb.X, E, T, L.attn_norm, q80, was, pb_mma_mode(aq));
-            pb_matmul(c, aq, EPI_QKV, T, p0, nullptr, 0, nullptr, was);
-            switch (m.n_head / m.n_head_kv) {
-                case 1: pb_attention<1>(c, li, T, p0); break;
-                case 2: pb_attention<2>(c, li, T, p0); break;
-                case 4: pb_attention<4>(c, li, T, p0); break;
-                default: pb_attention<8>(c, li, T, p0); break;
-            }
-            was = has_q6k(ao.seg, 1);
-            pb_quant(c, c->pb.ATT, QD, T, nullptr, q80, was, pb_mma_mode(ao));
-            pb_matmul(c, ao, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
-            was = has_q6k(ag.seg, 1);
-            pb_quant(c, c->pb.X, E, T, L.ffn_norm, q80, was, pb_mma_mode(ag));
-            pb_matmul(c, ag, EPI_SILU, T, p0, c->pb.FFH, FF, nullptr, was);
-            was = has_q6k(ad.seg, 1);
-            pb_quant(c, c->pb.FFH, FF, T, nullptr, q80, was, pb_mma_mode(ad));
-            pb_matmul(c, ad, EPI_RESID, T, p0, c->pb.X, E, c->pb.X, was);
-        }
-        CU(cudaGetLastError());
+        const int T = std::min(PB_MAX_T, n - t0);
+        prefill_embed(c, tokens + t0, T);
+        prefill_layers(c, T, pos0 + t0);
     }
     const int last = (n - 1) % PB_MAX_T;
-    CU(cudaMemcpyAsync(c->x, c->pb.X + (size_t) last * E, (size_t) E * 4, cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(c->x, c->pb.X + (size_t) last * m.n_embd, (size_t) m.n_embd * 4, cudaMemcpyDeviceToDevice, c->st));
+}
+
+// In-process layer split (bridge pods over several GPUs): one prompt chunk of n <= 512 tokens through THIS stage's layers with
+// the batched kernels. The first stage embeds the tokens; every other stage takes the predecessor's residual streams
+// [n][n_embd] with one peer copy (the batch counterpart of b200_stage_forward's hand-off, same events); the last stage
+// leaves the logits of the chunk's last token. Returns 2 when the batched kernels cannot run this chunk (the caller then
+// feeds the tokens one by one through b200_stage_forward).
+extern "C" int b200_stage_batch_usable(b200_ctx * c, int n) { return c && n <= PB_MAX_T && prefill_batch_usable(c, n) ? 1 : 0; }
+extern "C" int b200_stage_forward_batch(b200_ctx * c, const int32_t * tokens, int n, int pos0, b200_ctx * prev) {
+    try {
+        require_gpu();
+        if (!c || !tokens || n <= 0) throw std::runtime_error("bad arguments");
+        b200_model & m = *c->m;
+        if (pos0 < 0 || pos0 + n > c->n_ctx) throw std::runtime_error("positions exceed n_ctx");
+        if (m.has_embd() != (prev == nullptr)) throw std::runtime_error("stage chain mismatch: only the first stage has no predecessor");
+        if (m.has_embd()) for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= m.n_vocab) throw std::runtime_error("token id out of range");
+        if (n > PB_MAX_T || !prefill_batch_usable(c, n) || (prev && !prev->pb.cap)) return 2;
+        CU(cudaSetDevice(m.device));
+        prefill_alloc(c);
+        if (c->taken_pending) { CU(cudaStreamWaitEvent(c->st, c->ev_taken, 0)); c->taken_pending = false; }
+        if (prev) {
+            if (!prev->ev_done) { CU(cudaSetDevice(prev->m->device)); CU(cudaEventCreateWithFlags(&prev->ev_done, cudaEventDisableTiming)); CU(cudaSetDevice(m.device)); }
+            if (!prev->ev_taken) CU(cudaEventCreateWithFlags(&prev->ev_taken, cudaEventDisableTiming));
+            CU(cudaSetDevice(prev->m->device));
+            CU(cudaEventRecord(prev->ev_done, prev->st));
+            CU(cudaSetDevice(m.device));
+            CU(cudaStreamWaitEvent(c->st, prev->ev_done, 0));
+            CU(cudaMemcpyPeerAsync(c->pb.X, m.device, prev->pb.X, prev->m->device, (size_t) n * m.n_embd * 4, c->st));
+            CU(cudaEventRecord(prev->ev_taken, c->st));
+            prev->taken_pending = true;
+        } else {
+            prefill_embed(c, tokens, n);
+        }
+        note_positions(c, pos0 + n);
+        prefill_layers(c, n, pos0);
+        if (m.has_head()) {
+            CU(cudaMemcpyAsync(c->x, c->pb.X + (size_t) (n - 1) * m.n_embd, (size_t) m.n_embd * 4, cudaMemcpyDeviceToDevice, c->st));
+            g_only_kind = KIND_HEAD;
+            try { enqueue_forward(c); } catch (...) { g_only_kind = -1; throw; }
+            g_only_kind = -1;
+        }
+        CU(cudaGetLastError());
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
 }
 
 extern "C" int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, float * logits_out) {
@@ -1753,7 +1806,7 @@ extern "C" int b200_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0
         const double t0 = now_us();
         // reference semantics for batch > 1: q is rounded to f16 before K.q (cpp/ggml/src/ggml.c:12345-12371)
         const int round_q = n > 1 ? 1 : 0;
-        if (prefill_batch_usable(c, n)) {
+        if (prefill_batch_usable(c, n)) {   // (b200_decode is single-stage: checked above)
             // the prompt batch through the batched kernels, then the head on the last token's residual stream
             note_positions(c, pos0 + n);
             prefill_batch(c, tokens, n, pos0);

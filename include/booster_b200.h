@@ -178,6 +178,12 @@ int b200_pipeline_decode(b200_ctx * c, const int32_t * tokens, int n, int pos0, 
  * batch_gt1 != 0 selects the reference's batch>1 arithmetic (q rounded to f16 before K.q).
  * b200_stage_logits / b200_stage_argmax synchronise and read the LAST stage's result.                       */
 int b200_stage_forward(b200_ctx * c, int32_t token, int pos, int batch_gt1, b200_ctx * prev);
+/* one prompt chunk of n <= 512 tokens through THIS stage's layers with the batched prompt kernels (first stage: embeds `tokens`;
+   others: take the predecessor's residual streams [n][n_embd] with one peer copy; last stage: logits of the chunk's last token).
+   b200_stage_batch_usable(c, n) == 1 says whether the batched kernels can run the chunk on this stage (same answer on every
+   stage of a pod); b200_stage_forward_batch returns 2 without doing anything when they cannot. */
+int b200_stage_batch_usable(b200_ctx * c, int n);
+int b200_stage_forward_batch(b200_ctx * c, const int32_t * tokens, int n, int pos0, b200_ctx * prev);
 int b200_stage_sync(b200_ctx * c);    /* wait for everything enqueued on this stage (llama_synchronize, cpp/src/llama.cpp:18536) */
 int b200_stage_logits(b200_ctx * c, float * logits_out);
 int b200_stage_argmax(b200_ctx * c, int32_t * token_out);

@@ -298,3 +298,37 @@ def test_in_process_stage_split_equals_single_stage(golden_dir):
         x.close()
     for x in (m, m0, m1):
         x.close()
+
+
+def test_in_process_stage_split_prompt_batch(model_dir):
+    """a prompt chunk through the batched prompt kernels of every stage of an in-process layer split (b200_stage_forward_batch:
+    one peer copy of the residual streams [n][n_embd] per boundary) == the single-stage batch == token by token: logits,
+    and the greedy continuation through the per-token stage path on the KV rows the batch wrote. Two devices when present."""
+    import ctypes as C
+    path = _synth(model_dir, "llama3-8b-2l", "Q4_K_M")
+    conf = G.CONFIGS["llama3-8b-2l"]
+    prompt = np.random.default_rng(77).integers(0, conf.n_vocab, size=150).tolist()
+    m = engine.Model(path); c = engine.Context(m, 256)
+    full = c.decode(prompt, 0)
+    nxt = c.decode([int(np.argmax(full))], len(prompt))
+    d1 = 1 if engine.device_count() > 1 else 0
+    m0 = engine.Model(path, 0, 0, 1); m1 = engine.Model(path, d1, 1, 2)
+    c0 = engine.Context(m0, 256); c1 = engine.Context(m1, 256)
+    L = m.L
+    toks = (C.c_int32 * len(prompt))(*prompt)
+    out = np.empty(m.n_vocab, dtype=np.float32)
+    for rep in range(2):
+        assert L.b200_stage_batch_usable(c0.h, len(prompt)) == 1 and L.b200_stage_batch_usable(c1.h, len(prompt)) == 1
+        engine.check(L.b200_stage_forward_batch(c0.h, toks, len(prompt), 0, None), "stage 0 batch")
+        engine.check(L.b200_stage_forward_batch(c1.h, toks, len(prompt), 0, c0.h), "stage 1 batch")
+        engine.check(L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))), "logits")
+        _same(out, full, f"prompt batch through 2 stages (rep {rep})")
+    t = int(np.argmax(out))
+    engine.check(L.b200_stage_forward(c0.h, t, len(prompt), 0, None), "stage 0")
+    engine.check(L.b200_stage_forward(c1.h, t, len(prompt), 0, c0.h), "stage 1")
+    engine.check(L.b200_stage_logits(c1.h, out.ctypes.data_as(C.POINTER(C.c_float))), "logits")
+    _same(out, nxt, "decode after the staged prompt batch")
+    for x in (c, c0, c1):
+        x.close()
+    for x in (m, m0, m1):
+        x.close()
