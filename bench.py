@@ -193,6 +193,9 @@ def bridge_e2e(path, ctx, n_prompt, n_gen, reps):
                     marks["first"] = (now, n - n_prompt)
                 if n > n_prompt:
                     marks["last"] = (now, n - n_prompt)
+                # a streaming client polls at intervals (the Go server answers status requests, pkg/server/server.go:842-863);
+                # a spinning poller starves doInference's own lock / this process's GIL hand-back by tens of ms at job end
+                time.sleep(0.0002)
 
         th = threading.Thread(target=poll)
         th.start()
