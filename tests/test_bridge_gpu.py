@@ -175,3 +175,28 @@ def test_do_inference_janus_sampler_equals_reference_golden(kind, tmp_path, gold
         want = b"".join(tok.piece(t, True) for t in c["prompt"] + c["ids"])
         assert L.status(job) == want, (c["depth"], c["scale"], c["hi"], c["lo"], c["seed"])
     tok.close()
+
+
+def test_pod_split_over_two_gpus_equals_one_gpu(model_dir):
+    """the reference's gpu1 / gpu2 proportions (pkg/server/server.go:514-530 -> tensor_split): a pod whose layers sit on two
+    devices — prompt chunk through b200_stage_forward_batch (peer copy of the residual streams), generation through the
+    per-token stage chain — publishes the same ids as the pod on one device. Needs two visible GPUs."""
+    from booster_b200 import engine, gguf_io as G
+    if engine.device_count() < 2:
+        pytest.skip("one visible GPU")
+    path = os.path.join(model_dir, "llama3-8b-2l_Q4_K_M_s7.gguf")
+    if not os.path.exists(path):
+        G.synth_llama(path, G.CONFIGS["llama3-8b-2l"], "Q4_K_M", seed=7, source="blocks")
+    prompt = " ".join(str(int(t)) for t in np.random.default_rng(5).integers(0, 4096, size=120)).encode()
+    L = _lib.lib()
+    L.init(b"", b"")
+    texts = []
+    for idx, (g1, g2) in ((4, (100, 0)), (5, (50, 50))):
+        ctx = L.initContext(idx, path.encode(), 1, 0, g1, g2, 0, 0, 256, 12, 0, 0.0, 0.0, 0.0, 1, 1.0, 1.0, 1.0, 0, 1, 200,
+                            1.0, 1.0, 1.0, 42, b"")
+        assert ctx
+        job = f"split-{idx}".encode()
+        assert L.doInference(idx, ctx, job, b"", prompt) == 120 + 11
+        texts.append(L.status(job).decode())
+    assert texts[0] == texts[1]
+    assert len(texts[0].split()) == 132
