@@ -1639,14 +1639,14 @@ static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int p
         return;
     }
     if (mma_mode == 1) {
-        a.mb_a_bytes = (uint32_t) mb_a_bytes(q6);
+        a.mb_a_bytes = (uint32_t) mb_a_bytes(q6);             // one of the two A buffers
         a.mb_raw_stride = (uint32_t) ((sb + 127) / 128 * 128);
         a.mb_rec_copy = (uint32_t) mb_rec_copy_bytes(q4, q5);
         a.mb_stage_bytes = 2 * a.mb_raw_stride + (a.mb_rec_copy + 127) / 128 * 128;
         const size_t budget = 226 * 1024;
-        a.mb_stages = (int) std::min<size_t>(MB_MAX_STAGES, (budget - a.mb_a_bytes) / a.mb_stage_bytes);
+        a.mb_stages = (int) std::min<size_t>(MB_MAX_STAGES, (budget - 2 * a.mb_a_bytes) / a.mb_stage_bytes);
         if (a.mb_stages < 2) throw std::runtime_error("k_mma_batch: shared memory layout does not fit");
-        const size_t smem_m = std::max((size_t) a.mb_a_bytes + (size_t) a.mb_stages * a.mb_stage_bytes, (size_t) MB_CHAIN_BYTES);
+        const size_t smem_m = std::max((size_t) 2 * a.mb_a_bytes + (size_t) a.mb_stages * a.mb_stage_bytes, (size_t) MB_CHAIN_BYTES);
         static size_t attr_m[64] = {0};
         if (smem_m > attr_m[c->device & 63]) {
             std::lock_guard<std::mutex> lk(g_attr_mu);

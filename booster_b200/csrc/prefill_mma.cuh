@@ -56,7 +56,9 @@ static constexpr int MB_A_PART = 8 * MB_ROWS * 64;
 static constexpr int MB_A_MINS = MB_ROWS * 32;
 static constexpr int MB_A_SCAL = MB_ROWS * 8;
 __host__ __device__ __forceinline__ int mb_a_bytes(bool q6) { return (q6 ? 2 : 1) * MB_A_PART + MB_A_MINS + MB_A_SCAL; }
-static constexpr int MB_CHAIN_BYTES = 12 * MB_NT * MB_ROWS * 4;   // final chain exchange (re-uses the operand / stage memory)
+static constexpr int MB_CH_STRIDE = MB_ROWS + 4;                     // floats per (chain, token) row of the final exchange: +4 keeps the
+                                                                     // fragment-order stores (8 rows x 4 token pairs per instruction) conflict-free
+static constexpr int MB_CHAIN_BYTES = 12 * MB_NT * MB_CH_STRIDE * 4; // final chain exchange (re-uses the operand / stage memory)
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -310,10 +312,9 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch(const __grid_con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunk = blockIdx.x, unit0 = 2 * blockIdx.y;
     const UnitDesc ud = pb_describe_unit(a, unit0), ud1 = pb_describe_unit(a, unit0 + 1);   // same segment (host: even unit counts)
-    uint8_t * As = mb_smem;
-    uint8_t * stages = mb_smem + a.mb_a_bytes;
+    // the A operand is double-buffered: step b+1 is expanded while the tensor cores work on step b (one barrier per K step)
+    uint8_t * stages = mb_smem + 2 * a.mb_a_bytes;
     const uint32_t mins_off = a.mb_a_bytes - (MB_A_MINS + MB_A_SCAL);
-    const float * scal = reinterpret_cast<const float *>(As + mins_off + MB_A_MINS);
     const int n_steps = a.tiles_unit, n_stages = a.mb_stages;
     const uint32_t bar0 = smem_u32(&bars[0]);
     if (tid == 0) {
@@ -344,20 +345,26 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch(const __grid_con
                 for (int e = 0; e < 4; e++) { acc[i][j][e] = 0.f; accm[j][e] = 0.f; }
             }
         }
-        int s = 0;
-        uint32_t par = 0;
+        mbar_wait(bar0, 0u);
+        mb_expand<TYPE>(stages, a.mb_raw_stride, mb_smem, mins_off, warp, lane);
+        __syncthreads();
+        int s = 0, s1 = n_stages > 1 ? 1 : 0;                    // stage of step b, of step b + 1
+        uint32_t par1 = n_stages > 1 ? 0u : 1u;                  // full-flag parity of step b + 1's use of its stage
         for (int step = 0; step < n_steps; step++) {
-            mbar_wait(bar0 + 8 * s, par);
-            const uint8_t * stage = stages + (size_t) s * a.mb_stage_bytes;
-            mb_expand<TYPE>(stage, a.mb_raw_stride, As, mins_off, warp, lane);
-            __syncthreads();
-            const uint8_t * rec = stage + 2 * a.mb_raw_stride;
+            const uint8_t * As = mb_smem + (size_t) (step & 1) * a.mb_a_bytes;
+            const float * scal = reinterpret_cast<const float *>(As + mins_off + MB_A_MINS);
+            const uint8_t * rec = stages + (size_t) s * a.mb_stage_bytes + 2 * a.mb_raw_stride;
             mb_mma_main<TYPE>(As, rec, scal, warp, lane, acc);
             if (TYPE == T_Q4_K) mb_mma_mins4(As, mins_off, rec, scal, warp, lane, accm);
             if (TYPE == T_Q5_K) mb_mma_mins5(As, mins_off, rec, scal, warp, lane, accm[0]);
-            __syncthreads();                                   // the A operand and stage s are free
+            if (step + 1 < n_steps) {
+                mbar_wait(bar0 + 8 * s1, par1);
+                mb_expand<TYPE>(stages + (size_t) s1 * a.mb_stage_bytes, a.mb_raw_stride, mb_smem + (size_t) ((step + 1) & 1) * a.mb_a_bytes, mins_off, warp, lane);
+            }
+            __syncthreads();                                   // A[step & 1] and stage s are free, A[(step + 1) & 1] is complete
             if (tid == 0 && step + n_stages < n_steps) issue(step + n_stages, s);
-            if (++s == n_stages) { s = 0; par ^= 1u; }
+            s = s1;
+            if (++s1 == n_stages) { s1 = 0; par1 ^= 1u; }
         }
         // the 12 chains of every output meet in shared memory: CH[c][token][row]
         float * CH = reinterpret_cast<float *>(mb_smem);
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch(const __grid_con
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const int row = rh * 32 + mt * 16 + (lane >> 2) + 8 * (e >> 1), t = nt * 8 + 2 * (lane & 3) + (e & 1);
-                        CH[(m * MB_NT + t) * MB_ROWS + row] = acc[mt][nt][e];
+                        CH[(m * MB_NT + t) * MB_CH_STRIDE + row] = acc[mt][nt][e];
                     }
                 }
             }
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch(const __grid_con
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const int row = mt * 16 + (lane >> 2) + 8 * (e >> 1), t = 8 * tq + 2 * nt + ((lane & 3) >> 1), l = 2 * (lane & 1) + (e & 1);
-                        CH[((8 + l) * MB_NT + t) * MB_ROWS + row] = accm[nt][e];
+                        CH[((8 + l) * MB_NT + t) * MB_CH_STRIDE + row] = accm[nt][e];
                     }
                 }
             }
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch(const __grid_con
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int row = mt * 16 + (lane >> 2) + 8 * (e >> 1), t = 8 * nt + 2 * (lane & 3) + (e & 1);
-                    CH[(8 * MB_NT + t) * MB_ROWS + row] = accm[0][e];
+                    CH[(8 * MB_NT + t) * MB_CH_STRIDE + row] = accm[0][e];
                 }
             }
         }
@@ -402,7 +409,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch(const __grid_con
                 const int t = tb + 8 * jj;
                 float c[12];
 #pragma unroll
-                for (int i = 0; i < n_chains<TYPE>(); i++) c[i] = CH[(i * MB_NT + t) * MB_ROWS + r];
+                for (int i = 0; i < n_chains<TYPE>(); i++) c[i] = CH[(i * MB_NT + t) * MB_CH_STRIDE + r];
                 const float val = finish_row<TYPE>(c);
                 pb_epilogue(a, val, ud.row0 + r, lane, chunk * MB_NT + t);
             }
