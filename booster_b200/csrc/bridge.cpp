@@ -219,6 +219,7 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
     b200_ctx * last = p.stages.back();
 
     // ---- prompt, in chunks of n_batch (cpp/bridge.cpp:549-560, 613-624); pieces are published per chunk
+    static const bool pipeline_chunks = [] { const char * e = std::getenv("BOOSTER_B200_PIPELINE_CHUNKS"); return !(e && e[0] == '0'); }();   // A/B switch
     size_t consumed = 0;
     while (consumed < inp.size() && !g_stop[idx].load()) {
         const size_t n = std::min((size_t) p.n_batch, inp.size() - consumed);
@@ -247,8 +248,12 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
             }
         }
         // every chunk is a blocking llama_decode in the reference (cpp/bridge.cpp:549-560): synchronise the chain end so
-        // that the chunk's time is the prompt's and not the first generated token's
-        if (b200_stage_sync(last) != 0) return 1;
+        // that the chunk's time is the prompt's and not the first generated token's. A pod split over several GPUs keeps its
+        // prompt chunks IN FLIGHT instead: chunk i+1 runs on the first stage while chunk i runs on the next one (the events of
+        // the hand-off order them; what ggml's scheduler does with GGML_SCHED_MAX_COPIES micro-batches,
+        // cpp/ggml/src/ggml-backend.c:1029-1030) and only the last chunk is waited for
+        const bool last_chunk = consumed + n >= inp.size();
+        if (p.stages.size() == 1 || last_chunk || !pipeline_chunks) { if (b200_stage_sync(last) != 0) return 1; }
         const double dt = now_us() - t0;
         if (n > 1) { t_p_us += dt; n_p_eval += (int64_t) n; } else { t_e_us += dt; n_eval += 1; }
         n_past += (int) n;
@@ -257,6 +262,7 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
         { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += pieces; }
         consumed += n;
     }
+    if (p.stages.size() > 1 && b200_stage_sync(last) != 0) return 1;   // (a stopped job may have left chunks in flight)
 
     // ---- generation: sample, then decode the sampled token (cpp/bridge.cpp:586-646).
     //   janus != 0 (what the reference always does): the logits come to the host once per token and the Janus sampler picks;

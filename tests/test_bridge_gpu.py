@@ -191,12 +191,13 @@ def test_pod_split_over_two_gpus_equals_one_gpu(model_dir):
     L = _lib.lib()
     L.init(b"", b"")
     texts = []
-    for idx, (g1, g2) in ((4, (100, 0)), (5, (50, 50))):
-        ctx = L.initContext(idx, path.encode(), 1, 0, g1, g2, 0, 0, 256, 12, 0, 0.0, 0.0, 0.0, 1, 1.0, 1.0, 1.0, 0, 1, 200,
+    # (one GPU, 512-token chunks) / (two GPUs, one chunk) / (two GPUs, chunks of 32 kept in flight across the stages)
+    for idx, (g1, g2, nb) in ((4, (100, 0, 0)), (5, (50, 50, 0)), (6, (50, 50, 32))):
+        ctx = L.initContext(idx, path.encode(), 1, nb, g1, g2, 0, 0, 256, 12, 0, 0.0, 0.0, 0.0, 1, 1.0, 1.0, 1.0, 0, 1, 200,
                             1.0, 1.0, 1.0, 42, b"")
         assert ctx
         job = f"split-{idx}".encode()
         assert L.doInference(idx, ctx, job, b"", prompt) == 120 + 11
         texts.append(L.status(job).decode())
-    assert texts[0] == texts[1]
+    assert texts[0] == texts[1] == texts[2]
     assert len(texts[0].split()) == 132
