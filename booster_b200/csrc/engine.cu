@@ -1569,7 +1569,11 @@ extern "C" void b200_set_prefill_mma(int mode) { g_prefill_mma = mode < 0 ? 0 : 
 // record layout / kernel of a K-quant launch: 2 = k_umma_batch (segments of a multiple of 4 units), 1 = k_mma_batch (even), 0 = dp4a
 static int pb_mma_mode(const MatvecArgs & mv) {
     if (g_prefill_mma < 0) { const char * e = getenv("BOOSTER_B200_PREFILL_MMA"); g_prefill_mma = e ? std::max(0, std::min(2, atoi(e))) : 1; }
-    if (g_prefill_mma == 0 || mv.act_q8_0) return 0;
+    if (g_prefill_mma == 0) return 0;
+    if (mv.act_q8_0) {   // Q8_0 x Q8_0: block-diagonal HMMA (k_mma_batch_q80)
+        for (int i = 0; i < mv.n_seg; i++) if (mv.seg[i].type != T_Q8_0 || (mv.seg[i].n_units & 1)) return 0;
+        return 3;
+    }
     int mode = g_prefill_mma;
     for (int i = 0; i < mv.n_seg; i++) {
         const int t = mv.seg[i].type;
@@ -1618,6 +1622,25 @@ static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int p
     const int mma_mode = pb_mma_mode(mv);
     bool q4 = false, q5 = false, q6 = false;
     for (int i = 0; i < mv.n_seg; i++) { q4 |= mv.seg[i].type == T_Q4_K; q5 |= mv.seg[i].type == T_Q5_K; q6 |= mv.seg[i].type == T_Q6_K; }
+    if (mma_mode == 3) {
+        a.mb_a_bytes = (uint32_t) Q80_A_BYTES;
+        a.mb_raw_stride = (uint32_t) ((8 * sb + 127) / 128 * 128);
+        a.mb_rec_copy = (uint32_t) Q80_REC_BYTES;
+        a.mb_stage_bytes = 2 * a.mb_raw_stride + (a.mb_rec_copy + 127) / 128 * 128;
+        a.mb_stages = (int) std::min<size_t>(MB_MAX_STAGES, ((size_t) 226 * 1024 - 2 * a.mb_a_bytes) / a.mb_stage_bytes);
+        if (a.mb_stages < 2) throw std::runtime_error("k_mma_batch_q80: shared memory layout does not fit");
+        const size_t smem_q = (size_t) 2 * a.mb_a_bytes + (size_t) a.mb_stages * a.mb_stage_bytes;
+        static size_t attr_q[64] = {0};
+        if (smem_q > attr_q[c->device & 63]) {
+            std::lock_guard<std::mutex> lk(g_attr_mu);
+            CU(cudaFuncSetAttribute(k_mma_batch_q80, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_q));
+            attr_q[c->device & 63] = smem_q;
+        }
+        const dim3 grid_q((unsigned) ((T + MB_NT - 1) / MB_NT), (unsigned) (a.n_units / 2));
+        k_mma_batch_q80<<<grid_q, MB_WARPS * 32, smem_q, c->st>>>(a);
+        c->launches++;
+        return;
+    }
     if (mma_mode == 2) {
         a.mb_a_bytes = (uint32_t) um_a_bytes(q6);
         a.mb_raw_stride = (uint32_t) ((sb + 127) / 128 * 128);

@@ -422,4 +422,176 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch(const __grid_con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Q8_0 x Q8_0 prompt batches on the tensor cores. The reference (tinyBLAS_Q0_AVX, cpp/ggml/src/llamafile/sgemm.cpp) keeps 8
+// fp32 lanes per output: lane m sums the FOUR products of bytes 4m..4m+3 of a 32-weight block (dpbusd) and runs
+// acc[m] = fma(d_w d_a, (float) isum[m], acc[m]) block after block. A 4-term contraction is exactly a dp4a — but it is also
+// an m16n8k16 MMA with a block-diagonal B: K = 16 = four lanes x four bytes, the eight B columns = (2 tokens x 4 lanes), column
+// (t, q) carrying token t's bytes only in rows 4q..4q+3. One HMMA then returns 128 lane sums as exact floats (|isum| <= 4 *
+// 127 * 127 < 2^24, operands are int8 values in fp16), at a quarter of the tensor density but OFF the CUDA cores, which keep
+// only the ordered chain step (8 FFMA per output and block instead of 8 dp4a + 8 FADD + 8 FFMA).
+//   CTA 64 rows x 32 tokens, 16 warps; per K step of 256 weights: TMA bulk copies of the 2 x 8 raw tiles + the chunk's fp16
+//   activation rows; 512 threads expand int8 -> fp16 A rows (double-buffered); warp (16-row tile mt = w & 3, 8 tokens
+//   tq = w >> 2): per block 2 ldmatrix.x4 (A), 8 predicated 4-byte B loads, 8 HMMA, 32 chain FFMA.
+// ------------------------------------------------------------------------------------------------------------
+static constexpr int Q80_ROW = 512 + 16;                               // bytes of a token's 256 fp16 activations (+16: bank spread)
+static constexpr int Q80_OFF_DX = MB_NT * Q80_ROW;                     // f32 [32 tokens][8 blocks]
+static constexpr int Q80_REC_BYTES = Q80_OFF_DX + MB_NT * 8 * 4;       // 17920
+static constexpr int Q80_A_BYTES = 8 * 2 * MB_ROWS * 32 + 8 * MB_ROWS * 4;   // fp16 rows [block][16-group][row][16] | f32 d [block][row]
+
+// k_quant_batch_mma, layout 3: token t's Q8_0 image (natural order) -> fp16 rows + block scales
+__device__ __forceinline__ void q80_write_records(const ActSmem & A, int n256, uint8_t * rec, int t, int lane, int warp, int W) {
+    const int chunk = t / MB_NT, j = t % MB_NT;
+    for (int b = warp; b < n256; b += W) {
+        uint8_t * r = rec + ((size_t) chunk * n256 + b) * Q80_REC_BYTES;
+        const uint2 w = *reinterpret_cast<const uint2 *>(A.q + (size_t) b * 256 + lane * 8);
+        uint4 o;
+        o.x = h2_ints(sbyte_of(w.x, 0), sbyte_of(w.x, 1)); o.y = h2_ints(sbyte_of(w.x, 2), sbyte_of(w.x, 3));
+        o.z = h2_ints(sbyte_of(w.y, 0), sbyte_of(w.y, 1)); o.w = h2_ints(sbyte_of(w.y, 2), sbyte_of(w.y, 3));
+        *reinterpret_cast<uint4 *>(r + j * Q80_ROW + lane * 16) = o;
+        if (lane < 8) *reinterpret_cast<float *>(r + Q80_OFF_DX + (j * 8 + lane) * 4) = A.dx[b * 8 + lane];
+    }
+}
+
+__global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch_q80(const __grid_constant__ MatmulBatchArgs a) {
+    extern __shared__ __align__(128) uint8_t q8_smem[];
+    __shared__ __align__(8) uint64_t bars[MB_MAX_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = blockIdx.x, unit0 = 2 * blockIdx.y;
+    const UnitDesc ud = pb_describe_unit(a, unit0), ud1 = pb_describe_unit(a, unit0 + 1);
+    uint8_t * stages = q8_smem + 2 * Q80_A_BYTES;
+    const int n_steps = a.tiles_unit / 8, n_stages = a.mb_stages;      // a K step = eight 32-weight tiles per unit
+    const uint32_t raw_bytes = 8 * ud.bytes;
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; s++) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const uint8_t * rec_chunk = a.rec + (size_t) chunk * n_steps * Q80_REC_BYTES;
+    auto issue = [&](int step, int s) {
+        const uint32_t dst = smem_u32(stages + (size_t) s * a.mb_stage_bytes), bar = bar0 + 8 * s;
+        mbar_expect_tx(bar, 2 * raw_bytes + Q80_REC_BYTES);
+        bulk_g2s(dst, ud.tiles + (size_t) step * raw_bytes, raw_bytes, bar);
+        bulk_g2s(dst + a.mb_raw_stride, ud1.tiles + (size_t) step * raw_bytes, raw_bytes, bar);
+        bulk_g2s(dst + 2 * a.mb_raw_stride, rec_chunk + (size_t) step * Q80_REC_BYTES, Q80_REC_BYTES, bar);
+    };
+    if (tid == 0) { for (int s = 0; s < n_stages && s < n_steps; s++) issue(s, s); }
+
+    // int8 -> fp16 rows of the A operand: warp = (unit u, tile tt), lane = row; both 16-byte halves of the block
+    auto expand = [&](const uint8_t * stage, uint8_t * As) {
+        const int u = warp >> 3, tt = warp & 7, r = u * 32 + lane;
+        const uint8_t * tile = stage + (size_t) u * a.mb_raw_stride + (size_t) tt * ud.bytes;
+        const __half2 c1152 = __half2half2(__int2half_rn(1152));
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint4 w = lds_u4(tile + h * 512 + lane * 16);
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t x = word_of(w, i) ^ 0x80808080u;        // b + 128 in 0..255; (0x6400 | v) = 1024 + v
+                o[2 * i]     = h2_bits(__hsub2(bits_h2(__byte_perm(x, 0x64646464u, 0x4140u)), c1152));
+                o[2 * i + 1] = h2_bits(__hsub2(bits_h2(__byte_perm(x, 0x64646464u, 0x4342u)), c1152));
+            }
+            uint8_t * dst = As + (size_t) (tt * 2 + h) * (MB_ROWS * 32) + r * 32;
+            const uint32_t sw = (uint32_t) ((r >> 2) & 1);
+            *reinterpret_cast<uint4 *>(dst + ((0u ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4 *>(dst + ((1u ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        float * dwb = reinterpret_cast<float *>(As + 8 * 2 * MB_ROWS * 32);
+        dwb[tt * MB_ROWS + r] = __half2float(*reinterpret_cast<const __half *>(tile + 1024 + lane * 2));
+    };
+
+    const int mt = warp & 3, tq = warp >> 2;
+    float acc[4][2][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[i][g][e] = 0.f;
+        }
+    }
+    mbar_wait(bar0, 0u);
+    expand(stages, q8_smem);
+    __syncthreads();
+    int s = 0, s1 = n_stages > 1 ? 1 : 0;
+    uint32_t par1 = n_stages > 1 ? 0u : 1u;
+    // fragment constants: A rows for ldmatrix; the B element this thread supplies: rows k = 2 (lane & 3) [+8], column (token
+    // lane >> 4, lane-in-group q = (lane >> 2) & 3); it is non-zero only when k's group of four equals q
+    const int rl = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kc = lane >> 4;
+    const uint32_t a_off = (uint32_t) (rl * 32) + ((((uint32_t) kc) ^ ((rl >> 2) & 1)) << 4);
+    const int q = (lane >> 2) & 3, kq = (lane & 3) >> 1;
+    const bool b_on = (q & 1) == kq;                       // k / 4 == q  (b0 holds k < 8: q in {0, 1}; b1 holds k >= 8: q in {2, 3})
+    const uint32_t b_elem = (uint32_t) (2 * (lane & 3) + (q >= 2 ? 8 : 0)) * 2;
+    const int r0 = mt * 16 + (lane >> 2);
+    for (int step = 0; step < n_steps; step++) {
+        const uint8_t * As = q8_smem + (size_t) (step & 1) * Q80_A_BYTES;
+        const float * dwb = reinterpret_cast<const float *>(As + 8 * 2 * MB_ROWS * 32);
+        const uint8_t * rec = stages + (size_t) s * a.mb_stage_bytes + 2 * a.mb_raw_stride;
+        const float * dxr = reinterpret_cast<const float *>(rec + Q80_OFF_DX);
+#pragma unroll 1
+        for (int tt = 0; tt < 8; tt++) {
+            uint32_t af[2][4];
+            ldsm_x4(af[0], smem_u32(As) + (uint32_t) (tt * 2) * (MB_ROWS * 32) + a_off);
+            ldsm_x4(af[1], smem_u32(As) + (uint32_t) (tt * 2 + 1) * (MB_ROWS * 32) + a_off);
+            const float dw0 = dwb[tt * MB_ROWS + r0], dw1 = dwb[tt * MB_ROWS + r0 + 8];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const int tk = 8 * tq + 2 * nt;
+                const uint8_t * brow = rec + (size_t) (tk + (lane >> 4)) * Q80_ROW + (size_t) tt * 64 + b_elem;
+                const float dxv = dxr[(tk + ((lane & 3) >> 1)) * 8 + tt];
+                const float d0 = __fmul_rn(dw0, dxv), d1 = __fmul_rn(dw1, dxv);            // fp16(x.d) * fp16(y.d)
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const uint32_t v = *reinterpret_cast<const uint32_t *>(brow + g * 32);
+                    const uint32_t bv = b_on ? v : 0u;
+                    float c[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_f16(c, af[g], q < 2 ? bv : 0u, q < 2 ? 0u : bv);
+                    acc[nt][g][0] = __fmaf_rn(d0, c[0], acc[nt][g][0]);
+                    acc[nt][g][1] = __fmaf_rn(d0, c[1], acc[nt][g][1]);
+                    acc[nt][g][2] = __fmaf_rn(d1, c[2], acc[nt][g][2]);
+                    acc[nt][g][3] = __fmaf_rn(d1, c[3], acc[nt][g][3]);
+                }
+            }
+        }
+        if (step + 1 < n_steps) {
+            mbar_wait(bar0 + 8 * s1, par1);
+            expand(stages + (size_t) s1 * a.mb_stage_bytes, q8_smem + (size_t) ((step + 1) & 1) * Q80_A_BYTES);
+        }
+        __syncthreads();
+        if (tid == 0 && step + n_stages < n_steps) issue(step + n_stages, s);
+        s = s1;
+        if (++s1 == n_stages) { s1 = 0; par1 ^= 1u; }
+    }
+    // the 8 lanes of every output meet in shared memory: CH[m][token][row]
+    float * CH = reinterpret_cast<float *>(q8_smem);
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int row = r0 + 8 * (e >> 1), t = 8 * tq + 2 * nt + ((lane & 3) >> 1), m = 4 * g + 2 * (lane & 1) + (e & 1);
+                CH[(m * MB_NT + t) * MB_CH_STRIDE + row] = acc[nt][g][e];
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int r = tid & (MB_ROWS - 1), tb = tid >> 6;
+#pragma unroll 1
+        for (int jj = 0; jj < 4; jj++) {
+            const int t = tb + 8 * jj;
+            float c[12];
+#pragma unroll
+            for (int i = 0; i < 8; i++) c[i] = CH[(i * MB_NT + t) * MB_CH_STRIDE + r];
+            const float val = finish_row<T_Q8_0>(c);
+            pb_epilogue(a, val, ud.row0 + r, lane, chunk * MB_NT + t);
+        }
+    }
+}
+
 }  // namespace b200

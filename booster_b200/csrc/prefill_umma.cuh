@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(512) k_quant_batch_mma(const QuantBatchArgs a)
     extern __shared__ __align__(16) uint8_t qb_smem[];
     __shared__ double red_smem[MV_MAX_WARPS];
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const ActSmem A = act_smem_carve(qb_smem, a.k, 0);
+    const ActSmem A = act_smem_carve(qb_smem, a.k, a.act_q8_0);
     const bool norm = a.norm_w != nullptr;
     float ww[PRO_U][8] = {};
     if (norm) {
@@ -149,9 +149,10 @@ __global__ void __launch_bounds__(512) k_quant_batch_mma(const QuantBatchArgs a)
             if (b < a.k / 256) ldg8(a.norm_w + b * 256 + lane * 8, ww[u]);
         }
     }
-    prologue_quantize<false, true>(a.X + (size_t) t * a.k, norm, a.eps, a.k, a.inv_k, 0, A, red_smem, ww, []() {}, W);
+    prologue_quantize<false, true>(a.X + (size_t) t * a.k, norm, a.eps, a.k, a.inv_k, a.act_q8_0, A, red_smem, ww, []() {}, W);
     __syncthreads();
-    if (a.layout == 2) um_write_records(A, a.k / 256, a.rec, t, lane, warp, W);
+    if (a.layout == 3) q80_write_records(A, a.k / 256, a.rec, t, lane, warp, W);
+    else if (a.layout == 2) um_write_records(A, a.k / 256, a.rec, t, lane, warp, W);
     else mb_write_records(A, a.k / 256, a.rec, t, lane, warp, W);
 }
 

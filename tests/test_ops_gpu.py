@@ -192,10 +192,10 @@ def test_mul_mat_batch_extremes(name):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("name", ["Q4_K", "Q5_K", "Q6_K"])
+@pytest.mark.parametrize("name", ["Q4_K", "Q5_K", "Q6_K", "Q8_0"])
 def test_mul_mat_batch_kernel_variants(name, mode):
-    """the three batch kernels — mma.sync (1, default), tcgen05 (2), dp4a (0): A/B switch b200_set_prefill_mma — give the
-    reference's bits, on random blocks and on the worst-case magnitudes"""
+    """the batch kernels — mma.sync (1, default; Q8_0: the block-diagonal HMMA kernel), tcgen05 (2; K-quants), dp4a (0): A/B
+    switch b200_set_prefill_mma — give the reference's bits, on random blocks and on the worst-case magnitudes"""
     rng = np.random.default_rng(3)
     n, k, T = 256, 2048, 100
     x = rng.standard_normal((T, k)).astype(np.float32)
