@@ -532,28 +532,43 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch_q80(const __grid
         const float * dwb = reinterpret_cast<const float *>(As + 8 * 2 * MB_ROWS * 32);
         const uint8_t * rec = stages + (size_t) s * a.mb_stage_bytes + 2 * a.mb_raw_stride;
         const float * dxr = reinterpret_cast<const float *>(rec + Q80_OFF_DX);
-#pragma unroll 1
+#pragma unroll 2
         for (int tt = 0; tt < 8; tt++) {
             uint32_t af[2][4];
             ldsm_x4(af[0], smem_u32(As) + (uint32_t) (tt * 2) * (MB_ROWS * 32) + a_off);
             ldsm_x4(af[1], smem_u32(As) + (uint32_t) (tt * 2 + 1) * (MB_ROWS * 32) + a_off);
             const float dw0 = dwb[tt * MB_ROWS + r0], dw1 = dwb[tt * MB_ROWS + r0 + 8];
+            // all loads of the block first, then its eight independent MMAs, then the 32 chain steps
+            uint32_t bv[4][2];
+            float dxv[4];
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) {
                 const int tk = 8 * tq + 2 * nt;
                 const uint8_t * brow = rec + (size_t) (tk + (lane >> 4)) * Q80_ROW + (size_t) tt * 64 + b_elem;
-                const float dxv = dxr[(tk + ((lane & 3) >> 1)) * 8 + tt];
-                const float d0 = __fmul_rn(dw0, dxv), d1 = __fmul_rn(dw1, dxv);            // fp16(x.d) * fp16(y.d)
+                bv[nt][0] = *reinterpret_cast<const uint32_t *>(brow);
+                bv[nt][1] = *reinterpret_cast<const uint32_t *>(brow + 32);
+                dxv[nt] = dxr[(tk + ((lane & 3) >> 1)) * 8 + tt];
+            }
+            float c[4][2][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
-                    const uint32_t v = *reinterpret_cast<const uint32_t *>(brow + g * 32);
-                    const uint32_t bv = b_on ? v : 0u;
-                    float c[4] = {0.f, 0.f, 0.f, 0.f};
-                    mma_f16(c, af[g], q < 2 ? bv : 0u, q < 2 ? 0u : bv);
-                    acc[nt][g][0] = __fmaf_rn(d0, c[0], acc[nt][g][0]);
-                    acc[nt][g][1] = __fmaf_rn(d0, c[1], acc[nt][g][1]);
-                    acc[nt][g][2] = __fmaf_rn(d1, c[2], acc[nt][g][2]);
-                    acc[nt][g][3] = __fmaf_rn(d1, c[3], acc[nt][g][3]);
+                    const uint32_t v = b_on ? bv[nt][g] : 0u;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) c[nt][g][e] = 0.f;
+                    mma_f16(c[nt][g], af[g], q < 2 ? v : 0u, q < 2 ? 0u : v);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const float d0 = __fmul_rn(dw0, dxv[nt]), d1 = __fmul_rn(dw1, dxv[nt]);            // fp16(x.d) * fp16(y.d)
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    acc[nt][g][0] = __fmaf_rn(d0, c[nt][g][0], acc[nt][g][0]);
+                    acc[nt][g][1] = __fmaf_rn(d0, c[nt][g][1], acc[nt][g][1]);
+                    acc[nt][g][2] = __fmaf_rn(d1, c[nt][g][2], acc[nt][g][2]);
+                    acc[nt][g][3] = __fmaf_rn(d1, c[nt][g][3], acc[nt][g][3]);
                 }
             }
         }
