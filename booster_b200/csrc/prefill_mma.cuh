@@ -72,6 +72,11 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], u
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// D = A * B (no accumulator input: the zero registers are shared, not re-materialised per MMA)
+__device__ __forceinline__ void mma_f16_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
 __device__ __forceinline__ uint32_t h2_ints(int lo, int hi) { return h2_bits(__halves2half2(__int2half_rn(lo), __int2half_rn(hi))); }
@@ -435,21 +440,27 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch(const __grid_con
 //   activation rows; 512 threads expand int8 -> fp16 A rows (double-buffered); warp (16-row tile mt = w & 3, 8 tokens
 //   tq = w >> 2): per block 2 ldmatrix.x4 (A), 8 predicated 4-byte B loads, 8 HMMA, 32 chain FFMA.
 // ------------------------------------------------------------------------------------------------------------
-static constexpr int Q80_ROW = 512 + 16;                               // bytes of a token's 256 fp16 activations (+16: bank spread)
+// activation rows of a (32-token chunk, 256-weight step): token row = [block pair p (4)][element pair s (8)][w (4)] half2, w = 2 (block & 1) +
+// 16-group g: the four B words a thread needs for two blocks are one 16-byte load
+static constexpr int Q80_ROW = 512;
 static constexpr int Q80_OFF_DX = MB_NT * Q80_ROW;                     // f32 [32 tokens][8 blocks]
-static constexpr int Q80_REC_BYTES = Q80_OFF_DX + MB_NT * 8 * 4;       // 17920
-static constexpr int Q80_A_BYTES = 8 * 2 * MB_ROWS * 32 + 8 * MB_ROWS * 4;   // fp16 rows [block][16-group][row][16] | f32 d [block][row]
+static constexpr int Q80_REC_BYTES = Q80_OFF_DX + MB_NT * 8 * 4;       // 17408
+static constexpr int Q80_A_BYTES = 8 * 2 * MB_ROWS * 32 + 8 * MB_ROWS * 4;   // fp16 rows [block][16-group][row][16] | f32 d [row][block]
 
-// k_quant_batch_mma, layout 3: token t's Q8_0 image (natural order) -> fp16 rows + block scales
+// k_quant_batch_mma, layout 3: token t's Q8_0 image (natural order) -> fp16 words in fragment order + block scales
 __device__ __forceinline__ void q80_write_records(const ActSmem & A, int n256, uint8_t * rec, int t, int lane, int warp, int W) {
     const int chunk = t / MB_NT, j = t % MB_NT;
     for (int b = warp; b < n256; b += W) {
         uint8_t * r = rec + ((size_t) chunk * n256 + b) * Q80_REC_BYTES;
-        const uint2 w = *reinterpret_cast<const uint2 *>(A.q + (size_t) b * 256 + lane * 8);
-        uint4 o;
-        o.x = h2_ints(sbyte_of(w.x, 0), sbyte_of(w.x, 1)); o.y = h2_ints(sbyte_of(w.x, 2), sbyte_of(w.x, 3));
-        o.z = h2_ints(sbyte_of(w.y, 0), sbyte_of(w.y, 1)); o.w = h2_ints(sbyte_of(w.y, 2), sbyte_of(w.y, 3));
-        *reinterpret_cast<uint4 *>(r + j * Q80_ROW + lane * 16) = o;
+        const int8_t * qb = A.q + (size_t) b * 256;
+        const int p = lane >> 3, sl = lane & 7;
+        uint32_t o[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const int8_t * src = qb + (2 * p + (w >> 1)) * 32 + (w & 1) * 16 + 2 * sl;
+            o[w] = h2_ints((int) src[0], (int) src[1]);
+        }
+        *reinterpret_cast<uint4 *>(r + j * Q80_ROW + lane * 16) = make_uint4(o[0], o[1], o[2], o[3]);
         if (lane < 8) *reinterpret_cast<float *>(r + Q80_OFF_DX + (j * 8 + lane) * 4) = A.dx[b * 8 + lane];
     }
 }
@@ -501,7 +512,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch_q80(const __grid
             *reinterpret_cast<uint4 *>(dst + ((1u ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
         float * dwb = reinterpret_cast<float *>(As + 8 * 2 * MB_ROWS * 32);
-        dwb[tt * MB_ROWS + r] = __half2float(*reinterpret_cast<const __half *>(tile + 1024 + lane * 2));
+        dwb[r * 8 + tt] = __half2float(*reinterpret_cast<const __half *>(tile + 1024 + lane * 2));
     };
 
     const int mt = warp & 3, tq = warp >> 2;
@@ -525,50 +536,54 @@ __global__ void __launch_bounds__(MB_WARPS * 32, 1) k_mma_batch_q80(const __grid
     const uint32_t a_off = (uint32_t) (rl * 32) + ((((uint32_t) kc) ^ ((rl >> 2) & 1)) << 4);
     const int q = (lane >> 2) & 3, kq = (lane & 3) >> 1;
     const bool b_on = (q & 1) == kq;                       // k / 4 == q  (b0 holds k < 8: q in {0, 1}; b1 holds k >= 8: q in {2, 3})
-    const uint32_t b_elem = (uint32_t) (2 * (lane & 3) + (q >= 2 ? 8 : 0)) * 2;
+    const uint32_t m0 = (b_on && q < 2) ? 0xffffffffu : 0u, m1 = (b_on && q >= 2) ? 0xffffffffu : 0u;
+    const uint32_t b_slot = (uint32_t) ((lane & 3) + (q >= 2 ? 4 : 0)) * 16;      // element pair 2 (lane & 3) [+8] of the 16-group
     const int r0 = mt * 16 + (lane >> 2);
     for (int step = 0; step < n_steps; step++) {
         const uint8_t * As = q8_smem + (size_t) (step & 1) * Q80_A_BYTES;
         const float * dwb = reinterpret_cast<const float *>(As + 8 * 2 * MB_ROWS * 32);
         const uint8_t * rec = stages + (size_t) s * a.mb_stage_bytes + 2 * a.mb_raw_stride;
-        const float * dxr = reinterpret_cast<const float *>(rec + Q80_OFF_DX);
-#pragma unroll 2
-        for (int tt = 0; tt < 8; tt++) {
-            uint32_t af[2][4];
-            ldsm_x4(af[0], smem_u32(As) + (uint32_t) (tt * 2) * (MB_ROWS * 32) + a_off);
-            ldsm_x4(af[1], smem_u32(As) + (uint32_t) (tt * 2 + 1) * (MB_ROWS * 32) + a_off);
-            const float dw0 = dwb[tt * MB_ROWS + r0], dw1 = dwb[tt * MB_ROWS + r0 + 8];
-            // all loads of the block first, then its eight independent MMAs, then the 32 chain steps
-            uint32_t bv[4][2];
-            float dxv[4];
+        const uint8_t * dxr = rec + Q80_OFF_DX;
+#pragma unroll 1
+        for (int p = 0; p < 4; p++) {                          // two blocks per iteration: every operand is a vector load
+            uint32_t af[2][2][4];
+#pragma unroll
+            for (int bb = 0; bb < 2; bb++) {
+#pragma unroll
+                for (int g = 0; g < 2; g++) ldsm_x4(af[bb][g], smem_u32(As) + (uint32_t) ((2 * p + bb) * 2 + g) * (MB_ROWS * 32) + a_off);
+            }
+            const float2 dwa = *reinterpret_cast<const float2 *>(dwb + r0 * 8 + 2 * p), dwc = *reinterpret_cast<const float2 *>(dwb + (r0 + 8) * 8 + 2 * p);
+            uint4 bv[4];
+            float2 dxv[4];
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) {
                 const int tk = 8 * tq + 2 * nt;
-                const uint8_t * brow = rec + (size_t) (tk + (lane >> 4)) * Q80_ROW + (size_t) tt * 64 + b_elem;
-                bv[nt][0] = *reinterpret_cast<const uint32_t *>(brow);
-                bv[nt][1] = *reinterpret_cast<const uint32_t *>(brow + 32);
-                dxv[nt] = dxr[(tk + ((lane & 3) >> 1)) * 8 + tt];
+                bv[nt] = *reinterpret_cast<const uint4 *>(rec + (size_t) (tk + (lane >> 4)) * Q80_ROW + p * 128 + b_slot);
+                dxv[nt] = *reinterpret_cast<const float2 *>(dxr + ((tk + ((lane & 3) >> 1)) * 8 + 2 * p) * 4);
             }
-            float c[4][2][4];
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
+            for (int bb = 0; bb < 2; bb++) {
+                float c[4][2][4];
 #pragma unroll
-                for (int g = 0; g < 2; g++) {
-                    const uint32_t v = b_on ? bv[nt][g] : 0u;
+                for (int nt = 0; nt < 4; nt++) {
 #pragma unroll
-                    for (int e = 0; e < 4; e++) c[nt][g][e] = 0.f;
-                    mma_f16(c[nt][g], af[g], q < 2 ? v : 0u, q < 2 ? 0u : v);
+                    for (int g = 0; g < 2; g++) {
+                        const uint32_t v = word_of(bv[nt], 2 * bb + g);
+                        mma_f16_z(c[nt][g], af[bb][g], v & m0, v & m1);
+                    }
                 }
-            }
+                const float dw0 = bb ? dwa.y : dwa.x, dw1 = bb ? dwc.y : dwc.x;
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                const float d0 = __fmul_rn(dw0, dxv[nt]), d1 = __fmul_rn(dw1, dxv[nt]);            // fp16(x.d) * fp16(y.d)
+                for (int nt = 0; nt < 4; nt++) {
+                    const float dx = bb ? dxv[nt].y : dxv[nt].x;
+                    const float d0 = __fmul_rn(dw0, dx), d1 = __fmul_rn(dw1, dx);            // fp16(x.d) * fp16(y.d)
 #pragma unroll
-                for (int g = 0; g < 2; g++) {
-                    acc[nt][g][0] = __fmaf_rn(d0, c[nt][g][0], acc[nt][g][0]);
-                    acc[nt][g][1] = __fmaf_rn(d0, c[nt][g][1], acc[nt][g][1]);
-                    acc[nt][g][2] = __fmaf_rn(d1, c[nt][g][2], acc[nt][g][2]);
-                    acc[nt][g][3] = __fmaf_rn(d1, c[nt][g][3], acc[nt][g][3]);
+                    for (int g = 0; g < 2; g++) {
+                        acc[nt][g][0] = __fmaf_rn(d0, c[nt][g][0], acc[nt][g][0]);
+                        acc[nt][g][1] = __fmaf_rn(d0, c[nt][g][1], acc[nt][g][1]);
+                        acc[nt][g][2] = __fmaf_rn(d1, c[nt][g][2], acc[nt][g][2]);
+                        acc[nt][g][3] = __fmaf_rn(d1, c[nt][g][3], acc[nt][g][3]);
+                    }
                 }
             }
         }
