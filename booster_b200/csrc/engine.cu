@@ -559,6 +559,7 @@ struct b200_ctx {
     // prompt batches (prefill.cuh): activations of up to pb_cap tokens, allocated at the first batch
     struct PrefillBufs {
         int cap = 0;
+        int att_z = 64;          // tokens per attention launch group (bounded by the score buffer)
         float * X = nullptr, * Q = nullptr, * ATT = nullptr, * FFH = nullptr, * S = nullptr;
         uint8_t * rec = nullptr;
         int32_t * tokens = nullptr;
@@ -1527,7 +1528,7 @@ static double now_us() {
 // tokens. Same arithmetic as the token-by-token path (same device functions), so the logits are bit-identical to it.
 // ------------------------------------------------------------------------------------------------------------
 static constexpr int PB_MAX_T = 512;               // tokens per pass (the reference's n_ubatch: cpp/common/common.h:81)
-static constexpr int PB_ATT_Z = 64;                // tokens per attention launch group (bounds the score buffer)
+static constexpr size_t PB_SCORE_BYTES = (size_t) 256 << 20;   // score buffer budget: tokens per attention launch group = what fits (>= 64)
 static int g_prefill_batch = -1;       // 1: prompt batches run the batched kernels (default), 0: token by token (A/B, tests)
 extern "C" void b200_set_prefill_batch(int on) { g_prefill_batch = on ? 1 : 0; }
 static bool prefill_batch_enabled() {
@@ -1554,7 +1555,12 @@ static void prefill_alloc(b200_ctx * c) {
     CU(cudaMalloc(&c->pb.Q, (size_t) T * QD * 4));
     CU(cudaMalloc(&c->pb.ATT, (size_t) T * QD * 4));
     CU(cudaMalloc(&c->pb.FFH, (size_t) T * m.n_ff * 4));
-    CU(cudaMalloc(&c->pb.S, (size_t) PB_ATT_Z * m.n_head * c->n_ctx * 4));
+    {
+        const size_t per_token = (size_t) m.n_head * c->n_ctx * 4;
+        c->pb.att_z = (int) std::max<size_t>(64, std::min<size_t>((size_t) T, PB_SCORE_BYTES / per_token / 32 * 32));
+        if (g_prefill_attn_batch == 0) c->pb.att_z = 64;   // (the per-token kernels index blockIdx.z the same way)
+    }
+    CU(cudaMalloc(&c->pb.S, (size_t) c->pb.att_z * m.n_head * c->n_ctx * 4));
     const size_t rec_bytes = std::max((size_t) (T / PB_CHUNK) * (kmax / 256) * PB_CHUNK * pb_record_bytes(0, 1),
                                       std::max((size_t) (T / MB_NT) * (kmax / 256) * MB_REC_BYTES, (size_t) (T / UM_NT) * (kmax / 256) * UM_REC_BYTES));
     CU(cudaMalloc(&c->pb.rec, rec_bytes));
@@ -1696,8 +1702,8 @@ template <int GQA>
 static void pb_attention(b200_ctx * c, int li, int T, int pos0) {
     const b200_model & m = *c->m;
     const int HD = m.head_dim, KVD = m.n_head_kv * HD, QD = m.n_head * HD;
-    for (int z0 = 0; z0 < T; z0 += PB_ATT_Z) {
-        const int nz = std::min(PB_ATT_Z, T - z0);
+    for (int z0 = 0; z0 < T; z0 += c->pb.att_z) {
+        const int nz = std::min(c->pb.att_z, T - z0);
         AttnArgs a{};
         a.q = c->pb.Q + (size_t) z0 * QD; a.k_cache = c->kc[(size_t) li]; a.v_cache = c->vc[(size_t) li];
         a.S = c->pb.S; a.s_stride = c->n_ctx; a.out = c->pb.ATT + (size_t) z0 * QD;
@@ -1710,8 +1716,8 @@ static void pb_attention(b200_ctx * c, int li, int T, int pos0) {
             if (!launch_attention_2k<GQA>(c, a, n_pad_max, nz)) throw std::runtime_error("batched attention does not fit");
             continue;
         }
-        const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_pad_max + ATT_TILE - 1) / ATT_TILE), (unsigned) nz);
-        launch_fwd(k_attn_scores<GQA, false>, gs, dim3(ATT_THREADS), 0, c->st, a, false);
+        const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_pad_max + ATT_TILE - 1) / ATT_TILE), (unsigned) ((nz + SCB_TQ - 1) / SCB_TQ));
+        k_attn_scores_batch<GQA><<<gs, ATT_THREADS, 0, c->st>>>(a, nz);
         k_attn_softmax_rows<<<(unsigned) ((nz * a.n_head + 7) / 8), 256, 0, c->st>>>(a, nz);
         static bool attr_done[64] = {false};
         if (!attr_done[c->device & 63]) {

@@ -138,6 +138,71 @@ __global__ void __launch_bounds__(256) k_attn_softmax_rows(const AttnArgs a, int
     }
 }
 
+// scores of a prompt batch: CTA = (KV head, 64 keys, 8 tokens). The K rows of the tile are loaded ONCE into registers (4 lanes per
+// key row, as in k_attn_scores) and every (token, head) of the CTA runs ggml_vec_dot_f16 against them: q rounded to f16, 4
+// accumulators x 16 lanes over i in {0, 64}, (0+2)+(1+3), _mm512_reduce_add_ps (cpp/ggml/src/ggml.c:12345-12371) — the batch > 1
+// branch of k_attn_scores, token by token. A token's row ends at its own padded length (-inf from its n_kv to there).
+static constexpr int SCB_TQ = 8;
+template <int GQA>
+__global__ void __launch_bounds__(ATT_THREADS) k_attn_scores_batch(const AttnArgs a, int nz) {
+    constexpr int HD = 128;
+    __shared__ __align__(16) float qs[SCB_TQ][GQA][HD];
+    const int g = blockIdx.x, tile = blockIdx.y, z0 = blockIdx.z * SCB_TQ, tid = threadIdx.x;
+    const int ntok = min(SCB_TQ, nz - z0);
+    const int n_kv_last = a.n_kv_override + z0 + ntok - 1;
+    if (tile * ATT_TILE >= (n_kv_last + 31) / 32 * 32) return;
+    const int t = tile * ATT_TILE + (tid >> 2), c4 = tid & 3;
+    uint2 kv[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) kv[s] = make_uint2(0u, 0u);
+    if (t < n_kv_last) {
+        const uint2 * kr = reinterpret_cast<const uint2 *>(a.k_cache + (size_t) t * a.kv_dim + g * HD + 4 * c4);
+#pragma unroll
+        for (int s = 0; s < 8; s++) kv[s] = kr[s * 4];                        // 4 halfs at element 16s + 4c4
+    }
+    for (int i = tid; i < ntok * GQA * HD; i += ATT_THREADS) {
+        const int tok = i / (GQA * HD), rem = i - tok * (GQA * HD);
+        const float v = a.q[(size_t) (z0 + tok) * a.zq + (size_t) (g * GQA) * HD + rem];
+        (&qs[0][0][0])[i] = __half2float(__float2half_rn(v));                 // src1 converted to the vec_dot_type F16
+    }
+    float kf[8][4];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[s].y));
+        kf[s][0] = f0.x; kf[s][1] = f0.y; kf[s][2] = f1.x; kf[s][3] = f1.y;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int tok = 0; tok < ntok; tok++) {
+        const int n_kv = a.n_kv_override + z0 + tok, n_pad = (n_kv + 31) / 32 * 32;
+        if (t >= n_pad) continue;                                  // n_pad % 32 == 0 and a warp holds 8 consecutive keys: warp-uniform
+        float * Srow = a.S + (size_t) (z0 + tok) * a.zs + (size_t) (g * GQA) * a.s_stride + t;
+#pragma unroll 1
+        for (int h = 0; h < GQA; h++) {
+            float aj[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float4 q0 = *reinterpret_cast<const float4 *>(&qs[tok][h][16 * j + 4 * c4]);
+                const float4 q1 = *reinterpret_cast<const float4 *>(&qs[tok][h][64 + 16 * j + 4 * c4]);
+                aj[j][0] = __fmaf_rn(kf[4 + j][0], q1.x, __fmul_rn(kf[j][0], q0.x));
+                aj[j][1] = __fmaf_rn(kf[4 + j][1], q1.y, __fmul_rn(kf[j][1], q0.y));
+                aj[j][2] = __fmaf_rn(kf[4 + j][2], q1.z, __fmul_rn(kf[j][2], q0.z));
+                aj[j][3] = __fmaf_rn(kf[4 + j][3], q1.w, __fmul_rn(kf[j][3], q0.w));
+            }
+            float ch[4], t3[4], t6[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) ch[e] = __fadd_rn(__fadd_rn(aj[0][e], aj[2][e]), __fadd_rn(aj[1][e], aj[3][e]));
+#pragma unroll
+            for (int e = 0; e < 4; e++) t3[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, ch[e], 2), ch[e]);
+#pragma unroll
+            for (int e = 0; e < 4; e++) t6[e] = __fadd_rn(__shfl_xor_sync(0xffffffffu, t3[e], 1), t3[e]);
+            const float res = __fadd_rn(__fadd_rn(t6[0], t6[2]), __fadd_rn(t6[1], t6[3]));
+            if (c4 == 0) Srow[(size_t) h * a.s_stride] = t < n_kv ? __fmul_rn(res, a.scale) : -INFINITY;
+        }
+    }
+}
+
 static constexpr int PVB_ROWS = 32;            // (token, head) rows per CTA: 32 / GQA tokens x GQA heads
 static constexpr int PVB_CHUNK = 256;          // positions staged at a time
 static constexpr int PVB_DIMS = 16;
