@@ -393,9 +393,9 @@ def main():
             pc.close()
             pm = float(np.mean(pms[1:]))
             line["prompt_batch"] = {"tokens": 512, "ms": pm, "tokens_per_s": 512e3 / pm,
-                                    "kernels": ("k_quant_batch + k_matmul_batch (dp4a: Q8_0 lane sums are 4-byte contractions)" if ftype == "Q8_0" else
+                                    "kernels": ("k_quant_batch_mma + k_mma_batch_q80 (block-diagonal fp16 HMMA: exact 4-byte lane sums)" if ftype == "Q8_0" else
                                                 "k_quant_batch_mma + k_mma_batch (exact fp16 HMMA per AVX2 lane-slice)") +
-                                               " + k_attn_scores / k_attn_softmax_rows / k_attn_pv_batch",
+                                               " + k_attn_scores_batch / k_attn_softmax_rows / k_attn_pv_batch",
                                     "what": "b200_decode of one 512-token batch at positions 0..511, wall clock incl. the final synchronisation"}
         except Exception as e:
             line["prompt_batch"] = {"error": str(e)}

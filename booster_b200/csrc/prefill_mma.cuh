@@ -16,16 +16,17 @@
 //     = 8 groups x (lo, hi); for Q4_K the four lanes l of the reference's _mm_madd_epi16 are four B columns per token.
 //   * the chain step acc = fma(d, C, acc) then runs on the MMA's C fragment in registers, super-block after super-block.
 //
-// mma.sync.m16n8k16 (HMMA), not tcgen05: the accumulator of every (super-block, lane) must come back to the register file
-// for its own fp32 chain step — 8 + 4 FFMA per 256 MACs and output — so the kernel is bound by that CUDA-core epilogue, by
-// the 12 live fp32 chains per output element (a 64 x 32 tile fills the register file) and by fragment traffic, not by
-// tensor throughput; a TMEM-resident accumulator would have to be drained 8 times per super-block.
+// mma.sync.m16n8k16 (HMMA) is the default, not tcgen05: the accumulator of every (super-block, lane) must come back to the
+// register file for its own fp32 chain step — 8 + 4 FFMA per 256 MACs and output — so the kernel is bound by that CUDA-core
+// epilogue, by the 12 live fp32 chains per output element (a 64 x 32 tile fills the register file) and by fragment traffic
+// through shared memory, not by tensor throughput (ncu: HMMA pipe 22-26 % busy). The tcgen05 / TMEM variant is
+// prefill_umma.cuh: bit-exact too, measured slower (its header says why).
 //
 // Shape: CTA = 64 rows (two 32-row units of the tiled weight layout) x 32 tokens, 16 warps. Per super-block (K step):
 //   TMA bulk copies: the two raw weight tiles + the chunk's activation record block (fp16, MMA order, written by
 //     k_quant_batch) into a ring of stages (mbarrier full flags)
 //   expand: 512 threads turn the raw tiles into the fp16 A operand (scale folded in) in shared memory, XOR-swizzled for
-//     conflict-free ldmatrix
+//     conflict-free ldmatrix; the operand is double-buffered: step b+1 is expanded while step b runs (one barrier per step)
 //   mma: warp (m = w & 7, rh = w >> 3) owns lane-slice m of 32 rows x 32 tokens: 16 HMMA + 32 chain FFMA per super-block;
 //     the mins tiles are spread over the 16 warps
 // After the last super-block the 12 chains of every output meet in shared memory, finish_row() + the layer epilogues of the

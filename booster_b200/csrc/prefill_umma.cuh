@@ -3,10 +3,15 @@
 // AVX2 lane-slice m the contraction  isum[m] = sum_g scale[g] * sum_i w[g][4m+i] * a[g][4m+i]  is a K = 32 fp16 MMA whose operands
 // (weight x sub-block scale, int8 activation) and whose every partial sum are integers below 2^24, so D = (float) isum[m] exactly.
 //
-// Why this kernel exists next to the mma.sync one: on B200 the legacy HMMA path is the limiter of k_mma_batch (ncu:
-// sm__pipe_tensor_subpipe_hmma_cycles_active 86-100 % of the elapsed cycles at ~256 MAC/clk/SM, profiles/r02_prefill_*.txt),
-// tcgen05 moves the contraction off the SM's issue slots entirely; what remains is CUDA-core work: expanding the 4.5-6.5 bit
-// weights to fp16 operands and the ordered fp32 chain step acc[m] = fma(d_b, D_m, acc[m]) on every drained accumulator.
+// Why this kernel exists next to the mma.sync one: tcgen05 moves the contraction off the SM's issue slots and its accumulators
+// out of the register file; what remains is CUDA-core work — expanding the 4.5-6.5 bit weights to fp16 operands and the ordered
+// fp32 chain step acc[m] = fma(d_b, D_m, acc[m]) on every drained accumulator.
+// MEASURED (B200, 8B Q4_K_M, 512-token batch; profiles/r02h_prefill_umma_ncu_summary.txt): bit-exact, but SLOWER than k_mma_batch
+// (136 vs 92 ms per batch at the time of the A/B). The 12 fp32 chains per output element must stay in registers, which caps the
+// tile at 128 rows x 16 tokens: every expanded A tile is used for 16 tokens only (32 in k_mma_batch), SS-mode MMAs re-read the
+// 64 KB A tile from shared memory for 0.5 MMAC, and a third of the samples wait on the MMA-completion mbarrier because the
+// single A buffer serialises expansion and MMA. The HMMA kernel is not tensor-bound either (HMMA pipe 22-26 % busy), so the
+// 16x higher tcgen05 rate buys nothing here. Kept selectable (b200_set_prefill_mma(2)) as the measured tcgen05 variant.
 //
 // CTA = 128 rows (four 32-row units) x 16 tokens, 16 warps, one CTA per SM (TMEM: all 512 columns).
 //   TMA bulk copies   raw weight tiles of the four units + the chunk's activation record block (fp16, canonical no-swizzle
