@@ -81,6 +81,11 @@ __device__ __forceinline__ void mma_f16_z(float (&d)[4], const uint32_t (&a)[4],
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
 __device__ __forceinline__ uint32_t h2_ints(int lo, int hi) { return h2_bits(__halves2half2(__int2half_rn(lo), __int2half_rn(hi))); }
+// half2(v, v) for an integer 0 <= v < 1024 on the ALU / FMA pipes (0x6400 | v is 1024 + v in fp16), not the conversion unit
+__device__ __forceinline__ __half2 h2_small(int v) {
+    const uint32_t b = 0x64006400u | (uint32_t) v | ((uint32_t) v << 16);
+    return __hsub2(bits_h2(b), bits_h2(0x64006400u));
+}
 __device__ __forceinline__ int sbyte_of(uint32_t w, int i) { return (int) (int8_t) (w >> (8 * i)); }
 
 // k_quant_batch, MMA layout: the quantized image of token t (ActSmem, natural order) -> its rows of the chunk's record blocks
@@ -140,8 +145,9 @@ __device__ __forceinline__ void mb_expand(const uint8_t * raw, uint32_t raw_stri
         const int sh = (j & 1) * 16;
         const int sc_lo = (int) ((scw >> sh) & 0xffu), sc_hi = (int) ((scw >> (sh + 8)) & 0xffu);
         // (1024 + v) * s - 1024 s = v * s: one HFMA2 per pair, exact (v s <= 1953 is an fp16 integer, 1024 s <= 64512 too)
-        const __half2 s_lo = __half2half2(__int2half_rn(sc_lo)), s_hi = __half2half2(__int2half_rn(sc_hi));
-        const __half2 o_lo = __half2half2(__int2half_rn(-1024 * sc_lo)), o_hi = __half2half2(__int2half_rn(-1024 * sc_hi));
+        const __half2 s_lo = h2_small(sc_lo), s_hi = h2_small(sc_hi);
+        const __half2 m1024 = bits_h2(0xe400e400u);                     // -1024: -1024 s is an fp16 integer (|.| <= 64512)
+        const __half2 o_lo = __hmul2(s_lo, m1024), o_hi = __hmul2(s_hi, m1024);
         uint4 H4 = make_uint4(0u, 0u, 0u, 0u);
         if (TYPE == T_Q5_K) H4 = lds_u4(sl + 4608 + h * 512);
         uint8_t * dst = As + r * 64 + ((((uint32_t) j) ^ sw) << 4);
@@ -167,10 +173,10 @@ __device__ __forceinline__ void mb_expand(const uint8_t * raw, uint32_t raw_stri
             const uint32_t m_a = sd.y & 0x3f3f3f3fu, m_b = ((sd.z >> 4) & 0x0f0f0f0fu) | ((sd.y >> 2) & 0x30303030u);
             const uint32_t mw = c ? m_b : m_a;
             uint4 o;
-            o.x = h2_ints((int) (mw & 0xffu), (int) (mw & 0xffu));
-            o.y = h2_ints((int) ((mw >> 8) & 0xffu), (int) ((mw >> 8) & 0xffu));
-            o.z = h2_ints((int) ((mw >> 16) & 0xffu), (int) ((mw >> 16) & 0xffu));
-            o.w = h2_ints((int) (mw >> 24), (int) (mw >> 24));
+            o.x = h2_bits(h2_small((int) (mw & 0xffu)));
+            o.y = h2_bits(h2_small((int) ((mw >> 8) & 0xffu)));
+            o.z = h2_bits(h2_small((int) ((mw >> 16) & 0xffu)));
+            o.w = h2_bits(h2_small((int) (mw >> 24)));
             *reinterpret_cast<uint4 *>(As + mins_off + r * 32 + ((((uint32_t) c) ^ ((r >> 2) & 1)) << 4)) = o;
             if (c == 0) {
                 const __half2 dmh = bits_h2(sd.w);
@@ -240,11 +246,12 @@ __device__ __forceinline__ void mb_mma_main(const uint8_t * As, const uint8_t * 
         const float dw0 = scal[r0], dw1 = scal[r0 + 8];
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int p = 0; p < PARTS; p++) {
-                mma_f16(c, af[p][0], bf[nt][0], bf[nt][1]);
-                mma_f16(c, af[p][1], bf[nt][2], bf[nt][3]);
+            float c[4];
+            mma_f16_z(c, af[0][0], bf[nt][0], bf[nt][1]);
+            mma_f16(c, af[0][1], bf[nt][2], bf[nt][3]);
+            if (PARTS == 2) {
+                mma_f16(c, af[PARTS - 1][0], bf[nt][0], bf[nt][1]);
+                mma_f16(c, af[PARTS - 1][1], bf[nt][2], bf[nt][3]);
             }
             // d = y[i].d * fp16(x[i].d) (ggml-quants.c:6922), acc[m] = fma(d, (float) isum[m], acc[m]) (:6974)
             acc[mt][nt][0] = __fmaf_rn(__fmul_rn(yd[nt].x, dw0), c[0], acc[mt][nt][0]);
@@ -280,8 +287,8 @@ __device__ __forceinline__ void mb_mma_mins4(const uint8_t * As, uint32_t mins_o
 #pragma unroll
         for (int q = 0; q < 2; q++) {
             const int nt = 2 * p + q;
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_f16(c, af, bf[2 * q], bf[2 * q + 1]);
+            float c[4];
+            mma_f16_z(c, af, bf[2 * q], bf[2 * q + 1]);
             const float nyd = -ydp[8 * tq + 2 * nt + ((lane & 3) >> 1)];
             const float d0 = __fmul_rn(nyd, dm0), d1 = __fmul_rn(nyd, dm1);     // dmin = -y[i].d * fp16(x[i].dmin)
             accm[nt][0] = __fmaf_rn(d0, c[0], accm[nt][0]);
@@ -301,8 +308,8 @@ __device__ __forceinline__ void mb_mma_mins5(const uint8_t * As, uint32_t mins_o
         const int t = 8 * nt + (lane & 7), kc = (lane >> 3) & 1;
         ldsm_x2(bf, smem_u32(rec) + MB_OFF_M5 + t * 32 + ((((uint32_t) kc) ^ ((t >> 2) & 1)) << 4));
     }
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_f16(c, af, bf[0], bf[1]);
+    float c[4];
+    mma_f16_z(c, af, bf[0], bf[1]);
     const int r0 = mt * 16 + (lane >> 2);
     const float dm0 = scal[MB_ROWS + r0], dm1 = scal[MB_ROWS + r0 + 8];
     const float2 y = *reinterpret_cast<const float2 *>(rec + MB_OFF_YD + (8 * nt + 2 * (lane & 3)) * 4);
