@@ -279,9 +279,8 @@ def main():
         handoff = "ncclSend/ncclRecv per stage boundary"
         if os.environ.get("BOOSTER_B200_P2P", "1") != "0":
             # direct NVLink stores into the next stage's inbox (CUDA IPC) instead of NCCL point-to-point
-            nxt, first = pipeline.exchange_inbox_handles(dist, c.p2p_handle())
-            c.p2p_connect(rank, world, nxt, first)
-            handoff = "peer stores over NVLink into the next stage's inbox (CUDA IPC) + sequence flag, per stage boundary"
+            if pipeline.connect_peer_handoff(dist, c, rank, world):
+                handoff = "peer stores over NVLink into the next stage's inbox (CUDA IPC) + sequence flag, per stage boundary"
     gen = (lambda tok, pos, n: c.pipeline_generate_greedy(tok, pos, n)) if world > 1 else (lambda tok, pos, n: c.generate_greedy(tok, pos, n))
 
     def sync_all():

@@ -21,7 +21,7 @@ B200_SYMBOLS = ["b200_last_error", "b200_device_count", "b200_version", "b200_mo
                 "b200_model_info", "b200_model_weight_bytes", "b200_ctx_new", "b200_ctx_free", "b200_n_ctx",
                 "b200_kv_clear", "b200_decode", "b200_generate_greedy", "b200_step_greedy", "b200_set_taps", "b200_get_tap",
                 "b200_timings", "b200_reset_timings", "b200_kernel_launches", "b200_last_device_ms", "b200_profile_token", "b200_profile_kind", "b200_trace_token", "b200_trace_phases", "b200_set_token_kernel", "b200_set_prefill_batch", "b200_set_prefill_mma", "b200_set_prefill_attn_batch", "b200_job_timing_us", "b200_comm_unique_id",
-                "b200_comm_init", "b200_p2p_handle", "b200_p2p_connect", "b200_pipeline_generate_greedy", "b200_pipeline_decode", "b200_stage_forward", "b200_stage_batch_usable", "b200_stage_forward_batch",
+                "b200_comm_init", "b200_p2p_handle", "b200_p2p_connect", "b200_p2p_disable", "b200_pipeline_generate_greedy", "b200_pipeline_decode", "b200_stage_forward", "b200_stage_batch_usable", "b200_stage_forward_batch",
                 "b200_stage_logits", "b200_stage_argmax", "b200_stage_logits_view", "b200_decode_view", "b200_stage_sync", "b200_kv_write", "b200_kv_read", "b200_kv_seq_rm", "b200_kv_seq_add", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
                 "b200_op_dequantize_row", "b200_op_mul_mat_vec", "b200_op_mul_mat", "b200_op_rms_norm", "b200_op_rope",
                 "b200_op_attention", "b200_set_attention_route", "b200_tokenizer_load", "b200_tokenizer_free", "b200_tokenizer_n_vocab", "b200_tokenize",
@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
     sig("b200_comm_init", C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)])
     sig("b200_p2p_handle", C.c_int, [vp, C.POINTER(C.c_uint8)])
     sig("b200_p2p_connect", C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)])
+    sig("b200_p2p_disable", None, [vp])
     sig("b200_pipeline_generate_greedy", C.c_int, [vp, C.c_int32, C.c_int, C.c_int, i32p])
     sig("b200_pipeline_decode", C.c_int, [vp, i32p, C.c_int, C.c_int, f32p])
     sig("b200_stage_forward", C.c_int, [vp, C.c_int32, C.c_int, C.c_int, vp])

@@ -2222,6 +2222,9 @@ extern "C" int b200_p2p_connect(b200_ctx * c, int rank, int world, const uint8_t
         return 0;
     } catch (const std::exception & e) { return set_err(e.what()); }
 }
+// back to ncclSend / ncclRecv for this context (every rank of the group must take the same decision: a rank that could not
+// map a peer's inbox reports it through the host-side process group and all of them call this)
+extern "C" void b200_p2p_disable(b200_ctx * c) { if (c) c->p2p = false; }
 
 // one token through this rank's stage: [recv x] -> forward -> [send x] ; last stage: argmax -> token to stage 0
 static void enqueue_stage_step(b200_ctx * c, bool greedy) {

@@ -187,6 +187,9 @@ class Context:
         fh = (C.c_uint8 * 64).from_buffer_copy(first_handle)
         check(self.L.b200_p2p_connect(self.h, rank, world, nh, fh), "b200_p2p_connect")
 
+    def p2p_disable(self):
+        self.L.b200_p2p_disable(self.h)
+
     def pipeline_generate_greedy(self, first_token: int, pos0: int, n_steps: int) -> np.ndarray:
         out = np.empty(n_steps, dtype=np.int32)
         check(self.L.b200_pipeline_generate_greedy(self.h, first_token, pos0, n_steps,

@@ -78,3 +78,33 @@ def exchange_inbox_handles(dist, my_handle: bytes) -> Tuple[bytes, bytes]:
     if any(not isinstance(h, (bytes, bytearray)) or len(h) != 64 for h in handles):
         raise RuntimeError("bad inbox handle from a peer")
     return bytes(handles[min(rank + 1, world - 1)]), bytes(handles[0])
+
+
+def connect_peer_handoff(dist, ctx, rank: int, world: int) -> bool:
+    """set up the NVLink peer hand-off on every rank, or on none: a rank that cannot export / map an inbox (no peer access
+    between two devices, IPC refused) makes the whole group fall back to ncclSend / ncclRecv. Returns what was decided."""
+    ok, handle = 1, bytes(64)
+    try:
+        handle = ctx.p2p_handle()
+    except Exception:
+        ok = 0
+    try:
+        nxt, first = exchange_inbox_handles(dist, handle)
+        if ok:
+            ctx.p2p_connect(rank, world, nxt, first)
+    except Exception:
+        ok = 0
+    all_ok = min_over_ranks(dist, ok)
+    if not all_ok:
+        try:
+            ctx.p2p_disable()
+        except Exception:
+            pass
+    return bool(all_ok)
+
+
+def min_over_ranks(dist, v: int) -> int:
+    import torch
+    t = torch.tensor([int(v)], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item())

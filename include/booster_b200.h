@@ -163,6 +163,8 @@ int b200_comm_init(b200_ctx * c, int rank, int world, const uint8_t id[128]);
  * (first_handle; used by the last rank). b200_comm_init is still required (the ids of a burst are broadcast with NCCL). */
 int b200_p2p_handle(b200_ctx * c, uint8_t handle[64]);
 int b200_p2p_connect(b200_ctx * c, int rank, int world, const uint8_t next_handle[64], const uint8_t first_handle[64]);
+/* back to ncclSend / ncclRecv (collective decision of the group when a rank could not map a peer's inbox) */
+void b200_p2p_disable(b200_ctx * c);
 /* All ranks call this collectively: run n_steps greedy tokens through the pipeline, starting from
  * first_token at position pos0. Every rank receives the token ids in out_tokens. */
 int b200_pipeline_generate_greedy(b200_ctx * c, int32_t first_token, int pos0, int n_steps, int32_t * out_tokens);

@@ -58,8 +58,27 @@ def _worker(rank, world, port, q):
             dist.recv(x, src=0)
         # inbox handles of the direct NVLink hand-off: every rank learns its successor's and rank 0's
         nxt, first = P.exchange_inbox_handles(dist, bytes([rank]) * 64)
+
+        # the peer hand-off is taken by every rank or by none: rank 1 cannot map its peer here -> both fall back to NCCL
+        class FakeCtx:
+            def __init__(self, fail):
+                self.fail, self.connected, self.disabled = fail, False, False
+
+            def p2p_handle(self):
+                return bytes([rank]) * 64
+
+            def p2p_connect(self, r, w, n, f):
+                if self.fail:
+                    raise RuntimeError("cudaIpcOpenMemHandle failed")
+                self.connected = True
+
+            def p2p_disable(self):
+                self.disabled = True
+
+        bad, good = FakeCtx(rank == 1), FakeCtx(False)
+        decided = (P.connect_peer_handoff(dist, bad, rank, world), bad.disabled, P.connect_peer_handoff(dist, good, rank, world), good.disabled)
         dist.barrier()
-        q.put((rank, uid, lb, le, slowest, launches, float(x[0]), nxt[0], first[0]))
+        q.put((rank, uid, lb, le, slowest, launches, float(x[0]), nxt[0], first[0], decided))
     finally:
         dist.destroy_process_group()
 
@@ -83,3 +102,4 @@ def test_world2_gloo():
     assert all(r[5] == 300 for r in res)
     assert res[1][6] == 0.0                                        # stage 1 received stage 0's stream
     assert [(r[7], r[8]) for r in res] == [(1, 0), (1, 0)]         # next rank's handle (the last rank: its own), rank 0's handle
+    assert all(r[9] == (False, True, True, False) for r in res)    # one rank's failure disables the peer hand-off on both
