@@ -396,6 +396,11 @@ def main():
                                                 "k_quant_batch_mma + k_mma_batch (exact fp16 HMMA per AVX2 lane-slice)") +
                                                " + k_attn_scores_batch / k_attn_softmax_rows / k_attn_pv_batch",
                                     "what": "b200_decode of one 512-token batch at positions 0..511, wall clock incl. the final synchronisation"}
+            try:   # tensor-pipe utilisation of the batch mat-mul kernel from the committed ncu --set full capture
+                with open(os.path.join(ROOT, "profiles", "prefill_tensor.json")) as f:
+                    line["prompt_batch"]["tensor_pipe"] = json.load(f)["k_mma_batch_q80" if ftype == "Q8_0" else "k_mma_batch"]
+            except Exception:
+                pass
         except Exception as e:
             line["prompt_batch"] = {"error": str(e)}
         # ---- end to end, additive token-level seam: host token in, host logits out, host arg-max
