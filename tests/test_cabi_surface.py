@@ -71,3 +71,18 @@ def test_no_cpu_fallback(golden_dir):
     assert L.doInference(0, None, b"job", b"", b"1 2 3") == 0
     assert L.status(b"nope") == b""
     assert L.timing(b"nope") == 0 and L.promptEval(b"nope") == 0 and L.getPromptTokenCount(b"nope") == 0
+
+
+def test_sass_shows_the_hardware_paths():
+    """the shipped library is sm_100a code whose hot kernels use what DESIGN.md says they use: TMA bulk copies + mbarriers in
+    the mat-vec / batch kernels, mma.sync HMMA in the default prompt-batch kernels, tcgen05.mma / TMEM loads in k_umma_batch
+    (profiles/r02h_sass_summary.txt is the same listing per kernel)"""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "booster_b200", "libbooster_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UBLKCP", "SYNCS", "HMMA.16816.F32", "LDSM", "UTCHMMA", "UTCBAR", "LDTM", "IDP.4A"):
+        assert mnemonic in sass, mnemonic
