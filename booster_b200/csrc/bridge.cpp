@@ -112,7 +112,7 @@ void init(char * swap, char * debug) {
     for (auto & s : g_stop) s.store(false);
 }
 
-void * initContext(
+static void * init_context_impl(
     int idx, char * modelName, int threads, int batch_size,
     int gpu1, int gpu2, int gpu3, int gpu4,
     int context, int predict,
@@ -150,6 +150,7 @@ void * initContext(
         for (size_t i = (size_t) n_dev; i < prop.size(); i++) if (prop[i] > 0) { std::fprintf(stderr, "initContext: split names device %zu but only %d visible\n", i, n_dev); return nullptr; }
         prop.resize((size_t) n_dev);
     }
+    for (float & f : prop) if (!(f > 0.f)) f = 0.f;   // negative or NaN shares name no device
     float sum = 0; for (float f : prop) sum += f;
     if (sum <= 0) { prop.assign(1, 1.f); }   // the reference would run on the CPU; this library is the GPU path
 
@@ -189,7 +190,31 @@ void * initContext(
     return (void *) &p;
 }
 
-int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * prompt) {
+// No C++ exception may cross the cgo boundary (it would terminate the Go server): allocation failures and anything else
+// unexpected end the call with the reference's failure value (nullptr / 0) and a line on stderr.
+void * initContext(
+    int idx, char * modelName, int threads, int batch_size,
+    int gpu1, int gpu2, int gpu3, int gpu4,
+    int context, int predict,
+    int32_t mirostat, float mirostat_tau, float mirostat_eta,
+    float temperature, int top_k, float top_p, float typical_p,
+    float repetition_penalty, int penalty_last_n,
+    int32_t janus, int32_t depth, float scale, float hi, float lo,
+    uint32_t seed, char * debug) {
+    try {
+        return init_context_impl(idx, modelName, threads, batch_size, gpu1, gpu2, gpu3, gpu4, context, predict, mirostat, mirostat_tau,
+                                 mirostat_eta, temperature, top_k, top_p, typical_p, repetition_penalty, penalty_last_n, janus, depth,
+                                 scale, hi, lo, seed, debug);
+    } catch (const std::exception & e) {
+        std::fprintf(stderr, "initContext: %s\n", e.what());
+    } catch (...) {
+        std::fprintf(stderr, "initContext: unknown failure\n");
+    }
+    if (idx >= 0 && idx < MAX_PODS) g_pods[idx].release();
+    return nullptr;
+}
+
+static int64_t do_inference_impl(int idx, void * ctx, char * jobID, char * sessionID, char * prompt) {
     (void) sessionID;
     if (idx < 0 || idx >= MAX_PODS || !ctx || !jobID || !prompt) return 0;
     Pod & p = g_pods[idx];
@@ -341,6 +366,17 @@ int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * 
     return n_p_eval + n_eval;
 }
 
+int64_t doInference(int idx, void * ctx, char * jobID, char * sessionID, char * prompt) {
+    try {
+        return do_inference_impl(idx, ctx, jobID, sessionID, prompt);
+    } catch (const std::exception & e) {
+        std::fprintf(stderr, "doInference: %s\n", e.what());
+    } catch (...) {
+        std::fprintf(stderr, "doInference: unknown failure\n");
+    }
+    return 0;
+}
+
 void stopInference(int idx) {
     if (idx >= 0 && idx < MAX_PODS) g_stop[idx].store(true);
 }
@@ -379,7 +415,7 @@ uint32_t getSeed(char * jobID) {
 int b200_job_timing_us(const char * jobID, double * prompt_us_per_token, double * gen_us_per_token) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_jobs.find(jobID ? jobID : "");
-    if (it == g_jobs.end()) return 1;
+    if (it == g_jobs.end() || !prompt_us_per_token || !gen_us_per_token) return 1;
     *prompt_us_per_token = it->second.prompt_us_per_tok;
     *gen_us_per_token    = it->second.gen_us_per_tok;
     return 0;

@@ -6,8 +6,8 @@
 // (token, pos) live in device memory (DecodeState) so the graph never needs re-instantiation.
 //
 //   per layer:  k_matvec<QKV>   [RMSNorm(attn_norm)+Q8_K quant] -> wq|wk|wv -> RoPE -> q (f32), K/V (f16 cache)
-//               k_attn_partial  split-KV attention over the f16 cache (GQA group per CTA)
-//               k_attn_combine  merge splits -> kqv_merged_cont
+//               k_attn_scores      raw K.q scores of the f16 cache (GQA group per CTA, 64 positions each)
+//               k_attn_softmax_pv  soft-max of the score rows + P.V -> kqv_merged_cont
 //               k_matvec<RESID> [quant] -> wo -> + residual                          (ffn_inp)
 //               k_matvec<SILU>  [RMSNorm(ffn_norm)+quant] -> gate|up -> silu(g)*u    (ffn_gate_par)
 //               k_matvec<RESID> [quant] -> down -> + residual                        (l_out)
@@ -288,6 +288,7 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
     cudaStream_t st = nullptr;
     try {
         require_gpu();
+        if (!path) throw std::runtime_error("null model path");
         gguf_file g;
         const std::string err = g.open(path);
         if (!err.empty()) throw std::runtime_error(err);
@@ -305,7 +306,7 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
         m->n_head_kv   = (int) g.get_u("llama.attention.head_count_kv", (uint64_t) m->n_head);
         m->rms_eps     = (float) g.get_f("llama.attention.layer_norm_rms_epsilon", 1e-5);
         m->ftype       = (int) g.get_u("general.file_type", (uint64_t) -1);
-        if (m->n_embd <= 0 || m->n_layer <= 0 || m->n_head <= 0 || m->n_ff <= 0) throw std::runtime_error("missing llama.* hyper-parameters");
+        if (m->n_embd <= 0 || m->n_layer <= 0 || m->n_head <= 0 || m->n_head_kv <= 0 || m->n_ff <= 0) throw std::runtime_error("missing llama.* hyper-parameters");
         m->head_dim    = (int) g.get_u("llama.attention.key_length", (uint64_t) (m->n_embd / m->n_head));
         m->rope_dim    = (int) g.get_u("llama.rope.dimension_count", (uint64_t) m->head_dim);
         if (m->rope_dim != m->head_dim) throw std::runtime_error("n_rot != head_dim is not supported on this path");
@@ -323,6 +324,8 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
         m->yarn_attn_factor = (float) g.get_f("llama.rope.scaling.attn_factor", 1.0);
         const gguf_tensor * te = g.find("token_embd.weight");
         if (!te) throw std::runtime_error("missing token_embd.weight");
+        if ((int64_t) te->ne[0] != m->n_embd) throw std::runtime_error("token_embd.weight rows must have n_embd elements");
+        if (te->ne[1] == 0 || te->ne[1] > (uint64_t) INT32_MAX) throw std::runtime_error("bad vocabulary size");
         m->n_vocab = (int) te->ne[1];
         if (layer_end < 0 || layer_end > m->n_layer) layer_end = m->n_layer;
         if (layer_begin < 0 || layer_begin >= layer_end) throw std::runtime_error("bad layer range");
@@ -338,6 +341,7 @@ extern "C" b200_model * b200_model_load(const char * path, int device, int layer
         const int E = m->n_embd, HD = m->head_dim, KV = m->n_head_kv * HD, Q = m->n_head * HD, FF = m->n_ff;
         if (const gguf_tensor * rf = g.find("rope_freqs.weight")) {
             if (rf->type != 0) throw std::runtime_error("rope_freqs.weight must be F32");
+            if ((int64_t) rf->ne[0] < m->head_dim / 2) throw std::runtime_error("rope_freqs.weight is shorter than head_dim / 2");
             m->rope_freq_factors.assign((const float *) rf->data, (const float *) rf->data + rf->ne[0]);
         }
         int64_t wb = 0;
@@ -613,6 +617,16 @@ static thread_local int g_only_kind = -1;       // b200_profile_kind: enqueue_fo
 // there first
 static std::mutex g_attr_mu;
 static bool want(int kind) { return g_only_kind < 0 || g_only_kind == kind; }
+// raise a kernel's dynamic shared-memory limit at most once per size and device; `have` (the per-device high-water mark) is
+// read and written under g_attr_mu only — pods on different OS threads reach the same kernels concurrently
+template <typename K>
+static void raise_smem(K kern, size_t smem, size_t (&have)[64], int device) {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (smem <= have[device & 63]) return;
+    cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e_));
+    have[device & 63] = smem;
+}
 struct ProfScope {
     b200_ctx * c; cudaEvent_t a = nullptr, b = nullptr;
     explicit ProfScope(b200_ctx * c_);
@@ -1186,6 +1200,7 @@ extern "C" b200_ctx * b200_ctx_new(b200_model * m, int n_ctx) {
         c->device = m->device;
         CU(cudaSetDevice(m->device));
         if (n_ctx <= 0) n_ctx = m->n_ctx_train;
+        if (n_ctx <= 0) throw std::runtime_error("n_ctx must be positive (the model names no llama.context_length either)");
         c->n_ctx = (n_ctx + 31) / 32 * 32;                       // GGML_PAD(n_ctx, 32): cpp/src/llama.cpp:16655
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, m->device));
@@ -1507,7 +1522,7 @@ extern "C" int b200_kv_read(b200_ctx * c, int layer, int pos0, int n, uint16_t *
 
 extern "C" void b200_set_taps(b200_ctx * c, int enable) { if (c) { c->taps = enable != 0; c->tapstore.v.clear(); } }
 extern "C" int64_t b200_get_tap(b200_ctx * c, const char * name, int layer, float * out, int64_t cap) {
-    if (!c) return 0;
+    if (!c || !name) return 0;
     auto it = c->tapstore.v.find(std::string(name) + "-" + std::to_string(layer));
     if (it == c->tapstore.v.end()) return 0;
     const int64_t n = (int64_t) it->second.size();
@@ -1515,9 +1530,10 @@ extern "C" int64_t b200_get_tap(b200_ctx * c, const char * name, int layer, floa
     return n;
 }
 extern "C" void b200_timings(b200_ctx * c, double * tp, int64_t * np, double * tg, int64_t * ng) {
+    if (!c || !tp || !np || !tg || !ng) return;
     *tp = c->t_prompt_us; *np = c->n_prompt; *tg = c->t_gen_us; *ng = c->n_gen;
 }
-extern "C" void b200_reset_timings(b200_ctx * c) { c->t_prompt_us = c->t_gen_us = 0; c->n_prompt = c->n_gen = 0; }
+extern "C" void b200_reset_timings(b200_ctx * c) { if (!c) return; c->t_prompt_us = c->t_gen_us = 0; c->n_prompt = c->n_gen = 0; }
 
 static double now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -1596,19 +1612,11 @@ static void pb_quant(b200_ctx * c, const float * X, int k, int T, const float * 
     a.act_q8_0 = act_q8_0; a.with_as = with_as; a.rec = c->pb.rec; a.layout = mma;
     const size_t smem = act_smem_bytes(k, act_q8_0);
     static size_t attr[64] = {0};
-    if (smem > 48 * 1024 && smem > attr[c->device & 63]) {
-        std::lock_guard<std::mutex> lk(g_attr_mu);
-        CU(cudaFuncSetAttribute(k_quant_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attr[c->device & 63] = smem;
-    }
+    if (smem > 48 * 1024) raise_smem(k_quant_batch, smem, attr, c->device);
     if (norm_w && k / 256 > PRO_U * 16) throw std::runtime_error("normed vector too long for the batched quantizer");
     if (mma) {
         static size_t attr_m[64] = {0};
-        if (smem > 48 * 1024 && smem > attr_m[c->device & 63]) {
-            std::lock_guard<std::mutex> lk(g_attr_mu);
-            CU(cudaFuncSetAttribute(k_quant_batch_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            attr_m[c->device & 63] = smem;
-        }
+        if (smem > 48 * 1024) raise_smem(k_quant_batch_mma, smem, attr_m, c->device);
         k_quant_batch_mma<<<(unsigned) T, 512, smem, c->st>>>(a);
     } else {
         k_quant_batch<<<(unsigned) T, 512, smem, c->st>>>(a);
@@ -1637,11 +1645,7 @@ static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int p
         if (a.mb_stages < 2) throw std::runtime_error("k_mma_batch_q80: shared memory layout does not fit");
         const size_t smem_q = (size_t) 2 * a.mb_a_bytes + (size_t) a.mb_stages * a.mb_stage_bytes;
         static size_t attr_q[64] = {0};
-        if (smem_q > attr_q[c->device & 63]) {
-            std::lock_guard<std::mutex> lk(g_attr_mu);
-            CU(cudaFuncSetAttribute(k_mma_batch_q80, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_q));
-            attr_q[c->device & 63] = smem_q;
-        }
+        raise_smem(k_mma_batch_q80, smem_q, attr_q, c->device);
         const dim3 grid_q((unsigned) ((T + MB_NT - 1) / MB_NT), (unsigned) (a.n_units / 2));
         k_mma_batch_q80<<<grid_q, MB_WARPS * 32, smem_q, c->st>>>(a);
         c->launches++;
@@ -1657,11 +1661,7 @@ static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int p
         if (a.mb_stages < 2) throw std::runtime_error("k_umma_batch: shared memory layout does not fit");
         const size_t smem_u = std::max((size_t) a.mb_a_bytes + (size_t) a.mb_stages * a.mb_stage_bytes, (size_t) 120 * 1024);   // one CTA per SM (TMEM)
         static size_t attr_u[64] = {0};
-        if (smem_u > attr_u[c->device & 63]) {
-            std::lock_guard<std::mutex> lk(g_attr_mu);
-            CU(cudaFuncSetAttribute(k_umma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_u));
-            attr_u[c->device & 63] = smem_u;
-        }
+        raise_smem(k_umma_batch, smem_u, attr_u, c->device);
         const dim3 grid_u((unsigned) ((T + UM_NT - 1) / UM_NT), (unsigned) (a.n_units / 4));
         k_umma_batch<<<grid_u, UM_WARPS * 32, smem_u, c->st>>>(a);
         c->launches++;
@@ -1677,11 +1677,7 @@ static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int p
         if (a.mb_stages < 2) throw std::runtime_error("k_mma_batch: shared memory layout does not fit");
         const size_t smem_m = std::max((size_t) 2 * a.mb_a_bytes + (size_t) a.mb_stages * a.mb_stage_bytes, (size_t) MB_CHAIN_BYTES);
         static size_t attr_m[64] = {0};
-        if (smem_m > attr_m[c->device & 63]) {
-            std::lock_guard<std::mutex> lk(g_attr_mu);
-            CU(cudaFuncSetAttribute(k_mma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_m));
-            attr_m[c->device & 63] = smem_m;
-        }
+        raise_smem(k_mma_batch, smem_m, attr_m, c->device);
         const dim3 grid_m((unsigned) ((T + MB_NT - 1) / MB_NT), (unsigned) (a.n_units / 2));
         k_mma_batch<<<grid_m, MB_WARPS * 32, smem_m, c->st>>>(a);
         c->launches++;
@@ -1689,11 +1685,7 @@ static void pb_matmul(b200_ctx * c, const MatvecArgs & mv, int epi, int T, int p
     }
     const size_t smem = PB_STAGES * pb_stage_bytes(sb, a.act_q8_0, with_as);
     static size_t attr[64] = {0};
-    if (smem > attr[c->device & 63]) {
-        std::lock_guard<std::mutex> lk(g_attr_mu);
-        CU(cudaFuncSetAttribute(k_matmul_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attr[c->device & 63] = smem;
-    }
+    raise_smem(k_matmul_batch, smem, attr, c->device);
     const dim3 grid((unsigned) ((T + PB_CHUNK - 1) / PB_CHUNK), (unsigned) a.n_units);
     k_matmul_batch<<<grid, PB_WARPS * 32, smem, c->st>>>(a, sb);
     c->launches++;
@@ -1719,12 +1711,8 @@ static void pb_attention(b200_ctx * c, int li, int T, int pos0) {
         const dim3 gs((unsigned) a.n_head_kv, (unsigned) ((n_pad_max + ATT_TILE - 1) / ATT_TILE), (unsigned) ((nz + SCB_TQ - 1) / SCB_TQ));
         k_attn_scores_batch<GQA><<<gs, ATT_THREADS, 0, c->st>>>(a, nz);
         k_attn_softmax_rows<<<(unsigned) ((nz * a.n_head + 7) / 8), 256, 0, c->st>>>(a, nz);
-        static bool attr_done[64] = {false};
-        if (!attr_done[c->device & 63]) {
-            std::lock_guard<std::mutex> lk(g_attr_mu);
-            CU(cudaFuncSetAttribute(k_attn_pv_batch<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pvb_smem_bytes()));
-            attr_done[c->device & 63] = true;
-        }
+        static size_t attr_pvb[64] = {0};
+        raise_smem(k_attn_pv_batch<GQA>, pvb_smem_bytes(), attr_pvb, c->device);
         constexpr int TQ = PVB_ROWS / GQA;
         const dim3 gp((unsigned) a.n_head_kv, (unsigned) (128 / PVB_DIMS), (unsigned) ((nz + TQ - 1) / TQ));
         k_attn_pv_batch<GQA><<<gp, 256, pvb_smem_bytes(), c->st>>>(a, nz);
@@ -1990,7 +1978,7 @@ extern "C" int b200_profile_token(b200_ctx * c, int32_t token, int pos, float ms
         }
         c->prof_ev.clear();
         return 0;
-    } catch (const std::exception & e) { c->prof = false; return set_err(e.what()); }
+    } catch (const std::exception & e) { if (c) c->prof = false; return set_err(e.what()); }
 }
 
 // Kernel-in-isolation timing: the launches of ONE kind (e.g. the gate|up mat-vec) of every layer of this stage, back to
@@ -2060,7 +2048,7 @@ extern "C" int64_t b200_trace_token(b200_ctx * c, int32_t token, int pos, int re
         if (out && cap_words >= need) CU(cudaMemcpy(out, c->d_trace, (size_t) need * 8, cudaMemcpyDeviceToHost));
         if (meta) for (int64_t i = 0; i < nl && 2 * i + 1 < cap_meta; i++) { meta[2 * i] = c->trace_meta[(size_t) i][0]; meta[2 * i + 1] = c->trace_meta[(size_t) i][1]; }
         return nl;
-    } catch (const std::exception & e) { c->tracing = false; set_err(e.what()); return -1; }
+    } catch (const std::exception & e) { if (c) c->tracing = false; set_err(e.what()); return -1; }
 }
 
 // One token through the persistent kernel's tracing instantiation: out = [n_phases][n_ctas][4] globaltimer stamps (ns):
@@ -2102,11 +2090,12 @@ extern "C" int64_t b200_trace_phases(b200_ctx * c, int32_t token, int pos, int r
 // pipeline over NCCL: rank r holds one stage; one send/recv of f32[n_embd] per boundary per token
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int b200_comm_unique_id(uint8_t id[128]) {
-    try { nccl_load(); NC(g_nccl.GetUniqueId(id)); return 0; } catch (const std::exception & e) { return set_err(e.what()); }
+    try { if (!id) throw std::runtime_error("null id"); nccl_load(); NC(g_nccl.GetUniqueId(id)); return 0; } catch (const std::exception & e) { return set_err(e.what()); }
 }
 extern "C" int b200_comm_init(b200_ctx * c, int rank, int world, const uint8_t id[128]) {
     try {
         require_gpu();
+        if (!c || !id || world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad arguments");
         nccl_load();
         CU(cudaSetDevice(c->m->device));
         NcclId nid; std::memcpy(nid.b, id, 128);
@@ -2399,6 +2388,7 @@ extern "C" int b200_stage_logits(b200_ctx * c, float * logits_out) {
     try {
         require_gpu();
         if (!c || !c->m->has_head()) throw std::runtime_error("not the last stage");
+        if (!logits_out) throw std::runtime_error("null output");
         CU(cudaSetDevice(c->m->device));
         CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t) c->m->n_vocab * 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
@@ -2428,6 +2418,7 @@ extern "C" int b200_stage_argmax(b200_ctx * c, int32_t * token_out) {
     try {
         require_gpu();
         if (!c || !c->m->has_head()) throw std::runtime_error("not the last stage");
+        if (!token_out) throw std::runtime_error("null output");
         CU(cudaSetDevice(c->m->device));
         enqueue_argmax(c, 0);
         CU(cudaMemcpyAsync(&c->h_state->token, c->d_out_tokens, 4, cudaMemcpyDeviceToHost, c->st));
