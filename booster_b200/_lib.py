@@ -25,8 +25,8 @@ B200_SYMBOLS = ["b200_last_error", "b200_device_count", "b200_version", "b200_mo
                 "b200_stage_logits", "b200_stage_argmax", "b200_stage_logits_view", "b200_decode_view", "b200_stage_sync", "b200_kv_write", "b200_kv_read", "b200_kv_seq_rm", "b200_kv_seq_add", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
                 "b200_op_dequantize_row", "b200_op_mul_mat_vec", "b200_op_mul_mat", "b200_op_rms_norm", "b200_op_rope",
                 "b200_op_attention", "b200_set_attention_route", "b200_tokenizer_load", "b200_tokenizer_free", "b200_tokenizer_n_vocab", "b200_tokenize",
-                "b200_token_to_piece", "b200_token_is_eog", "b200_cpt_class", "b200_op_launch_shape",
-                "b200_sampler_new", "b200_sampler_free", "b200_sampler_reset", "b200_sampler_sample"]
+                "b200_token_to_piece", "b200_token_is_eog", "b200_token_nl", "b200_cpt_class", "b200_op_launch_shape",
+                "b200_sampler_new", "b200_sampler_set_standard", "b200_sampler_free", "b200_sampler_reset", "b200_sampler_sample"]
 
 
 def lib() -> C.CDLL:
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     sig("b200_tokenize", C.c_int32, [vp, C.c_char_p, C.c_int32, i32p, C.c_int32, C.c_int, C.c_int])
     sig("b200_token_to_piece", C.c_int32, [vp, C.c_int32, C.c_char_p, C.c_int32, C.c_int])
     sig("b200_token_is_eog", C.c_int, [vp, C.c_int32])
+    sig("b200_token_nl", C.c_int32, [vp])
     sig("b200_cpt_class", C.c_int, [C.c_uint32])
     sig("b200_op_launch_shape", C.c_int, [i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, i32p])
     sig("b200_profile_token", C.c_int, [vp, C.c_int32, C.c_int, f32p, i32p])
@@ -122,6 +123,7 @@ def lib() -> C.CDLL:
     sig("b200_kv_seq_rm", C.c_int, [vp, C.c_int, C.c_int])
     sig("b200_kv_seq_add", C.c_int, [vp, C.c_int, C.c_int, C.c_int])
     sig("b200_sampler_new", vp, [cp, C.c_int, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int])
+    sig("b200_sampler_set_standard", None, [vp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float])
     sig("b200_sampler_free", None, [vp])
     sig("b200_sampler_reset", None, [vp, i32p, C.c_int32, C.c_uint32])
     sig("b200_sampler_sample", C.c_int32, [vp, f32p, C.c_int32, C.c_int32])

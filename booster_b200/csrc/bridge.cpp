@@ -122,10 +122,10 @@ static void * init_context_impl(
     int32_t janus, int32_t depth, float scale, float hi, float lo,
     uint32_t seed, char * debug) {
     (void) threads; (void) debug;
-    // mirostat and typical-p belong to the standard chain the reference keeps commented out; not implemented here either
-    if (mirostat != 0 || (typical_p > 0.f && typical_p < 1.f))
-        std::fprintf(stderr, "initContext: mirostat / typical_p are ignored (the reference's bridge never applies them: cpp/bridge.cpp:586-596)\n");
-    (void) mirostat_tau; (void) mirostat_eta;
+    // mirostat and typical-p belong to the standard chain, which the reference's bridge never calls (cpp/bridge.cpp:586-599):
+    // with janus != 0 they have no effect here either; with janus = 0 the chain runs with them
+    if (janus != 0 && (mirostat != 0 || (typical_p > 0.f && typical_p < 1.f)))
+        std::fprintf(stderr, "initContext: mirostat / typical_p have no effect with janus != 0 (as in the reference: cpp/bridge.cpp:586-596); janus = 0 selects the standard chain\n");
     if (idx < 0 || idx >= MAX_PODS || !modelName) return nullptr;
     Pod & p = g_pods[idx];
     p.release();                          // re-initialising a pod frees its previous weights and KV cache
@@ -186,6 +186,9 @@ static void * init_context_impl(
     p.jparams.janus = janus; p.jparams.depth = depth; p.jparams.scale = scale; p.jparams.hi = hi; p.jparams.lo = lo;
     p.sparams.temp = temperature; p.sparams.top_k = top_k; p.sparams.top_p = top_p;
     p.sparams.penalty_repeat = repetition_penalty; p.sparams.penalty_last_n = penalty_last_n;
+    p.sparams.mirostat = mirostat; p.sparams.mirostat_tau = mirostat_tau; p.sparams.mirostat_eta = mirostat_eta;
+    p.sparams.typical_p = typical_p > 0 ? typical_p : 1.0f;       // cpp/bridge.cpp:773
+    p.sparams.nl_token = p.tok->linefeed();
     if (janus != 0) p.janus.init(*p.tok, p.jparams, 0);
     return (void *) &p;
 }
@@ -300,10 +303,11 @@ static int64_t do_inference_impl(int idx, void * ctx, char * jobID, char * sessi
     const bool use_janus = p.jparams.janus != 0 && !force_greedy;
     b200::StandardSampler std_sampler;
     std_sampler.init(p.sparams, seed);
+    std_sampler.n_vocab_model = p.n_vocab;
+    for (int32_t t : inp) std_sampler.accept(t);           // cpp/bridge.cpp:618: prompt tokens enter the penalty window
     const bool device_argmax = !use_janus && (force_greedy || std_sampler.greedy());
     if (use_janus) p.janus.rng.seed(seed);                 // llama_set_rng_seed(ctx, seed): cpp/bridge.cpp:216-217
     std::vector<int32_t> last_tokens((size_t) p.n_ctx, 0); // cpp/bridge.cpp:437-438: only generated tokens enter
-    std::vector<int32_t> history(inp);                     // prompt + generated: the standard chain's penalty window
     int32_t id = 0;
     bool have_next = false;                                // device arg-max path: the next id came back with the decode
     float * lg = nullptr;                                  // host path: the logits of the last decoded token (the engine's pinned buffer)
@@ -319,11 +323,11 @@ static int64_t do_inference_impl(int idx, void * ctx, char * jobID, char * sessi
                 last_tokens.erase(last_tokens.begin());    // cpp/bridge.cpp:602-603
                 last_tokens.push_back(id);
             } else {
-                id = std_sampler.sample(lg, p.n_vocab, history);
+                id = std_sampler.sample(lg, p.n_vocab);
             }
             lg = nullptr;
         }
-        history.push_back(id);
+        std_sampler.accept(id);                            // cpp/bridge.cpp:605
         --n_remain;
         { std::lock_guard<std::mutex> lk(g_mu); g_jobs[job].text += p.tok->piece(id, true); }
         if (p.tok->is_eog(id)) break;                      // cpp/bridge.cpp:640

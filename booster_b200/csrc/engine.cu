@@ -2465,6 +2465,7 @@ extern "C" int32_t b200_token_to_piece(const b200_tokenizer * h, int32_t token, 
     return (int32_t) p.size();
 }
 extern "C" int b200_token_is_eog(const b200_tokenizer * h, int32_t token) { return h && h->t->is_eog(token) ? 1 : 0; }
+extern "C" int32_t b200_token_nl(const b200_tokenizer * h) { return h ? h->t->linefeed() : -1; }
 
 // ------------------------------------------------------------------------------------------------------------
 // operator-level entry points (tests): host in, host out, SAME kernels

@@ -2,6 +2,7 @@
 #include "janus.hpp"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -246,50 +247,233 @@ int32_t JanusSampler::sample(float * logits, const std::vector<int32_t> & last_t
     return cand[(size_t) dist(rng)].id;
 }
 
-// llama_sampling_sample's default chain (cpp/common/sampling.cpp llama_sampling_prepare + sampler_queue "kfypmt"):
-// repetition penalty over the last penalty_last_n tokens (llama_sample_repetition_penalties_impl), top-k, (tail-free z = 1
-// and typical p = 1 are no-ops), top-p, min-p, temperature, softmax draw
-int32_t StandardSampler::sample(const float * logits_in, int32_t n_vocab, const std::vector<int32_t> & prev) {
-    struct Cand { int32_t id; float logit; float p; };
-    std::vector<Cand> cand((size_t) n_vocab);
-    for (int32_t id = 0; id < n_vocab; id++) cand[(size_t) id] = {id, logits_in[id], 0.f};
-    if (p.penalty_repeat != 1.0f && p.penalty_last_n != 0 && !prev.empty()) {
-        const size_t n = p.penalty_last_n < 0 ? prev.size() : std::min(prev.size(), (size_t) p.penalty_last_n);
-        std::vector<uint8_t> seen((size_t) n_vocab, 0);
-        for (size_t i = prev.size() - n; i < prev.size(); i++) if (prev[i] >= 0 && prev[i] < n_vocab) seen[(size_t) prev[i]] = 1;
-        for (auto & c : cand) if (seen[(size_t) c.id]) c.logit = c.logit <= 0 ? c.logit * p.penalty_repeat : c.logit / p.penalty_repeat;
+// ------------------------------------------------------------------------------------------------------------
+// the standard chain: llama_sampling_sample (cpp/common/sampling.cpp:271-340) over cpp/src/llama-sampling.cpp
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Cand { int32_t id; float logit; float p; };
+struct Cands {                          // llama_token_data_array: the live prefix of `v` and whether it is sorted by logit
+    std::vector<Cand> v;
+    bool sorted = false;
+};
+const auto by_logit_desc = [](const Cand & a, const Cand & b) { return a.logit > b.logit; };
+
+// llama_sample_softmax_impl (:32-59)
+void softmax(Cands & c) {
+    if (!c.sorted) { std::sort(c.v.begin(), c.v.end(), by_logit_desc); c.sorted = true; }
+    const float top = c.v[0].logit;
+    float total = 0.0f;
+    for (Cand & x : c.v) { x.p = expf(x.logit - top); total += x.p; }
+    for (Cand & x : c.v) x.p /= total;
+}
+
+// llama_sample_top_k_impl (:61-140). k <= 128: partial sort. Larger k: 128 buckets over logits -10..10, the buckets above the
+// one that holds the k-th candidate fully sorted, that one partially — restated because the order of tied logits (and with it
+// a later draw) depends on it. The bucket index is one fused multiply-add in the reference's build.
+void top_k(Cands & c, int32_t k, size_t min_keep) {
+    const int n = (int) c.v.size();
+    if (k <= 0) k = n;
+    k = std::max(k, (int) min_keep);
+    k = std::min(k, n);
+    if (!c.sorted) {
+        if (k <= 128) {
+            std::partial_sort(c.v.begin(), c.v.begin() + k, c.v.end(), by_logit_desc);
+        } else {
+            constexpr int NB = 128;
+            constexpr float lo = -10.0f, hi = 10.0f, scale = NB / (hi - lo), inter = -lo * scale;
+            std::vector<int> which((size_t) n), count(NB, 0);
+            for (int i = 0; i < n; i++) {
+                int b = (int) fmaf(scale, c.v[(size_t) i].logit, inter);
+                b = std::max(0, std::min(NB - 1, b));
+                which[(size_t) i] = b; count[(size_t) b]++;
+            }
+            int have = 0, cut = NB - 1;
+            for (; cut >= 0; cut--) { have += count[(size_t) cut]; if (have >= k) break; }
+            std::vector<Cand> kept((size_t) have);
+            std::vector<size_t> fill((size_t) NB, 0);         // write cursor of every kept bucket, highest bucket first
+            { size_t at = 0; for (int b = NB - 1; b >= cut; b--) { fill[(size_t) b] = at; at += (size_t) count[(size_t) b]; } }
+            for (int i = 0; i < n; i++) { const int b = which[(size_t) i]; if (b >= cut) kept[fill[(size_t) b]++] = c.v[(size_t) i]; }
+            size_t at = 0; int done = 0;
+            for (int b = NB - 1; b > cut; b--) {
+                std::sort(kept.begin() + (long) at, kept.begin() + (long) (at + (size_t) count[(size_t) b]), by_logit_desc);
+                at += (size_t) count[(size_t) b]; done += count[(size_t) b];
+            }
+            std::partial_sort(kept.begin() + (long) at, kept.begin() + (long) at + (k - done), kept.begin() + (long) (at + (size_t) count[(size_t) cut]), by_logit_desc);
+            std::copy(kept.begin(), kept.begin() + k, c.v.begin());
+        }
+        c.sorted = true;
     }
-    const auto by_logit = [](const Cand & a, const Cand & b) { return a.logit > b.logit; };
-    if (p.temp <= 0.f) return std::max_element(cand.begin(), cand.end(), [](const Cand & a, const Cand & b) { return a.logit < b.logit; })->id;
-    size_t k = p.top_k <= 0 ? cand.size() : std::min(cand.size(), (size_t) p.top_k);
-    std::partial_sort(cand.begin(), cand.begin() + (long) k, cand.end(), by_logit);
-    cand.resize(k);
-    auto softmax = [&]() {
-        const float mx = cand[0].logit;
-        float cum = 0.f;
-        for (auto & c : cand) { c.p = expf(c.logit - mx); cum += c.p; }
-        for (auto & c : cand) c.p /= cum;
-    };
-    if (p.top_p < 1.0f) {
-        softmax();
-        float cum = 0.f;
-        size_t last = cand.size();
-        for (size_t i = 0; i < cand.size(); i++) { cum += cand[i].p; if (cum >= p.top_p) { last = i + 1; break; } }
-        cand.resize(std::max<size_t>(1, last));
+    c.v.resize((size_t) k);
+}
+
+// llama_sample_top_p_impl (:142-172)
+void top_p(Cands & c, float p, size_t min_keep) {
+    if (p >= 1.0f) return;
+    softmax(c);
+    float cum = 0.0f;
+    size_t last = c.v.size();
+    for (size_t i = 0; i < c.v.size(); i++) {
+        cum += c.v[i].p;
+        if (cum >= p && i + 1 >= min_keep) { last = i + 1; break; }
     }
-    if (p.min_p > 0.0f) {
-        softmax();
-        const float thr = cand[0].p * p.min_p;
-        size_t keep = 1;
-        while (keep < cand.size() && cand[keep].p >= thr) keep++;
-        cand.resize(keep);
+    c.v.resize(last);
+}
+
+// llama_sample_min_p_impl (:174-233): on LOGITS (logit >= top + logf(p)), unsorted filter first when it keeps enough
+void min_p(Cands & c, float p, size_t min_keep) {
+    if (p <= 0.0f || c.v.empty()) return;
+    if (!c.sorted) {
+        float top = -FLT_MAX;
+        for (const Cand & x : c.v) top = std::max(top, x.logit);
+        const float floor_logit = top + logf(p);
+        std::vector<Cand> keep;
+        for (const Cand & x : c.v) if (x.logit >= floor_logit) keep.push_back(x);
+        if (keep.size() >= min_keep) { c.v.swap(keep); return; }
+        std::sort(c.v.begin(), c.v.end(), by_logit_desc);
+        c.sorted = true;
     }
-    for (auto & c : cand) c.logit /= p.temp;
-    softmax();
+    const float floor_logit = c.v[0].logit + logf(p);
+    size_t i = 1;
+    for (; i < c.v.size(); i++) if (c.v[i].logit < floor_logit && i >= min_keep) break;
+    c.v.resize(i);
+}
+
+// llama_sample_tail_free_impl (:235-292)
+void tail_free(Cands & c, float z, size_t min_keep) {
+    if (z >= 1.0f || c.v.size() <= 2) return;
+    softmax(c);
+    const size_t n = c.v.size();
+    std::vector<float> d1(n - 1), d2(n - 2);
+    for (size_t i = 0; i + 1 < n; i++) d1[i] = c.v[i].p - c.v[i + 1].p;
+    for (size_t i = 0; i + 2 < n; i++) d2[i] = std::abs(d1[i] - d1[i + 1]);
+    float total = 0.0f;
+    for (float x : d2) total += x;
+    if (total > 1e-6f) { for (float & x : d2) x /= total; }
+    else               { for (float & x : d2) x = 1.0f / d2.size(); }
+    float cum = 0.0f;
+    size_t last = n;
+    for (size_t i = 0; i < d2.size(); i++) {
+        cum += d2[i];
+        if (cum > z && i >= min_keep) { last = i; break; }
+    }
+    c.v.resize(last);
+}
+
+// llama_sample_typical_impl (:294-356): candidates ordered by |surprise - entropy|; leaves the array unsorted
+void typical(Cands & c, float p, size_t min_keep) {
+    if (p >= 1.0f) return;
+    softmax(c);
+    const size_t n = c.v.size();
+    float entropy = 0.0f;
+    for (const Cand & x : c.v) entropy += -x.p * logf(x.p);
+    std::vector<float> dist(n);
+    for (size_t i = 0; i < n; i++) dist[i] = fabsf(-logf(c.v[i].p) - entropy);
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return dist[a] < dist[b]; });
+    float cum = 0.0f;
+    size_t last = n;
+    for (size_t i = 0; i < n; i++) {
+        cum += c.v[order[i]].p;
+        if (cum > p && i >= min_keep - 1) { last = i + 1; break; }      // (min_keep - 1 in size_t, as in the reference)
+    }
+    std::vector<Cand> keep;
+    keep.reserve(last);
+    for (size_t i = 0; i < last; i++) keep.push_back(c.v[order[i]]);
+    c.v.swap(keep);
+    c.sorted = false;
+}
+
+// llama_sample_token_with_rng_impl (:610-631)
+int32_t draw(Cands & c, std::mt19937 & rng) {
+    softmax(c);
     std::vector<float> probs;
-    for (auto & c : cand) probs.push_back(c.p);
+    probs.reserve(c.v.size());
+    for (const Cand & x : c.v) probs.push_back(x.p);
     std::discrete_distribution<> dist(probs.begin(), probs.end());
-    return cand[(size_t) dist(rng)].id;
+    return c.v[(size_t) dist(rng)].id;
+}
+
+float surprise_of(const Cands & c, int32_t id) {
+    size_t i = 0;
+    while (i < c.v.size() && c.v[i].id != id) i++;
+    return -log2f(c.v[i].p);
+}
+
+}  // namespace
+
+int32_t StandardSampler::sample(const float * logits, int32_t n_vocab) {
+    // llama_sampling_prepare_impl (cpp/common/sampling.cpp:342-409): every token a candidate, penalties over the tail of prev
+    Cands c;
+    c.v.resize((size_t) n_vocab);
+    for (int32_t id = 0; id < n_vocab; id++) c.v[(size_t) id] = {id, logits[id], 0.0f};
+    const int window = p.penalty_last_n < 0 ? p.n_prev : p.penalty_last_n;
+    const int used = std::min((int) prev.size(), window);
+    if (used) {
+        const bool have_nl = p.nl_token >= 0 && p.nl_token < n_vocab;
+        const float nl_logit = have_nl ? logits[p.nl_token] : 0.0f;
+        // llama_sample_repetition_penalties_impl (cpp/src/llama-sampling.cpp:437-482) with frequency / presence penalties 0
+        if (p.penalty_repeat != 1.0f) {
+            std::vector<uint8_t> seen((size_t) n_vocab, 0);
+            for (size_t i = prev.size() - (size_t) used; i < prev.size(); i++) if (prev[i] >= 0 && prev[i] < n_vocab) seen[(size_t) prev[i]] = 1;
+            for (Cand & x : c.v) {
+                if (!seen[(size_t) x.id]) continue;
+                if (x.logit <= 0) x.logit *= p.penalty_repeat; else x.logit /= p.penalty_repeat;
+                x.logit -= 0.0f;      // count * penalty_freq + present * penalty_present, both 0 here
+            }
+        }
+        if (!p.penalize_nl && have_nl) c.v[(size_t) p.nl_token].logit = nl_logit;
+    }
+    // llama_sampling_sample_impl (cpp/common/sampling.cpp:271-340)
+    if (p.temp < 0.0f) { softmax(c); return c.v[0].id; }
+    if (p.temp == 0.0f) {
+        // llama_sample_token_greedy_impl: std::max_element, the FIRST of equal maxima
+        return std::max_element(c.v.begin(), c.v.end(), [](const Cand & a, const Cand & b) { return a.logit < b.logit; })->id;
+    }
+    if (p.mirostat == 1) {
+        // llama_sample_token_mirostat_impl (:507-550), m = 100
+        for (Cand & x : c.v) x.logit /= p.temp;
+        softmax(c);
+        const int m = 100;
+        float sum_tb = 0.0f, sum_tt = 0.0f;
+        for (size_t i = 0; i < (size_t) (m - 1) && i < c.v.size() - 1; i++) {
+            const float t_i = logf((float) (i + 2) / (float) (i + 1));
+            const float b_i = logf(c.v[i].p / c.v[i + 1].p);
+            sum_tb = fmaf(t_i, b_i, sum_tb);
+            sum_tt = fmaf(t_i, t_i, sum_tt);
+        }
+        const float s_hat = sum_tb / sum_tt;
+        const float eps_hat = s_hat - 1;
+        const float k = powf((eps_hat * powf(2, mirostat_mu)) / (1 - powf((float) n_vocab_model, -eps_hat)), 1 / s_hat);
+        top_k(c, (int) k, 1);
+        const int32_t id = draw(c, ctx_rng);
+        const float e = surprise_of(c, id) - p.mirostat_tau;
+        mirostat_mu = fmaf(-p.mirostat_eta, e, mirostat_mu);
+        return id;
+    }
+    if (p.mirostat == 2) {
+        // llama_sample_token_mirostat_v2_impl (:552-592)
+        for (Cand & x : c.v) x.logit /= p.temp;
+        softmax(c);
+        size_t keep = 0;
+        while (keep < c.v.size() && !(-log2f(c.v[keep].p) > mirostat_mu)) keep++;
+        c.v.resize(std::max<size_t>(1, keep));
+        softmax(c);
+        const int32_t id = draw(c, ctx_rng);
+        const float e = surprise_of(c, id) - p.mirostat_tau;
+        mirostat_mu = fmaf(-p.mirostat_eta, e, mirostat_mu);
+        return id;
+    }
+    // sampler_queue (cpp/common/sampling.cpp:231-269), default order k f y p m t
+    const size_t min_keep = (size_t) std::max(1, p.min_keep);
+    top_k(c, p.top_k, min_keep);
+    tail_free(c, p.tfs_z, min_keep);
+    typical(c, p.typical_p, min_keep);
+    top_p(c, p.top_p, min_keep);
+    min_p(c, p.min_p, min_keep);
+    for (Cand & x : c.v) x.logit /= p.temp;
+    return draw(c, rng);
 }
 
 }  // namespace b200
@@ -304,8 +488,9 @@ struct b200_sampler {
     std::unique_ptr<b200::Tokenizer> tok;
     b200::JanusSampler janus;
     b200::StandardSampler standard;
+    b200::StandardParams sp;
     bool use_janus = true;
-    std::vector<int32_t> last_tokens, history;
+    std::vector<int32_t> last_tokens;
     size_t n_prompt = 0;
 };
 
@@ -318,23 +503,34 @@ extern "C" b200_sampler * b200_sampler_new(const char * gguf_path, int n_ctx, in
         s->tok = b200::make_tokenizer(gguf_path, err);
         if (!s->tok) return nullptr;
         b200::JanusParams jp; jp.janus = janus; jp.depth = depth; jp.scale = scale; jp.hi = hi; jp.lo = lo;
-        b200::StandardParams sp; sp.temp = temperature; sp.top_k = top_k; sp.top_p = top_p; sp.penalty_repeat = repetition_penalty; sp.penalty_last_n = penalty_last_n;
+        s->sp.temp = temperature; s->sp.top_k = top_k; s->sp.top_p = top_p; s->sp.penalty_repeat = repetition_penalty; s->sp.penalty_last_n = penalty_last_n;
+        s->sp.nl_token = s->tok->linefeed();
         s->use_janus = janus != 0;
         if (s->use_janus) s->janus.init(*s->tok, jp, 0);
-        s->standard.init(sp, 0);
+        s->standard.init(s->sp, 0);
+        s->standard.n_vocab_model = s->tok->n_vocab();
         s->last_tokens.assign((size_t) n_ctx, 0);
         return s.release();
     } catch (const std::exception &) { return nullptr; }
 }
-extern "C" void b200_sampler_free(b200_sampler * s) { delete s; }
-// a new job: the prompt's ids (the standard chain's penalty window; Janus only needs their count) and the rng seed
-extern "C" void b200_sampler_reset(b200_sampler * s, const int32_t * prompt, int32_t n_prompt, uint32_t seed) {
+// the parameters of the standard chain that b200_sampler_new's (initContext-shaped) signature does not carry; takes effect at
+// the next b200_sampler_reset. typical_p <= 0 means 1 (off), as in initContext (cpp/bridge.cpp:773).
+extern "C" void b200_sampler_set_standard(b200_sampler * s, int32_t mirostat, float mirostat_tau, float mirostat_eta, float typical_p,
+                                          float tfs_z, float min_p) {
     if (!s) return;
+    s->sp.mirostat = mirostat; s->sp.mirostat_tau = mirostat_tau; s->sp.mirostat_eta = mirostat_eta;
+    s->sp.typical_p = typical_p > 0 ? typical_p : 1.0f; s->sp.tfs_z = tfs_z; s->sp.min_p = min_p;
+}
+extern "C" void b200_sampler_free(b200_sampler * s) { delete s; }
+// a new job: the prompt's ids (accepted into the standard chain's penalty window like cpp/bridge.cpp:618; Janus only needs their
+// count) and the rng seed
+extern "C" void b200_sampler_reset(b200_sampler * s, const int32_t * prompt, int32_t n_prompt, uint32_t seed) {
+    if (!s || (n_prompt > 0 && !prompt)) return;
     std::fill(s->last_tokens.begin(), s->last_tokens.end(), 0);
-    s->history.assign(prompt, prompt + n_prompt);
-    s->n_prompt = (size_t) n_prompt;
+    s->n_prompt = (size_t) (n_prompt > 0 ? n_prompt : 0);
     s->janus.rng.seed(seed);
-    s->standard.rng.seed(seed);
+    s->standard.init(s->sp, seed);
+    for (int32_t i = 0; i < n_prompt; i++) s->standard.accept(prompt[i]);
 }
 // one token from logits[n_vocab] (modified in place by Janus, as the reference modifies the context's logits) at position
 // pos = tokens decoded so far; n_predict as passed to initContext
@@ -346,8 +542,8 @@ extern "C" int32_t b200_sampler_sample(b200_sampler * s, float * logits, int32_t
         s->last_tokens.erase(s->last_tokens.begin());
         s->last_tokens.push_back(id);
     } else {
-        id = s->standard.sample(logits, s->tok->n_vocab(), s->history);
+        id = s->standard.sample(logits, s->tok->n_vocab());
     }
-    s->history.push_back(id);
+    s->standard.accept(id);      // cpp/bridge.cpp:605: accepted whichever sampler drew it
     return id;
 }

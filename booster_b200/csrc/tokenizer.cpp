@@ -152,13 +152,14 @@ struct TextTokenizer final : Tokenizer {
     std::unordered_map<std::pair<std::string, std::string>, int, PairHash> rank;   // first listing wins (:5327 emplace)
     std::vector<int32_t> specials;                     // control | user-defined | unknown ids, longest text first (:5680-5694)
     std::vector<std::string> piece_cache;              // llama_token_to_piece(id, special = true) of every id (:5698-5709)
-    int32_t bos_id = -1, eos_id = -1, unk_id = -1, eot_id = -1, eom_id = -1;
+    int32_t bos_id = -1, eos_id = -1, unk_id = -1, eot_id = -1, eom_id = -1, lf_id = -1;
     bool add_bos = false, add_eos = false, add_space_prefix = false, ignore_merges = false;
 
     int32_t n_vocab() const override { return (int32_t) text.size(); }
     int32_t bos() const override { return bos_id; }
     int32_t eos() const override { return eos_id; }
     int32_t eot() const override { return eot_id; }
+    int32_t linefeed() const override { return lf_id; }
     bool is_eog(int32_t id) const override { return id != -1 && (id == eos_id || id == eot_id || id == eom_id); }   // llama-vocab.cpp:1433-1439
 
     bool is_special_kind(int32_t id) const { return kind[(size_t) id] == TT_UNKNOWN || kind[(size_t) id] == TT_CONTROL; }
@@ -506,6 +507,17 @@ std::unique_ptr<Tokenizer> load_text_tokenizer(const gguf_file & g, const std::s
               [&](const int32_t a, const int32_t b) { return t->text[(size_t) a].size() > t->text[(size_t) b].size(); });
     t->piece_cache.resize(n);
     for (size_t i = 0; i < n; i++) t->piece_cache[i] = t->render((int32_t) i);
+    // the newline token (cpp/src/llama.cpp:5585-5597): SPM = the byte token of '\n' (else the padding id, -1 by default);
+    // BPE = the first token of the TEXT U+010A pushed through the byte-level tokenizer (for a LLaMA-3 vocabulary that is the
+    // token of byte 0xC4, 'Ä', not a newline — the reference's load log says so itself; reproduced, the sampler depends on it)
+    if (!t->bpe) {
+        auto it = t->id_of.find("<0x0A>");
+        if (it == t->id_of.end()) it = t->id_of.find("\n");
+        if (it != t->id_of.end()) t->lf_id = it->second;
+    } else {
+        std::vector<int32_t> ids;
+        if (t->tokenize("\xC4\x8A", false, false, ids) && !ids.empty()) t->lf_id = ids[0];
+    }
     return t;
 }
 

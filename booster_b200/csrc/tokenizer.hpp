@@ -31,6 +31,7 @@ struct Tokenizer {
     virtual int32_t bos() const { return -1; }
     virtual int32_t eos() const { return -1; }
     virtual int32_t eot() const { return -1; }   // llama_token_eot (cpp/src/llama-vocab.cpp:1489-1491)
+    virtual int32_t linefeed() const { return -1; }   // llama_token_nl (cpp/src/llama-vocab.cpp:1461-1463; found at cpp/src/llama.cpp:5585-5597)
 };
 
 // bit 0 \p{L}, bit 1 \p{N}, bit 2 \s of a codepoint (unicode_tables.hpp)

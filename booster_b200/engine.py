@@ -308,11 +308,14 @@ class Sampler:
     """doInference's sampler on its own (include/booster_b200.h b200_sampler_*): Janus (janus != 0) or the standard chain"""
 
     def __init__(self, path: str, n_ctx: int, janus: int = 1, depth: int = 200, scale: float = 0.96, hi: float = 0.99, lo: float = 0.96,
-                 temperature: float = 0.8, top_k: int = 40, top_p: float = 0.95, repetition_penalty: float = 1.0, penalty_last_n: int = 64):
+                 temperature: float = 0.8, top_k: int = 40, top_p: float = 0.95, repetition_penalty: float = 1.0, penalty_last_n: int = 64,
+                 mirostat: int = 0, mirostat_tau: float = 5.0, mirostat_eta: float = 0.1, typical_p: float = 1.0, tfs_z: float = 1.0,
+                 min_p: float = 0.05):
         self.L = _lib.lib()
         self.h = self.L.b200_sampler_new(path.encode(), n_ctx, janus, depth, scale, hi, lo, temperature, top_k, top_p, repetition_penalty, penalty_last_n)
         if not self.h:
             raise B200Error(f"b200_sampler_new({path}) failed")
+        self.L.b200_sampler_set_standard(self.h, mirostat, mirostat_tau, mirostat_eta, typical_p, tfs_z, min_p)
 
     def close(self):
         if self.h:
@@ -362,3 +365,8 @@ class Tokenizer:
 
     def is_eog(self, token: int) -> bool:
         return bool(self.L.b200_token_is_eog(self.h, token))
+
+    @property
+    def token_nl(self) -> int:
+        """llama_token_nl: the newline token (-1 if the vocabulary has none)"""
+        return int(self.L.b200_token_nl(self.h))

@@ -208,6 +208,8 @@ int b200_op_launch_shape(const int32_t * types, int n_types, int64_t n_units, in
  * b200_token_to_piece  == llama_token_to_piece(model, token, buf, length, 0, special) (cpp/src/llama-vocab.cpp:1539-1608):
  *                         bytes written (no terminator), or minus the size needed.
  * b200_token_is_eog    == llama_token_is_eog (cpp/src/llama-vocab.cpp:1433-1439).
+ * b200_token_nl        == llama_token_nl (cpp/src/llama-vocab.cpp:1461-1463; the id is found at load, cpp/src/llama.cpp:5585-5597):
+ *                         the newline token whose logit the standard sampling chain restores after its penalties; -1 if none.
  * The bridge (doInference / status) uses exactly these with add_special = 0, parse_special = 1, special = 1
  * (cpp/bridge.cpp:275-278, 630, 640). */
 typedef struct b200_tokenizer b200_tokenizer;
@@ -218,16 +220,23 @@ int32_t b200_tokenize(const b200_tokenizer * t, const char * text, int32_t text_
                       int add_special, int parse_special);
 int32_t b200_token_to_piece(const b200_tokenizer * t, int32_t token, char * buf, int32_t length, int special);
 int     b200_token_is_eog(const b200_tokenizer * t, int32_t token);
+int32_t b200_token_nl(const b200_tokenizer * t);
 /* ---- samplers (host side) ----------------------------------------------------------------------------
  * What doInference does with the logits of every token, exposed on its own so that it can be pinned against the reference's
  * sampler on the reference's logits (no GPU involved): janus != 0 -> sample_janus_token (cpp/janus.cpp:191-331) with the
  * tables of initJanus (:405-700) built from the GGUF's vocabulary; janus == 0 -> llama_sampling_sample's default chain
- * (repetition penalty, top-k, top-p, min-p 0.05, temperature; cpp/common/sampling.cpp), which the reference's bridge keeps
- * commented out. b200_sampler_reset starts a job (prompt ids, rng seed = llama_set_rng_seed); b200_sampler_sample draws the next
- * token from logits[n_vocab] (Janus modifies them in place) at position pos = number of tokens decoded so far. */
+ * (llama_sampling_sample, cpp/common/sampling.cpp:271-340 over cpp/src/llama-sampling.cpp: repetition penalty over the last
+ * accepted tokens, then top-k, tail-free, typical, top-p, min-p 0.05, temperature and a draw — or mirostat 1 / 2), which the
+ * reference links but its bridge never calls (cpp/bridge.cpp:598). b200_sampler_set_standard carries the chain's parameters that
+ * are not in b200_sampler_new's initContext-shaped signature (mirostat, mirostat_tau, mirostat_eta, typical_p of initContext;
+ * tfs_z and min_p, which initContext cannot set). b200_sampler_reset starts a job (prompt ids, rng seed = llama_set_rng_seed);
+ * b200_sampler_sample draws the next token from logits[n_vocab] (Janus modifies them in place) at position pos = number of
+ * tokens decoded so far. */
 typedef struct b200_sampler b200_sampler;
 b200_sampler * b200_sampler_new(const char * gguf_path, int n_ctx, int32_t janus, int32_t depth, float scale, float hi, float lo,
                                 float temperature, int top_k, float top_p, float repetition_penalty, int penalty_last_n);
+void    b200_sampler_set_standard(b200_sampler * s, int32_t mirostat, float mirostat_tau, float mirostat_eta, float typical_p,
+                                  float tfs_z, float min_p);
 void    b200_sampler_free(b200_sampler * s);
 void    b200_sampler_reset(b200_sampler * s, const int32_t * prompt, int32_t n_prompt, uint32_t seed);
 int32_t b200_sampler_sample(b200_sampler * s, float * logits, int32_t pos, int32_t n_predict);

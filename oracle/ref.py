@@ -113,6 +113,9 @@ def lib() -> C.CDLL:
         L.refshim_token_to_piece.restype = C.c_int
         L.refshim_token_is_eog.argtypes = [C.c_void_p, C.c_int32]
         L.refshim_token_is_eog.restype = C.c_int
+        if hasattr(L, "refshim_vocab_token_nl"):
+            L.refshim_vocab_token_nl.argtypes = [C.c_void_p]
+            L.refshim_vocab_token_nl.restype = C.c_int
         L.refshim_cpt_flags.argtypes = [C.c_uint32]
         L.refshim_cpt_flags.restype = C.c_uint16
     if hasattr(L, "refshim_janus_generate"):
@@ -121,6 +124,13 @@ def lib() -> C.CDLL:
         L.refshim_janus_generate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                              C.c_uint32, C.c_int, C.POINTER(C.c_int32)]
         L.refshim_janus_generate.restype = C.c_int
+    if hasattr(L, "refshim_standard_generate"):
+        L.refshim_standard_generate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                                C.c_uint32, C.POINTER(C.c_int32)]
+        L.refshim_standard_generate.restype = C.c_int
+        L.refshim_token_nl.argtypes = [C.c_void_p]
+        L.refshim_token_nl.restype = C.c_int
     L.refshim_init(1)
     return L
 
@@ -161,6 +171,10 @@ class RefVocab:
 
     def is_eog(self, token: int) -> bool:
         return bool(self.L.refshim_token_is_eog(self.h, token))
+
+    def token_nl(self) -> int:
+        """llama_token_nl(model)"""
+        return int(self.L.refshim_vocab_token_nl(self.h))
 
 
 def cpt_flags(cp: int) -> int:
@@ -255,6 +269,23 @@ class RefModel:
         if n < 0:
             raise RuntimeError("llama_decode failed")
         return out[:n].tolist()
+
+    def standard_generate(self, prompt: Sequence[int], n_gen: int, seed: int, *, mirostat: int = 0, mirostat_tau: float = 5.0,
+                          mirostat_eta: float = 0.1, temp: float = 0.8, top_k: int = 40, top_p: float = 0.95, typical_p: float = 1.0,
+                          tfs_z: float = 1.0, min_p: float = 0.05, penalty_repeat: float = 1.0, penalty_last_n: int = 64) -> List[int]:
+        """the bridge's generation loop with the standard chain the reference keeps commented out (cpp/bridge.cpp:598):
+        llama_sampling_init / llama_sampling_sample / llama_sampling_accept of common/sampling.cpp"""
+        toks = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.empty(n_gen, dtype=np.int32)
+        n = self.L.refshim_standard_generate(self.h, toks.ctypes.data_as(C.POINTER(C.c_int32)), len(toks), n_gen, mirostat, mirostat_tau,
+                                             mirostat_eta, temp, top_k, top_p, typical_p, tfs_z, min_p, penalty_repeat, penalty_last_n,
+                                             seed, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        if n < 0:
+            raise RuntimeError("llama_sampling_init / llama_decode failed")
+        return out[:n].tolist()
+
+    def token_nl(self) -> int:
+        return int(self.L.refshim_token_nl(self.h))
 
     def reset_timings(self):
         self.L.refshim_reset_timings(self.h)

@@ -17,6 +17,7 @@
 //                                  cpp/bridge.cpp:630 (llama_token_to_piece), :640 (llama_token_is_eog)
 //   sampler:                       cpp/bridge.cpp:196 (initJanus), :437-438, :586-603 (sample_janus_token + last_tokens)
 //   context shift:                 cpp/bridge.cpp:500-503 (llama_kv_cache_seq_rm / llama_kv_cache_seq_add)
+//   standard sampling chain:       cpp/bridge.cpp:456, 598, 605, 618 (llama_sampling_init / _sample / _accept), :763-776
 
 #include "llama.h"
 #include "ggml.h"
@@ -213,6 +214,45 @@ int refshim_janus_generate(void * hv, const int32_t * prompt, int n_prompt, int 
     return n;
 }
 
+// ---- standard-chain oracle: the generation loop of cpp/bridge.cpp with the branch the reference keeps commented out
+// (cpp/bridge.cpp:586-599 "FIXME: Allow standard samplings": id = llama_sampling_sample(ctx_sampling, ctx, ctx_guidance)) taken
+// instead of sample_janus_token. Everything is the reference's own code (common/sampling.cpp, src/llama-sampling.cpp):
+// llama_sampling_init on the parameters initContext stores (cpp/bridge.cpp:763-776), llama_set_rng_seed (cpp/bridge.cpp:216-217; the
+// mirostat draws use the context's rng), prompt tokens accepted without grammar (:618), every sampled token accepted (:605).
+// The sampling context's own rng is seeded with the caller's seed too (the reference leaves it to std::random_device).
+int refshim_standard_generate(void * hv, const int32_t * prompt, int n_prompt, int n_gen,
+                              int mirostat, float mirostat_tau, float mirostat_eta,
+                              float temp, int top_k, float top_p, float typical_p, float tfs_z, float min_p,
+                              float penalty_repeat, int penalty_last_n, uint32_t seed, int32_t * out_ids) {
+    auto * h = static_cast<ref_handle *>(hv);
+    llama_sampling_params sp;
+    sp.mirostat = mirostat; sp.mirostat_tau = mirostat_tau; sp.mirostat_eta = mirostat_eta;
+    sp.temp = temp; sp.top_k = top_k; sp.top_p = top_p;
+    sp.typical_p = typical_p > 0 ? typical_p : 1.0f;          // cpp/bridge.cpp:773
+    sp.tfs_z = tfs_z; sp.min_p = min_p;
+    sp.penalty_repeat = penalty_repeat; sp.penalty_last_n = penalty_last_n;
+    sp.seed = seed;
+    llama_sampling_context * cs = llama_sampling_init(sp);
+    if (!cs) return -1;
+    llama_set_rng_seed(h->ctx, seed);
+    llama_kv_cache_clear(h->ctx);
+    std::vector<llama_token> toks(prompt, prompt + n_prompt);
+    if (llama_decode(h->ctx, llama_batch_get_one(toks.data(), n_prompt, 0, 0))) { llama_sampling_free(cs); return -1; }
+    for (int i = 0; i < n_prompt; i++) llama_sampling_accept(cs, h->ctx, toks[(size_t) i], false);
+    int n_past = n_prompt, n = 0;
+    for (int i = 0; i < n_gen; i++) {
+        llama_token id = llama_sampling_sample(cs, h->ctx, nullptr);
+        llama_sampling_accept(cs, h->ctx, id, true);
+        out_ids[n++] = id;
+        if (llama_token_is_eog(h->model, id)) break;
+        if (llama_decode(h->ctx, llama_batch_get_one(&id, 1, n_past, 0))) { llama_sampling_free(cs); return -1; }
+        n_past += 1;
+    }
+    llama_sampling_free(cs);
+    return n;
+}
+int refshim_token_nl(void * hv) { return llama_token_nl(static_cast<ref_handle *>(hv)->model); }
+
 // ---- tokenizer oracle: the reference's own llama_tokenize / llama_token_to_piece / llama_token_is_eog on a
 // vocab-only load of a GGUF (llama_model_params.vocab_only, cpp/include/llama.h)
 void * refshim_vocab_load(const char * path) {
@@ -228,6 +268,7 @@ int refshim_tokenize(void * m, const char * text, int text_len, int32_t * out, i
 int refshim_token_to_piece(void * m, int32_t token, char * buf, int cap, int special) {
     return llama_token_to_piece(static_cast<llama_model *>(m), token, buf, cap, 0, special != 0);
 }
+int refshim_vocab_token_nl(void * m) { return llama_token_nl(static_cast<llama_model *>(m)); }
 int refshim_token_is_eog(void * m, int32_t token) { return llama_token_is_eog(static_cast<llama_model *>(m), token) ? 1 : 0; }
 
 }  // extern "C"

@@ -140,6 +140,50 @@ def make_janus():
     print(f"janus.json: {len(out)} cases")
 
 
+# initContext-reachable settings of the standard chain (janus = 0): (mirostat, tau, eta, temperature, top_k, top_p, typical_p,
+# repetition_penalty, penalty_last_n)
+STANDARD_CASES = [
+    (0, 0.0, 0.0, 0.8, 40, 0.95, 1.0, 1.0, 64),
+    (0, 0.0, 0.0, 1.1, 200, 0.9, 1.0, 1.2, 32),
+    (0, 0.0, 0.0, 1.0, 0, 1.0, 0.6, 1.0, 0),
+    (0, 0.0, 0.0, 0.0, 40, 0.95, 1.0, 1.4, 64),
+    (1, 3.0, 0.2, 1.0, 40, 0.95, 1.0, 1.0, 64),
+    (2, 4.0, 0.3, 0.8, 40, 0.95, 1.0, 1.1, 64),
+]
+
+
+def make_standard():
+    """tests/golden/standard_chain.json: token ids the reference's bridge loop WOULD generate with the standard chain it keeps
+    commented out (cpp/bridge.cpp:598; refshim_standard_generate runs the reference's own llama_sampling_init /
+    llama_sampling_sample / llama_sampling_accept) on tiny models with small synthetic vocabularies, for fixed seeds."""
+    import dataclasses
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import tokenizer_fixtures as F
+    from booster_b200 import engine
+    out = []
+    for kind in ("spm", "bpe"):
+        extra = F.vocab_kv(kind, pad_to=32)
+        cfg = dataclasses.replace(G.CONFIGS["tiny"], n_vocab=extra["llama.vocab_size"][1])
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, f"tiny_{kind}.gguf")
+            G.synth_llama(path, cfg, "Q4_K_M", seed=5, extra_kv=extra)
+            tok = engine.Tokenizer(path)
+            r = ref.RefModel(path, n_ctx=64, n_threads=2)
+            for text in ("Hello world, it's 42 tokens\nand more", "русский язык и ещё"):
+                prompt = tok.tokenize(text.encode(), False, True)
+                for (mi, tau, eta, temp, top_k, top_p, typ, rep, last_n) in STANDARD_CASES:
+                    for seed in (7, 4242):
+                        ids = r.standard_generate(prompt, 20, seed, mirostat=mi, mirostat_tau=tau, mirostat_eta=eta, temp=temp, top_k=top_k,
+                                                  top_p=top_p, typical_p=typ, penalty_repeat=rep, penalty_last_n=last_n)
+                        out.append({"kind": kind, "text": text, "prompt": prompt, "mirostat": mi, "mirostat_tau": tau, "mirostat_eta": eta,
+                                    "temperature": temp, "top_k": top_k, "top_p": top_p, "typical_p": typ, "repetition_penalty": rep,
+                                    "penalty_last_n": last_n, "seed": seed, "n_predict": 20, "ids": ids})
+            r.close(); tok.close()
+    json.dump(out, open(os.path.join(HERE, "standard_chain.json"), "w"), indent=0)
+    print(f"standard_chain.json: {len(out)} cases")
+
+
 if __name__ == "__main__":
     if not ref.available():
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` in the build container")
@@ -148,11 +192,15 @@ if __name__ == "__main__":
     if only == ["janus"]:
         make_janus()
         sys.exit(0)
+    if only == ["standard"]:
+        make_standard()
+        sys.exit(0)
     if only == ["kvshift"]:
         make_kvshift()
         sys.exit(0)
     if not only:
         make_ops()
         make_janus()
+        make_standard()
         make_kvshift()
     make_models(only)

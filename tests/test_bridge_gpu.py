@@ -177,6 +177,36 @@ def test_do_inference_janus_sampler_equals_reference_golden(kind, tmp_path, gold
     tok.close()
 
 
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_do_inference_standard_chain_equals_reference_golden(kind, tmp_path, golden_dir):
+    """janus = 0 through the nine symbols: doInference samples with the standard chain (repetition penalty, top-k, typical, top-p,
+    min-p, temperature, mirostat 1 / 2) and publishes the token ids the reference's own llama_sampling_sample generates in the
+    bridge's loop for the same seed (tests/golden/standard_chain.json, made by oracle/_ref: common/sampling.cpp +
+    src/llama-sampling.cpp unmodified) — logits bit-identical, candidate order, float arithmetic and mt19937 draws identical."""
+    import json
+
+    import test_sampler
+    from booster_b200 import engine
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "standard_chain.json"))) if c["kind"] == kind]
+    assert len(cases) >= 24
+    path = test_sampler._model(tmp_path, kind, big=False)
+    tok = engine.Tokenizer(path)
+    L = _lib.lib()
+    L.init(b"", b"")
+    idx = 5
+    for i, c in enumerate(cases):
+        assert tok.tokenize(c["text"].encode(), False, True) == c["prompt"]
+        ctx = L.initContext(idx, path.encode(), 1, 0, 100, 0, 0, 0, 64, c["n_predict"], c["mirostat"], c["mirostat_tau"], c["mirostat_eta"],
+                            c["temperature"], c["top_k"], c["top_p"], c["typical_p"], c["repetition_penalty"], c["penalty_last_n"],
+                            0, 200, 1.0, 1.0, 1.0, c["seed"], b"")
+        assert ctx
+        job = f"standard-{kind}-{i}".encode()
+        L.doInference(idx, ctx, job, b"", c["text"].encode())
+        want = b"".join(tok.piece(t, True) for t in c["prompt"] + c["ids"])
+        assert L.status(job) == want, {k: v for k, v in c.items() if k not in ("prompt", "ids", "text")}
+    tok.close()
+
+
 def test_pod_split_over_two_gpus_equals_one_gpu(model_dir):
     """the reference's gpu1 / gpu2 proportions (pkg/server/server.go:514-530 -> tensor_split): a pod whose layers sit on two
     devices — prompt chunk through b200_stage_forward_batch (peer copy of the residual streams), generation through the

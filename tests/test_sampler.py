@@ -67,6 +67,66 @@ def test_janus_equals_reference_token_for_token(kind, tmp_path, ref_or_none):
     r.close()
 
 
+# the standard chain (janus = 0): settings of llama_sampling_params that initContext can reach, plus tfs_z / min_p
+STANDARD = [
+    dict(),                                                                  # the defaults: k f y p m t (temp 0.8, top-k 40, top-p 0.95, min-p 0.05)
+    dict(temp=1.3, top_k=0, top_p=1.0, min_p=0.0),                           # pure temperature over the whole vocabulary
+    dict(temp=1.0, top_k=200, top_p=0.9, min_p=0.02),                        # top-k > 128: the bucket pre-sort
+    dict(temp=0.9, penalty_repeat=1.3, penalty_last_n=16),                   # penalties over a short window (+ newline restore)
+    dict(temp=0.9, penalty_repeat=1.15, penalty_last_n=-1, top_k=60),        # the whole window
+    dict(temp=1.0, typical_p=0.6, top_k=0, min_p=0.0),                       # locally typical (leaves the candidates unsorted)
+    dict(temp=1.0, tfs_z=0.9, top_k=100, min_p=0.0),                         # tail-free
+    dict(temp=0.0, penalty_repeat=1.5),                                      # greedy over the penalised logits
+    dict(temp=-1.0, penalty_repeat=1.2),                                     # "greedy with probabilities"
+    dict(temp=1.0, mirostat=1, mirostat_tau=3.0, mirostat_eta=0.2),          # mirostat (mu starts at 0: llama_sampling_init never sets it)
+    dict(temp=0.8, mirostat=2, mirostat_tau=4.0, mirostat_eta=0.3, penalty_repeat=1.1),
+]
+
+
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_standard_chain_equals_reference_token_for_token(kind, tmp_path, ref_or_none):
+    """janus = 0: llama_sampling_sample as the reference links it (common/sampling.cpp over src/llama-sampling.cpp) generates with
+    a fixed seed; the reference's logits, step by step, through b200_sampler_* must give the same ids — the same candidate order
+    (std::sort / partial_sort / the top-k bucket sort), float arithmetic and mt19937 draws"""
+    ref = ref_or_none
+    if ref is None or not hasattr(ref.lib(), "refshim_standard_generate"):
+        pytest.skip("oracle/_ref with the standard-chain shim is not available")
+    if ref.variant() != "native":
+        pytest.skip("the restated chain follows the fused multiply-adds of the reference's -march=native build")
+    path = _model(tmp_path, kind, big=False)
+    tok = engine.Tokenizer(path)
+    prompts = [tok.tokenize(s.encode(), False, True) for s in ("Hello world, it's 42 tokens\nand a second line", "русский язык и ещё")]
+    n_vocab = tok.n_vocab
+    tok.close()
+    assert n_vocab > 200                                                     # so that top_k = 200 takes the bucket path
+    r = ref.RefModel(path, n_ctx=96, n_threads=2)
+    n_varied = 0
+    for si, kw in enumerate(STANDARD):
+        ours_kw = dict(kw)
+        s = engine.Sampler(path, 96, janus=0, temperature=ours_kw.pop("temp", 0.8), top_k=ours_kw.pop("top_k", 40), top_p=ours_kw.pop("top_p", 0.95),
+                           repetition_penalty=ours_kw.pop("penalty_repeat", 1.0), penalty_last_n=ours_kw.pop("penalty_last_n", 64), **ours_kw)
+        for pi, prompt in enumerate(prompts):
+            for seed in (3, 777):
+                ids_ref = r.standard_generate(prompt, 40, seed, **kw)
+                r.kv_clear()
+                lg = r.decode(prompt, 0)
+                s.reset(prompt, seed)
+                pos = len(prompt)
+                ours = []
+                for want in ids_ref:
+                    got = s.sample(lg, pos)
+                    ours.append(got)
+                    if got != want:
+                        break
+                    lg = r.decode([got], pos)
+                    pos += 1
+                assert ours == ids_ref, (kind, si, kw, pi, seed)
+                n_varied += len(set(ids_ref)) > 3
+        s.close()
+    assert n_varied >= len(STANDARD)                                         # real draws, not one token repeated
+    r.close()
+
+
 def test_standard_chain_properties(tmp_path):
     """janus = 0 (a setting the reference ignores): temperature <= 0 and top_k = 1 are arg-max; a fixed seed is deterministic;
     the repetition penalty moves a repeated arg-max; top-k bounds the support"""

@@ -50,6 +50,11 @@ def test_golden_pieces_and_eog(kind):
         assert t.piece(i, False) == base64.b64decode(nosp), i
         assert t.is_eog(i) == bool(eog), i
     assert sum(e for _, _, e in g["pieces"]) >= 1
+    # llama_token_nl of the committed vocabularies, as the reference reports it. SPM: the <0x0A> byte token. BPE: the FIRST token
+    # of the text U+010A run through the byte-level tokenizer — the token of byte 0xC4 ("LF token = 128 'Ä'" in the reference's
+    # load log of a LLaMA-3 model), not a newline; the sampler restores that token's logit, so the quirk is reproduced.
+    assert t.token_nl == {"spm": 13, "bpe": 196}[kind]
+    assert t.piece(t.token_nl, True) == {"spm": b"\n", "bpe": b"\xc4"}[kind]
     t.close()
 
 
@@ -96,6 +101,8 @@ def test_live_against_reference_random_strings(kind, tmp_path):
                 assert t.tokenize(b, add_special, parse_special) == rv.tokenize(b, add_special, parse_special), (s, add_special, parse_special)
     for i in range(t.n_vocab):
         assert t.piece(i, True) == rv.piece(i, True) and t.piece(i, False) == rv.piece(i, False) and t.is_eog(i) == rv.is_eog(i)
+    if hasattr(ref.lib(), "refshim_vocab_token_nl"):
+        assert t.token_nl == rv.token_nl()                    # llama_token_nl: the standard sampling chain restores its logit
     rv.close(); t.close()
 
 
