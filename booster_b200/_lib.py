@@ -22,7 +22,7 @@ B200_SYMBOLS = ["b200_last_error", "b200_device_count", "b200_version", "b200_mo
                 "b200_kv_clear", "b200_decode", "b200_generate_greedy", "b200_step_greedy", "b200_set_taps", "b200_get_tap",
                 "b200_timings", "b200_reset_timings", "b200_kernel_launches", "b200_last_device_ms", "b200_profile_token", "b200_profile_kind", "b200_trace_token", "b200_trace_phases", "b200_set_token_kernel", "b200_set_prefill_batch", "b200_set_prefill_mma", "b200_set_prefill_attn_batch", "b200_job_timing_us", "b200_comm_unique_id",
                 "b200_comm_init", "b200_p2p_handle", "b200_p2p_connect", "b200_p2p_disable", "b200_pipeline_generate_greedy", "b200_pipeline_decode", "b200_stage_forward", "b200_stage_batch_usable", "b200_stage_forward_batch",
-                "b200_stage_logits", "b200_stage_argmax", "b200_stage_logits_view", "b200_decode_view", "b200_stage_sync", "b200_kv_write", "b200_kv_read", "b200_kv_seq_rm", "b200_kv_seq_add", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
+                "b200_stage_logits", "b200_stage_argmax", "b200_stage_logits_view", "b200_decode_view", "b200_stage_sync", "b200_kv_write", "b200_kv_read", "b200_kv_seq_rm", "b200_kv_seq_add", "b200_kv_seq_div", "b200_op_quantize_q8_K", "b200_op_quantize_q8_0",
                 "b200_op_dequantize_row", "b200_op_mul_mat_vec", "b200_op_mul_mat", "b200_op_rms_norm", "b200_op_rope",
                 "b200_op_attention", "b200_set_attention_route", "b200_tokenizer_load", "b200_tokenizer_free", "b200_tokenizer_n_vocab", "b200_tokenize",
                 "b200_token_to_piece", "b200_token_is_eog", "b200_token_nl", "b200_cpt_class", "b200_op_launch_shape",
@@ -122,6 +122,7 @@ def lib() -> C.CDLL:
     sig("b200_set_attention_route", None, [C.c_int])
     sig("b200_kv_seq_rm", C.c_int, [vp, C.c_int, C.c_int])
     sig("b200_kv_seq_add", C.c_int, [vp, C.c_int, C.c_int, C.c_int])
+    sig("b200_kv_seq_div", C.c_int, [vp, C.c_int, C.c_int, C.c_int])
     sig("b200_sampler_new", vp, [cp, C.c_int, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int])
     sig("b200_sampler_set_standard", None, [vp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float])
     sig("b200_sampler_free", None, [vp])

@@ -39,6 +39,7 @@ constexpr int MAX_PODS = 8;   // cpp/bridge.cpp:102-110: all per-pod arrays are 
 struct Pod {
     std::string model_path;
     int n_ctx = 0, n_batch = 512, n_predict = -1;
+    int ga_n = 1, ga_w = 512;           // Self-Extend: gpt_params.grp_attn_n / grp_attn_w (cpp/common/common.h defaults; cpp/bridge.cpp:430-431)
     uint32_t seed = 0;
     std::vector<b200_model *> models;   // one per stage (in-process layer split)
     std::vector<b200_ctx *>   stages;
@@ -182,6 +183,10 @@ static void * init_context_impl(
     std::string terr;
     p.tok = b200::make_tokenizer(modelName, terr);
     if (!p.tok) { std::fprintf(stderr, "initContext: %s\n", terr.c_str()); p.release(); return nullptr; }
+    // Self-Extend: the reference reads gpt_params.grp_attn_n / grp_attn_w (cpp/bridge.cpp:430-431), which initContext cannot
+    // set (always 1 / 512 there); here the two come from the environment so that the branch can be switched on
+    if (const char * e = std::getenv("BOOSTER_B200_GRP_ATTN_N")) p.ga_n = std::atoi(e);
+    if (const char * e = std::getenv("BOOSTER_B200_GRP_ATTN_W")) p.ga_w = std::atoi(e);
     // sampler parameters (cpp/bridge.cpp:746-761)
     p.jparams.janus = janus; p.jparams.depth = depth; p.jparams.scale = scale; p.jparams.hi = hi; p.jparams.lo = lo;
     p.sparams.temp = temperature; p.sparams.top_k = top_k; p.sparams.top_p = top_p;
@@ -238,6 +243,8 @@ static int64_t do_inference_impl(int idx, void * ctx, char * jobID, char * sessi
         std::fprintf(stderr, "doInference: prompt is too long (%d tokens, max %d) or empty\n", (int) inp.size(), max_embd);
         return 0;
     }
+    if (p.ga_n != 1 && p.ga_n <= 0) return 0;               // cpp/bridge.cpp:433: grp_attn_n must be positive
+    if (p.ga_n != 1 && (p.ga_w % p.ga_n != 0)) return 0;    // cpp/bridge.cpp:434: grp_attn_w must be a multiple of grp_attn_n
     for (b200_ctx * c : p.stages) b200_kv_clear(c);        // cpp/bridge.cpp:459
 
     int n_past = 0;
@@ -245,12 +252,31 @@ static int64_t do_inference_impl(int idx, void * ctx, char * jobID, char * sessi
     double t_p_us = 0, t_e_us = 0;
     int n_remain = p.n_predict;                            // -1 = until EOG / context
     b200_ctx * last = p.stages.back();
+    // context extension via Self-Extend (cpp/bridge.cpp:509-524), before every llama_decode when grp_attn_n != 1: whole windows of
+    // ga_w positions are compressed by ga_n and n_past falls back; the K rows are re-rotated lazily inside the next decode
+    int ga_i = 0;
+    const auto self_extend = [&]() -> bool {
+        while (p.ga_n != 1 && n_past >= ga_i + p.ga_w) {
+            const int ib = (p.ga_n * ga_i) / p.ga_w;
+            const int bd = (p.ga_w / p.ga_n) * (p.ga_n - 1);
+            const int dd = (p.ga_w / p.ga_n) - ib * bd - p.ga_w;
+            for (b200_ctx * c : p.stages) {
+                if (b200_kv_seq_add(c, ga_i, n_past, ib * bd) != 0 ||
+                    b200_kv_seq_div(c, ga_i + ib * bd, ga_i + ib * bd + p.ga_w, p.ga_n) != 0 ||
+                    b200_kv_seq_add(c, ga_i + ib * bd + p.ga_w, n_past + ib * bd, dd) != 0) return false;
+            }
+            n_past -= bd;
+            ga_i += p.ga_w / p.ga_n;
+        }
+        return true;
+    };
 
     // ---- prompt, in chunks of n_batch (cpp/bridge.cpp:549-560, 613-624); pieces are published per chunk
     static const bool pipeline_chunks = [] { const char * e = std::getenv("BOOSTER_B200_PIPELINE_CHUNKS"); return !(e && e[0] == '0'); }();   // A/B switch
     size_t consumed = 0;
     while (consumed < inp.size() && !g_stop[idx].load()) {
         const size_t n = std::min((size_t) p.n_batch, inp.size() - consumed);
+        if (!self_extend()) return 1;
         const double t0 = now_us();
         if (p.stages.size() == 1) {
             // one llama_decode of the chunk (cpp/bridge.cpp:549-560): the batched prompt kernels on a pod that sits on one GPU
@@ -336,7 +362,9 @@ static int64_t do_inference_impl(int idx, void * ctx, char * jobID, char * sessi
         // first n_keep tokens, drop half of the rest, move the tail down. As in the reference the loop condition above
         // (n_past < n_ctx - 4) ends the job before n_past + 1 can exceed n_ctx, so the branch only documents the behaviour —
         // the operation itself is b200_kv_seq_rm / b200_kv_seq_add, tested against the reference on their own.
-        if (n_past + 1 > p.n_ctx) {
+        if (p.ga_n != 1) {
+            if (!self_extend()) return 1;
+        } else if (n_past + 1 > p.n_ctx) {
             const int n_keep = 0, n_left = n_past - n_keep, n_discard = n_left / 2;
             for (b200_ctx * c : p.stages) {
                 if (b200_kv_seq_rm(c, n_keep, n_keep + n_discard) != 0 || b200_kv_seq_add(c, n_keep + n_discard, n_past, -n_discard) != 0) return 1;

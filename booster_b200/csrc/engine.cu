@@ -1484,6 +1484,34 @@ extern "C" int b200_kv_seq_add(b200_ctx * c, int p0, int p1, int delta) {
     } catch (const std::exception & e) { return set_err(e.what()); }
 }
 
+// llama_kv_cache_seq_div(ctx, 0, p0, p1, d) (cpp/bridge.cpp:518, Self-Extend; cpp/src/llama.cpp:3316-3349): the positions of the
+// cells in [p0, p1) are divided by d (integer division); the K rows are re-rotated by the accumulated delta at the next decode
+// like after a seq_add. Several cells may then hold the same position; attention only compares positions.
+extern "C" int b200_kv_seq_div(b200_ctx * c, int p0, int p1, int d) {
+    try {
+        require_gpu();
+        if (!c) throw std::runtime_error("null context");
+        if (d <= 0) throw std::runtime_error("b200_kv_seq_div: the divisor must be positive");
+        CU(cudaSetDevice(c->m->device));
+        kv_enter_managed(c);
+        auto & k = c->cells;
+        if (p0 < 0) p0 = 0;
+        if (p1 < 0) p1 = INT32_MAX;
+        if (p0 == p1) return 0;
+        for (int i = 0; i < c->n_ctx; i++) {
+            if (k.pos[(size_t) i] >= p0 && k.pos[(size_t) i] < p1) {
+                k.has_shift = true;
+                const int32_t p_old = k.pos[(size_t) i];
+                k.pos[(size_t) i] /= d;
+                k.delta[(size_t) i] += k.pos[(size_t) i] - p_old;
+            }
+        }
+        CU(cudaMemcpyAsync(c->d_cell_pos, k.pos.data(), (size_t) c->n_ctx * 4, cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        return 0;
+    } catch (const std::exception & e) { return set_err(e.what()); }
+}
+
 // Rows [pos0, pos0 + n) of one local layer's K (post-RoPE) and V cache, f16 bits [n][n_head_kv * head_dim] — the view
 // llama_kv_cache exposes through k_l / v_l (cpp/src/llama.cpp:2495-2539; V returned position-major). Tests use the pair
 // to start both sides of a parity check from the same cache at n_kv in the thousands, and to check the K-shift.

@@ -83,6 +83,10 @@ class Context:
         """llama_kv_cache_seq_add(ctx, 0, p0, p1, delta); the K-shift runs inside the next decode"""
         check(self.L.b200_kv_seq_add(self.h, p0, p1, delta), "b200_kv_seq_add")
 
+    def kv_seq_div(self, p0: int, p1: int, d: int):
+        """llama_kv_cache_seq_div(ctx, 0, p0, p1, d) (cpp/bridge.cpp:518): Self-Extend's grouping of positions"""
+        check(self.L.b200_kv_seq_div(self.h, p0, p1, d), "b200_kv_seq_div")
+
     def decode(self, tokens: Sequence[int], pos0: int, want_logits: bool = True) -> Optional[np.ndarray]:
         """llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0)) then llama_get_logits (last token's row)."""
         toks = np.ascontiguousarray(tokens, dtype=np.int32)

@@ -75,6 +75,9 @@ int b200_kv_read(b200_ctx * c, int layer, int pos0, int n, uint16_t * k_rows, ui
  * b200_step_greedy / b200_stage_forward (the device-resident greedy loop and b200_kv_write need an unshifted cache). */
 int b200_kv_seq_rm(b200_ctx * c, int p0, int p1);
 int b200_kv_seq_add(b200_ctx * c, int p0, int p1, int delta);
+/* Self-Extend (cpp/bridge.cpp:509-524): llama_kv_cache_seq_div(ctx, 0, p0, p1, d) (cpp/src/llama.cpp:3316-3349) — the positions
+ * of the cells in [p0, p1) are divided by d; K rows re-rotated lazily like after b200_kv_seq_add. */
+int b200_kv_seq_div(b200_ctx * c, int p0, int p1, int d);
 
 /* ---- the hot path ------------------------------------------------------------------------------------------
  * b200_decode == llama_decode(ctx, llama_batch_get_one(tokens, n, pos0, 0))  (cpp/bridge.cpp:549-560,

@@ -121,6 +121,8 @@ def lib() -> C.CDLL:
     if hasattr(L, "refshim_janus_generate"):
         L.refshim_kv_seq_rm.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.refshim_kv_seq_add.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        if hasattr(L, "refshim_kv_seq_div"):
+            L.refshim_kv_seq_div.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.refshim_janus_generate.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                              C.c_uint32, C.c_int, C.POINTER(C.c_int32)]
         L.refshim_janus_generate.restype = C.c_int
@@ -258,6 +260,10 @@ class RefModel:
     def kv_seq_add(self, p0: int, p1: int, delta: int):
         """llama_kv_cache_seq_add(ctx, 0, p0, p1, delta) (cpp/bridge.cpp:501); the K-shift runs inside the next decode"""
         self.L.refshim_kv_seq_add(self.h, p0, p1, delta)
+
+    def kv_seq_div(self, p0: int, p1: int, d: int):
+        """llama_kv_cache_seq_div(ctx, 0, p0, p1, d) (cpp/bridge.cpp:518, Self-Extend)"""
+        self.L.refshim_kv_seq_div(self.h, p0, p1, d)
 
     def janus_generate(self, prompt: Sequence[int], n_gen: int, depth: int, scale: float, hi: float, lo: float, seed: int,
                        n_predict: int = -1) -> List[int]:

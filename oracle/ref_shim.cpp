@@ -182,6 +182,7 @@ void refshim_timings(void * hv, double * t_p_eval_ms, int * n_p_eval, double * t
 // ---- context shift: the two calls of cpp/bridge.cpp:500-503; the K-shift itself runs inside the next llama_decode
 // (llama_kv_cache_update -> build_k_shift, cpp/src/llama.cpp:8482-8510)
 void refshim_kv_seq_rm(void * hv, int p0, int p1)             { llama_kv_cache_seq_rm(static_cast<ref_handle *>(hv)->ctx, 0, p0, p1); }
+void refshim_kv_seq_div(void * hv, int p0, int p1, int d)     { llama_kv_cache_seq_div(static_cast<ref_handle *>(hv)->ctx, 0, p0, p1, d); }   // cpp/bridge.cpp:518
 void refshim_kv_seq_add(void * hv, int p0, int p1, int delta) { llama_kv_cache_seq_add(static_cast<ref_handle *>(hv)->ctx, 0, p0, p1, delta); }
 
 // ---- sampler oracle: the generation loop of cpp/bridge.cpp with the reference's own initJanus / sample_janus_token

@@ -107,6 +107,10 @@ def make_kvshift():
         lg = kvshift_script.run(r, prompt)
         np.savez_compressed(os.path.join(HERE, f"kvshift_{model}.npz"), prompt=np.array(prompt, dtype=np.int32), logits=lg)
         print(f"kvshift_{model}.npz: {lg.shape[0]} steps")
+        # Self-Extend (cpp/bridge.cpp:509-524): 30 prompt tokens in chunks of 8 + 28 generated, windows of 16 compressed by 2
+        se = kvshift_script.run_self_extend(r, prompt)
+        np.savez_compressed(os.path.join(HERE, f"selfextend_{model}.npz"), prompt=np.array(prompt, dtype=np.int32), logits=se)
+        print(f"selfextend_{model}.npz: {se.shape[0]} steps")
         r.close()
 
 

@@ -42,3 +42,40 @@ def run(r, prompt, n_ctx=64, n_keep=4):
     shift()                                        # second shift: cells moved once, and cells written in between
     greedy(10)
     return np.stack(logits)
+
+
+def run_self_extend(r, prompt, ga_n=2, ga_w=16, n_batch=8, n_gen=28):
+    """Self-Extend (cpp/bridge.cpp:509-524, grp_attn_n = ga_n, grp_attn_w = ga_w): before EVERY llama_decode — prompt chunks of
+    n_batch tokens and generated tokens alike — whole windows of ga_w positions are compressed by ga_n
+    (llama_kv_cache_seq_add / seq_div / seq_add) and n_past falls back accordingly. Cells never move or free; several cells end
+    up with the same position; every window is re-rotated by a different per-cell delta at the next decode."""
+    logits = []
+    r.kv_clear()
+    n_past, ga_i = 0, 0
+
+    def extend():
+        nonlocal n_past, ga_i
+        while n_past >= ga_i + ga_w:
+            ib = (ga_n * ga_i) // ga_w
+            bd = (ga_w // ga_n) * (ga_n - 1)
+            dd = (ga_w // ga_n) - ib * bd - ga_w
+            r.kv_seq_add(ga_i, n_past, ib * bd)
+            r.kv_seq_div(ga_i + ib * bd, ga_i + ib * bd + ga_w, ga_n)
+            r.kv_seq_add(ga_i + ib * bd + ga_w, n_past + ib * bd, dd)
+            n_past -= bd
+            ga_i += ga_w // ga_n
+
+    lg = None
+    for i in range(0, len(prompt), n_batch):
+        chunk = prompt[i:i + n_batch]
+        extend()
+        lg = r.decode(chunk, n_past)
+        logits.append(lg)
+        n_past += len(chunk)
+    for _ in range(n_gen):
+        t = int(np.argmax(lg))
+        extend()
+        lg = r.decode([t], n_past)
+        logits.append(lg)
+        n_past += 1
+    return np.stack(logits)

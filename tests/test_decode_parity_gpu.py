@@ -173,6 +173,25 @@ def test_context_shift_bitwise_golden(golden_dir, model):
     c.close(); m.close()
 
 
+@pytest.mark.parametrize("model", ["tiny-gqa4_Q4_K_M", "tiny-gqa4-yarn_Q4_K_M"])
+def test_self_extend_bitwise_golden(golden_dir, model):
+    """SURVEY §8 f-3, Self-Extend (cpp/bridge.cpp:509-524, grp_attn_n = 2, grp_attn_w = 16): llama_kv_cache_seq_add / seq_div /
+    seq_add before every decode — prompt chunks and generated tokens — compress whole windows of positions; cells keep their
+    places, several cells share a position, every window is re-rotated by its own delta. Every logit of
+    tests/kvshift_script.py::run_self_extend equals the reference's, bit for bit."""
+    import kvshift_script
+    g = np.load(os.path.join(golden_dir, f"selfextend_{model}.npz"))
+    m = engine.Model(os.path.join(golden_dir, model + ".gguf"))
+    c = engine.Context(m, 64)
+    lg = kvshift_script.run_self_extend(c, g["prompt"].tolist())
+    assert lg.shape == g["logits"].shape
+    for i in range(lg.shape[0]):
+        _same(lg[i], g["logits"][i], f"step {i}")
+    with pytest.raises(engine.B200Error):
+        c.kv_seq_div(0, 8, 0)                      # a zero divisor is an error, not a crash
+    c.close(); m.close()
+
+
 @pytest.mark.parametrize("cfg,ftype,n_prompt", [("llama3-8b-2l", "Q4_K_M", 200), ("llama3-8b-2l", "Q8_0", 130), ("llama3-8b-2l", "Q5_K_M", 70),
                                                 ("llama3-70b-1l", "Q4_K_M", 65), ("tiny-gqa4", "Q4_K_M", 450)])
 def test_prompt_batch_kernels_equal_token_by_token_bitwise(model_dir, cfg, ftype, n_prompt):
