@@ -2247,7 +2247,11 @@ extern "C" void b200_p2p_disable(b200_ctx * c) { if (c) c->p2p = false; }
 static void enqueue_stage_step(b200_ctx * c, bool greedy) {
     b200_model & m = *c->m;
     const bool first = c->rank == 0, last = c->rank == c->world - 1;
-    if (c->p2p) {
+    // The inbox of the peer hand-off is ONE slot: it is safe only while at most one token is in flight, which the greedy loop
+    // guarantees (stage 0 cannot start token i + 1 before the last stage has handed token i's arg-max back). Prompt tokens
+    // (greedy == false) have no hand-back — stage 0 would overwrite the slot while a slower stage still has to read it — so they
+    // go through ncclSend / ncclRecv, whose FIFO is the flow control.
+    if (c->p2p && greedy) {
         if (!first) { k_p2p_recv_x<<<1, 256, 0, c->st>>>(c->x, m.n_embd, c->inbox, c->p2p_counts); c->launches++; }
         enqueue_forward(c);
         if (!last) { k_p2p_send_x<<<1, 256, 0, c->st>>>(c->x, m.n_embd, c->next_inbox, c->p2p_counts); c->launches++; }
