@@ -86,3 +86,22 @@ def test_sass_shows_the_hardware_paths():
     assert "sm_100a" in sass
     for mnemonic in ("UBLKCP", "SYNCS", "HMMA.16816.F32", "LDSM", "UTCHMMA", "UTCBAR", "LDTM", "IDP.4A"):
         assert mnemonic in sass, mnemonic
+
+
+def test_plain_c_client_compiles_links_and_runs(tmp_path):
+    """the cgo caller's view (pkg/server/server.go:7-36) without a Go toolchain: tests/c_harness/bridge_client.c includes both
+    headers from a C translation unit (-std=c11 -Wall -Werror -pedantic: the boundary is plain C), links against the shared
+    library like `#cgo LDFLAGS: -lbooster_b200` and drives the nine symbols; without a model every call answers with the
+    reference's failure values instead of crashing"""
+    import shutil
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler on PATH")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "bridge_client")
+    subprocess.run([cc, "-std=c11", "-D_DEFAULT_SOURCE", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_harness", "bridge_client.c"), "-o", exe,
+                    "-L", libdir, "-lbooster_b200", "-lpthread", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok: bad configuration handled" in r.stdout and "version: booster_b200" in r.stdout
