@@ -2509,6 +2509,17 @@ struct DBuf {
     ~DBuf() { cudaFree(p); }
     template <typename T> T * as() { return (T *) p; }
 };
+// a stream / a tiled matrix that an operator call owns: released on every exit, the error paths included
+struct OpStream {
+    cudaStream_t st = nullptr;
+    OpStream() { CU(cudaStreamCreate(&st)); }
+    ~OpStream() { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } }
+};
+struct OwnedMat {
+    DevMat d;
+    explicit OwnedMat(DevMat m) : d(m) {}
+    ~OwnedMat() { cudaFree(d.alloc); }
+};
 }  // namespace
 
 static int op_quantize(const float * x, int64_t k, void * out, int q80) {
@@ -2546,8 +2557,8 @@ extern "C" int b200_op_dequantize_row(int type, const void * w, int64_t k, float
 extern "C" int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int64_t k, const float * x, float * y) {
     try {
         require_gpu();
-        cudaStream_t st;
-        CU(cudaStreamCreate(&st));
+        OpStream os;
+        cudaStream_t st = os.st;
         // the operator accepts any row count: pad with all-zero blocks (d = 0 -> 0.0) up to the work-unit height
         const int64_t rows_pad = (n_rows + 31) / 32 * 32;
         std::vector<uint8_t> padded;
@@ -2557,7 +2568,8 @@ extern "C" int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int
             memcpy(padded.data(), w, (size_t) n_rows * rb);
             w = padded.data();
         }
-        DevMat d = upload_matrix(type, w, rows_pad, k, st);
+        OwnedMat om(upload_matrix(type, w, rows_pad, k, st));
+        const DevMat & d = om.d;
         DBuf dx((size_t) k * 4), dy((size_t) rows_pad * 4);
         CU(cudaMemcpyAsync(dx.p, x, (size_t) k * 4, cudaMemcpyHostToDevice, st));
         b200_ctx tmp;   // only st / sm_count / launches are used by launch_matvec
@@ -2573,8 +2585,6 @@ extern "C" int b200_op_mul_mat_vec(int type, const void * w, int64_t n_rows, int
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(y, dy.p, (size_t) n_rows * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        cudaFree(d.alloc);
-        CU(cudaStreamDestroy(st));
         return 0;
     } catch (const std::exception & e) { return set_err(e.what()); }
 }
@@ -2585,8 +2595,8 @@ extern "C" int b200_op_mul_mat(int type, const void * w, int64_t n_rows, int64_t
     try {
         require_gpu();
         if (T <= 0 || T > PB_MAX_T) throw std::runtime_error("b200_op_mul_mat: 1..512 tokens");
-        cudaStream_t st;
-        CU(cudaStreamCreate(&st));
+        OpStream os;
+        cudaStream_t st = os.st;
         const int64_t rows_pad = (n_rows + 63) / 64 * 64;
         std::vector<uint8_t> padded;
         if (rows_pad != n_rows) {
@@ -2595,7 +2605,8 @@ extern "C" int b200_op_mul_mat(int type, const void * w, int64_t n_rows, int64_t
             memcpy(padded.data(), w, (size_t) n_rows * rb);
             w = padded.data();
         }
-        DevMat d = upload_matrix(type, w, rows_pad, k, st);
+        OwnedMat om(upload_matrix(type, w, rows_pad, k, st));
+        const DevMat & d = om.d;
         const size_t rec_bytes = std::max((size_t) ((T + PB_CHUNK - 1) / PB_CHUNK) * (k / 256) * PB_CHUNK * pb_record_bytes(0, 1),
                                           std::max((size_t) ((T + MB_NT - 1) / MB_NT) * (k / 256) * MB_REC_BYTES, (size_t) ((T + UM_NT - 1) / UM_NT) * (k / 256) * UM_REC_BYTES));
         DBuf dx((size_t) T * k * 4), dy((size_t) T * rows_pad * 4), drec(rec_bytes);
@@ -2617,8 +2628,6 @@ extern "C" int b200_op_mul_mat(int type, const void * w, int64_t n_rows, int64_t
         CU(cudaStreamSynchronize(st));
         for (int64_t t = 0; t < T; t++) memcpy(y + t * n_rows, hy.data() + t * rows_pad, (size_t) n_rows * 4);
         tmp.pb.rec = nullptr;
-        cudaFree(d.alloc);
-        CU(cudaStreamDestroy(st));
         return 0;
     } catch (const std::exception & e) { return set_err(e.what()); }
 }
@@ -2661,9 +2670,10 @@ extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, cons
     try {
         require_gpu();
         if (n_kv <= 0) throw std::runtime_error("n_kv must be positive");
+        if (!q || !k_cache || !v_cache || !out || n_head <= 0 || n_head_kv <= 0 || n_head % n_head_kv) throw std::runtime_error("bad arguments");
         const int kvd = n_head_kv * head_dim, qd = n_head * head_dim;
-        cudaStream_t st;
-        CU(cudaStreamCreate(&st));
+        OpStream os;
+        cudaStream_t st = os.st;
         int dev = 0; CU(cudaGetDevice(&dev));
         cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
         b200_ctx tmp;
@@ -2684,7 +2694,6 @@ extern "C" int b200_op_attention(const float * q, const uint16_t * k_cache, cons
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out, dout.p, (size_t) qd * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        CU(cudaStreamDestroy(st));
         return 0;
     } catch (const std::exception & e) { return set_err(e.what()); }
 }
