@@ -411,7 +411,7 @@ def main():
             t = int(np.argmax(lg))
             lg = c.decode([t], pos0 + (i % min(burst, 64)))
         e2e_dt = time.perf_counter() - t0
-        decode_e2e = {"value": n_e2e / e2e_dt, "unit": "tokens/s", "h2d_bytes_per_token": 16, "d2h_bytes_per_token": 4 * cfg.n_vocab,
+        decode_e2e = {"value": n_e2e / e2e_dt, "unit": "tokens/s", "h2d_bytes_per_token": 32, "d2h_bytes_per_token": 4 * cfg.n_vocab,
                       "what": "b200_decode(token from host) -> logits to host -> host arg-max, per token"}
         # ---- end to end through the nine bridge symbols (second copy of the model in HBM: the pod's own)
         try:
@@ -420,13 +420,15 @@ def main():
             if prefill:
                 n_gen = 256
             be = bridge_e2e(path, ctx, n_prompt, n_gen, reps=2 if args.config == DEFAULT_CONFIG else 1)
-            line["e2e"] = {"value": be["value"], "unit": "tokens/s", "h2d_bytes_per_step": 16 * be["generated"],
-                           "d2h_bytes_per_step": 4 * be["generated"],
+            # per generated token the bridge copies the 32-byte decode state to the device and — the Janus sampler runs on the host,
+            # like the reference's — the whole logits row (4 * n_vocab bytes) back; the prompt goes in once as token ids
+            line["e2e"] = {"value": be["value"], "unit": "tokens/s", "h2d_bytes_per_step": 32 * be["generated"] + 4 * n_prompt,
+                           "d2h_bytes_per_step": 4 * cfg.n_vocab * be["generated"],
                            "what": f"init -> initContext -> doInference(host text prompt of {n_prompt} token ids, predict {n_gen}) -> status poller: "
                                    f"generated tokens / time from the first generated piece to doInference's return (n_kv {n_prompt}..{n_prompt + n_gen})",
                            "doInference": be, "b200_decode": decode_e2e}
         except Exception as e:
-            line["e2e"] = dict(decode_e2e, h2d_bytes_per_step=16 * burst, d2h_bytes_per_step=4 * cfg.n_vocab * burst,
+            line["e2e"] = dict(decode_e2e, h2d_bytes_per_step=32 * burst, d2h_bytes_per_step=4 * cfg.n_vocab * burst,
                                bridge_error=str(e))
         # ---- live per-kernel roofline (event pair around every launch of an un-graphed token at n_kv ~ ctx)
         acc = {}
