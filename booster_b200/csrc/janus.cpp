@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -78,24 +79,49 @@ bool is_pedantic(const std::string & token) {
     return false;
 }
 
-// max of x[0..n) (n >= 1), 16 lanes the compiler turns into vector maxima
-float vec_max(const float * x, int32_t n) {
-    float m[16];
-    int32_t i = 0;
-    if (n >= 16) {
-        for (int j = 0; j < 16; j++) m[j] = x[j];
-        for (i = 16; i + 16 <= n; i += 16)
-            for (int j = 0; j < 16; j++) m[j] = x[i + j] > m[j] ? x[i + j] : m[j];
-    } else {
-        for (int j = 0; j < 16; j++) m[j] = x[0];
+// The two scans below touch all 128 k logits of a token; the library is built for baseline x86-64, so they are compiled a second
+// time for AVX2 and picked at load time (GNU function multi-versioning). Same comparisons, same results: only wider vectors.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define B200_WIDE __attribute__((target_clones("avx2", "default")))
+#else
+#define B200_WIDE
+#endif
+// The maximum of x[0..n) (n >= 1) — order-independent, so exact — in 8-float vectors (GNU vector extensions: one vmaxps per 8
+// logits in the AVX2 clone, two maxps in the baseline one; a scalar running maximum is a 4-cycle dependency per element and
+// costs more than the GPU spends on the token), and on the way the maximum of every block of 64 logits (bm[(n + 63) / 64]): the
+// scan for the short list then only opens the blocks that can hold a candidate instead of reading all 128 k logits a second time
+typedef float vf8 __attribute__((vector_size(32)));
+constexpr int32_t BM_BLOCK = 64;
+B200_WIDE float block_maxima(const float * x, int32_t n, float * bm) {
+    const int32_t nb = n / BM_BLOCK;
+    const float ninf = -std::numeric_limits<float>::infinity();   // every lane starts below everything: a NaN logit never wins and
+    const vf8 vinf = { ninf, ninf, ninf, ninf, ninf, ninf, ninf, ninf };   // never sticks (x > m is false for it), as in a scalar scan
+    float r = ninf;
+    for (int32_t b = 0; b < nb; b++) {
+        const float * q = x + (size_t) b * BM_BLOCK;
+        vf8 m0 = vinf, m1 = vinf, a;
+        for (int j = 0; j < BM_BLOCK; j += 16) {
+            std::memcpy(&a, q + j, 32);     m0 = a > m0 ? a : m0;
+            std::memcpy(&a, q + j + 8, 32); m1 = a > m1 ? a : m1;
+        }
+        m0 = m1 > m0 ? m1 : m0;
+        float t[8];
+        std::memcpy(t, &m0, 32);
+        float v = t[0];
+        for (int j = 1; j < 8; j++) v = t[j] > v ? t[j] : v;
+        bm[b] = v;
+        r = v > r ? v : r;
     }
-    float r = m[0];
-    for (int j = 1; j < 16; j++) r = m[j] > r ? m[j] : r;
-    for (; i < n; i++) r = x[i] > r ? x[i] : r;
+    if (nb * BM_BLOCK < n) {
+        float v = ninf;
+        for (int32_t i = nb * BM_BLOCK; i < n; i++) v = x[i] > v ? x[i] : v;
+        bm[nb] = v;
+        r = v > r ? v : r;
+    }
     return r;
 }
 // first index >= from with x[index] >= thr, or n (blocks of 64 tested branch-free, then the hit located)
-int32_t first_at_least(const float * x, int32_t n, float thr, int32_t from) {
+B200_WIDE int32_t first_at_least(const float * x, int32_t n, float thr, int32_t from) {
     int32_t i = from;
     for (; i < n && (i & 63); i++) if (x[i] >= thr) return i;
     for (; i + 64 <= n; i += 64) {
@@ -211,30 +237,55 @@ int32_t JanusSampler::sample(float * logits, const std::vector<int32_t> & last_t
     // The reference sorts all candidates by logit (descending) and cuts the list at the first one whose ratio to the top
     // logit is below the cutoff (cpp/janus.cpp:289-324). For a positive top logit the ratio falls along the sorted order,
     // so the short list is exactly the candidates whose ratio is not below the cutoff — found in one pass, no full sort.
-    // the maximum of 128 k logits in 16 independent lanes (a single running maximum is a 4-cycle dependency per element and
-    // costs more than the GPU spends on the token); the maximum is order-independent, so this is exact
-    float top_logit = vec_max(logits, n_vocab);
-    int32_t top = first_at_least(logits, n_vocab, top_logit, 0);
-    float cutoff = p.lo;
-    const float top_type = types[(size_t) top];
-    if (pedantic[(size_t) top] || top_type == LANG_RU || top_type == LANG_EN) cutoff = p.hi;
+    block_max.resize((size_t) (n_vocab + BM_BLOCK - 1) / BM_BLOCK);
+    float top_logit = block_maxima(logits, n_vocab, block_max.data());
     struct Cand { int32_t id; float logit; float p; };
     std::vector<Cand> cand;
     const auto by_logit = [](const Cand & a, const Cand & b) { return a.logit > b.logit; };
-    if (top_logit > 0.f && cutoff > 0.f) {
-        // the exact test is the reference's division; a multiplication with a safety margin first keeps 128 k divisions per
-        // token out of the loop (x / top < cutoff certainly holds when x < top * cutoff * (1 - 2^-10))
-        const float guard = top_logit * cutoff * 0.999f;
-        for (int32_t id = first_at_least(logits, n_vocab, guard, 0); id < n_vocab; id = first_at_least(logits, n_vocab, guard, id + 1))
-            if (!(logits[id] / top_logit < cutoff)) cand.push_back({id, logits[id], 0.f});
+    int32_t top;
+    float cutoff;
+    const auto cutoff_for = [&](int32_t t) {                // cpp/janus.cpp:306-312: the pedantic / single-language top token takes `hi`
+        const float top_type = types[(size_t) t];
+        return (pedantic[(size_t) t] || top_type == LANG_RU || top_type == LANG_EN) ? p.hi : p.lo;
+    };
+    if (top_logit > 0.f && p.lo > 0.f && p.hi > 0.f) {
+        // ONE more scan finds both the top token (the first logit equal to the maximum) and the short list. The cutoff depends on
+        // the top token, so the scan uses the smaller of the two possible cutoffs and the exact test follows: the reference's
+        // division x / top < cutoff; the multiplication with a safety margin only keeps 128 k divisions per token out of the
+        // loop (x / top < cutoff certainly holds when x < top * cutoff * (1 - 2^-10)).
+        const float guard = top_logit * std::min(p.lo, p.hi) * 0.999f;
+        top = -1;
+        for (size_t b = 0; b < block_max.size(); b++) {
+            if (!(block_max[b] >= guard)) continue;
+            const int32_t end = std::min(n_vocab, (int32_t) (b + 1) * BM_BLOCK);
+            for (int32_t id = (int32_t) b * BM_BLOCK; id < end; id++) {
+                if (!(logits[id] >= guard)) continue;
+                if (top < 0 && logits[id] == top_logit) top = id;
+                cand.push_back({id, logits[id], 0.f});
+            }
+        }
+        cutoff = cutoff_for(top);
+        size_t kept = 0;
+        for (const Cand & c : cand) if (!(c.logit / top_logit < cutoff)) cand[kept++] = c;
+        cand.resize(kept);
         std::sort(cand.begin(), cand.end(), by_logit);
     } else {
-        // top logit <= 0 (or NaN somewhere): the ratio does not fall along the order; walk the fully sorted list as the
-        // reference does (the whole vocabulary survives when every logit is negative)
-        cand.reserve((size_t) n_vocab);
-        for (int32_t id = 0; id < n_vocab; id++) cand.push_back({id, logits[id], 0.f});
-        std::sort(cand.begin(), cand.end(), by_logit);
-        for (size_t i = 1; i < cand.size(); i++) if (cand[i].logit / cand[0].logit < cutoff) { cand.resize(i); break; }
+        // (init() clamps lo and hi into (0, 1], so this is the top-logit <= 0 / NaN case) the two-step form: top token first
+        top = first_at_least(logits, n_vocab, top_logit, 0);
+        cutoff = top < n_vocab ? cutoff_for(top) : p.lo;
+        if (top_logit > 0.f && cutoff > 0.f) {
+            const float guard = top_logit * cutoff * 0.999f;
+            for (int32_t id = first_at_least(logits, n_vocab, guard, 0); id < n_vocab; id = first_at_least(logits, n_vocab, guard, id + 1))
+                if (!(logits[id] / top_logit < cutoff)) cand.push_back({id, logits[id], 0.f});
+            std::sort(cand.begin(), cand.end(), by_logit);
+        } else {
+            // the ratio does not fall along the order; walk the fully sorted list as the reference does (the whole vocabulary
+            // survives when every logit is negative)
+            cand.reserve((size_t) n_vocab);
+            for (int32_t id = 0; id < n_vocab; id++) cand.push_back({id, logits[id], 0.f});
+            std::sort(cand.begin(), cand.end(), by_logit);
+            for (size_t i = 1; i < cand.size(); i++) if (cand[i].logit / cand[0].logit < cutoff) { cand.resize(i); break; }
+        }
     }
     // llama_sample_token: softmax over the short list, then one draw (cpp/src/llama-sampling.cpp:32-59, 610-631)
     const float max_l = cand[0].logit;

@@ -40,6 +40,7 @@ struct JanusSampler {
     JanusParams p;
     std::vector<float> scales, types;      // per token id (cpp/janus.cpp ::scales, ::types)
     std::vector<uint8_t> pedantic;         // isPedantic(id), cached (the reference re-derives it from the piece per call)
+    std::vector<float> block_max;          // scratch of sample(): the maximum of every block of 64 logits
     std::mt19937 rng;                      // llama_context's sampling rng (cpp/src/llama.cpp:18610 llama_set_rng_seed)
     int32_t n_vocab = 0;
 
