@@ -391,8 +391,18 @@ typedef struct {
  *                  _mm512_reduce_add_ps, then p *= (float)(1/sum)   (cpp/ggml/src/ggml.c:13682-13778, 2619-2640)
  *   kqv          : tinyBLAS<16> over the (32-padded) kv length: lane c chains fma(v[16s+c][d], p[16s+c], acc)
  * n_kv is padded to 32 by the reference (kv_self.n, cpp/src/llama.cpp:14698); padded slots have p = 0. */
+static void attention_impl(const float * q, const uint16_t * kc, const uint16_t * vc, int n_kv, int n_head, int n_head_kv,
+                           int hd, float scale, int round_q, const int32_t * cell_pos, int pos, float * out);
 void port_attention(const float * q, const uint16_t * kc, const uint16_t * vc, int n_kv, int n_head, int n_head_kv,
                     int hd, float scale, int round_q, float * out) {
+    attention_impl(q, kc, vc, n_kv, n_head, n_head_kv, hd, scale, round_q, NULL, 0, out);
+}
+/* cell_pos != NULL: the KV cells are managed like struct llama_kv_cache after llama_kv_cache_seq_rm / seq_add / seq_div — cell t
+ * holds position cell_pos[t] (-1: empty) and the query at position pos sees the cells with 0 <= cell_pos[t] <= pos; every other
+ * cell gets -INFINITY from KQ_mask (llama_set_inputs, cpp/src/llama.cpp:14132-14200) and so probability 0, which the P.V chains
+ * still step through (fma(v, 0, acc)), in CELL order. */
+static void attention_impl(const float * q, const uint16_t * kc, const uint16_t * vc, int n_kv, int n_head, int n_head_kv,
+                           int hd, float scale, int round_q, const int32_t * cell_pos, int pos, float * out) {
     const int kvd = n_head_kv * hd, gqa = n_head / n_head_kv;
     const int n_pad = (n_kv + 31) / 32 * 32;
 #pragma omp parallel for schedule(static)
@@ -404,6 +414,7 @@ void port_attention(const float * q, const uint16_t * kc, const uint16_t * vc, i
         float max = -INFINITY;
         for (int t = 0; t < n_pad; t++) {
             if (t >= n_kv) { p[t] = -INFINITY; continue; }
+            if (cell_pos && (cell_pos[t] < 0 || cell_pos[t] > pos)) { p[t] = -INFINITY; continue; }
             const uint16_t * kr = kc + (int64_t) t * kvd + g * hd;
             float s;
             if (!round_q) {
@@ -452,9 +463,39 @@ static void attention(const port_model * M, int il, const float * q, int pos, in
  * (llama_decode_internal cpp/src/llama.cpp:14537-14840; graph build_llama :8781-8925). Tokens are processed one
  * after the other — per-token arithmetic of a batch is independent in the reference except for the f16 rounding
  * of q when n > 1. logits[n_vocab] = last token's row. Returns 0, or 1 if positions exceed n_ctx. */
+static int decode_impl(const port_model * M, const int32_t * tokens, int n, int pos0, const int32_t * cell_of,
+                       const int32_t * cell_pos, int n_kv_cells, float * logits);
 int port_decode(const port_model * M, const int32_t * tokens, int n, int pos0, float * logits) {
+    return decode_impl(M, tokens, n, pos0, NULL, NULL, 0, logits);
+}
+/* the same with managed KV cells (after a context shift / Self-Extend, cpp/bridge.cpp:487-524): token t of the batch is written
+ * to cell cell_of[t] (llama_kv_cache_find_slot, cpp/src/llama.cpp:3028-3125), cell_pos[n_ctx] holds every cell's position AFTER
+ * the batch was placed, n_kv_cells = llama_kv_cache_cell_max (:3397-3407; padded to 32 inside the attention like kv_self.n). */
+int port_decode_cells(const port_model * M, const int32_t * tokens, int n, int pos0, const int32_t * cell_of,
+                      const int32_t * cell_pos, int n_kv_cells, float * logits) {
+    return decode_impl(M, tokens, n, pos0, cell_of, cell_pos, n_kv_cells, logits);
+}
+/* llama_kv_cache_update -> build_k_shift (cpp/src/llama.cpp:15245-15277, 8482-8510): EVERY cell's cached K row (post-RoPE, f16)
+ * is rotated in place by that cell's accumulated position delta — ggml_compute_forward_rope_f16 (cpp/ggml/src/ggml.c:14169-14291):
+ * f16 -> f32, the un-fused rotation, f32 -> f16; delta 0 is cos = attn_factor-scaled 1, sin = 0. */
+void port_k_shift(const port_model * M, const int32_t * delta) {
+    const int hd = M->head_dim, KVD = M->n_head_kv * hd;
+    float * row = malloc(sizeof(float) * KVD);
+    for (int il = 0; il < M->n_layer; il++) {
+        for (int i = 0; i < M->n_ctx; i++) {
+            uint16_t * kc = M->k_cache + ((int64_t) il * M->n_ctx + i) * KVD;
+            for (int j = 0; j < KVD; j++) row[j] = h2f(kc[j]);
+            port_rope_ext(row, M->n_head_kv, hd, delta[i], M->rope_freq_base, M->rope_freq_scale, M->rope_freq_factors,
+                          M->yarn_ext_factor, M->yarn_attn_factor, M->n_ctx_orig);
+            for (int j = 0; j < KVD; j++) kc[j] = f2h(row[j]);
+        }
+    }
+    free(row);
+}
+static int decode_impl(const port_model * M, const int32_t * tokens, int n, int pos0, const int32_t * cell_of,
+                       const int32_t * cell_pos, int n_kv_cells, float * logits) {
     const int E = M->n_embd, hd = M->head_dim, QD = M->n_head * hd, KVD = M->n_head_kv * hd, FF = M->n_ff;
-    if (pos0 < 0 || pos0 + n > M->n_ctx) return 1;
+    if (pos0 < 0 || (!cell_of && pos0 + n > M->n_ctx)) return 1;
     float * x = malloc(sizeof(float) * E), * nx = malloc(sizeof(float) * E), * q = malloc(sizeof(float) * QD);
     float * kk = malloc(sizeof(float) * KVD), * vv = malloc(sizeof(float) * KVD), * att = malloc(sizeof(float) * QD);
     float * tmp = malloc(sizeof(float) * E), * g = malloc(sizeof(float) * FF), * u = malloc(sizeof(float) * FF);
@@ -473,10 +514,15 @@ int port_decode(const port_model * M, const int32_t * tokens, int n, int pos0, f
                           M->yarn_ext_factor, M->yarn_attn_factor, M->n_ctx_orig);
             port_rope_ext(kk, M->n_head_kv, hd, pos, M->rope_freq_base, M->rope_freq_scale, M->rope_freq_factors,
                           M->yarn_ext_factor, M->yarn_attn_factor, M->n_ctx_orig);
-            uint16_t * kc = M->k_cache + ((int64_t) il * M->n_ctx + pos) * KVD;
-            uint16_t * vc = M->v_cache + ((int64_t) il * M->n_ctx + pos) * KVD;
+            const int cell = cell_of ? cell_of[t] : pos;
+            uint16_t * kc = M->k_cache + ((int64_t) il * M->n_ctx + cell) * KVD;
+            uint16_t * vc = M->v_cache + ((int64_t) il * M->n_ctx + cell) * KVD;
             for (int i = 0; i < KVD; i++) { kc[i] = f2h(kk[i]); vc[i] = f2h(vv[i]); }
-            attention(M, il, q, pos, round_q, att);
+            if (cell_of)
+                attention_impl(q, M->k_cache + (int64_t) il * M->n_ctx * KVD, M->v_cache + (int64_t) il * M->n_ctx * KVD, n_kv_cells,
+                               M->n_head, M->n_head_kv, hd, 1.0f / sqrtf((float) hd), round_q, cell_pos, pos, att);
+            else
+                attention(M, il, q, pos, round_q, att);
             if (last && M->tap_q)   memcpy(M->tap_q + (int64_t) il * QD, q, sizeof(float) * QD);
             if (last && M->tap_kqv) memcpy(M->tap_kqv + (int64_t) il * QD, att, sizeof(float) * QD);
             port_mul_mat_vec(L->wo.type, L->wo.data, E, QD, att, tmp);

@@ -56,6 +56,9 @@ def lib() -> C.CDLL:
         L.port_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.port_decode.argtypes = [C.POINTER(PortModel), C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.port_decode.restype = C.c_int
+        L.port_decode_cells.argtypes = [C.POINTER(PortModel), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.port_decode_cells.restype = C.c_int
+        L.port_k_shift.argtypes = [C.POINTER(PortModel), C.c_void_p]
         _lib = L
     return _lib
 
@@ -178,20 +181,138 @@ class PortModelRunner:
         M.tap_l_out, M.tap_q, M.tap_kqv = self.tap_l_out.ctypes.data, self.tap_q.ctypes.data, self.tap_kqv.ctypes.data
         self.M = M
         self.n_vocab, self.n_ctx = M.n_vocab, M.n_ctx
+        self._cells_reset()
 
     def close(self):
         pass
 
     def kv_clear(self):
+        """llama_kv_cache_clear (cpp/src/llama.cpp:3135-3152)"""
         self.kc[:] = 0
         self.vc[:] = 0
+        self._cells_reset()
+
+    # ---- struct llama_kv_cache's cell bookkeeping (cpp/src/llama.cpp:2495-2539), host side. Until the first seq_rm / seq_add /
+    # seq_div a sequence only grows and cell == position; afterwards cells are placed by find_slot, carry a position and a pending
+    # K-shift delta, and attention masks by position.
+    def _cells_reset(self):
+        self.managed = False
+        self.n_hi = 0                                   # identity mode: highest position written + 1
+        self.cell_pos = np.full(self.n_ctx, -1, dtype=np.int32)
+        self.cell_delta = np.zeros(self.n_ctx, dtype=np.int32)
+        self.head, self.used, self.has_shift = 0, 0, False
+
+    def _enter_managed(self):
+        if self.managed:
+            return
+        self.managed = True
+        n = min(self.n_hi, self.n_ctx)
+        self.cell_pos[:n] = np.arange(n, dtype=np.int32)
+        self.used = n
+        self.head = 0 if n >= self.n_ctx else n         # cpp/src/llama.cpp:14821-14826: head += n_tokens, wrapped
+
+    def kv_seq_rm(self, p0: int, p1: int):
+        """llama_kv_cache_seq_rm(ctx, 0, p0, p1) (cpp/src/llama.cpp:3154-3206)"""
+        self._enter_managed()
+        p0 = max(p0, 0)
+        p1 = 2 ** 31 - 1 if p1 < 0 else p1
+        new_head = self.n_ctx
+        for i in range(self.n_ctx):
+            if p0 <= self.cell_pos[i] < p1:
+                self.used -= 1
+                self.cell_pos[i] = -1
+                if new_head == self.n_ctx:
+                    new_head = i
+        if new_head != self.n_ctx and new_head < self.head:
+            self.head = new_head
+
+    def kv_seq_add(self, p0: int, p1: int, delta: int):
+        """llama_kv_cache_seq_add(ctx, 0, p0, p1, delta) (cpp/src/llama.cpp:3268-3314)"""
+        self._enter_managed()
+        p0 = max(p0, 0)
+        p1 = 2 ** 31 - 1 if p1 < 0 else p1
+        if p0 == p1:
+            return
+        new_head = self.n_ctx
+        for i in range(self.n_ctx):
+            if p0 <= self.cell_pos[i] < p1:
+                self.has_shift = True
+                self.cell_pos[i] += delta
+                self.cell_delta[i] += delta
+                if self.cell_pos[i] < 0:
+                    self.used -= 1
+                    self.cell_pos[i] = -1
+                    if new_head == self.n_ctx:
+                        new_head = i
+        self.head = new_head if new_head != self.n_ctx else 0
+
+    def kv_seq_div(self, p0: int, p1: int, d: int):
+        """llama_kv_cache_seq_div(ctx, 0, p0, p1, d) (cpp/src/llama.cpp:3316-3349)"""
+        self._enter_managed()
+        p0 = max(p0, 0)
+        p1 = 2 ** 31 - 1 if p1 < 0 else p1
+        if p0 == p1:
+            return
+        for i in range(self.n_ctx):
+            if p0 <= self.cell_pos[i] < p1:
+                self.has_shift = True
+                old = int(self.cell_pos[i])
+                self.cell_pos[i] = old // d
+                self.cell_delta[i] += self.cell_pos[i] - old
+
+    def _find_slot(self, n: int) -> int:
+        """llama_kv_cache_find_slot for n tokens of one sequence (cpp/src/llama.cpp:3028-3125, 14684-14688)"""
+        size = self.n_ctx
+        if n > size:
+            return -1
+        if self.head > self.used + 2 * n:
+            self.head = 0
+        n_tested = 0
+        while True:
+            if self.head + n > size:
+                n_tested += size - self.head
+                self.head = 0
+                continue
+            found = True
+            for i in range(n):
+                if self.cell_pos[self.head + i] >= 0:
+                    found = False
+                    self.head += i + 1
+                    n_tested += i + 1
+                    break
+            if found:
+                return self.head
+            if n_tested >= size:
+                return -1
 
     def decode(self, tokens: Sequence[int], pos0: int) -> np.ndarray:
         toks = np.ascontiguousarray(tokens, dtype=np.int32)
         out = np.empty(self.n_vocab, dtype=np.float32)
-        rc = self.L.port_decode(C.byref(self.M), toks.ctypes.data, len(toks), pos0, out.ctypes.data)
+        if not self.managed:
+            rc = self.L.port_decode(C.byref(self.M), toks.ctypes.data, len(toks), pos0, out.ctypes.data)
+            if rc != 0:
+                raise RuntimeError(f"port_decode rc={rc}")
+            self.n_hi = max(self.n_hi, pos0 + len(toks))
+            return out
+        if self.has_shift:                              # llama_kv_cache_update: the pending K-shift, then the deltas are cleared
+            self.L.port_k_shift(C.byref(self.M), self.cell_delta.ctypes.data)
+            self.cell_delta[:] = 0
+            self.has_shift = False
+        n = len(toks)
+        first = self._find_slot(n)
+        if first < 0:
+            raise RuntimeError("no free KV cells for the batch")     # llama_decode returns 1 (cpp/src/llama.cpp:14690)
+        self.cell_pos[first:first + n] = np.arange(pos0, pos0 + n, dtype=np.int32)
+        self.used += n
+        n_kv = int(np.max(np.nonzero(self.cell_pos >= 0)[0])) + 1   # llama_kv_cache_cell_max
+        cell_of = np.arange(first, first + n, dtype=np.int32)
+        rc = self.L.port_decode_cells(C.byref(self.M), toks.ctypes.data, n, pos0, cell_of.ctypes.data, self.cell_pos.ctypes.data,
+                                      n_kv, out.ctypes.data)
         if rc != 0:
-            raise RuntimeError(f"port_decode rc={rc}")
+            raise RuntimeError(f"port_decode_cells rc={rc}")
+        self.head = first + n                           # cpp/src/llama.cpp:14821-14826 (after the graph ran)
+        if self.head >= self.n_ctx:
+            self.head = 0
         return out
 
     def greedy(self, prompt: Sequence[int], n_gen: int) -> (List[int], List[np.ndarray]):

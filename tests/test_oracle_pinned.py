@@ -70,6 +70,24 @@ def test_model_logits_vs_golden_bitwise(golden_dir, model):
         assert np.array_equal(m.decode([t], i), g["single"][i])
 
 
+@pytest.mark.parametrize("model", ["tiny-gqa4_Q4_K_M", "tiny-gqa4-yarn_Q4_K_M"])
+@pytest.mark.parametrize("scenario", ["kvshift", "selfextend"])
+def test_port_kv_cells_vs_golden_bitwise(golden_dir, model, scenario):
+    """SURVEY §8 f-3 restated on the CPU: struct llama_kv_cache's cell bookkeeping (find_slot, seq_rm, seq_add, seq_div), the
+    K-shift of the cached f16 K rows by each cell's accumulated delta (build_k_shift) and attention masked by the cells'
+    positions — the port reproduces every logit of the reference's context-shift scenario (cpp/bridge.cpp:487-507) and of its
+    Self-Extend scenario (:509-524), bit for bit, incl. the YaRN model whose K-shift rescales every cell."""
+    import kvshift_script
+    g = np.load(os.path.join(golden_dir, f"{scenario}_{model}.npz"))
+    m = port.PortModelRunner(os.path.join(golden_dir, model + ".gguf"), n_ctx=64)
+    run = kvshift_script.run if scenario == "kvshift" else kvshift_script.run_self_extend
+    lg = run(m, g["prompt"].tolist())
+    assert lg.shape == g["logits"].shape
+    for i in range(lg.shape[0]):
+        assert np.array_equal(lg[i], g["logits"][i]), f"step {i}"
+    assert m.managed and not m.has_shift
+
+
 def test_port_vs_reference_live(ref_or_none, model_dir):
     """when oracle/_ref loads on this host: random-block twin with the 8B per-layer shapes' arithmetic paths
     (mixed Q4_K/Q6_K, GQA 4) — port and reference must agree."""
