@@ -88,6 +88,85 @@ def test_port_kv_cells_vs_golden_bitwise(golden_dir, model, scenario):
     assert m.managed and not m.has_shift
 
 
+def _random_kv_ops(r, p, rng, n_ctx):
+    """one random walk of decodes (single tokens and batches) and KV operations (context shift, a removed middle range closed
+    again, a window of positions divided Self-Extend style, a tail moved up) applied to the reference and to the port alike;
+    returns False at the first logit difference. A cache that runs full must run full on both sides."""
+    n_past, cells = 0, 0
+    lg = None
+
+    def both(fn, *a):
+        getattr(r, fn)(*a)
+        getattr(p, fn)(*a)
+
+    def dec(toks):
+        nonlocal n_past, lg
+        ea = eb = None
+        try:
+            a = r.decode(toks, n_past)
+        except RuntimeError as e:
+            ea = e
+        try:
+            b = p.decode(toks, n_past)
+        except RuntimeError as e:
+            eb = e
+        if ea or eb:
+            assert bool(ea) == bool(eb), (ea, eb)
+            return None                                     # full on both sides: the walk ends
+        n_past += len(toks)
+        lg = a
+        return np.array_equal(a, b)
+
+    ok = dec([int(t) for t in rng.integers(0, 512, size=int(rng.integers(1, 20)))])
+    cells = n_past
+    for _ in range(60):
+        if ok is not True:
+            return ok is None
+        op = int(rng.integers(0, 10))
+        if op < 5 or n_past < 8:
+            n = int(rng.integers(1, 6)) if op < 4 else 1
+            if cells + n > n_ctx - 1:                       # cpp/bridge.cpp:495-503
+                n_keep = int(rng.integers(0, 4)); n_disc = (n_past - n_keep) // 2
+                both("kv_seq_rm", n_keep, n_keep + n_disc); both("kv_seq_add", n_keep + n_disc, n_past, -n_disc)
+                n_past -= n_disc; cells -= n_disc
+                continue
+            ok = dec([int(np.argmax(lg))] if n == 1 else [int(t) for t in rng.integers(0, 512, size=n)])
+            cells += n
+        elif op < 7:
+            a = int(rng.integers(0, n_past - 2)); b = int(rng.integers(a + 1, min(n_past, a + 8)))
+            both("kv_seq_rm", a, b); both("kv_seq_add", b, n_past, -(b - a))
+            cells -= b - a; n_past -= b - a
+        elif op < 9:
+            w = int(rng.choice([4, 8]))
+            if n_past >= w + 2:                             # cpp/bridge.cpp:512-523
+                a = int(rng.integers(0, n_past - w)); end = (a + w - 1) // 2 + 1
+                both("kv_seq_div", a, a + w, 2); both("kv_seq_add", a + w, n_past, end - (a + w))
+                n_past += end - (a + w)
+        else:
+            both("kv_seq_add", int(rng.integers(0, n_past)), -1, int(rng.integers(1, 4)))
+            n_past += 3
+    return ok is not False
+
+
+def test_port_kv_cells_random_ops_vs_reference_live(ref_or_none, golden_dir):
+    """the port's KV-cell bookkeeping, K-shift and position mask against the LIVE reference on random walks of decodes and
+    llama_kv_cache_seq_rm / seq_add / seq_div calls (freed cells re-used out of order, positions that coincide, deltas that
+    accumulate over several operations before the next decode applies them): every logit bit-identical, and a full cache is
+    full on both sides"""
+    ref = ref_or_none
+    if ref is None or not hasattr(ref.lib(), "refshim_kv_seq_div"):
+        pytest.skip("oracle/_ref with the KV shim is not available")
+    if ref.variant() != "native":
+        pytest.skip("bitwise parity is defined against the reference's -march=native build")
+    path = os.path.join(golden_dir, "tiny-gqa4_Q4_K_M.gguf")
+    r = ref.RefModel(path, n_ctx=64, n_threads=2)
+    for seed in range(16):
+        p = port.PortModelRunner(path, n_ctx=64)
+        r.kv_clear()
+        assert _random_kv_ops(r, p, np.random.default_rng(seed), 64), f"seed {seed}"
+    r.close()
+
+
 def test_port_vs_reference_live(ref_or_none, model_dir):
     """when oracle/_ref loads on this host: random-block twin with the 8B per-layer shapes' arithmetic paths
     (mixed Q4_K/Q6_K, GQA 4) — port and reference must agree."""
