@@ -133,6 +133,19 @@ B200_WIDE int32_t first_at_least(const float * x, int32_t n, float thr, int32_t 
     return n;
 }
 
+// first index >= from with x[index] > thr (strict), or n
+B200_WIDE int32_t first_above(const float * x, int32_t n, float thr, int32_t from) {
+    int32_t i = from;
+    for (; i < n && (i & 63); i++) if (x[i] > thr) return i;
+    for (; i + 64 <= n; i += 64) {
+        int any = 0;
+        for (int j = 0; j < 64; j++) any |= x[i + j] > thr;
+        if (any) { for (int j = 0; j < 64; j++) if (x[i + j] > thr) return i + j; }
+    }
+    for (; i < n; i++) if (x[i] > thr) return i;
+    return n;
+}
+
 }  // namespace
 
 void JanusSampler::init(const Tokenizer & tok, const JanusParams & params, uint32_t seed) {
@@ -454,28 +467,59 @@ float surprise_of(const Cands & c, int32_t id) {
 
 }  // namespace
 
-int32_t StandardSampler::sample(const float * logits, int32_t n_vocab) {
-    // llama_sampling_prepare_impl (cpp/common/sampling.cpp:342-409): every token a candidate, penalties over the tail of prev
-    Cands c;
-    c.v.resize((size_t) n_vocab);
-    for (int32_t id = 0; id < n_vocab; id++) c.v[(size_t) id] = {id, logits[id], 0.0f};
+int32_t StandardSampler::sample(float * logits, int32_t n_vocab) {
+    // llama_sampling_prepare_impl (cpp/common/sampling.cpp:342-409): every token a candidate, penalties over the tail of prev.
+    // The penalised values are written into `logits` (the caller's buffer, like the Janus sampler does): the candidates are
+    // then simply (id, logits[id]).
     const int window = p.penalty_last_n < 0 ? p.n_prev : p.penalty_last_n;
     const int used = std::min((int) prev.size(), window);
     if (used) {
         const bool have_nl = p.nl_token >= 0 && p.nl_token < n_vocab;
         const float nl_logit = have_nl ? logits[p.nl_token] : 0.0f;
-        // llama_sample_repetition_penalties_impl (cpp/src/llama-sampling.cpp:437-482) with frequency / presence penalties 0
+        // llama_sample_repetition_penalties_impl (cpp/src/llama-sampling.cpp:437-482) with frequency / presence penalties 0:
+        // every DISTINCT token of the window once
         if (p.penalty_repeat != 1.0f) {
-            std::vector<uint8_t> seen((size_t) n_vocab, 0);
-            for (size_t i = prev.size() - (size_t) used; i < prev.size(); i++) if (prev[i] >= 0 && prev[i] < n_vocab) seen[(size_t) prev[i]] = 1;
-            for (Cand & x : c.v) {
-                if (!seen[(size_t) x.id]) continue;
-                if (x.logit <= 0) x.logit *= p.penalty_repeat; else x.logit /= p.penalty_repeat;
-                x.logit -= 0.0f;      // count * penalty_freq + present * penalty_present, both 0 here
+            std::vector<int32_t> distinct;
+            for (size_t i = prev.size() - (size_t) used; i < prev.size(); i++) {
+                const int32_t id = prev[i];
+                if (id < 0 || id >= n_vocab || std::find(distinct.begin(), distinct.end(), id) != distinct.end()) continue;
+                distinct.push_back(id);
+                if (logits[id] <= 0) logits[id] *= p.penalty_repeat; else logits[id] /= p.penalty_repeat;
             }
         }
-        if (!p.penalize_nl && have_nl) c.v[(size_t) p.nl_token].logit = nl_logit;
+        if (!p.penalize_nl && have_nl) logits[p.nl_token] = nl_logit;
     }
+    Cands c;
+    // top-k of at most 128 candidates out of the vocabulary is std::partial_sort in the reference (llama_sample_top_k_impl,
+    // cpp/src/llama-sampling.cpp:61-140), i.e. libstdc++'s heap select: a heap of the first k candidates, then every later
+    // candidate that beats the heap's smallest replaces it (__pop_heap into the heap), then sort_heap. The same heap operations
+    // in the same order give the same k candidates in the same order (ties included) without materialising 128 k candidates:
+    // the scan for "beats the smallest" runs over the logits themselves, and std::pop_heap over k + 1 slots with the newcomer in
+    // the last one IS that replacement step.
+    const size_t min_keep_q = (size_t) std::max(1, p.min_keep);
+    int k_eff = p.top_k <= 0 ? n_vocab : p.top_k;
+    k_eff = std::min(std::max(k_eff, (int) min_keep_q), n_vocab);
+    if (p.temp > 0.0f && p.mirostat == 0 && k_eff <= 128 && k_eff < n_vocab) {
+        std::vector<Cand> & h = c.v;
+        h.resize((size_t) k_eff + 1);
+        for (int32_t id = 0; id < k_eff; id++) h[(size_t) id] = {id, logits[id], 0.0f};
+        std::make_heap(h.begin(), h.begin() + k_eff, by_logit_desc);
+        for (int32_t id = first_above(logits, n_vocab, h[0].logit, k_eff); id < n_vocab; id = first_above(logits, n_vocab, h[0].logit, id + 1)) {
+            h[(size_t) k_eff] = {id, logits[id], 0.0f};
+            std::pop_heap(h.begin(), h.end(), by_logit_desc);
+        }
+        std::sort_heap(h.begin(), h.begin() + k_eff, by_logit_desc);
+        h.resize((size_t) k_eff);
+        c.sorted = true;
+        tail_free(c, p.tfs_z, min_keep_q);
+        typical(c, p.typical_p, min_keep_q);
+        top_p(c, p.top_p, min_keep_q);
+        min_p(c, p.min_p, min_keep_q);
+        for (Cand & x : c.v) x.logit /= p.temp;
+        return draw(c, rng);
+    }
+    c.v.resize((size_t) n_vocab);
+    for (int32_t id = 0; id < n_vocab; id++) c.v[(size_t) id] = {id, logits[id], 0.0f};
     // llama_sampling_sample_impl (cpp/common/sampling.cpp:271-340)
     if (p.temp < 0.0f) { softmax(c); return c.v[0].id; }
     if (p.temp == 0.0f) {

@@ -90,7 +90,7 @@ struct StandardSampler {
     bool penalties_active() const { return p.penalty_last_n != 0 && p.penalty_repeat != 1.0f && !prev.empty(); }
     // true when the chain reduces to the arg-max of the RAW logits (the bridge then keeps the arg-max on the device)
     bool greedy() const { return !penalties_active() && (p.temp <= 0.f || (p.mirostat == 0 && p.top_k == 1)); }
-    int32_t sample(const float * logits, int32_t n_vocab);
+    int32_t sample(float * logits, int32_t n_vocab);      // the penalties are written into logits
 };
 
 }  // namespace b200

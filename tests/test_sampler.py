@@ -125,6 +125,30 @@ def test_standard_chain_equals_reference_token_for_token(kind, tmp_path, ref_or_
         s.close()
     assert n_varied >= len(STANDARD)                                         # real draws, not one token repeated
     r.close()
+    # the full-size vocabularies (30 016 / 128 256 tokens): the top-k <= 128 path selects with the heap operations of
+    # std::partial_sort over the raw logits instead of materialising every candidate — same ids, same order, same draws
+    path = _model(tmp_path, kind)
+    r = ref.RefModel(path, n_ctx=96, n_threads=2)
+    for kw in (dict(), dict(temp=1.0, top_k=128, typical_p=0.7, penalty_repeat=1.2, penalty_last_n=16)):
+        ours_kw = dict(kw)
+        s = engine.Sampler(path, 96, janus=0, temperature=ours_kw.pop("temp", 0.8), top_k=ours_kw.pop("top_k", 40), top_p=ours_kw.pop("top_p", 0.95),
+                           repetition_penalty=ours_kw.pop("penalty_repeat", 1.0), penalty_last_n=ours_kw.pop("penalty_last_n", 64), **ours_kw)
+        ids_ref = r.standard_generate(prompts[0], 24, 11, **kw)
+        r.kv_clear()
+        lg = r.decode(prompts[0], 0)
+        s.reset(prompts[0], 11)
+        pos = len(prompts[0])
+        ours = []
+        for want in ids_ref:
+            got = s.sample(lg, pos)
+            ours.append(got)
+            if got != want:
+                break
+            lg = r.decode([got], pos)
+            pos += 1
+        assert ours == ids_ref and len(set(ids_ref)) > 3, (kind, kw)
+        s.close()
+    r.close()
 
 
 def test_standard_chain_properties(tmp_path):
