@@ -151,6 +151,67 @@ def test_standard_chain_equals_reference_token_for_token(kind, tmp_path, ref_or_
     r.close()
 
 
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_janus_golden_ids_on_port_logits(kind, tmp_path, golden_dir):
+    """the committed ids of tests/golden/janus.json (the reference's bridge loop with its own Janus sampler) from the PORT's
+    logits — needs no reference library; the GPU test drives the same cases through doInference"""
+    import json
+
+    from oracle import port
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "janus.json"))) if c["kind"] == kind]
+    assert len(cases) >= 12
+    path = _model(tmp_path, kind)
+    m = port.PortModelRunner(path, n_ctx=64)
+    for c in cases:
+        s = engine.Sampler(path, 64, janus=1, depth=c["depth"], scale=c["scale"], hi=c["hi"], lo=c["lo"])
+        m.kv_clear()
+        lg = m.decode(c["prompt"], 0)
+        s.reset(c["prompt"], c["seed"])
+        pos = len(c["prompt"])
+        ours = []
+        for want in c["ids"]:
+            got = s.sample(lg, pos, c["n_predict"])
+            ours.append(got)
+            if got != want:
+                break
+            lg = m.decode([got], pos)
+            pos += 1
+        assert ours == c["ids"], {k: v for k, v in c.items() if k not in ("prompt", "ids", "text")}
+        s.close()
+
+
+@pytest.mark.parametrize("kind", ["spm", "bpe"])
+def test_standard_chain_golden_ids_on_port_logits(kind, tmp_path, golden_dir):
+    """the committed ids of tests/golden/standard_chain.json (generated by the reference's own chain inside the bridge's loop)
+    from logits the PORT computes — no reference library needed: oracle_port.c is bit-identical to the reference's logits, the
+    sampler restates its chain, so the ids must come out the same. The GPU test drives the same cases through doInference."""
+    import json
+
+    from oracle import port
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "standard_chain.json"))) if c["kind"] == kind]
+    assert len(cases) >= 24
+    path = _model(tmp_path, kind, big=False)
+    m = port.PortModelRunner(path, n_ctx=64)
+    for c in cases:
+        s = engine.Sampler(path, 64, janus=0, temperature=c["temperature"], top_k=c["top_k"], top_p=c["top_p"],
+                           repetition_penalty=c["repetition_penalty"], penalty_last_n=c["penalty_last_n"], mirostat=c["mirostat"],
+                           mirostat_tau=c["mirostat_tau"], mirostat_eta=c["mirostat_eta"], typical_p=c["typical_p"])
+        m.kv_clear()
+        lg = m.decode(c["prompt"], 0)
+        s.reset(c["prompt"], c["seed"])
+        pos = len(c["prompt"])
+        ours = []
+        for want in c["ids"]:
+            got = s.sample(lg, pos)
+            ours.append(got)
+            if got != want:
+                break
+            lg = m.decode([got], pos)
+            pos += 1
+        assert ours == c["ids"], {k: v for k, v in c.items() if k not in ("prompt", "ids", "text")}
+        s.close()
+
+
 def test_standard_chain_properties(tmp_path):
     """janus = 0 (a setting the reference ignores): temperature <= 0 and top_k = 1 are arg-max; a fixed seed is deterministic;
     the repetition penalty moves a repeated arg-max; top-k bounds the support"""
